@@ -1,0 +1,75 @@
+"""fp32 restatement of the SSL losses on the hot path (utils/loss/medloss.py:5-56,
+utils/loss/diceloss.py:64-81,155-191 and the inline trainer expressions cited per function)."""
+import torch
+import torch.nn.functional as F
+
+
+def dice_loss(probs, target, n_classes, weight=None, softmax=False):
+    """DiceLoss.forward (utils/loss/diceloss.py:178-191 == utils/loss/medloss.py:28-41).
+
+    probs [n,C,H,W]; target [n,1,H,W] (class ids).  Sums run over the whole batch; smooth = 1e-5;
+    denominators use squares (diceloss.py:168-176).  ignore_index is NOT honoured (255 matches no class).
+    """
+    if softmax:
+        probs = torch.softmax(probs, dim=1)
+    onehot = torch.cat([(target == i) for i in range(n_classes)], dim=1).float()   # _one_hot_encoder :160-166
+    if weight is None:
+        weight = [1] * n_classes
+    assert probs.size() == onehot.size(), 'predict & target shape do not match'
+    smooth = 1e-5
+    loss = 0.0
+    for i in range(n_classes):
+        s, t = probs[:, i], onehot[:, i]
+        inter = torch.sum(s * t)
+        y_sum = torch.sum(t * t)
+        z_sum = torch.sum(s * s)
+        loss = loss + (1 - (2 * inter + smooth) / (z_sum + y_sum + smooth)) * weight[i]
+    return loss / n_classes
+
+
+def ce_loss(logits, target, ignore_index=255):
+    """nn.CrossEntropyLoss(ignore_index=255): mean over non-ignored pixels (medloss.py:49)."""
+    return F.cross_entropy(logits, target, ignore_index=ignore_index)
+
+
+def med_sup_loss(logits, target, n_classes, ce=0.5, dice=0.5):
+    """Med_Sup_Loss.forward (utils/loss/medloss.py:54-56)."""
+    return ce * ce_loss(logits, target) + dice * dice_loss(torch.softmax(logits, dim=1), target.unsqueeze(1),
+                                                           n_classes)
+
+
+def softmax_mse(input_logits, target_logits):
+    """softmax_mse_loss (utils/loss/diceloss.py:64-81; local copy 2019_07...:63-79): elementwise, unreduced."""
+    assert input_logits.size() == target_logits.size()
+    return (F.softmax(input_logits, dim=1) - F.softmax(target_logits, dim=1)) ** 2
+
+
+def mt_consistency(student_logits_u, teacher_logits_u):
+    """Mean-Teacher consistency (2017_03_NIPS_Mean-Teacher_ACDC.py:97,101,104)."""
+    return torch.mean((torch.softmax(student_logits_u, dim=1) - torch.softmax(teacher_logits_u, dim=1)) ** 2)
+
+
+def cps_losses(out1, out2, target, label_bs, n_classes):
+    """CPS supervised + cross pseudo supervision terms (2021_06_CVPR_CPS_ACDC.py:99-110).
+    Returns (loss_sup, loss_semi, pseudo1, pseudo2)."""
+    soft1 = torch.softmax(out1, dim=1)
+    soft2 = torch.softmax(out2, dim=1)
+    loss_sup = med_sup_loss(out1[:label_bs], target, n_classes) + med_sup_loss(out2[:label_bs], target, n_classes)
+    pl1 = torch.argmax(soft1[label_bs:].detach(), dim=1, keepdim=False)
+    pl2 = torch.argmax(soft2[label_bs:].detach(), dim=1, keepdim=False)
+    loss_semi = med_sup_loss(out1[label_bs:], pl2, n_classes) + med_sup_loss(out2[label_bs:], pl1, n_classes)
+    return loss_sup, loss_semi, pl1, pl2
+
+
+def uamt_consistency(student_logits_u, teacher_logits_u, teacher_mc_logits, T, threshold):
+    """UAMT uncertainty-masked consistency (2019_07_MICCAI_Uncertainty_Aware_ACDC.py:145-160).
+
+    teacher_mc_logits: [T*n_u, C, H, W] logits of the T stochastic teacher passes, in the reference's
+    buffer order (pass-major).  Returns (consistency_loss, uncertainty[n_u,1,H,W], mask)."""
+    n_u, C, H, W = student_logits_u.shape
+    preds = F.softmax(teacher_mc_logits, dim=1).reshape(T, n_u, C, H, W).mean(dim=0)
+    uncertainty = -1.0 * torch.sum(preds * torch.log(preds + 1e-6), dim=1, keepdim=True)
+    dist = softmax_mse(student_logits_u, teacher_logits_u)
+    mask = (uncertainty < threshold).float()
+    loss = torch.sum(mask * dist) / (2 * torch.sum(mask) + 1e-16)     # the literal 2 is the reference's
+    return loss, uncertainty, mask

@@ -1,0 +1,251 @@
+"""Generate tests/golden/*.pt by running the REAL reference (loaded by file path from /root/reference or
+$HPFG_REF).  Run from the repo root in the build container:  python tests/golden/make_golden.py
+
+Every fixture stores OUTPUTS of the reference's own objects (model/unet.py UNet, utils/loss Med_Sup_Loss /
+DiceLoss / softmax_mse_loss, utils/utils.py update_ema_variables, utils/scheduler Medical_LR,
+torch.optim.SGD as utils/__init__.py:14-16 builds it) on inputs regenerated from seeds by common.py.
+The trainer scripts themselves cannot run here (datasets, tensorboardX, medpy are absent), so the step
+fixtures are literal transcriptions of the step bodies calling those reference objects.
+"""
+import copy
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
+from oracle.ref_loader import load_reference            # noqa: E402
+from tests.golden.common import (make_state, make_masks, make_batch, summarize, ENC_PREFIXES)  # noqa: E402
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ref = load_reference()
+torch.set_num_threads(8)
+
+
+class Args(dict):
+    __getattr__ = dict.__getitem__
+
+
+def ref_model(st, in_ch, n_cls):
+    m = ref.UNet(in_channels=in_ch, num_classes=n_cls)
+    m.load_state_dict(st)
+    m.train()
+    return m
+
+
+def inject_masks(model, masks):
+    """Replace each nn.Dropout's output by inp*mask/(1-p) (what nn.Dropout computes for that mask)."""
+    handles = []
+    for prefix in ENC_PREFIXES:
+        drop = model.get_submodule(prefix + ".conv_conv.3")
+        assert isinstance(drop, nn.Dropout)
+        if masks is None or prefix not in masks:
+            h = drop.register_forward_hook(lambda mod, inp, out: inp[0])
+        else:
+            mk = masks[prefix]
+            h = drop.register_forward_hook(
+                lambda mod, inp, out, mk=mk, p=drop.p: inp[0] * mk.to(inp[0].dtype) / (1.0 - p))
+        handles.append(h)
+    return handles
+
+
+def golden_unet(tag, in_ch, n_cls, n, h, w, seed, use_masks):
+    st = make_state(in_ch, n_cls, seed)
+    x_l, x_u, y = make_batch(n, 0, in_ch, n_cls, h, w, seed + 7)
+    masks = make_masks(n, h, w, seed + 11) if use_masks else None
+    m = ref_model(st, in_ch, n_cls)
+    hs = inject_masks(m, masks)
+    taps = {}
+    for name in ["encoder.in_conv.conv_conv.0", "encoder.in_conv", "encoder.down2", "encoder.down4",
+                 "decoder.up1", "decoder.up4"]:
+        m.get_submodule(name).register_forward_hook(
+            lambda mod, inp, out, name=name: taps.__setitem__(name, out.detach().clone()))
+    logits = m(x_l)
+    loss = ref.Med_Sup_Loss(n_cls)(logits, y)
+    loss.backward()
+    out = {"cfg": dict(in_ch=in_ch, n_cls=n_cls, n=n, h=h, w=w, seed=seed, use_masks=use_masks),
+           "logits": logits.detach().clone(), "loss": loss.item(),
+           "taps": {k: summarize(v) for k, v in taps.items()},
+           "grads": {k: summarize(p.grad) for k, p in m.named_parameters()},
+           "buffers": {k: v.clone() for k, v in m.state_dict().items() if "running" in k or "tracked" in k}}
+    # eval-mode forward with the updated running statistics
+    for hnd in hs:
+        hnd.remove()
+    m.eval()
+    with torch.no_grad():
+        out["logits_eval"] = m(x_l).clone()
+    torch.save(out, os.path.join(HERE, "unet_%s.pt" % tag))
+    print("unet_%s: loss %.8f" % (tag, out["loss"]))
+
+
+def golden_losses():
+    g = torch.Generator().manual_seed(4242)
+    out = {}
+    for tag, (n_l, n_u, C, H, W) in {"c4": (3, 2, 4, 24, 40), "c2": (2, 3, 2, 16, 16)}.items():
+        s = (3.0 * torch.randn(n_l + n_u, C, H, W, generator=g)).requires_grad_(True)
+        t = 3.0 * torch.randn(n_l + n_u, C, H, W, generator=g)
+        y = torch.randint(0, C, (n_l, H, W), generator=g)
+        y255 = y.clone()
+        y255[torch.rand(y.shape, generator=g) < 0.1] = 255
+        rec = {"shape": (n_l, n_u, C, H, W)}
+        # Med_Sup_Loss with and without ignored pixels (utils/loss/medloss.py:44-56)
+        for nm, yy in (("sup", y), ("sup255", y255)):
+            l = ref.Med_Sup_Loss(C)(s[:n_l], yy)
+            (gr,) = torch.autograd.grad(l, s)
+            rec[nm] = l.item()
+            rec[nm + "_grad"] = gr.clone()
+        # DiceLoss with class weights and softmax flag (utils/loss/diceloss.py:178-191)
+        wts = [0.5 + 0.25 * i for i in range(C)]
+        l = ref.DiceLoss(C)(s[:n_l], y.unsqueeze(1), weight=wts, softmax=True)
+        (gr,) = torch.autograd.grad(l, s)
+        rec["dice_w"], rec["dice_w_grad"], rec["dice_weights"] = l.item(), gr.clone(), wts
+        l = ref.DiceLoss(C)(torch.softmax(s, 1)[:n_l], y.unsqueeze(1))
+        rec["dice"] = l.item()
+        # Mean-Teacher step loss (2017_03...:97-106) with w = 0.37
+        w = 0.37
+        soft, tsoft = torch.softmax(s, 1), torch.softmax(t, 1)
+        sup = ref.Med_Sup_Loss(C)(s[:n_l], y)
+        cons = torch.mean((soft[n_l:] - tsoft[n_l:]) ** 2)
+        l = sup + w * cons
+        (gr,) = torch.autograd.grad(l, s)
+        rec["mt"] = dict(w=w, loss=l.item(), sup=sup.item(), cons=cons.item(), grad=gr.clone())
+        # CPS (2021_06...:99-111)
+        s2 = (3.0 * torch.randn(n_l + n_u, C, H, W, generator=g)).requires_grad_(True)
+        med = ref.Med_Sup_Loss(C)
+        soft1, soft2 = torch.softmax(s, 1), torch.softmax(s2, 1)
+        lsup = med(s[:n_l], y) + med(s2[:n_l], y)
+        pl1 = torch.argmax(soft1[n_l:].detach(), dim=1)
+        pl2 = torch.argmax(soft2[n_l:].detach(), dim=1)
+        lsemi = med(s[n_l:], pl2) + med(s2[n_l:], pl1)
+        l = lsup + w * lsemi
+        g1, g2 = torch.autograd.grad(l, [s, s2])
+        rec["cps"] = dict(w=w, loss=l.item(), sup=lsup.item(), semi=lsemi.item(), pl1=pl1.clone(),
+                          pl2=pl2.clone(), grad1=g1.clone(), grad2=g2.clone(), logits2=s2.detach().clone())
+        # UAMT (2019_07...:145-160), T = 8
+        T = 8
+        base = 3.0 * torch.randn(1, n_u, C, H, W, generator=g)      # correlated passes -> a non-trivial mask
+        mc = (base + 0.7 * torch.randn(T, n_u, C, H, W, generator=g)).reshape(T * n_u, C, H, W)
+        t_u = t[n_l:]
+        preds = F.softmax(mc, dim=1).reshape(T, n_u, C, H, W)
+        preds = torch.mean(preds, dim=0)
+        unc = -1.0 * torch.sum(preds * torch.log(preds + 1e-6), dim=1, keepdim=True)
+        loss_ce = nn.CrossEntropyLoss(ignore_index=255)(s[:n_l], y)
+        loss_dice = ref.DiceLoss(C)(torch.softmax(s, 1)[:n_l], y.unsqueeze(1))
+        sup_u = 0.5 * (loss_dice + loss_ce)
+        dist = ref.softmax_mse_loss(s[n_l:], t_u)
+        thr = (0.75 + 0.25 * ref.sigmoid_rampup(5000, 30000)) * np.log(2)
+        mask = (unc < thr).float()
+        cons_u = torch.sum(mask * dist) / (2 * torch.sum(mask) + 1e-16)
+        l = sup_u + w * cons_u
+        (gr,) = torch.autograd.grad(l, s)
+        rec["uamt"] = dict(w=w, T=T, threshold=float(thr), loss=l.item(), sup=sup_u.item(), cons=cons_u.item(),
+                           grad=gr.clone(), mc_logits=mc.clone(), uncertainty=unc.clone(),
+                           mask_sum=mask.sum().item())
+        rec["student"], rec["teacher"], rec["y"], rec["y255"] = s.detach().clone(), t.clone(), y, y255
+        out[tag] = rec
+    torch.save(out, os.path.join(HERE, "losses.pt"))
+    print("losses: sup %.8f mt %.8f cps %.8f uamt %.8f" % (out["c4"]["sup"], out["c4"]["mt"]["loss"],
+                                                           out["c4"]["cps"]["loss"], out["c4"]["uamt"]["loss"]))
+
+
+def golden_schedules():
+    out = {"rampup": [(it, ref.get_current_consistency_weight(it // 150, Args(consistency=0.1,
+                                                                              consistency_rampup=200.0)))
+                      for it in (1, 149, 150, 1500, 15000, 29999, 30000, 45000)],
+           "sigmoid": [(c, L, ref.sigmoid_rampup(c, L)) for c, L in ((0, 200.0), (17, 200.0), (250, 200.0),
+                                                                      (3, 0))]}
+    p = [nn.Parameter(torch.zeros(3))]
+    opt = torch.optim.SGD(p, lr=0.01, momentum=0.9, weight_decay=1e-4)
+    sch = ref.Medical_LR(optimizer=opt, base_lr=0.01, max_iterations=30000)
+    lrs = []
+    for _ in range(5):
+        lrs.append(opt.param_groups[0]["lr"])
+        opt.step()
+        sch.step()
+    out["medical_lr_first5"] = lrs
+    # EMA (utils/utils.py:82-86) on two small "models"
+    g = torch.Generator().manual_seed(99)
+    a, b = nn.Linear(7, 5), nn.Linear(7, 5)
+    with torch.no_grad():
+        for q in list(a.parameters()) + list(b.parameters()):
+            q.copy_(torch.randn(q.shape, generator=g))
+    ema_in = {"student": [q.detach().clone() for q in a.parameters()],
+              "teacher": [q.detach().clone() for q in b.parameters()]}
+    ema_out = {}
+    for step in (1, 2, 50, 99, 100, 5000):
+        bb = copy.deepcopy(b)
+        ref.update_ema_variables(a, bb, 0.99, step)
+        ema_out[step] = [q.detach().clone() for q in bb.parameters()]
+    out["ema_in"], out["ema_out"] = ema_in, ema_out
+    torch.save(out, os.path.join(HERE, "schedules.pt"))
+    print("schedules: lrs", lrs)
+
+
+def golden_mt_steps(tag, in_ch, n_cls, n_l, n_u, h, w, seed, steps=3):
+    """Literal Mean-Teacher step (2017_03_NIPS_Mean-Teacher_ACDC.py:55-57,64-70,89-113) on reference objects."""
+    st = make_state(in_ch, n_cls, seed)
+    model = ref_model(st, in_ch, n_cls)
+    ema_model = copy.deepcopy(model)
+    for name, p in ema_model.named_parameters():
+        p.requires_grad = False
+    args = Args(lr=0.01, momentum=0.9, weight_decay=1e-4, total_itrs=30000, ema_decay=0.99, consistency=0.1,
+                consistency_rampup=200.0, num_classes=n_cls)
+    optimizer = torch.optim.SGD(model.parameters(), lr=args.lr, momentum=args.momentum,
+                                weight_decay=args.weight_decay)
+    lr_scheduler = ref.Medical_LR(optimizer=optimizer, base_lr=args.lr, max_iterations=args.total_itrs)
+    med_loss = ref.Med_Sup_Loss(args.num_classes)
+    model.train()
+    ema_model.train()
+    recs = []
+    cur_itrs = 0
+    for it in range(steps):
+        cur_itrs += 1
+        label_img, unlabel_img, target_label = make_batch(n_l, n_u, in_ch, n_cls, h, w, seed + 100 * cur_itrs)
+        hs = inject_masks(model, make_masks(n_l + n_u, h, w, seed + 100 * cur_itrs + 1))
+        hs += inject_masks(ema_model, make_masks(n_l + n_u, h, w, seed + 100 * cur_itrs + 2))
+        label_bs = label_img.shape[0]
+        x = torch.cat([label_img, unlabel_img], dim=0)
+        output = model(x)
+        output_soft = torch.softmax(output, dim=1)
+        with torch.no_grad():
+            ema_output = ema_model(x)
+            ema_output_soft = torch.softmax(ema_output, dim=1)
+        loss_sup = med_loss(output[:label_bs], target_label)
+        loss_consistence = torch.mean((output_soft[label_bs:] - ema_output_soft[label_bs:]) ** 2)
+        consistency_weight = ref.get_current_consistency_weight(epoch=cur_itrs // 150, args=args)
+        loss = loss_sup + consistency_weight * loss_consistence
+        optimizer.zero_grad()
+        loss.backward()
+        lr = optimizer.param_groups[0]["lr"]
+        optimizer.step()
+        lr_scheduler.step()
+        ref.update_ema_variables(model, ema_model, args.ema_decay, cur_itrs)
+        for hnd in hs:
+            hnd.remove()
+        recs.append(dict(loss=loss.item(), sup=loss_sup.item(), cons=loss_consistence.item(),
+                         w=consistency_weight, lr=lr,
+                         logits=summarize(output), teacher_logits=summarize(ema_output),
+                         student_sum=sum(p.double().sum().item() for p in model.parameters()),
+                         teacher_sum=sum(p.double().sum().item() for p in ema_model.parameters()),
+                         student_out_conv=model.decoder.out_conv.weight.detach().clone(),
+                         teacher_out_conv=ema_model.decoder.out_conv.weight.detach().clone(),
+                         student_in_conv=model.encoder.in_conv.conv_conv[0].weight.detach().clone(),
+                         teacher_rm=ema_model.encoder.in_conv.conv_conv[1].running_mean.clone(),
+                         student_rv=model.decoder.up4.conv.conv_conv[5].running_var.clone()))
+    out = {"cfg": dict(in_ch=in_ch, n_cls=n_cls, n_l=n_l, n_u=n_u, h=h, w=w, seed=seed, steps=steps),
+           "steps": recs}
+    torch.save(out, os.path.join(HERE, "mt_steps_%s.pt" % tag))
+    print("mt_steps_%s:" % tag, [r["loss"] for r in recs])
+
+
+if __name__ == "__main__":
+    golden_unet("acdc_masks", 1, 4, 2, 32, 48, 101, True)
+    golden_unet("acdc_nodrop", 1, 4, 3, 32, 32, 202, False)
+    golden_unet("isic_masks", 3, 2, 2, 48, 32, 303, True)
+    golden_losses()
+    golden_schedules()
+    golden_mt_steps("acdc", 1, 4, 2, 2, 32, 32, 404)
+    golden_mt_steps("isic", 3, 2, 1, 3, 32, 32, 505, steps=2)

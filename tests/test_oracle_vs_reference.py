@@ -1,0 +1,70 @@
+"""CPU, build container only: the oracle against the REAL reference modules loaded by file path, including
+torch-RNG dropout (same seed => identical masks) and a full-size Mean-Teacher step that reproduces the
+survey's sanity values."""
+import copy
+
+import pytest
+import torch
+
+import oracle
+from oracle.ref_loader import find_reference, load_reference
+
+pytestmark = pytest.mark.skipif(find_reference() is None, reason="reference tree not present on this machine")
+
+
+def test_names_shapes_and_rng_dropout_forward():
+    ref = load_reference()
+    torch.manual_seed(1337)
+    m = ref.UNet(3, 2)
+    assert [(n, tuple(p.shape)) for n, p in m.named_parameters()] == oracle.unet_param_spec(3, 2)
+    st = {k: v.clone() for k, v in m.state_dict().items()}
+    assert set(st) == {n for n, _ in oracle.unet_param_spec(3, 2)} | {n for n, _, _ in oracle.unet_buffer_spec(3, 2)}
+    x = torch.rand(2, 3, 48, 32)
+    m.train()
+    torch.manual_seed(5)
+    a = m(x)
+    torch.manual_seed(5)
+    b = oracle.unet_forward(st, x, True)
+    assert torch.equal(a, b)
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, st[k]), k
+
+
+def test_full_size_mt_step_matches_reference_objects():
+    """One literal MT step at the benchmark shape (12+12, 1x224x224) with torch-RNG dropout."""
+    ref = load_reference()
+    torch.manual_seed(1337)
+    m = ref.UNet(1, 4)
+    ema = copy.deepcopy(m)
+    x_l, x_u = torch.rand(12, 1, 224, 224), torch.rand(12, 1, 224, 224)
+    y = torch.randint(0, 4, (12, 224, 224))
+    student = {k: v.clone() for k, v in m.state_dict().items()}
+    teacher = {k: v.clone() for k, v in ema.state_dict().items()}
+    opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    sch = ref.Medical_LR(opt, 0.01, 30000)
+    med = ref.Med_Sup_Loss(4)
+    m.train(), ema.train()
+    rng = torch.get_rng_state()
+    x = torch.cat([x_l, x_u])
+    out = m(x)
+    with torch.no_grad():
+        eout = ema(x)
+    sup = med(out[:12], y)
+    cons = torch.mean((torch.softmax(out, 1)[12:] - torch.softmax(eout, 1)[12:]) ** 2)
+    w = 0.1 * ref.sigmoid_rampup(1 // 150, 200.0)
+    loss = sup + w * cons
+    opt.zero_grad()
+    loss.backward()
+    opt.step()
+    sch.step()
+    ref.update_ema_variables(m, ema, 0.99, 1)
+    # survey sanity values (Appendix B): loss 1.01571846, cons 2.27281800e-3
+    assert loss.item() == pytest.approx(1.01571846, abs=5e-5)
+    torch.set_rng_state(rng)
+    r = oracle.mt_step(student, teacher, oracle.SGDState(), x_l, x_u, y, 1)
+    assert r["loss"] == pytest.approx(loss.item(), abs=1e-6)
+    assert r["loss_cons"] == pytest.approx(cons.item(), rel=1e-5)
+    for k, v in m.state_dict().items():
+        assert torch.allclose(student[k].float(), v.float(), atol=1e-6), k
+    for k, v in ema.state_dict().items():
+        assert torch.allclose(teacher[k].float(), v.float(), atol=1e-6), k
