@@ -1,0 +1,20 @@
+"""hpfg_b200 -- B200-native (sm_100a) implementation of HPFG's semi-supervised U-Net training hot path,
+behind the reference's own Python API:
+
+    build_model(args)                      model/builder.py:14-62 ('unet' branch)
+    UNet(in_channels, num_classes)         model/unet.py:155-175
+    Med_Sup_Loss, DiceLoss, softmax_mse_loss   utils/loss/medloss.py, utils/loss/diceloss.py
+    update_ema_variables, get_current_consistency_weight, sigmoid_rampup   utils/utils.py:67-86
+
+plus fused whole-step drivers (MeanTeacherStep / CPSStep / UAMTStep).  All compute goes through
+libhpfg_b200.so (include/hpfg_b200.h); there is no CPU or PyTorch fallback."""
+from .builder import build_model
+from .unet import UNet
+from .losses import Med_Sup_Loss, DiceLoss, softmax_mse_loss, mean_teacher_loss, cps_loss, uamt_loss, ssl_loss_raw
+from .utils import (update_ema_variables, get_current_consistency_weight, sigmoid_rampup, linear_rampup,
+                    ema_update_flat)
+from .trainer import MeanTeacherStep, CPSStep, UAMTStep, medical_lr
+
+__all__ = ["build_model", "UNet", "Med_Sup_Loss", "DiceLoss", "softmax_mse_loss", "mean_teacher_loss", "cps_loss",
+           "uamt_loss", "ssl_loss_raw", "update_ema_variables", "get_current_consistency_weight", "sigmoid_rampup",
+           "linear_rampup", "ema_update_flat", "MeanTeacherStep", "CPSStep", "UAMTStep", "medical_lr"]

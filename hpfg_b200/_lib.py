@@ -1,0 +1,90 @@
+"""ctypes binding of libhpfg_b200.so (the C ABI declared in include/hpfg_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, an exception is raised."""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libhpfg_b200.so")
+
+c_i64p = ctypes.POINTER(ctypes.c_int64)
+c_vp = ctypes.c_void_p
+c_int = ctypes.c_int
+c_f = ctypes.c_float
+c_i64 = ctypes.c_int64
+c_u64 = ctypes.c_uint64
+
+# every symbol include/hpfg_b200.h declares: name -> (restype, argtypes)
+SIGNATURES = {
+    "hpfg_last_error": (ctypes.c_char_p, []),
+    "hpfg_version": (c_int, []),
+    "hpfg_launch_count": (c_i64, []),
+    "hpfg_unet_param_layout": (c_int, [c_int, c_int, c_i64p, c_i64p, c_i64p]),
+    "hpfg_unet_bn_layout": (c_int, [c_int, c_int, c_i64p, c_i64p, c_i64p]),
+    "hpfg_unet_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
+    "hpfg_unet_plan_destroy": (c_int, [c_vp]),
+    "hpfg_unet_plan_workspace_bytes": (c_i64, [c_vp]),
+    "hpfg_unet_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u64, c_u64,
+                                  ctypes.POINTER(c_vp), c_vp]),
+    "hpfg_unet_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "hpfg_unet_num_buckets": (c_int, [c_vp]),
+    "hpfg_unet_bucket_range": (c_int, [c_vp, c_int, c_i64p, c_i64p]),
+    "hpfg_unet_bucket_wait": (c_int, [c_vp, c_int, c_vp]),
+    "hpfg_unet_debug_tap": (c_int, [c_vp, ctypes.c_char_p, c_vp, c_i64, c_vp]),
+    "hpfg_ssl_loss_workspace_bytes": (c_i64, [c_int] * 6),
+    "hpfg_ssl_loss": (c_int, [c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_f,
+                              ctypes.POINTER(c_f), c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hpfg_dice_loss": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f), c_vp, c_vp, c_vp,
+                               c_vp]),
+    "hpfg_ema_update": (c_int, [c_vp, c_vp, c_i64, c_f, c_vp]),
+    "hpfg_sgd_momentum": (c_int, [c_vp, c_vp, c_vp, c_i64, c_f, c_f, c_f, c_f, c_int, c_vp]),
+    "hpfg_sgd_momentum_ema": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f, c_f, c_f, c_f, c_int, c_f, c_vp]),
+}
+
+PREC_FP32, PREC_BF16 = 0, 1
+LOSS_SUP, LOSS_MT, LOSS_CPS, LOSS_UAMT = 0, 1, 2, 3
+NUM_BN, NUM_DROPOUT, NUM_PARAMS = 18, 5, 82
+
+_lib = None
+
+
+class HpfgError(RuntimeError):
+    pass
+
+
+def lib():
+    """The loaded library (loads on first use; raises if libhpfg_b200.so has not been built)."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise HpfgError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(there is no CPU / PyTorch fallback)" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the .so does not export a declared symbol
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().hpfg_last_error()
+        raise HpfgError("%s failed (code %d): %s" % (what or "hpfg call", rc, msg.decode() if msg else "?"))
+
+
+def ptr(t):
+    """Device/host pointer of a tensor (None -> NULL)."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return ctypes.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(t, what):
+    if not t.is_cuda:
+        raise HpfgError("%s must be a CUDA tensor: hpfg_b200 has no CPU path (got device %s)" % (what, t.device))

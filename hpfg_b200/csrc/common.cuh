@@ -1,0 +1,92 @@
+// Shared device/host helpers for the hpfg_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+
+#include "../../include/hpfg_b200.h"
+
+namespace hpfg {
+
+// ---- error plumbing (no exceptions across the C ABI) --------------------------------------------------
+void set_error(const std::string &msg);
+extern int64_t g_launch_count;
+
+#define HPFG_CUDA_CHECK(expr)                                                                      \
+    do {                                                                                           \
+        cudaError_t _e = (expr);                                                                   \
+        if (_e != cudaSuccess) {                                                                   \
+            ::hpfg::set_error(std::string(#expr) + ": " + cudaGetErrorString(_e) + " (" + __FILE__ + \
+                              ":" + std::to_string(__LINE__) + ")");                               \
+            return HPFG_ERR_CUDA;                                                                  \
+        }                                                                                          \
+    } while (0)
+
+#define HPFG_RETURN_IF(expr)                \
+    do {                                    \
+        int _rc = (expr);                   \
+        if (_rc != HPFG_OK) return _rc;     \
+    } while (0)
+
+#define HPFG_REQUIRE(cond, msg)                     \
+    do {                                            \
+        if (!(cond)) {                              \
+            ::hpfg::set_error(std::string(msg));    \
+            return HPFG_ERR_INVALID;                \
+        }                                           \
+    } while (0)
+
+// counts launches and surfaces launch-configuration errors immediately
+#define HPFG_LAUNCH_CHECK()                 \
+    do {                                    \
+        ++::hpfg::g_launch_count;           \
+        HPFG_CUDA_CHECK(cudaGetLastError()); \
+    } while (0)
+
+constexpr float kLeakySlope = 0.01f;   // nn.LeakyReLU() default (model/unet.py:20,24)
+constexpr float kBnEps = 1e-5f;        // nn.BatchNorm2d defaults
+constexpr float kBnMomentum = 0.1f;
+constexpr int kNumSMs = 148;
+
+// ---- dtype helpers ------------------------------------------------------------------------------------
+using bf16 = __nv_bfloat16;
+
+__device__ __forceinline__ float to_f32(float v) { return v; }
+__device__ __forceinline__ float to_f32(bf16 v) { return __bfloat162float(v); }
+template <typename T> __device__ __forceinline__ T from_f32(float v);
+template <> __device__ __forceinline__ float from_f32<float>(float v) { return v; }
+template <> __device__ __forceinline__ bf16 from_f32<bf16>(float v) { return __float2bfloat16_rn(v); }
+
+__device__ __forceinline__ float leaky(float v) { return v > 0.f ? v : kLeakySlope * v; }
+__device__ __forceinline__ float leaky_grad(float v) { return v > 0.f ? 1.f : kLeakySlope; }
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---- Philox4x32-10 (counter-based; keyed by (seed), counter = (element_index/4, offset)) ----------------
+__device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 ctr) {
+    constexpr uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+
+inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+}  // namespace hpfg

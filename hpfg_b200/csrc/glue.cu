@@ -1,0 +1,500 @@
+// Glue kernels (see glue.cuh).  All HBM-bound element-wise / gather / per-channel-reduction work:
+// 16-byte vector accesses along the contiguous channel dimension, grids sized from the SM count.
+// Reference semantics: nn.BatchNorm2d / nn.LeakyReLU / nn.Dropout / nn.MaxPool2d(2) /
+// nn.Upsample(scale_factor=2, bilinear, align_corners=True) / torch.cat as wired in model/unet.py:12-58.
+#include "glue.cuh"
+
+namespace hpfg {
+
+template <typename T> struct Vec;
+template <> struct Vec<float> {
+    static constexpr int N = 4;
+    __device__ static void load(const float *p, float (&v)[4]) {
+        const float4 r = *reinterpret_cast<const float4 *>(p);
+        v[0] = r.x; v[1] = r.y; v[2] = r.z; v[3] = r.w;
+    }
+    __device__ static void store(float *p, const float (&v)[4]) {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+    }
+};
+template <> struct Vec<bf16> {
+    static constexpr int N = 8;
+    __device__ static void load(const bf16 *p, float (&v)[8]) {
+        const uint4 r = *reinterpret_cast<const uint4 *>(p);
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            v[2 * i] = __uint_as_float(w[i] << 16);
+            v[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+        }
+    }
+    __device__ static void store(bf16 *p, const float (&v)[8]) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const __nv_bfloat162 h = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            w[i] = *reinterpret_cast<const uint32_t *>(&h);
+        }
+        *reinterpret_cast<uint4 *>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+};
+
+static int ew_grid(int64_t work_items, int threads = 256) {
+    int64_t b = (work_items + threads - 1) / threads;
+    const int64_t cap = (int64_t)kNumSMs * 16;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+// ------------------------------------------------------------------------------------------ bn_finalize
+__global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restrict__ partials, int P, int C,
+                                                          double inv_count, double unbias,
+                                                          const float *__restrict__ gamma,
+                                                          const float *__restrict__ beta,
+                                                          const float *__restrict__ conv_bias, float *running_mean,
+                                                          float *running_var, int64_t *counter, int training,
+                                                          BnState st) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= C) return;
+    const int c = warp;
+    double s = 0.0, q = 0.0;
+    for (int p = lane; p < P; p += 32) {
+        s += (double)partials[(int64_t)p * 2 * C + c];
+        q += (double)partials[(int64_t)p * 2 * C + C + c];
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane != 0) return;
+    const double mean = s * inv_count;
+    double var = q * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double invstd = 1.0 / sqrt(var + (double)kBnEps);
+    st.scale[c] = (float)((double)gamma[c] * invstd);
+    st.shift[c] = (float)((double)beta[c] - mean * (double)gamma[c] * invstd);
+    st.mean[c] = (float)mean;
+    st.invstd[c] = (float)invstd;
+    if (training) {   // running estimates track the biased conv output (bias is left out of the stored tensor)
+        const float b = conv_bias ? conv_bias[c] : 0.f;
+        running_mean[c] = (1.f - kBnMomentum) * running_mean[c] + kBnMomentum * ((float)mean + b);
+        running_var[c] = (1.f - kBnMomentum) * running_var[c] + kBnMomentum * (float)(var * unbias);
+        if (c == 0 && counter) *counter += 1;
+    }
+}
+
+int bn_finalize(const float *partials, int P, int C, int64_t count, const float *gamma, const float *beta,
+                const float *conv_bias, float *running_mean, float *running_var, int64_t *counter, int training,
+                BnState st, cudaStream_t s) {
+    const double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
+    bn_finalize_kernel<<<ceil_div(C * 32, 256), 256, 0, s>>>(partials, P, C, 1.0 / (double)count, unbias, gamma,
+                                                             beta, conv_bias, running_mean, running_var, counter,
+                                                             training, st);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+__global__ void bn_eval_affine_kernel(int C, const float *gamma, const float *beta, const float *conv_bias,
+                                      const float *rm, const float *rv, BnState st) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const float invstd = 1.f / sqrtf(rv[c] + kBnEps);
+    const float b = conv_bias ? conv_bias[c] : 0.f;
+    st.scale[c] = gamma[c] * invstd;
+    st.shift[c] = beta[c] - (rm[c] - b) * gamma[c] * invstd;   // stored tensor excludes the conv bias
+    st.mean[c] = rm[c] - b;
+    st.invstd[c] = invstd;
+}
+
+int bn_eval_affine(int C, const float *gamma, const float *beta, const float *conv_bias, const float *running_mean,
+                   const float *running_var, BnState st, cudaStream_t s) {
+    bn_eval_affine_kernel<<<ceil_div(C, 128), 128, 0, s>>>(C, gamma, beta, conv_bias, running_mean, running_var, st);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+// --------------------------------------------------------------------------------------------- pool_act
+template <typename T>
+__global__ void __launch_bounds__(256) pool_act_kernel(const T *__restrict__ raw, T *__restrict__ pooled, int N, int H,
+                                                       int W, int C, BnState bn) {
+    constexpr int V = Vec<T>::N;
+    const int CV = C / V, Ho = H >> 1, Wo = W >> 1;
+    const int64_t total = (int64_t)N * Ho * Wo * CV;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        int64_t pix = i / CV;
+        const int wo = (int)(pix % Wo);
+        pix /= Wo;
+        const int ho = (int)(pix % Ho), n = (int)(pix / Ho);
+        float sc[V], sh[V], best[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) { sc[k] = bn.scale[cv * V + k]; sh[k] = bn.shift[cv * V + k]; }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int h = 2 * ho + (d >> 1), w = 2 * wo + (d & 1);
+            float v[V];
+            Vec<T>::load(raw + (((int64_t)n * H + h) * W + w) * C + cv * V, v);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const float a = leaky(fmaf(v[k], sc[k], sh[k]));
+                best[k] = d == 0 ? a : fmaxf(best[k], a);
+            }
+        }
+        Vec<T>::store(pooled + (((int64_t)n * Ho + ho) * Wo + wo) * C + cv * V, best);
+    }
+}
+
+template <typename T>
+int pool_act(const T *raw, T *pooled, int N, int H, int W, int C, BnState bn, cudaStream_t s) {
+    const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / Vec<T>::N);
+    pool_act_kernel<T><<<ew_grid(total), 256, 0, s>>>(raw, pooled, N, H, W, C, bn);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ upcat
+// bilinear source coordinates exactly as ATen's upsample_bilinear2d (align_corners=True):
+// scale = (in-1)/(out-1) in fp32, src = scale*dst, i0 = (int)src, lambda1 = src - i0.
+__device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, int &i0, int &i1, float &l0, float &l1) {
+    const float src = scale * (float)dst;
+    i0 = (int)src;
+    if (i0 > in_size - 1) i0 = in_size - 1;
+    i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+    l1 = src - (float)i0;
+    l0 = 1.f - l1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) upcat_kernel(const T *__restrict__ raw_skip, BnState bn, const T *__restrict__ low,
+                                                    T *__restrict__ cat, int N, int h, int w, int F, float sh_, float sw_) {
+    constexpr int V = Vec<T>::N;
+    const int H = 2 * h, W = 2 * w, FV = F / V, CV = 2 * FV;
+    const int64_t total = (int64_t)N * H * W * CV;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % CV);
+        int64_t pix = i / CV;
+        const int x = (int)(pix % W);
+        pix /= W;
+        const int y = (int)(pix % H), n = (int)(pix / H);
+        float out[V];
+        if (cv < FV) {   // skip half: the encoder feature = leaky(bn(raw))
+            float v[V];
+            Vec<T>::load(raw_skip + (((int64_t)n * H + y) * W + x) * F + cv * V, v);
+#pragma unroll
+            for (int k = 0; k < V; ++k) out[k] = leaky(fmaf(v[k], bn.scale[cv * V + k], bn.shift[cv * V + k]));
+        } else {         // upsampled half
+            const int c0 = (cv - FV) * V;
+            int y0, y1, x0, x1;
+            float ly0, ly1, lx0, lx1;
+            bilinear_src(y, sh_, h, y0, y1, ly0, ly1);
+            bilinear_src(x, sw_, w, x0, x1, lx0, lx1);
+            float a[V], b[V], c[V], d[V];
+            const T *base = low + (int64_t)n * h * w * F + c0;
+            Vec<T>::load(base + ((int64_t)y0 * w + x0) * F, a);
+            Vec<T>::load(base + ((int64_t)y0 * w + x1) * F, b);
+            Vec<T>::load(base + ((int64_t)y1 * w + x0) * F, c);
+            Vec<T>::load(base + ((int64_t)y1 * w + x1) * F, d);
+#pragma unroll
+            for (int k = 0; k < V; ++k) out[k] = ly0 * (lx0 * a[k] + lx1 * b[k]) + ly1 * (lx0 * c[k] + lx1 * d[k]);
+        }
+        Vec<T>::store(cat + (((int64_t)n * H + y) * W + x) * (2 * F) + cv * V, out);
+    }
+}
+
+template <typename T>
+int upcat(const T *raw_skip, BnState bn_skip, const T *low, T *cat, int N, int h, int w, int F, cudaStream_t s) {
+    const int64_t total = (int64_t)N * 4 * h * w * (2 * F / Vec<T>::N);
+    const float sh_ = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
+    const float sw_ = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
+    upcat_kernel<T><<<ew_grid(total), 256, 0, s>>>(raw_skip, bn_skip, low, cat, N, h, w, F, sh_, sw_);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+// ----------------------------------------------------------------------------------------------- bn_bwd
+// g = dact * dropout' * leaky'(z);  xhat = (raw-mean)*invstd.  MODE 0: reduce sum(g), sum(g*xhat) into partials.
+// MODE 1: draw = scale*(g - c1 - xhat*c2).
+template <typename T, int MODE>
+__global__ void __launch_bounds__(256) bn_bwd_kernel(const T *__restrict__ dact, const T *__restrict__ raw,
+                                                     T *__restrict__ draw, int64_t M, int C, BnState bn, DropSpec drop,
+                                                     float *__restrict__ partials) {
+    constexpr int V = Vec<T>::N;
+    __shared__ float red[2 * 256 * V];
+    const int CV = C / V, R = 256 / CV;
+    const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
+    const bool active = r < R;
+    float sc[V], sh[V], mu[V], is[V], c1[V], c2[V], a0[V], a1[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        const int c = cv * V + k;
+        sc[k] = bn.scale[c]; sh[k] = bn.shift[c]; mu[k] = bn.mean[c]; is[k] = bn.invstd[c];
+        c1[k] = c2[k] = 0.f;
+        if (MODE == 1) { c1[k] = bn.c1[c]; c2[k] = bn.c2[c]; }
+        a0[k] = a1[k] = 0.f;
+    }
+    const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
+    const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
+    const int64_t p1 = (p0 + rows_per_block < M) ? p0 + rows_per_block : M;
+    if (active)
+        for (int64_t p = p0 + r; p < p1; p += R) {
+            float d[V], x[V];
+            Vec<T>::load(dact + p * C + cv * V, d);
+            Vec<T>::load(raw + p * C + cv * V, x);
+            uint32_t mbits = 0xffffffffu;
+            if (drop.bits) {
+                const int64_t e = p * C + cv * V;          // V divides 32, so the V bits sit in one word
+                mbits = drop.bits[e >> 5] >> (e & 31);
+            }
+            float o[V];
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const float z = fmaf(x[k], sc[k], sh[k]);
+                float g = d[k] * leaky_grad(z);
+                if (drop.bits) g = ((mbits >> k) & 1u) ? g * drop.inv_keep : 0.f;
+                const float xh = (x[k] - mu[k]) * is[k];
+                if (MODE == 0) { a0[k] += g; a1[k] += g * xh; }
+                else o[k] = sc[k] * (g - c1[k] - xh * c2[k]);
+            }
+            if (MODE == 1) Vec<T>::store(draw + p * C + cv * V, o);
+        }
+    if (MODE == 0) {
+        // deterministic cross-row reduction through shared memory: red[which][r][c]
+        if (active) {
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                red[(0 * 256 + r * CV + cv) * V + k] = a0[k];
+                red[(1 * 256 + r * CV + cv) * V + k] = a1[k];
+            }
+        }
+        __syncthreads();
+        for (int o = threadIdx.x; o < 2 * C; o += 256) {
+            const int which = o / C, c = o % C;
+            float s = 0.f;
+            for (int rr = 0; rr < R; ++rr) s += red[(which * 256 + rr * CV + c / V) * V + (c % V)];
+            partials[(int64_t)blockIdx.x * 2 * C + o] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float *__restrict__ partials, int P, int C,
+                                                              double inv_count, BnState bn, float *dgamma, float *dbeta,
+                                                              int accumulate) {
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= C) return;
+    const int c = warp;
+    double s = 0.0, q = 0.0;
+    for (int p = lane; p < P; p += 32) {
+        s += (double)partials[(int64_t)p * 2 * C + c];
+        q += (double)partials[(int64_t)p * 2 * C + C + c];
+    }
+    s = warp_sum(s);
+    q = warp_sum(q);
+    if (lane != 0) return;
+    bn.c1[c] = (float)(s * inv_count);
+    bn.c2[c] = (float)(q * inv_count);
+    if (accumulate) { dgamma[c] += (float)q; dbeta[c] += (float)s; }
+    else { dgamma[c] = (float)q; dbeta[c] = (float)s; }
+}
+
+template <typename T>
+int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, DropSpec drop, float *partials,
+           int max_partials, float *dgamma, float *dbeta, int accumulate, cudaStream_t s) {
+    int P = (int)((M + 63) / 64);
+    if (P > kNumSMs * 4) P = kNumSMs * 4;
+    if (P > max_partials) P = max_partials;
+    bn_bwd_kernel<T, 0><<<P, 256, 0, s>>>(dact, raw, draw, M, C, bn, drop, partials);
+    HPFG_LAUNCH_CHECK();
+    bn_bwd_finalize_kernel<<<ceil_div(C * 32, 256), 256, 0, s>>>(partials, P, C, 1.0 / (double)M, bn, dgamma, dbeta,
+                                                                 accumulate);
+    HPFG_LAUNCH_CHECK();
+    int P2 = (int)((M + 63) / 64);
+    if (P2 > kNumSMs * 8) P2 = kNumSMs * 8;
+    bn_bwd_kernel<T, 1><<<P2, 256, 0, s>>>(dact, raw, draw, M, C, bn, drop, nullptr);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+// ------------------------------------------------------------------------------------------ skip_pool_bwd
+template <typename T>
+__global__ void __launch_bounds__(256) skip_pool_bwd_kernel(const T *__restrict__ dcat, const T *__restrict__ dpooled,
+                                                            const T *__restrict__ raw, BnState bn, T *__restrict__ dact,
+                                                            int N, int H, int W, int F) {
+    constexpr int V = Vec<T>::N;
+    const int FV = F / V, Ho = H >> 1, Wo = W >> 1;
+    const int64_t total = (int64_t)N * Ho * Wo * FV;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % FV);
+        int64_t pix = i / FV;
+        const int wo = (int)(pix % Wo);
+        pix /= Wo;
+        const int ho = (int)(pix % Ho), n = (int)(pix / Ho);
+        float sc[V], sh[V], best[V], dp[V];
+        int arg[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) { sc[k] = bn.scale[cv * V + k]; sh[k] = bn.shift[cv * V + k]; dp[k] = 0.f; arg[k] = 0; best[k] = 0.f; }
+        if (dpooled) Vec<T>::load(dpooled + (((int64_t)n * Ho + ho) * Wo + wo) * F + cv * V, dp);
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {   // first maximum in (h,w) scan order, as max_pool2d_with_indices
+            const int h = 2 * ho + (d >> 1), w = 2 * wo + (d & 1);
+            float v[V];
+            Vec<T>::load(raw + (((int64_t)n * H + h) * W + w) * F + cv * V, v);
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                const float a = leaky(fmaf(v[k], sc[k], sh[k]));
+                if (d == 0 || a > best[k]) { best[k] = a; arg[k] = d; }
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < 4; ++d) {
+            const int h = 2 * ho + (d >> 1), w = 2 * wo + (d & 1);
+            const int64_t p = ((int64_t)n * H + h) * W + w;
+            float o[V];
+            if (dcat) Vec<T>::load(dcat + p * (2 * F) + cv * V, o);
+            else {
+#pragma unroll
+                for (int k = 0; k < V; ++k) o[k] = 0.f;
+            }
+            if (dpooled) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) if (arg[k] == d) o[k] += dp[k];
+            }
+            Vec<T>::store(dact + p * F + cv * V, o);
+        }
+    }
+}
+
+template <typename T>
+int skip_pool_bwd(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *dact, int N, int H, int W, int F,
+                  cudaStream_t s) {
+    const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (F / Vec<T>::N);
+    skip_pool_bwd_kernel<T><<<ew_grid(total), 256, 0, s>>>(dcat, dpooled, raw, bn, dact, N, H, W, F);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ up_bwd
+template <typename T>
+__global__ void __launch_bounds__(256) up_bwd_kernel(const T *__restrict__ dcat, T *__restrict__ dlow, int N, int h, int w,
+                                                     int F, float sh_, float sw_) {
+    constexpr int V = Vec<T>::N;
+    const int FV = F / V, H = 2 * h, W = 2 * w;
+    const int64_t total = (int64_t)N * h * w * FV;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int cv = (int)(i % FV);
+        int64_t pix = i / FV;
+        const int x = (int)(pix % w);
+        pix /= w;
+        const int y = (int)(pix % h), n = (int)(pix / h);
+        float acc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) acc[k] = 0.f;
+        // destination rows whose bilinear footprint can touch source row y: dst in [2y-2, 2y+3]
+        for (int Y = max(0, 2 * y - 2); Y <= min(H - 1, 2 * y + 3); ++Y) {
+            int y0, y1; float ly0, ly1;
+            bilinear_src(Y, sh_, h, y0, y1, ly0, ly1);
+            float wy = 0.f;
+            if (y0 == y) wy += ly0;
+            if (y1 == y) wy += ly1;
+            if (wy == 0.f) continue;
+            for (int X = max(0, 2 * x - 2); X <= min(W - 1, 2 * x + 3); ++X) {
+                int x0, x1; float lx0, lx1;
+                bilinear_src(X, sw_, w, x0, x1, lx0, lx1);
+                float wx = 0.f;
+                if (x0 == x) wx += lx0;
+                if (x1 == x) wx += lx1;
+                if (wx == 0.f) continue;
+                float g[V];
+                Vec<T>::load(dcat + (((int64_t)n * H + Y) * W + X) * (2 * F) + F + cv * V, g);
+                const float wgt = wy * wx;
+#pragma unroll
+                for (int k = 0; k < V; ++k) acc[k] = fmaf(wgt, g[k], acc[k]);
+            }
+        }
+        Vec<T>::store(dlow + (((int64_t)n * h + y) * w + x) * F + cv * V, acc);
+    }
+}
+
+template <typename T>
+int up_bwd(const T *dcat, T *dlow, int N, int h, int w, int F, cudaStream_t s) {
+    const int64_t total = (int64_t)N * h * w * (F / Vec<T>::N);
+    const float sh_ = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
+    const float sw_ = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
+    up_bwd_kernel<T><<<ew_grid(total), 256, 0, s>>>(dcat, dlow, N, h, w, F, sh_, sw_);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+// ------------------------------------------------------------------------------------------ dropout_bits
+// One thread per 32-bit word of the NHWC bit mask.  Philox stream: counter = NCHW element index / 4 (so the
+// draw is layout independent), key = seed, second counter word = offset.  keep <=> u >= p  (Bernoulli(1-p)).
+__global__ void __launch_bounds__(256) dropout_bits_kernel(uint32_t *__restrict__ bits, const uint8_t *__restrict__ mask,
+                                                           int N, int H, int W, int C, float p, uint64_t seed,
+                                                           uint64_t offset, int64_t n_words) {
+    const int64_t total = (int64_t)N * H * W * C;
+    for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += (int64_t)gridDim.x * blockDim.x) {
+        uint32_t word = 0;
+        for (int b = 0; b < 32; ++b) {
+            const int64_t e = wi * 32 + b;
+            if (e >= total) break;
+            const int c = (int)(e % C);
+            int64_t pix = e / C;
+            const int x = (int)(pix % W);
+            pix /= W;
+            const int y = (int)(pix % H), n = (int)(pix / H);
+            const int64_t nchw = (((int64_t)n * C + c) * H + y) * W + x;
+            bool keep;
+            if (mask) keep = mask[nchw] != 0;
+            else {
+                const uint64_t ctr = (uint64_t)nchw >> 2;
+                const uint4 r = philox4x32_10(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)),
+                                              make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)offset,
+                                                         (uint32_t)(offset >> 32)));
+                const uint32_t rv = (nchw & 3) == 0 ? r.x : (nchw & 3) == 1 ? r.y : (nchw & 3) == 2 ? r.z : r.w;
+                keep = ((float)(rv >> 8) * (1.0f / 16777216.0f)) >= p;
+            }
+            word |= (keep ? 1u : 0u) << b;
+        }
+        bits[wi] = word;
+    }
+}
+
+int dropout_bits(uint32_t *bits, const uint8_t *mask_nchw, int N, int H, int W, int C, float p, uint64_t seed,
+                 uint64_t offset, cudaStream_t s) {
+    const int64_t n_words = ((int64_t)N * H * W * C + 31) / 32;
+    dropout_bits_kernel<<<ew_grid(n_words), 256, 0, s>>>(bits, mask_nchw, N, H, W, C, p, seed, offset, n_words);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+// -------------------------------------------------------------------------------------- nhwc_to_nchw_f32
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, float *__restrict__ dst, int N, int H, int W, int C,
+                                    const float *__restrict__ bias) {
+    const int64_t total = (int64_t)N * C * H * W;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int x = (int)(i % W);
+        int64_t t = i / W;
+        const int y = (int)(t % H);
+        t /= H;
+        const int c = (int)(t % C), n = (int)(t / C);
+        dst[i] = to_f32(src[(((int64_t)n * H + y) * W + x) * C + c]) + (bias ? bias[c] : 0.f);
+    }
+}
+
+template <typename T>
+int nhwc_to_nchw_f32(const T *src, float *dst, int N, int H, int W, int C, const float *bias, cudaStream_t s) {
+    nhwc_to_nchw_kernel<T><<<ew_grid((int64_t)N * C * H * W), 256, 0, s>>>(src, dst, N, H, W, C, bias);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+#define INSTANTIATE(T)                                                                                              \
+    template int pool_act<T>(const T *, T *, int, int, int, int, BnState, cudaStream_t);                            \
+    template int upcat<T>(const T *, BnState, const T *, T *, int, int, int, int, cudaStream_t);                    \
+    template int bn_bwd<T>(const T *, const T *, T *, int64_t, int, BnState, DropSpec, float *, int, float *,       \
+                           float *, int, cudaStream_t);                                                             \
+    template int skip_pool_bwd<T>(const T *, const T *, const T *, BnState, T *, int, int, int, int, cudaStream_t); \
+    template int up_bwd<T>(const T *, T *, int, int, int, int, cudaStream_t);                                       \
+    template int nhwc_to_nchw_f32<T>(const T *, float *, int, int, int, int, const float *, cudaStream_t);
+INSTANTIATE(float)
+INSTANTIATE(bf16)
+
+}  // namespace hpfg

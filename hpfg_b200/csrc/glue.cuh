@@ -1,0 +1,55 @@
+// Declarations of the layout-generic "glue" kernels shared by the fp32 check path and the bf16 tensor-core
+// path: BatchNorm statistics finalisation / backward, activated max-pool, bilinear-upsample + concat gather
+// and their adjoints, dropout bit-mask generation.  All activations are NHWC, T = float|bf16.
+#pragma once
+#include "common.cuh"
+
+namespace hpfg {
+
+// Per-BatchNorm device state owned by the plan (all fp32, C entries each).
+struct BnState {
+    float *scale, *shift;      // fused affine: y = x*scale + shift  (scale = gamma*invstd, shift = beta - mean*scale)
+    float *mean, *invstd;      // batch statistics of the bias-free conv output (saved for backward)
+    float *c1, *c2;            // backward: mean(g), mean(g*xhat)
+};
+
+struct DropSpec {
+    const uint32_t *bits;      // NHWC bit-packed keep mask (bit = element index & 31), or nullptr = no dropout
+    float inv_keep;            // 1/(1-p)
+};
+
+// stats partials: [P][2*C] floats (sum | sum of squares); finalize -> BnState (+ running stats when training)
+int bn_finalize(const float *partials, int P, int C, int64_t count, const float *gamma, const float *beta,
+                const float *conv_bias, float *running_mean, float *running_var, int64_t *counter, int training,
+                BnState st, cudaStream_t s);
+// eval mode: scale/shift from the running statistics (conv bias folded in)
+int bn_eval_affine(int C, const float *gamma, const float *beta, const float *conv_bias, const float *running_mean,
+                   const float *running_var, BnState st, cudaStream_t s);
+
+template <typename T>
+int pool_act(const T *raw, T *pooled, int N, int H, int W, int C, BnState bn, cudaStream_t s);
+template <typename T>
+int upcat(const T *raw_skip, BnState bn_skip, const T *low, T *cat, int N, int h, int w, int F, cudaStream_t s);
+
+// BatchNorm (+LeakyReLU +dropout) backward.  dact: grad wrt dropout(leaky(bn(raw))).  draw: grad wrt raw.
+template <typename T>
+int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, DropSpec drop, float *partials,
+           int max_partials, float *dgamma, float *dbeta, int accumulate, cudaStream_t s);
+
+// grad wrt an encoder feature = skip half of dcat (+) un-pooled grad of the pooled tensor
+template <typename T>
+int skip_pool_bwd(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *dact, int N, int H, int W, int F,
+                  cudaStream_t s);
+// adjoint of the bilinear x2 (align_corners) upsample: dcat[..., F:2F] at (2h,2w) -> dlow at (h,w)
+template <typename T>
+int up_bwd(const T *dcat, T *dlow, int N, int h, int w, int F, cudaStream_t s);
+
+// dropout keep-mask bits (NHWC order) from a user NCHW uint8 mask or from Philox(seed, offset, NCHW index)
+int dropout_bits(uint32_t *bits, const uint8_t *mask_nchw, int N, int H, int W, int C, float p, uint64_t seed,
+                 uint64_t offset, cudaStream_t s);
+
+// NHWC (T) -> NCHW fp32 copy with optional per-channel bias (debug taps)
+template <typename T>
+int nhwc_to_nchw_f32(const T *src, float *dst, int N, int H, int W, int C, const float *bias, cudaStream_t s);
+
+}  // namespace hpfg

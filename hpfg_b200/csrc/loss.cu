@@ -1,0 +1,570 @@
+// Fused SSL loss: softmax, cross-entropy, batch-wide soft Dice, Mean-Teacher softmax-MSE consistency, CPS
+// argmax pseudo-labelling and UAMT uncertainty masking, forward value AND d loss / d logits.
+//   utils/loss/medloss.py:5-56 (Med_Sup_Loss, DiceLoss), utils/loss/diceloss.py:64-81,155-191,
+//   2017_03_NIPS_Mean-Teacher_ACDC.py:97-106, 2021_06_CVPR_CPS_ACDC.py:99-111,
+//   2019_07_MICCAI_Uncertainty_Aware_ACDC.py:145-162.
+// Dice is a ratio of batch-wide sums, so the gradient needs those sums first: phase 1 (reduce kernel) streams
+// the logits once and reduces with warp shuffles -> one double atomic per block per quantity; phase 2 (grad
+// kernel) streams them again (L2-resident: the logits are << 126 MB) and writes dlogits.  Both are pure HBM
+// kernels: NCHW fp32, 4 consecutive pixels per thread, 128-bit loads per class plane.
+// Algorithmic bytes (MT): (n_l+n_u)*C*HW*4 read + n_u*C*HW*4 read + n_l*HW*8 read + (n_l+n_u)*C*HW*4 written.
+#include "common.cuh"
+
+namespace hpfg {
+
+constexpr int kMaxC = 8;
+constexpr int kAccPerSet = 3 * kMaxC + 2;   // I[8] Z[8] Y[8] ce n_valid
+constexpr int kAccMse = 4 * kAccPerSet;     // after the 4 (net,set) groups
+constexpr int kAccMaskSum = kAccMse + 1;
+constexpr int kAccMaskedDist = kAccMse + 2;
+constexpr int kAccTotal = 128;
+constexpr float kDiceSmooth = 1e-5f;
+
+struct LossArgs {
+    int mode, n_l, n_u, hw, mc_passes;
+    const float *student, *other, *mc;
+    const int64_t *labels;
+    float cons_weight, uamt_threshold, ce_coef, dice_coef;
+    float class_w[kMaxC];
+    float *dstudent, *dother, *scalars;
+    int64_t *pseudo1, *pseudo2;
+    double *acc;
+    uint8_t *aux;   // CPS: pl1 | pl2 (n_u*hw each); UAMT: mask (n_u*hw)
+};
+
+template <int C>
+__device__ __forceinline__ void load4(const float *base, int64_t hw, float (&z)[C][4]) {
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        const float4 v = __ldg(reinterpret_cast<const float4 *>(base + (int64_t)c * hw));
+        z[c][0] = v.x; z[c][1] = v.y; z[c][2] = v.z; z[c][3] = v.w;
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void softmax4(const float (&z)[C][4], float (&p)[C][4], float (&lse)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float m = z[0][j];
+#pragma unroll
+        for (int c = 1; c < C; ++c) m = fmaxf(m, z[c][j]);
+        float s = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { p[c][j] = expf(z[c][j] - m); s += p[c][j]; }
+        const float inv = 1.f / s;
+#pragma unroll
+        for (int c = 0; c < C; ++c) p[c][j] *= inv;
+        lse[j] = m + logf(s);
+    }
+}
+
+template <int C>
+__device__ __forceinline__ int argmax_first(const float (&p)[C][4], int j) {
+    int best = 0;
+    float bv = p[0][j];
+#pragma unroll
+    for (int c = 1; c < C; ++c)
+        if (p[c][j] > bv) { bv = p[c][j]; best = c; }
+    return best;
+}
+
+// accumulate CE + Dice partial sums of 4 pixels against labels lab[4] (255 -> ignored by CE, no class for Dice)
+template <int C>
+__device__ __forceinline__ void acc_sup(const float (&z)[C][4], const float (&p)[C][4], const float (&lse)[4],
+                                        const int (&lab)[4], float (&a)[3 * C + 2]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float t = (lab[j] == c) ? 1.f : 0.f;
+            a[c] += p[c][j] * t;
+            a[C + c] += p[c][j] * p[c][j];
+            a[2 * C + c] += t;
+            if (lab[j] == c) a[3 * C] += lse[j] - z[c][j];
+        }
+        if (lab[j] != 255) a[3 * C + 1] += 1.f;
+    }
+}
+
+template <int N>
+__device__ __forceinline__ void flush(float (&a)[N], double *dst_base, const int *slot, float *smem) {
+    // warp reduce each accumulator, then cross-warp through shared memory, then one atomic per block
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+#pragma unroll
+    for (int i = 0; i < N; ++i) {
+        const float v = warp_sum(a[i]);
+        if (lane == 0) smem[warp * N + i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < N) {
+        double s = 0.0;
+        for (int w = 0; w < nwarp; ++w) s += (double)smem[w * N + threadIdx.x];
+        if (s != 0.0) atomicAdd(dst_base + slot[threadIdx.x], s);
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ void load_labels4(const int64_t *p, int (&lab)[4]) {
+    const longlong2 a = __ldg(reinterpret_cast<const longlong2 *>(p));
+    const longlong2 b = __ldg(reinterpret_cast<const longlong2 *>(p + 2));
+    lab[0] = (int)a.x; lab[1] = (int)a.y; lab[2] = (int)b.x; lab[3] = (int)b.y;
+}
+
+// ---------------------------------------------------------------------------------------------- phase 1
+template <int C>
+__global__ void __launch_bounds__(256) loss_reduce_kernel(LossArgs A) {
+    constexpr int NS = 3 * C + 2;
+    __shared__ float smem[8 * (2 * NS + 3)];
+    __shared__ int slots[2 * NS + 3];
+    const int64_t hw = A.hw, q_per_img = hw >> 2;
+    const int64_t n_img = A.n_l + A.n_u;
+    const int64_t total_q = n_img * q_per_img;
+    float sl[2][NS];   // labeled sums, net 0 / net 1
+    float su[2][NS];   // CPS: unlabeled sums wrt the peer's pseudo labels
+    float misc[3] = {0.f, 0.f, 0.f};   // mse, mask_sum, masked_dist
+#pragma unroll
+    for (int i = 0; i < NS; ++i) sl[0][i] = sl[1][i] = su[0][i] = su[1][i] = 0.f;
+
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_q;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = q / q_per_img, pix = (q - img * q_per_img) << 2;
+        float z[C][4], p[C][4], lse[4];
+        load4<C>(A.student + (img * C) * hw + pix, hw, z);
+        softmax4<C>(z, p, lse);
+        if (img < A.n_l) {
+            int lab[4];
+            load_labels4(A.labels + img * hw + pix, lab);
+            acc_sup<C>(z, p, lse, lab, sl[0]);
+            if (A.mode == HPFG_LOSS_CPS) {
+                float z2[C][4], p2[C][4], lse2[4];
+                load4<C>(A.other + (img * C) * hw + pix, hw, z2);
+                softmax4<C>(z2, p2, lse2);
+                acc_sup<C>(z2, p2, lse2, lab, sl[1]);
+            }
+        } else if (A.mode != HPFG_LOSS_SUP) {
+            const int64_t u = img - A.n_l;
+            float z2[C][4], p2[C][4], lse2[4];
+            const float *ob = (A.mode == HPFG_LOSS_CPS) ? A.other + (img * C) * hw + pix
+                                                        : A.other + (u * C) * hw + pix;
+            load4<C>(ob, hw, z2);
+            softmax4<C>(z2, p2, lse2);
+            if (A.mode == HPFG_LOSS_MT) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) { const float d = p[c][j] - p2[c][j]; misc[0] += d * d; }
+            } else if (A.mode == HPFG_LOSS_CPS) {
+                int pl1[4], pl2[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { pl1[j] = argmax_first<C>(p, j); pl2[j] = argmax_first<C>(p2, j); }
+                acc_sup<C>(z, p, lse, pl2, su[0]);      // net 1 learns from net 2's labels
+                acc_sup<C>(z2, p2, lse2, pl1, su[1]);   // and vice versa
+                const int64_t o = u * hw + pix;
+                *reinterpret_cast<uchar4 *>(A.aux + o) = make_uchar4(pl1[0], pl1[1], pl1[2], pl1[3]);
+                *reinterpret_cast<uchar4 *>(A.aux + (int64_t)A.n_u * hw + o) = make_uchar4(pl2[0], pl2[1], pl2[2], pl2[3]);
+                if (A.pseudo1)
+                    for (int j = 0; j < 4; ++j) A.pseudo1[o + j] = pl1[j];
+                if (A.pseudo2)
+                    for (int j = 0; j < 4; ++j) A.pseudo2[o + j] = pl2[j];
+            } else {   // UAMT: mean softmax of the T stochastic teacher passes -> entropy -> mask
+                float mean[C][4];
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) mean[c][j] = 0.f;
+                for (int t = 0; t < A.mc_passes; ++t) {
+                    float zm[C][4], pm[C][4], lm[4];
+                    load4<C>(A.mc + (((int64_t)t * A.n_u + u) * C) * hw + pix, hw, zm);
+                    softmax4<C>(zm, pm, lm);
+#pragma unroll
+                    for (int c = 0; c < C; ++c)
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) mean[c][j] += pm[c][j];
+                }
+                const float invT = 1.f / (float)A.mc_passes;
+                unsigned char mk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float ent = 0.f, dist = 0.f;
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float m = mean[c][j] * invT;
+                        ent -= m * logf(m + 1e-6f);
+                        const float d = p[c][j] - p2[c][j];
+                        dist += d * d;
+                    }
+                    mk[j] = ent < A.uamt_threshold ? 1 : 0;
+                    if (mk[j]) { misc[1] += 1.f; misc[2] += dist; }
+                }
+                *reinterpret_cast<uchar4 *>(A.aux + u * hw + pix) = make_uchar4(mk[0], mk[1], mk[2], mk[3]);
+            }
+        }
+    }
+    // map compact per-thread accumulators to the global slots (class index padded to kMaxC)
+    auto slot_of = [](int set_base, int i) {
+        const int grp = i / C, c = i % C;
+        return set_base + (grp < 3 ? grp * kMaxC + c : 3 * kMaxC + (i - 3 * C));
+    };
+    if (threadIdx.x < NS) slots[threadIdx.x] = slot_of(0, threadIdx.x);
+    __syncthreads();
+    flush<NS>(sl[0], A.acc + 0 * kAccPerSet, slots, smem);
+    if (A.mode == HPFG_LOSS_CPS) {
+        flush<NS>(sl[1], A.acc + 2 * kAccPerSet, slots, smem);
+        flush<NS>(su[0], A.acc + 1 * kAccPerSet, slots, smem);
+        flush<NS>(su[1], A.acc + 3 * kAccPerSet, slots, smem);
+    }
+    if (A.mode == HPFG_LOSS_MT || A.mode == HPFG_LOSS_UAMT) {
+        if (threadIdx.x < 3) slots[threadIdx.x] = threadIdx.x;
+        __syncthreads();
+        flush<3>(misc, A.acc + kAccMse, slots, smem);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------- phase 2
+// per-(net,set) coefficients derived from the global sums
+struct SupCoef {
+    float alpha[kMaxC], beta[kMaxC], inv_nv, ce, dice;
+};
+
+template <int C>
+__device__ void make_coef(const double *acc, const float *cw, SupCoef &k) {
+    double dice = 0.0;
+    for (int c = 0; c < C; ++c) {
+        const double I = acc[c], Z = acc[kMaxC + c], Y = acc[2 * kMaxC + c];
+        const double D = Z + Y + (double)kDiceSmooth;
+        const double num = 2.0 * I + (double)kDiceSmooth;
+        dice += (1.0 - num / D) * (double)cw[c];
+        k.alpha[c] = (float)(-2.0 * cw[c] / (C * D));
+        k.beta[c] = (float)(2.0 * cw[c] * num / (C * D * D));
+    }
+    const double nv = acc[3 * kMaxC + 1];
+    k.dice = (float)(dice / C);
+    k.ce = (float)(acc[3 * kMaxC] / nv);
+    k.inv_nv = (float)(1.0 / nv);
+}
+
+// gradient of coef_ce*CE + coef_dice*Dice wrt the logits of 4 pixels, times `scale`
+template <int C>
+__device__ __forceinline__ void grad_sup(const float (&p)[C][4], const int (&lab)[4], const SupCoef &k, float ce_coef,
+                                         float dice_coef, float scale, float (&g)[C][4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a[C], dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float t = (lab[j] == c) ? 1.f : 0.f;
+            a[c] = dice_coef * (k.alpha[c] * t + k.beta[c] * p[c][j]);
+            dot += p[c][j] * a[c];
+        }
+        const float cev = (lab[j] != 255) ? ce_coef * k.inv_nv : 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const float t = (lab[j] == c) ? 1.f : 0.f;
+            g[c][j] = scale * (p[c][j] * (a[c] - dot) + cev * (p[c][j] - t));
+        }
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void grad_mse(const float (&p)[C][4], const float (&q)[C][4], const float (&coef)[4],
+                                         float (&g)[C][4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        float a[C], dot = 0.f;
+#pragma unroll
+        for (int c = 0; c < C; ++c) { a[c] = coef[j] * (p[c][j] - q[c][j]); dot += p[c][j] * a[c]; }
+#pragma unroll
+        for (int c = 0; c < C; ++c) g[c][j] = p[c][j] * (a[c] - dot);
+    }
+}
+
+template <int C>
+__device__ __forceinline__ void store4(float *base, int64_t hw, const float (&g)[C][4]) {
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        *reinterpret_cast<float4 *>(base + (int64_t)c * hw) = make_float4(g[c][0], g[c][1], g[c][2], g[c][3]);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
+    __shared__ SupCoef coef[4];   // [net*2 + set]
+    __shared__ float s_cons;      // per-element consistency coefficient
+    const bool cps = A.mode == HPFG_LOSS_CPS;
+    if (threadIdx.x == 0) {
+        make_coef<C>(A.acc + 0 * kAccPerSet, A.class_w, coef[0]);
+        if (cps) {
+            make_coef<C>(A.acc + 1 * kAccPerSet, A.class_w, coef[1]);
+            make_coef<C>(A.acc + 2 * kAccPerSet, A.class_w, coef[2]);
+            make_coef<C>(A.acc + 3 * kAccPerSet, A.class_w, coef[3]);
+        }
+        float cons = 0.f, cons_val = 0.f;
+        const double M = (double)A.n_u * C * (double)A.hw;
+        if (A.mode == HPFG_LOSS_MT) {
+            cons_val = (float)(A.acc[kAccMse] / M);
+            cons = (float)(2.0 * A.cons_weight / M);
+        } else if (A.mode == HPFG_LOSS_UAMT) {
+            const double den = 2.0 * A.acc[kAccMaskSum] + 1e-16;
+            cons_val = (float)(A.acc[kAccMaskedDist] / den);
+            cons = (float)(2.0 * A.cons_weight / den);
+        }
+        s_cons = cons;
+        if (blockIdx.x == 0) {
+            const float sup0 = A.ce_coef * coef[0].ce + A.dice_coef * coef[0].dice;
+            float sup = sup0, aux = cons_val;
+            if (cps) {
+                sup = sup0 + A.ce_coef * coef[2].ce + A.dice_coef * coef[2].dice;
+                aux = A.ce_coef * coef[1].ce + A.dice_coef * coef[1].dice + A.ce_coef * coef[3].ce +
+                      A.dice_coef * coef[3].dice;
+            }
+            const float loss = (A.mode == HPFG_LOSS_SUP) ? sup : sup + A.cons_weight * aux;
+            A.scalars[0] = loss;
+            A.scalars[1] = sup;
+            A.scalars[2] = aux;
+            A.scalars[3] = coef[0].ce;
+            A.scalars[4] = coef[0].dice;
+            A.scalars[5] = (float)A.acc[3 * kMaxC + 1];
+            A.scalars[6] = (float)A.acc[kAccMaskSum];
+            A.scalars[7] = 0.f;
+        }
+    }
+    __syncthreads();
+    const int64_t hw = A.hw, q_per_img = hw >> 2;
+    const int64_t total_q = (int64_t)(A.n_l + A.n_u) * q_per_img;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_q;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = q / q_per_img, pix = (q - img * q_per_img) << 2;
+        const int64_t so = (img * C) * hw + pix;
+        float z[C][4], p[C][4], lse[4], g[C][4];
+        if (img < A.n_l) {
+            int lab[4];
+            load_labels4(A.labels + img * hw + pix, lab);
+            load4<C>(A.student + so, hw, z);
+            softmax4<C>(z, p, lse);
+            grad_sup<C>(p, lab, coef[0], A.ce_coef, A.dice_coef, 1.f, g);
+            store4<C>(A.dstudent + so, hw, g);
+            if (cps) {
+                load4<C>(A.other + so, hw, z);
+                softmax4<C>(z, p, lse);
+                grad_sup<C>(p, lab, coef[2], A.ce_coef, A.dice_coef, 1.f, g);
+                store4<C>(A.dother + so, hw, g);
+            }
+            continue;
+        }
+        const int64_t u = img - A.n_l;
+        if (A.mode == HPFG_LOSS_SUP) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) g[c][j] = 0.f;
+            store4<C>(A.dstudent + so, hw, g);
+            continue;
+        }
+        load4<C>(A.student + so, hw, z);
+        softmax4<C>(z, p, lse);
+        if (cps) {
+            const uchar4 a1 = *reinterpret_cast<const uchar4 *>(A.aux + u * hw + pix);
+            const uchar4 a2 = *reinterpret_cast<const uchar4 *>(A.aux + (int64_t)A.n_u * hw + u * hw + pix);
+            const int pl1[4] = {a1.x, a1.y, a1.z, a1.w}, pl2[4] = {a2.x, a2.y, a2.z, a2.w};
+            grad_sup<C>(p, pl2, coef[1], A.ce_coef, A.dice_coef, A.cons_weight, g);
+            store4<C>(A.dstudent + so, hw, g);
+            load4<C>(A.other + so, hw, z);
+            softmax4<C>(z, p, lse);
+            grad_sup<C>(p, pl1, coef[3], A.ce_coef, A.dice_coef, A.cons_weight, g);
+            store4<C>(A.dother + so, hw, g);
+        } else {
+            float z2[C][4], q2[C][4], l2[4], cf[4];
+            load4<C>(A.other + (u * C) * hw + pix, hw, z2);
+            softmax4<C>(z2, q2, l2);
+            if (A.mode == HPFG_LOSS_UAMT) {
+                const uchar4 mk = *reinterpret_cast<const uchar4 *>(A.aux + u * hw + pix);
+                cf[0] = mk.x ? s_cons : 0.f; cf[1] = mk.y ? s_cons : 0.f;
+                cf[2] = mk.z ? s_cons : 0.f; cf[3] = mk.w ? s_cons : 0.f;
+            } else {
+                cf[0] = cf[1] = cf[2] = cf[3] = s_cons;
+            }
+            grad_mse<C>(p, q2, cf, g);
+            store4<C>(A.dstudent + so, hw, g);
+        }
+    }
+}
+
+// -------------------------------------------------------------------------- stand-alone DiceLoss.forward
+struct DiceArgs {
+    const float *inputs;
+    const int64_t *target;
+    int n, hw, softmax;
+    float class_w[kMaxC];
+    float *dinputs, *scalars;
+    double *acc;
+};
+
+template <int C>
+__global__ void __launch_bounds__(256) dice_reduce_kernel(DiceArgs A) {
+    constexpr int NS = 3 * C + 2;
+    __shared__ float smem[8 * NS];
+    __shared__ int slots[NS];
+    const int64_t hw = A.hw, q_per_img = hw >> 2, total_q = (int64_t)A.n * q_per_img;
+    float a[NS];
+#pragma unroll
+    for (int i = 0; i < NS; ++i) a[i] = 0.f;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_q;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = q / q_per_img, pix = (q - img * q_per_img) << 2;
+        float z[C][4], p[C][4], lse[4];
+        int lab[4];
+        load4<C>(A.inputs + (img * C) * hw + pix, hw, z);
+        load_labels4(A.target + img * hw + pix, lab);
+        if (A.softmax) {
+            softmax4<C>(z, p, lse);
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) p[c][j] = z[c][j];
+            lse[0] = lse[1] = lse[2] = lse[3] = 0.f;
+        }
+        acc_sup<C>(z, p, lse, lab, a);
+    }
+    if (threadIdx.x < NS) {
+        const int i = threadIdx.x, grp = i / C, c = i % C;
+        slots[i] = grp < 3 ? grp * kMaxC + c : 3 * kMaxC + (i - 3 * C);
+    }
+    __syncthreads();
+    flush<NS>(a, A.acc, slots, smem);
+}
+
+template <int C>
+__global__ void __launch_bounds__(256) dice_grad_kernel(DiceArgs A) {
+    __shared__ SupCoef k;
+    if (threadIdx.x == 0) {
+        make_coef<C>(A.acc, A.class_w, k);
+        if (blockIdx.x == 0) {
+            A.scalars[0] = k.dice;
+            for (int c = 0; c < C; ++c) {
+                const double I = A.acc[c], Z = A.acc[kMaxC + c], Y = A.acc[2 * kMaxC + c];
+                A.scalars[1 + c] = (float)((2.0 * I + kDiceSmooth) / (Z + Y + kDiceSmooth));
+            }
+        }
+    }
+    __syncthreads();
+    if (A.dinputs == nullptr) return;
+    const int64_t hw = A.hw, q_per_img = hw >> 2, total_q = (int64_t)A.n * q_per_img;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_q;
+         q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = q / q_per_img, pix = (q - img * q_per_img) << 2;
+        float z[C][4], p[C][4], lse[4], g[C][4];
+        int lab[4];
+        load4<C>(A.inputs + (img * C) * hw + pix, hw, z);
+        load_labels4(A.target + img * hw + pix, lab);
+        if (A.softmax) {
+            softmax4<C>(z, p, lse);
+            grad_sup<C>(p, lab, k, 0.f, 1.f, 1.f, g);
+        } else {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    g[c][j] = k.alpha[c] * ((lab[j] == c) ? 1.f : 0.f) + k.beta[c] * z[c][j];
+        }
+        store4<C>(A.dinputs + (img * C) * hw + pix, hw, g);
+    }
+}
+
+static int loss_grid(int64_t quads) {
+    int64_t blocks = (quads + 255) / 256;
+    const int64_t cap = (int64_t)kNumSMs * 8;
+    if (blocks > cap) blocks = cap;
+    return (int)(blocks < 1 ? 1 : blocks);
+}
+
+template <int C>
+static int launch_loss(const LossArgs &A, cudaStream_t st) {
+    const int grid = loss_grid((int64_t)(A.n_l + A.n_u) * (A.hw >> 2));
+    loss_reduce_kernel<C><<<grid, 256, 0, st>>>(A);
+    HPFG_LAUNCH_CHECK();
+    loss_grad_kernel<C><<<grid, 256, 0, st>>>(A);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+template <int C>
+static int launch_dice(const DiceArgs &A, cudaStream_t st) {
+    const int grid = loss_grid((int64_t)A.n * (A.hw >> 2));
+    dice_reduce_kernel<C><<<grid, 256, 0, st>>>(A);
+    HPFG_LAUNCH_CHECK();
+    dice_grad_kernel<C><<<A.dinputs ? grid : 1, 256, 0, st>>>(A);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+}  // namespace hpfg
+
+using namespace hpfg;
+
+extern "C" int64_t hpfg_ssl_loss_workspace_bytes(int mode, int n_l, int n_u, int num_classes, int height,
+                                                 int width) {
+    (void)n_l; (void)num_classes;
+    int64_t aux = 0;
+    if (mode == HPFG_LOSS_CPS) aux = 2LL * n_u * height * width;
+    if (mode == HPFG_LOSS_UAMT) aux = 1LL * n_u * height * width;
+    return kAccTotal * (int64_t)sizeof(double) + ((aux + 255) / 256) * 256;
+}
+
+extern "C" int hpfg_ssl_loss(int mode, const float *student, const float *other, const float *mc_logits,
+                             int mc_passes, const int64_t *labels, int n_l, int n_u, int num_classes, int height,
+                             int width, float cons_weight, float uamt_threshold, const float *class_weights_host,
+                             float ce_coef, float dice_coef, float *dstudent, float *dother, float *scalars_out,
+                             int64_t *pseudo1, int64_t *pseudo2, void *workspace, void *stream) {
+    HPFG_REQUIRE(mode >= HPFG_LOSS_SUP && mode <= HPFG_LOSS_UAMT, "hpfg_ssl_loss: unknown mode");
+    HPFG_REQUIRE(student && dstudent && scalars_out && workspace, "hpfg_ssl_loss: null buffer");
+    HPFG_REQUIRE(n_l >= 0 && n_u >= 0 && n_l + n_u > 0, "hpfg_ssl_loss: empty batch");
+    HPFG_REQUIRE(n_l == 0 || labels, "hpfg_ssl_loss: labels required");
+    HPFG_REQUIRE(num_classes >= 2 && num_classes <= kMaxC, "hpfg_ssl_loss: num_classes must be in [2,8]");
+    HPFG_REQUIRE(((int64_t)height * width) % 4 == 0, "hpfg_ssl_loss: H*W must be a multiple of 4");
+    if (mode != HPFG_LOSS_SUP && n_u > 0) HPFG_REQUIRE(other, "hpfg_ssl_loss: teacher/peer logits required");
+    if (mode == HPFG_LOSS_CPS) HPFG_REQUIRE(dother && other, "hpfg_ssl_loss: CPS needs peer logits and dother");
+    if (mode == HPFG_LOSS_UAMT) HPFG_REQUIRE(mc_logits && mc_passes > 0, "hpfg_ssl_loss: UAMT needs mc_logits");
+    cudaStream_t st = (cudaStream_t)stream;
+    LossArgs A{};
+    A.mode = mode; A.n_l = n_l; A.n_u = n_u; A.hw = height * width; A.mc_passes = mc_passes;
+    A.student = student; A.other = other; A.mc = mc_logits; A.labels = labels;
+    A.cons_weight = cons_weight; A.uamt_threshold = uamt_threshold; A.ce_coef = ce_coef; A.dice_coef = dice_coef;
+    for (int c = 0; c < kMaxC; ++c) A.class_w[c] = (class_weights_host && c < num_classes) ? class_weights_host[c] : 1.f;
+    A.dstudent = dstudent; A.dother = dother; A.scalars = scalars_out; A.pseudo1 = pseudo1; A.pseudo2 = pseudo2;
+    A.acc = reinterpret_cast<double *>(workspace);
+    A.aux = reinterpret_cast<uint8_t *>(workspace) + kAccTotal * sizeof(double);
+    HPFG_CUDA_CHECK(cudaMemsetAsync(A.acc, 0, kAccTotal * sizeof(double), st));
+    switch (num_classes) {
+        case 2: return launch_loss<2>(A, st);
+        case 3: return launch_loss<3>(A, st);
+        case 4: return launch_loss<4>(A, st);
+        case 5: return launch_loss<5>(A, st);
+        case 6: return launch_loss<6>(A, st);
+        case 7: return launch_loss<7>(A, st);
+        default: return launch_loss<8>(A, st);
+    }
+}
+
+extern "C" int hpfg_dice_loss(const float *inputs, const int64_t *target, int n, int num_classes, int height,
+                              int width, int softmax, const float *class_weights_host, float *dinputs,
+                              float *scalars_out, void *workspace, void *stream) {
+    HPFG_REQUIRE(inputs && target && scalars_out && workspace, "hpfg_dice_loss: null buffer");
+    HPFG_REQUIRE(n > 0, "hpfg_dice_loss: empty batch");
+    HPFG_REQUIRE(num_classes >= 2 && num_classes <= kMaxC, "hpfg_dice_loss: num_classes must be in [2,8]");
+    HPFG_REQUIRE(((int64_t)height * width) % 4 == 0, "hpfg_dice_loss: H*W must be a multiple of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    DiceArgs A{};
+    A.inputs = inputs; A.target = target; A.n = n; A.hw = height * width; A.softmax = softmax;
+    for (int c = 0; c < kMaxC; ++c) A.class_w[c] = (class_weights_host && c < num_classes) ? class_weights_host[c] : 1.f;
+    A.dinputs = dinputs; A.scalars = scalars_out; A.acc = reinterpret_cast<double *>(workspace);
+    HPFG_CUDA_CHECK(cudaMemsetAsync(A.acc, 0, kAccTotal * sizeof(double), st));
+    switch (num_classes) {
+        case 2: return launch_dice<2>(A, st);
+        case 3: return launch_dice<3>(A, st);
+        case 4: return launch_dice<4>(A, st);
+        case 5: return launch_dice<5>(A, st);
+        case 6: return launch_dice<6>(A, st);
+        case 7: return launch_dice<7>(A, st);
+        default: return launch_dice<8>(A, st);
+    }
+}

@@ -1,0 +1,480 @@
+// UNet plan: network description, workspace, forward/backward schedules and the C ABI entry points for them.
+// Wiring follows model/unet.py: Encoder :61-82, Decoder :85-117, ConvBlock :12-28, DownBlock :31-42, UpBlock :45-58.
+#include "unet_plan.cuh"
+
+#include <cstring>
+
+#include "conv_tc.cuh"
+
+namespace hpfg {
+
+static thread_local std::string g_error;
+int64_t g_launch_count = 0;
+void set_error(const std::string &msg) { g_error = msg; }
+
+void describe_unet(int in_ch, int n_cls, int H, int W, UNetDesc &d) {
+    d.in_ch = in_ch;
+    d.n_cls = n_cls;
+    d.convs.clear();
+    d.bns.clear();
+    int64_t off = 0, run = 0;
+    int pi = 0;
+    auto add_param = [&](int64_t n) {
+        d.offsets[pi] = off;
+        d.sizes[pi] = n;
+        ++pi;
+        const int64_t o = off;
+        off += n;
+        return o;
+    };
+    auto add_conv = [&](const std::string &name, int cin, int cout, int ks, int h, int w, bool with_bn) {
+        ConvLayer c;
+        c.name = name;
+        c.cin = cin; c.cout = cout; c.ks = ks; c.H = h; c.W = w;
+        c.w_off = add_param((int64_t)cout * cin * ks * ks);
+        c.b_off = add_param(cout);
+        c.bn = -1;
+        if (with_bn) {
+            BnLayer b;
+            b.C = cout;
+            b.g_off = add_param(cout);
+            b.b_off = add_param(cout);
+            b.run_off = run;
+            run += 2 * cout;
+            b.conv = (int)d.convs.size();
+            b.H = h; b.W = w;
+            c.bn = (int)d.bns.size();
+            d.bns.push_back(b);
+        }
+        d.convs.push_back(c);
+    };
+    auto add_block = [&](const std::string &prefix, int cin, int cout, int h, int w) {
+        add_conv(prefix + ".conv_conv.0", cin, cout, 3, h, w, true);
+        add_conv(prefix + ".conv_conv.4", cout, cout, 3, h, w, true);
+    };
+    int64_t bounds[5] = {0, 0, 0, 0, 0};
+    add_block("encoder.in_conv", in_ch, kFt[0], H, W);
+    for (int l = 1; l < 5; ++l) {
+        if (l == 4) bounds[1] = off;
+        add_block("encoder.down" + std::to_string(l) + ".maxpool_conv.1", kFt[l - 1], kFt[l], H >> l, W >> l);
+    }
+    for (int j = 1; j < 5; ++j) {
+        const int lvl = 4 - j;   // skip level; output resolution
+        if (j == 1) bounds[2] = off;
+        if (j == 3) bounds[3] = off;
+        const std::string p = "decoder.up" + std::to_string(j);
+        add_conv(p + ".conv1x1", kFt[lvl + 1], kFt[lvl], 1, H >> (lvl + 1), W >> (lvl + 1), false);
+        add_block(p + ".conv", 2 * kFt[lvl], kFt[lvl], H >> lvl, W >> lvl);
+    }
+    add_conv("decoder.out_conv", kFt[0], n_cls, 3, H, W, false);
+    bounds[4] = off;
+    d.n_params = off;
+    d.n_bn_floats = run;
+    // buckets in completion order (tail first)
+    for (int b = 0; b <= kNumBuckets; ++b) d.bucket_begin[b] = bounds[kNumBuckets - b];
+}
+
+static int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+struct Carver {
+    char *base;
+    int64_t off = 0;
+    template <typename P> void take(P *&ptr, int64_t bytes) {
+        ptr = base ? reinterpret_cast<P *>(base + off) : nullptr;
+        off += align_up(bytes, 256);
+    }
+};
+
+static void carve(hpfg_unet_plan *p, char *base, int64_t &total) {
+    Carver c{base};
+    const int64_t N = p->N, H = p->H, W = p->W;
+    const int64_t e = (int64_t)p->elt;
+    for (auto &b : p->d.bns) c.take(b.raw, N * b.H * b.W * b.C * e);
+    for (int l = 1; l < 5; ++l) c.take(p->pooled[l], N * (H >> l) * (W >> l) * kFt[l - 1] * e);
+    for (int j = 1; j < 5; ++j) {
+        const int lvl = 4 - j;
+        c.take(p->low[j], N * (H >> (lvl + 1)) * (W >> (lvl + 1)) * kFt[lvl] * e);
+        c.take(p->cat[j], N * (H >> lvl) * (W >> lvl) * 2 * kFt[lvl] * e);
+        c.take(p->dcat[j], N * (H >> lvl) * (W >> lvl) * 2 * kFt[lvl] * e);
+    }
+    for (int k = 0; k < 4; ++k) c.take(p->g[k], N * H * W * 16 * e);
+    for (int l = 0; l < 5; ++l) c.take(p->dropbits[l], (N * (H >> l) * (W >> l) * kFt[l] + 31) / 32 * 4);
+    // BN statistic partials: one row of 2*C floats per 8x8 pixel tile (CUDA-core path) / per CTA tile (tensor path)
+    int64_t sf = 0, wf = 0;
+    for (auto &b : p->d.bns) {
+        const int64_t tiles = conv_ref_num_tiles((int)N, b.H, b.W);
+        sf = std::max<int64_t>(sf, tiles * 2 * b.C);
+    }
+    sf = std::max<int64_t>(sf, (int64_t)kNumSMs * 8 * 2 * 256);   // bn_bwd partials
+    p->stats_floats = sf;
+    c.take(p->stats, sf * 4);
+    for (auto &cv : p->d.convs)
+        wf = std::max(wf, conv_ref_wgrad_scratch_floats((int)N, cv.H, cv.W, cv.cin, cv.cout, cv.ks));
+    p->wscratch_floats = wf;
+    c.take(p->wscratch, wf * 4);
+    int64_t bnf = 0;
+    for (auto &b : p->d.bns) bnf += 6 * (int64_t)align_up(b.C, 64);
+    c.take(p->bnmem, bnf * 4);
+    if (base) {
+        float *q = p->bnmem;
+        for (auto &b : p->d.bns) {
+            const int64_t s = align_up(b.C, 64);
+            b.st = BnState{q, q + s, q + 2 * s, q + 3 * s, q + 4 * s, q + 5 * s};
+            q += 6 * s;
+        }
+    }
+    for (auto &cv : p->d.convs) {
+        const int64_t n = (int64_t)cv.cout * cv.cin * cv.ks * cv.ks;
+        c.take(cv.wf, n * 4);
+        c.take(cv.wd, n * 4);
+    }
+    total = c.off;
+}
+
+// ------------------------------------------------------------------------------------------------------
+template <typename T>
+static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_running, int64_t *bn_counters, const float *x,
+                        float *logits, int training, int no_dropout, int save, uint64_t seed, uint64_t offset,
+                        const uint8_t *const *masks, cudaStream_t s) {
+    UNetDesc &d = p->d;
+    const int N = p->N, H = p->H, W = p->W;
+    const bool use_drop = training && !no_dropout;
+    const bool tc = p->precision == HPFG_PREC_BF16;
+
+    // per-step weight preparation (parameters change every optimiser step)
+    for (auto &cv : d.convs)
+        HPFG_RETURN_IF(pack_weights_ref(params + cv.w_off, cv.wf, cv.wd, cv.cin, cv.cout, cv.ks, s));
+    if (tc) HPFG_RETURN_IF(tc_pack_all(p, params, s));
+    if (use_drop)
+        for (int l = 0; l < 5; ++l)
+            HPFG_RETURN_IF(dropout_bits(p->dropbits[l], masks ? masks[l] : nullptr, N, H >> l, W >> l, kFt[l],
+                                        kEncDropout[l], seed, offset + (uint64_t)l, s));
+
+    // conv + (train: statistics -> finalize | eval: running-stat affine)
+    auto conv_bn = [&](int ci, TView in, bool in_is_f32, LoadXform xf) -> int {
+        ConvLayer &cv = d.convs[ci];
+        BnLayer &b = d.bns[cv.bn];
+        TView out = nhwc_view(b.raw, cv.H, cv.W, cv.cout);
+        float *stats = training ? p->stats : nullptr;
+        int P = conv_ref_num_tiles(N, cv.H, cv.W);
+        bool done = false;
+        if (tc && !in_is_f32) HPFG_RETURN_IF(tc_fprop(p, ci, in.p, b.raw, xf, stats, &P, &done, s));
+        if (!done) {
+            if (in_is_f32)
+                HPFG_RETURN_IF((conv_ref_fprop<float, T>(in, out, cv.wf, nullptr, N, cv.H, cv.W, cv.cin, cv.cout, cv.ks,
+                                                         xf, stats, s)));
+            else
+                HPFG_RETURN_IF((conv_ref_fprop<T, T>(in, out, cv.wf, nullptr, N, cv.H, cv.W, cv.cin, cv.cout, cv.ks, xf,
+                                                     stats, s)));
+        }
+        if (training)
+            return bn_finalize(p->stats, P, b.C, (int64_t)N * cv.H * cv.W, params + b.g_off, params + b.b_off,
+                               params + cv.b_off, bn_running + b.run_off, bn_running + b.run_off + b.C,
+                               bn_counters ? bn_counters + cv.bn : nullptr, 1, b.st, s);
+        return bn_eval_affine(b.C, params + b.g_off, params + b.b_off, params + cv.b_off, bn_running + b.run_off,
+                              bn_running + b.run_off + b.C, b.st, s);
+    };
+    auto xf_of = [&](int bn, const uint32_t *bits, float p_drop) {
+        LoadXform xf{};
+        xf.scale = d.bns[bn].st.scale;
+        xf.shift = d.bns[bn].st.shift;
+        xf.drop.bits = bits;
+        xf.drop.inv_keep = bits ? 1.f / (1.f - p_drop) : 1.f;
+        return xf;
+    };
+    const LoadXform none{};
+
+    // ---- encoder (model/unet.py:76-82)
+    for (int l = 0; l < 5; ++l) {
+        const int h = H >> l, w = W >> l, c0 = 2 * l, c1 = 2 * l + 1;
+        if (l == 0)
+            HPFG_RETURN_IF(conv_bn(c0, nchw_view(const_cast<float *>(x), p->in_ch, H, W), true, none));
+        else
+            HPFG_RETURN_IF(conv_bn(c0, nhwc_view(p->pooled[l], h, w, kFt[l - 1]), false, none));
+        HPFG_RETURN_IF(conv_bn(c1, nhwc_view(d.bns[c0].raw, h, w, kFt[l]), false,
+                               xf_of(c0, use_drop ? p->dropbits[l] : nullptr, kEncDropout[l])));
+        if (l < 4)
+            HPFG_RETURN_IF(pool_act<T>((const T *)d.bns[c1].raw, (T *)p->pooled[l + 1], N, h, w, kFt[l], d.bns[c1].st, s));
+    }
+    // ---- decoder (model/unet.py:101-117)
+    int prev_bn = 9;
+    for (int j = 1; j < 5; ++j) {
+        const int lvl = 4 - j, F = kFt[lvl], hl = H >> (lvl + 1), wl = W >> (lvl + 1);
+        const int c1x1 = 10 + 3 * (j - 1), cA = c1x1 + 1, cB = c1x1 + 2;
+        ConvLayer &c11 = d.convs[c1x1];
+        {
+            bool done = false;
+            LoadXform xf = xf_of(prev_bn, nullptr, 0.f);
+            if (tc) HPFG_RETURN_IF(tc_fprop_1x1(p, c1x1, d.bns[prev_bn].raw, p->low[j], xf, params + c11.b_off, &done, s));
+            if (!done)
+                HPFG_RETURN_IF((conv_ref_fprop<T, T>(nhwc_view(d.bns[prev_bn].raw, hl, wl, 2 * F), nhwc_view(p->low[j], hl, wl, F),
+                                                     c11.wf, params + c11.b_off, N, hl, wl, 2 * F, F, 1, xf, nullptr, s)));
+        }
+        const int skip_bn = 2 * lvl + 1;
+        HPFG_RETURN_IF(upcat<T>((const T *)d.bns[skip_bn].raw, d.bns[skip_bn].st, (const T *)p->low[j], (T *)p->cat[j], N, hl,
+                                wl, F, s));
+        HPFG_RETURN_IF(conv_bn(cA, nhwc_view(p->cat[j], 2 * hl, 2 * wl, 2 * F), false, none));
+        HPFG_RETURN_IF(conv_bn(cB, nhwc_view(d.bns[d.convs[cA].bn].raw, 2 * hl, 2 * wl, F), false,
+                               xf_of(d.convs[cA].bn, nullptr, 0.f)));
+        prev_bn = d.convs[cB].bn;
+    }
+    // ---- out_conv (model/unet.py:99,116): 3x3 16 -> num_classes with bias, logits fp32 NCHW
+    ConvLayer &oc = d.convs[22];
+    HPFG_RETURN_IF((conv_ref_fprop<T, float>(nhwc_view(d.bns[17].raw, H, W, 16), nchw_view(logits, p->n_cls, H, W), oc.wf,
+                                             params + oc.b_off, N, H, W, 16, p->n_cls, 3, xf_of(17, nullptr, 0.f), nullptr,
+                                             s)));
+    p->saved = save != 0 && training != 0;
+    p->saved_dropout = use_drop;
+    p->saved_x = x;
+    return HPFG_OK;
+}
+
+template <typename T>
+static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dlogits, float *grads, int acc,
+                         cudaStream_t s) {
+    UNetDesc &d = p->d;
+    const int N = p->N, H = p->H, W = p->W;
+    const bool tc = p->precision == HPFG_PREC_BF16;
+    const LoadXform none{};
+    auto xf_of = [&](int bn, const uint32_t *bits, float p_drop) {
+        LoadXform xf{};
+        xf.scale = d.bns[bn].st.scale;
+        xf.shift = d.bns[bn].st.shift;
+        xf.drop.bits = bits;
+        xf.drop.inv_keep = bits ? 1.f / (1.f - p_drop) : 1.f;
+        return xf;
+    };
+    // weight gradient of conv `ci`: in (T NHWC, optionally transformed on load) x dout (T NHWC)
+    auto wgrad = [&](int ci, void *in, LoadXform xf, void *dout) -> int {
+        ConvLayer &cv = d.convs[ci];
+        bool done = false;
+        if (tc) HPFG_RETURN_IF(tc_wgrad(p, ci, in, xf, dout, grads + cv.w_off, grads + cv.b_off, acc, &done, s));
+        if (done) return HPFG_OK;
+        return conv_ref_wgrad<T, T>(nhwc_view(in, cv.H, cv.W, cv.cin), nhwc_view(dout, cv.H, cv.W, cv.cout), N, cv.H, cv.W,
+                                    cv.cin, cv.cout, cv.ks, xf, p->wscratch, p->wscratch_floats, grads + cv.w_off,
+                                    grads + cv.b_off, acc, s);
+    };
+    // data gradient of conv `ci`: din[.., cin] = conv(dout[.., cout], flipped weights)
+    auto dgrad = [&](int ci, void *dout, void *din) -> int {
+        ConvLayer &cv = d.convs[ci];
+        bool done = false;
+        if (tc) HPFG_RETURN_IF(tc_dgrad(p, ci, dout, din, &done, s));
+        if (done) return HPFG_OK;
+        return conv_ref_fprop<T, T>(nhwc_view(dout, cv.H, cv.W, cv.cout), nhwc_view(din, cv.H, cv.W, cv.cin), cv.wd, nullptr,
+                                    N, cv.H, cv.W, cv.cout, cv.cin, cv.ks, none, nullptr, s);
+    };
+    auto bnb = [&](int bn, void *dact, void *draw, const uint32_t *bits, float p_drop) -> int {
+        BnLayer &b = d.bns[bn];
+        DropSpec ds{bits, bits ? 1.f / (1.f - p_drop) : 1.f};
+        return bn_bwd<T>((const T *)dact, (const T *)b.raw, (T *)draw, (int64_t)N * b.H * b.W, b.C, b.st, ds, p->stats,
+                         (int)(p->stats_floats / (2 * b.C)), grads + b.g_off, grads + b.b_off, acc, s);
+    };
+
+    // ---- out_conv
+    {
+        ConvLayer &oc = d.convs[22];
+        HPFG_RETURN_IF((conv_ref_wgrad<T, float>(nhwc_view(d.bns[17].raw, H, W, 16),
+                                                 nchw_view(const_cast<float *>(dlogits), p->n_cls, H, W), N, H, W, 16, p->n_cls,
+                                                 3, xf_of(17, nullptr, 0.f), p->wscratch, p->wscratch_floats,
+                                                 grads + oc.w_off, grads + oc.b_off, acc, s)));
+        HPFG_RETURN_IF((conv_ref_fprop<float, T>(nchw_view(const_cast<float *>(dlogits), p->n_cls, H, W),
+                                                 nhwc_view(p->g[0], H, W, 16), oc.wd, nullptr, N, H, W, p->n_cls, 16, 3, none,
+                                                 nullptr, s)));
+    }
+    // gradient scratch rotation: `a` holds the grad wrt the activated output of the block being processed
+    void *a = p->g[0], *b = p->g[1], *c = p->g[2];
+    // ---- decoder, up4 .. up1
+    for (int j = 4; j >= 1; --j) {
+        const int lvl = 4 - j, c1x1 = 10 + 3 * (j - 1), cA = c1x1 + 1, cB = c1x1 + 2;
+        const int bA = d.convs[cA].bn, bB = d.convs[cB].bn;
+        HPFG_RETURN_IF(bnb(bB, a, b, nullptr, 0.f));                                // a -> draw(B) in b
+        HPFG_RETURN_IF(wgrad(cB, d.bns[bA].raw, xf_of(bA, nullptr, 0.f), b));
+        HPFG_RETURN_IF(dgrad(cB, b, c));                                            // -> dact(A) in c
+        HPFG_RETURN_IF(bnb(bA, c, b, nullptr, 0.f));                                // -> draw(A) in b
+        HPFG_RETURN_IF(wgrad(cA, p->cat[j], none, b));
+        HPFG_RETURN_IF(dgrad(cA, b, p->dcat[j]));                                   // -> dcat (skip | upsampled)
+        const int F = kFt[lvl], hl = H >> (lvl + 1), wl = W >> (lvl + 1);
+        HPFG_RETURN_IF(up_bwd<T>((const T *)p->dcat[j], (T *)b, N, hl, wl, F, s));  // -> dlow in b
+        const int prev_bn = (j == 1) ? 9 : d.convs[cB - 3].bn;
+        HPFG_RETURN_IF(wgrad(c1x1, d.bns[prev_bn].raw, xf_of(prev_bn, nullptr, 0.f), b));
+        HPFG_RETURN_IF(dgrad(c1x1, b, c));                                          // -> dact(prev) in c
+        std::swap(a, c);
+        if (j == 3) HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[0], s));
+        if (j == 1) HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[1], s));
+    }
+    // ---- encoder, down4 .. in_conv
+    void *dpooled = nullptr;
+    for (int l = 4; l >= 0; --l) {
+        const int cA = 2 * l, cB = 2 * l + 1, bA = cA, bB = cB, h = H >> l, w = W >> l;
+        const uint32_t *bits = p->saved_dropout ? p->dropbits[l] : nullptr;
+        if (l < 4)   // grad wrt the encoder feature = skip half of dcat + un-pooled grad from the level below
+            HPFG_RETURN_IF(skip_pool_bwd<T>((const T *)p->dcat[4 - l], (const T *)dpooled, (const T *)d.bns[bB].raw, d.bns[bB].st,
+                                            (T *)a, N, h, w, kFt[l], s));
+        HPFG_RETURN_IF(bnb(bB, a, b, nullptr, 0.f));                                // draw(B) in b
+        HPFG_RETURN_IF(wgrad(cB, d.bns[bA].raw, xf_of(bA, bits, kEncDropout[l]), b));
+        HPFG_RETURN_IF(dgrad(cB, b, c));                                            // dact(A) in c
+        HPFG_RETURN_IF(bnb(bA, c, b, bits, kEncDropout[l]));                        // draw(A) in b
+        if (l == 0) {
+            ConvLayer &cv = d.convs[0];
+            HPFG_RETURN_IF((conv_ref_wgrad<float, T>(nchw_view(const_cast<float *>(p->saved_x), p->in_ch, H, W),
+                                                     nhwc_view(b, H, W, 16), N, H, W, p->in_ch, 16, 3, none, p->wscratch,
+                                                     p->wscratch_floats, grads + cv.w_off, grads + cv.b_off, acc, s)));
+        } else {
+            HPFG_RETURN_IF(wgrad(cA, p->pooled[l], none, b));
+            HPFG_RETURN_IF(dgrad(cA, b, p->g[3]));                                  // dpooled for level l-1
+            dpooled = p->g[3];
+        }
+        if (l == 4) HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[2], s));
+        if (l == 0) HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[3], s));
+    }
+    return HPFG_OK;
+}
+
+}  // namespace hpfg
+
+using namespace hpfg;
+
+extern "C" const char *hpfg_last_error(void) { return g_error.c_str(); }
+extern "C" int hpfg_version(void) { return 100; }
+extern "C" int64_t hpfg_launch_count(void) { return g_launch_count; }
+
+extern "C" int hpfg_unet_param_layout(int in_channels, int num_classes, int64_t *offsets_host, int64_t *sizes_host,
+                                      int64_t *total_host) {
+    HPFG_REQUIRE(in_channels >= 1 && num_classes >= 1, "hpfg_unet_param_layout: bad channel counts");
+    UNetDesc d;
+    describe_unet(in_channels, num_classes, 16, 16, d);
+    if (offsets_host) std::memcpy(offsets_host, d.offsets, sizeof(d.offsets));
+    if (sizes_host) std::memcpy(sizes_host, d.sizes, sizeof(d.sizes));
+    if (total_host) *total_host = d.n_params;
+    return HPFG_OK;
+}
+
+extern "C" int hpfg_unet_bn_layout(int in_channels, int num_classes, int64_t *bn_offsets_host, int64_t *bn_channels_host,
+                                   int64_t *total_host) {
+    HPFG_REQUIRE(in_channels >= 1 && num_classes >= 1, "hpfg_unet_bn_layout: bad channel counts");
+    UNetDesc d;
+    describe_unet(in_channels, num_classes, 16, 16, d);
+    for (int i = 0; i < HPFG_NUM_BN; ++i) {
+        if (bn_offsets_host) bn_offsets_host[i] = d.bns[i].run_off;
+        if (bn_channels_host) bn_channels_host[i] = d.bns[i].C;
+    }
+    if (total_host) *total_host = d.n_bn_floats;
+    return HPFG_OK;
+}
+
+extern "C" int hpfg_unet_plan_create(int batch, int in_channels, int num_classes, int height, int width, int precision,
+                                     hpfg_unet_plan_t *plan_out) {
+    HPFG_REQUIRE(plan_out, "hpfg_unet_plan_create: plan_out is null");
+    HPFG_REQUIRE(batch >= 1 && in_channels >= 1 && in_channels <= 16, "hpfg_unet_plan_create: bad batch / in_channels");
+    HPFG_REQUIRE(num_classes >= 1 && num_classes <= 64, "hpfg_unet_plan_create: bad num_classes");
+    HPFG_REQUIRE(height >= 16 && width >= 16 && height % 16 == 0 && width % 16 == 0,
+                 "hpfg_unet_plan_create: H and W must be multiples of 16 (four 2x2 poolings)");
+    HPFG_REQUIRE(precision == HPFG_PREC_FP32 || precision == HPFG_PREC_BF16, "hpfg_unet_plan_create: unknown precision");
+    int dev = 0;
+    HPFG_CUDA_CHECK(cudaGetDevice(&dev));
+    cudaDeviceProp prop;
+    HPFG_CUDA_CHECK(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) {
+        set_error("hpfg_b200 is built for sm_100a only; device is sm_" + std::to_string(prop.major * 10 + prop.minor));
+        return HPFG_ERR_UNSUPPORTED;
+    }
+    auto *p = new hpfg_unet_plan();
+    p->N = batch; p->in_ch = in_channels; p->n_cls = num_classes; p->H = height; p->W = width; p->precision = precision;
+    p->elt = precision == HPFG_PREC_FP32 ? 4 : 2;
+    describe_unet(in_channels, num_classes, height, width, p->d);
+    int64_t total = 0;
+    carve(p, nullptr, total);
+    if (cudaMalloc(&p->ws, (size_t)total) != cudaSuccess) {
+        set_error("hpfg_unet_plan_create: cudaMalloc of " + std::to_string(total) + " bytes failed");
+        cudaGetLastError();
+        delete p;
+        return HPFG_ERR_CUDA;
+    }
+    p->ws_bytes = total;
+    carve(p, p->ws, total);
+    for (int b = 0; b < kNumBuckets; ++b) HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->bucket_ev[b], cudaEventDisableTiming));
+    if (precision == HPFG_PREC_BF16) {
+        const int rc = tc_plan_init(p);
+        if (rc != HPFG_OK) {
+            hpfg_unet_plan_destroy(p);
+            return rc;
+        }
+    }
+    *plan_out = p;
+    return HPFG_OK;
+}
+
+extern "C" int hpfg_unet_plan_destroy(hpfg_unet_plan_t p) {
+    if (!p) return HPFG_OK;
+    cudaDeviceSynchronize();
+    if (p->precision == HPFG_PREC_BF16) tc_plan_free(p);
+    for (int b = 0; b < kNumBuckets; ++b)
+        if (p->bucket_ev[b]) cudaEventDestroy(p->bucket_ev[b]);
+    if (p->ws) cudaFree(p->ws);
+    delete p;
+    return HPFG_OK;
+}
+
+extern "C" int64_t hpfg_unet_plan_workspace_bytes(hpfg_unet_plan_t p) { return p ? p->ws_bytes : 0; }
+
+extern "C" int hpfg_unet_forward(hpfg_unet_plan_t p, const float *params, float *bn_running, int64_t *bn_counters,
+                                 const float *x, float *logits, int training, int no_dropout, int save_for_backward,
+                                 uint64_t dropout_seed, uint64_t dropout_offset, const uint8_t *const *dropout_masks_host,
+                                 void *stream) {
+    HPFG_REQUIRE(p && params && bn_running && x && logits, "hpfg_unet_forward: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->precision == HPFG_PREC_FP32)
+        return forward_impl<float>(p, params, bn_running, bn_counters, x, logits, training, no_dropout, save_for_backward,
+                                   dropout_seed, dropout_offset, dropout_masks_host, s);
+    return forward_impl<bf16>(p, params, bn_running, bn_counters, x, logits, training, no_dropout, save_for_backward,
+                              dropout_seed, dropout_offset, dropout_masks_host, s);
+}
+
+extern "C" int hpfg_unet_backward(hpfg_unet_plan_t p, const float *params, const float *dlogits, float *grads,
+                                  int accumulate, void *stream) {
+    HPFG_REQUIRE(p && params && dlogits && grads, "hpfg_unet_backward: null argument");
+    HPFG_REQUIRE(p->saved, "hpfg_unet_backward: no training forward with save_for_backward on this plan");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->precision == HPFG_PREC_FP32) return backward_impl<float>(p, params, dlogits, grads, accumulate, s);
+    return backward_impl<bf16>(p, params, dlogits, grads, accumulate, s);
+}
+
+extern "C" int hpfg_unet_num_buckets(hpfg_unet_plan_t p) { return p ? kNumBuckets : 0; }
+
+extern "C" int hpfg_unet_bucket_range(hpfg_unet_plan_t p, int bucket, int64_t *offset_host, int64_t *count_host) {
+    HPFG_REQUIRE(p && bucket >= 0 && bucket < kNumBuckets, "hpfg_unet_bucket_range: bad bucket");
+    const int64_t lo = p->d.bucket_begin[bucket + 1], hi = p->d.bucket_begin[bucket];
+    if (offset_host) *offset_host = lo;
+    if (count_host) *count_host = hi - lo;
+    return HPFG_OK;
+}
+
+extern "C" int hpfg_unet_bucket_wait(hpfg_unet_plan_t p, int bucket, void *comm_stream) {
+    HPFG_REQUIRE(p && bucket >= 0 && bucket < kNumBuckets, "hpfg_unet_bucket_wait: bad bucket");
+    HPFG_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)comm_stream, p->bucket_ev[bucket], 0));
+    return HPFG_OK;
+}
+
+extern "C" int hpfg_unet_debug_tap(hpfg_unet_plan_t p, const char *name, float *out_nchw, int64_t capacity, void *stream) {
+    HPFG_REQUIRE(p && name && out_nchw, "hpfg_unet_debug_tap: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const std::string nm(name);
+    const bool f32 = p->precision == HPFG_PREC_FP32;
+    auto copy = [&](void *src, int h, int w, int c, const float *bias) -> int {
+        HPFG_REQUIRE((int64_t)p->N * h * w * c <= capacity, "hpfg_unet_debug_tap: output buffer too small");
+        return f32 ? nhwc_to_nchw_f32<float>((const float *)src, out_nchw, p->N, h, w, c, bias, s)
+                   : nhwc_to_nchw_f32<bf16>((const bf16 *)src, out_nchw, p->N, h, w, c, bias, s);
+    };
+    for (auto &cv : p->d.convs)
+        if (cv.name == nm && cv.bn >= 0) return copy(p->d.bns[cv.bn].raw, cv.H, cv.W, cv.cout, nullptr);
+    for (int j = 1; j < 5; ++j) {
+        const int lvl = 4 - j;
+        const std::string pre = "decoder.up" + std::to_string(j);
+        if (nm == pre + ".conv1x1") return copy(p->low[j], p->H >> (lvl + 1), p->W >> (lvl + 1), kFt[lvl], nullptr);
+        if (nm == pre + ".cat") return copy(p->cat[j], p->H >> lvl, p->W >> lvl, 2 * kFt[lvl], nullptr);
+    }
+    for (int l = 1; l < 5; ++l)
+        if (nm == "pooled" + std::to_string(l)) return copy(p->pooled[l], p->H >> l, p->W >> l, kFt[l - 1], nullptr);
+    set_error("hpfg_unet_debug_tap: unknown tap '" + nm + "'");
+    return HPFG_ERR_INVALID;
+}

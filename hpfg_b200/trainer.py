@@ -1,0 +1,179 @@
+"""Fused training steps for the three north-star trainers, built from the C-ABI calls only:
+
+* ``MeanTeacherStep``  -- 2017_03_NIPS_Mean-Teacher_ACDC.py:89-113
+* ``CPSStep``          -- 2021_06_CVPR_CPS_ACDC.py:90-120
+* ``UAMTStep``         -- 2019_07_MICCAI_Uncertainty_Aware_ACDC.py:120-170
+
+Each ``step()`` enqueues: student forward (activations kept in the plan), teacher/peer forward(s), ONE fused
+loss launch pair (value + dlogits), backward into a persistent flat gradient buffer, (data parallel: NCCL
+all-reduce of the gradient buckets on a side stream, overlapped with the rest of backward), and ONE fused
+SGD-momentum(+EMA) pass over the flat parameter buffers.  Nothing synchronises the host; the returned loss is
+a device scalar.  Host-side schedules (Medical_LR, consistency ramp-up, EMA alpha) are python floats exactly as
+in the reference (utils/scheduler/medical_lr.py:13-17, utils/utils.py:67-86)."""
+import math
+
+import torch
+
+from . import _lib as L
+from .losses import ssl_loss_raw
+from .utils import sigmoid_rampup
+
+
+def medical_lr(cur_itrs, base_lr, max_iterations):
+    """Learning rate used at iteration ``cur_itrs`` (1-based) by Medical_LR constructed with last_epoch=-1."""
+    return base_lr * (1.0 - (cur_itrs - 2) / max_iterations) ** 0.9
+
+
+class _StepBase:
+    def __init__(self, *, lr=0.01, momentum=0.9, weight_decay=1e-4, total_itrs=30000, consistency=0.1,
+                 consistency_rampup=200.0, process_group=None):
+        self.base_lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
+        self.total_itrs, self.consistency, self.consistency_rampup = total_itrs, consistency, consistency_rampup
+        self.cur_itrs = 0
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self._comm = None
+        self.last = {}
+
+    def _consistency_weight(self):
+        return self.consistency * sigmoid_rampup(self.cur_itrs // 150, self.consistency_rampup)
+
+    def _forward(self, model, x, save):
+        model.ensure_flat()
+        plan = model._acquire_plan(x, need_grad=save)
+        logits = model._run_forward(plan, x, save=save)
+        return plan, logits
+
+    def _backward(self, model, plan, dlogits, grads):
+        L.check(L.lib().hpfg_unet_backward(plan.handle, L.ptr(model.flat_params), L.ptr(dlogits), L.ptr(grads), 0,
+                                           L.stream_ptr(grads.device)), "hpfg_unet_backward")
+        if self.world > 1:
+            self._allreduce_buckets(plan, grads)
+
+    def _allreduce_buckets(self, plan, grads):
+        """Bucketed gradient all-reduce overlapped with the tail of backward: the comm stream waits on the
+        per-bucket events the plan recorded, NCCL runs there, the compute stream joins before the SGD pass."""
+        import ctypes
+        import torch.distributed as dist
+        if self._comm is None:
+            self._comm = torch.cuda.Stream(device=grads.device)
+        lib = L.lib()
+        off, cnt = ctypes.c_int64(), ctypes.c_int64()
+        works = []
+        for b in range(lib.hpfg_unet_num_buckets(plan.handle)):
+            L.check(lib.hpfg_unet_bucket_range(plan.handle, b, ctypes.byref(off), ctypes.byref(cnt)))
+            L.check(lib.hpfg_unet_bucket_wait(plan.handle, b, ctypes.c_void_p(self._comm.cuda_stream)))
+            with torch.cuda.stream(self._comm):
+                works.append(dist.all_reduce(grads[off.value:off.value + cnt.value], group=self.pg, async_op=True))
+        for w in works:
+            w.wait()            # stream-level wait on the compute stream, not a host sync
+
+    def _sgd(self, model, grads, buf, ema_model=None, ema_alpha=0.0):
+        lr = medical_lr(self.cur_itrs, self.base_lr, self.total_itrs)
+        n = model.flat_params.numel()
+        st = L.stream_ptr(grads.device)
+        first = int(self.cur_itrs == 1)
+        if ema_model is None:
+            L.check(L.lib().hpfg_sgd_momentum(L.ptr(model.flat_params), L.ptr(grads), L.ptr(buf), n, lr, self.momentum,
+                                              self.weight_decay, 1.0 / self.world, first, st), "hpfg_sgd_momentum")
+        else:
+            L.check(L.lib().hpfg_sgd_momentum_ema(L.ptr(model.flat_params), L.ptr(grads), L.ptr(buf),
+                                                  L.ptr(ema_model.flat_params), n, lr, self.momentum, self.weight_decay,
+                                                  1.0 / self.world, first, ema_alpha, st), "hpfg_sgd_momentum_ema")
+        return lr
+
+
+class MeanTeacherStep(_StepBase):
+    def __init__(self, model, ema_model, *, ema_decay=0.99, **kw):
+        super().__init__(**kw)
+        self.model, self.ema_model, self.ema_decay = model, ema_model, ema_decay
+        model.train()
+        ema_model.train()                               # the teacher runs in train() mode (2017_03...:70)
+        model.ensure_flat()
+        ema_model.ensure_flat()
+        self.grads = torch.zeros_like(model.flat_params)
+        self.mom = torch.zeros_like(model.flat_params)
+
+    def step(self, x, labels):
+        """x: [n_l+n_u, C, H, W] fp32 CUDA (labeled slices first); labels: [n_l, H, W] int64 CUDA."""
+        self.cur_itrs += 1
+        n_l = labels.shape[0]
+        plan, out = self._forward(self.model, x, True)
+        _, t_out = self._forward(self.ema_model, x, False)            # teacher sees the whole batch (:100)
+        w = self._consistency_weight()
+        r = ssl_loss_raw(L.LOSS_MT, out, t_out[n_l:], labels, n_l, cons_weight=w)
+        self._backward(self.model, plan, r["dstudent"], self.grads)
+        alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)      # utils/utils.py:84
+        lr = self._sgd(self.model, self.grads, self.mom, self.ema_model, alpha)
+        self.last = dict(scalars=r["scalars"], lr=lr, w=w, logits=out, teacher_logits=t_out)
+        return r["scalars"][0]
+
+
+class CPSStep(_StepBase):
+    def __init__(self, model1, model2, **kw):
+        super().__init__(**kw)
+        self.m1, self.m2 = model1, model2
+        model1.train()
+        model2.train()
+        model1.ensure_flat()
+        model2.ensure_flat()
+        self.g1, self.g2 = torch.zeros_like(model1.flat_params), torch.zeros_like(model2.flat_params)
+        self.b1, self.b2 = torch.zeros_like(model1.flat_params), torch.zeros_like(model2.flat_params)
+
+    def step(self, x, labels):
+        self.cur_itrs += 1
+        n_l = labels.shape[0]
+        p1, o1 = self._forward(self.m1, x, True)
+        p2, o2 = self._forward(self.m2, x, True)
+        w = self._consistency_weight()
+        r = ssl_loss_raw(L.LOSS_CPS, o1, o2, labels, n_l, cons_weight=w, want_pseudo=False)
+        self._backward(self.m1, p1, r["dstudent"], self.g1)
+        self._backward(self.m2, p2, r["dother"], self.g2)
+        lr = self._sgd(self.m1, self.g1, self.b1)
+        self._sgd(self.m2, self.g2, self.b2)
+        self.last = dict(scalars=r["scalars"], lr=lr, w=w, logits1=o1, logits2=o2)
+        return r["scalars"][0]
+
+
+class UAMTStep(_StepBase):
+    def __init__(self, model, ema_model, *, ema_decay=0.99, T=8, **kw):
+        super().__init__(**kw)
+        self.model, self.ema_model, self.ema_decay, self.T = model, ema_model, ema_decay, T
+        model.train()
+        ema_model.train()
+        model.ensure_flat()
+        ema_model.ensure_flat()
+        self.grads = torch.zeros_like(model.flat_params)
+        self.mom = torch.zeros_like(model.flat_params)
+
+    @staticmethod
+    def make_noise(like):
+        return torch.clamp(torch.randn_like(like) * 0.1, -0.2, 0.2)      # 2019_07...:130,141
+
+    def step(self, x, labels, noise=None, mc_noise=None):
+        """noise [n_u,...] / mc_noise [T//2, 2*n_u, ...]: the clamped perturbations; drawn here if None."""
+        self.cur_itrs += 1
+        n_l = labels.shape[0]
+        x_u = x[n_l:]
+        n_u = x_u.shape[0]
+        plan, out = self._forward(self.model, x, True)
+        if noise is None:
+            noise = self.make_noise(x_u)
+        _, t_out = self._forward(self.ema_model, (x_u + noise).contiguous(), False)
+        xr = x_u.repeat(2, 1, 1, 1)
+        mc = torch.empty((self.T * n_u, out.shape[1], x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
+        for i in range(self.T // 2):
+            nz = mc_noise[i] if mc_noise is not None else self.make_noise(xr)
+            _, o = self._forward(self.ema_model, (xr + nz).contiguous(), False)
+            mc[2 * n_u * i:2 * n_u * (i + 1)] = o
+        w = self._consistency_weight()
+        thr = (0.75 + 0.25 * sigmoid_rampup(self.cur_itrs, self.total_itrs)) * math.log(2)
+        r = ssl_loss_raw(L.LOSS_UAMT, out, t_out, labels, n_l, cons_weight=w, mc_logits=mc, mc_passes=self.T,
+                         uamt_threshold=thr)
+        self._backward(self.model, plan, r["dstudent"], self.grads)
+        alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)
+        lr = self._sgd(self.model, self.grads, self.mom, self.ema_model, alpha)
+        self.last = dict(scalars=r["scalars"], lr=lr, w=w, threshold=thr, logits=out, teacher_logits=t_out, mc_logits=mc)
+        return r["scalars"][0]

@@ -1,0 +1,237 @@
+"""Drop-in for the reference ``UNet`` (model/unet.py:155-175): an ``nn.Module`` with the same parameter and
+buffer names, shapes, registration order and initialisation stream, whose forward/backward run on the
+hand-written sm_100a kernels behind the C ABI (``include/hpfg_b200.h``).
+
+Parameters live in ONE flat fp32 buffer (``flat_params``); every ``nn.Parameter`` is a view into it, so
+``torch.optim.SGD(model.parameters())``, ``deepcopy(model)``, ``.to(device)``, ``state_dict()`` and the
+per-parameter EMA loop of the reference keep working, while the fused SGD/EMA/all-reduce passes operate on
+the flat buffer directly."""
+import copy
+import ctypes
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+
+FT_CHNS = [16, 32, 64, 128, 256]            # model/unet.py:160
+ENC_DROPOUT = [0.05, 0.1, 0.2, 0.3, 0.5]    # model/unet.py:161
+ENC_PREFIXES = ["encoder.in_conv"] + ["encoder.down%d.maxpool_conv.1" % i for i in range(1, 5)]
+
+
+def _conv_block(cin, cout, p):
+    # holder modules only: their own forward() is never called, they give the reference's names / init
+    blk = nn.Module()
+    blk.conv_conv = nn.Sequential(
+        nn.Conv2d(cin, cout, kernel_size=3, padding=1), nn.BatchNorm2d(cout), nn.LeakyReLU(), nn.Dropout(p),
+        nn.Conv2d(cout, cout, kernel_size=3, padding=1), nn.BatchNorm2d(cout), nn.LeakyReLU())
+    return blk
+
+
+class _Plan:
+    """One C-side plan (workspace + saved activations) for a given batch shape."""
+
+    def __init__(self, n, in_ch, n_cls, h, w, precision):
+        self.handle = ctypes.c_void_p()
+        L.check(L.lib().hpfg_unet_plan_create(n, in_ch, n_cls, h, w, precision, ctypes.byref(self.handle)),
+                "hpfg_unet_plan_create")
+        self.busy = False           # holds activations of a forward whose backward has not run yet
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.lib().hpfg_unet_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class _UNetFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, module, *params):
+        plan = module._acquire_plan(x, need_grad=True)
+        logits = module._run_forward(plan, x, save=True)
+        plan.busy = True
+        ctx.module, ctx.plan = module, plan
+        return logits
+
+    @staticmethod
+    def backward(ctx, dlogits):
+        m, plan = ctx.module, ctx.plan
+        grads = torch.empty_like(m.flat_params)        # fresh buffer: param.grad views must not alias a reused one
+        L.check(L.lib().hpfg_unet_backward(plan.handle, L.ptr(m.flat_params), L.ptr(dlogits.contiguous().float()),
+                                           L.ptr(grads), 0, L.stream_ptr(grads.device)), "hpfg_unet_backward")
+        plan.busy = False
+        m.last_flat_grad = grads
+        views = tuple(grads[o:o + n].view(s) for o, n, s in m._layout)
+        return (None, None) + views
+
+
+class UNet(nn.Module):
+    """``UNet(in_channels=1, num_classes=4)`` -- same signature as model/unet.py:156."""
+
+    def __init__(self, in_channels=1, num_classes=4, precision="bf16"):
+        super().__init__()
+        self.in_channels, self.num_classes = in_channels, num_classes
+        self.precision = precision
+        f = FT_CHNS
+        enc = nn.Module()
+        enc.in_conv = _conv_block(in_channels, f[0], ENC_DROPOUT[0])
+        for i in range(1, 5):
+            down = nn.Module()
+            down.maxpool_conv = nn.Sequential(nn.MaxPool2d(2), _conv_block(f[i - 1], f[i], ENC_DROPOUT[i]))
+            setattr(enc, "down%d" % i, down)
+        dec = nn.Module()
+        for i in range(1, 5):
+            up = nn.Module()
+            up.conv1x1 = nn.Conv2d(f[5 - i], f[4 - i], kernel_size=1)
+            up.up = nn.Upsample(scale_factor=2, mode="bilinear", align_corners=True)
+            up.conv = _conv_block(2 * f[4 - i], f[4 - i], 0.0)
+            setattr(dec, "up%d" % i, up)
+        dec.out_conv = nn.Conv2d(f[0], num_classes, kernel_size=3, padding=1)
+        self.encoder, self.decoder = enc, dec
+        self._plans = {}
+        self._dropout_masks = None
+        self._no_dropout = False
+        self._philox_offset = 0
+        self.last_flat_grad = None
+        self._flatten()
+
+    # ------------------------------------------------------------------ flat storage
+    def _bn_modules(self):
+        return [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
+
+    def _flatten(self):
+        params = list(self.parameters())
+        assert len(params) == L.NUM_PARAMS
+        dev = params[0].device
+        with torch.no_grad():
+            flat = torch.cat([p.detach().reshape(-1).float() for p in params]).contiguous()
+            layout, off = [], 0
+            for p in params:
+                n = p.numel()
+                p.data = flat[off:off + n].view(p.shape)
+                layout.append((off, n, tuple(p.shape)))
+                off += n
+            bns = self._bn_modules()
+            assert len(bns) == L.NUM_BN
+            run = torch.cat([torch.cat([b.running_mean.reshape(-1), b.running_var.reshape(-1)]) for b in bns]).float()
+            run = run.contiguous().to(dev)
+            cnt = torch.stack([b.num_batches_tracked.reshape(()) for b in bns]).to(torch.int64).contiguous().to(dev)
+            o = 0
+            for i, b in enumerate(bns):
+                c = b.num_features
+                b.running_mean = run[o:o + c]
+                b.running_var = run[o + c:o + 2 * c]
+                b.num_batches_tracked = cnt[i]
+                o += 2 * c
+        self.__dict__["flat_params"] = flat
+        self.__dict__["bn_running"] = run
+        self.__dict__["bn_counters"] = cnt
+        self.__dict__["_layout"] = layout
+
+    def _is_flat(self):
+        flat = self.__dict__.get("flat_params")
+        if flat is None:
+            return False
+        base = flat.data_ptr()
+        for p, (o, n, _) in zip(self.parameters(), self._layout):
+            if p.data_ptr() != base + 4 * o or p.dtype != torch.float32:
+                return False
+        bns = self._bn_modules()
+        o, rbase = 0, self.bn_running.data_ptr()
+        for i, b in enumerate(bns):
+            c = b.num_features
+            if b.running_mean.data_ptr() != rbase + 4 * o or b.running_var.data_ptr() != rbase + 4 * (o + c):
+                return False
+            if b.num_batches_tracked.data_ptr() != self.bn_counters.data_ptr() + 8 * i:
+                return False
+            o += 2 * c
+        return True
+
+    def ensure_flat(self):
+        if not self._is_flat():
+            self._flatten()
+        return self.flat_params
+
+    def _apply(self, fn, recurse=True):
+        out = super()._apply(fn, recurse)
+        self._plans = {}
+        self._flatten()
+        return out
+
+    def load_state_dict(self, *a, **k):
+        out = super().load_state_dict(*a, **k)
+        self.ensure_flat()
+        return out
+
+    def __deepcopy__(self, memo):
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self.__dict__.items():
+            new.__dict__[k] = {} if k == "_plans" else (None if k == "last_flat_grad" else copy.deepcopy(v, memo))
+        new.ensure_flat()
+        return new
+
+    # ------------------------------------------------------------------ test / parity hooks
+    def set_dropout_masks(self, masks):
+        """masks: None (library Philox stream) or {encoder block prefix: bool/uint8 keep-mask [N,C,H,W]} for all
+        five encoder ConvBlocks -- the parity harness feeds the oracle's masks through this."""
+        if masks is None:
+            self._dropout_masks = None
+            return
+        dev = self.flat_params.device
+        self._dropout_masks = [masks[p].to(device=dev, dtype=torch.uint8).contiguous() for p in ENC_PREFIXES]
+
+    def set_dropout_enabled(self, enabled=True):
+        self._no_dropout = not enabled
+
+    def debug_tap(self, name, x_shape):
+        plan = self._plans[(tuple(x_shape), self.precision)][-1]
+        n, _, h, w = x_shape
+        out = torch.empty(n * 256 * h * w, device=self.flat_params.device, dtype=torch.float32)
+        L.check(L.lib().hpfg_unet_debug_tap(plan.handle, name.encode(), L.ptr(out), out.numel(),
+                                            L.stream_ptr(out.device)), "hpfg_unet_debug_tap")
+        return out
+
+    # ------------------------------------------------------------------ forward
+    def _acquire_plan(self, x, need_grad):
+        key = (tuple(x.shape), self.precision)
+        pool = self._plans.setdefault(key, [])
+        for pl in pool:
+            if not pl.busy:
+                return pl
+        n, c, h, w = x.shape
+        prec = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}[self.precision]
+        pl = _Plan(n, c, self.num_classes, h, w, prec)
+        pool.append(pl)
+        return pl
+
+    def _run_forward(self, plan, x, save):
+        dev = x.device
+        logits = torch.empty((x.shape[0], self.num_classes, x.shape[2], x.shape[3]), device=dev, dtype=torch.float32)
+        masks = None
+        if self._dropout_masks is not None:
+            masks = (ctypes.c_void_p * L.NUM_DROPOUT)(*[m.data_ptr() for m in self._dropout_masks])
+        seed = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].initial_seed()
+        offset = self._philox_offset
+        if self.training:
+            self._philox_offset += 8
+        L.check(L.lib().hpfg_unet_forward(plan.handle, L.ptr(self.flat_params), L.ptr(self.bn_running),
+                                          L.ptr(self.bn_counters), L.ptr(x), L.ptr(logits), int(self.training),
+                                          int(self._no_dropout), int(save), seed & (2 ** 64 - 1), offset, masks,
+                                          L.stream_ptr(dev)), "hpfg_unet_forward")
+        return logits
+
+    def forward(self, x):
+        L.require_cuda(x, "UNet input")
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise ValueError("expected input [N,%d,H,W], got %s" % (self.in_channels, tuple(x.shape)))
+        self.ensure_flat()
+        if self.flat_params.device != x.device:
+            raise L.HpfgError("model is on %s but the input is on %s" % (self.flat_params.device, x.device))
+        x = x.contiguous().float()
+        need_grad = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
+        if need_grad:
+            return _UNetFunction.apply(x, self, *self.parameters())
+        return self._run_forward(self._acquire_plan(x, False), x, save=False)

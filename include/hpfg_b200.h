@@ -1,0 +1,134 @@
+/*
+ * hpfg_b200 -- C ABI of the B200-native (sm_100a) semi-supervised U-Net training hot path.
+ *
+ * This is the drop-in boundary for the path the reference reaches through PyTorch:
+ *   model/builder.py:29-30 build_model -> model/unet.py:155-175 UNet.forward   (hpfg_unet_forward)
+ *   loss.backward() through that module (2017_03_NIPS_Mean-Teacher_ACDC.py:108)  (hpfg_unet_backward)
+ *   utils/loss/medloss.py:44-56 Med_Sup_Loss, utils/loss/diceloss.py:155-191 DiceLoss,
+ *   the inline consistency / pseudo-label terms of the MT / CPS / UAMT trainers    (hpfg_ssl_loss_*)
+ *   utils/utils.py:82-86 update_ema_variables                                      (hpfg_ema_update)
+ *   torch.optim.SGD as built by utils/__init__.py:14-16                            (hpfg_sgd_momentum*)
+ *
+ * Conventions: plain pointers and sizes only.  Every pointer is a DEVICE pointer unless its name ends in
+ * _host.  All work is enqueued on the caller's stream (passed as void* == cudaStream_t); no call
+ * synchronises the host except plan create/destroy.  Return value: 0 = ok, non-zero = error code; the
+ * message is available from hpfg_last_error() (thread-local).  The caller owns every buffer it passes; a
+ * plan owns only its internal workspace.  A plan is re-entrant per handle but not thread-safe per handle.
+ * There is NO CPU fallback: on a machine without an sm_100 device every compute entry point fails.
+ */
+#ifndef HPFG_B200_H
+#define HPFG_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define HPFG_OK 0
+#define HPFG_ERR_INVALID 1     /* bad argument                                   */
+#define HPFG_ERR_CUDA 2        /* a CUDA runtime / driver call failed            */
+#define HPFG_ERR_UNSUPPORTED 3 /* shape / device not supported by this build     */
+
+#define HPFG_PREC_FP32 0 /* fp32 NHWC activations, CUDA-core FMA convs: the 1e-5 check path            */
+#define HPFG_PREC_BF16 1 /* bf16 NHWC activations, tcgen05/TMEM implicit-GEMM convs, fp32 accumulation */
+
+#define HPFG_LOSS_SUP 0  /* Med_Sup_Loss on the labeled slices only                                   */
+#define HPFG_LOSS_MT 1   /* + w * mean((softmax(s_u)-softmax(t_u))^2)        (Mean-Teacher)           */
+#define HPFG_LOSS_CPS 2  /* two nets, cross pseudo supervision                (CPS)                    */
+#define HPFG_LOSS_UAMT 3 /* + w * uncertainty-masked softmax-MSE              (UAMT)                   */
+
+#define HPFG_NUM_BN 18
+#define HPFG_NUM_DROPOUT 5
+
+typedef struct hpfg_unet_plan *hpfg_unet_plan_t;
+
+const char *hpfg_last_error(void);
+int hpfg_version(void);
+/* Number of CUDA kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t hpfg_launch_count(void);
+
+/* ---- model layout (mirrors model/unet.py state_dict order) -------------------------------------------
+ * Flat parameter buffer: the 82 tensors of UNet.named_parameters() in registration order, each in its
+ * native PyTorch layout (conv weight OIHW), fp32, back to back.  offsets/sizes: int64[82] in elements.
+ * bn_running: fp32 [running_mean(C) | running_var(C)] for each of the 18 BatchNorms in registration order;
+ * bn_offsets: int64[18] element offset of each BN's running_mean (running_var follows at +C). */
+int hpfg_unet_param_layout(int in_channels, int num_classes, int64_t *offsets_host, int64_t *sizes_host,
+                           int64_t *total_host);
+int hpfg_unet_bn_layout(int in_channels, int num_classes, int64_t *bn_offsets_host, int64_t *bn_channels_host,
+                        int64_t *total_host);
+
+/* ---- plan ------------------------------------------------------------------------------------------- */
+int hpfg_unet_plan_create(int batch, int in_channels, int num_classes, int height, int width, int precision,
+                          hpfg_unet_plan_t *plan_out);
+int hpfg_unet_plan_destroy(hpfg_unet_plan_t plan);
+int64_t hpfg_unet_plan_workspace_bytes(hpfg_unet_plan_t plan);
+
+/* UNet.forward.  x: fp32 NCHW [batch,in_channels,H,W]; logits: fp32 NCHW [batch,num_classes,H,W].
+ * training != 0: BatchNorm uses batch statistics and updates bn_running / bn_counters (+1 each), dropout is
+ * active in the five encoder ConvBlocks (p = .05,.1,.2,.3,.5).  Dropout keep-masks come from
+ * dropout_masks_host (host array of HPFG_NUM_DROPOUT device pointers to uint8 NCHW keep-masks; a NULL entry
+ * or NULL array means "draw with the library's Philox stream keyed by dropout_seed/dropout_offset"; pass
+ * no_dropout != 0 to disable dropout entirely while keeping batch-statistics BN).
+ * save_for_backward != 0 keeps the activations hpfg_unet_backward needs inside the plan. */
+int hpfg_unet_forward(hpfg_unet_plan_t plan, const float *params, float *bn_running, int64_t *bn_counters,
+                      const float *x, float *logits, int training, int no_dropout, int save_for_backward,
+                      uint64_t dropout_seed, uint64_t dropout_offset, const uint8_t *const *dropout_masks_host,
+                      void *stream);
+
+/* Backward of the last save_for_backward forward on this plan.  dlogits: fp32 NCHW.  grads: flat fp32
+ * buffer with the parameter layout; overwritten (accumulate == 0) or added to (accumulate != 0). */
+int hpfg_unet_backward(hpfg_unet_plan_t plan, const float *params, const float *dlogits, float *grads,
+                       int accumulate, void *stream);
+
+/* Data-parallel hook: gradients complete back-to-front.  The flat gradient buffer is cut into
+ * hpfg_unet_num_buckets() contiguous ranges (bucket 0 = the tail: out_conv, up4, ...).  After
+ * hpfg_unet_backward has been enqueued, hpfg_unet_bucket_wait makes comm_stream wait until bucket i is
+ * final, so an NCCL all-reduce of that range can be enqueued on comm_stream and overlap the rest of backward. */
+int hpfg_unet_num_buckets(hpfg_unet_plan_t plan);
+int hpfg_unet_bucket_range(hpfg_unet_plan_t plan, int bucket, int64_t *offset_host, int64_t *count_host);
+int hpfg_unet_bucket_wait(hpfg_unet_plan_t plan, int bucket, void *comm_stream);
+
+/* Debug / parity taps: copy an internal activation of the last forward as fp32 NCHW.  name is one of the
+ * conv names ("encoder.in_conv.conv_conv.0", ..., raw conv outputs incl. bias) . */
+int hpfg_unet_debug_tap(hpfg_unet_plan_t plan, const char *name, float *out_nchw, int64_t capacity, void *stream);
+
+/* ---- fused SSL loss (forward value + d loss / d logits) ---------------------------------------------
+ * student: fp32 NCHW [n_l+n_u, C, H, W] logits.  labels: int64 [n_l, H, W] (255 = ignored by CE only).
+ * other: MT/UAMT -> teacher logits for the UNLABELED slices [n_u, C, H, W];
+ *        CPS     -> the peer network's logits [n_l+n_u, C, H, W];  SUP -> NULL.
+ * mc_logits (UAMT only): [T*n_u, C, H, W] logits of the T stochastic teacher passes (pass-major).
+ * dstudent / dother: gradients (dother only for CPS, else NULL).  class_weights: C floats or NULL (=1).
+ * scalars_out: float[8] device: {loss, loss_sup, loss_cons_or_semi, ce, dice, n_valid, mask_sum, 0}.
+ * pseudo1/pseudo2 (CPS, optional): int64 [n_u,H,W] argmax pseudo-labels of net1 / net2.
+ * workspace: at least hpfg_ssl_loss_workspace_bytes(...) bytes of device scratch. */
+int64_t hpfg_ssl_loss_workspace_bytes(int mode, int n_l, int n_u, int num_classes, int height, int width);
+int hpfg_ssl_loss(int mode, const float *student, const float *other, const float *mc_logits, int mc_passes,
+                  const int64_t *labels, int n_l, int n_u, int num_classes, int height, int width,
+                  float cons_weight, float uamt_threshold, const float *class_weights, float ce_coef,
+                  float dice_coef, float *dstudent, float *dother, float *scalars_out, int64_t *pseudo1,
+                  int64_t *pseudo2, void *workspace, void *stream);
+
+/* DiceLoss.forward (utils/loss/diceloss.py:178-191) alone: inputs are probabilities (softmax == 0) or
+ * logits (softmax != 0); target int64 [n,H,W]; dinputs optional. scalars_out: float[1+C] = {loss, dice_c..}. */
+int hpfg_dice_loss(const float *inputs, const int64_t *target, int n, int num_classes, int height, int width,
+                   int softmax, const float *class_weights, float *dinputs, float *scalars_out, void *workspace,
+                   void *stream);
+
+/* ---- optimiser-side passes over the flat buffers --------------------------------------------------- */
+/* update_ema_variables (utils/utils.py:82-86): ema <- alpha*ema + (1-alpha)*param, alpha already clamped. */
+int hpfg_ema_update(float *ema, const float *param, int64_t n, float alpha, void *stream);
+/* torch.optim.SGD step (momentum, weight decay, no nesterov/dampening): first_step != 0 initialises the
+ * momentum buffer with the decayed gradient.  grad_scale multiplies the gradient first (1/world for DP). */
+int hpfg_sgd_momentum(float *param, const float *grad, float *momentum_buf, int64_t n, float lr, float momentum,
+                      float weight_decay, float grad_scale, int first_step, void *stream);
+/* SGD step and EMA teacher update in one pass (the two calls above, fused). */
+int hpfg_sgd_momentum_ema(float *param, const float *grad, float *momentum_buf, float *ema, int64_t n, float lr,
+                          float momentum, float weight_decay, float grad_scale, int first_step, float ema_alpha,
+                          void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* HPFG_B200_H */

@@ -1,0 +1,85 @@
+"""CPU: the C-ABI library loads and exports every declared symbol, layout queries agree with the oracle's
+parameter spec, the nn.Module mirrors the reference's state_dict, and the no-fallback rule holds."""
+import copy
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+import oracle
+import hpfg_b200 as hb
+from hpfg_b200 import _lib as L
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "hpfg_b200.h")).read()
+    declared = set(re.findall(r"\b(hpfg_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(L.SIGNATURES), declared ^ set(L.SIGNATURES)
+    lib = L.lib()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.hpfg_version() >= 100
+
+
+@pytest.mark.parametrize("in_ch,n_cls", [(1, 4), (3, 2)])
+def test_layout_queries_match_oracle_spec(in_ch, n_cls):
+    lib = L.lib()
+    offs, sizes, tot = (ctypes.c_int64 * 82)(), (ctypes.c_int64 * 82)(), ctypes.c_int64()
+    L.check(lib.hpfg_unet_param_layout(in_ch, n_cls, offs, sizes, ctypes.byref(tot)))
+    spec = oracle.unet_param_spec(in_ch, n_cls)
+    exp_sizes = [int(torch.Size(s).numel()) for _, s in spec]
+    assert list(sizes) == exp_sizes and tot.value == sum(exp_sizes)
+    assert list(offs) == [sum(exp_sizes[:i]) for i in range(82)]
+    boffs, bch, btot = (ctypes.c_int64 * 18)(), (ctypes.c_int64 * 18)(), ctypes.c_int64()
+    L.check(lib.hpfg_unet_bn_layout(in_ch, n_cls, boffs, bch, ctypes.byref(btot)))
+    chans = [s[0] for n, s, _ in oracle.unet_buffer_spec(in_ch, n_cls) if n.endswith("running_mean")]
+    assert list(bch) == chans and btot.value == 2 * sum(chans)
+
+
+def test_module_mirrors_reference_state_dict_and_survives_copies():
+    torch.manual_seed(3)
+    m = hb.build_model(type("A", (), dict(model="unet", in_channels=3, num_classes=2))())
+    assert isinstance(m, hb.UNet) and isinstance(m, torch.nn.Module)
+    assert [(n, tuple(p.shape)) for n, p in m.named_parameters()] == oracle.unet_param_spec(3, 2)
+    bufs = [n for n, _ in m.named_buffers()]
+    assert bufs == [n for n, _, _ in oracle.unet_buffer_spec(3, 2)]
+    assert len(m.state_dict()) == 136
+    assert m._is_flat()
+    m2 = copy.deepcopy(m)
+    assert m2._is_flat() and m2.flat_params.data_ptr() != m.flat_params.data_ptr()
+    assert torch.equal(m2.flat_params, m.flat_params)
+    for _, p in m2.named_parameters():
+        p.requires_grad = False                      # what the MT trainer does to the teacher (:56-57)
+    m.load_state_dict(copy.deepcopy(m.state_dict()))
+    assert m._is_flat()
+    opt = torch.optim.SGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    assert len(opt.param_groups[0]["params"]) == 82
+    with pytest.raises(NotImplementedError):
+        hb.build_model(type("A", (), dict(model="swinunet", in_channels=1, num_classes=4))())
+
+
+def test_no_cpu_fallback():
+    m = hb.UNet(1, 4)
+    with pytest.raises(L.HpfgError):
+        m(torch.zeros(1, 1, 32, 32))
+    with pytest.raises(L.HpfgError):
+        hb.Med_Sup_Loss(4)(torch.zeros(1, 4, 16, 16, requires_grad=True), torch.zeros(1, 16, 16, dtype=torch.long))
+    with pytest.raises(L.HpfgError):
+        hb.update_ema_variables(m, copy.deepcopy(m), 0.99, 1)
+    with pytest.raises(AssertionError):
+        hb.DiceLoss(4)(torch.zeros(1, 4, 16, 16), torch.zeros(1, 1, 8, 8))
+    # argument validation happens before any device work
+    assert L.lib().hpfg_ema_update(None, None, 4, 0.5, None) == 1
+    assert b"null" in L.lib().hpfg_last_error()
+
+
+def test_host_schedules_match_oracle():
+    for it in (1, 2, 3, 149, 150, 4000, 30000):
+        assert hb.medical_lr(it, 0.01, 30000) == pytest.approx(oracle.medical_lr(it - 1), rel=1e-14)
+    a = type("A", (), dict(consistency=0.1, consistency_rampup=200.0))()
+    for it in (1, 150, 1500, 40000):
+        assert hb.get_current_consistency_weight(it // 150, a) == pytest.approx(oracle.consistency_weight(it), rel=1e-14)

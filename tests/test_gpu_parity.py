@@ -1,0 +1,309 @@
+"""GPU parity tests (B200): the CUDA path, called through the nn.Module / loss classes / C ABI, against
+(a) the golden vectors produced by the REAL reference and (b) the CPU oracle on seeded inputs.
+
+Tolerances (north_star): fp32 check path 1e-5 relative on activations (we allow 1e-4 rel-L2 on gradients, whose
+reductions over ~1e5 pixels are ordered differently), bf16 path 1e-2 per layer; loss 1e-3 relative; argmax
+pseudo-labels identical on the fp32 path."""
+import copy
+import math
+
+import pytest
+import torch
+
+import oracle
+import hpfg_b200 as hb
+from hpfg_b200 import _lib as L
+from tests.golden.common import make_state, make_masks, make_batch
+from tests.helpers import load_golden, check_summary, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(st, in_ch, n_cls, precision):
+    m = hb.UNet(in_ch, n_cls, precision=precision)
+    m.load_state_dict(st)
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["acdc_masks", "acdc_nodrop", "isic_masks"])
+def test_unet_forward_backward_vs_reference_golden(tag, precision):
+    g = load_golden("unet_%s.pt" % tag)
+    c = g["cfg"]
+    st = make_state(c["in_ch"], c["n_cls"], c["seed"])
+    x, _, y = make_batch(c["n"], 0, c["in_ch"], c["n_cls"], c["h"], c["w"], c["seed"] + 7)
+    m = _model(st, c["in_ch"], c["n_cls"], precision)
+    if c["use_masks"]:
+        m.set_dropout_masks(make_masks(c["n"], c["h"], c["w"], c["seed"] + 11))
+    else:
+        m.set_dropout_enabled(False)
+    m.train()
+    logits = m(x.to(DEV))
+    loss = hb.Med_Sup_Loss(c["n_cls"])(logits, y.to(DEV))
+    loss.backward()
+    tol_act, tol_grad, tol_loss = (1e-5, 1e-4, 1e-5) if precision == "fp32" else (2e-2, 6e-2, 1e-3)
+    assert rel_l2(logits, g["logits"]) < tol_act
+    assert abs(loss.item() - g["loss"]) / abs(g["loss"]) < tol_loss
+    worst = 0.0
+    for n, p in m.named_parameters():
+        s = g["grads"][n]
+        # conv biases ahead of train-mode BN have analytically zero gradient: compare on an absolute scale
+        atol = 1e-5 if (n.endswith(".bias") and s["abs_sum"] < 1e-4) else 0.0
+        if atol:
+            assert p.grad.abs().max().item() < 1e-4, n
+            continue
+        check_summary(p.grad, s, rtol=tol_grad, atol=1e-7, what=n)
+    for k, v in g["buffers"].items():
+        got = m.state_dict()[k].cpu()
+        if "tracked" in k:
+            assert int(got) == int(v), k
+        else:
+            assert torch.allclose(got, v, rtol=1e-4 if precision == "fp32" else 3e-2, atol=1e-5 if precision == "fp32" else 3e-3), k
+    m.eval()
+    with torch.no_grad():
+        le = m(x.to(DEV))
+    assert rel_l2(le, g["logits_eval"]) < (1e-5 if precision == "fp32" else 3e-2)
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-5), ("bf16", 1e-2)])
+def test_per_layer_activations_vs_oracle(precision, tol):
+    """Layer-isolated check: every raw conv output against the oracle's, at a ragged (non tile-multiple) size."""
+    in_ch, n_cls, n, h, w = 1, 4, 2, 48, 80
+    st = make_state(in_ch, n_cls, 21)
+    x, _, _ = make_batch(n, 0, in_ch, n_cls, h, w, 22)
+    masks = make_masks(n, h, w, 23)
+    m = _model(st, in_ch, n_cls, precision)
+    m.set_dropout_masks(masks)
+    m.train()
+    with torch.no_grad():
+        logits = m(x.to(DEV))
+    ost = {k: v.clone() for k, v in st.items()}
+    ref_logits, taps = oracle.unet_forward(ost, x, True, masks, return_taps=True)
+    names = [k for k in taps if k.endswith(".conv_conv.0") or k.endswith(".conv_conv.4") or k.endswith(".conv1x1")
+             or k.endswith(".cat")]
+    assert len(names) == 18 + 4 + 4
+    worst = {}
+    for k in names:
+        t = taps[k]
+        got = m.debug_tap(k, x.shape)[:t.numel()].view(t.shape).cpu()
+        if k.endswith(".conv_conv.0") or k.endswith(".conv_conv.4"):
+            got = got + ost[k + ".bias"].view(1, -1, 1, 1)          # the stored tensor is bias-free
+        worst[k] = rel_l2(got, t)
+    if precision == "fp32":
+        bad = {k: v for k, v in worst.items() if v > tol}
+        assert not bad, bad
+        assert rel_l2(logits, ref_logits) < tol
+    else:
+        # bf16: compounded error grows with depth; bound the end-to-end drift instead
+        assert max(worst.values()) < 8e-2, worst
+        assert rel_l2(logits, ref_logits) < 5e-2
+
+
+@pytest.mark.parametrize("tag", ["c4", "c2"])
+def test_fused_losses_vs_reference_golden(tag):
+    g = load_golden("losses.pt")[tag]
+    n_l, n_u, C, H, W = g["shape"]
+    s = g["student"].to(DEV).requires_grad_(True)
+    t, y, y255 = g["teacher"].to(DEV), g["y"].to(DEV), g["y255"].to(DEV)
+    for nm, yy in (("sup", y), ("sup255", y255)):
+        l = hb.Med_Sup_Loss(C)(s[:n_l], yy)
+        (gr,) = torch.autograd.grad(l, s)
+        assert abs(l.item() - g[nm]) / abs(g[nm]) < 1e-5
+        assert rel_l2(gr, g[nm + "_grad"]) < 1e-5
+    l = hb.DiceLoss(C)(s[:n_l], y.unsqueeze(1), weight=g["dice_weights"], softmax=True)
+    (gr,) = torch.autograd.grad(l, s)
+    assert abs(l.item() - g["dice_w"]) / abs(g["dice_w"]) < 1e-5 and rel_l2(gr, g["dice_w_grad"]) < 1e-5
+    probs = torch.softmax(s, 1)[:n_l]
+    l = hb.DiceLoss(C)(probs, y.unsqueeze(1))
+    assert abs(l.item() - g["dice"]) / abs(g["dice"]) < 1e-5
+    (gr,) = torch.autograd.grad(l, s)                                  # grad through torch's softmax
+    lo = oracle.dice_loss(torch.softmax(g["student"].clone().requires_grad_(True), 1)[:n_l], g["y"].unsqueeze(1), C)
+    mt = g["mt"]
+    l = hb.mean_teacher_loss(s, t[n_l:], y, mt["w"])
+    (gr,) = torch.autograd.grad(l, s)
+    assert abs(l.item() - mt["loss"]) / abs(mt["loss"]) < 1e-5 and rel_l2(gr, mt["grad"]) < 1e-5
+    cps = g["cps"]
+    s2 = cps["logits2"].to(DEV).requires_grad_(True)
+    r = hb.ssl_loss_raw(L.LOSS_CPS, s.detach(), s2.detach(), y, n_l, cons_weight=cps["w"], want_pseudo=True)
+    assert torch.equal(r["pseudo1"].cpu(), cps["pl1"]) and torch.equal(r["pseudo2"].cpu(), cps["pl2"])
+    l = hb.cps_loss(s, s2, y, cps["w"])
+    g1, g2 = torch.autograd.grad(l, [s, s2])
+    assert abs(l.item() - cps["loss"]) / abs(cps["loss"]) < 1e-5
+    assert rel_l2(g1, cps["grad1"]) < 1e-5 and rel_l2(g2, cps["grad2"]) < 1e-5
+    u = g["uamt"]
+    l = hb.uamt_loss(s, t[n_l:], u["mc_logits"].to(DEV), y, u["w"], u["threshold"], T=u["T"])
+    (gr,) = torch.autograd.grad(l, s)
+    assert abs(l.item() - u["loss"]) / abs(u["loss"]) < 1e-5 and rel_l2(gr, u["grad"]) < 1e-5
+
+
+def test_loss_full_size_properties():
+    """At the benchmark shape (12+12, 4x224x224): against the oracle on the same seeded logits, plus the
+    size-independent property that the MT gradient of every pixel sums to zero over classes."""
+    g = torch.Generator().manual_seed(5)
+    s = 2 * torch.randn(24, 4, 224, 224, generator=g)
+    t = 2 * torch.randn(12, 4, 224, 224, generator=g)
+    y = torch.randint(0, 4, (12, 224, 224), generator=g)
+    sr = s.clone().requires_grad_(True)
+    lo = oracle.med_sup_loss(sr[:12], y, 4) + 0.05 * oracle.mt_consistency(sr[12:], t)
+    (go,) = torch.autograd.grad(lo, sr)
+    r = hb.ssl_loss_raw(L.LOSS_MT, s.to(DEV), t.to(DEV), y.to(DEV), 12, cons_weight=0.05)
+    assert abs(r["scalars"][0].item() - lo.item()) / lo.item() < 1e-5
+    assert rel_l2(r["dstudent"], go) < 1e-5
+    assert r["dstudent"].sum(dim=1).abs().max().item() < 1e-9
+
+
+def test_ema_and_sgd_flat_kernels():
+    g = load_golden("schedules.pt")
+    a, b = torch.nn.Linear(7, 5).to(DEV), torch.nn.Linear(7, 5).to(DEV)
+    for step, outs in g["ema_out"].items():
+        with torch.no_grad():
+            for q, v in zip(a.parameters(), g["ema_in"]["student"]):
+                q.copy_(v)
+            for q, v in zip(b.parameters(), g["ema_in"]["teacher"]):
+                q.copy_(v)
+        # nn.Linear's 5-float bias is not 16-byte sized but is 16-byte aligned (own allocation)
+        hb.update_ema_variables(a, b, 0.99, step)
+        for q, o in zip(b.parameters(), outs):
+            assert torch.allclose(q.cpu(), o, rtol=0, atol=1e-7)
+    # flat SGD(+EMA) against torch.optim.SGD + the reference EMA formula, odd length to exercise the tail
+    n = 100003
+    gen = torch.Generator().manual_seed(1)
+    p0, e0 = torch.randn(n, generator=gen), torch.randn(n, generator=gen)
+    pt = torch.nn.Parameter(p0.clone())
+    opt = torch.optim.SGD([pt], lr=0.01, momentum=0.9, weight_decay=1e-4)
+    p, e, buf = p0.clone().to(DEV), e0.clone().to(DEV), torch.zeros(n, device=DEV)
+    et = e0.clone()
+    lib = L.lib()
+    for it in range(1, 4):
+        gr = torch.randn(n, generator=gen)
+        pt.grad = gr.clone()
+        opt.step()
+        alpha = min(1 - 1 / (it + 1), 0.99)
+        et.mul_(alpha).add_(pt.data, alpha=1 - alpha)
+        L.check(lib.hpfg_sgd_momentum_ema(L.ptr(p), L.ptr(gr.to(DEV)), L.ptr(buf), L.ptr(e), n, 0.01, 0.9, 1e-4, 1.0,
+                                          int(it == 1), alpha, L.stream_ptr(torch.device(DEV))))
+        assert torch.allclose(p.cpu(), pt.data, rtol=0, atol=2e-7)
+        assert torch.allclose(e.cpu(), et, rtol=0, atol=2e-7)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("tag", ["acdc", "isic"])
+def test_mean_teacher_steps_vs_reference_golden(tag, precision):
+    g = load_golden("mt_steps_%s.pt" % tag)
+    c = g["cfg"]
+    st = make_state(c["in_ch"], c["n_cls"], c["seed"])
+    student = _model(st, c["in_ch"], c["n_cls"], precision)
+    teacher = copy.deepcopy(student)
+    step = hb.MeanTeacherStep(student, teacher)
+    n = c["n_l"] + c["n_u"]
+    f32 = precision == "fp32"
+    for it, rec in enumerate(g["steps"], start=1):
+        x_l, x_u, y = make_batch(c["n_l"], c["n_u"], c["in_ch"], c["n_cls"], c["h"], c["w"], c["seed"] + 100 * it)
+        student.set_dropout_masks(make_masks(n, c["h"], c["w"], c["seed"] + 100 * it + 1))
+        teacher.set_dropout_masks(make_masks(n, c["h"], c["w"], c["seed"] + 100 * it + 2))
+        loss = step.step(torch.cat([x_l, x_u]).to(DEV), y.to(DEV))
+        assert abs(loss.item() - rec["loss"]) / rec["loss"] < (1e-5 if f32 else 1e-3)
+        assert step.last["lr"] == pytest.approx(rec["lr"], rel=1e-12) and step.last["w"] == pytest.approx(rec["w"], rel=1e-12)
+        check_summary(step.last["logits"], rec["logits"], rtol=1e-5 if f32 else 3e-2, what="logits")
+        check_summary(step.last["teacher_logits"], rec["teacher_logits"], rtol=1e-5 if f32 else 3e-2, what="teacher")
+        sd, td = student.state_dict(), teacher.state_dict()
+        atol = 2e-6 if f32 else 2e-4
+        assert torch.allclose(sd["decoder.out_conv.weight"].cpu(), rec["student_out_conv"], atol=atol)
+        assert torch.allclose(td["decoder.out_conv.weight"].cpu(), rec["teacher_out_conv"], atol=atol)
+        assert torch.allclose(sd["encoder.in_conv.conv_conv.0.weight"].cpu(), rec["student_in_conv"], atol=atol)
+        assert torch.allclose(td["encoder.in_conv.conv_conv.1.running_mean"].cpu(), rec["teacher_rm"], atol=1e-5 if f32 else 2e-3)
+        assert math.isclose(student.flat_params.double().sum().item(), rec["student_sum"], abs_tol=1e-3 if f32 else 5e-2)
+        assert math.isclose(teacher.flat_params.double().sum().item(), rec["teacher_sum"], abs_tol=1e-3 if f32 else 5e-2)
+
+
+def test_drop_in_trainer_loop_matches_reference_golden():
+    """The unmodified trainer idiom (2017_03...:54-57,64-70,89-113) on the drop-in objects: build_model, deepcopy,
+    torch.optim.SGD over model.parameters(), Med_Sup_Loss, inline torch consistency, update_ema_variables."""
+    g = load_golden("mt_steps_acdc.pt")
+    c = g["cfg"]
+    args = type("A", (), dict(model="unet", in_channels=c["in_ch"], num_classes=c["n_cls"], precision="fp32",
+                              consistency=0.1, consistency_rampup=200.0, ema_decay=0.99))()
+    model = hb.build_model(args)
+    model.load_state_dict(make_state(c["in_ch"], c["n_cls"], c["seed"]))
+    model = model.to(DEV)
+    ema_model = copy.deepcopy(model)
+    for name, p in ema_model.named_parameters():
+        p.requires_grad = False
+    optimizer = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+    med_loss = hb.Med_Sup_Loss(args.num_classes)
+    model.train()
+    ema_model.train()
+    n = c["n_l"] + c["n_u"]
+    for cur_itrs, rec in enumerate(g["steps"], start=1):
+        label_img, unlabel_img, target_label = make_batch(c["n_l"], c["n_u"], c["in_ch"], c["n_cls"], c["h"], c["w"],
+                                                          c["seed"] + 100 * cur_itrs)
+        model.set_dropout_masks(make_masks(n, c["h"], c["w"], c["seed"] + 100 * cur_itrs + 1))
+        ema_model.set_dropout_masks(make_masks(n, c["h"], c["w"], c["seed"] + 100 * cur_itrs + 2))
+        label_img, unlabel_img = label_img.to(DEV).float(), unlabel_img.to(DEV).float()
+        target_label = target_label.to(DEV).long()
+        label_bs = label_img.shape[0]
+        x = torch.cat([label_img, unlabel_img], dim=0)
+        output = model(x)
+        output_soft = torch.softmax(output, dim=1)
+        with torch.no_grad():
+            ema_output = ema_model(x)
+            ema_output_soft = torch.softmax(ema_output, dim=1)
+        loss_sup = med_loss(output[:label_bs], target_label)
+        loss_consistence = torch.mean((output_soft[label_bs:] - ema_output_soft[label_bs:]) ** 2)
+        consistency_weight = hb.get_current_consistency_weight(epoch=cur_itrs // 150, args=args)
+        loss = loss_sup + consistency_weight * loss_consistence
+        for gparam in optimizer.param_groups:
+            gparam["lr"] = rec["lr"]                      # Medical_LR value recorded from the reference run
+        optimizer.zero_grad()
+        loss.backward()
+        optimizer.step()
+        hb.update_ema_variables(model, ema_model, args.ema_decay, cur_itrs)
+        assert abs(loss.item() - rec["loss"]) / rec["loss"] < 1e-5
+        assert model._is_flat() and ema_model._is_flat()
+        assert torch.allclose(model.state_dict()["decoder.out_conv.weight"].cpu(), rec["student_out_conv"], atol=2e-6)
+        assert torch.allclose(ema_model.state_dict()["decoder.out_conv.weight"].cpu(), rec["teacher_out_conv"], atol=2e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cps_and_uamt_steps_vs_oracle(precision):
+    in_ch, n_cls, n_l, n_u, h, w = 1, 4, 2, 2, 32, 32
+    f32 = precision == "fp32"
+    # ---- CPS
+    st1, st2 = make_state(in_ch, n_cls, 31), make_state(in_ch, n_cls, 32)
+    m1, m2 = _model(st1, in_ch, n_cls, precision), _model(st2, in_ch, n_cls, precision)
+    o1, o2 = {k: v.clone() for k, v in st1.items()}, {k: v.clone() for k, v in st2.items()}
+    step = hb.CPSStep(m1, m2)
+    opt1, opt2 = oracle.SGDState(), oracle.SGDState()
+    for it in (1, 2):
+        x_l, x_u, y = make_batch(n_l, n_u, in_ch, n_cls, h, w, 40 + it)
+        k1, k2 = make_masks(n_l + n_u, h, w, 50 + it), make_masks(n_l + n_u, h, w, 60 + it)
+        m1.set_dropout_masks(k1)
+        m2.set_dropout_masks(k2)
+        loss = step.step(torch.cat([x_l, x_u]).to(DEV), y.to(DEV))
+        r = oracle.cps_step(o1, o2, opt1, opt2, x_l, x_u, y, it, masks1=k1, masks2=k2)
+        if f32:
+            assert abs(loss.item() - r["loss"]) / r["loss"] < 1e-4
+            assert rel_l2(step.last["logits1"], r["logits1"]) < 1e-5
+            assert torch.allclose(m2.state_dict()["decoder.out_conv.weight"].cpu(), o2["decoder.out_conv.weight"], atol=5e-6)
+        else:
+            assert abs(loss.item() - r["loss"]) / r["loss"] < 2e-2     # pseudo-label flips at near-ties move the CE term
+    # ---- UAMT
+    st = make_state(in_ch, n_cls, 33)
+    s, t = _model(st, in_ch, n_cls, precision), _model(st, in_ch, n_cls, precision)
+    os_, ot = {k: v.clone() for k, v in st.items()}, {k: v.clone() for k, v in st.items()}
+    ustep = hb.UAMTStep(s, t, total_itrs=30000)
+    opt = oracle.SGDState()
+    gen = torch.Generator().manual_seed(77)
+    for it in (1, 2):
+        x_l, x_u, y = make_batch(n_l, n_u, in_ch, n_cls, h, w, 70 + it)
+        noise = torch.clamp(torch.randn(x_u.shape, generator=gen) * 0.1, -0.2, 0.2)
+        mc_noise = torch.clamp(torch.randn((4, 2 * n_u) + tuple(x_u.shape[1:]), generator=gen) * 0.1, -0.2, 0.2)
+        s.set_dropout_enabled(False)
+        t.set_dropout_enabled(False)       # (T stochastic passes share one mask set otherwise; noise still varies)
+        loss = ustep.step(torch.cat([x_l, x_u]).to(DEV), y.to(DEV), noise.to(DEV), mc_noise.to(DEV))
+        r = oracle.uamt_step(os_, ot, opt, x_l, x_u, y, it, noise, mc_noise, student_masks={}, teacher_masks=[{}] * 5)
+        assert abs(loss.item() - r["loss"]) / r["loss"] < (1e-4 if f32 else 2e-2)
+        if f32:
+            assert rel_l2(ustep.last["mc_logits"], r["mc_logits"]) < 1e-5
+            assert ustep.last["scalars"][6].item() == r["mask"].sum().item()
