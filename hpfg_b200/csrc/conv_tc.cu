@@ -1,27 +1,573 @@
-// Tensor-core convolution path (placeholder until the tcgen05 kernels land: every layer falls through to the
-// CUDA-core kernels, so a bf16 plan already runs end to end with bf16 storage and fp32 accumulation).
+// Tensor-core implicit-GEMM convolution for the bf16 path (sm_100a): tcgen05.mma with TMEM accumulators,
+// TMA-staged NHWC bf16 halo tiles, warp-specialised persistent CTAs.
+//
+//   D[128 pixels, BN out-channels] = sum over taps (r,s) and input-channel steps of
+//        A_tap[128 pixels, 16 ch] (smem, K-major)  x  W_tap[BN, 16 ch] (smem, K-major)
+//
+// One CTA tile = 16 rows x 8 columns of output pixels of one image.  The (16+2)x(8+2) input halo of a channel
+// chunk is fetched ONCE by TMA (4-D box over [C,W,H,N], out-of-bounds = zero = the conv padding), re-laid out by
+// the transform warps into "channel-chunk major" order [chunk of 8 ch][halo pixel][8 ch] while the producer's
+// BatchNorm + LeakyReLU + dropout are applied (model/unet.py:17-25 fused into the consumer's loader), and the
+// nine taps are nine UMMA descriptors into that ONE staged tile: start address shifted by (r*10+s)*16 bytes,
+// SBO = one halo row.  Input bytes therefore cross L2->SMEM once per tile instead of nine times.
+// Epilogue (4 warps): tcgen05.ld -> per-channel sum / sum-of-squares partials for train-mode BatchNorm
+// (shuffle butterfly) -> bf16 NHWC store.  fprop, dgrad (flipped/transposed packed weights) and the 1x1
+// convolutions of the up-blocks all run through this kernel.
 #include "conv_tc.cuh"
+
+#include <algorithm>
+#include <map>
+#include <tuple>
+
+#include "tc_ptx.cuh"
 
 namespace hpfg {
 
-int tc_plan_init(hpfg_unet_plan *) { return HPFG_OK; }
-void tc_plan_free(hpfg_unet_plan *) {}
-int tc_pack_all(hpfg_unet_plan *, const float *, cudaStream_t) { return HPFG_OK; }
-int tc_fprop(hpfg_unet_plan *, int, const void *, void *, LoadXform, float *, int *, bool *done, cudaStream_t) {
-    *done = false;
+// ------------------------------------------------------------------------------------------ configuration
+constexpr int kTH = 16, kTW = 8;            // output tile (rows x cols) = 128 pixels = UMMA M
+constexpr int kTcThreads = 384;             // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 transform, 8-11 epilogue
+constexpr int kMaxStages = 6;
+constexpr int kSmemBudget = 200 * 1024;
+
+template <int KS, int KC, int BN>
+struct TcCfg {
+    static constexpr int PAD = KS / 2, KK = KS * KS;
+    static constexpr int HH = kTH + KS - 1, HW = kTW + KS - 1;     // halo tile
+    static constexpr int NPIX = HH * HW;
+    static constexpr int NCH = KC / 8;                             // 16-byte channel chunks per stage
+    static constexpr int RAW_BYTES = NPIX * KC * 2;                // TMA destination, [pixel][KC]
+    static constexpr int CH_STRIDE = (NPIX + 1) * 16;              // operand tile: [chunk][pixel][8ch], padded (bank spread)
+    static constexpr int OP_BYTES = NCH * CH_STRIDE;
+    static constexpr int B_TAP_BYTES = KC * BN * 2;                // [KC/8][BN][8]
+    static constexpr int B_BYTES = KK * B_TAP_BYTES;
+    static constexpr int al(int v) { return (v + 127) / 128 * 128; }
+    static constexpr int OFF_OP = al(RAW_BYTES), OFF_B = OFF_OP + al(OP_BYTES);
+    static constexpr int STAGE_BYTES = OFF_B + al(B_BYTES);
+    static constexpr int FIXED_BYTES = 1024 /*barriers*/ + 2 * 256 * 4 /*scale,shift*/ + 4 * 2 * BN * 4 /*stat partials*/;
+    static constexpr int STAGES_RAW = (kSmemBudget - FIXED_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > kMaxStages ? kMaxStages : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES + 1024 /*alignment slack*/;
+    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static_assert(STAGES >= 2, "need at least a double buffer");
+};
+
+struct TcConvParams {
+    const bf16 *bpk;          // packed weights: [n_block][k_chunk][tap][KC/8][BN][8]
+    bf16 *out;                // NHWC [N,H,W,Cout]
+    const float *bias;        // Cout floats or nullptr
+    const float *scale, *shift;   // per input channel (producer's fused BN affine) or nullptr = identity
+    const uint8_t *dropbits;  // producer's dropout keep bits, NHWC bit order, or nullptr
+    float inv_keep;
+    float *stats;             // [m_tiles][2*Cout] partial sums or nullptr
+    int N, H, W, Cin, Cout, tiles_h, tiles_w, m_tiles, n_blocks, k_chunks;
+};
+
+__device__ __forceinline__ void unpack8(const uint4 &v, float (&f)[8]) {
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+    }
+}
+__device__ __forceinline__ uint32_t pack2(float a, float b) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<const uint32_t *>(&h);
+}
+
+// Reduce 16 per-lane values over the 32 lanes of a warp with 16 shuffles (recursive halving); afterwards every
+// lane holds the full column sum of column col16(lane).
+__device__ __forceinline__ int col16(int lane) { return ((lane >> 4) & 1) * 8 + ((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1); }
+__device__ __forceinline__ float butterfly16(const float (&v)[16], int lane) {
+    float a[8], b[4], c[2], d;
+    const bool h16 = lane & 16, h8 = lane & 8, h4 = lane & 4, h2 = lane & 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const float send = h16 ? v[i] : v[i + 8], keep = h16 ? v[i + 8] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const float send = h8 ? a[i] : a[i + 4], keep = h8 ? a[i + 4] : a[i];
+        b[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+        const float send = h4 ? b[i] : b[i + 2], keep = h4 ? b[i + 2] : b[i];
+        c[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    }
+    {
+        const float send = h2 ? c[0] : c[1], keep = h2 ? c[1] : c[0];
+        d = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+    return d + __shfl_xor_sync(0xffffffffu, d, 1);
+}
+
+template <int KS, int KC, int BN>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const TcConvParams P) {
+    using C = TcCfg<KS, KC, BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *stage_base = smem;
+    uint8_t *fixed = smem + C::STAGES * C::STAGE_BYTES;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fixed);          // full[S] xf[S] empty[S] tfull[2] tempty[2]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fixed + 512);
+    float *s_scale = reinterpret_cast<float *>(fixed + 1024);
+    float *s_shift = s_scale + 256;
+    float *s_part = s_shift + 256;                                 // [4 warps][2*BN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = ptx::smem_u32(bars), bar_xf = bar_full + 8 * C::STAGES, bar_empty = bar_xf + 8 * C::STAGES;
+    const uint32_t bar_tfull = bar_empty + 8 * C::STAGES, bar_tempty = bar_tfull + 16;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            ptx::mbar_init(bar_full + 8 * s, 1);
+            ptx::mbar_init(bar_xf + 8 * s, 128);
+            ptx::mbar_init(bar_empty + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            ptx::mbar_init(bar_tfull + 8 * a, 1);
+            ptx::mbar_init(bar_tempty + 8 * a, 128);
+        }
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&tmA);
+    }
+    if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+    if (P.scale)
+        for (int i = threadIdx.x; i < P.Cin; i += blockDim.x) { s_scale[i] = P.scale[i]; s_shift[i] = P.shift[i]; }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_work = P.m_tiles * P.n_blocks;
+    const int tiles_per_img = P.tiles_h * P.tiles_w;
+
+    if (warp == 0) {
+        // ================================================================= TMA producer (one lane)
+        if (lane == 0) {
+            int stage = 0, phase = 0;
+            for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+                const int nb = work % P.n_blocks, mt = work / P.n_blocks;
+                const int n_img = mt / tiles_per_img, rem = mt % tiles_per_img;
+                const int h0 = (rem / P.tiles_w) * kTH, w0 = (rem % P.tiles_w) * kTW;
+                for (int kc = 0; kc < P.k_chunks; ++kc) {
+                    ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
+                    const uint32_t sb = ptx::smem_u32(stage_base + stage * C::STAGE_BYTES);
+                    ptx::mbar_expect_tx(bar_full + 8 * stage, C::RAW_BYTES + C::B_BYTES);
+                    ptx::tma_load_4d(sb, &tmA, bar_full + 8 * stage, kc * KC, w0 - C::PAD, h0 - C::PAD, n_img);
+                    ptx::bulk_load(sb + C::OFF_B, P.bpk + ((size_t)nb * P.k_chunks + kc) * (C::B_BYTES / 2), C::B_BYTES,
+                                   bar_full + 8 * stage);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================================================= MMA issuer (one lane)
+        if (lane == 0) {
+            constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN, 0, 0);
+            int stage = 0, phase = 0, it = 0;
+            for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+                const int acc = it & 1, acc_phase = (it >> 1) & 1;
+                ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, 2);
+                ptx::tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * BN;
+                for (int kc = 0; kc < P.k_chunks; ++kc) {
+                    ptx::mbar_wait(bar_full + 8 * stage, phase, 3);
+                    ptx::mbar_wait(bar_xf + 8 * stage, phase, 4);
+                    ptx::tc_fence_after();
+                    const uint32_t sb = ptx::smem_u32(stage_base + stage * C::STAGE_BYTES);
+#pragma unroll
+                    for (int tap = 0; tap < C::KK; ++tap) {
+                        const int r = tap / KS, s = tap % KS;
+#pragma unroll
+                        for (int kk = 0; kk < KC / 16; ++kk) {
+                            const uint64_t ad = ptx::umma_desc(sb + C::OFF_OP + 2 * kk * C::CH_STRIDE + (r * C::HW + s) * 16,
+                                                               C::CH_STRIDE, C::HW * 16);
+                            const uint64_t bd = ptx::umma_desc(sb + C::OFF_B + tap * C::B_TAP_BYTES + 2 * kk * BN * 16, BN * 16, 128);
+                            ptx::umma_bf16(d_tmem, ad, bd, idesc, (kc | tap | kk) != 0);
+                        }
+                    }
+                    ptx::umma_commit(bar_empty + 8 * stage);      // smem slot reusable once these MMAs retire
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(bar_tfull + 8 * acc);            // accumulator complete -> epilogue
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ================================================================= transform / re-layout warps
+        const int t = threadIdx.x - 128;
+        int stage = 0, phase = 0;
+        for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+            const int mt = work / P.n_blocks;
+            const int n_img = mt / tiles_per_img, rem = mt % tiles_per_img;
+            const int h0 = (rem / P.tiles_w) * kTH - C::PAD, w0 = (rem % P.tiles_w) * kTW - C::PAD;
+            for (int kc = 0; kc < P.k_chunks; ++kc) {
+                ptx::mbar_wait(bar_full + 8 * stage, phase, 5);
+                const uint8_t *raw = stage_base + stage * C::STAGE_BYTES;
+                uint8_t *op = stage_base + stage * C::STAGE_BYTES + C::OFF_OP;
+                for (int i = t; i < C::NPIX * C::NCH; i += 128) {
+                    const int c = i % C::NCH, p = i / C::NCH;
+                    uint4 v = *reinterpret_cast<const uint4 *>(raw + p * (KC * 2) + c * 16);
+                    if (P.scale) {
+                        const int gh = h0 + p / C::HW, gw = w0 + p % C::HW;
+                        if (gh >= 0 && gh < P.H && gw >= 0 && gw < P.W) {
+                            float f[8];
+                            unpack8(v, f);
+                            const int ch = kc * KC + c * 8;
+                            uint32_t keep = 0xffu;
+                            if (P.dropbits) keep = P.dropbits[((((size_t)n_img * P.H + gh) * P.W + gw) * P.Cin + ch) >> 3];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                float a = fmaf(f[j], s_scale[ch + j], s_shift[ch + j]);
+                                a = a > 0.f ? a : kLeakySlope * a;
+                                if (P.dropbits) a = ((keep >> j) & 1u) ? a * P.inv_keep : 0.f;
+                                f[j] = a;
+                            }
+                            v = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+                        } else {
+                            v = make_uint4(0u, 0u, 0u, 0u);       // conv zero padding applies AFTER the activation
+                        }
+                    }
+                    *reinterpret_cast<uint4 *>(op + c * C::CH_STRIDE + p * 16) = v;
+                }
+                ptx::fence_proxy_async_smem();
+                ptx::mbar_arrive(bar_xf + 8 * stage);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+        }
+    } else if (warp >= 8) {
+        // ================================================================= epilogue warps
+        const int q = warp & 3;                      // TMEM lane quarter this warp may read
+        const int m = q * 32 + lane;                 // output pixel within the tile
+        const int et = threadIdx.x - 256;
+        int it = 0;
+        for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+            const int acc = it & 1, acc_phase = (it >> 1) & 1;
+            const int nb = work % P.n_blocks, mt = work / P.n_blocks;
+            const int n_img = mt / tiles_per_img, rem = mt % tiles_per_img;
+            const int gh = (rem / P.tiles_w) * kTH + m / kTW, gw = (rem % P.tiles_w) * kTW + m % kTW;
+            const bool valid = gh < P.H && gw < P.W;
+            ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase, 6);
+            ptx::tc_fence_after();
+            bf16 *orow = P.out + (((size_t)n_img * P.H + gh) * P.W + gw) * P.Cout + nb * BN;
+#pragma unroll 1
+            for (int n0 = 0; n0 < BN; n0 += 16) {
+                uint32_t r[16];
+                ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + n0, r);
+                ptx::tmem_ld_wait();
+                float v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
+                if (P.stats) {
+                    float sq[16];
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+                    const float s1 = butterfly16(v, lane), s2 = butterfly16(sq, lane);
+                    if ((lane & 1) == 0) {
+                        s_part[q * 2 * BN + n0 + col16(lane)] = s1;
+                        s_part[q * 2 * BN + BN + n0 + col16(lane)] = s2;
+                    }
+                }
+                if (valid) {
+                    if (P.bias) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) v[j] += P.bias[nb * BN + n0 + j];
+                    }
+                    uint4 lo = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+                    uint4 hi = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+                    *reinterpret_cast<uint4 *>(orow + n0) = lo;
+                    *reinterpret_cast<uint4 *>(orow + n0 + 8) = hi;
+                }
+            }
+            ptx::tc_fence_before();
+            ptx::mbar_arrive(bar_tempty + 8 * acc);               // accumulator buffer free for the MMA warp
+            if (P.stats) {
+                ptx::named_bar_sync(1, 128);
+                for (int i = et; i < 2 * BN; i += 128) {
+                    const float s = s_part[i] + s_part[2 * BN + i] + s_part[4 * BN + i] + s_part[6 * BN + i];
+                    const int which = i / BN, n = i % BN;
+                    P.stats[(size_t)mt * 2 * P.Cout + which * P.Cout + nb * BN + n] = s;
+                }
+                ptx::named_bar_sync(1, 128);
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ weight packing
+struct PackEntry {
+    long long dst_begin;      // element offset into the packed buffer
+    long long w_off;          // element offset of the OIHW fp32 weight in the flat parameter buffer
+    int cin, cout, kk, KC, BN, dgrad;
+};
+constexpr int kMaxPack = 48;
+struct PackTable {
+    int n;
+    long long total;
+    PackEntry e[kMaxPack];
+};
+
+__global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ params, bf16 *__restrict__ dst, const PackTable T) {
+    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < T.total; g += (long long)gridDim.x * blockDim.x) {
+        int lo = 0;
+        while (lo + 1 < T.n && T.e[lo + 1].dst_begin <= g) ++lo;
+        const PackEntry &E = T.e[lo];
+        long long e = g - E.dst_begin;
+        const int cin_v = E.dgrad ? E.cout : E.cin;
+        const int k_chunks = cin_v / E.KC;
+        const int k = (int)(e % 8);
+        e /= 8;
+        const int n = (int)(e % E.BN);
+        e /= E.BN;
+        const int k8 = (int)(e % (E.KC / 8));
+        e /= (E.KC / 8);
+        const int tap = (int)(e % E.kk);
+        e /= E.kk;
+        const int kc = (int)(e % k_chunks);
+        const int nb = (int)(e / k_chunks);
+        const int co_v = nb * E.BN + n, ci_v = kc * E.KC + k8 * 8 + k;
+        float w;
+        if (!E.dgrad) w = params[E.w_off + ((long long)co_v * E.cin + ci_v) * E.kk + tap];
+        else w = params[E.w_off + ((long long)ci_v * E.cin + co_v) * E.kk + (E.kk - 1 - tap)];   // rot180 + transpose
+        dst[g] = __float2bfloat16_rn(w);
+    }
+}
+
+// ------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// 4-D tiled map over a bf16 NHWC tensor: dims (C, W, H, N), box (kc, box_w, box_h, 1), zero fill out of bounds
+static int make_map(CUtensorMap *m, const void *base, int N, int H, int W, int Cc, int kc, int box_w, int box_h) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return HPFG_ERR_CUDA;
+    }
+    cuuint64_t dims[4] = {(cuuint64_t)Cc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+    cuuint64_t strides[3] = {(cuuint64_t)Cc * 2, (cuuint64_t)W * Cc * 2, (cuuint64_t)H * W * Cc * 2};
+    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+        return HPFG_ERR_CUDA;
+    }
     return HPFG_OK;
 }
-int tc_fprop_1x1(hpfg_unet_plan *, int, const void *, void *, LoadXform, const float *, bool *done, cudaStream_t) {
-    *done = false;
+
+static void pick_cfg(int cin_v, int cout_v, int &KC, int &BN) {
+    BN = std::min(cout_v, 128);
+    KC = (cin_v == 16 || BN == 128) ? 16 : 32;
+}
+
+template <int KS, int KC, int BN>
+static int launch_cfg(const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+    using C = TcCfg<KS, KC, BN>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<KS, KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int total = P.m_tiles * P.n_blocks;
+    const int grid = std::min(total, kNumSMs);
+    tc_conv_kernel<KS, KC, BN><<<grid, kTcThreads, C::SMEM_BYTES, s>>>(map, P);
+    HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
-int tc_dgrad(hpfg_unet_plan *, int, const void *, void *, bool *done, cudaStream_t) {
-    *done = false;
+
+template <int KS>
+static int launch_ks(int KC, int BN, const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+    if (KC == 16 && BN == 16) return launch_cfg<KS, 16, 16>(map, P, s);
+    if (KC == 16 && BN == 32) return launch_cfg<KS, 16, 32>(map, P, s);
+    if (KC == 16 && BN == 128) return launch_cfg<KS, 16, 128>(map, P, s);
+    if (KC == 32 && BN == 16) return launch_cfg<KS, 32, 16>(map, P, s);
+    if (KC == 32 && BN == 32) return launch_cfg<KS, 32, 32>(map, P, s);
+    if (KC == 32 && BN == 64) return launch_cfg<KS, 32, 64>(map, P, s);
+    set_error("tc conv: no kernel for KC=" + std::to_string(KC) + " BN=" + std::to_string(BN));
+    return HPFG_ERR_UNSUPPORTED;
+}
+
+// Run one convolution (conv-view channels cin_v -> cout_v) on the tensor cores.
+static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void *in, void *out, const bf16 *bpk,
+                  const float *bias, LoadXform xf, float *stats, int *P_out, cudaStream_t s) {
+    int KC, BN;
+    pick_cfg(cin_v, cout_v, KC, BN);
+    CUtensorMap map;
+    HPFG_RETURN_IF(make_map(&map, in, N, H, W, cin_v, KC, kTW + ks - 1, kTH + ks - 1));
+    TcConvParams P{};
+    P.bpk = bpk; P.out = (bf16 *)out; P.bias = bias;
+    P.scale = xf.scale; P.shift = xf.shift;
+    P.dropbits = reinterpret_cast<const uint8_t *>(xf.drop.bits); P.inv_keep = xf.drop.inv_keep;
+    P.stats = stats;
+    P.N = N; P.H = H; P.W = W; P.Cin = cin_v; P.Cout = cout_v;
+    P.tiles_h = (H + kTH - 1) / kTH; P.tiles_w = (W + kTW - 1) / kTW;
+    P.m_tiles = N * P.tiles_h * P.tiles_w; P.n_blocks = cout_v / BN; P.k_chunks = cin_v / KC;
+    if (P_out) *P_out = P.m_tiles;
+    return ks == 3 ? launch_ks<3>(KC, BN, map, P, s) : launch_ks<1>(KC, BN, map, P, s);
+}
+
+struct TcPlanState {
+    bf16 *packed = nullptr;
+    PackTable table;
+    long long f_off[kNumConv], d_off[kNumConv];   // -1 = layer not on the tensor-core path
+};
+
+static bool tc_eligible(const ConvLayer &cv) { return cv.cin % 16 == 0 && cv.cout % 16 == 0; }
+
+int tc_plan_init(hpfg_unet_plan *p) {
+    auto *st = new TcPlanState();
+    p->tc = st;
+    st->table.n = 0;
+    long long off = 0;
+    for (int i = 0; i < kNumConv; ++i) {
+        const ConvLayer &cv = p->d.convs[i];
+        st->f_off[i] = st->d_off[i] = -1;
+        if (!tc_eligible(cv)) continue;
+        const long long n = (long long)cv.cin * cv.cout * cv.ks * cv.ks;
+        for (int dg = 0; dg < 2; ++dg) {
+            int KC, BN;
+            pick_cfg(dg ? cv.cout : cv.cin, dg ? cv.cin : cv.cout, KC, BN);
+            PackEntry &E = st->table.e[st->table.n++];
+            E.dst_begin = off; E.w_off = cv.w_off; E.cin = cv.cin; E.cout = cv.cout; E.kk = cv.ks * cv.ks;
+            E.KC = KC; E.BN = BN; E.dgrad = dg;
+            (dg ? st->d_off[i] : st->f_off[i]) = off;
+            off += n;
+        }
+    }
+    st->table.total = off;
+    // stats partial rows: one per 16x8 tile -- never more than the 8x8-tile count the workspace was sized for
+    if (cudaMalloc(&st->packed, (size_t)off * sizeof(bf16)) != cudaSuccess) {
+        set_error("tc_plan_init: cudaMalloc failed");
+        cudaGetLastError();
+        return HPFG_ERR_CUDA;
+    }
+    if (!get_encode()) {
+        set_error("tc_plan_init: cuTensorMapEncodeTiled not available from the driver");
+        return HPFG_ERR_CUDA;
+    }
     return HPFG_OK;
 }
+
+void tc_plan_free(hpfg_unet_plan *p) {
+    auto *st = reinterpret_cast<TcPlanState *>(p->tc);
+    if (!st) return;
+    if (st->packed) cudaFree(st->packed);
+    delete st;
+    p->tc = nullptr;
+}
+
+int tc_pack_all(hpfg_unet_plan *p, const float *params, cudaStream_t s) {
+    auto *st = reinterpret_cast<TcPlanState *>(p->tc);
+    const int blocks = (int)std::min<long long>((st->table.total + 255) / 256, (long long)kNumSMs * 8);
+    tc_pack_kernel<<<blocks, 256, 0, s>>>(params, st->packed, st->table);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+int tc_fprop(hpfg_unet_plan *p, int conv, const void *in, void *out, LoadXform xf, float *stats, int *P, bool *done,
+             cudaStream_t s) {
+    auto *st = reinterpret_cast<TcPlanState *>(p->tc);
+    const ConvLayer &cv = p->d.convs[conv];
+    *done = false;
+    if (st->f_off[conv] < 0) return HPFG_OK;
+    HPFG_RETURN_IF(tc_run(cv.ks, p->N, cv.H, cv.W, cv.cin, cv.cout, in, out, st->packed + st->f_off[conv], nullptr, xf, stats, P, s));
+    *done = true;
+    return HPFG_OK;
+}
+
+int tc_fprop_1x1(hpfg_unet_plan *p, int conv, const void *in, void *out, LoadXform xf, const float *bias, bool *done,
+                 cudaStream_t s) {
+    auto *st = reinterpret_cast<TcPlanState *>(p->tc);
+    const ConvLayer &cv = p->d.convs[conv];
+    *done = false;
+    if (st->f_off[conv] < 0) return HPFG_OK;
+    HPFG_RETURN_IF(tc_run(cv.ks, p->N, cv.H, cv.W, cv.cin, cv.cout, in, out, st->packed + st->f_off[conv], bias, xf, nullptr, nullptr, s));
+    *done = true;
+    return HPFG_OK;
+}
+
+int tc_dgrad(hpfg_unet_plan *p, int conv, const void *dout, void *din, bool *done, cudaStream_t s) {
+    auto *st = reinterpret_cast<TcPlanState *>(p->tc);
+    const ConvLayer &cv = p->d.convs[conv];
+    *done = false;
+    if (st->d_off[conv] < 0) return HPFG_OK;
+    const LoadXform none{};
+    HPFG_RETURN_IF(tc_run(cv.ks, p->N, cv.H, cv.W, cv.cout, cv.cin, dout, din, st->packed + st->d_off[conv], nullptr, none, nullptr, nullptr, s));
+    *done = true;
+    return HPFG_OK;
+}
+
 int tc_wgrad(hpfg_unet_plan *, int, const void *, LoadXform, const void *, float *, float *, int, bool *done, cudaStream_t) {
     *done = false;
     return HPFG_OK;
 }
 
 }  // namespace hpfg
+
+// ---- layer-isolated test hook ----------------------------------------------------------------------------
+using namespace hpfg;
+
+__global__ void tc_debug_reduce_stats(const float *partials, int P, int C2, float *out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C2) return;
+    double s = 0.0;
+    for (int p = 0; p < P; ++p) s += (double)partials[(size_t)p * C2 + c];
+    out[c] = (float)s;
+}
+
+extern "C" int hpfg_conv_tc_debug(int op, int N, int H, int W, int cin, int cout, int ks, const void *in_bf16_nhwc,
+                                  const float *w_oihw, const float *bias, const float *scale, const float *shift,
+                                  void *out_bf16_nhwc, float *stats_out, void *stream) {
+    HPFG_REQUIRE(op == 0 || op == 1, "hpfg_conv_tc_debug: op must be 0 (fprop) or 1 (dgrad)");
+    HPFG_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && (ks == 1 || ks == 3), "hpfg_conv_tc_debug: unsupported shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int cin_v = op ? cout : cin, cout_v = op ? cin : cout;
+    PackTable T{};
+    T.n = 1;
+    T.total = (long long)cin * cout * ks * ks;
+    pick_cfg(cin_v, cout_v, T.e[0].KC, T.e[0].BN);
+    T.e[0].dst_begin = 0; T.e[0].w_off = 0; T.e[0].cin = cin; T.e[0].cout = cout; T.e[0].kk = ks * ks; T.e[0].dgrad = op;
+    bf16 *packed = nullptr;
+    float *partials = nullptr;
+    const int m_tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
+    HPFG_CUDA_CHECK(cudaMalloc(&packed, (size_t)T.total * 2));
+    HPFG_CUDA_CHECK(cudaMalloc(&partials, (size_t)m_tiles * 2 * cout_v * 4));
+    tc_pack_kernel<<<(int)std::min<long long>((T.total + 255) / 256, 1024), 256, 0, s>>>(w_oihw, packed, T);
+    HPFG_LAUNCH_CHECK();
+    LoadXform xf{};
+    xf.scale = scale; xf.shift = shift; xf.drop.bits = nullptr; xf.drop.inv_keep = 1.f;
+    int P = 0;
+    int rc = tc_run(ks, N, H, W, cin_v, cout_v, in_bf16_nhwc, out_bf16_nhwc, packed, bias, xf, stats_out ? partials : nullptr, &P, s);
+    if (rc == HPFG_OK && stats_out) {
+        tc_debug_reduce_stats<<<(2 * cout_v + 127) / 128, 128, 0, s>>>(partials, P, 2 * cout_v, stats_out);
+        ++g_launch_count;
+    }
+    cudaStreamSynchronize(s);
+    cudaFree(packed);
+    cudaFree(partials);
+    if (rc == HPFG_OK) HPFG_CUDA_CHECK(cudaGetLastError());
+    return rc;
+}

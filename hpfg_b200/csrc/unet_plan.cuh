@@ -23,7 +23,6 @@ struct ConvLayer {
     int bn;                      // index of the BatchNorm that follows, or -1
     float *wf = nullptr;         // fp32 packed [tap][ci][co]              (CUDA-core fprop)
     float *wd = nullptr;         // fp32 packed [tap'][co][ci], flipped    (CUDA-core dgrad)
-    void *tc = nullptr;          // tensor-core path per-layer state (conv_tc.cu), bf16 plans only
 };
 
 struct BnLayer {
@@ -69,4 +68,5 @@ struct hpfg_unet_plan {
     bool saved = false, saved_dropout = false;
     const float *saved_x = nullptr;
     cudaEvent_t bucket_ev[hpfg::kNumBuckets] = {};
+    void *tc = nullptr;               // tensor-core path state (conv_tc.cu), bf16 plans only
 };

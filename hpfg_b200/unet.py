@@ -53,6 +53,7 @@ class _UNetFunction(torch.autograd.Function):
         logits = module._run_forward(plan, x, save=True)
         plan.busy = True
         ctx.module, ctx.plan = module, plan
+        ctx.x = x        # the first layer's weight gradient re-reads the input: keep it alive until backward
         return logits
 
     @staticmethod

@@ -71,7 +71,9 @@ int64_t hpfg_unet_plan_workspace_bytes(hpfg_unet_plan_t plan);
  * dropout_masks_host (host array of HPFG_NUM_DROPOUT device pointers to uint8 NCHW keep-masks; a NULL entry
  * or NULL array means "draw with the library's Philox stream keyed by dropout_seed/dropout_offset"; pass
  * no_dropout != 0 to disable dropout entirely while keeping batch-statistics BN).
- * save_for_backward != 0 keeps the activations hpfg_unet_backward needs inside the plan. */
+ * save_for_backward != 0 keeps the activations hpfg_unet_backward needs inside the plan; x itself is NOT copied
+ * and must stay valid and unchanged until that backward has been enqueued (the first layer's weight gradient
+ * re-reads it). */
 int hpfg_unet_forward(hpfg_unet_plan_t plan, const float *params, float *bn_running, int64_t *bn_counters,
                       const float *x, float *logits, int training, int no_dropout, int save_for_backward,
                       uint64_t dropout_seed, uint64_t dropout_offset, const uint8_t *const *dropout_masks_host,
@@ -94,12 +96,21 @@ int hpfg_unet_bucket_wait(hpfg_unet_plan_t plan, int bucket, void *comm_stream);
  * conv names ("encoder.in_conv.conv_conv.0", ..., raw conv outputs incl. bias) . */
 int hpfg_unet_debug_tap(hpfg_unet_plan_t plan, const char *name, float *out_nchw, int64_t capacity, void *stream);
 
+/* Layer-isolated test hook for the bf16 tensor-core convolution kernels: runs ONE convolution on caller
+ * tensors (bf16 NHWC activations, fp32 OIHW weights) and synchronises.  op 0 = fprop (in has cin channels, out
+ * cout; optional per-input-channel scale/shift = the fused BN+LeakyReLU loader; optional bias[cout]);
+ * op 1 = dgrad (in = dout with cout channels, out = din with cin channels).  stats_out (optional):
+ * float[2*C_out_of_the_op] = per-channel sum | sum of squares of the fp32 accumulators. */
+int hpfg_conv_tc_debug(int op, int batch, int height, int width, int cin, int cout, int ksize,
+                       const void *in_bf16_nhwc, const float *w_oihw, const float *bias, const float *scale,
+                       const float *shift, void *out_bf16_nhwc, float *stats_out, void *stream);
+
 /* ---- fused SSL loss (forward value + d loss / d logits) ---------------------------------------------
  * student: fp32 NCHW [n_l+n_u, C, H, W] logits.  labels: int64 [n_l, H, W] (255 = ignored by CE only).
  * other: MT/UAMT -> teacher logits for the UNLABELED slices [n_u, C, H, W];
  *        CPS     -> the peer network's logits [n_l+n_u, C, H, W];  SUP -> NULL.
  * mc_logits (UAMT only): [T*n_u, C, H, W] logits of the T stochastic teacher passes (pass-major).
- * dstudent / dother: gradients (dother only for CPS, else NULL).  class_weights: C floats or NULL (=1).
+ * dstudent / dother: gradients (dother only for CPS, else NULL).  class_weights: HOST array of C floats or NULL (=1).
  * scalars_out: float[8] device: {loss, loss_sup, loss_cons_or_semi, ce, dice, n_valid, mask_sum, 0}.
  * pseudo1/pseudo2 (CPS, optional): int64 [n_u,H,W] argmax pseudo-labels of net1 / net2.
  * workspace: at least hpfg_ssl_loss_workspace_bytes(...) bytes of device scratch. */
