@@ -21,6 +21,8 @@ SIGNATURES = {
     "hpfg_last_error": (ctypes.c_char_p, []),
     "hpfg_version": (c_int, []),
     "hpfg_launch_count": (c_i64, []),
+    "hpfg_profile_begin": (c_int, []),
+    "hpfg_profile_end": (c_int, [ctypes.POINTER(ctypes.c_double), c_i64p]),
     "hpfg_unet_param_layout": (c_int, [c_int, c_int, c_i64p, c_i64p, c_i64p]),
     "hpfg_unet_bn_layout": (c_int, [c_int, c_int, c_i64p, c_i64p, c_i64p]),
     "hpfg_unet_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),

@@ -123,6 +123,7 @@ int conv_ref_num_tiles(int N, int H, int W) { return N * ((H + kTile - 1) / kTil
 template <typename TI, typename TO>
 int conv_ref_fprop(TView in, TView out, const float *wpk, const float *bias, int N, int H, int W, int Cin, int Cout,
                    int KS, LoadXform xf, float *stats, cudaStream_t s) {
+    ProfScope _prof(PROF_CONV_CUDA, s);
     dim3 grid(conv_ref_num_tiles(N, H, W), (Cout + kBN - 1) / kBN);
     if (KS == 3)
         conv_ref_fprop_kernel<TI, TO, 3><<<grid, 256, 0, s>>>(in, out, wpk, bias, N, H, W, Cin, Cout, xf, stats);
@@ -230,6 +231,7 @@ int64_t conv_ref_wgrad_scratch_floats(int N, int H, int W, int Cin, int Cout, in
 template <typename TI, typename TD>
 int conv_ref_wgrad(TView in, TView dout, int N, int H, int W, int Cin, int Cout, int KS, LoadXform xf, float *scratch,
                    int64_t scratch_floats, float *dw_oihw, float *dbias, int accumulate, cudaStream_t s) {
+    ProfScope _prof(PROF_WGRAD, s);
     const int S = wgrad_splits(N, H, W, Cin, Cout);
     HPFG_REQUIRE(conv_ref_wgrad_scratch_floats(N, H, W, Cin, Cout, KS) <= scratch_floats, "conv_ref_wgrad: scratch too small");
     const int co_chunks = (Cout + kBN - 1) / kBN;
@@ -265,6 +267,7 @@ __global__ void pack_weights_ref_kernel(const float *__restrict__ w, float *__re
 }
 
 int pack_weights_ref(const float *w_oihw, float *wpk_fprop, float *wpk_dgrad, int Cin, int Cout, int KS, cudaStream_t s) {
+    ProfScope _prof(PROF_PACK, s);
     const int64_t total = (int64_t)Cout * Cin * KS * KS;
     int blocks = (int)((total + 255) / 256);
     if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;

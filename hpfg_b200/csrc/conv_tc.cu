@@ -413,6 +413,7 @@ static int launch_ks(int KC, int BN, const CUtensorMap &map, const TcConvParams 
 // Run one convolution (conv-view channels cin_v -> cout_v) on the tensor cores.
 static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void *in, void *out, const bf16 *bpk,
                   const float *bias, LoadXform xf, float *stats, int *P_out, cudaStream_t s) {
+    ProfScope _prof(PROF_CONV_TC, s);
     int KC, BN;
     pick_cfg(cin_v, cout_v, KC, BN);
     CUtensorMap map;
@@ -480,6 +481,7 @@ void tc_plan_free(hpfg_unet_plan *p) {
 }
 
 int tc_pack_all(hpfg_unet_plan *p, const float *params, cudaStream_t s) {
+    ProfScope _prof(PROF_PACK, s);
     auto *st = reinterpret_cast<TcPlanState *>(p->tc);
     const int blocks = (int)std::min<long long>((st->table.total + 255) / 256, (long long)kNumSMs * 8);
     tc_pack_kernel<<<blocks, 256, 0, s>>>(params, st->packed, st->table);

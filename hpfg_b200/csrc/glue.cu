@@ -84,6 +84,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restric
 int bn_finalize(const float *partials, int P, int C, int64_t count, const float *gamma, const float *beta,
                 const float *conv_bias, float *running_mean, float *running_var, int64_t *counter, int training,
                 BnState st, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
     const double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
     bn_finalize_kernel<<<ceil_div(C * 32, 256), 256, 0, s>>>(partials, P, C, 1.0 / (double)count, unbias, gamma,
                                                              beta, conv_bias, running_mean, running_var, counter,
@@ -106,6 +107,7 @@ __global__ void bn_eval_affine_kernel(int C, const float *gamma, const float *be
 
 int bn_eval_affine(int C, const float *gamma, const float *beta, const float *conv_bias, const float *running_mean,
                    const float *running_var, BnState st, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
     bn_eval_affine_kernel<<<ceil_div(C, 128), 128, 0, s>>>(C, gamma, beta, conv_bias, running_mean, running_var, st);
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
@@ -144,6 +146,7 @@ __global__ void __launch_bounds__(256) pool_act_kernel(const T *__restrict__ raw
 
 template <typename T>
 int pool_act(const T *raw, T *pooled, int N, int H, int W, int C, BnState bn, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
     const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / Vec<T>::N);
     pool_act_kernel<T><<<ew_grid(total), 256, 0, s>>>(raw, pooled, N, H, W, C, bn);
     HPFG_LAUNCH_CHECK();
@@ -201,6 +204,7 @@ __global__ void __launch_bounds__(256) upcat_kernel(const T *__restrict__ raw_sk
 
 template <typename T>
 int upcat(const T *raw_skip, BnState bn_skip, const T *low, T *cat, int N, int h, int w, int F, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
     const int64_t total = (int64_t)N * 4 * h * w * (2 * F / Vec<T>::N);
     const float sh_ = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
     const float sw_ = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
@@ -297,6 +301,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float *__res
 template <typename T>
 int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, DropSpec drop, float *partials,
            int max_partials, float *dgamma, float *dbeta, int accumulate, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
     int P = (int)((M + 63) / 64);
     if (P > kNumSMs * 4) P = kNumSMs * 4;
     if (P > max_partials) P = max_partials;
@@ -364,6 +369,7 @@ __global__ void __launch_bounds__(256) skip_pool_bwd_kernel(const T *__restrict_
 template <typename T>
 int skip_pool_bwd(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *dact, int N, int H, int W, int F,
                   cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
     const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (F / Vec<T>::N);
     skip_pool_bwd_kernel<T><<<ew_grid(total), 256, 0, s>>>(dcat, dpooled, raw, bn, dact, N, H, W, F);
     HPFG_LAUNCH_CHECK();
@@ -414,6 +420,7 @@ __global__ void __launch_bounds__(256) up_bwd_kernel(const T *__restrict__ dcat,
 
 template <typename T>
 int up_bwd(const T *dcat, T *dlow, int N, int h, int w, int F, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
     const int64_t total = (int64_t)N * h * w * (F / Vec<T>::N);
     const float sh_ = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
     const float sw_ = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
@@ -458,6 +465,7 @@ __global__ void __launch_bounds__(256) dropout_bits_kernel(uint32_t *__restrict_
 
 int dropout_bits(uint32_t *bits, const uint8_t *mask_nchw, int N, int H, int W, int C, float p, uint64_t seed,
                  uint64_t offset, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
     const int64_t n_words = ((int64_t)N * H * W * C + 31) / 32;
     dropout_bits_kernel<<<ew_grid(n_words), 256, 0, s>>>(bits, mask_nchw, N, H, W, C, p, seed, offset, n_words);
     HPFG_LAUNCH_CHECK();
@@ -481,6 +489,7 @@ __global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, float *__restrict
 
 template <typename T>
 int nhwc_to_nchw_f32(const T *src, float *dst, int N, int H, int W, int C, const float *bias, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
     nhwc_to_nchw_kernel<T><<<ew_grid((int64_t)N * C * H * W), 256, 0, s>>>(src, dst, N, H, W, C, bias);
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;

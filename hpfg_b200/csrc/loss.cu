@@ -533,6 +533,7 @@ extern "C" int hpfg_ssl_loss(int mode, const float *student, const float *other,
     A.dstudent = dstudent; A.dother = dother; A.scalars = scalars_out; A.pseudo1 = pseudo1; A.pseudo2 = pseudo2;
     A.acc = reinterpret_cast<double *>(workspace);
     A.aux = reinterpret_cast<uint8_t *>(workspace) + kAccTotal * sizeof(double);
+    ProfScope _prof(PROF_LOSS, st);
     HPFG_CUDA_CHECK(cudaMemsetAsync(A.acc, 0, kAccTotal * sizeof(double), st));
     switch (num_classes) {
         case 2: return launch_loss<2>(A, st);

@@ -96,6 +96,7 @@ extern "C" int hpfg_ema_update(float *ema, const float *param, int64_t n, float 
     HPFG_REQUIRE(ema && param && n >= 0, "hpfg_ema_update: null buffer");
     HPFG_REQUIRE(aligned16(ema) && aligned16(param), "hpfg_ema_update: buffers must be 16-byte aligned");
     if (n == 0) return HPFG_OK;
+    ProfScope _prof(PROF_OPTIM, (cudaStream_t)stream);
     ema_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(ema, param, n, alpha, 1.0f - alpha);
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
@@ -108,6 +109,7 @@ extern "C" int hpfg_sgd_momentum(float *param, const float *grad, float *momentu
     HPFG_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(momentum_buf),
                  "hpfg_sgd_momentum: buffers must be 16-byte aligned");
     if (n == 0) return HPFG_OK;
+    ProfScope _prof(PROF_OPTIM, (cudaStream_t)stream);
     SgdArgs a{lr, momentum, weight_decay, grad_scale, 0.f, 0.f, first_step};
     sgd_kernel<false><<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, nullptr, n, a);
     HPFG_LAUNCH_CHECK();
@@ -121,6 +123,7 @@ extern "C" int hpfg_sgd_momentum_ema(float *param, const float *grad, float *mom
     HPFG_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(momentum_buf) && aligned16(ema),
                  "hpfg_sgd_momentum_ema: buffers must be 16-byte aligned");
     if (n == 0) return HPFG_OK;
+    ProfScope _prof(PROF_OPTIM, (cudaStream_t)stream);
     SgdArgs a{lr, momentum, weight_decay, grad_scale, ema_alpha, 1.0f - ema_alpha, first_step};
     sgd_kernel<true><<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, ema, n, a);
     HPFG_LAUNCH_CHECK();

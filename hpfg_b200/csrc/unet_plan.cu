@@ -12,6 +12,22 @@ static thread_local std::string g_error;
 int64_t g_launch_count = 0;
 void set_error(const std::string &msg) { g_error = msg; }
 
+bool g_prof_on = false;
+struct ProfRec { int cat; cudaEvent_t a, b; };
+static std::vector<ProfRec> g_prof;
+void prof_push(int cat, cudaStream_t s, bool begin) {
+    if (begin) {
+        ProfRec r{cat, nullptr, nullptr};
+        cudaEventCreate(&r.a);
+        cudaEventCreate(&r.b);
+        cudaEventRecord(r.a, s);
+        g_prof.push_back(r);
+    } else {
+        for (int i = (int)g_prof.size() - 1; i >= 0; --i)
+            if (g_prof[i].cat == cat) { cudaEventRecord(g_prof[i].b, s); break; }
+    }
+}
+
 void describe_unet(int in_ch, int n_cls, int H, int W, UNetDesc &d) {
     d.in_ch = in_ch;
     d.n_cls = n_cls;
@@ -337,6 +353,34 @@ using namespace hpfg;
 extern "C" const char *hpfg_last_error(void) { return g_error.c_str(); }
 extern "C" int hpfg_version(void) { return 100; }
 extern "C" int64_t hpfg_launch_count(void) { return g_launch_count; }
+
+extern "C" int hpfg_profile_begin(void) {
+    for (auto &r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+    g_prof.clear();
+    g_prof_on = true;
+    return HPFG_OK;
+}
+
+extern "C" int hpfg_profile_end(double *ms_per_category_host, int64_t *calls_per_category_host) {
+    g_prof_on = false;
+    HPFG_CUDA_CHECK(cudaDeviceSynchronize());
+    for (int c = 0; c < PROF_NCAT; ++c) {
+        if (ms_per_category_host) ms_per_category_host[c] = 0.0;
+        if (calls_per_category_host) calls_per_category_host[c] = 0;
+    }
+    for (auto &r : g_prof) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, r.a, r.b) == cudaSuccess) {
+            if (ms_per_category_host) ms_per_category_host[r.cat] += ms;
+            if (calls_per_category_host) calls_per_category_host[r.cat] += 1;
+        }
+        cudaEventDestroy(r.a);
+        cudaEventDestroy(r.b);
+    }
+    cudaGetLastError();
+    g_prof.clear();
+    return HPFG_OK;
+}
 
 extern "C" int hpfg_unet_param_layout(int in_channels, int num_classes, int64_t *offsets_host, int64_t *sizes_host,
                                       int64_t *total_host) {

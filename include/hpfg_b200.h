@@ -49,6 +49,13 @@ int hpfg_version(void);
 /* Number of CUDA kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t hpfg_launch_count(void);
 
+/* Optional device timing per kernel category (bench.py's roofline leg): between begin and end every host-side
+ * launcher brackets its kernels with CUDA events on the caller's stream; end synchronises and returns the summed
+ * milliseconds and call counts for categories {0 tensor-core conv, 1 CUDA-core conv, 2 CUDA-core wgrad, 3 BN /
+ * pool / upsample glue, 4 loss, 5 SGD/EMA, 6 weight packing, 7 unused}: double[8], int64[8] on the host. */
+int hpfg_profile_begin(void);
+int hpfg_profile_end(double *ms_per_category_host, int64_t *calls_per_category_host);
+
 /* ---- model layout (mirrors model/unet.py state_dict order) -------------------------------------------
  * Flat parameter buffer: the 82 tensors of UNet.named_parameters() in registration order, each in its
  * native PyTorch layout (conv weight OIHW), fp32, back to back.  offsets/sizes: int64[82] in elements.
