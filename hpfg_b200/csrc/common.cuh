@@ -90,7 +90,7 @@ __device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 ctr) {
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- optional per-category device timing (bench.py's roofline leg): CUDA events around each host launcher ----
-enum ProfCat { PROF_CONV_TC = 0, PROF_CONV_CUDA = 1, PROF_WGRAD = 2, PROF_GLUE = 3, PROF_LOSS = 4, PROF_OPTIM = 5, PROF_PACK = 6, PROF_NCAT = 8 };
+enum ProfCat { PROF_CONV_TC = 0, PROF_CONV_CUDA = 1, PROF_WGRAD = 2, PROF_GLUE = 3, PROF_LOSS = 4, PROF_OPTIM = 5, PROF_PACK = 6, PROF_WGRAD_TC = 7, PROF_NCAT = 8 };
 extern bool g_prof_on;
 void prof_push(int cat, cudaStream_t s, bool begin);
 struct ProfScope {

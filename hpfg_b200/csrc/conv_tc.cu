@@ -19,12 +19,11 @@
 #include <map>
 #include <tuple>
 
-#include "tc_ptx.cuh"
+#include "tc_common.cuh"
 
 namespace hpfg {
 
 // ------------------------------------------------------------------------------------------ configuration
-constexpr int kTH = 16, kTW = 8;            // output tile (rows x cols) = 128 pixels = UMMA M
 constexpr int kTcThreads = 384;             // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 transform, 8-11 epilogue
 constexpr int kMaxStages = 6;
 constexpr int kSmemBudget = 200 * 1024;
@@ -59,21 +58,10 @@ struct TcConvParams {
     const uint8_t *dropbits;  // producer's dropout keep bits, NHWC bit order, or nullptr
     float inv_keep;
     float *stats;             // [m_tiles][2*Cout] partial sums or nullptr
+    float *out_nchw;          // if set: write fp32 NCHW [N,out_c_real,H,W] (+bias) instead of bf16 NHWC (out_conv logits)
+    int out_c_real;
     int N, H, W, Cin, Cout, tiles_h, tiles_w, m_tiles, n_blocks, k_chunks;
 };
-
-__device__ __forceinline__ void unpack8(const uint4 &v, float (&f)[8]) {
-    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        f[2 * i] = __uint_as_float(w[i] << 16);
-        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
-    }
-}
-__device__ __forceinline__ uint32_t pack2(float a, float b) {
-    const __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-    return *reinterpret_cast<const uint32_t *>(&h);
-}
 
 // Reduce 16 per-lane values over the 32 lanes of a warp with 16 shuffles (recursive halving); afterwards every
 // lane holds the full column sum of column col16(lane).
@@ -270,7 +258,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                         s_part[q * 2 * BN + BN + n0 + col16(lane)] = s2;
                     }
                 }
-                if (valid) {
+                if (valid && P.out_nchw) {
+                    float *o = P.out_nchw + ((size_t)n_img * P.out_c_real * P.H + gh) * P.W + gw;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j)
+                        if (nb * BN + n0 + j < P.out_c_real)
+                            o[(size_t)(nb * BN + n0 + j) * P.H * P.W] = v[j] + (P.bias ? P.bias[nb * BN + n0 + j] : 0.f);
+                } else if (valid) {
                     if (P.bias) {
 #pragma unroll
                         for (int j = 0; j < 16; ++j) v[j] += P.bias[nb * BN + n0 + j];
@@ -306,7 +300,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
 struct PackEntry {
     long long dst_begin;      // element offset into the packed buffer
     long long w_off;          // element offset of the OIHW fp32 weight in the flat parameter buffer
-    int cin, cout, kk, KC, BN, dgrad;
+    int cin, cout, kk, KC, BN, dgrad;   // cin/cout: channel counts padded to multiples of 16 (layout)
+    int cin_real, cout_real;            // true tensor dims (source indexing; padded entries are zero)
 };
 constexpr int kMaxPack = 48;
 struct PackTable {
@@ -334,50 +329,17 @@ __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ 
         const int kc = (int)(e % k_chunks);
         const int nb = (int)(e / k_chunks);
         const int co_v = nb * E.BN + n, ci_v = kc * E.KC + k8 * 8 + k;
-        float w;
-        if (!E.dgrad) w = params[E.w_off + ((long long)co_v * E.cin + ci_v) * E.kk + tap];
-        else w = params[E.w_off + ((long long)ci_v * E.cin + co_v) * E.kk + (E.kk - 1 - tap)];   // rot180 + transpose
+        float w = 0.f;
+        if (!E.dgrad) {
+            if (co_v < E.cout_real && ci_v < E.cin_real) w = params[E.w_off + ((long long)co_v * E.cin_real + ci_v) * E.kk + tap];
+        } else if (ci_v < E.cout_real && co_v < E.cin_real) {       // rot180 + transpose
+            w = params[E.w_off + ((long long)ci_v * E.cin_real + co_v) * E.kk + (E.kk - 1 - tap)];
+        }
         dst[g] = __float2bfloat16_rn(w);
     }
 }
 
 // ------------------------------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
-                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn get_encode() {
-    static EncodeTiledFn fn = nullptr;
-    if (!fn) {
-        void *p = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-            qres == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-    }
-    return fn;
-}
-
-// 4-D tiled map over a bf16 NHWC tensor: dims (C, W, H, N), box (kc, box_w, box_h, 1), zero fill out of bounds
-static int make_map(CUtensorMap *m, const void *base, int N, int H, int W, int Cc, int kc, int box_w, int box_h) {
-    EncodeTiledFn enc = get_encode();
-    if (!enc) {
-        set_error("cuTensorMapEncodeTiled entry point not available");
-        return HPFG_ERR_CUDA;
-    }
-    cuuint64_t dims[4] = {(cuuint64_t)Cc, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
-    cuuint64_t strides[3] = {(cuuint64_t)Cc * 2, (cuuint64_t)W * Cc * 2, (cuuint64_t)H * W * Cc * 2};
-    cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)box_w, (cuuint32_t)box_h, 1};
-    cuuint32_t estr[4] = {1, 1, 1, 1};
-    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void *>(base), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
-        return HPFG_ERR_CUDA;
-    }
-    return HPFG_OK;
-}
-
 static void pick_cfg(int cin_v, int cout_v, int &KC, int &BN) {
     BN = std::min(cout_v, 128);
     KC = (cin_v == 16 || BN == 128) ? 16 : 32;
@@ -412,7 +374,8 @@ static int launch_ks(int KC, int BN, const CUtensorMap &map, const TcConvParams 
 
 // Run one convolution (conv-view channels cin_v -> cout_v) on the tensor cores.
 static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void *in, void *out, const bf16 *bpk,
-                  const float *bias, LoadXform xf, float *stats, int *P_out, cudaStream_t s) {
+                  const float *bias, LoadXform xf, float *stats, int *P_out, cudaStream_t s, float *out_nchw = nullptr,
+                  int out_c_real = 0) {
     ProfScope _prof(PROF_CONV_TC, s);
     int KC, BN;
     pick_cfg(cin_v, cout_v, KC, BN);
@@ -423,6 +386,7 @@ static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void
     P.scale = xf.scale; P.shift = xf.shift;
     P.dropbits = reinterpret_cast<const uint8_t *>(xf.drop.bits); P.inv_keep = xf.drop.inv_keep;
     P.stats = stats;
+    P.out_nchw = out_nchw; P.out_c_real = out_c_real;
     P.N = N; P.H = H; P.W = W; P.Cin = cin_v; P.Cout = cout_v;
     P.tiles_h = (H + kTH - 1) / kTH; P.tiles_w = (W + kTW - 1) / kTW;
     P.m_tiles = N * P.tiles_h * P.tiles_w; P.n_blocks = cout_v / BN; P.k_chunks = cin_v / KC;
@@ -436,7 +400,7 @@ struct TcPlanState {
     long long f_off[kNumConv], d_off[kNumConv];   // -1 = layer not on the tensor-core path
 };
 
-static bool tc_eligible(const ConvLayer &cv) { return cv.cin % 16 == 0 && cv.cout % 16 == 0; }
+static int pad16(int c) { return (c + 15) / 16 * 16; }
 
 int tc_plan_init(hpfg_unet_plan *p) {
     auto *st = new TcPlanState();
@@ -446,13 +410,15 @@ int tc_plan_init(hpfg_unet_plan *p) {
     for (int i = 0; i < kNumConv; ++i) {
         const ConvLayer &cv = p->d.convs[i];
         st->f_off[i] = st->d_off[i] = -1;
-        if (!tc_eligible(cv)) continue;
-        const long long n = (long long)cv.cin * cv.cout * cv.ks * cv.ks;
+        const int cinp = pad16(cv.cin), coutp = pad16(cv.cout);
+        const long long n = (long long)cinp * coutp * cv.ks * cv.ks;
         for (int dg = 0; dg < 2; ++dg) {
+            if (dg && i == 0) continue;                      // the network input needs no data gradient
             int KC, BN;
-            pick_cfg(dg ? cv.cout : cv.cin, dg ? cv.cin : cv.cout, KC, BN);
+            pick_cfg(dg ? coutp : cinp, dg ? cinp : coutp, KC, BN);
             PackEntry &E = st->table.e[st->table.n++];
-            E.dst_begin = off; E.w_off = cv.w_off; E.cin = cv.cin; E.cout = cv.cout; E.kk = cv.ks * cv.ks;
+            E.dst_begin = off; E.w_off = cv.w_off; E.cin = cinp; E.cout = coutp; E.kk = cv.ks * cv.ks;
+            E.cin_real = cv.cin; E.cout_real = cv.cout;
             E.KC = KC; E.BN = BN; E.dgrad = dg;
             (dg ? st->d_off[i] : st->f_off[i]) = off;
             off += n;
@@ -495,7 +461,7 @@ int tc_fprop(hpfg_unet_plan *p, int conv, const void *in, void *out, LoadXform x
     const ConvLayer &cv = p->d.convs[conv];
     *done = false;
     if (st->f_off[conv] < 0) return HPFG_OK;
-    HPFG_RETURN_IF(tc_run(cv.ks, p->N, cv.H, cv.W, cv.cin, cv.cout, in, out, st->packed + st->f_off[conv], nullptr, xf, stats, P, s));
+    HPFG_RETURN_IF(tc_run(cv.ks, p->N, cv.H, cv.W, pad16(cv.cin), cv.cout, in, out, st->packed + st->f_off[conv], nullptr, xf, stats, P, s));
     *done = true;
     return HPFG_OK;
 }
@@ -511,19 +477,31 @@ int tc_fprop_1x1(hpfg_unet_plan *p, int conv, const void *in, void *out, LoadXfo
     return HPFG_OK;
 }
 
+int tc_fprop_logits(hpfg_unet_plan *p, int conv, const void *in, LoadXform xf, const float *bias, float *logits_nchw, cudaStream_t s) {
+    auto *st = reinterpret_cast<TcPlanState *>(p->tc);
+    const ConvLayer &cv = p->d.convs[conv];
+    return tc_run(cv.ks, p->N, cv.H, cv.W, cv.cin, pad16(cv.cout), in, nullptr, st->packed + st->f_off[conv], bias, xf, nullptr, nullptr, s,
+                  logits_nchw, cv.cout);
+}
+
 int tc_dgrad(hpfg_unet_plan *p, int conv, const void *dout, void *din, bool *done, cudaStream_t s) {
     auto *st = reinterpret_cast<TcPlanState *>(p->tc);
     const ConvLayer &cv = p->d.convs[conv];
     *done = false;
     if (st->d_off[conv] < 0) return HPFG_OK;
     const LoadXform none{};
-    HPFG_RETURN_IF(tc_run(cv.ks, p->N, cv.H, cv.W, cv.cout, cv.cin, dout, din, st->packed + st->d_off[conv], nullptr, none, nullptr, nullptr, s));
+    HPFG_RETURN_IF(tc_run(cv.ks, p->N, cv.H, cv.W, pad16(cv.cout), cv.cin, dout, din, st->packed + st->d_off[conv], nullptr, none, nullptr, nullptr, s));
     *done = true;
     return HPFG_OK;
 }
 
-int tc_wgrad(hpfg_unet_plan *, int, const void *, LoadXform, const void *, float *, float *, int, bool *done, cudaStream_t) {
+int tc_wgrad(hpfg_unet_plan *p, int conv, const void *in, LoadXform xf, const void *dout, float *dw_oihw, float *dbias,
+             int accumulate, bool *done, cudaStream_t s) {
+    const ConvLayer &cv = p->d.convs[conv];
     *done = false;
+    HPFG_RETURN_IF(tc_wgrad_run(cv.ks, p->N, cv.H, cv.W, pad16(cv.cin), pad16(cv.cout), cv.cin, cv.cout, in, xf, dout, p->wscratch,
+                                p->wscratch_floats, dw_oihw, dbias, accumulate, s));
+    *done = true;
     return HPFG_OK;
 }
 
@@ -552,6 +530,7 @@ extern "C" int hpfg_conv_tc_debug(int op, int N, int H, int W, int cin, int cout
     T.total = (long long)cin * cout * ks * ks;
     pick_cfg(cin_v, cout_v, T.e[0].KC, T.e[0].BN);
     T.e[0].dst_begin = 0; T.e[0].w_off = 0; T.e[0].cin = cin; T.e[0].cout = cout; T.e[0].kk = ks * ks; T.e[0].dgrad = op;
+    T.e[0].cin_real = cin; T.e[0].cout_real = cout;
     bf16 *packed = nullptr;
     float *partials = nullptr;
     const int m_tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);

@@ -114,6 +114,10 @@ static void carve(hpfg_unet_plan *p, char *base, int64_t &total) {
         c.take(p->dcat[j], N * (H >> lvl) * (W >> lvl) * 2 * kFt[lvl] * e);
     }
     for (int k = 0; k < 4; ++k) c.take(p->g[k], N * H * W * 16 * e);
+    if (p->precision == HPFG_PREC_BF16) {
+        c.take(p->xpad, N * H * W * 16 * 2);
+        c.take(p->dlpad, N * H * W * 16 * 2);
+    }
     for (int l = 0; l < 5; ++l) c.take(p->dropbits[l], (N * (H >> l) * (W >> l) * kFt[l] + 31) / 32 * 4);
     // BN statistic partials: one row of 2*C floats per 8x8 pixel tile (CUDA-core path) / per CTA tile (tensor path)
     int64_t sf = 0, wf = 0;
@@ -125,7 +129,11 @@ static void carve(hpfg_unet_plan *p, char *base, int64_t &total) {
     p->stats_floats = sf;
     c.take(p->stats, sf * 4);
     for (auto &cv : p->d.convs)
+    {
         wf = std::max(wf, conv_ref_wgrad_scratch_floats((int)N, cv.H, cv.W, cv.cin, cv.cout, cv.ks));
+        if (p->precision == HPFG_PREC_BF16)
+            wf = std::max(wf, tc_wgrad_scratch_floats((int)N, cv.H, cv.W, (cv.cin + 15) / 16 * 16, (cv.cout + 15) / 16 * 16, cv.ks));
+    }
     p->wscratch_floats = wf;
     c.take(p->wscratch, wf * 4);
     int64_t bnf = 0;
@@ -158,8 +166,9 @@ static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_runnin
     const bool tc = p->precision == HPFG_PREC_BF16;
 
     // per-step weight preparation (parameters change every optimiser step)
-    for (auto &cv : d.convs)
-        HPFG_RETURN_IF(pack_weights_ref(params + cv.w_off, cv.wf, cv.wd, cv.cin, cv.cout, cv.ks, s));
+    if (!tc)
+        for (auto &cv : d.convs)
+            HPFG_RETURN_IF(pack_weights_ref(params + cv.w_off, cv.wf, cv.wd, cv.cin, cv.cout, cv.ks, s));
     if (tc) HPFG_RETURN_IF(tc_pack_all(p, params, s));
     if (use_drop)
         for (int l = 0; l < 5; ++l)
@@ -203,7 +212,10 @@ static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_runnin
     // ---- encoder (model/unet.py:76-82)
     for (int l = 0; l < 5; ++l) {
         const int h = H >> l, w = W >> l, c0 = 2 * l, c1 = 2 * l + 1;
-        if (l == 0)
+        if (l == 0 && tc) {      // network input: fp32 NCHW -> bf16 NHWC padded to 16 channels, then a regular tensor-core layer
+            HPFG_RETURN_IF(pad_to_nhwc16(x, p->xpad, N, p->in_ch, H, W, s));
+            HPFG_RETURN_IF(conv_bn(c0, nhwc_view(p->xpad, H, W, 16), false, none));
+        } else if (l == 0)
             HPFG_RETURN_IF(conv_bn(c0, nchw_view(const_cast<float *>(x), p->in_ch, H, W), true, none));
         else
             HPFG_RETURN_IF(conv_bn(c0, nhwc_view(p->pooled[l], h, w, kFt[l - 1]), false, none));
@@ -236,6 +248,9 @@ static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_runnin
     }
     // ---- out_conv (model/unet.py:99,116): 3x3 16 -> num_classes with bias, logits fp32 NCHW
     ConvLayer &oc = d.convs[22];
+    if (tc)
+        HPFG_RETURN_IF(tc_fprop_logits(p, 22, d.bns[17].raw, xf_of(17, nullptr, 0.f), params + oc.b_off, logits, s));
+    else
     HPFG_RETURN_IF((conv_ref_fprop<T, float>(nhwc_view(d.bns[17].raw, H, W, 16), nchw_view(logits, p->n_cls, H, W), oc.wf,
                                              params + oc.b_off, N, H, W, 16, p->n_cls, 3, xf_of(17, nullptr, 0.f), nullptr,
                                              s)));
@@ -287,7 +302,11 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
     };
 
     // ---- out_conv
-    {
+    if (tc) {   // dlogits: fp32 NCHW -> bf16 NHWC16, then regular tensor-core wgrad / dgrad with Cout padded to 16
+        HPFG_RETURN_IF(pad_to_nhwc16(dlogits, p->dlpad, N, p->n_cls, H, W, s));
+        HPFG_RETURN_IF(wgrad(22, d.bns[17].raw, xf_of(17, nullptr, 0.f), p->dlpad));
+        HPFG_RETURN_IF(dgrad(22, p->dlpad, p->g[0]));
+    } else {
         ConvLayer &oc = d.convs[22];
         HPFG_RETURN_IF((conv_ref_wgrad<T, float>(nhwc_view(d.bns[17].raw, H, W, 16),
                                                  nchw_view(const_cast<float *>(dlogits), p->n_cls, H, W), N, H, W, 16, p->n_cls,
@@ -330,7 +349,9 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
         HPFG_RETURN_IF(wgrad(cB, d.bns[bA].raw, xf_of(bA, bits, kEncDropout[l]), b));
         HPFG_RETURN_IF(dgrad(cB, b, c));                                            // dact(A) in c
         HPFG_RETURN_IF(bnb(bA, c, b, bits, kEncDropout[l]));                        // draw(A) in b
-        if (l == 0) {
+        if (l == 0 && tc) {
+            HPFG_RETURN_IF(wgrad(0, p->xpad, none, b));
+        } else if (l == 0) {
             ConvLayer &cv = d.convs[0];
             HPFG_RETURN_IF((conv_ref_wgrad<float, T>(nchw_view(const_cast<float *>(p->saved_x), p->in_ch, H, W),
                                                      nhwc_view(b, H, W, 16), N, H, W, p->in_ch, 16, 3, none, p->wscratch,

@@ -59,6 +59,7 @@ struct hpfg_unet_plan {
     void *cat[5] = {};                // [1..4]
     void *dcat[5] = {};               // [1..4]
     void *g[4] = {};                  // gradient scratch, N*H*W*16 elements each
+    void *xpad = nullptr, *dlpad = nullptr;   // bf16 NHWC16 copies of the network input / dlogits (bf16 plans)
     uint32_t *dropbits[5] = {};
     float *stats = nullptr;           // BN statistics partials
     int64_t stats_floats = 0;

@@ -1,0 +1,359 @@
+// Tensor-core weight gradient for the bf16 path (sm_100a):
+//
+//   dW[tap][ci][co] = sum over pixels  X_act[pixel + tap][ci] * dY[pixel][co]
+//
+// as nine TMEM-resident accumulators D_tap[co (M, padded to 128), ci block (N)] fed by tcgen05.mma with BOTH
+// operands MN-major: the reduction (K) dimension is the pixel index, which is the slow dimension of NHWC tiles.
+// Staging mirrors the fprop kernel: per 16x8-pixel tile TMA fetches the dY tile and the (16+2)x(8+2) halo of the
+// layer input once; the transform warps re-lay both out as [8-channel chunk][pixel][8 ch] (applying the
+// producer's BatchNorm+LeakyReLU+dropout to X and accumulating the bias gradient from dY on the way); each tap is
+// a shifted descriptor into the one staged X tile.  The pixel dimension is split over persistent CTAs
+// (split-K); each CTA keeps its accumulators in TMEM across all its tiles and writes one fp32 partial, and a
+// fixed-order reduction kernel sums the partials straight into the flat OIHW gradient (deterministic).
+#include <algorithm>
+
+#include "conv_ref.cuh"
+#include "conv_tc.cuh"
+#include "tc_common.cuh"
+
+namespace hpfg {
+
+constexpr int kWgThreads = 384;     // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 transform, 8-11 epilogue
+constexpr int kWgSmemBudget = 222 * 1024;
+
+template <int KS, int NB, int COB>
+struct WgCfg {
+    static constexpr int PAD = KS / 2, KK = KS * KS;
+    static constexpr int HH = kTH + KS - 1, HW = kTW + KS - 1, NPIX_X = HH * HW;
+    static constexpr int X_RAW = NPIX_X * NB * 2, X_CHS = (NPIX_X + 1) * 16, X_OP = (NB / 8) * X_CHS;
+    static constexpr int D_RAW = 128 * COB * 2, D_CHS = (128 + 1) * 16, D_OP = (COB / 8) * D_CHS;
+    static constexpr int al(int v) { return (v + 127) / 128 * 128; }
+    static constexpr int OFF_DOP = 0, OFF_XOP = al(D_OP), OFF_DRAW = OFF_XOP + al(X_OP), OFF_XRAW = OFF_DRAW + al(D_RAW);
+    static constexpr int STAGE_BYTES = OFF_XRAW + al(X_RAW);
+    // the A descriptor always spans 16 row groups (M = 128); with COB < 128 the groups past the real channels read
+    // whatever follows in shared memory (their D rows are never stored) -- keep those reads inside the allocation
+    static constexpr int TAIL_PAD = al((16 - COB / 8) * D_CHS);
+    static constexpr int FIXED_BYTES = 1024 + 2 * 256 * 4 + 128 * 8 * 4 /*dbias reduce*/;
+    static constexpr int STAGES_RAW = (kWgSmemBudget - FIXED_BYTES - TAIL_PAD) / STAGE_BYTES;
+    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_PAD + FIXED_BYTES + 1024;
+    static constexpr int TMEM_COLS = (KK * NB <= 32) ? 32 : (KK * NB <= 64) ? 64 : (KK * NB <= 128) ? 128 : (KK * NB <= 256) ? 256 : 512;
+    static_assert(STAGES >= 2, "need at least a double buffer");
+    static_assert(KK * NB <= 512, "accumulators exceed TMEM");
+};
+
+struct WgParams {
+    const float *scale, *shift;     // producer transform of X (nullptr = identity)
+    const uint8_t *dropbits;
+    float inv_keep;
+    float *scratch;                 // [S][KK*Cin*Cout + Cout] fp32 partials
+    int N, H, W, Cin, Cout, tiles_h, tiles_w, m_tiles, ci_blocks, co_blocks, S;
+};
+
+template <int KS, int NB, int COB>
+__global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
+                                                                 const __grid_constant__ CUtensorMap tmD, const WgParams P) {
+    using C = WgCfg<KS, NB, COB>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *fixed = smem + C::STAGES * C::STAGE_BYTES + C::TAIL_PAD;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(fixed);          // full[S] xf[S] empty[S] done
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fixed + 512);
+    float *s_scale = reinterpret_cast<float *>(fixed + 1024);
+    float *s_shift = s_scale + 256;
+    float *s_bias = s_shift + 256;                                 // [128 threads][... reduced to COB]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t bar_full = ptx::smem_u32(bars), bar_xf = bar_full + 8 * C::STAGES, bar_empty = bar_xf + 8 * C::STAGES;
+    const uint32_t bar_done = bar_empty + 8 * C::STAGES;
+
+    // work assignment: block pair (co block, ci block) x pixel split
+    const int n_bp = P.ci_blocks * P.co_blocks;
+    const int bp = blockIdx.x % n_bp, split = blockIdx.x / n_bp;
+    const bool active = split < P.S;
+    const int cib = bp % P.ci_blocks, cob = bp / P.ci_blocks;
+    const int ci0 = cib * NB, co0 = cob * COB;
+    const int tiles_per_img = P.tiles_h * P.tiles_w;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < C::STAGES; ++s) {
+            ptx::mbar_init(bar_full + 8 * s, 1);
+            ptx::mbar_init(bar_xf + 8 * s, 128);
+            ptx::mbar_init(bar_empty + 8 * s, 1);
+        }
+        ptx::mbar_init(bar_done, 1);
+        ptx::fence_barrier_init();
+        ptx::prefetch_tensormap(&tmX);
+        ptx::prefetch_tensormap(&tmD);
+    }
+    if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+    if (P.scale)
+        for (int i = threadIdx.x; i < P.Cin; i += blockDim.x) { s_scale[i] = P.scale[i]; s_shift[i] = P.shift[i]; }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (active) {
+        if (warp == 0) {
+            if (lane == 0) {     // ============================================================ TMA producer
+                int stage = 0, phase = 0;
+                for (int mt = split; mt < P.m_tiles; mt += P.S) {
+                    const int n_img = mt / tiles_per_img, rem = mt % tiles_per_img;
+                    const int h0 = (rem / P.tiles_w) * kTH, w0 = (rem % P.tiles_w) * kTW;
+                    ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 11);
+                    const uint32_t sb = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+                    ptx::mbar_expect_tx(bar_full + 8 * stage, C::D_RAW + C::X_RAW);
+                    ptx::tma_load_4d(sb + C::OFF_DRAW, &tmD, bar_full + 8 * stage, co0, w0, h0, n_img);
+                    ptx::tma_load_4d(sb + C::OFF_XRAW, &tmX, bar_full + 8 * stage, ci0, w0 - C::PAD, h0 - C::PAD, n_img);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {     // ============================================================ MMA issuer
+                constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, NB, 1, 1);   // both operands MN-major
+                int stage = 0, phase = 0;
+                bool first = true;
+                for (int mt = split; mt < P.m_tiles; mt += P.S) {
+                    ptx::mbar_wait(bar_full + 8 * stage, phase, 13);
+                    ptx::mbar_wait(bar_xf + 8 * stage, phase, 14);
+                    ptx::tc_fence_after();
+                    const uint32_t sb = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
+#pragma unroll 1
+                    for (int j = 0; j < 8; ++j) {            // K step = 16 pixels = tile rows 2j, 2j+1
+                        // A = dY^T: M groups (8 co) SBO = chunk stride; K groups (8 pixels) LBO = 128 B
+                        const uint64_t ad = ptx::umma_desc(sb + C::OFF_DOP + j * 256, 128, C::D_CHS);
+#pragma unroll
+                        for (int tap = 0; tap < C::KK; ++tap) {
+                            const int r = tap / KS, s = tap % KS;
+                            // B = X shifted by the tap: N groups (8 ci) SBO = chunk stride; K groups LBO = one halo row
+                            const uint64_t bd = ptx::umma_desc(sb + C::OFF_XOP + ((2 * j + r) * C::HW + s) * 16, C::HW * 16, C::X_CHS);
+                            ptx::umma_bf16(tmem_base + tap * NB, ad, bd, idesc, (first && j == 0) ? 0u : 1u);
+                        }
+                    }
+                    first = false;
+                    ptx::umma_commit(bar_empty + 8 * stage);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                }
+                ptx::umma_commit(bar_done);
+            }
+        } else if (warp >= 4 && warp < 8) {
+            // ================================================================================ transform warps
+            const int t = threadIdx.x - 128;
+            constexpr int DCH = COB / 8, XCH = NB / 8;
+            float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias gradient of chunk (t % DCH), DCH | 128
+            int stage = 0, phase = 0;
+            for (int mt = split; mt < P.m_tiles; mt += P.S) {
+                const int n_img = mt / tiles_per_img, rem = mt % tiles_per_img;
+                const int h0 = (rem / P.tiles_w) * kTH - C::PAD, w0 = (rem % P.tiles_w) * kTW - C::PAD;
+                ptx::mbar_wait(bar_full + 8 * stage, phase, 15);
+                uint8_t *sb = smem + stage * C::STAGE_BYTES;
+                // dY: [pixel][COB] -> [chunk][pixel][8]
+                for (int i = t; i < 128 * DCH; i += 128) {
+                    const int c = i % DCH, p = i / DCH;
+                    const uint4 v = *reinterpret_cast<const uint4 *>(sb + C::OFF_DRAW + p * (COB * 2) + c * 16);
+                    *reinterpret_cast<uint4 *>(sb + C::OFF_DOP + c * C::D_CHS + p * 16) = v;
+                    float f[8];
+                    unpack8(v, f);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) bsum[k] += f[k];
+                }
+                // X halo: [pixel][NB] -> [chunk][pixel][8] with the producer's BN + LeakyReLU + dropout
+                for (int i = t; i < C::NPIX_X * XCH; i += 128) {
+                    const int c = i % XCH, p = i / XCH;
+                    uint4 v = *reinterpret_cast<const uint4 *>(sb + C::OFF_XRAW + p * (NB * 2) + c * 16);
+                    if (P.scale) {
+                        const int gh = h0 + p / C::HW, gw = w0 + p % C::HW;
+                        if (gh >= 0 && gh < P.H && gw >= 0 && gw < P.W) {
+                            float f[8];
+                            unpack8(v, f);
+                            const int ch = ci0 + c * 8;
+                            uint32_t keep = 0xffu;
+                            if (P.dropbits) keep = P.dropbits[((((size_t)n_img * P.H + gh) * P.W + gw) * P.Cin + ch) >> 3];
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                float a = fmaf(f[k], s_scale[ch + k], s_shift[ch + k]);
+                                a = a > 0.f ? a : kLeakySlope * a;
+                                if (P.dropbits) a = ((keep >> k) & 1u) ? a * P.inv_keep : 0.f;
+                                f[k] = a;
+                            }
+                            v = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+                        } else {
+                            v = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                    }
+                    *reinterpret_cast<uint4 *>(sb + C::OFF_XOP + c * C::X_CHS + p * 16) = v;
+                }
+                ptx::fence_proxy_async_smem();
+                ptx::mbar_arrive(bar_xf + 8 * stage);
+                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            }
+            // bias gradient: thread t owns chunk (t % DCH); fixed-order reduce over the 128/DCH threads of a chunk
+            if (cib == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k) s_bias[t * 8 + k] = bsum[k];
+                ptx::named_bar_sync(2, 128);
+                if (t < COB) {
+                    const int c = t / 8, k = t % 8;
+                    float s = 0.f;
+                    for (int u = c; u < 128; u += DCH) s += s_bias[u * 8 + k];
+                    if (co0 + t < P.Cout)
+                        P.scratch[(size_t)split * ((size_t)C::KK * P.Cin * P.Cout + P.Cout) + (size_t)C::KK * P.Cin * P.Cout + co0 + t] = s;
+                }
+            }
+        } else if (warp >= 8) {
+            // ================================================================================ epilogue (once)
+            const int q = warp & 3, row = q * 32 + lane, co = co0 + row;
+            ptx::mbar_wait(bar_done, 0, 16);
+            ptx::tc_fence_after();
+            float *dst = P.scratch + (size_t)split * ((size_t)C::KK * P.Cin * P.Cout + P.Cout);
+#pragma unroll 1
+            for (int tap = 0; tap < C::KK; ++tap) {
+#pragma unroll 1
+                for (int n0 = 0; n0 < NB; n0 += 16) {
+                    uint32_t r[16];
+                    ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tap * NB + n0, r);
+                    ptx::tmem_ld_wait();
+                    if (row < COB && co < P.Cout) {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j)
+                            dst[((size_t)tap * P.Cin + ci0 + n0 + j) * P.Cout + co] = __uint_as_float(r[j]);
+                    }
+                }
+            }
+        }
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+    }
+}
+
+// fixed-order sum of the split partials, scattered into the flat OIHW gradient (+ bias gradient)
+__global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const float *__restrict__ scratch, int S, int Cin, int Cout, int KK,
+                                                              int cin_real, int cout_real, float *__restrict__ dw_oihw,
+                                                              float *__restrict__ dbias, int accumulate) {
+    const int64_t per = (int64_t)KK * Cin * Cout + Cout;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += (int64_t)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < S; ++k) s += scratch[(int64_t)k * per + e];
+        if (e < (int64_t)KK * Cin * Cout) {
+            const int co = (int)(e % Cout), ci = (int)((e / Cout) % Cin), tap = (int)(e / ((int64_t)Cout * Cin));
+            if (co < cout_real && ci < cin_real) {           // padded channels carry no parameter
+                float *d = dw_oihw + ((int64_t)co * cin_real + ci) * KK + tap;
+                *d = accumulate ? *d + s : s;
+            }
+        } else if (dbias && e - (int64_t)KK * Cin * Cout < cout_real) {
+            float *d = dbias + (e - (int64_t)KK * Cin * Cout);
+            *d = accumulate ? *d + s : s;
+        }
+    }
+}
+
+static void wg_shape(int N, int H, int W, int Cin, int Cout, int &NB, int &COB, int &ci_blocks, int &co_blocks, int &S, int &m_tiles) {
+    NB = Cin == 16 ? 16 : 32;
+    COB = std::min(Cout, 128);
+    ci_blocks = Cin / NB;
+    co_blocks = Cout / COB;
+    m_tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
+    S = std::max(1, std::min(kNumSMs / (ci_blocks * co_blocks), m_tiles));
+}
+
+int64_t tc_wgrad_scratch_floats(int N, int H, int W, int Cin, int Cout, int KS) {
+    int NB, COB, cib, cob, S, mt;
+    wg_shape(N, H, W, Cin, Cout, NB, COB, cib, cob, S, mt);
+    return (int64_t)S * ((int64_t)KS * KS * Cin * Cout + Cout);
+}
+
+template <int KS, int NB, int COB>
+static int wg_launch(const CUtensorMap &mx, const CUtensorMap &md, const WgParams &P, cudaStream_t s) {
+    using C = WgCfg<KS, NB, COB>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<KS, NB, COB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        attr_set = true;
+    }
+    const int grid = P.ci_blocks * P.co_blocks * P.S;
+    tc_wgrad_kernel<KS, NB, COB><<<grid, kWgThreads, C::SMEM_BYTES, s>>>(mx, md, P);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+template <int KS>
+static int wg_dispatch(int NB, int COB, const CUtensorMap &mx, const CUtensorMap &md, const WgParams &P, cudaStream_t s) {
+#define HPFG_WG_CASE(nb, cob) \
+    if (NB == nb && COB == cob) return wg_launch<KS, nb, cob>(mx, md, P, s);
+    HPFG_WG_CASE(16, 16) HPFG_WG_CASE(16, 32) HPFG_WG_CASE(16, 64) HPFG_WG_CASE(16, 128)
+    HPFG_WG_CASE(32, 16) HPFG_WG_CASE(32, 32) HPFG_WG_CASE(32, 64) HPFG_WG_CASE(32, 128)
+#undef HPFG_WG_CASE
+    set_error("tc wgrad: no kernel for NB=" + std::to_string(NB) + " COB=" + std::to_string(COB));
+    return HPFG_ERR_UNSUPPORTED;
+}
+
+int tc_wgrad_run(int ks, int N, int H, int W, int Cin, int Cout, int cin_real, int cout_real, const void *x, LoadXform xf, const void *dy, float *scratch,
+                 int64_t scratch_floats, float *dw_oihw, float *dbias, int accumulate, cudaStream_t s) {
+    ProfScope _prof(PROF_WGRAD_TC, s);
+    int NB, COB;
+    WgParams P{};
+    wg_shape(N, H, W, Cin, Cout, NB, COB, P.ci_blocks, P.co_blocks, P.S, P.m_tiles);
+    HPFG_REQUIRE(tc_wgrad_scratch_floats(N, H, W, Cin, Cout, ks) <= scratch_floats, "tc_wgrad: scratch too small");
+    CUtensorMap mx, md;
+    HPFG_RETURN_IF(make_map(&mx, x, N, H, W, Cin, NB, kTW + ks - 1, kTH + ks - 1));
+    HPFG_RETURN_IF(make_map(&md, dy, N, H, W, Cout, COB, kTW, kTH));
+    P.scale = xf.scale; P.shift = xf.shift;
+    P.dropbits = reinterpret_cast<const uint8_t *>(xf.drop.bits); P.inv_keep = xf.drop.inv_keep;
+    P.scratch = scratch;
+    P.N = N; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
+    P.tiles_h = (H + kTH - 1) / kTH; P.tiles_w = (W + kTW - 1) / kTW;
+    HPFG_RETURN_IF(ks == 3 ? wg_dispatch<3>(NB, COB, mx, md, P, s) : wg_dispatch<1>(NB, COB, mx, md, P, s));
+    const int64_t per = (int64_t)ks * ks * Cin * Cout + Cout;
+    const int blocks = (int)std::min<int64_t>((per + 255) / 256, (int64_t)kNumSMs * 4);
+    tc_wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(scratch, P.S, Cin, Cout, ks * ks, cin_real, cout_real, dw_oihw, dbias, accumulate);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+}  // namespace hpfg
+
+namespace hpfg {
+__global__ void __launch_bounds__(256) pad_to_nhwc16_kernel(const float *__restrict__ src, uint4 *__restrict__ dst, int N, int C, int H, int W) {
+    const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t n = i / HW, pix = i % HW;
+        float v[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) v[c] = c < C ? __ldg(src + (n * C + c) * HW + pix) : 0.f;
+        dst[2 * i] = make_uint4(pack2(v[0], v[1]), pack2(v[2], v[3]), pack2(v[4], v[5]), pack2(v[6], v[7]));
+        dst[2 * i + 1] = make_uint4(pack2(v[8], v[9]), pack2(v[10], v[11]), pack2(v[12], v[13]), pack2(v[14], v[15]));
+    }
+}
+int pad_to_nhwc16(const float *src_nchw, void *dst, int N, int C, int H, int W, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
+    const int64_t total = (int64_t)N * H * W;
+    const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 16);
+    pad_to_nhwc16_kernel<<<blocks, 256, 0, s>>>(src_nchw, reinterpret_cast<uint4 *>(dst), N, C, H, W);
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+}  // namespace hpfg
+
+// ---- layer-isolated test hook -------------------------------------------------------------------------------
+using namespace hpfg;
+extern "C" int hpfg_wgrad_tc_debug(int N, int H, int W, int cin, int cout, int ks, const void *x_bf16_nhwc,
+                                   const void *dy_bf16_nhwc, const float *scale, const float *shift, float *dw_oihw,
+                                   float *dbias, void *stream) {
+    HPFG_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && (ks == 1 || ks == 3), "hpfg_wgrad_tc_debug: unsupported shape");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t nf = tc_wgrad_scratch_floats(N, H, W, cin, cout, ks);
+    float *scratch = nullptr;
+    HPFG_CUDA_CHECK(cudaMalloc(&scratch, (size_t)nf * 4));
+    LoadXform xf{};
+    xf.scale = scale; xf.shift = shift; xf.drop.bits = nullptr; xf.drop.inv_keep = 1.f;
+    const int rc = tc_wgrad_run(ks, N, H, W, cin, cout, cin, cout, x_bf16_nhwc, xf, dy_bf16_nhwc, scratch, nf, dw_oihw, dbias, 0, s);
+    cudaStreamSynchronize(s);
+    cudaFree(scratch);
+    if (rc == HPFG_OK) HPFG_CUDA_CHECK(cudaGetLastError());
+    return rc;
+}

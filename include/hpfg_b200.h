@@ -52,7 +52,7 @@ int64_t hpfg_launch_count(void);
 /* Optional device timing per kernel category (bench.py's roofline leg): between begin and end every host-side
  * launcher brackets its kernels with CUDA events on the caller's stream; end synchronises and returns the summed
  * milliseconds and call counts for categories {0 tensor-core conv, 1 CUDA-core conv, 2 CUDA-core wgrad, 3 BN /
- * pool / upsample glue, 4 loss, 5 SGD/EMA, 6 weight packing, 7 unused}: double[8], int64[8] on the host. */
+ * pool / upsample glue, 4 loss, 5 SGD/EMA, 6 weight packing, 7 tensor-core wgrad}: double[8], int64[8] on the host. */
 int hpfg_profile_begin(void);
 int hpfg_profile_end(double *ms_per_category_host, int64_t *calls_per_category_host);
 
@@ -111,6 +111,12 @@ int hpfg_unet_debug_tap(hpfg_unet_plan_t plan, const char *name, float *out_nchw
 int hpfg_conv_tc_debug(int op, int batch, int height, int width, int cin, int cout, int ksize,
                        const void *in_bf16_nhwc, const float *w_oihw, const float *bias, const float *scale,
                        const float *shift, void *out_bf16_nhwc, float *stats_out, void *stream);
+
+/* Same for the tensor-core weight-gradient kernel: dw_oihw[cout,cin,k,k] = sum_pixels act(x)[pixel+tap] * dy[pixel],
+ * dbias[cout] = sum_pixels dy; x is transformed on load by scale/shift (+LeakyReLU) when given. */
+int hpfg_wgrad_tc_debug(int batch, int height, int width, int cin, int cout, int ksize, const void *x_bf16_nhwc,
+                        const void *dy_bf16_nhwc, const float *scale, const float *shift, float *dw_oihw, float *dbias,
+                        void *stream);
 
 /* ---- fused SSL loss (forward value + d loss / d logits) ---------------------------------------------
  * student: fp32 NCHW [n_l+n_u, C, H, W] logits.  labels: int64 [n_l, H, W] (255 = ignored by CE only).

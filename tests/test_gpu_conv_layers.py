@@ -84,3 +84,40 @@ def test_fprop_full_resolution():
     ref = F.conv2d(x.to(torch.bfloat16).float(), wt.to(torch.bfloat16).float(), padding=1)
     assert rel_l2(got, ref) < 6e-3
     assert torch.allclose(stats[16:], (ref * ref).sum(dim=(0, 2, 3)), rtol=1e-3)
+
+
+@pytest.mark.parametrize("cin,cout,ks", SHAPES)
+@pytest.mark.parametrize("n,h,w", [(2, 32, 16), (3, 24, 20)])
+def test_wgrad(cin, cout, ks, n, h, w):
+    g = torch.Generator(device="cpu").manual_seed(cin * 77 + cout + ks)
+    x = torch.randn(n, cin, h, w, generator=g).to(DEV)
+    dy = torch.randn(n, cout, h, w, generator=g).to(DEV)
+    scale = (0.5 + torch.rand(cin, generator=g)).to(DEV)
+    shift = (torch.rand(cin, generator=g) - 0.5).to(DEV)
+    dw = torch.empty(cout, cin, ks, ks, device=DEV)
+    db = torch.empty(cout, device=DEV)
+    xn, dyn = _nhwc_bf16(x), _nhwc_bf16(dy)          # keep alive: ctypes pointers do not hold references
+    L.check(L.lib().hpfg_wgrad_tc_debug(n, h, w, cin, cout, ks, L.ptr(xn), L.ptr(dyn), L.ptr(scale),
+                                        L.ptr(shift), L.ptr(dw), L.ptr(db), L.stream_ptr(torch.device(DEV))), "wgrad")
+    xb, dyb = x.to(torch.bfloat16).float(), dy.to(torch.bfloat16).float()
+    act = F.leaky_relu(xb * scale.view(1, -1, 1, 1) + shift.view(1, -1, 1, 1), 0.01).to(torch.bfloat16).float()
+    act.requires_grad_(False)
+    wref = torch.zeros(cout, cin, ks, ks, device=DEV, requires_grad=True)
+    bref = torch.zeros(cout, device=DEV, requires_grad=True)
+    (F.conv2d(act, wref, bref, padding=ks // 2) * dyb).sum().backward()
+    assert rel_l2(dw, wref.grad) < 2e-3, "dW"
+    assert rel_l2(db, bref.grad) < 2e-3, "dbias"
+
+
+def test_wgrad_full_resolution():
+    g = torch.Generator(device="cpu").manual_seed(5)
+    x = torch.randn(4, 32, 224, 224, generator=g).to(DEV)
+    dy = torch.randn(4, 16, 224, 224, generator=g).to(DEV)
+    dw = torch.empty(16, 32, 3, 3, device=DEV)
+    db = torch.empty(16, device=DEV)
+    xn, dyn = _nhwc_bf16(x), _nhwc_bf16(dy)
+    L.check(L.lib().hpfg_wgrad_tc_debug(4, 224, 224, 32, 16, 3, L.ptr(xn), L.ptr(dyn), None, None,
+                                        L.ptr(dw), L.ptr(db), L.stream_ptr(torch.device(DEV))), "wgrad")
+    wref = torch.zeros(16, 32, 3, 3, device=DEV, requires_grad=True)
+    (F.conv2d(x.to(torch.bfloat16).float(), wref, padding=1) * dy.to(torch.bfloat16).float()).sum().backward()
+    assert rel_l2(dw, wref.grad) < 2e-3
