@@ -36,6 +36,7 @@ SIGNATURES = {
     "hpfg_unet_bucket_wait": (c_int, [c_vp, c_int, c_vp]),
     "hpfg_unet_debug_tap": (c_int, [c_vp, ctypes.c_char_p, c_vp, c_i64, c_vp]),
     "hpfg_conv_tc_debug": (c_int, [c_int] * 7 + [c_vp] * 8),
+    "hpfg_conv_tc_bench": (c_int, [c_int] * 8 + [ctypes.POINTER(c_f), c_vp]),
     "hpfg_wgrad_tc_debug": (c_int, [c_int] * 6 + [c_vp] * 7),
     "hpfg_ssl_loss_workspace_bytes": (c_i64, [c_int] * 6),
     "hpfg_ssl_loss": (c_int, [c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_f,

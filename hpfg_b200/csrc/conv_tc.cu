@@ -5,17 +5,19 @@
 //        A_tap[128 pixels, 16 ch] (smem, K-major)  x  W_tap[BN, 16 ch] (smem, K-major)
 //
 // One CTA tile = 16 rows x 8 columns of output pixels of one image.  The (16+2)x(8+2) input halo of a channel
-// chunk is fetched ONCE by TMA (4-D box over [C,W,H,N], out-of-bounds = zero = the conv padding), re-laid out by
-// the transform warps into "channel-chunk major" order [chunk of 8 ch][halo pixel][8 ch] while the producer's
-// BatchNorm + LeakyReLU + dropout are applied (model/unet.py:17-25 fused into the consumer's loader), and the
-// nine taps are nine UMMA descriptors into that ONE staged tile: start address shifted by (r*10+s)*16 bytes,
-// SBO = one halo row.  Input bytes therefore cross L2->SMEM once per tile instead of nine times.
+// chunk is fetched ONCE by TMA through a 5-D "chunked" tensor map (8 ch, W, H, C/8, N: the chunk dimension has a
+// 16-byte stride), so the bytes land directly in the UMMA operand order [chunk of 8 ch][halo pixel][8 ch];
+// out-of-bounds = zero = the conv padding.  When the producer's BatchNorm + LeakyReLU + dropout are fused into
+// this consumer's loader (model/unet.py:17-25), eight transform warps apply them in place.  The nine taps are nine
+// UMMA descriptors into that ONE staged tile: start address shifted by (r*10+s)*16 bytes, SBO = one halo row.
+// Input bytes therefore cross L2->SMEM once per tile instead of nine times.
 // Epilogue (4 warps): tcgen05.ld -> per-channel sum / sum-of-squares partials for train-mode BatchNorm
 // (shuffle butterfly) -> bf16 NHWC store.  fprop, dgrad (flipped/transposed packed weights) and the 1x1
 // convolutions of the up-blocks all run through this kernel.
 #include "conv_tc.cuh"
 
 #include <algorithm>
+#include <cstdlib>
 #include <map>
 #include <tuple>
 
@@ -24,28 +26,31 @@
 namespace hpfg {
 
 // ------------------------------------------------------------------------------------------ configuration
-constexpr int kTcThreads = 384;             // 12 warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 transform, 8-11 epilogue
-constexpr int kMaxStages = 6;
+constexpr int kXfThreads = 256;            // loader-transform threads (warps 4-11)
+constexpr int kTcThreads = 128 + kXfThreads + 128;   // + warps 0-3 (TMA, MMA, TMEM alloc, idle) + 4 epilogue warps
+constexpr int kMaxStages = 12;
 constexpr int kSmemBudget = 200 * 1024;
 
-template <int KS, int KC, int BN>
+template <int KS, int KC, int BN, bool RES>
 struct TcCfg {
     static constexpr int PAD = KS / 2, KK = KS * KS;
     static constexpr int HH = kTH + KS - 1, HW = kTW + KS - 1;     // halo tile
     static constexpr int NPIX = HH * HW;
     static constexpr int NCH = KC / 8;                             // 16-byte channel chunks per stage
-    static constexpr int RAW_BYTES = NPIX * KC * 2;                // TMA destination, [pixel][KC]
-    static constexpr int CH_STRIDE = (NPIX + 1) * 16;              // operand tile: [chunk][pixel][8ch], padded (bank spread)
+    // operand tile [chunk][halo pixel][8 ch], written in exactly this order by TMA (5-D chunked tensor map)
+    static constexpr int CH_STRIDE = NPIX * 16;
     static constexpr int OP_BYTES = NCH * CH_STRIDE;
     static constexpr int B_TAP_BYTES = KC * BN * 2;                // [KC/8][BN][8]
     static constexpr int B_BYTES = KK * B_TAP_BYTES;
     static constexpr int al(int v) { return (v + 127) / 128 * 128; }
-    static constexpr int OFF_OP = al(RAW_BYTES), OFF_B = OFF_OP + al(OP_BYTES);
-    static constexpr int STAGE_BYTES = OFF_B + al(B_BYTES);
+    static constexpr int OFF_B = al(OP_BYTES);
+    // RES: the whole packed weight of the layer (one k-chunk, one n-block) stays resident in shared memory
+    static constexpr int STAGE_BYTES = OFF_B + (RES ? 0 : al(B_BYTES));
+    static constexpr int RESB_BYTES = RES ? al(B_BYTES) : 0;
     static constexpr int FIXED_BYTES = 1024 /*barriers*/ + 2 * 256 * 4 /*scale,shift*/ + 4 * 2 * BN * 4 /*stat partials*/;
-    static constexpr int STAGES_RAW = (kSmemBudget - FIXED_BYTES) / STAGE_BYTES;
+    static constexpr int STAGES_RAW = (kSmemBudget - FIXED_BYTES - RESB_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > kMaxStages ? kMaxStages : STAGES_RAW;
-    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + FIXED_BYTES + 1024 /*alignment slack*/;
+    static constexpr int SMEM_BYTES = RESB_BYTES + STAGES * STAGE_BYTES + FIXED_BYTES + 1024 /*alignment slack*/;
     static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
     static_assert(STAGES >= 2, "need at least a double buffer");
 };
@@ -57,10 +62,33 @@ struct TcConvParams {
     const float *scale, *shift;   // per input channel (producer's fused BN affine) or nullptr = identity
     const uint8_t *dropbits;  // producer's dropout keep bits, NHWC bit order, or nullptr
     float inv_keep;
-    float *stats;             // [m_tiles][2*Cout] partial sums or nullptr
+    float *stats;             // [gridDim.x][2*Cout] per-CTA partial sums (sum | sum of squares) or nullptr
     float *out_nchw;          // if set: write fp32 NCHW [N,out_c_real,H,W] (+bias) instead of bf16 NHWC (out_conv logits)
     int out_c_real;
     int N, H, W, Cin, Cout, tiles_h, tiles_w, m_tiles, n_blocks, k_chunks;
+};
+
+// Walks the m-tiles this CTA owns (mt0, mt0+step, ...) without per-tile integer divisions.
+struct TileIter {
+    int n_img, th, tw, dn, dh, dw;
+    __device__ __forceinline__ void init(int mt, int step, int tiles_h, int tiles_w) {
+        const int tpi = tiles_h * tiles_w;
+        n_img = mt / tpi;
+        int r = mt % tpi;
+        th = r / tiles_w;
+        tw = r % tiles_w;
+        dn = step / tpi;
+        r = step % tpi;
+        dh = r / tiles_w;
+        dw = r % tiles_w;
+    }
+    __device__ __forceinline__ void next(int tiles_h, int tiles_w) {
+        tw += dw;
+        if (tw >= tiles_w) { tw -= tiles_w; ++th; }
+        th += dh;
+        if (th >= tiles_h) { th -= tiles_h; ++n_img; }
+        n_img += dn;
+    }
 };
 
 // Reduce 16 per-lane values over the 32 lanes of a warp with 16 shuffles (recursive halving); afterwards every
@@ -91,13 +119,17 @@ __device__ __forceinline__ float butterfly16(const float (&v)[16], int lane) {
     return d + __shfl_xor_sync(0xffffffffu, d, 1);
 }
 
-template <int KS, int KC, int BN>
+// warps: 0 TMA producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-11 transform (only when a loader transform is
+// fused), 12-15 epilogue.  Per-tile instruction counts of the single-thread roles are kept minimal: the MMA thread
+// patches precomputed descriptor words with compile-time offsets and never computes tile coordinates.
+template <int KS, int KC, int BN, bool RES>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const TcConvParams P) {
-    using C = TcCfg<KS, KC, BN>;
+    using C = TcCfg<KS, KC, BN, RES>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t *stage_base = smem;
-    uint8_t *fixed = smem + C::STAGES * C::STAGE_BYTES;
+    uint8_t *res_b = smem;                                         // resident weights (RES only)
+    uint8_t *stage_base = smem + C::RESB_BYTES;
+    uint8_t *fixed = stage_base + C::STAGES * C::STAGE_BYTES;
     uint64_t *bars = reinterpret_cast<uint64_t *>(fixed);          // full[S] xf[S] empty[S] tfull[2] tempty[2]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fixed + 512);
     float *s_scale = reinterpret_cast<float *>(fixed + 1024);
@@ -107,11 +139,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = ptx::smem_u32(bars), bar_xf = bar_full + 8 * C::STAGES, bar_empty = bar_xf + 8 * C::STAGES;
     const uint32_t bar_tfull = bar_empty + 8 * C::STAGES, bar_tempty = bar_tfull + 16;
+    const uint32_t stage_u32 = ptx::smem_u32(stage_base);
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(bar_full + 8 * s, 1);
-            ptx::mbar_init(bar_xf + 8 * s, 128);
+            ptx::mbar_init(bar_xf + 8 * s, kXfThreads);
             ptx::mbar_init(bar_empty + 8 * s, 1);
         }
         for (int a = 0; a < 2; ++a) {
@@ -129,119 +162,150 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
+    // this CTA's work items: fixed n-block, m-tiles mt0, mt0+mstep, ... (n_blocks divides the grid)
     const int total_work = P.m_tiles * P.n_blocks;
-    const int tiles_per_img = P.tiles_h * P.tiles_w;
+    const int nb = blockIdx.x % P.n_blocks, mt0 = blockIdx.x / P.n_blocks, mstep = gridDim.x / P.n_blocks;
+    const int n_work = (total_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    const bool xform = P.scale != nullptr;
 
     if (warp == 0) {
-        // ================================================================= TMA producer (one lane)
-        if (lane == 0) {
+        // ================================================================= TMA producer (warp-uniform, one lane issues)
+        {
+            TileIter ti;
+            ti.init(mt0, mstep, P.tiles_h, P.tiles_w);
             int stage = 0, phase = 0;
-            for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-                const int nb = work % P.n_blocks, mt = work / P.n_blocks;
-                const int n_img = mt / tiles_per_img, rem = mt % tiles_per_img;
-                const int h0 = (rem / P.tiles_w) * kTH, w0 = (rem % P.tiles_w) * kTW;
+            const bf16 *bsrc = P.bpk + (size_t)nb * P.k_chunks * (C::B_BYTES / 2);
+            for (int it = 0; it < n_work; ++it) {
+                const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * kTW - C::PAD;
                 for (int kc = 0; kc < P.k_chunks; ++kc) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
-                    const uint32_t sb = ptx::smem_u32(stage_base + stage * C::STAGE_BYTES);
-                    ptx::mbar_expect_tx(bar_full + 8 * stage, C::RAW_BYTES + C::B_BYTES);
-                    ptx::tma_load_4d(sb, &tmA, bar_full + 8 * stage, kc * KC, w0 - C::PAD, h0 - C::PAD, n_img);
-                    ptx::bulk_load(sb + C::OFF_B, P.bpk + ((size_t)nb * P.k_chunks + kc) * (C::B_BYTES / 2), C::B_BYTES,
-                                   bar_full + 8 * stage);
+                    const uint32_t sb = stage_u32 + stage * C::STAGE_BYTES, fb = bar_full + 8 * stage;
+                    if (ptx::elect_one()) {
+                        if (RES) {       // weights ride along with the first tile only and stay resident
+                            ptx::mbar_expect_tx(fb, C::OP_BYTES + (it == 0 ? C::B_BYTES : 0));
+                            if (it == 0) ptx::bulk_load(ptx::smem_u32(res_b), P.bpk, C::B_BYTES, fb);
+                        } else {
+                            ptx::mbar_expect_tx(fb, C::OP_BYTES + C::B_BYTES);
+                            ptx::bulk_load(sb + C::OFF_B, bsrc + (size_t)kc * (C::B_BYTES / 2), C::B_BYTES, fb);
+                        }
+                        ptx::tma_load_5d(sb, &tmA, fb, 0, w0, h0, kc * C::NCH, ti.n_img);
+                    }
+                    __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
+                ti.next(P.tiles_h, P.tiles_w);
             }
         }
     } else if (warp == 1) {
-        // ================================================================= MMA issuer (one lane)
-        if (lane == 0) {
+        // ================================================================= MMA issuer (warp-uniform, one lane issues)
+        {
             constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN, 0, 0);
-            int stage = 0, phase = 0, it = 0;
-            for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+            // descriptor words: hi = SBO | version, lo = (addr >> 4) | LBO << 16; per-MMA offsets are compile-time adds
+            constexpr uint32_t a_hi = (uint32_t)((C::HW * 16) >> 4) | (1u << 14), b_hi = (uint32_t)(128 >> 4) | (1u << 14);
+            const uint32_t a_lo0 = ((stage_u32 >> 4) & 0x3FFFu) | ((uint32_t)(C::CH_STRIDE >> 4) << 16);
+            const uint32_t b_lo0 = (((RES ? ptx::smem_u32(res_b) : stage_u32 + C::OFF_B) >> 4) & 0x3FFFu) | ((uint32_t)((BN * 16) >> 4) << 16);
+            int stage = 0, phase = 0;
+            for (int it = 0; it < n_work; ++it) {
                 const int acc = it & 1, acc_phase = (it >> 1) & 1;
                 ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, 2);
                 ptx::tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BN;
                 for (int kc = 0; kc < P.k_chunks; ++kc) {
                     ptx::mbar_wait(bar_full + 8 * stage, phase, 3);
-                    ptx::mbar_wait(bar_xf + 8 * stage, phase, 4);
+                    if (xform) ptx::mbar_wait(bar_xf + 8 * stage, phase, 4);
                     ptx::tc_fence_after();
-                    const uint32_t sb = ptx::smem_u32(stage_base + stage * C::STAGE_BYTES);
+                    const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
+                    const uint32_t b_lo = RES ? b_lo0 : b_lo0 + stage * (C::STAGE_BYTES >> 4);
+                    if (ptx::elect_one()) {
 #pragma unroll
                     for (int tap = 0; tap < C::KK; ++tap) {
-                        const int r = tap / KS, s = tap % KS;
 #pragma unroll
                         for (int kk = 0; kk < KC / 16; ++kk) {
-                            const uint64_t ad = ptx::umma_desc(sb + C::OFF_OP + 2 * kk * C::CH_STRIDE + (r * C::HW + s) * 16,
-                                                               C::CH_STRIDE, C::HW * 16);
-                            const uint64_t bd = ptx::umma_desc(sb + C::OFF_B + tap * C::B_TAP_BYTES + 2 * kk * BN * 16, BN * 16, 128);
+                            constexpr int dummy = 0;
+                            (void)dummy;
+                            const uint32_t ao = (uint32_t)((2 * kk * C::CH_STRIDE + ((tap / KS) * C::HW + (tap % KS)) * 16) >> 4);
+                            const uint32_t bo = (uint32_t)((tap * C::B_TAP_BYTES + 2 * kk * BN * 16) >> 4);
+                            const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + ao);
+                            const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + bo);
                             ptx::umma_bf16(d_tmem, ad, bd, idesc, (kc | tap | kk) != 0);
                         }
                     }
                     ptx::umma_commit(bar_empty + 8 * stage);      // smem slot reusable once these MMAs retire
+                    if (kc == P.k_chunks - 1) ptx::umma_commit(bar_tfull + 8 * acc);   // accumulator complete -> epilogue
+                    }
+                    __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(bar_tfull + 8 * acc);            // accumulator complete -> epilogue
             }
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ================================================================= transform / re-layout warps
-        const int t = threadIdx.x - 128;
-        int stage = 0, phase = 0;
-        for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-            const int mt = work / P.n_blocks;
-            const int n_img = mt / tiles_per_img, rem = mt % tiles_per_img;
-            const int h0 = (rem / P.tiles_w) * kTH - C::PAD, w0 = (rem % P.tiles_w) * kTW - C::PAD;
-            for (int kc = 0; kc < P.k_chunks; ++kc) {
-                ptx::mbar_wait(bar_full + 8 * stage, phase, 5);
-                const uint8_t *raw = stage_base + stage * C::STAGE_BYTES;
-                uint8_t *op = stage_base + stage * C::STAGE_BYTES + C::OFF_OP;
-                for (int i = t; i < C::NPIX * C::NCH; i += 128) {
-                    const int c = i % C::NCH, p = i / C::NCH;
-                    uint4 v = *reinterpret_cast<const uint4 *>(raw + p * (KC * 2) + c * 16);
-                    if (P.scale) {
+    } else if (warp >= 4 && warp < 4 + kXfThreads / 32) {
+        // ================================================================= loader-transform warps (in place)
+        if (xform) {
+            const int t = threadIdx.x - 128;
+            TileIter ti;
+            ti.init(mt0, mstep, P.tiles_h, P.tiles_w);
+            int stage = 0, phase = 0;
+            for (int it = 0; it < n_work; ++it) {
+                const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * kTW - C::PAD;
+                const size_t img_px = (size_t)ti.n_img * P.H;
+                for (int kc = 0; kc < P.k_chunks; ++kc) {
+                    ptx::mbar_wait(bar_full + 8 * stage, phase, 5);
+                    const uint32_t op = stage_u32 + stage * C::STAGE_BYTES;
+                    for (int i = t; i < C::NPIX * C::NCH; i += kXfThreads) {
+                        const int c = i / C::NPIX, p = i % C::NPIX;
                         const int gh = h0 + p / C::HW, gw = w0 + p % C::HW;
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);     // conv zero padding applies AFTER the activation
                         if (gh >= 0 && gh < P.H && gw >= 0 && gw < P.W) {
+                            v = ptx::lds128(op + i * 16);
                             float f[8];
                             unpack8(v, f);
                             const int ch = kc * KC + c * 8;
                             uint32_t keep = 0xffu;
-                            if (P.dropbits) keep = P.dropbits[((((size_t)n_img * P.H + gh) * P.W + gw) * P.Cin + ch) >> 3];
+                            if (P.dropbits) keep = P.dropbits[(((img_px + gh) * P.W + gw) * P.Cin + ch) >> 3];
+                            const float4 sc0 = *reinterpret_cast<const float4 *>(s_scale + ch), sc1 = *reinterpret_cast<const float4 *>(s_scale + ch + 4);
+                            const float4 sh0 = *reinterpret_cast<const float4 *>(s_shift + ch), sh1 = *reinterpret_cast<const float4 *>(s_shift + ch + 4);
+                            const float scl[8] = {sc0.x, sc0.y, sc0.z, sc0.w, sc1.x, sc1.y, sc1.z, sc1.w};
+                            const float shf[8] = {sh0.x, sh0.y, sh0.z, sh0.w, sh1.x, sh1.y, sh1.z, sh1.w};
 #pragma unroll
                             for (int j = 0; j < 8; ++j) {
-                                float a = fmaf(f[j], s_scale[ch + j], s_shift[ch + j]);
+                                float a = fmaf(f[j], scl[j], shf[j]);
                                 a = a > 0.f ? a : kLeakySlope * a;
                                 if (P.dropbits) a = ((keep >> j) & 1u) ? a * P.inv_keep : 0.f;
                                 f[j] = a;
                             }
                             v = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-                        } else {
-                            v = make_uint4(0u, 0u, 0u, 0u);       // conv zero padding applies AFTER the activation
                         }
+                        ptx::sts128(op + i * 16, v);
                     }
-                    *reinterpret_cast<uint4 *>(op + c * C::CH_STRIDE + p * 16) = v;
+                    ptx::fence_proxy_async_smem();
+                    ptx::mbar_arrive(bar_xf + 8 * stage);
+                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::fence_proxy_async_smem();
-                ptx::mbar_arrive(bar_xf + 8 * stage);
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                ti.next(P.tiles_h, P.tiles_w);
             }
         }
-    } else if (warp >= 8) {
+    } else if (warp >= 4 + kXfThreads / 32) {
         // ================================================================= epilogue warps
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int m = q * 32 + lane;                 // output pixel within the tile
-        const int et = threadIdx.x - 256;
-        int it = 0;
-        for (int work = blockIdx.x; work < total_work; work += gridDim.x, ++it) {
+        const int et = threadIdx.x - (128 + kXfThreads);
+        // BatchNorm statistics: every lane keeps the running sum of column col16(lane) of each 16-column group over
+        // ALL tiles of this CTA -> one partial row per CTA
+        float run1[BN / 16], run2[BN / 16];
+#pragma unroll
+        for (int gidx = 0; gidx < BN / 16; ++gidx) run1[gidx] = run2[gidx] = 0.f;
+        TileIter ti;
+        ti.init(mt0, mstep, P.tiles_h, P.tiles_w);
+        for (int it = 0; it < n_work; ++it) {
             const int acc = it & 1, acc_phase = (it >> 1) & 1;
-            const int nb = work % P.n_blocks, mt = work / P.n_blocks;
-            const int n_img = mt / tiles_per_img, rem = mt % tiles_per_img;
-            const int gh = (rem / P.tiles_w) * kTH + m / kTW, gw = (rem % P.tiles_w) * kTW + m % kTW;
+            const int gh = ti.th * kTH + m / kTW, gw = ti.tw * kTW + m % kTW;
             const bool valid = gh < P.H && gw < P.W;
+            bf16 *orow = P.out + (((size_t)ti.n_img * P.H + gh) * P.W + gw) * P.Cout + nb * BN;
             ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase, 6);
             ptx::tc_fence_after();
-            bf16 *orow = P.out + (((size_t)n_img * P.H + gh) * P.W + gw) * P.Cout + nb * BN;
-#pragma unroll 1
-            for (int n0 = 0; n0 < BN; n0 += 16) {
+#pragma unroll
+            for (int gidx = 0; gidx < BN / 16; ++gidx) {
+                const int n0 = gidx * 16;
                 uint32_t r[16];
                 ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + n0, r);
                 ptx::tmem_ld_wait();
@@ -252,14 +316,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                     float sq[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
-                    const float s1 = butterfly16(v, lane), s2 = butterfly16(sq, lane);
-                    if ((lane & 1) == 0) {
-                        s_part[q * 2 * BN + n0 + col16(lane)] = s1;
-                        s_part[q * 2 * BN + BN + n0 + col16(lane)] = s2;
-                    }
+                    run1[gidx] += butterfly16(v, lane);
+                    run2[gidx] += butterfly16(sq, lane);
                 }
                 if (valid && P.out_nchw) {
-                    float *o = P.out_nchw + ((size_t)n_img * P.out_c_real * P.H + gh) * P.W + gw;
+                    float *o = P.out_nchw + ((size_t)ti.n_img * P.out_c_real * P.H + gh) * P.W + gw;
 #pragma unroll
                     for (int j = 0; j < 16; ++j)
                         if (nb * BN + n0 + j < P.out_c_real)
@@ -277,14 +338,24 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * acc);               // accumulator buffer free for the MMA warp
-            if (P.stats) {
-                ptx::named_bar_sync(1, 128);
-                for (int i = et; i < 2 * BN; i += 128) {
-                    const float s = s_part[i] + s_part[2 * BN + i] + s_part[4 * BN + i] + s_part[6 * BN + i];
-                    const int which = i / BN, n = i % BN;
-                    P.stats[(size_t)mt * 2 * P.Cout + which * P.Cout + nb * BN + n] = s;
+            ti.next(P.tiles_h, P.tiles_w);
+        }
+        if (P.stats) {    // once per CTA: combine the four epilogue warps, write this CTA's partial row (zeros elsewhere)
+            if ((lane & 1) == 0) {
+#pragma unroll
+                for (int gidx = 0; gidx < BN / 16; ++gidx) {
+                    s_part[q * 2 * BN + gidx * 16 + col16(lane)] = run1[gidx];
+                    s_part[q * 2 * BN + BN + gidx * 16 + col16(lane)] = run2[gidx];
                 }
-                ptx::named_bar_sync(1, 128);
+            }
+            ptx::named_bar_sync(1, 128);
+            for (int i = et; i < 2 * P.Cout; i += 128) {
+                const int which = i / P.Cout, c = i % P.Cout, n = c - nb * BN;
+                float sum = 0.f;
+                if (n >= 0 && n < BN && n_work > 0)
+                    sum = s_part[which * BN + n] + s_part[2 * BN + which * BN + n] + s_part[4 * BN + which * BN + n] +
+                          s_part[6 * BN + which * BN + n];
+                P.stats[(size_t)blockIdx.x * 2 * P.Cout + i] = sum;
             }
         }
     }
@@ -345,19 +416,26 @@ static void pick_cfg(int cin_v, int cout_v, int &KC, int &BN) {
     KC = (cin_v == 16 || BN == 128) ? 16 : 32;
 }
 
-template <int KS, int KC, int BN>
-static int launch_cfg(const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
-    using C = TcCfg<KS, KC, BN>;
+template <int KS, int KC, int BN, bool RES>
+static int launch_cfg2(const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+    using C = TcCfg<KS, KC, BN, RES>;
     static bool attr_set = false;
     if (!attr_set) {
-        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<KS, KC, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<KS, KC, BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
     const int total = P.m_tiles * P.n_blocks;
     const int grid = std::min(total, kNumSMs);
-    tc_conv_kernel<KS, KC, BN><<<grid, kTcThreads, C::SMEM_BYTES, s>>>(map, P);
+    tc_conv_kernel<KS, KC, BN, RES><<<grid, kTcThreads, C::SMEM_BYTES, s>>>(map, P);
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
+}
+template <int KS, int KC, int BN>
+static int launch_cfg(const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+    if constexpr (BN <= 64) {     // resident weights whenever the layer's whole weight is one (k-chunk, n-block) stage
+        if (P.k_chunks == 1 && P.n_blocks == 1) return launch_cfg2<KS, KC, BN, true>(map, P, s);
+    }
+    return launch_cfg2<KS, KC, BN, false>(map, P, s);
 }
 
 template <int KS>
@@ -380,7 +458,7 @@ static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void
     int KC, BN;
     pick_cfg(cin_v, cout_v, KC, BN);
     CUtensorMap map;
-    HPFG_RETURN_IF(make_map(&map, in, N, H, W, cin_v, KC, kTW + ks - 1, kTH + ks - 1));
+    HPFG_RETURN_IF(make_map_chunked(&map, in, N, H, W, cin_v, KC / 8, kTW + ks - 1, kTH + ks - 1));
     TcConvParams P{};
     P.bpk = bpk; P.out = (bf16 *)out; P.bias = bias;
     P.scale = xf.scale; P.shift = xf.shift;
@@ -390,8 +468,27 @@ static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void
     P.N = N; P.H = H; P.W = W; P.Cin = cin_v; P.Cout = cout_v;
     P.tiles_h = (H + kTH - 1) / kTH; P.tiles_w = (W + kTW - 1) / kTW;
     P.m_tiles = N * P.tiles_h * P.tiles_w; P.n_blocks = cout_v / BN; P.k_chunks = cin_v / KC;
-    if (P_out) *P_out = P.m_tiles;
+    if (P_out) *P_out = std::min(P.m_tiles * P.n_blocks, kNumSMs);
     return ks == 3 ? launch_ks<3>(KC, BN, map, P, s) : launch_ks<1>(KC, BN, map, P, s);
+}
+
+// micro-benchmark entry (wgrad_tc.cu: hpfg_conv_tc_bench): packs once per call (cheap) and launches one convolution
+int tc_run_bench(int op, int ks, int N, int H, int W, int cin, int cout, const void *in, void *out, const float *w, const float *scale,
+                 const float *shift, float *stats, cudaStream_t s) {
+    static bf16 *packed = nullptr;
+    static long long packed_n = 0;
+    const long long n = (long long)cin * cout * ks * ks;
+    if (packed_n < n) {
+        if (packed) cudaFree(packed);
+        if (cudaMalloc(&packed, (size_t)n * 2) != cudaSuccess) return HPFG_ERR_CUDA;
+        packed_n = n;
+        cudaMemsetAsync(packed, 0, (size_t)n * 2, s);
+    }
+    (void)w;
+    const int cin_v = op ? cout : cin, cout_v = op ? cin : cout;
+    LoadXform xf{};
+    xf.scale = scale; xf.shift = shift; xf.drop.bits = nullptr; xf.drop.inv_keep = 1.f;
+    return tc_run(ks, N, H, W, cin_v, cout_v, in, out, packed, nullptr, xf, stats, nullptr, s);
 }
 
 struct TcPlanState {

@@ -303,7 +303,7 @@ int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, D
            int max_partials, float *dgamma, float *dbeta, int accumulate, cudaStream_t s) {
     ProfScope _prof(PROF_GLUE, s);
     int P = (int)((M + 63) / 64);
-    if (P > kNumSMs * 4) P = kNumSMs * 4;
+    if (P > kNumSMs * 2) P = kNumSMs * 2;
     if (P > max_partials) P = max_partials;
     bn_bwd_kernel<T, 0><<<P, 256, 0, s>>>(dact, raw, draw, M, C, bn, drop, partials);
     HPFG_LAUNCH_CHECK();
@@ -430,34 +430,39 @@ int up_bwd(const T *dcat, T *dlow, int N, int h, int w, int F, cudaStream_t s) {
 }
 
 // ------------------------------------------------------------------------------------------ dropout_bits
-// One thread per 32-bit word of the NHWC bit mask.  Philox stream: counter = NCHW element index / 4 (so the
-// draw is layout independent), key = seed, second counter word = offset.  keep <=> u >= p  (Bernoulli(1-p)).
+// Keep-mask bits in NHWC element order.  Library stream: one Philox4x32-10 call per 4 consecutive NHWC elements
+// (counter = element index / 4, key = seed, counter words 2-3 = offset); keep <=> u >= p  (Bernoulli(1-p), as
+// nn.Dropout).  User masks (parity harness) arrive as NCHW uint8 and are gathered into the same bit layout.
 __global__ void __launch_bounds__(256) dropout_bits_kernel(uint32_t *__restrict__ bits, const uint8_t *__restrict__ mask,
                                                            int N, int H, int W, int C, float p, uint64_t seed,
                                                            uint64_t offset, int64_t n_words) {
     const int64_t total = (int64_t)N * H * W * C;
+    const uint32_t thresh = (uint32_t)(p * 16777216.0f);          // compare the top 24 random bits
     for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += (int64_t)gridDim.x * blockDim.x) {
         uint32_t word = 0;
-        for (int b = 0; b < 32; ++b) {
-            const int64_t e = wi * 32 + b;
-            if (e >= total) break;
-            const int c = (int)(e % C);
-            int64_t pix = e / C;
-            const int x = (int)(pix % W);
-            pix /= W;
-            const int y = (int)(pix % H), n = (int)(pix / H);
-            const int64_t nchw = (((int64_t)n * C + c) * H + y) * W + x;
-            bool keep;
-            if (mask) keep = mask[nchw] != 0;
-            else {
-                const uint64_t ctr = (uint64_t)nchw >> 2;
+        if (mask) {
+            for (int b = 0; b < 32; ++b) {
+                const int64_t e = wi * 32 + b;
+                if (e >= total) break;
+                const int c = (int)(e % C);
+                int64_t pix = e / C;
+                const int x = (int)(pix % W);
+                pix /= W;
+                const int y = (int)(pix % H), n = (int)(pix / H);
+                word |= (mask[(((int64_t)n * C + c) * H + y) * W + x] != 0 ? 1u : 0u) << b;
+            }
+        } else {
+#pragma unroll
+            for (int g4 = 0; g4 < 8; ++g4) {
+                const uint64_t ctr = (uint64_t)wi * 8 + g4;
                 const uint4 r = philox4x32_10(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)),
                                               make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)offset,
                                                          (uint32_t)(offset >> 32)));
-                const uint32_t rv = (nchw & 3) == 0 ? r.x : (nchw & 3) == 1 ? r.y : (nchw & 3) == 2 ? r.z : r.w;
-                keep = ((float)(rv >> 8) * (1.0f / 16777216.0f)) >= p;
+                word |= ((r.x >> 8) >= thresh ? 1u : 0u) << (4 * g4);
+                word |= ((r.y >> 8) >= thresh ? 1u : 0u) << (4 * g4 + 1);
+                word |= ((r.z >> 8) >= thresh ? 1u : 0u) << (4 * g4 + 2);
+                word |= ((r.w >> 8) >= thresh ? 1u : 0u) << (4 * g4 + 3);
             }
-            word |= (keep ? 1u : 0u) << b;
         }
         bits[wi] = word;
     }

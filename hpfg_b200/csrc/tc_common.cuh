@@ -59,4 +59,26 @@ inline int make_map(CUtensorMap *m, const void *base, int N, int H, int W, int C
 }
 
 
+// 5-D tiled map that makes TMA itself produce the UMMA operand layout [8-channel chunk][h][w][8 ch]:
+// dims (8 ch, W, H, C/8 chunks, N) with the chunk dimension strided by 16 bytes, box (8, box_w, box_h, chunks, 1).
+inline int make_map_chunked(CUtensorMap *m, const void *base, int N, int H, int W, int Cc, int chunks, int box_w, int box_h) {
+    EncodeTiledFn enc = get_encode();
+    if (!enc) {
+        set_error("cuTensorMapEncodeTiled entry point not available");
+        return HPFG_ERR_CUDA;
+    }
+    cuuint64_t dims[5] = {8, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)(Cc / 8), (cuuint64_t)N};
+    cuuint64_t strides[4] = {(cuuint64_t)Cc * 2, (cuuint64_t)W * Cc * 2, 16, (cuuint64_t)H * W * Cc * 2};
+    cuuint32_t box[5] = {8, (cuuint32_t)box_w, (cuuint32_t)box_h, (cuuint32_t)chunks, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void *>(base), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled (chunked 5-D) failed with code " + std::to_string((int)r));
+        return HPFG_ERR_CUDA;
+    }
+    return HPFG_OK;
+}
+
 }  // namespace hpfg

@@ -30,12 +30,13 @@ struct WgCfg {
     static constexpr int al(int v) { return (v + 127) / 128 * 128; }
     static constexpr int OFF_DOP = 0, OFF_XOP = al(D_OP), OFF_DRAW = OFF_XOP + al(X_OP), OFF_XRAW = OFF_DRAW + al(D_RAW);
     static constexpr int STAGE_BYTES = OFF_XRAW + al(X_RAW);
-    // the A descriptor always spans 16 row groups (M = 128); with COB < 128 the groups past the real channels read
+    // the A descriptor spans UM/8 row groups; with COB < UM the groups past the real channels read
     // whatever follows in shared memory (their D rows are never stored) -- keep those reads inside the allocation
-    static constexpr int TAIL_PAD = al((16 - COB / 8) * D_CHS);
+    static constexpr int UM = COB <= 64 ? 64 : 128;                 // UMMA M (accumulator rows = output channels of dY)
+    static constexpr int TAIL_PAD = al((UM / 8 - COB / 8) * D_CHS);
     static constexpr int FIXED_BYTES = 1024 + 2 * 256 * 4 + 128 * 8 * 4 /*dbias reduce*/;
     static constexpr int STAGES_RAW = (kWgSmemBudget - FIXED_BYTES - TAIL_PAD) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+    static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_PAD + FIXED_BYTES + 1024;
     static constexpr int TMEM_COLS = (KK * NB <= 32) ? 32 : (KK * NB <= 64) ? 64 : (KK * NB <= 128) ? 128 : (KK * NB <= 256) ? 256 : 512;
     static_assert(STAGES >= 2, "need at least a double buffer");
@@ -96,22 +97,25 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
 
     if (active) {
         if (warp == 0) {
-            if (lane == 0) {     // ============================================================ TMA producer
+            {                    // ============================================================ TMA producer (warp-uniform)
                 int stage = 0, phase = 0;
                 for (int mt = split; mt < P.m_tiles; mt += P.S) {
                     const int n_img = mt / tiles_per_img, rem = mt % tiles_per_img;
                     const int h0 = (rem / P.tiles_w) * kTH, w0 = (rem % P.tiles_w) * kTW;
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 11);
                     const uint32_t sb = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
-                    ptx::mbar_expect_tx(bar_full + 8 * stage, C::D_RAW + C::X_RAW);
-                    ptx::tma_load_4d(sb + C::OFF_DRAW, &tmD, bar_full + 8 * stage, co0, w0, h0, n_img);
-                    ptx::tma_load_4d(sb + C::OFF_XRAW, &tmX, bar_full + 8 * stage, ci0, w0 - C::PAD, h0 - C::PAD, n_img);
+                    if (ptx::elect_one()) {
+                        ptx::mbar_expect_tx(bar_full + 8 * stage, C::D_RAW + C::X_RAW);
+                        ptx::tma_load_4d(sb + C::OFF_DRAW, &tmD, bar_full + 8 * stage, co0, w0, h0, n_img);
+                        ptx::tma_load_4d(sb + C::OFF_XRAW, &tmX, bar_full + 8 * stage, ci0, w0 - C::PAD, h0 - C::PAD, n_img);
+                    }
+                    __syncwarp();
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         } else if (warp == 1) {
-            if (lane == 0) {     // ============================================================ MMA issuer
-                constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, NB, 1, 1);   // both operands MN-major
+            {                    // ============================================================ MMA issuer (warp-uniform)
+                constexpr uint32_t idesc = ptx::umma_idesc_bf16(C::UM, NB, 1, 1);   // both operands MN-major
                 int stage = 0, phase = 0;
                 bool first = true;
                 for (int mt = split; mt < P.m_tiles; mt += P.S) {
@@ -119,23 +123,31 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
                     ptx::mbar_wait(bar_xf + 8 * stage, phase, 14);
                     ptx::tc_fence_after();
                     const uint32_t sb = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
-#pragma unroll 1
-                    for (int j = 0; j < 8; ++j) {            // K step = 16 pixels = tile rows 2j, 2j+1
-                        // A = dY^T: M groups (8 co) SBO = chunk stride; K groups (8 pixels) LBO = 128 B
-                        const uint64_t ad = ptx::umma_desc(sb + C::OFF_DOP + j * 256, 128, C::D_CHS);
+                    // descriptor words: hi = SBO | version, lo = (addr >> 4) | LBO << 16; per-MMA offsets are compile-time adds
+                    // A = dY^T: M groups (8 co) SBO = chunk stride, K groups (8 pixels) LBO = 128 B
+                    // B = X shifted by the tap: N groups (8 ci) SBO = chunk stride, K groups LBO = one halo row
+                    constexpr uint32_t a_hi = (uint32_t)(C::D_CHS >> 4) | (1u << 14), b_hi = (uint32_t)(C::X_CHS >> 4) | (1u << 14);
+                    const uint32_t a_lo = (((sb + C::OFF_DOP) >> 4) & 0x3FFFu) | ((uint32_t)(128 >> 4) << 16);
+                    const uint32_t b_lo = (((sb + C::OFF_XOP) >> 4) & 0x3FFFu) | ((uint32_t)((C::HW * 16) >> 4) << 16);
+                    const bool last = mt + P.S >= P.m_tiles;
+                    if (ptx::elect_one()) {
 #pragma unroll
-                        for (int tap = 0; tap < C::KK; ++tap) {
-                            const int r = tap / KS, s = tap % KS;
-                            // B = X shifted by the tap: N groups (8 ci) SBO = chunk stride; K groups LBO = one halo row
-                            const uint64_t bd = ptx::umma_desc(sb + C::OFF_XOP + ((2 * j + r) * C::HW + s) * 16, C::HW * 16, C::X_CHS);
-                            ptx::umma_bf16(tmem_base + tap * NB, ad, bd, idesc, (first && j == 0) ? 0u : 1u);
+                        for (int j = 0; j < 8; ++j) {            // K step = 16 pixels = tile rows 2j, 2j+1
+                            const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)((j * 256) >> 4));
+#pragma unroll
+                            for (int tap = 0; tap < C::KK; ++tap) {
+                                const uint32_t bo = (uint32_t)((((2 * j + tap / KS) * C::HW + tap % KS) * 16) >> 4);
+                                const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + bo);
+                                ptx::umma_bf16(tmem_base + tap * NB, ad, bd, idesc, (first && j == 0) ? 0u : 1u);
+                            }
                         }
+                        ptx::umma_commit(bar_empty + 8 * stage);
+                        if (last) ptx::umma_commit(bar_done);
                     }
+                    __syncwarp();
                     first = false;
-                    ptx::umma_commit(bar_empty + 8 * stage);
                     if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
-                ptx::umma_commit(bar_done);
             }
         } else if (warp >= 4 && warp < 8) {
             // ================================================================================ transform warps
@@ -203,7 +215,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
             }
         } else if (warp >= 8) {
             // ================================================================================ epilogue (once)
-            const int q = warp & 3, row = q * 32 + lane, co = co0 + row;
+            // accumulator row -> TMEM lane: M=128: lane = row; M=64: lane = (row/16)*32 + row%16 (measured, tests/probes)
+            const int q = warp & 3;
+            const int row = C::UM == 128 ? q * 32 + lane : (lane < 16 ? q * 16 + lane : COB);
+            const int co = co0 + row;
             ptx::mbar_wait(bar_done, 0, 16);
             ptx::tc_fence_after();
             float *dst = P.scratch + (size_t)split * ((size_t)C::KK * P.Cin * P.Cout + P.Cout);
@@ -354,6 +369,57 @@ extern "C" int hpfg_wgrad_tc_debug(int N, int H, int W, int cin, int cout, int k
     const int rc = tc_wgrad_run(ks, N, H, W, cin, cout, cin, cout, x_bf16_nhwc, xf, dy_bf16_nhwc, scratch, nf, dw_oihw, dbias, 0, s);
     cudaStreamSynchronize(s);
     cudaFree(scratch);
+    if (rc == HPFG_OK) HPFG_CUDA_CHECK(cudaGetLastError());
+    return rc;
+}
+
+// ---- layer micro-benchmark hook (profiles/layer_bench.py): times `iters` back-to-back launches of ONE tensor-core
+// convolution (op 0 fprop with fused loader + BN-stat epilogue, 1 dgrad, 2 wgrad) on internally allocated
+// buffers with CUDA events on `stream`; returns the average milliseconds per launch.
+namespace hpfg {
+int tc_run_bench(int op, int ks, int N, int H, int W, int cin, int cout, const void *in, void *out, const float *w, const float *scale,
+                 const float *shift, float *stats, cudaStream_t s);   // conv_tc.cu
+}
+__global__ void fill_pattern_bf16(__nv_bfloat16 *p, size_t n, float scale) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = __float2bfloat16(scale * (float)((int)((i * 2654435761u) >> 24) - 128) / 128.f);
+}
+extern "C" int hpfg_conv_tc_bench(int op, int N, int H, int W, int cin, int cout, int ks, int iters, float *ms_out_host, void *stream) {
+    HPFG_REQUIRE(op >= 0 && op <= 2 && iters > 0 && ms_out_host, "hpfg_conv_tc_bench: bad arguments");
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t px = (size_t)N * H * W;
+    __nv_bfloat16 *a = nullptr, *b = nullptr;
+    float *w = nullptr, *sc = nullptr, *stats = nullptr, *scratch = nullptr, *dw = nullptr;
+    const int64_t nf = tc_wgrad_scratch_floats(N, H, W, cin, cout, ks);
+    HPFG_CUDA_CHECK(cudaMalloc(&a, px * std::max(cin, cout) * 2));
+    HPFG_CUDA_CHECK(cudaMalloc(&b, px * std::max(cin, cout) * 2));
+    HPFG_CUDA_CHECK(cudaMalloc(&w, (size_t)cin * cout * ks * ks * 4));
+    HPFG_CUDA_CHECK(cudaMalloc(&sc, 2 * 256 * 4));
+    HPFG_CUDA_CHECK(cudaMalloc(&stats, (size_t)kNumSMs * 2 * 256 * 4 * 4));
+    HPFG_CUDA_CHECK(cudaMalloc(&scratch, (size_t)nf * 4));
+    HPFG_CUDA_CHECK(cudaMalloc(&dw, ((size_t)cin * cout * ks * ks + cout) * 4));
+    fill_pattern_bf16<<<1024, 256, 0, s>>>(a, px * std::max(cin, cout), 1.f);
+    fill_pattern_bf16<<<1024, 256, 0, s>>>(b, px * std::max(cin, cout), 1.f);
+    HPFG_CUDA_CHECK(cudaMemsetAsync(w, 0, (size_t)cin * cout * ks * ks * 4, s));
+    HPFG_CUDA_CHECK(cudaMemsetAsync(sc, 0, 2 * 256 * 4, s));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    LoadXform xf{};
+    xf.scale = sc; xf.shift = sc + 256; xf.drop.bits = nullptr; xf.drop.inv_keep = 1.f;
+    int rc = HPFG_OK;
+    for (int i = -2; i < iters && rc == HPFG_OK; ++i) {
+        if (i == 0) cudaEventRecord(e0, s);
+        if (op == 2) rc = tc_wgrad_run(ks, N, H, W, cin, cout, cin, cout, a, xf, b, scratch, nf, dw, dw + (size_t)cin * cout * ks * ks, 0, s);
+        else rc = tc_run_bench(op, ks, N, H, W, cin, cout, a, b, w, op == 0 ? sc : nullptr, op == 0 ? sc + 256 : nullptr, op == 0 ? stats : nullptr, s);
+    }
+    cudaEventRecord(e1, s);
+    cudaStreamSynchronize(s);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    *ms_out_host = ms / iters;
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    cudaFree(a); cudaFree(b); cudaFree(w); cudaFree(sc); cudaFree(stats); cudaFree(scratch); cudaFree(dw);
     if (rc == HPFG_OK) HPFG_CUDA_CHECK(cudaGetLastError());
     return rc;
 }

@@ -118,6 +118,11 @@ int hpfg_wgrad_tc_debug(int batch, int height, int width, int cin, int cout, int
                         const void *dy_bf16_nhwc, const float *scale, const float *shift, float *dw_oihw, float *dbias,
                         void *stream);
 
+/* Layer micro-benchmark: average milliseconds of `iters` back-to-back launches of one tensor-core convolution
+ * (op 0 fprop incl. fused loader and BN-stat epilogue, 1 dgrad, 2 wgrad) on internally allocated buffers. */
+int hpfg_conv_tc_bench(int op, int batch, int height, int width, int cin, int cout, int ksize, int iters,
+                       float *ms_out_host, void *stream);
+
 /* ---- fused SSL loss (forward value + d loss / d logits) ---------------------------------------------
  * student: fp32 NCHW [n_l+n_u, C, H, W] logits.  labels: int64 [n_l, H, W] (255 = ignored by CE only).
  * other: MT/UAMT -> teacher logits for the UNLABELED slices [n_u, C, H, W];
