@@ -13,8 +13,9 @@ from .unet import UNet
 from .losses import Med_Sup_Loss, DiceLoss, softmax_mse_loss, mean_teacher_loss, cps_loss, uamt_loss, ssl_loss_raw
 from .utils import (update_ema_variables, get_current_consistency_weight, sigmoid_rampup, linear_rampup,
                     ema_update_flat)
-from .trainer import MeanTeacherStep, CPSStep, UAMTStep, medical_lr
+from .trainer import (MeanTeacherStep, CPSStep, UAMTStep, medical_lr, gradient_buckets, allreduce_flat_buckets,
+                      shard_batch)
 
 __all__ = ["build_model", "UNet", "Med_Sup_Loss", "DiceLoss", "softmax_mse_loss", "mean_teacher_loss", "cps_loss",
            "uamt_loss", "ssl_loss_raw", "update_ema_variables", "get_current_consistency_weight", "sigmoid_rampup",
-           "linear_rampup", "ema_update_flat", "MeanTeacherStep", "CPSStep", "UAMTStep", "medical_lr"]
+           "linear_rampup", "ema_update_flat", "MeanTeacherStep", "CPSStep", "UAMTStep", "medical_lr", "gradient_buckets", "allreduce_flat_buckets", "shard_batch"]

@@ -34,6 +34,7 @@ SIGNATURES = {
     "hpfg_unet_num_buckets": (c_int, [c_vp]),
     "hpfg_unet_bucket_range": (c_int, [c_vp, c_int, c_i64p, c_i64p]),
     "hpfg_unet_bucket_wait": (c_int, [c_vp, c_int, c_vp]),
+    "hpfg_unet_bucket_layout": (c_int, [c_int, c_int, c_i64p, c_i64p]),
     "hpfg_unet_debug_tap": (c_int, [c_vp, ctypes.c_char_p, c_vp, c_i64, c_vp]),
     "hpfg_conv_tc_debug": (c_int, [c_int] * 7 + [c_vp] * 8),
     "hpfg_conv_tc_bench": (c_int, [c_int] * 8 + [ctypes.POINTER(c_f), c_vp]),

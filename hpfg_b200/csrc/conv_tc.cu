@@ -31,10 +31,13 @@ constexpr int kTcThreads = 128 + kXfThreads + 128;   // + warps 0-3 (TMA, MMA, T
 constexpr int kMaxStages = 12;
 constexpr int kSmemBudget = 200 * 1024;
 
-template <int KS, int KC, int BN, bool RES>
+template <int KS, int KC, int BN, bool RES, int MT>
 struct TcCfg {
     static constexpr int PAD = KS / 2, KK = KS * KS;
-    static constexpr int HH = kTH + KS - 1, HW = kTW + KS - 1;     // halo tile
+    // one pipeline stage = MT side-by-side 16x8-pixel UMMA tiles (16 rows x 8*MT columns) sharing one halo fetch:
+    // per-stage fixed costs (barrier round trips, tile bookkeeping, proxy fences) are amortised over MT*128 pixels
+    static constexpr int TWP = kTW * MT;
+    static constexpr int HH = kTH + KS - 1, HW = TWP + KS - 1;     // halo tile
     static constexpr int NPIX = HH * HW;
     static constexpr int NCH = KC / 8;                             // 16-byte channel chunks per stage
     // operand tile [chunk][halo pixel][8 ch], written in exactly this order by TMA (5-D chunked tensor map)
@@ -51,8 +54,10 @@ struct TcCfg {
     static constexpr int STAGES_RAW = (kSmemBudget - FIXED_BYTES - RESB_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > kMaxStages ? kMaxStages : STAGES_RAW;
     static constexpr int SMEM_BYTES = RESB_BYTES + STAGES * STAGE_BYTES + FIXED_BYTES + 1024 /*alignment slack*/;
-    static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+    static constexpr int ACC_COLS = MT * BN;                       // accumulator columns per TMEM buffer
+    static constexpr int TMEM_COLS = (2 * ACC_COLS <= 32) ? 32 : (2 * ACC_COLS <= 64) ? 64 : (2 * ACC_COLS <= 128) ? 128 : (2 * ACC_COLS <= 256) ? 256 : 512;
     static_assert(STAGES >= 2, "need at least a double buffer");
+    static_assert(2 * ACC_COLS <= 512, "accumulators exceed TMEM");
 };
 
 struct TcConvParams {
@@ -66,29 +71,6 @@ struct TcConvParams {
     float *out_nchw;          // if set: write fp32 NCHW [N,out_c_real,H,W] (+bias) instead of bf16 NHWC (out_conv logits)
     int out_c_real;
     int N, H, W, Cin, Cout, tiles_h, tiles_w, m_tiles, n_blocks, k_chunks;
-};
-
-// Walks the m-tiles this CTA owns (mt0, mt0+step, ...) without per-tile integer divisions.
-struct TileIter {
-    int n_img, th, tw, dn, dh, dw;
-    __device__ __forceinline__ void init(int mt, int step, int tiles_h, int tiles_w) {
-        const int tpi = tiles_h * tiles_w;
-        n_img = mt / tpi;
-        int r = mt % tpi;
-        th = r / tiles_w;
-        tw = r % tiles_w;
-        dn = step / tpi;
-        r = step % tpi;
-        dh = r / tiles_w;
-        dw = r % tiles_w;
-    }
-    __device__ __forceinline__ void next(int tiles_h, int tiles_w) {
-        tw += dw;
-        if (tw >= tiles_w) { tw -= tiles_w; ++th; }
-        th += dh;
-        if (th >= tiles_h) { th -= tiles_h; ++n_img; }
-        n_img += dn;
-    }
 };
 
 // Reduce 16 per-lane values over the 32 lanes of a warp with 16 shuffles (recursive halving); afterwards every
@@ -122,9 +104,9 @@ __device__ __forceinline__ float butterfly16(const float (&v)[16], int lane) {
 // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-11 transform (only when a loader transform is
 // fused), 12-15 epilogue.  Per-tile instruction counts of the single-thread roles are kept minimal: the MMA thread
 // patches precomputed descriptor words with compile-time offsets and never computes tile coordinates.
-template <int KS, int KC, int BN, bool RES>
+template <int KS, int KC, int BN, bool RES, int MT>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const TcConvParams P) {
-    using C = TcCfg<KS, KC, BN, RES>;
+    using C = TcCfg<KS, KC, BN, RES, MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *res_b = smem;                                         // resident weights (RES only)
@@ -176,7 +158,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             int stage = 0, phase = 0;
             const bf16 *bsrc = P.bpk + (size_t)nb * P.k_chunks * (C::B_BYTES / 2);
             for (int it = 0; it < n_work; ++it) {
-                const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * kTW - C::PAD;
+                const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * C::TWP - C::PAD;
                 for (int kc = 0; kc < P.k_chunks; ++kc) {
                     ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
                     const uint32_t sb = stage_u32 + stage * C::STAGE_BYTES, fb = bar_full + 8 * stage;
@@ -209,7 +191,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                 const int acc = it & 1, acc_phase = (it >> 1) & 1;
                 ptx::mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1, 2);
                 ptx::tc_fence_after();
-                const uint32_t d_tmem = tmem_base + acc * BN;
+                const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
                 for (int kc = 0; kc < P.k_chunks; ++kc) {
                     ptx::mbar_wait(bar_full + 8 * stage, phase, 3);
                     if (xform) ptx::mbar_wait(bar_xf + 8 * stage, phase, 4);
@@ -218,17 +200,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                     const uint32_t b_lo = RES ? b_lo0 : b_lo0 + stage * (C::STAGE_BYTES >> 4);
                     if (ptx::elect_one()) {
 #pragma unroll
+                    for (int j = 0; j < MT; ++j) {                 // UMMA tile j = output columns 8j..8j+7 of the stage
+#pragma unroll
                     for (int tap = 0; tap < C::KK; ++tap) {
 #pragma unroll
                         for (int kk = 0; kk < KC / 16; ++kk) {
-                            constexpr int dummy = 0;
-                            (void)dummy;
-                            const uint32_t ao = (uint32_t)((2 * kk * C::CH_STRIDE + ((tap / KS) * C::HW + (tap % KS)) * 16) >> 4);
+                            const uint32_t ao = (uint32_t)((2 * kk * C::CH_STRIDE + ((tap / KS) * C::HW + (tap % KS) + j * kTW) * 16) >> 4);
                             const uint32_t bo = (uint32_t)((tap * C::B_TAP_BYTES + 2 * kk * BN * 16) >> 4);
                             const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + ao);
                             const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + bo);
-                            ptx::umma_bf16(d_tmem, ad, bd, idesc, (kc | tap | kk) != 0);
+                            ptx::umma_bf16(d_tmem + j * BN, ad, bd, idesc, (kc | tap | kk) != 0);
                         }
+                    }
                     }
                     ptx::umma_commit(bar_empty + 8 * stage);      // smem slot reusable once these MMAs retire
                     if (kc == P.k_chunks - 1) ptx::umma_commit(bar_tfull + 8 * acc);   // accumulator complete -> epilogue
@@ -246,7 +229,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             ti.init(mt0, mstep, P.tiles_h, P.tiles_w);
             int stage = 0, phase = 0;
             for (int it = 0; it < n_work; ++it) {
-                const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * kTW - C::PAD;
+                const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * C::TWP - C::PAD;
                 const size_t img_px = (size_t)ti.n_img * P.H;
                 for (int kc = 0; kc < P.k_chunks; ++kc) {
                     ptx::mbar_wait(bar_full + 8 * stage, phase, 5);
@@ -298,16 +281,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         ti.init(mt0, mstep, P.tiles_h, P.tiles_w);
         for (int it = 0; it < n_work; ++it) {
             const int acc = it & 1, acc_phase = (it >> 1) & 1;
-            const int gh = ti.th * kTH + m / kTW, gw = ti.tw * kTW + m % kTW;
-            const bool valid = gh < P.H && gw < P.W;
-            bf16 *orow = P.out + (((size_t)ti.n_img * P.H + gh) * P.W + gw) * P.Cout + nb * BN;
             ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase, 6);
             ptx::tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < MT; ++j) {
+            const int gh = ti.th * kTH + m / kTW, gw = ti.tw * C::TWP + j * kTW + m % kTW;
+            const bool valid = gh < P.H && gw < P.W;
+            bf16 *orow = P.out + (((size_t)ti.n_img * P.H + gh) * P.W + gw) * P.Cout + nb * BN;
 #pragma unroll
             for (int gidx = 0; gidx < BN / 16; ++gidx) {
                 const int n0 = gidx * 16;
                 uint32_t r[16];
-                ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * BN + n0, r);
+                ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS + j * BN + n0, r);
                 ptx::tmem_ld_wait();
                 float v[16];
 #pragma unroll
@@ -335,6 +320,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                     *reinterpret_cast<uint4 *>(orow + n0) = lo;
                     *reinterpret_cast<uint4 *>(orow + n0 + 8) = hi;
                 }
+            }
             }
             ptx::tc_fence_before();
             ptx::mbar_arrive(bar_tempty + 8 * acc);               // accumulator buffer free for the MMA warp
@@ -416,36 +402,44 @@ static void pick_cfg(int cin_v, int cout_v, int &KC, int &BN) {
     KC = (cin_v == 16 || BN == 128) ? 16 : 32;
 }
 
-template <int KS, int KC, int BN, bool RES>
-static int launch_cfg2(const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
-    using C = TcCfg<KS, KC, BN, RES>;
+template <int KS, int KC, int BN, bool RES, int MT>
+static int launch_cfg3(const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+    using C = TcCfg<KS, KC, BN, RES, MT>;
     static bool attr_set = false;
     if (!attr_set) {
-        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<KS, KC, BN, RES>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<KS, KC, BN, RES, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
     const int total = P.m_tiles * P.n_blocks;
     const int grid = std::min(total, kNumSMs);
-    tc_conv_kernel<KS, KC, BN, RES><<<grid, kTcThreads, C::SMEM_BYTES, s>>>(map, P);
+    tc_conv_kernel<KS, KC, BN, RES, MT><<<grid, kTcThreads, C::SMEM_BYTES, s>>>(map, P);
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
-template <int KS, int KC, int BN>
-static int launch_cfg(const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
-    if constexpr (BN <= 64) {     // resident weights whenever the layer's whole weight is one (k-chunk, n-block) stage
-        if (P.k_chunks == 1 && P.n_blocks == 1) return launch_cfg2<KS, KC, BN, true>(map, P, s);
+template <int KS, int KC, int BN, bool RES>
+static int launch_cfg2(int mt, const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+    if constexpr (KS == 3 && BN <= 32) {      // wide stages only where per-tile overheads dominate (few channels, large images)
+        if (mt == 4) return launch_cfg3<KS, KC, BN, RES, 4>(map, P, s);
+        if (mt == 2) return launch_cfg3<KS, KC, BN, RES, 2>(map, P, s);
     }
-    return launch_cfg2<KS, KC, BN, false>(map, P, s);
+    return launch_cfg3<KS, KC, BN, RES, 1>(map, P, s);
+}
+template <int KS, int KC, int BN>
+static int launch_cfg(int mt, const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+    if constexpr (BN <= 64) {     // resident weights whenever the layer's whole weight is one (k-chunk, n-block) stage
+        if (P.k_chunks == 1 && P.n_blocks == 1) return launch_cfg2<KS, KC, BN, true>(mt, map, P, s);
+    }
+    return launch_cfg2<KS, KC, BN, false>(mt, map, P, s);
 }
 
 template <int KS>
-static int launch_ks(int KC, int BN, const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
-    if (KC == 16 && BN == 16) return launch_cfg<KS, 16, 16>(map, P, s);
-    if (KC == 16 && BN == 32) return launch_cfg<KS, 16, 32>(map, P, s);
-    if (KC == 16 && BN == 128) return launch_cfg<KS, 16, 128>(map, P, s);
-    if (KC == 32 && BN == 16) return launch_cfg<KS, 32, 16>(map, P, s);
-    if (KC == 32 && BN == 32) return launch_cfg<KS, 32, 32>(map, P, s);
-    if (KC == 32 && BN == 64) return launch_cfg<KS, 32, 64>(map, P, s);
+static int launch_ks(int KC, int BN, int mt, const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+    if (KC == 16 && BN == 16) return launch_cfg<KS, 16, 16>(mt, map, P, s);
+    if (KC == 16 && BN == 32) return launch_cfg<KS, 16, 32>(mt, map, P, s);
+    if (KC == 16 && BN == 128) return launch_cfg<KS, 16, 128>(mt, map, P, s);
+    if (KC == 32 && BN == 16) return launch_cfg<KS, 32, 16>(mt, map, P, s);
+    if (KC == 32 && BN == 32) return launch_cfg<KS, 32, 32>(mt, map, P, s);
+    if (KC == 32 && BN == 64) return launch_cfg<KS, 32, 64>(mt, map, P, s);
     set_error("tc conv: no kernel for KC=" + std::to_string(KC) + " BN=" + std::to_string(BN));
     return HPFG_ERR_UNSUPPORTED;
 }
@@ -457,8 +451,15 @@ static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void
     ProfScope _prof(PROF_CONV_TC, s);
     int KC, BN;
     pick_cfg(cin_v, cout_v, KC, BN);
+    // stage width: 4 / 2 UMMA tiles side by side when the image is wide enough to keep every SM busy with wide stages
+    int mt = 1;
+    if (ks == 3 && BN <= 32) {
+        const int th = (H + kTH - 1) / kTH;
+        if (W % (4 * kTW) == 0 && N * th * (W / (4 * kTW)) >= 2 * kNumSMs) mt = 4;
+        else if (W % (2 * kTW) == 0 && N * th * (W / (2 * kTW)) >= 2 * kNumSMs) mt = 2;
+    }
     CUtensorMap map;
-    HPFG_RETURN_IF(make_map_chunked(&map, in, N, H, W, cin_v, KC / 8, kTW + ks - 1, kTH + ks - 1));
+    HPFG_RETURN_IF(make_map_chunked(&map, in, N, H, W, cin_v, KC / 8, kTW * mt + ks - 1, kTH + ks - 1));
     TcConvParams P{};
     P.bpk = bpk; P.out = (bf16 *)out; P.bias = bias;
     P.scale = xf.scale; P.shift = xf.shift;
@@ -466,10 +467,10 @@ static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void
     P.stats = stats;
     P.out_nchw = out_nchw; P.out_c_real = out_c_real;
     P.N = N; P.H = H; P.W = W; P.Cin = cin_v; P.Cout = cout_v;
-    P.tiles_h = (H + kTH - 1) / kTH; P.tiles_w = (W + kTW - 1) / kTW;
+    P.tiles_h = (H + kTH - 1) / kTH; P.tiles_w = (W + kTW * mt - 1) / (kTW * mt);
     P.m_tiles = N * P.tiles_h * P.tiles_w; P.n_blocks = cout_v / BN; P.k_chunks = cin_v / KC;
     if (P_out) *P_out = std::min(P.m_tiles * P.n_blocks, kNumSMs);
-    return ks == 3 ? launch_ks<3>(KC, BN, map, P, s) : launch_ks<1>(KC, BN, map, P, s);
+    return ks == 3 ? launch_ks<3>(KC, BN, mt, map, P, s) : launch_ks<1>(KC, BN, mt, map, P, s);
 }
 
 // micro-benchmark entry (wgrad_tc.cu: hpfg_conv_tc_bench): packs once per call (cheap) and launches one convolution

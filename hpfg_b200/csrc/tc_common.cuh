@@ -22,6 +22,29 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     return *reinterpret_cast<const uint32_t *>(&h);
 }
 
+// Walks the m-tiles this CTA owns (mt0, mt0+step, ...) without per-tile integer divisions.
+struct TileIter {
+    int n_img, th, tw, dn, dh, dw;
+    __device__ __forceinline__ void init(int mt, int step, int tiles_h, int tiles_w) {
+        const int tpi = tiles_h * tiles_w;
+        n_img = mt / tpi;
+        int r = mt % tpi;
+        th = r / tiles_w;
+        tw = r % tiles_w;
+        dn = step / tpi;
+        r = step % tpi;
+        dh = r / tiles_w;
+        dw = r % tiles_w;
+    }
+    __device__ __forceinline__ void next(int tiles_h, int tiles_w) {
+        tw += dw;
+        if (tw >= tiles_w) { tw -= tiles_w; ++th; }
+        th += dh;
+        if (th >= tiles_h) { th -= tiles_h; ++n_img; }
+        n_img += dn;
+    }
+};
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
                                   const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);

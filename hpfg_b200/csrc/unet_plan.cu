@@ -514,6 +514,17 @@ extern "C" int hpfg_unet_bucket_range(hpfg_unet_plan_t p, int bucket, int64_t *o
     return HPFG_OK;
 }
 
+extern "C" int hpfg_unet_bucket_layout(int in_channels, int num_classes, int64_t *offsets_host, int64_t *counts_host) {
+    HPFG_REQUIRE(in_channels >= 1 && num_classes >= 1 && offsets_host && counts_host, "hpfg_unet_bucket_layout: bad arguments");
+    UNetDesc d;
+    describe_unet(in_channels, num_classes, 16, 16, d);
+    for (int b = 0; b < kNumBuckets; ++b) {
+        offsets_host[b] = d.bucket_begin[b + 1];
+        counts_host[b] = d.bucket_begin[b] - d.bucket_begin[b + 1];
+    }
+    return HPFG_OK;
+}
+
 extern "C" int hpfg_unet_bucket_wait(hpfg_unet_plan_t p, int bucket, void *comm_stream) {
     HPFG_REQUIRE(p && bucket >= 0 && bucket < kNumBuckets, "hpfg_unet_bucket_wait: bad bucket");
     HPFG_CUDA_CHECK(cudaStreamWaitEvent((cudaStream_t)comm_stream, p->bucket_ev[bucket], 0));

@@ -18,23 +18,25 @@
 
 namespace hpfg {
 
-constexpr int kWgThreads = 384;     // warps: 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-7 transform, 8-11 epilogue
+constexpr int kWgXfThreads = 256;   // transform threads (warps 4-11): in-place loader transform of X + bias-gradient sums
+constexpr int kWgThreads = 128 + kWgXfThreads + 128;   // warps 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 transform, 12-15 epilogue
 constexpr int kWgSmemBudget = 222 * 1024;
 
 template <int KS, int NB, int COB>
 struct WgCfg {
     static constexpr int PAD = KS / 2, KK = KS * KS;
     static constexpr int HH = kTH + KS - 1, HW = kTW + KS - 1, NPIX_X = HH * HW;
-    static constexpr int X_RAW = NPIX_X * NB * 2, X_CHS = (NPIX_X + 1) * 16, X_OP = (NB / 8) * X_CHS;
-    static constexpr int D_RAW = 128 * COB * 2, D_CHS = (128 + 1) * 16, D_OP = (COB / 8) * D_CHS;
+    // both operand tiles land directly in UMMA order [8-channel chunk][pixel][8 ch] (chunked 5-D TMA maps)
+    static constexpr int X_CHS = NPIX_X * 16, X_OP = (NB / 8) * X_CHS;
+    static constexpr int D_CHS = 128 * 16, D_OP = (COB / 8) * D_CHS;
     static constexpr int al(int v) { return (v + 127) / 128 * 128; }
-    static constexpr int OFF_DOP = 0, OFF_XOP = al(D_OP), OFF_DRAW = OFF_XOP + al(X_OP), OFF_XRAW = OFF_DRAW + al(D_RAW);
-    static constexpr int STAGE_BYTES = OFF_XRAW + al(X_RAW);
+    static constexpr int OFF_DOP = 0, OFF_XOP = al(D_OP);
+    static constexpr int STAGE_BYTES = OFF_XOP + al(X_OP);
+    static constexpr int UM = COB <= 64 ? 64 : 128;                 // UMMA M (accumulator rows = output channels of dY)
     // the A descriptor spans UM/8 row groups; with COB < UM the groups past the real channels read
     // whatever follows in shared memory (their D rows are never stored) -- keep those reads inside the allocation
-    static constexpr int UM = COB <= 64 ? 64 : 128;                 // UMMA M (accumulator rows = output channels of dY)
     static constexpr int TAIL_PAD = al((UM / 8 - COB / 8) * D_CHS);
-    static constexpr int FIXED_BYTES = 1024 + 2 * 256 * 4 + 128 * 8 * 4 /*dbias reduce*/;
+    static constexpr int FIXED_BYTES = 1024 + 2 * 256 * 4 + kWgXfThreads * 8 * 4 /*dbias reduce*/;
     static constexpr int STAGES_RAW = (kWgSmemBudget - FIXED_BYTES - TAIL_PAD) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_PAD + FIXED_BYTES + 1024;
@@ -62,24 +64,26 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fixed + 512);
     float *s_scale = reinterpret_cast<float *>(fixed + 1024);
     float *s_shift = s_scale + 256;
-    float *s_bias = s_shift + 256;                                 // [128 threads][... reduced to COB]
+    float *s_bias = s_shift + 256;                                 // [transform threads][8]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = ptx::smem_u32(bars), bar_xf = bar_full + 8 * C::STAGES, bar_empty = bar_xf + 8 * C::STAGES;
     const uint32_t bar_done = bar_empty + 8 * C::STAGES;
+    const uint32_t smem_u32 = ptx::smem_u32(smem);
 
     // work assignment: block pair (co block, ci block) x pixel split
     const int n_bp = P.ci_blocks * P.co_blocks;
     const int bp = blockIdx.x % n_bp, split = blockIdx.x / n_bp;
-    const bool active = split < P.S;
     const int cib = bp % P.ci_blocks, cob = bp / P.ci_blocks;
     const int ci0 = cib * NB, co0 = cob * COB;
-    const int tiles_per_img = P.tiles_h * P.tiles_w;
+    const int n_work = (P.m_tiles - split + P.S - 1) / P.S;        // tiles split, split+S, ...
+    const bool xform = P.scale != nullptr, want_bias = cib == 0;
+    const bool use_xf = xform || want_bias;                       // transform warps touch the stage -> MMA waits for them
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(bar_full + 8 * s, 1);
-            ptx::mbar_init(bar_xf + 8 * s, 128);
+            ptx::mbar_init(bar_xf + 8 * s, kWgXfThreads);
             ptx::mbar_init(bar_empty + 8 * s, 1);
         }
         ptx::mbar_init(bar_done, 1);
@@ -95,130 +99,128 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (active) {
-        if (warp == 0) {
-            {                    // ============================================================ TMA producer (warp-uniform)
-                int stage = 0, phase = 0;
-                for (int mt = split; mt < P.m_tiles; mt += P.S) {
-                    const int n_img = mt / tiles_per_img, rem = mt % tiles_per_img;
-                    const int h0 = (rem / P.tiles_w) * kTH, w0 = (rem % P.tiles_w) * kTW;
-                    ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 11);
-                    const uint32_t sb = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
-                    if (ptx::elect_one()) {
-                        ptx::mbar_expect_tx(bar_full + 8 * stage, C::D_RAW + C::X_RAW);
-                        ptx::tma_load_4d(sb + C::OFF_DRAW, &tmD, bar_full + 8 * stage, co0, w0, h0, n_img);
-                        ptx::tma_load_4d(sb + C::OFF_XRAW, &tmX, bar_full + 8 * stage, ci0, w0 - C::PAD, h0 - C::PAD, n_img);
-                    }
-                    __syncwarp();
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-                }
+    if (warp == 0) {             // ==================================================== TMA producer (warp-uniform)
+        TileIter ti;
+        ti.init(split, P.S, P.tiles_h, P.tiles_w);
+        int stage = 0, phase = 0;
+        for (int it = 0; it < n_work; ++it) {
+            const int h0 = ti.th * kTH, w0 = ti.tw * kTW;
+            ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 11);
+            const uint32_t sb = smem_u32 + stage * C::STAGE_BYTES;
+            if (ptx::elect_one()) {
+                ptx::mbar_expect_tx(bar_full + 8 * stage, C::D_OP + C::X_OP);
+                ptx::tma_load_5d(sb + C::OFF_DOP, &tmD, bar_full + 8 * stage, 0, w0, h0, co0 / 8, ti.n_img);
+                ptx::tma_load_5d(sb + C::OFF_XOP, &tmX, bar_full + 8 * stage, 0, w0 - C::PAD, h0 - C::PAD, ci0 / 8, ti.n_img);
             }
-        } else if (warp == 1) {
-            {                    // ============================================================ MMA issuer (warp-uniform)
-                constexpr uint32_t idesc = ptx::umma_idesc_bf16(C::UM, NB, 1, 1);   // both operands MN-major
-                int stage = 0, phase = 0;
-                bool first = true;
-                for (int mt = split; mt < P.m_tiles; mt += P.S) {
-                    ptx::mbar_wait(bar_full + 8 * stage, phase, 13);
-                    ptx::mbar_wait(bar_xf + 8 * stage, phase, 14);
-                    ptx::tc_fence_after();
-                    const uint32_t sb = ptx::smem_u32(smem + stage * C::STAGE_BYTES);
-                    // descriptor words: hi = SBO | version, lo = (addr >> 4) | LBO << 16; per-MMA offsets are compile-time adds
-                    // A = dY^T: M groups (8 co) SBO = chunk stride, K groups (8 pixels) LBO = 128 B
-                    // B = X shifted by the tap: N groups (8 ci) SBO = chunk stride, K groups LBO = one halo row
-                    constexpr uint32_t a_hi = (uint32_t)(C::D_CHS >> 4) | (1u << 14), b_hi = (uint32_t)(C::X_CHS >> 4) | (1u << 14);
-                    const uint32_t a_lo = (((sb + C::OFF_DOP) >> 4) & 0x3FFFu) | ((uint32_t)(128 >> 4) << 16);
-                    const uint32_t b_lo = (((sb + C::OFF_XOP) >> 4) & 0x3FFFu) | ((uint32_t)((C::HW * 16) >> 4) << 16);
-                    const bool last = mt + P.S >= P.m_tiles;
-                    if (ptx::elect_one()) {
+            __syncwarp();
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            ti.next(P.tiles_h, P.tiles_w);
+        }
+    } else if (warp == 1) {      // ==================================================== MMA issuer (warp-uniform)
+        constexpr uint32_t idesc = ptx::umma_idesc_bf16(C::UM, NB, 1, 1);   // both operands MN-major
+        // descriptor words: hi = SBO | version, lo = (addr >> 4) | LBO << 16; per-MMA offsets are compile-time adds
+        // A = dY^T: M groups (8 co) SBO = chunk stride, K groups (8 pixels) LBO = 128 B
+        // B = X shifted by the tap: N groups (8 ci) SBO = chunk stride, K groups LBO = one halo row
+        constexpr uint32_t a_hi = (uint32_t)(C::D_CHS >> 4) | (1u << 14), b_hi = (uint32_t)(C::X_CHS >> 4) | (1u << 14);
+        const uint32_t a_lo0 = (((smem_u32 + C::OFF_DOP) >> 4) & 0x3FFFu) | ((uint32_t)(128 >> 4) << 16);
+        const uint32_t b_lo0 = (((smem_u32 + C::OFF_XOP) >> 4) & 0x3FFFu) | ((uint32_t)((C::HW * 16) >> 4) << 16);
+        int stage = 0, phase = 0;
+        for (int it = 0; it < n_work; ++it) {
+            ptx::mbar_wait(bar_full + 8 * stage, phase, 13);
+            if (use_xf) ptx::mbar_wait(bar_xf + 8 * stage, phase, 14);
+            ptx::tc_fence_after();
+            const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4), b_lo = b_lo0 + stage * (C::STAGE_BYTES >> 4);
+            if (ptx::elect_one()) {
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {            // K step = 16 pixels = tile rows 2j, 2j+1
-                            const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)((j * 256) >> 4));
+                for (int j = 0; j < 8; ++j) {            // K step = 16 pixels = tile rows 2j, 2j+1
+                    const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)((j * 256) >> 4));
 #pragma unroll
-                            for (int tap = 0; tap < C::KK; ++tap) {
-                                const uint32_t bo = (uint32_t)((((2 * j + tap / KS) * C::HW + tap % KS) * 16) >> 4);
-                                const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + bo);
-                                ptx::umma_bf16(tmem_base + tap * NB, ad, bd, idesc, (first && j == 0) ? 0u : 1u);
-                            }
-                        }
-                        ptx::umma_commit(bar_empty + 8 * stage);
-                        if (last) ptx::umma_commit(bar_done);
+                    for (int tap = 0; tap < C::KK; ++tap) {
+                        const uint32_t bo = (uint32_t)((((2 * j + tap / KS) * C::HW + tap % KS) * 16) >> 4);
+                        const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + bo);
+                        ptx::umma_bf16(tmem_base + tap * NB, ad, bd, idesc, (it == 0 && j == 0) ? 0u : 1u);
                     }
-                    __syncwarp();
-                    first = false;
-                    if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
                 }
+                ptx::umma_commit(bar_empty + 8 * stage);
+                if (it == n_work - 1) ptx::umma_commit(bar_done);
             }
-        } else if (warp >= 4 && warp < 8) {
-            // ================================================================================ transform warps
+            __syncwarp();
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+        }
+    } else if (warp >= 4 && warp < 4 + kWgXfThreads / 32) {
+        // ================================================================================ transform warps
+        if (use_xf) {
             const int t = threadIdx.x - 128;
-            constexpr int DCH = COB / 8, XCH = NB / 8;
-            float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias gradient of chunk (t % DCH), DCH | 128
+            constexpr int XITEMS = C::NPIX_X * (NB / 8);
+            float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias-gradient partial sums of this thread's chunk
+            TileIter ti;
+            ti.init(split, P.S, P.tiles_h, P.tiles_w);
             int stage = 0, phase = 0;
-            for (int mt = split; mt < P.m_tiles; mt += P.S) {
-                const int n_img = mt / tiles_per_img, rem = mt % tiles_per_img;
-                const int h0 = (rem / P.tiles_w) * kTH - C::PAD, w0 = (rem % P.tiles_w) * kTW - C::PAD;
+            for (int it = 0; it < n_work; ++it) {
+                const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * kTW - C::PAD;
+                const size_t img_px = (size_t)ti.n_img * P.H;
                 ptx::mbar_wait(bar_full + 8 * stage, phase, 15);
-                uint8_t *sb = smem + stage * C::STAGE_BYTES;
-                // dY: [pixel][COB] -> [chunk][pixel][8]
-                for (int i = t; i < 128 * DCH; i += 128) {
-                    const int c = i % DCH, p = i / DCH;
-                    const uint4 v = *reinterpret_cast<const uint4 *>(sb + C::OFF_DRAW + p * (COB * 2) + c * 16);
-                    *reinterpret_cast<uint4 *>(sb + C::OFF_DOP + c * C::D_CHS + p * 16) = v;
-                    float f[8];
-                    unpack8(v, f);
+                const uint32_t sb = smem_u32 + stage * C::STAGE_BYTES;
+                if (want_bias) {
+                    // thread t owns chunk t / TPC and pixels (t % TPC), +TPC, ...: consecutive lanes read consecutive 16-byte units
+                    constexpr int TPC = kWgXfThreads / (COB / 8);
+                    const int bc = t / TPC;
+                    for (int px = t % TPC; px < 128; px += TPC) {
+                        float f[8];
+                        unpack8(ptx::lds128(sb + C::OFF_DOP + (bc * 128 + px) * 16), f);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) bsum[k] += f[k];
+                        for (int k = 0; k < 8; ++k) bsum[k] += f[k];
+                    }
                 }
-                // X halo: [pixel][NB] -> [chunk][pixel][8] with the producer's BN + LeakyReLU + dropout
-                for (int i = t; i < C::NPIX_X * XCH; i += 128) {
-                    const int c = i % XCH, p = i / XCH;
-                    uint4 v = *reinterpret_cast<const uint4 *>(sb + C::OFF_XRAW + p * (NB * 2) + c * 16);
-                    if (P.scale) {
+                if (xform) {
+                    for (int i = t; i < XITEMS; i += kWgXfThreads) {
+                        const int c = i / C::NPIX_X, p = i % C::NPIX_X;
                         const int gh = h0 + p / C::HW, gw = w0 + p % C::HW;
+                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
                         if (gh >= 0 && gh < P.H && gw >= 0 && gw < P.W) {
                             float f[8];
-                            unpack8(v, f);
+                            unpack8(ptx::lds128(sb + C::OFF_XOP + i * 16), f);
                             const int ch = ci0 + c * 8;
                             uint32_t keep = 0xffu;
-                            if (P.dropbits) keep = P.dropbits[((((size_t)n_img * P.H + gh) * P.W + gw) * P.Cin + ch) >> 3];
+                            if (P.dropbits) keep = P.dropbits[(((img_px + gh) * P.W + gw) * P.Cin + ch) >> 3];
 #pragma unroll
                             for (int k = 0; k < 8; ++k) {
                                 float a = fmaf(f[k], s_scale[ch + k], s_shift[ch + k]);
-                                a = a > 0.f ? a : kLeakySlope * a;
+                                a = fmaxf(a, kLeakySlope * a);
                                 if (P.dropbits) a = ((keep >> k) & 1u) ? a * P.inv_keep : 0.f;
                                 f[k] = a;
                             }
                             v = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-                        } else {
-                            v = make_uint4(0u, 0u, 0u, 0u);
                         }
+                        ptx::sts128(sb + C::OFF_XOP + i * 16, v);
                     }
-                    *reinterpret_cast<uint4 *>(sb + C::OFF_XOP + c * C::X_CHS + p * 16) = v;
+                    ptx::fence_proxy_async_smem();
                 }
-                ptx::fence_proxy_async_smem();
                 ptx::mbar_arrive(bar_xf + 8 * stage);
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+                ti.next(P.tiles_h, P.tiles_w);
             }
-            // bias gradient: thread t owns chunk (t % DCH); fixed-order reduce over the 128/DCH threads of a chunk
-            if (cib == 0) {
+            if (want_bias) {     // fixed-order reduce of the per-thread partial sums of each channel
 #pragma unroll
                 for (int k = 0; k < 8; ++k) s_bias[t * 8 + k] = bsum[k];
-                ptx::named_bar_sync(2, 128);
+                ptx::named_bar_sync(2, kWgXfThreads);
                 if (t < COB) {
+                    constexpr int TPC = kWgXfThreads / (COB / 8);
                     const int c = t / 8, k = t % 8;
                     float s = 0.f;
-                    for (int u = c; u < 128; u += DCH) s += s_bias[u * 8 + k];
+                    for (int u = c * TPC; u < (c + 1) * TPC; ++u) s += s_bias[u * 8 + k];
                     if (co0 + t < P.Cout)
                         P.scratch[(size_t)split * ((size_t)C::KK * P.Cin * P.Cout + P.Cout) + (size_t)C::KK * P.Cin * P.Cout + co0 + t] = s;
                 }
             }
-        } else if (warp >= 8) {
-            // ================================================================================ epilogue (once)
-            // accumulator row -> TMEM lane: M=128: lane = row; M=64: lane = (row/16)*32 + row%16 (measured, tests/probes)
-            const int q = warp & 3;
-            const int row = C::UM == 128 ? q * 32 + lane : (lane < 16 ? q * 16 + lane : COB);
-            const int co = co0 + row;
+        }
+    } else if (warp >= 4 + kWgXfThreads / 32) {
+        // ================================================================================ epilogue (once)
+        // accumulator row -> TMEM lane: M=128: lane = row; M=64: lane = (row/16)*32 + row%16 (measured, tests/probes)
+        const int q = warp & 3;
+        const int row = C::UM == 128 ? q * 32 + lane : (lane < 16 ? q * 16 + lane : COB);
+        const int co = co0 + row;
+        if (n_work > 0) {
             ptx::mbar_wait(bar_done, 0, 16);
             ptx::tc_fence_after();
             float *dst = P.scratch + (size_t)split * ((size_t)C::KK * P.Cin * P.Cout + P.Cout);
@@ -315,8 +317,8 @@ int tc_wgrad_run(int ks, int N, int H, int W, int Cin, int Cout, int cin_real, i
     wg_shape(N, H, W, Cin, Cout, NB, COB, P.ci_blocks, P.co_blocks, P.S, P.m_tiles);
     HPFG_REQUIRE(tc_wgrad_scratch_floats(N, H, W, Cin, Cout, ks) <= scratch_floats, "tc_wgrad: scratch too small");
     CUtensorMap mx, md;
-    HPFG_RETURN_IF(make_map(&mx, x, N, H, W, Cin, NB, kTW + ks - 1, kTH + ks - 1));
-    HPFG_RETURN_IF(make_map(&md, dy, N, H, W, Cout, COB, kTW, kTH));
+    HPFG_RETURN_IF(make_map_chunked(&mx, x, N, H, W, Cin, NB / 8, kTW + ks - 1, kTH + ks - 1));
+    HPFG_RETURN_IF(make_map_chunked(&md, dy, N, H, W, Cout, COB / 8, kTW, kTH));
     P.scale = xf.scale; P.shift = xf.shift;
     P.dropbits = reinterpret_cast<const uint8_t *>(xf.drop.bits); P.inv_keep = xf.drop.inv_keep;
     P.scratch = scratch;

@@ -24,6 +24,40 @@ def medical_lr(cur_itrs, base_lr, max_iterations):
     return base_lr * (1.0 - (cur_itrs - 2) / max_iterations) ** 0.9
 
 
+def gradient_buckets(in_channels, num_classes):
+    """[(offset, count)] of the flat-gradient buckets in the order backward completes them (tail of the
+    parameter list first: out_conv/up4/up3 | up2/up1 | down4 | in_conv..down3)."""
+    import ctypes
+    offs, cnts = (ctypes.c_int64 * 4)(), (ctypes.c_int64 * 4)()
+    L.check(L.lib().hpfg_unet_bucket_layout(in_channels, num_classes, offs, cnts), "hpfg_unet_bucket_layout")
+    return [(int(o), int(c)) for o, c in zip(offs, cnts)]
+
+
+def allreduce_flat_buckets(flat_grad, buckets, group=None, before_bucket=None, stream=None):
+    """Sum-all-reduce ``flat_grad`` bucket by bucket (async), returning the work handles.  ``before_bucket(i)`` is
+    called before bucket i is enqueued (the CUDA path makes the comm stream wait for that bucket's event there).
+    Works for CPU tensors + gloo (host-logic tests) and CUDA tensors + NCCL alike."""
+    import contextlib
+    import torch.distributed as dist
+    works = []
+    for i, (off, cnt) in enumerate(buckets):
+        if before_bucket is not None:
+            before_bucket(i)
+        ctx = torch.cuda.stream(stream) if stream is not None else contextlib.nullcontext()
+        with ctx:
+            works.append(dist.all_reduce(flat_grad[off:off + cnt], group=group, async_op=True))
+    return works
+
+
+def shard_batch(x_l, x_u, y, rank, world):
+    """Data-parallel split that keeps the labeled:unlabeled ratio per rank (both sub-batches are split, because the
+    supervised and consistency terms normalise over their own pixels)."""
+    n_l, n_u = x_l.shape[0], x_u.shape[0]
+    assert n_l % world == 0 and n_u % world == 0, "labeled and unlabeled batch sizes must divide by the world size"
+    a, b = n_l // world, n_u // world
+    return x_l[rank * a:(rank + 1) * a], x_u[rank * b:(rank + 1) * b], y[rank * a:(rank + 1) * a]
+
+
 class _StepBase:
     def __init__(self, *, lr=0.01, momentum=0.9, weight_decay=1e-4, total_itrs=30000, consistency=0.1,
                  consistency_rampup=200.0, process_group=None):
@@ -56,17 +90,14 @@ class _StepBase:
         """Bucketed gradient all-reduce overlapped with the tail of backward: the comm stream waits on the
         per-bucket events the plan recorded, NCCL runs there, the compute stream joins before the SGD pass."""
         import ctypes
-        import torch.distributed as dist
         if self._comm is None:
             self._comm = torch.cuda.Stream(device=grads.device)
+            self._buckets = gradient_buckets(self.in_channels, self.num_classes)
         lib = L.lib()
-        off, cnt = ctypes.c_int64(), ctypes.c_int64()
-        works = []
-        for b in range(lib.hpfg_unet_num_buckets(plan.handle)):
-            L.check(lib.hpfg_unet_bucket_range(plan.handle, b, ctypes.byref(off), ctypes.byref(cnt)))
-            L.check(lib.hpfg_unet_bucket_wait(plan.handle, b, ctypes.c_void_p(self._comm.cuda_stream)))
-            with torch.cuda.stream(self._comm):
-                works.append(dist.all_reduce(grads[off.value:off.value + cnt.value], group=self.pg, async_op=True))
+        comm = ctypes.c_void_p(self._comm.cuda_stream)
+        works = allreduce_flat_buckets(
+            grads, self._buckets, self.pg, stream=self._comm,
+            before_bucket=lambda b: L.check(lib.hpfg_unet_bucket_wait(plan.handle, b, comm), "hpfg_unet_bucket_wait"))
         for w in works:
             w.wait()            # stream-level wait on the compute stream, not a host sync
 
@@ -89,6 +120,7 @@ class MeanTeacherStep(_StepBase):
     def __init__(self, model, ema_model, *, ema_decay=0.99, **kw):
         super().__init__(**kw)
         self.model, self.ema_model, self.ema_decay = model, ema_model, ema_decay
+        self.in_channels, self.num_classes = model.in_channels, model.num_classes
         model.train()
         ema_model.train()                               # the teacher runs in train() mode (2017_03...:70)
         model.ensure_flat()
@@ -115,6 +147,7 @@ class CPSStep(_StepBase):
     def __init__(self, model1, model2, **kw):
         super().__init__(**kw)
         self.m1, self.m2 = model1, model2
+        self.in_channels, self.num_classes = model1.in_channels, model1.num_classes
         model1.train()
         model2.train()
         model1.ensure_flat()
@@ -141,6 +174,7 @@ class UAMTStep(_StepBase):
     def __init__(self, model, ema_model, *, ema_decay=0.99, T=8, **kw):
         super().__init__(**kw)
         self.model, self.ema_model, self.ema_decay, self.T = model, ema_model, ema_decay, T
+        self.in_channels, self.num_classes = model.in_channels, model.num_classes
         model.train()
         ema_model.train()
         model.ensure_flat()

@@ -98,6 +98,8 @@ int hpfg_unet_backward(hpfg_unet_plan_t plan, const float *params, const float *
 int hpfg_unet_num_buckets(hpfg_unet_plan_t plan);
 int hpfg_unet_bucket_range(hpfg_unet_plan_t plan, int bucket, int64_t *offset_host, int64_t *count_host);
 int hpfg_unet_bucket_wait(hpfg_unet_plan_t plan, int bucket, void *comm_stream);
+/* The same ranges without a plan (host only): int64[4] offsets / counts, bucket 0 first. */
+int hpfg_unet_bucket_layout(int in_channels, int num_classes, int64_t *offsets_host, int64_t *counts_host);
 
 /* Debug / parity taps: copy an internal activation of the last forward as fp32 NCHW.  name is one of the
  * conv names ("encoder.in_conv.conv_conv.0", ..., raw conv outputs incl. bias) . */
