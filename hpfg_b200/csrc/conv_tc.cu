@@ -71,6 +71,7 @@ struct TcConvParams {
     float *out_nchw;          // if set: write fp32 NCHW [N,out_c_real,H,W] (+bias) instead of bf16 NHWC (out_conv logits)
     int out_c_real;
     int N, H, W, Cin, Cout, tiles_h, tiles_w, m_tiles, n_blocks, k_chunks;
+    int dbg;                  // bottleneck-isolation switches (env HPFG_TC_DBG, profiles/layer_bench.py only): 1 no MMA, 2 no stores, 4 no stats, 8 no TMA, 16 no transform
 };
 
 // Reduce 16 per-lane values over the 32 lanes of a warp with 16 shuffles (recursive halving); afterwards every
@@ -148,7 +149,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     const int total_work = P.m_tiles * P.n_blocks;
     const int nb = blockIdx.x % P.n_blocks, mt0 = blockIdx.x / P.n_blocks, mstep = gridDim.x / P.n_blocks;
     const int n_work = (total_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-    const bool xform = P.scale != nullptr;
+    const bool xform = P.scale != nullptr && !(P.dbg & 16);
 
     if (warp == 0) {
         // ================================================================= TMA producer (warp-uniform, one lane issues)
@@ -156,6 +157,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             TileIter ti;
             ti.init(mt0, mstep, P.tiles_h, P.tiles_w);
             int stage = 0, phase = 0;
+            const uint32_t op_bytes = (P.dbg & 8) ? 0u : (uint32_t)C::OP_BYTES;
             const bf16 *bsrc = P.bpk + (size_t)nb * P.k_chunks * (C::B_BYTES / 2);
             for (int it = 0; it < n_work; ++it) {
                 const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * C::TWP - C::PAD;
@@ -164,12 +166,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                     const uint32_t sb = stage_u32 + stage * C::STAGE_BYTES, fb = bar_full + 8 * stage;
                     if (ptx::elect_one()) {
                         if (RES) {       // weights ride along with the first tile only and stay resident
-                            ptx::mbar_expect_tx(fb, C::OP_BYTES + (it == 0 ? C::B_BYTES : 0));
+                            ptx::mbar_expect_tx(fb, op_bytes + (it == 0 ? C::B_BYTES : 0));
                             if (it == 0) ptx::bulk_load(ptx::smem_u32(res_b), P.bpk, C::B_BYTES, fb);
                         } else {
-                            ptx::mbar_expect_tx(fb, C::OP_BYTES + C::B_BYTES);
+                            ptx::mbar_expect_tx(fb, op_bytes + C::B_BYTES);
                             ptx::bulk_load(sb + C::OFF_B, bsrc + (size_t)kc * (C::B_BYTES / 2), C::B_BYTES, fb);
                         }
+                        if (!(P.dbg & 8))
                         ptx::tma_load_5d(sb, &tmA, fb, 0, w0, h0, kc * C::NCH, ti.n_img);
                     }
                     __syncwarp();
@@ -199,6 +202,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                     const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
                     const uint32_t b_lo = RES ? b_lo0 : b_lo0 + stage * (C::STAGE_BYTES >> 4);
                     if (ptx::elect_one()) {
+                    if (!(P.dbg & 1))
 #pragma unroll
                     for (int j = 0; j < MT; ++j) {                 // UMMA tile j = output columns 8j..8j+7 of the stage
 #pragma unroll
@@ -297,13 +301,14 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                 float v[16];
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = valid ? __uint_as_float(r[j]) : 0.f;
-                if (P.stats) {
+                if (P.stats && !(P.dbg & 4)) {
                     float sq[16];
 #pragma unroll
                     for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
                     run1[gidx] += butterfly16(v, lane);
                     run2[gidx] += butterfly16(sq, lane);
                 }
+                if (P.dbg & 2) continue;
                 if (valid && P.out_nchw) {
                     float *o = P.out_nchw + ((size_t)ti.n_img * P.out_c_real * P.H + gh) * P.W + gw;
 #pragma unroll
@@ -469,6 +474,7 @@ static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void
     P.N = N; P.H = H; P.W = W; P.Cin = cin_v; P.Cout = cout_v;
     P.tiles_h = (H + kTH - 1) / kTH; P.tiles_w = (W + kTW * mt - 1) / (kTW * mt);
     P.m_tiles = N * P.tiles_h * P.tiles_w; P.n_blocks = cout_v / BN; P.k_chunks = cin_v / KC;
+    { static const char *e = getenv("HPFG_TC_DBG"); P.dbg = e ? atoi(e) : 0; }
     if (P_out) *P_out = std::min(P.m_tiles * P.n_blocks, kNumSMs);
     return ks == 3 ? launch_ks<3>(KC, BN, mt, map, P, s) : launch_ks<1>(KC, BN, mt, map, P, s);
 }
