@@ -22,6 +22,19 @@ def run(op, n, cin, cout, ks, res, iters=20):
 
 if __name__ == "__main__":
     torch.cuda.init()
+    if len(sys.argv) > 1 and sys.argv[1] == "sweep":
+        # bottleneck isolation: python profiles/layer_bench.py sweep N "cin cout ks res" ... ; flags 1 no MMA, 2 no stores, 4 no stats, 8 no TMA
+        n = int(sys.argv[2])
+        for shape in sys.argv[3:]:
+            cin, cout, ks, res = [int(v) for v in shape.split()]
+            for op in (0, 1):
+                row = []
+                for d in [int(v) for v in os.environ.get("SWEEP_FLAGS", "0,1,2,4,8,3,9,11,15").split(",")]:
+                    os.environ["HPFG_TC_DBG"] = str(d)
+                    row.append("%d:%.1f" % (d, 1e3 * run(op, n, cin, cout, ks, res, 20)))
+                os.environ["HPFG_TC_DBG"] = "0"
+                print("(%s) op=%d  dbg:us  %s" % (shape, op, "  ".join(row)), flush=True)
+        sys.exit(0)
     if len(sys.argv) > 2:
         n, op, cin, cout, ks, res, iters = [int(v) for v in sys.argv[1:8]]
         print("%.2f us" % (1e3 * run(op, n, cin, cout, ks, res, iters)))
