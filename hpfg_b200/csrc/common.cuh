@@ -5,6 +5,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <string>
+#include <utility>
 
 #include "../../include/hpfg_b200.h"
 
@@ -85,6 +86,52 @@ __device__ __forceinline__ uint4 philox4x32_10(uint2 key, uint4 ctr) {
         key.y += W1;
     }
     return ctr;
+}
+
+// ---- programmatic dependent launch (PDL) ----------------------------------------------------------------------
+// Every kernel of this library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and runs
+// pdl_prologue() (or launch_dependents early + wait after its private setup) before it touches global memory the
+// previous kernel may still be writing: the next kernel's launch latency and prologue overlap this kernel's tail.
+// griddepcontrol.wait returns only when the prerequisite grid has completed and flushed, so correctness never
+// depends on where launch_dependents sits.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+    pdl_launch_dependents();
+    pdl_wait();
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
+// ---- division by a runtime constant without the (very slow) 64-bit integer divide ------------------------------
+// q = (umulhi(n, m) + n) >> s, exact for n < 2^31 (all element counts here are checked against that on the host).
+struct FastDiv {
+    uint32_t d, m, s;
+};
+inline FastDiv make_fastdiv(uint32_t d) {
+    FastDiv f;
+    f.d = d;
+    f.s = 0;
+    while ((1u << f.s) < d) ++f.s;
+    f.m = (uint32_t)(((uint64_t(1) << 32) * ((uint64_t(1) << f.s) - d)) / d + 1);
+    return f;
+}
+__device__ __forceinline__ uint32_t fast_div(uint32_t n, const FastDiv &f) { return (__umulhi(n, f.m) + n) >> f.s; }
+__device__ __forceinline__ void fast_divmod(uint32_t n, const FastDiv &f, uint32_t &q, uint32_t &r) {
+    q = fast_div(n, f);
+    r = n - q * f.d;
 }
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }

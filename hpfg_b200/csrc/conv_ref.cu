@@ -39,6 +39,7 @@ template <typename TI, typename TO, int KS>
 __global__ void __launch_bounds__(256) conv_ref_fprop_kernel(TView in, TView out, const float *__restrict__ wpk,
                                                              const float *__restrict__ bias, int N, int H, int W, int Cin,
                                                              int Cout, LoadXform xf, float *__restrict__ stats) {
+    pdl_prologue();
     constexpr int TS = kTile + KS - 1, KK = KS * KS;
     __shared__ float in_s[kCK][TS * TS + 1];
     __shared__ float w_s[KK][kCK][kBN];
@@ -126,9 +127,9 @@ int conv_ref_fprop(TView in, TView out, const float *wpk, const float *bias, int
     ProfScope _prof(PROF_CONV_CUDA, s);
     dim3 grid(conv_ref_num_tiles(N, H, W), (Cout + kBN - 1) / kBN);
     if (KS == 3)
-        conv_ref_fprop_kernel<TI, TO, 3><<<grid, 256, 0, s>>>(in, out, wpk, bias, N, H, W, Cin, Cout, xf, stats);
+        HPFG_CUDA_CHECK(launch_pdl(conv_ref_fprop_kernel<TI, TO, 3>, grid, 256, 0, s, in, out, wpk, bias, N, H, W, Cin, Cout, xf, stats));
     else if (KS == 1)
-        conv_ref_fprop_kernel<TI, TO, 1><<<grid, 256, 0, s>>>(in, out, wpk, bias, N, H, W, Cin, Cout, xf, stats);
+        HPFG_CUDA_CHECK(launch_pdl(conv_ref_fprop_kernel<TI, TO, 1>, grid, 256, 0, s, in, out, wpk, bias, N, H, W, Cin, Cout, xf, stats));
     else {
         set_error("conv_ref_fprop: kernel size must be 1 or 3");
         return HPFG_ERR_UNSUPPORTED;
@@ -141,6 +142,7 @@ int conv_ref_fprop(TView in, TView out, const float *wpk, const float *bias, int
 template <typename TI, typename TD, int KS>
 __global__ void __launch_bounds__(256) conv_ref_wgrad_kernel(TView in, TView dout, int N, int H, int W, int Cin, int Cout,
                                                              LoadXform xf, float *__restrict__ scratch, int co_chunks) {
+    pdl_prologue();
     constexpr int TS = kTile + KS - 1, KK = KS * KS;
     __shared__ float in_s[kCK][TS * TS + 1];
     __shared__ float d_s[kTile * kTile][kBN];
@@ -199,6 +201,7 @@ __global__ void __launch_bounds__(256) conv_ref_wgrad_kernel(TView in, TView dou
 __global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float *__restrict__ scratch, int S, int Cin, int Cout, int KK,
                                                            float *__restrict__ dw_oihw, float *__restrict__ dbias,
                                                            int accumulate) {
+    pdl_prologue();
     const int64_t per = (int64_t)KK * Cin * Cout + Cout;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += (int64_t)gridDim.x * blockDim.x) {
         float s = 0.f;
@@ -237,9 +240,9 @@ int conv_ref_wgrad(TView in, TView dout, int N, int H, int W, int Cin, int Cout,
     const int co_chunks = (Cout + kBN - 1) / kBN;
     dim3 grid(((Cin + kCK - 1) / kCK) * co_chunks, S);
     if (KS == 3)
-        conv_ref_wgrad_kernel<TI, TD, 3><<<grid, 256, 0, s>>>(in, dout, N, H, W, Cin, Cout, xf, scratch, co_chunks);
+        HPFG_CUDA_CHECK(launch_pdl(conv_ref_wgrad_kernel<TI, TD, 3>, grid, 256, 0, s, in, dout, N, H, W, Cin, Cout, xf, scratch, co_chunks));
     else if (KS == 1)
-        conv_ref_wgrad_kernel<TI, TD, 1><<<grid, 256, 0, s>>>(in, dout, N, H, W, Cin, Cout, xf, scratch, co_chunks);
+        HPFG_CUDA_CHECK(launch_pdl(conv_ref_wgrad_kernel<TI, TD, 1>, grid, 256, 0, s, in, dout, N, H, W, Cin, Cout, xf, scratch, co_chunks));
     else {
         set_error("conv_ref_wgrad: kernel size must be 1 or 3");
         return HPFG_ERR_UNSUPPORTED;
@@ -248,7 +251,7 @@ int conv_ref_wgrad(TView in, TView dout, int N, int H, int W, int Cin, int Cout,
     const int64_t per = (int64_t)KS * KS * Cin * Cout + Cout;
     int blocks = (int)((per + 255) / 256);
     if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-    wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(scratch, S, Cin, Cout, KS * KS, dw_oihw, dbias, accumulate);
+    HPFG_CUDA_CHECK(launch_pdl(wgrad_reduce_kernel, blocks, 256, 0, s, scratch, S, Cin, Cout, KS * KS, dw_oihw, dbias, accumulate));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -256,6 +259,7 @@ int conv_ref_wgrad(TView in, TView dout, int N, int H, int W, int Cin, int Cout,
 // ---------------------------------------------------------------------------------------- weight packing
 __global__ void pack_weights_ref_kernel(const float *__restrict__ w, float *__restrict__ wf, float *__restrict__ wd, int Cin,
                                         int Cout, int KS) {
+    pdl_prologue();
     const int KK = KS * KS;
     const int64_t total = (int64_t)Cout * Cin * KK;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
@@ -271,7 +275,7 @@ int pack_weights_ref(const float *w_oihw, float *wpk_fprop, float *wpk_dgrad, in
     const int64_t total = (int64_t)Cout * Cin * KS * KS;
     int blocks = (int)((total + 255) / 256);
     if (blocks > kNumSMs * 4) blocks = kNumSMs * 4;
-    pack_weights_ref_kernel<<<blocks, 256, 0, s>>>(w_oihw, wpk_fprop, wpk_dgrad, Cin, Cout, KS);
+    HPFG_CUDA_CHECK(launch_pdl(pack_weights_ref_kernel, blocks, 256, 0, s, w_oihw, wpk_fprop, wpk_dgrad, Cin, Cout, KS));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }

@@ -39,33 +39,42 @@ struct PackTable {
     PackEntry e[kMaxPack];
 };
 
+// blockIdx.y = table entry (one layer, fprop or dgrad order); one thread packs 8 consecutive k (one 16-byte store)
 __global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ params, bf16 *__restrict__ dst, const PackTable T) {
-    for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < T.total; g += (long long)gridDim.x * blockDim.x) {
-        int lo = 0;
-        while (lo + 1 < T.n && T.e[lo + 1].dst_begin <= g) ++lo;
-        const PackEntry &E = T.e[lo];
-        long long e = g - E.dst_begin;
-        const int cin_v = E.dgrad ? E.cout : E.cin;
-        const int k_chunks = cin_v / E.KC;
-        const int k = (int)(e % 8);
-        e /= 8;
-        const int n = (int)(e % E.BN);
-        e /= E.BN;
-        const int k8 = (int)(e % (E.KC / 8));
-        e /= (E.KC / 8);
-        const int tap = (int)(e % E.kk);
-        e /= E.kk;
-        const int kc = (int)(e % k_chunks);
-        const int nb = (int)(e / k_chunks);
-        const int co_v = nb * E.BN + n, ci_v = kc * E.KC + k8 * 8 + k;
-        float w = 0.f;
-        if (!E.dgrad) {
-            if (co_v < E.cout_real && ci_v < E.cin_real) w = params[E.w_off + ((long long)co_v * E.cin_real + ci_v) * E.kk + tap];
-        } else if (ci_v < E.cout_real && co_v < E.cin_real) {       // rot180 + transpose
-            w = params[E.w_off + ((long long)ci_v * E.cin_real + co_v) * E.kk + (E.kk - 1 - tap)];
+    pdl_prologue();
+    const PackEntry &E = T.e[blockIdx.y];
+    const unsigned cin_v = E.dgrad ? E.cout : E.cin, cout_v = E.dgrad ? E.cin : E.cout;
+    const unsigned groups = cin_v * cout_v * E.kk / 8;          // 8-element groups of this entry
+    const unsigned k8s = E.KC / 8, k_chunks = cin_v / E.KC;
+    for (unsigned g = blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += gridDim.x * blockDim.x) {
+        unsigned e = g;
+        const unsigned n = e % E.BN;   e /= E.BN;
+        const unsigned k8 = e % k8s;   e /= k8s;
+        const unsigned tap = e % E.kk; e /= E.kk;
+        const unsigned kc = e % k_chunks, nb = e / k_chunks;
+        const unsigned co_v = nb * E.BN + n, ci0 = kc * E.KC + k8 * 8;
+        float w[8];
+#pragma unroll
+        for (unsigned k = 0; k < 8; ++k) {
+            const unsigned ci_v = ci0 + k;
+            w[k] = 0.f;
+            if (!E.dgrad) {
+                if (co_v < (unsigned)E.cout_real && ci_v < (unsigned)E.cin_real) w[k] = params[E.w_off + ((long long)co_v * E.cin_real + ci_v) * E.kk + tap];
+            } else if (ci_v < (unsigned)E.cout_real && co_v < (unsigned)E.cin_real) {       // rot180 + transpose
+                w[k] = params[E.w_off + ((long long)ci_v * E.cin_real + co_v) * E.kk + (E.kk - 1 - tap)];
+            }
         }
-        dst[g] = __float2bfloat16_rn(w);
+        *reinterpret_cast<uint4 *>(dst + E.dst_begin + (long long)g * 8) = make_uint4(pack2(w[0], w[1]), pack2(w[2], w[3]), pack2(w[4], w[5]), pack2(w[6], w[7]));
     }
+}
+
+static dim3 pack_grid(const PackTable &T) {
+    long long mx = 1;
+    for (int i = 0; i < T.n; ++i) {
+        const long long n = (i + 1 < T.n ? T.e[i + 1].dst_begin : T.total) - T.e[i].dst_begin;
+        mx = std::max(mx, n);
+    }
+    return dim3((unsigned)std::min<long long>((mx / 8 + 255) / 256, 64), (unsigned)T.n);
 }
 
 // ------------------------------------------------------------------------------------------ host side
@@ -214,8 +223,7 @@ void tc_plan_free(hpfg_unet_plan *p) {
 int tc_pack_all(hpfg_unet_plan *p, const float *params, cudaStream_t s) {
     ProfScope _prof(PROF_PACK, s);
     auto *st = reinterpret_cast<TcPlanState *>(p->tc);
-    const int blocks = (int)std::min<long long>((st->table.total + 255) / 256, (long long)kNumSMs * 8);
-    tc_pack_kernel<<<blocks, 256, 0, s>>>(params, st->packed, st->table);
+    HPFG_CUDA_CHECK(launch_pdl(tc_pack_kernel, pack_grid(st->table), 256, 0, s, params, st->packed, st->table));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -276,6 +284,7 @@ int tc_wgrad(hpfg_unet_plan *p, int conv, const void *in, LoadXform xf, const vo
 using namespace hpfg;
 
 __global__ void tc_debug_reduce_stats(const float *partials, int P, int C2, float *out) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C2) return;
     double s = 0.0;
@@ -301,14 +310,14 @@ extern "C" int hpfg_conv_tc_debug(int op, int N, int H, int W, int cin, int cout
     const int m_tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
     HPFG_CUDA_CHECK(cudaMalloc(&packed, (size_t)T.total * 2));
     HPFG_CUDA_CHECK(cudaMalloc(&partials, (size_t)m_tiles * 2 * cout_v * 4));
-    tc_pack_kernel<<<(int)std::min<long long>((T.total + 255) / 256, 1024), 256, 0, s>>>(w_oihw, packed, T);
+    HPFG_CUDA_CHECK(launch_pdl(tc_pack_kernel, pack_grid(T), 256, 0, s, w_oihw, packed, T));
     HPFG_LAUNCH_CHECK();
     LoadXform xf{};
     xf.scale = scale; xf.shift = shift; xf.drop.bits = nullptr; xf.drop.inv_keep = 1.f;
     int P = 0;
     int rc = tc_run(ks, N, H, W, cin_v, cout_v, in_bf16_nhwc, out_bf16_nhwc, packed, bias, xf, stats_out ? partials : nullptr, &P, s);
     if (rc == HPFG_OK && stats_out) {
-        tc_debug_reduce_stats<<<(2 * cout_v + 127) / 128, 128, 0, s>>>(partials, P, 2 * cout_v, stats_out);
+        HPFG_CUDA_CHECK(launch_pdl(tc_debug_reduce_stats, (2 * cout_v + 127) / 128, 128, 0, s, partials, P, 2 * cout_v, stats_out));
         ++g_launch_count;
     }
     cudaStreamSynchronize(s);

@@ -117,6 +117,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     float *s_shift = s_scale + 256;
     float *s_part = s_shift + 256;                                 // [4 warps][2*BN]
 
+    pdl_launch_dependents();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t bar_full = ptx::smem_u32(bars), bar_xf = bar_full + 8 * C::STAGES, bar_empty = bar_xf + 8 * C::STAGES;
     const uint32_t bar_tfull = bar_empty + 8 * C::STAGES, bar_tempty = bar_tfull + 8 * C::NACC;
@@ -136,6 +137,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         ptx::prefetch_tensormap(&tmA);
     }
     if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+    pdl_wait();       // everything above is private setup; below reads what the previous kernel wrote
     if (XF > 0)
         for (int i = threadIdx.x; i < P.Cin; i += blockDim.x) { s_scale[i] = P.scale[i]; s_shift[i] = P.shift[i]; }
     ptx::tc_fence_before();
@@ -321,16 +323,22 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         float run1[NRUN], run2[NRUN];
 #pragma unroll
         for (int i = 0; i < NRUN; ++i) run1[i] = run2[i] = 0.f;
-        const bool want_stats = P.stats != nullptr && !(P.dbg & 4);
+        const bool want_stats = !NCHW && P.stats != nullptr && !(P.dbg & 4);    // the logits layer has no BatchNorm
         const bool no_store = (P.dbg & 2) != 0;
         // store one tile-row pixel: NC consecutive output channels starting at channel c0 of this n-block
+        // NCHW (logits) kernels: BN == 16, one n-block; the bias of the real output channels lives in registers
+        float bias_r[NCHW ? 16 : 1];
+        const size_t plane = (size_t)P.H * P.W;
+        if constexpr (NCHW) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) bias_r[i] = (P.bias && i < P.out_c_real) ? P.bias[i] : 0.f;
+        }
         auto store16 = [&](const float *v, size_t pix, int n_img, int gh, int gw, int c0) {
-            if (NCHW) {
+            if constexpr (NCHW) {
                 float *o = P.out_nchw + ((size_t)n_img * P.out_c_real * P.H + gh) * P.W + gw;
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
-                    if (nb * BN + c0 + i < P.out_c_real)
-                        o[(size_t)(nb * BN + c0 + i) * P.H * P.W] = v[i] + (P.bias ? P.bias[nb * BN + c0 + i] : 0.f);
+                    if (i < P.out_c_real) o[(size_t)i * plane] = v[i] + bias_r[i];
             } else {
                 bf16 *orow = P.out + pix * P.Cout + nb * BN + c0;
                 float b[16];
@@ -414,7 +422,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             if (q == 0) HPFG_TRACE(4, it);
             ti.next(P.tiles_h, P.tiles_w);
         }
-        if (P.stats) {    // once per CTA: combine lanes and the four epilogue warps, write this CTA's partial row
+        if (!NCHW && P.stats) {    // once per CTA: combine lanes and the four epilogue warps, write this CTA's partial row
 #pragma unroll
             for (int gidx = 0; gidx < NG; ++gidx) {
                 float c1, c2;
@@ -466,7 +474,7 @@ static int tc_launch_one(const CUtensorMap &map, const TcConvParams &P, cudaStre
     }
     const int total = P.m_tiles * P.n_blocks;
     const int grid = total < kNumSMs ? total : kNumSMs;
-    tc_conv_kernel<KS, KC, BN, RES, MT, XF, NCHW><<<grid, kTcThreads, C::SMEM_BYTES, s>>>(map, P);
+    HPFG_CUDA_CHECK(launch_pdl(tc_conv_kernel<KS, KC, BN, RES, MT, XF, NCHW>, grid, kTcThreads, C::SMEM_BYTES, s, map, P));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }

@@ -4,6 +4,8 @@
 // nn.Upsample(scale_factor=2, bilinear, align_corners=True) / torch.cat as wired in model/unet.py:12-58.
 #include "glue.cuh"
 
+#include <algorithm>
+
 namespace hpfg {
 
 template <typename T> struct Vec;
@@ -54,6 +56,7 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restric
                                                           const float *__restrict__ conv_bias, float *running_mean,
                                                           float *running_var, int64_t *counter, int training,
                                                           BnState st) {
+    pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= C) return;
     const int c = warp;
@@ -86,15 +89,16 @@ int bn_finalize(const float *partials, int P, int C, int64_t count, const float 
                 BnState st, cudaStream_t s) {
     ProfScope _prof(PROF_GLUE, s);
     const double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
-    bn_finalize_kernel<<<ceil_div(C * 32, 256), 256, 0, s>>>(partials, P, C, 1.0 / (double)count, unbias, gamma,
+    HPFG_CUDA_CHECK(launch_pdl(bn_finalize_kernel, ceil_div(C * 32, 256), 256, 0, s, partials, P, C, 1.0 / (double)count, unbias, gamma,
                                                              beta, conv_bias, running_mean, running_var, counter,
-                                                             training, st);
+                                                             training, st));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
 
 __global__ void bn_eval_affine_kernel(int C, const float *gamma, const float *beta, const float *conv_bias,
                                       const float *rm, const float *rv, BnState st) {
+    pdl_prologue();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     const float invstd = 1.f / sqrtf(rv[c] + kBnEps);
@@ -108,7 +112,7 @@ __global__ void bn_eval_affine_kernel(int C, const float *gamma, const float *be
 int bn_eval_affine(int C, const float *gamma, const float *beta, const float *conv_bias, const float *running_mean,
                    const float *running_var, BnState st, cudaStream_t s) {
     ProfScope _prof(PROF_GLUE, s);
-    bn_eval_affine_kernel<<<ceil_div(C, 128), 128, 0, s>>>(C, gamma, beta, conv_bias, running_mean, running_var, st);
+    HPFG_CUDA_CHECK(launch_pdl(bn_eval_affine_kernel, ceil_div(C, 128), 128, 0, s, C, gamma, beta, conv_bias, running_mean, running_var, st));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -116,16 +120,16 @@ int bn_eval_affine(int C, const float *gamma, const float *beta, const float *co
 // --------------------------------------------------------------------------------------------- pool_act
 template <typename T>
 __global__ void __launch_bounds__(256) pool_act_kernel(const T *__restrict__ raw, T *__restrict__ pooled, int N, int H,
-                                                       int W, int C, BnState bn) {
+                                                       int W, int C, BnState bn, FastDiv dCV, FastDiv dWo, FastDiv dHo) {
+    pdl_prologue();
     constexpr int V = Vec<T>::N;
-    const int CV = C / V, Ho = H >> 1, Wo = W >> 1;
-    const int64_t total = (int64_t)N * Ho * Wo * CV;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % CV);
-        int64_t pix = i / CV;
-        const int wo = (int)(pix % Wo);
-        pix /= Wo;
-        const int ho = (int)(pix % Ho), n = (int)(pix / Ho);
+    const int Ho = H >> 1, Wo = W >> 1;
+    const uint32_t total = (uint32_t)N * Ho * Wo * dCV.d;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t cv, pix, wo, ho, n;
+        fast_divmod(i, dCV, pix, cv);
+        fast_divmod(pix, dWo, pix, wo);
+        fast_divmod(pix, dHo, n, ho);
         float sc[V], sh[V], best[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) { sc[k] = bn.scale[cv * V + k]; sh[k] = bn.shift[cv * V + k]; }
@@ -148,7 +152,8 @@ template <typename T>
 int pool_act(const T *raw, T *pooled, int N, int H, int W, int C, BnState bn, cudaStream_t s) {
     ProfScope _prof(PROF_GLUE, s);
     const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (C / Vec<T>::N);
-    pool_act_kernel<T><<<ew_grid(total), 256, 0, s>>>(raw, pooled, N, H, W, C, bn);
+    HPFG_REQUIRE(total < (1ll << 31), "pool_act: tensor too large for 32-bit indexing");
+    HPFG_CUDA_CHECK(launch_pdl(pool_act_kernel<T>, ew_grid(total), 256, 0, s, raw, pooled, N, H, W, C, bn, make_fastdiv(C / Vec<T>::N), make_fastdiv(W / 2), make_fastdiv(H / 2)));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -167,16 +172,17 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, 
 
 template <typename T>
 __global__ void __launch_bounds__(256) upcat_kernel(const T *__restrict__ raw_skip, BnState bn, const T *__restrict__ low,
-                                                    T *__restrict__ cat, int N, int h, int w, int F, float sh_, float sw_) {
+                                                    T *__restrict__ cat, int N, int h, int w, int F, float sh_, float sw_,
+                                                    FastDiv dCV, FastDiv dW, FastDiv dH) {
+    pdl_prologue();
     constexpr int V = Vec<T>::N;
-    const int H = 2 * h, W = 2 * w, FV = F / V, CV = 2 * FV;
-    const int64_t total = (int64_t)N * H * W * CV;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % CV);
-        int64_t pix = i / CV;
-        const int x = (int)(pix % W);
-        pix /= W;
-        const int y = (int)(pix % H), n = (int)(pix / H);
+    const int H = 2 * h, W = 2 * w, FV = F / V;
+    const uint32_t total = (uint32_t)N * H * W * dCV.d;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t cv, pix, x, y, n;
+        fast_divmod(i, dCV, pix, cv);
+        fast_divmod(pix, dW, pix, x);
+        fast_divmod(pix, dH, n, y);
         float out[V];
         if (cv < FV) {   // skip half: the encoder feature = leaky(bn(raw))
             float v[V];
@@ -208,7 +214,8 @@ int upcat(const T *raw_skip, BnState bn_skip, const T *low, T *cat, int N, int h
     const int64_t total = (int64_t)N * 4 * h * w * (2 * F / Vec<T>::N);
     const float sh_ = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
     const float sw_ = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
-    upcat_kernel<T><<<ew_grid(total), 256, 0, s>>>(raw_skip, bn_skip, low, cat, N, h, w, F, sh_, sw_);
+    HPFG_REQUIRE(total < (1ll << 31), "upcat: tensor too large for 32-bit indexing");
+    HPFG_CUDA_CHECK(launch_pdl(upcat_kernel<T>, ew_grid(total), 256, 0, s, raw_skip, bn_skip, low, cat, N, h, w, F, sh_, sw_, make_fastdiv(2 * F / Vec<T>::N), make_fastdiv(2 * w), make_fastdiv(2 * h)));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -220,6 +227,7 @@ template <typename T, int MODE>
 __global__ void __launch_bounds__(256) bn_bwd_kernel(const T *__restrict__ dact, const T *__restrict__ raw,
                                                      T *__restrict__ draw, int64_t M, int C, BnState bn, DropSpec drop,
                                                      float *__restrict__ partials) {
+    pdl_prologue();
     constexpr int V = Vec<T>::N;
     __shared__ float red[2 * 256 * V];
     const int CV = C / V, R = 256 / CV;
@@ -281,6 +289,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const T *__restrict__ dact,
 __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float *__restrict__ partials, int P, int C,
                                                               double inv_count, BnState bn, float *dgamma, float *dbeta,
                                                               int accumulate) {
+    pdl_prologue();
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (warp >= C) return;
     const int c = warp;
@@ -305,14 +314,14 @@ int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, D
     int P = (int)((M + 63) / 64);
     if (P > kNumSMs * 2) P = kNumSMs * 2;
     if (P > max_partials) P = max_partials;
-    bn_bwd_kernel<T, 0><<<P, 256, 0, s>>>(dact, raw, draw, M, C, bn, drop, partials);
+    HPFG_CUDA_CHECK(launch_pdl(bn_bwd_kernel<T, 0>, P, 256, 0, s, dact, raw, draw, M, C, bn, drop, partials));
     HPFG_LAUNCH_CHECK();
-    bn_bwd_finalize_kernel<<<ceil_div(C * 32, 256), 256, 0, s>>>(partials, P, C, 1.0 / (double)M, bn, dgamma, dbeta,
-                                                                 accumulate);
+    HPFG_CUDA_CHECK(launch_pdl(bn_bwd_finalize_kernel, ceil_div(C * 32, 256), 256, 0, s, partials, P, C, 1.0 / (double)M, bn, dgamma, dbeta,
+                                                                 accumulate));
     HPFG_LAUNCH_CHECK();
     int P2 = (int)((M + 63) / 64);
     if (P2 > kNumSMs * 8) P2 = kNumSMs * 8;
-    bn_bwd_kernel<T, 1><<<P2, 256, 0, s>>>(dact, raw, draw, M, C, bn, drop, nullptr);
+    HPFG_CUDA_CHECK(launch_pdl(bn_bwd_kernel<T, 1>, P2, 256, 0, s, dact, raw, draw, M, C, bn, drop, nullptr));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -321,16 +330,16 @@ int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, D
 template <typename T>
 __global__ void __launch_bounds__(256) skip_pool_bwd_kernel(const T *__restrict__ dcat, const T *__restrict__ dpooled,
                                                             const T *__restrict__ raw, BnState bn, T *__restrict__ dact,
-                                                            int N, int H, int W, int F) {
+                                                            int N, int H, int W, int F, FastDiv dFV, FastDiv dWo, FastDiv dHo) {
+    pdl_prologue();
     constexpr int V = Vec<T>::N;
-    const int FV = F / V, Ho = H >> 1, Wo = W >> 1;
-    const int64_t total = (int64_t)N * Ho * Wo * FV;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % FV);
-        int64_t pix = i / FV;
-        const int wo = (int)(pix % Wo);
-        pix /= Wo;
-        const int ho = (int)(pix % Ho), n = (int)(pix / Ho);
+    const int Ho = H >> 1, Wo = W >> 1;
+    const uint32_t total = (uint32_t)N * Ho * Wo * dFV.d;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t cv, pix, wo, ho, n;
+        fast_divmod(i, dFV, pix, cv);
+        fast_divmod(pix, dWo, pix, wo);
+        fast_divmod(pix, dHo, n, ho);
         float sc[V], sh[V], best[V], dp[V];
         int arg[V];
 #pragma unroll
@@ -371,7 +380,8 @@ int skip_pool_bwd(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *
                   cudaStream_t s) {
     ProfScope _prof(PROF_GLUE, s);
     const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (F / Vec<T>::N);
-    skip_pool_bwd_kernel<T><<<ew_grid(total), 256, 0, s>>>(dcat, dpooled, raw, bn, dact, N, H, W, F);
+    HPFG_REQUIRE(total < (1ll << 31), "skip_pool_bwd: tensor too large for 32-bit indexing");
+    HPFG_CUDA_CHECK(launch_pdl(skip_pool_bwd_kernel<T>, ew_grid(total), 256, 0, s, dcat, dpooled, raw, bn, dact, N, H, W, F, make_fastdiv(F / Vec<T>::N), make_fastdiv(W / 2), make_fastdiv(H / 2)));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -379,16 +389,17 @@ int skip_pool_bwd(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *
 // ------------------------------------------------------------------------------------------------ up_bwd
 template <typename T>
 __global__ void __launch_bounds__(256) up_bwd_kernel(const T *__restrict__ dcat, T *__restrict__ dlow, int N, int h, int w,
-                                                     int F, float sh_, float sw_) {
+                                                     int F, float sh_, float sw_, FastDiv dFV, FastDiv dw, FastDiv dh) {
+    pdl_prologue();
     constexpr int V = Vec<T>::N;
-    const int FV = F / V, H = 2 * h, W = 2 * w;
-    const int64_t total = (int64_t)N * h * w * FV;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int cv = (int)(i % FV);
-        int64_t pix = i / FV;
-        const int x = (int)(pix % w);
-        pix /= w;
-        const int y = (int)(pix % h), n = (int)(pix / h);
+    const int H = 2 * h, W = 2 * w;
+    const uint32_t total = (uint32_t)N * h * w * dFV.d;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t cv, pix, xx, yy, n;
+        fast_divmod(i, dFV, pix, cv);
+        fast_divmod(pix, dw, pix, xx);
+        fast_divmod(pix, dh, n, yy);
+        const int x = (int)xx, y = (int)yy;
         float acc[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) acc[k] = 0.f;
@@ -424,63 +435,97 @@ int up_bwd(const T *dcat, T *dlow, int N, int h, int w, int F, cudaStream_t s) {
     const int64_t total = (int64_t)N * h * w * (F / Vec<T>::N);
     const float sh_ = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
     const float sw_ = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
-    up_bwd_kernel<T><<<ew_grid(total), 256, 0, s>>>(dcat, dlow, N, h, w, F, sh_, sw_);
+    HPFG_REQUIRE(total < (1ll << 31), "up_bwd: tensor too large for 32-bit indexing");
+    HPFG_CUDA_CHECK(launch_pdl(up_bwd_kernel<T>, ew_grid(total), 256, 0, s, dcat, dlow, N, h, w, F, sh_, sw_, make_fastdiv(F / Vec<T>::N), make_fastdiv(w), make_fastdiv(h)));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
 
 // ------------------------------------------------------------------------------------------ dropout_bits
-// Keep-mask bits in NHWC element order.  Library stream: one Philox4x32-10 call per 4 consecutive NHWC elements
-// (counter = element index / 4, key = seed, counter words 2-3 = offset); keep <=> u >= p  (Bernoulli(1-p), as
-// nn.Dropout).  User masks (parity harness) arrive as NCHW uint8 and are gathered into the same bit layout.
-__global__ void __launch_bounds__(256) dropout_bits_kernel(uint32_t *__restrict__ bits, const uint8_t *__restrict__ mask,
-                                                           int N, int H, int W, int C, float p, uint64_t seed,
-                                                           uint64_t offset, int64_t n_words) {
-    const int64_t total = (int64_t)N * H * W * C;
-    const uint32_t thresh = (uint32_t)(p * 16777216.0f);          // compare the top 24 random bits
-    for (int64_t wi = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; wi < n_words; wi += (int64_t)gridDim.x * blockDim.x) {
+// Keep-mask bits in NHWC element order for up to 8 tensors in ONE launch (blockIdx.y = tensor).  Library stream: one
+// Philox4x32-10 call per 8 consecutive NHWC elements (counter = element index / 8, key = seed, counter words 2-3 =
+// offset + tensor); each 32-bit output word gives two 16-bit uniforms, keep <=> u16 >= p * 65536 (Bernoulli(1-p) to
+// within 8e-6, as nn.Dropout).  User masks (parity harness) arrive as NCHW uint8 and are gathered into the same
+// bit layout.
+struct DropJob {
+    uint32_t *bits;
+    const uint8_t *mask;      // NCHW uint8 keep mask or nullptr
+    int H, W, C;
+    uint32_t thresh;          // p * 65536
+    long long total, n_words;
+};
+struct DropJobs {
+    int n;
+    DropJob j[8];
+};
+
+__global__ void __launch_bounds__(256) dropout_bits_kernel(const DropJobs J, int N, uint64_t seed, uint64_t offset) {
+    pdl_prologue();
+    const DropJob &D = J.j[blockIdx.y];
+    const uint64_t off = offset + blockIdx.y;
+    for (long long wi = (long long)blockIdx.x * blockDim.x + threadIdx.x; wi < D.n_words; wi += (long long)gridDim.x * blockDim.x) {
         uint32_t word = 0;
-        if (mask) {
+        if (D.mask) {
             for (int b = 0; b < 32; ++b) {
-                const int64_t e = wi * 32 + b;
-                if (e >= total) break;
-                const int c = (int)(e % C);
-                int64_t pix = e / C;
-                const int x = (int)(pix % W);
-                pix /= W;
-                const int y = (int)(pix % H), n = (int)(pix / H);
-                word |= (mask[(((int64_t)n * C + c) * H + y) * W + x] != 0 ? 1u : 0u) << b;
+                const long long e = wi * 32 + b;
+                if (e >= D.total) break;
+                const int c = (int)(e % D.C);
+                long long pix = e / D.C;
+                const int x = (int)(pix % D.W);
+                pix /= D.W;
+                const int y = (int)(pix % D.H), n = (int)(pix / D.H);
+                word |= (D.mask[(((long long)n * D.C + c) * D.H + y) * D.W + x] != 0 ? 1u : 0u) << b;
             }
         } else {
 #pragma unroll
-            for (int g4 = 0; g4 < 8; ++g4) {
-                const uint64_t ctr = (uint64_t)wi * 8 + g4;
+            for (int g8 = 0; g8 < 4; ++g8) {
+                const uint64_t ctr = (uint64_t)wi * 4 + g8;
                 const uint4 r = philox4x32_10(make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)),
-                                              make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)offset,
-                                                         (uint32_t)(offset >> 32)));
-                word |= ((r.x >> 8) >= thresh ? 1u : 0u) << (4 * g4);
-                word |= ((r.y >> 8) >= thresh ? 1u : 0u) << (4 * g4 + 1);
-                word |= ((r.z >> 8) >= thresh ? 1u : 0u) << (4 * g4 + 2);
-                word |= ((r.w >> 8) >= thresh ? 1u : 0u) << (4 * g4 + 3);
+                                              make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), (uint32_t)off, (uint32_t)(off >> 32)));
+                const uint32_t v[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    word |= ((v[q] & 0xffffu) >= D.thresh ? 1u : 0u) << (8 * g8 + 2 * q);
+                    word |= ((v[q] >> 16) >= D.thresh ? 1u : 0u) << (8 * g8 + 2 * q + 1);
+                }
             }
         }
-        bits[wi] = word;
+        D.bits[wi] = word;
     }
+}
+
+int dropout_bits_multi(int n_jobs, uint32_t *const *bits, const uint8_t *const *masks_nchw, int N, const int *H, const int *W,
+                       const int *C, const float *p, uint64_t seed, uint64_t offset, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
+    HPFG_REQUIRE(n_jobs >= 1 && n_jobs <= 8, "dropout_bits_multi: 1..8 tensors per launch");
+    DropJobs J{};
+    J.n = n_jobs;
+    long long max_words = 1;
+    for (int i = 0; i < n_jobs; ++i) {
+        DropJob &D = J.j[i];
+        D.bits = bits[i];
+        D.mask = masks_nchw ? masks_nchw[i] : nullptr;
+        D.H = H[i]; D.W = W[i]; D.C = C[i];
+        D.thresh = (uint32_t)(p[i] * 65536.0f + 0.5f);
+        D.total = (long long)N * H[i] * W[i] * C[i];
+        D.n_words = (D.total + 31) / 32;
+        max_words = std::max(max_words, D.n_words);
+    }
+    HPFG_CUDA_CHECK(launch_pdl(dropout_bits_kernel, dim3((unsigned)ew_grid(max_words), (unsigned)n_jobs), 256, 0, s, J, N, seed, offset));
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
 }
 
 int dropout_bits(uint32_t *bits, const uint8_t *mask_nchw, int N, int H, int W, int C, float p, uint64_t seed,
                  uint64_t offset, cudaStream_t s) {
-    ProfScope _prof(PROF_GLUE, s);
-    const int64_t n_words = ((int64_t)N * H * W * C + 31) / 32;
-    dropout_bits_kernel<<<ew_grid(n_words), 256, 0, s>>>(bits, mask_nchw, N, H, W, C, p, seed, offset, n_words);
-    HPFG_LAUNCH_CHECK();
-    return HPFG_OK;
+    return dropout_bits_multi(1, &bits, mask_nchw ? &mask_nchw : nullptr, N, &H, &W, &C, &p, seed, offset, s);
 }
 
 // -------------------------------------------------------------------------------------- nhwc_to_nchw_f32
 template <typename T>
 __global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, float *__restrict__ dst, int N, int H, int W, int C,
                                     const float *__restrict__ bias) {
+    pdl_prologue();
     const int64_t total = (int64_t)N * C * H * W;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
         const int x = (int)(i % W);
@@ -495,7 +540,7 @@ __global__ void nhwc_to_nchw_kernel(const T *__restrict__ src, float *__restrict
 template <typename T>
 int nhwc_to_nchw_f32(const T *src, float *dst, int N, int H, int W, int C, const float *bias, cudaStream_t s) {
     ProfScope _prof(PROF_GLUE, s);
-    nhwc_to_nchw_kernel<T><<<ew_grid((int64_t)N * C * H * W), 256, 0, s>>>(src, dst, N, H, W, C, bias);
+    HPFG_CUDA_CHECK(launch_pdl(nhwc_to_nchw_kernel<T>, ew_grid((int64_t)N * C * H * W), 256, 0, s, src, dst, N, H, W, C, bias));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }

@@ -48,6 +48,10 @@ int up_bwd(const T *dcat, T *dlow, int N, int h, int w, int F, cudaStream_t s);
 int dropout_bits(uint32_t *bits, const uint8_t *mask_nchw, int N, int H, int W, int C, float p, uint64_t seed,
                  uint64_t offset, cudaStream_t s);
 
+// the same for up to 8 tensors in one launch (tensor i uses Philox offset + i)
+int dropout_bits_multi(int n_jobs, uint32_t *const *bits, const uint8_t *const *masks_nchw, int N, const int *H, const int *W,
+                       const int *C, const float *p, uint64_t seed, uint64_t offset, cudaStream_t s);
+
 // NHWC (T) -> NCHW fp32 copy with optional per-channel bias (debug taps)
 template <typename T>
 int nhwc_to_nchw_f32(const T *src, float *dst, int N, int H, int W, int C, const float *bias, cudaStream_t s);

@@ -113,6 +113,7 @@ __device__ __forceinline__ void load_labels4(const int64_t *p, int (&lab)[4]) {
 // ---------------------------------------------------------------------------------------------- phase 1
 template <int C>
 __global__ void __launch_bounds__(256) loss_reduce_kernel(LossArgs A) {
+    pdl_prologue();
     constexpr int NS = 3 * C + 2;
     __shared__ float smem[8 * (2 * NS + 3)];
     __shared__ int slots[2 * NS + 3];
@@ -287,6 +288,7 @@ __device__ __forceinline__ void store4(float *base, int64_t hw, const float (&g)
 
 template <int C>
 __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
+    pdl_prologue();
     __shared__ SupCoef coef[4];   // [net*2 + set]
     __shared__ float s_cons;      // per-element consistency coefficient
     const bool cps = A.mode == HPFG_LOSS_CPS;
@@ -400,6 +402,7 @@ struct DiceArgs {
 
 template <int C>
 __global__ void __launch_bounds__(256) dice_reduce_kernel(DiceArgs A) {
+    pdl_prologue();
     constexpr int NS = 3 * C + 2;
     __shared__ float smem[8 * NS];
     __shared__ int slots[NS];
@@ -435,6 +438,7 @@ __global__ void __launch_bounds__(256) dice_reduce_kernel(DiceArgs A) {
 
 template <int C>
 __global__ void __launch_bounds__(256) dice_grad_kernel(DiceArgs A) {
+    pdl_prologue();
     __shared__ SupCoef k;
     if (threadIdx.x == 0) {
         make_coef<C>(A.acc, A.class_w, k);
@@ -480,9 +484,9 @@ static int loss_grid(int64_t quads) {
 template <int C>
 static int launch_loss(const LossArgs &A, cudaStream_t st) {
     const int grid = loss_grid((int64_t)(A.n_l + A.n_u) * (A.hw >> 2));
-    loss_reduce_kernel<C><<<grid, 256, 0, st>>>(A);
+    HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C>, grid, 256, 0, st, A));
     HPFG_LAUNCH_CHECK();
-    loss_grad_kernel<C><<<grid, 256, 0, st>>>(A);
+    HPFG_CUDA_CHECK(launch_pdl(loss_grad_kernel<C>, grid, 256, 0, st, A));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -490,9 +494,9 @@ static int launch_loss(const LossArgs &A, cudaStream_t st) {
 template <int C>
 static int launch_dice(const DiceArgs &A, cudaStream_t st) {
     const int grid = loss_grid((int64_t)A.n * (A.hw >> 2));
-    dice_reduce_kernel<C><<<grid, 256, 0, st>>>(A);
+    HPFG_CUDA_CHECK(launch_pdl(dice_reduce_kernel<C>, grid, 256, 0, st, A));
     HPFG_LAUNCH_CHECK();
-    dice_grad_kernel<C><<<A.dinputs ? grid : 1, 256, 0, st>>>(A);
+    HPFG_CUDA_CHECK(launch_pdl(dice_grad_kernel<C>, A.dinputs ? grid : 1, 256, 0, st, A));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }

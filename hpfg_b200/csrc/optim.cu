@@ -16,6 +16,7 @@ __device__ __forceinline__ float ema1(float e, float p, float alpha, float one_m
 
 __global__ void __launch_bounds__(256) ema_kernel(float *__restrict__ ema, const float *__restrict__ param,
                                                   int64_t n, float alpha, float one_minus) {
+    pdl_prologue();
     const int64_t n4 = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -52,6 +53,7 @@ template <bool kEma>
 __global__ void __launch_bounds__(256) sgd_kernel(float *__restrict__ param, const float *__restrict__ grad,
                                                   float *__restrict__ buf, float *__restrict__ ema, int64_t n,
                                                   SgdArgs a) {
+    pdl_prologue();
     const int64_t n4 = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -97,7 +99,7 @@ extern "C" int hpfg_ema_update(float *ema, const float *param, int64_t n, float 
     HPFG_REQUIRE(aligned16(ema) && aligned16(param), "hpfg_ema_update: buffers must be 16-byte aligned");
     if (n == 0) return HPFG_OK;
     ProfScope _prof(PROF_OPTIM, (cudaStream_t)stream);
-    ema_kernel<<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(ema, param, n, alpha, 1.0f - alpha);
+    HPFG_CUDA_CHECK(launch_pdl(ema_kernel, flat_grid(n), 256, 0, (cudaStream_t)stream, ema, param, n, alpha, 1.0f - alpha));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -111,7 +113,7 @@ extern "C" int hpfg_sgd_momentum(float *param, const float *grad, float *momentu
     if (n == 0) return HPFG_OK;
     ProfScope _prof(PROF_OPTIM, (cudaStream_t)stream);
     SgdArgs a{lr, momentum, weight_decay, grad_scale, 0.f, 0.f, first_step};
-    sgd_kernel<false><<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, nullptr, n, a);
+    HPFG_CUDA_CHECK(launch_pdl(sgd_kernel<false>, flat_grid(n), 256, 0, (cudaStream_t)stream, param, grad, momentum_buf, nullptr, n, a));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -125,7 +127,7 @@ extern "C" int hpfg_sgd_momentum_ema(float *param, const float *grad, float *mom
     if (n == 0) return HPFG_OK;
     ProfScope _prof(PROF_OPTIM, (cudaStream_t)stream);
     SgdArgs a{lr, momentum, weight_decay, grad_scale, ema_alpha, 1.0f - ema_alpha, first_step};
-    sgd_kernel<true><<<flat_grid(n), 256, 0, (cudaStream_t)stream>>>(param, grad, momentum_buf, ema, n, a);
+    HPFG_CUDA_CHECK(launch_pdl(sgd_kernel<true>, flat_grid(n), 256, 0, (cudaStream_t)stream, param, grad, momentum_buf, ema, n, a));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }

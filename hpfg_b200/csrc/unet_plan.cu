@@ -170,10 +170,12 @@ static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_runnin
         for (auto &cv : d.convs)
             HPFG_RETURN_IF(pack_weights_ref(params + cv.w_off, cv.wf, cv.wd, cv.cin, cv.cout, cv.ks, s));
     if (tc) HPFG_RETURN_IF(tc_pack_all(p, params, s));
-    if (use_drop)
-        for (int l = 0; l < 5; ++l)
-            HPFG_RETURN_IF(dropout_bits(p->dropbits[l], masks ? masks[l] : nullptr, N, H >> l, W >> l, kFt[l],
-                                        kEncDropout[l], seed, offset + (uint64_t)l, s));
+    if (use_drop) {      // all five encoder keep-masks in one launch
+        int hs[5], wsz[5], cs[5];
+        float ps[5];
+        for (int l = 0; l < 5; ++l) { hs[l] = H >> l; wsz[l] = W >> l; cs[l] = kFt[l]; ps[l] = kEncDropout[l]; }
+        HPFG_RETURN_IF(dropout_bits_multi(5, p->dropbits, masks, N, hs, wsz, cs, ps, seed, offset, s));
+    }
 
     // conv + (train: statistics -> finalize | eval: running-stat affine)
     auto conv_bn = [&](int ci, TView in, bool in_is_f32, LoadXform xf) -> int {

@@ -56,6 +56,7 @@ struct WgParams {
 template <int KS, int NB, int COB>
 __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                  const __grid_constant__ CUtensorMap tmD, const WgParams P) {
+    pdl_launch_dependents();
     using C = WgCfg<KS, NB, COB>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         ptx::prefetch_tensormap(&tmD);
     }
     if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+    pdl_wait();
     if (P.scale)
         for (int i = threadIdx.x; i < P.Cin; i += blockDim.x) { s_scale[i] = P.scale[i]; s_shift[i] = P.shift[i]; }
     ptx::tc_fence_before();
@@ -252,6 +254,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
 __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const float *__restrict__ scratch, int S, int Cin, int Cout, int KK,
                                                               int cin_real, int cout_real, float *__restrict__ dw_oihw,
                                                               float *__restrict__ dbias, int accumulate) {
+    pdl_prologue();
     const int64_t per = (int64_t)KK * Cin * Cout + Cout;
     for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < per; e += (int64_t)gridDim.x * blockDim.x) {
         float s = 0.f;
@@ -293,7 +296,7 @@ static int wg_launch(const CUtensorMap &mx, const CUtensorMap &md, const WgParam
         attr_set = true;
     }
     const int grid = P.ci_blocks * P.co_blocks * P.S;
-    tc_wgrad_kernel<KS, NB, COB><<<grid, kWgThreads, C::SMEM_BYTES, s>>>(mx, md, P);
+    HPFG_CUDA_CHECK(launch_pdl(tc_wgrad_kernel<KS, NB, COB>, grid, kWgThreads, C::SMEM_BYTES, s, mx, md, P));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -327,7 +330,7 @@ int tc_wgrad_run(int ks, int N, int H, int W, int Cin, int Cout, int cin_real, i
     HPFG_RETURN_IF(ks == 3 ? wg_dispatch<3>(NB, COB, mx, md, P, s) : wg_dispatch<1>(NB, COB, mx, md, P, s));
     const int64_t per = (int64_t)ks * ks * Cin * Cout + Cout;
     const int blocks = (int)std::min<int64_t>((per + 255) / 256, (int64_t)kNumSMs * 4);
-    tc_wgrad_reduce_kernel<<<blocks, 256, 0, s>>>(scratch, P.S, Cin, Cout, ks * ks, cin_real, cout_real, dw_oihw, dbias, accumulate);
+    HPFG_CUDA_CHECK(launch_pdl(tc_wgrad_reduce_kernel, blocks, 256, 0, s, scratch, P.S, Cin, Cout, ks * ks, cin_real, cout_real, dw_oihw, dbias, accumulate));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -335,10 +338,13 @@ int tc_wgrad_run(int ks, int N, int H, int W, int Cin, int Cout, int cin_real, i
 }  // namespace hpfg
 
 namespace hpfg {
-__global__ void __launch_bounds__(256) pad_to_nhwc16_kernel(const float *__restrict__ src, uint4 *__restrict__ dst, int N, int C, int H, int W) {
-    const int64_t HW = (int64_t)H * W, total = (int64_t)N * HW;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t n = i / HW, pix = i % HW;
+__global__ void __launch_bounds__(256) pad_to_nhwc16_kernel(const float *__restrict__ src, uint4 *__restrict__ dst, int N, int C, int H, int W, FastDiv dHW) {
+    pdl_prologue();
+    const int64_t HW = (int64_t)H * W;
+    const uint32_t total = (uint32_t)N * dHW.d;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t n, pix;
+        fast_divmod(i, dHW, n, pix);
         float v[16];
 #pragma unroll
         for (int c = 0; c < 16; ++c) v[c] = c < C ? __ldg(src + (n * C + c) * HW + pix) : 0.f;
@@ -350,7 +356,7 @@ int pad_to_nhwc16(const float *src_nchw, void *dst, int N, int C, int H, int W, 
     ProfScope _prof(PROF_GLUE, s);
     const int64_t total = (int64_t)N * H * W;
     const int blocks = (int)std::min<int64_t>((total + 255) / 256, (int64_t)kNumSMs * 16);
-    pad_to_nhwc16_kernel<<<blocks, 256, 0, s>>>(src_nchw, reinterpret_cast<uint4 *>(dst), N, C, H, W);
+    HPFG_CUDA_CHECK(launch_pdl(pad_to_nhwc16_kernel, blocks, 256, 0, s, src_nchw, reinterpret_cast<uint4 *>(dst), N, C, H, W, make_fastdiv((uint32_t)(H * W))));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -383,6 +389,7 @@ int tc_run_bench(int op, int ks, int N, int H, int W, int cin, int cout, const v
                  const float *shift, float *stats, cudaStream_t s);   // conv_tc.cu
 }
 __global__ void fill_pattern_bf16(__nv_bfloat16 *p, size_t n, float scale) {
+    pdl_prologue();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
         p[i] = __float2bfloat16(scale * (float)((int)((i * 2654435761u) >> 24) - 128) / 128.f);
 }
@@ -400,8 +407,8 @@ extern "C" int hpfg_conv_tc_bench(int op, int N, int H, int W, int cin, int cout
     HPFG_CUDA_CHECK(cudaMalloc(&stats, (size_t)kNumSMs * 2 * 256 * 4 * 4));
     HPFG_CUDA_CHECK(cudaMalloc(&scratch, (size_t)nf * 4));
     HPFG_CUDA_CHECK(cudaMalloc(&dw, ((size_t)cin * cout * ks * ks + cout) * 4));
-    fill_pattern_bf16<<<1024, 256, 0, s>>>(a, px * std::max(cin, cout), 1.f);
-    fill_pattern_bf16<<<1024, 256, 0, s>>>(b, px * std::max(cin, cout), 1.f);
+    HPFG_CUDA_CHECK(launch_pdl(fill_pattern_bf16, 1024, 256, 0, s, a, px * std::max(cin, cout), 1.f));
+    HPFG_CUDA_CHECK(launch_pdl(fill_pattern_bf16, 1024, 256, 0, s, b, px * std::max(cin, cout), 1.f));
     HPFG_CUDA_CHECK(cudaMemsetAsync(w, 0, (size_t)cin * cout * ks * ks * 4, s));
     HPFG_CUDA_CHECK(cudaMemsetAsync(sc, 0, 2 * 256 * 4, s));
     cudaEvent_t e0, e1;
