@@ -125,14 +125,17 @@ __global__ void __launch_bounds__(256) pool_act_kernel(const T *__restrict__ raw
     constexpr int V = Vec<T>::N;
     const int Ho = H >> 1, Wo = W >> 1;
     const uint32_t total = (uint32_t)N * Ho * Wo * dCV.d;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        uint32_t cv, pix, wo, ho, n;
-        fast_divmod(i, dCV, pix, cv);
+    // the grid stride (256 * gridDim) is a multiple of CV, so a thread keeps one channel vector: its affine lives in registers
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cv = i0 - fast_div(i0, dCV) * dCV.d;
+    float sc[V], sh[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { sc[k] = bn.scale[cv * V + k]; sh[k] = bn.shift[cv * V + k]; }
+    for (uint32_t i = i0; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t pix = fast_div(i, dCV), wo, ho, n;
         fast_divmod(pix, dWo, pix, wo);
         fast_divmod(pix, dHo, n, ho);
-        float sc[V], sh[V], best[V];
-#pragma unroll
-        for (int k = 0; k < V; ++k) { sc[k] = bn.scale[cv * V + k]; sh[k] = bn.shift[cv * V + k]; }
+        float best[V];
 #pragma unroll
         for (int d = 0; d < 4; ++d) {
             const int h = 2 * ho + (d >> 1), w = 2 * wo + (d & 1);
@@ -178,9 +181,17 @@ __global__ void __launch_bounds__(256) upcat_kernel(const T *__restrict__ raw_sk
     constexpr int V = Vec<T>::N;
     const int H = 2 * h, W = 2 * w, FV = F / V;
     const uint32_t total = (uint32_t)N * H * W * dCV.d;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        uint32_t cv, pix, x, y, n;
-        fast_divmod(i, dCV, pix, cv);
+    // the grid stride is a multiple of CV: a thread keeps one channel vector of the concatenated tensor
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cv = i0 - fast_div(i0, dCV) * dCV.d;
+    float sc[V], sf[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+        sc[k] = cv < (uint32_t)FV ? bn.scale[cv * V + k] : 0.f;
+        sf[k] = cv < (uint32_t)FV ? bn.shift[cv * V + k] : 0.f;
+    }
+    for (uint32_t i = i0; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t pix = fast_div(i, dCV), x, y, n;
         fast_divmod(pix, dW, pix, x);
         fast_divmod(pix, dH, n, y);
         float out[V];
@@ -188,7 +199,7 @@ __global__ void __launch_bounds__(256) upcat_kernel(const T *__restrict__ raw_sk
             float v[V];
             Vec<T>::load(raw_skip + (((int64_t)n * H + y) * W + x) * F + cv * V, v);
 #pragma unroll
-            for (int k = 0; k < V; ++k) out[k] = leaky(fmaf(v[k], bn.scale[cv * V + k], bn.shift[cv * V + k]));
+            for (int k = 0; k < V; ++k) out[k] = leaky(fmaf(v[k], sc[k], sf[k]));
         } else {         // upsampled half
             const int c0 = (cv - FV) * V;
             int y0, y1, x0, x1;
@@ -246,6 +257,7 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const T *__restrict__ dact,
     const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t p1 = (p0 + rows_per_block < M) ? p0 + rows_per_block : M;
     if (active)
+#pragma unroll 4
         for (int64_t p = p0 + r; p < p1; p += R) {
             float d[V], x[V];
             Vec<T>::load(dact + p * C + cv * V, d);
@@ -312,7 +324,7 @@ int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, D
            int max_partials, float *dgamma, float *dbeta, int accumulate, cudaStream_t s) {
     ProfScope _prof(PROF_GLUE, s);
     int P = (int)((M + 63) / 64);
-    if (P > kNumSMs * 2) P = kNumSMs * 2;
+    if (P > kNumSMs * 4) P = kNumSMs * 4;
     if (P > max_partials) P = max_partials;
     HPFG_CUDA_CHECK(launch_pdl(bn_bwd_kernel<T, 0>, P, 256, 0, s, dact, raw, draw, M, C, bn, drop, partials));
     HPFG_LAUNCH_CHECK();
@@ -335,15 +347,19 @@ __global__ void __launch_bounds__(256) skip_pool_bwd_kernel(const T *__restrict_
     constexpr int V = Vec<T>::N;
     const int Ho = H >> 1, Wo = W >> 1;
     const uint32_t total = (uint32_t)N * Ho * Wo * dFV.d;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        uint32_t cv, pix, wo, ho, n;
-        fast_divmod(i, dFV, pix, cv);
+    const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t cv = i0 - fast_div(i0, dFV) * dFV.d;      // fixed per thread (grid stride is a multiple of FV)
+    float sc[V], sh[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) { sc[k] = bn.scale[cv * V + k]; sh[k] = bn.shift[cv * V + k]; }
+    for (uint32_t i = i0; i < total; i += gridDim.x * blockDim.x) {
+        uint32_t pix = fast_div(i, dFV), wo, ho, n;
         fast_divmod(pix, dWo, pix, wo);
         fast_divmod(pix, dHo, n, ho);
-        float sc[V], sh[V], best[V], dp[V];
+        float best[V], dp[V];
         int arg[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) { sc[k] = bn.scale[cv * V + k]; sh[k] = bn.shift[cv * V + k]; dp[k] = 0.f; arg[k] = 0; best[k] = 0.f; }
+        for (int k = 0; k < V; ++k) { dp[k] = 0.f; arg[k] = 0; best[k] = 0.f; }
         if (dpooled) Vec<T>::load(dpooled + (((int64_t)n * Ho + ho) * Wo + wo) * F + cv * V, dp);
 #pragma unroll
         for (int d = 0; d < 4; ++d) {   // first maximum in (h,w) scan order, as max_pool2d_with_indices

@@ -113,7 +113,7 @@ static void carve(hpfg_unet_plan *p, char *base, int64_t &total) {
         c.take(p->cat[j], N * (H >> lvl) * (W >> lvl) * 2 * kFt[lvl] * e);
         c.take(p->dcat[j], N * (H >> lvl) * (W >> lvl) * 2 * kFt[lvl] * e);
     }
-    for (int k = 0; k < 4; ++k) c.take(p->g[k], N * H * W * 16 * e);
+    for (int k = 0; k < 5; ++k) c.take(p->g[k], N * H * W * 16 * e);
     if (p->precision == HPFG_PREC_BF16) {
         c.take(p->xpad, N * H * W * 16 * 2);
         c.take(p->dlpad, N * H * W * 16 * 2);
@@ -277,15 +277,43 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
         xf.drop.inv_keep = bits ? 1.f / (1.f - p_drop) : 1.f;
         return xf;
     };
+    // Weight gradients run on the plan's side stream, concurrently with the data-gradient chain: wgrad(layer) and
+    // dgrad(layer) both consume the layer's raw gradient and are independent of each other.  The raw gradient lives
+    // in one of two alternating buffers; before a buffer is rewritten the main stream waits for the wgrad that read it.
+    cudaStream_t side = p->side;
+    void *dr[2] = {p->g[1], p->g[4]};
+    bool dr_busy[2] = {false, false};
+    int bi = 1;
+    void *b = nullptr;
+    auto next_b = [&]() -> int {
+        bi ^= 1;
+        b = dr[bi];
+        if (dr_busy[bi]) HPFG_CUDA_CHECK(cudaStreamWaitEvent(s, p->ev_done[bi], 0));
+        dr_busy[bi] = false;
+        return HPFG_OK;
+    };
     // weight gradient of conv `ci`: in (T NHWC, optionally transformed on load) x dout (T NHWC)
     auto wgrad = [&](int ci, void *in, LoadXform xf, void *dout) -> int {
         ConvLayer &cv = d.convs[ci];
+        HPFG_CUDA_CHECK(cudaEventRecord(p->ev_ready, s));
+        HPFG_CUDA_CHECK(cudaStreamWaitEvent(side, p->ev_ready, 0));
         bool done = false;
-        if (tc) HPFG_RETURN_IF(tc_wgrad(p, ci, in, xf, dout, grads + cv.w_off, grads + cv.b_off, acc, &done, s));
-        if (done) return HPFG_OK;
-        return conv_ref_wgrad<T, T>(nhwc_view(in, cv.H, cv.W, cv.cin), nhwc_view(dout, cv.H, cv.W, cv.cout), N, cv.H, cv.W,
-                                    cv.cin, cv.cout, cv.ks, xf, p->wscratch, p->wscratch_floats, grads + cv.w_off,
-                                    grads + cv.b_off, acc, s);
+        if (tc) HPFG_RETURN_IF(tc_wgrad(p, ci, in, xf, dout, grads + cv.w_off, grads + cv.b_off, acc, &done, side));
+        if (!done)
+            HPFG_RETURN_IF((conv_ref_wgrad<T, T>(nhwc_view(in, cv.H, cv.W, cv.cin), nhwc_view(dout, cv.H, cv.W, cv.cout), N, cv.H,
+                                                 cv.W, cv.cin, cv.cout, cv.ks, xf, p->wscratch, p->wscratch_floats,
+                                                 grads + cv.w_off, grads + cv.b_off, acc, side)));
+        for (int k = 0; k < 2; ++k)
+            if (dout == dr[k]) {
+                HPFG_CUDA_CHECK(cudaEventRecord(p->ev_done[k], side));
+                dr_busy[k] = true;
+            }
+        return HPFG_OK;
+    };
+    auto join_side = [&]() -> int {     // main stream waits for every weight gradient enqueued so far
+        HPFG_CUDA_CHECK(cudaEventRecord(p->ev_join, side));
+        HPFG_CUDA_CHECK(cudaStreamWaitEvent(s, p->ev_join, 0));
+        return HPFG_OK;
     };
     // data gradient of conv `ci`: din[.., cin] = conv(dout[.., cout], flipped weights)
     auto dgrad = [&](int ci, void *dout, void *din) -> int {
@@ -297,10 +325,10 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
                                     N, cv.H, cv.W, cv.cout, cv.cin, cv.ks, none, nullptr, s);
     };
     auto bnb = [&](int bn, void *dact, void *draw, const uint32_t *bits, float p_drop) -> int {
-        BnLayer &b = d.bns[bn];
+        BnLayer &bl = d.bns[bn];
         DropSpec ds{bits, bits ? 1.f / (1.f - p_drop) : 1.f};
-        return bn_bwd<T>((const T *)dact, (const T *)b.raw, (T *)draw, (int64_t)N * b.H * b.W, b.C, b.st, ds, p->stats,
-                         (int)(p->stats_floats / (2 * b.C)), grads + b.g_off, grads + b.b_off, acc, s);
+        return bn_bwd<T>((const T *)dact, (const T *)bl.raw, (T *)draw, (int64_t)N * bl.H * bl.W, bl.C, bl.st, ds, p->stats,
+                         (int)(p->stats_floats / (2 * bl.C)), grads + bl.g_off, grads + bl.b_off, acc, s);
     };
 
     // ---- out_conv
@@ -309,35 +337,42 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
         HPFG_RETURN_IF(wgrad(22, d.bns[17].raw, xf_of(17, nullptr, 0.f), p->dlpad));
         HPFG_RETURN_IF(dgrad(22, p->dlpad, p->g[0]));
     } else {
-        ConvLayer &oc = d.convs[22];
+        ConvLayer &oc = d.convs[22];       // (all weight gradients share wscratch, so this one is ordered on the side stream too)
+        HPFG_CUDA_CHECK(cudaEventRecord(p->ev_ready, s));
+        HPFG_CUDA_CHECK(cudaStreamWaitEvent(side, p->ev_ready, 0));
         HPFG_RETURN_IF((conv_ref_wgrad<T, float>(nhwc_view(d.bns[17].raw, H, W, 16),
                                                  nchw_view(const_cast<float *>(dlogits), p->n_cls, H, W), N, H, W, 16, p->n_cls,
                                                  3, xf_of(17, nullptr, 0.f), p->wscratch, p->wscratch_floats,
-                                                 grads + oc.w_off, grads + oc.b_off, acc, s)));
+                                                 grads + oc.w_off, grads + oc.b_off, acc, side)));
         HPFG_RETURN_IF((conv_ref_fprop<float, T>(nchw_view(const_cast<float *>(dlogits), p->n_cls, H, W),
                                                  nhwc_view(p->g[0], H, W, 16), oc.wd, nullptr, N, H, W, p->n_cls, 16, 3, none,
                                                  nullptr, s)));
     }
     // gradient scratch rotation: `a` holds the grad wrt the activated output of the block being processed
-    void *a = p->g[0], *b = p->g[1], *c = p->g[2];
+    void *a = p->g[0], *c = p->g[2];
     // ---- decoder, up4 .. up1
     for (int j = 4; j >= 1; --j) {
         const int lvl = 4 - j, c1x1 = 10 + 3 * (j - 1), cA = c1x1 + 1, cB = c1x1 + 2;
         const int bA = d.convs[cA].bn, bB = d.convs[cB].bn;
+        HPFG_RETURN_IF(next_b());
         HPFG_RETURN_IF(bnb(bB, a, b, nullptr, 0.f));                                // a -> draw(B) in b
         HPFG_RETURN_IF(wgrad(cB, d.bns[bA].raw, xf_of(bA, nullptr, 0.f), b));
         HPFG_RETURN_IF(dgrad(cB, b, c));                                            // -> dact(A) in c
+        HPFG_RETURN_IF(next_b());
         HPFG_RETURN_IF(bnb(bA, c, b, nullptr, 0.f));                                // -> draw(A) in b
         HPFG_RETURN_IF(wgrad(cA, p->cat[j], none, b));
         HPFG_RETURN_IF(dgrad(cA, b, p->dcat[j]));                                   // -> dcat (skip | upsampled)
         const int F = kFt[lvl], hl = H >> (lvl + 1), wl = W >> (lvl + 1);
+        HPFG_RETURN_IF(next_b());
         HPFG_RETURN_IF(up_bwd<T>((const T *)p->dcat[j], (T *)b, N, hl, wl, F, s));  // -> dlow in b
         const int prev_bn = (j == 1) ? 9 : d.convs[cB - 3].bn;
         HPFG_RETURN_IF(wgrad(c1x1, d.bns[prev_bn].raw, xf_of(prev_bn, nullptr, 0.f), b));
         HPFG_RETURN_IF(dgrad(c1x1, b, c));                                          // -> dact(prev) in c
         std::swap(a, c);
-        if (j == 3) HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[0], s));
-        if (j == 1) HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[1], s));
+        if (j == 3 || j == 1) {
+            HPFG_RETURN_IF(join_side());
+            HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[j == 3 ? 0 : 1], s));
+        }
     }
     // ---- encoder, down4 .. in_conv
     void *dpooled = nullptr;
@@ -347,24 +382,30 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
         if (l < 4)   // grad wrt the encoder feature = skip half of dcat + un-pooled grad from the level below
             HPFG_RETURN_IF(skip_pool_bwd<T>((const T *)p->dcat[4 - l], (const T *)dpooled, (const T *)d.bns[bB].raw, d.bns[bB].st,
                                             (T *)a, N, h, w, kFt[l], s));
+        HPFG_RETURN_IF(next_b());
         HPFG_RETURN_IF(bnb(bB, a, b, nullptr, 0.f));                                // draw(B) in b
         HPFG_RETURN_IF(wgrad(cB, d.bns[bA].raw, xf_of(bA, bits, kEncDropout[l]), b));
         HPFG_RETURN_IF(dgrad(cB, b, c));                                            // dact(A) in c
+        HPFG_RETURN_IF(next_b());
         HPFG_RETURN_IF(bnb(bA, c, b, bits, kEncDropout[l]));                        // draw(A) in b
         if (l == 0 && tc) {
             HPFG_RETURN_IF(wgrad(0, p->xpad, none, b));
         } else if (l == 0) {
             ConvLayer &cv = d.convs[0];
+            HPFG_CUDA_CHECK(cudaEventRecord(p->ev_ready, s));
+            HPFG_CUDA_CHECK(cudaStreamWaitEvent(side, p->ev_ready, 0));
             HPFG_RETURN_IF((conv_ref_wgrad<float, T>(nchw_view(const_cast<float *>(p->saved_x), p->in_ch, H, W),
                                                      nhwc_view(b, H, W, 16), N, H, W, p->in_ch, 16, 3, none, p->wscratch,
-                                                     p->wscratch_floats, grads + cv.w_off, grads + cv.b_off, acc, s)));
+                                                     p->wscratch_floats, grads + cv.w_off, grads + cv.b_off, acc, side)));
         } else {
             HPFG_RETURN_IF(wgrad(cA, p->pooled[l], none, b));
             HPFG_RETURN_IF(dgrad(cA, b, p->g[3]));                                  // dpooled for level l-1
             dpooled = p->g[3];
         }
-        if (l == 4) HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[2], s));
-        if (l == 0) HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[3], s));
+        if (l == 4 || l == 0) {
+            HPFG_RETURN_IF(join_side());
+            HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[l == 4 ? 2 : 3], s));
+        }
     }
     return HPFG_OK;
 }
@@ -460,6 +501,10 @@ extern "C" int hpfg_unet_plan_create(int batch, int in_channels, int num_classes
     p->ws_bytes = total;
     carve(p, p->ws, total);
     for (int b = 0; b < kNumBuckets; ++b) HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->bucket_ev[b], cudaEventDisableTiming));
+    HPFG_CUDA_CHECK(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming));
+    for (int k = 0; k < 2; ++k) HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_done[k], cudaEventDisableTiming));
+    HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     if (precision == HPFG_PREC_BF16) {
         const int rc = tc_plan_init(p);
         if (rc != HPFG_OK) {
@@ -477,6 +522,11 @@ extern "C" int hpfg_unet_plan_destroy(hpfg_unet_plan_t p) {
     if (p->precision == HPFG_PREC_BF16) tc_plan_free(p);
     for (int b = 0; b < kNumBuckets; ++b)
         if (p->bucket_ev[b]) cudaEventDestroy(p->bucket_ev[b]);
+    if (p->ev_ready) cudaEventDestroy(p->ev_ready);
+    if (p->ev_join) cudaEventDestroy(p->ev_join);
+    for (int k = 0; k < 2; ++k)
+        if (p->ev_done[k]) cudaEventDestroy(p->ev_done[k]);
+    if (p->side) cudaStreamDestroy(p->side);
     if (p->ws) cudaFree(p->ws);
     delete p;
     return HPFG_OK;

@@ -58,7 +58,7 @@ struct hpfg_unet_plan {
     void *low[5] = {};                // [1..4] conv1x1 outputs
     void *cat[5] = {};                // [1..4]
     void *dcat[5] = {};               // [1..4]
-    void *g[4] = {};                  // gradient scratch, N*H*W*16 elements each
+    void *g[5] = {};                  // gradient scratch, N*H*W*16 elements each ([1] and [4]: alternating raw-gradient buffers)
     void *xpad = nullptr, *dlpad = nullptr;   // bf16 NHWC16 copies of the network input / dlogits (bf16 plans)
     uint32_t *dropbits[5] = {};
     float *stats = nullptr;           // BN statistics partials
@@ -69,5 +69,8 @@ struct hpfg_unet_plan {
     bool saved = false, saved_dropout = false;
     const float *saved_x = nullptr;
     cudaEvent_t bucket_ev[hpfg::kNumBuckets] = {};
+    // weight gradients run on a side stream, concurrently with the data-gradient chain of the same layer
+    cudaStream_t side = nullptr;
+    cudaEvent_t ev_ready = nullptr, ev_join = nullptr, ev_done[2] = {};
     void *tc = nullptr;               // tensor-core path state (conv_tc.cu), bf16 plans only
 };

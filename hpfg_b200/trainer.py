@@ -71,14 +71,28 @@ class _StepBase:
         self._comm = None
         self.last = {}
 
+    def _side_stream(self, device):
+        if getattr(self, "_side", None) is None:
+            self._side = torch.cuda.Stream(device=device)
+        return self._side
+
     def _consistency_weight(self):
         return self.consistency * sigmoid_rampup(self.cur_itrs // 150, self.consistency_rampup)
 
-    def _forward(self, model, x, save):
+    def _forward(self, model, x, save, out=None):
         model.ensure_flat()
         plan = model._acquire_plan(x, need_grad=save)
-        logits = model._run_forward(plan, x, save=save)
+        logits = model._run_forward(plan, x, save=save, out=out)
         return plan, logits
+
+    def _persistent(self, name, shape, device):
+        """Step-persistent fp32 buffer (no per-step allocation: tensors that cross streams would otherwise need
+        record_stream, which defeats the caching allocator when the host runs ahead of the device)."""
+        buf = self.__dict__.setdefault("_bufs", {}).get(name)
+        if buf is None or tuple(buf.shape) != tuple(shape) or buf.device != device:
+            buf = torch.empty(shape, device=device, dtype=torch.float32)
+            self._bufs[name] = buf
+        return buf
 
     def _backward(self, model, plan, dlogits, grads):
         L.check(L.lib().hpfg_unet_backward(plan.handle, L.ptr(model.flat_params), L.ptr(dlogits), L.ptr(grads), 0,
@@ -132,8 +146,15 @@ class MeanTeacherStep(_StepBase):
         """x: [n_l+n_u, C, H, W] fp32 CUDA (labeled slices first); labels: [n_l, H, W] int64 CUDA."""
         self.cur_itrs += 1
         n_l = labels.shape[0]
-        plan, out = self._forward(self.model, x, True)
-        _, t_out = self._forward(self.ema_model, x, False)            # teacher sees the whole batch (:100)
+        # the teacher forward is independent of the student forward: it runs on a side stream so that each network's
+        # small / dependent kernels fill the other's bubbles (the teacher sees the whole batch, 2017_03...:100)
+        main, side = torch.cuda.current_stream(x.device), self._side_stream(x.device)
+        side.wait_stream(main)
+        shape = (x.shape[0], self.num_classes, x.shape[2], x.shape[3])
+        with torch.cuda.stream(side):
+            _, t_out = self._forward(self.ema_model, x, False, out=self._persistent("t_out", shape, x.device))
+        plan, out = self._forward(self.model, x, True, out=self._persistent("s_out", shape, x.device))
+        main.wait_stream(side)
         w = self._consistency_weight()
         r = ssl_loss_raw(L.LOSS_MT, out, t_out[n_l:], labels, n_l, cons_weight=w)
         self._backward(self.model, plan, r["dstudent"], self.grads)

@@ -208,9 +208,11 @@ class UNet(nn.Module):
         pool.append(pl)
         return pl
 
-    def _run_forward(self, plan, x, save):
+    def _run_forward(self, plan, x, save, out=None):
         dev = x.device
-        logits = torch.empty((x.shape[0], self.num_classes, x.shape[2], x.shape[3]), device=dev, dtype=torch.float32)
+        shape = (x.shape[0], self.num_classes, x.shape[2], x.shape[3])
+        logits = out if out is not None else torch.empty(shape, device=dev, dtype=torch.float32)
+        assert tuple(logits.shape) == shape and logits.dtype == torch.float32 and logits.is_contiguous()
         masks = None
         if self._dropout_masks is not None:
             masks = (ctypes.c_void_p * L.NUM_DROPOUT)(*[m.data_ptr() for m in self._dropout_masks])
