@@ -102,6 +102,80 @@ __device__ __forceinline__ float butterfly16(const float *v, int lane) {
 
 #define HPFG_TRACE(role, idx) do { if (P.trace && blockIdx.x == 0 && lane == 0 && (idx) < 64) P.trace[(role) * 64 + (idx)] = clock64(); } while (0)
 
+// MMA issuer role (warp 1; warp-uniform, one elected lane issues).  A separate non-inlined function so that ptxas
+// allocates its (uniform) registers independently of the other roles: inlined, the 2 x 36 smem descriptors of a
+// stage were spilled / recycled through two uniform-register pairs, and every rewrite of a pair stalled until the
+// previous UTCHMMA using it had been dispatched (measured 50 instead of 39 cycles per MMA).
+template <int KS, int KC, int BN, bool RES, int MT, int XF>
+__device__ __forceinline__ void tc_mma_role(uint32_t bar_full, uint32_t bar_xf, uint32_t bar_empty, uint32_t bar_tfull, uint32_t bar_tempty,
+                                         uint32_t stage_u32, uint32_t res_u32, uint32_t tmem_base, int n_work, int k_chunks, int dbg,
+                                         long long *trace) {
+    using C = TcCfg<KS, KC, BN, RES, MT>;
+    const int lane = threadIdx.x & 31;
+    {
+        constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN, 0, 0);
+        // descriptor words: hi = SBO | version, lo = (addr >> 4) | LBO << 16; per-MMA offsets are compile-time adds
+        constexpr uint32_t a_hi = (uint32_t)((C::HW * 16) >> 4) | (1u << 14), b_hi = (uint32_t)(128 >> 4) | (1u << 14);
+        const uint32_t a_lo0 = ((stage_u32 >> 4) & 0x3FFFu) | ((uint32_t)(C::CH_STRIDE >> 4) << 16);
+        const uint32_t b_lo0 = (((RES ? res_u32 : stage_u32 + C::OFF_B) >> 4) & 0x3FFFu) | ((uint32_t)((BN * 16) >> 4) << 16);
+        // Barrier polls issued after a stage's MMAs would queue behind them in the warp's in-order MIO queue (measured:
+        // ~400 cycles per poll), so the NEXT stage's barriers are polled before this stage's MMAs are pushed; the
+        // blocking waits only run when that early poll failed.
+        int stage = 0, phase = 0, kc = 0, it = 0;
+        const int total = n_work * k_chunks;
+        bool ready = false;
+#pragma unroll 1
+        for (int f = 0; f < total; ++f) {
+            const int acc = it % C::NACC;
+            if (!ready) {
+                if (kc == 0) ptx::mbar_wait(bar_tempty + 8 * acc, ((it / C::NACC) & 1) ^ 1, 2);
+                ptx::mbar_wait(bar_full + 8 * stage, phase, 3);
+                if (XF > 0) ptx::mbar_wait(bar_xf + 8 * stage, phase, 4);
+            }
+            ptx::tc_fence_after();
+            if (trace && blockIdx.x == 0 && lane == 0 && f < 64) trace[1 * 64 + f] = clock64();
+            int nstage = stage + 1, nphase = phase, nkc = kc + 1, nit = it;
+            if (nstage == C::STAGES) { nstage = 0; nphase ^= 1; }
+            if (nkc == k_chunks) { nkc = 0; ++nit; }
+            {
+                bool ok = f + 1 < total && ptx::mbar_try_wait(bar_full + 8 * nstage, nphase);
+                if (XF > 0) ok = ok && ptx::mbar_try_wait(bar_xf + 8 * nstage, nphase);
+                if (nkc == 0) ok = ok && ptx::mbar_try_wait(bar_tempty + 8 * (nit % C::NACC), ((nit / C::NACC) & 1) ^ 1);
+                ready = __all_sync(0xffffffffu, ok);
+            }
+            const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
+            const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
+            const uint32_t b_lo = RES ? b_lo0 : b_lo0 + stage * (C::STAGE_BYTES >> 4);
+            if (ptx::elect_one()) {
+                if (!(dbg & 1)) {
+                    // fully unrolled: a rolled loop stalls ~75 cycles at every back-edge until the queued UTCHMMAs have
+                    // consumed their uniform-register operands (measured 47 instead of 39 cycles per MMA)
+#pragma unroll 1
+                    for (int j = 0; j < MT; ++j) {             // UMMA tile j = output columns 8j..8j+7 of the stage
+                        const uint32_t a_j = a_lo + (uint32_t)j * (uint32_t)((kTW * 16) >> 4), d_j = d_tmem + j * BN;
+#pragma unroll
+                        for (int tap = 0; tap < C::KK; ++tap) {
+#pragma unroll
+                            for (int kk = 0; kk < KC / 16; ++kk) {
+                                const uint32_t ao = (uint32_t)((2 * kk * C::CH_STRIDE + ((tap / KS) * C::HW + (tap % KS)) * 16) >> 4);
+                                const uint32_t bo = (uint32_t)((tap * C::B_TAP_BYTES + 2 * kk * BN * 16) >> 4);
+                                const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_j + ao);
+                                const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + bo);
+                                ptx::umma_bf16(d_j, ad, bd, idesc, (kc | tap | kk) != 0);
+                            }
+                        }
+                    }
+                }
+                ptx::umma_commit(bar_empty + 8 * stage);      // smem slot reusable once these MMAs retire
+                if (nkc == 0) ptx::umma_commit(bar_tfull + 8 * acc);   // accumulator complete -> epilogue
+            }
+            __syncwarp();
+            if (trace && blockIdx.x == 0 && lane == 0 && f < 64) trace[2 * 64 + f] = clock64();
+            stage = nstage; phase = nphase; kc = nkc; it = nit;
+        }
+    }
+}
+
 // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-11 transform (XF > 0 only), 12-15 epilogue.
 template <int KS, int KC, int BN, bool RES, int MT, int XF, bool NCHW>
 __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const TcConvParams P) {
@@ -118,7 +192,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     float *s_part = s_shift + 256;                                 // [4 warps][2*BN]
 
     pdl_launch_dependents();
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // broadcast from lane 0: tells the compiler the warp index is warp-uniform, so role branches and everything
+    // loop-carried inside them (stage counters, descriptor bases) can live in the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t bar_full = ptx::smem_u32(bars), bar_xf = bar_full + 8 * C::STAGES, bar_empty = bar_xf + 8 * C::STAGES;
     const uint32_t bar_tfull = bar_empty + 8 * C::STAGES, bar_tempty = bar_tfull + 8 * C::NACC;
     const uint32_t stage_u32 = ptx::smem_u32(stage_base);
@@ -182,67 +258,9 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             ti.next(P.tiles_h, P.tiles_w);
         }
     } else if (warp == 1) {
-        // ================================================================= MMA issuer (warp-uniform, one lane issues)
-        constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN, 0, 0);
-        // descriptor words: hi = SBO | version, lo = (addr >> 4) | LBO << 16; per-MMA offsets are compile-time adds
-        constexpr uint32_t a_hi = (uint32_t)((C::HW * 16) >> 4) | (1u << 14), b_hi = (uint32_t)(128 >> 4) | (1u << 14);
-        const uint32_t a_lo0 = ((stage_u32 >> 4) & 0x3FFFu) | ((uint32_t)(C::CH_STRIDE >> 4) << 16);
-        const uint32_t b_lo0 = (((RES ? ptx::smem_u32(res_b) : stage_u32 + C::OFF_B) >> 4) & 0x3FFFu) | ((uint32_t)((BN * 16) >> 4) << 16);
-        // Barrier polls issued after a stage's MMAs would queue behind them in the warp's in-order MIO queue (measured:
-        // ~400 cycles per poll), so the NEXT stage's barriers are polled before this stage's MMAs are pushed; the
-        // blocking waits only run when that early poll failed.
-        int stage = 0, phase = 0, kc = 0, it = 0;
-        const int total = n_work * P.k_chunks;
-        bool ready = false;
-#pragma unroll 1
-        for (int f = 0; f < total; ++f) {
-            const int acc = it % C::NACC;
-            if (!ready) {
-                if (kc == 0) ptx::mbar_wait(bar_tempty + 8 * acc, ((it / C::NACC) & 1) ^ 1, 2);
-                ptx::mbar_wait(bar_full + 8 * stage, phase, 3);
-                if (XF > 0) ptx::mbar_wait(bar_xf + 8 * stage, phase, 4);
-            }
-            ptx::tc_fence_after();
-            HPFG_TRACE(1, f);
-            int nstage = stage + 1, nphase = phase, nkc = kc + 1, nit = it;
-            if (nstage == C::STAGES) { nstage = 0; nphase ^= 1; }
-            if (nkc == P.k_chunks) { nkc = 0; ++nit; }
-            {
-                bool ok = f + 1 < total && ptx::mbar_try_wait(bar_full + 8 * nstage, nphase);
-                if (XF > 0) ok = ok && ptx::mbar_try_wait(bar_xf + 8 * nstage, nphase);
-                if (nkc == 0) ok = ok && ptx::mbar_try_wait(bar_tempty + 8 * (nit % C::NACC), ((nit / C::NACC) & 1) ^ 1);
-                ready = __all_sync(0xffffffffu, ok);
-            }
-            const uint32_t d_tmem = tmem_base + acc * C::ACC_COLS;
-            const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4);
-            const uint32_t b_lo = RES ? b_lo0 : b_lo0 + stage * (C::STAGE_BYTES >> 4);
-            if (ptx::elect_one()) {
-                if (!(P.dbg & 1)) {
-                    // fully unrolled: a rolled loop stalls ~75 cycles at every back-edge until the queued UTCHMMAs have
-                    // consumed their uniform-register operands (measured 47 instead of 39 cycles per MMA)
-#pragma unroll
-                    for (int j = 0; j < MT; ++j) {             // UMMA tile j = output columns 8j..8j+7 of the stage
-                        const uint32_t a_j = a_lo + (uint32_t)j * (uint32_t)((kTW * 16) >> 4), d_j = d_tmem + j * BN;
-#pragma unroll
-                        for (int tap = 0; tap < C::KK; ++tap) {
-#pragma unroll
-                            for (int kk = 0; kk < KC / 16; ++kk) {
-                                const uint32_t ao = (uint32_t)((2 * kk * C::CH_STRIDE + ((tap / KS) * C::HW + (tap % KS)) * 16) >> 4);
-                                const uint32_t bo = (uint32_t)((tap * C::B_TAP_BYTES + 2 * kk * BN * 16) >> 4);
-                                const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_j + ao);
-                                const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + bo);
-                                ptx::umma_bf16(d_j, ad, bd, idesc, (kc | tap | kk) != 0);
-                            }
-                        }
-                    }
-                }
-                ptx::umma_commit(bar_empty + 8 * stage);      // smem slot reusable once these MMAs retire
-                if (nkc == 0) ptx::umma_commit(bar_tfull + 8 * acc);   // accumulator complete -> epilogue
-            }
-            __syncwarp();
-            HPFG_TRACE(2, f);
-            stage = nstage; phase = nphase; kc = nkc; it = nit;
-        }
+        // ================================================================= MMA issuer (separate function: own register allocation)
+        tc_mma_role<KS, KC, BN, RES, MT, XF>(bar_full, bar_xf, bar_empty, bar_tfull, bar_tempty, stage_u32, ptx::smem_u32(res_b),
+                                             tmem_base, n_work, P.k_chunks, P.dbg, P.trace);
     } else if (warp >= 4 && warp < 4 + kXfWarps) {
         // ================================================================= loader-transform warps (in place)
         if (XF > 0) {

@@ -47,6 +47,13 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int tag
     }
 }
 
+// Warp-level wait: only lane 0 polls the barrier (32x fewer SYNCS operations competing with the tensor core's
+// shared-memory operand fetch), the other lanes park at the warp barrier.  Call with the full warp converged.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity, int tag) {
+    if ((threadIdx.x & 31) == 0) mbar_wait(bar, parity, tag);
+    __syncwarp();
+}
+
 // generic-proxy writes (st.shared) -> visible to the async proxy (tcgen05.mma / TMA reads of smem)
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 

@@ -67,7 +67,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     float *s_shift = s_scale + 256;
     float *s_bias = s_shift + 256;                                 // [transform threads][8]
 
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // broadcast from lane 0: tells the compiler the warp index is warp-uniform, so role branches and everything
+    // loop-carried inside them (stage counters, descriptor bases) can live in the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t bar_full = ptx::smem_u32(bars), bar_xf = bar_full + 8 * C::STAGES, bar_empty = bar_xf + 8 * C::STAGES;
     const uint32_t bar_done = bar_empty + 8 * C::STAGES;
     const uint32_t smem_u32 = ptx::smem_u32(smem);
