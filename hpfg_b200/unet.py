@@ -130,16 +130,23 @@ class UNet(nn.Module):
         self.__dict__["bn_running"] = run
         self.__dict__["bn_counters"] = cnt
         self.__dict__["_layout"] = layout
+        # cached object lists: the per-step flatness check must not walk the module tree (it sits in front of the first
+        # kernel launch of every step)
+        self.__dict__["_flat_params_list"] = params
+        self.__dict__["_flat_bn_list"] = bns
 
     def _is_flat(self):
         flat = self.__dict__.get("flat_params")
         if flat is None:
             return False
         base = flat.data_ptr()
-        for p, (o, n, _) in zip(self.parameters(), self._layout):
+        plist = self.__dict__.get("_flat_params_list")
+        if plist is None:
+            return False
+        for p, (o, n, _) in zip(plist, self._layout):
             if p.data_ptr() != base + 4 * o or p.dtype != torch.float32:
                 return False
-        bns = self._bn_modules()
+        bns = self.__dict__["_flat_bn_list"]
         o, rbase = 0, self.bn_running.data_ptr()
         for i, b in enumerate(bns):
             c = b.num_features
@@ -170,8 +177,10 @@ class UNet(nn.Module):
         new = self.__class__.__new__(self.__class__)
         memo[id(self)] = new
         for k, v in self.__dict__.items():
+            if k in ("_flat_params_list", "_flat_bn_list"):
+                continue                                   # rebuilt by _flatten() below
             new.__dict__[k] = {} if k == "_plans" else (None if k == "last_flat_grad" else copy.deepcopy(v, memo))
-        new.ensure_flat()
+        new._flatten()
         return new
 
     # ------------------------------------------------------------------ test / parity hooks
