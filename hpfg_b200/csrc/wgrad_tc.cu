@@ -1,15 +1,22 @@
 // Tensor-core weight gradient for the bf16 path (sm_100a):
 //
-//   dW[tap][ci][co] = sum over pixels  X_act[pixel + tap][ci] * dY[pixel][co]
+//   dW[tap=(r,s)][ci][co] = sum over pixels  X_act[pixel + (r,s)][ci] * dY[pixel][co]
 //
-// as nine TMEM-resident accumulators D_tap[co (M, padded to 128), ci block (N)] fed by tcgen05.mma with BOTH
-// operands MN-major: the reduction (K) dimension is the pixel index, which is the slow dimension of NHWC tiles.
-// Staging mirrors the fprop kernel: per 16x8-pixel tile TMA fetches the dY tile and the (16+2)x(8+2) halo of the
-// layer input once; the transform warps re-lay both out as [8-channel chunk][pixel][8 ch] (applying the
-// producer's BatchNorm+LeakyReLU+dropout to X and accumulating the bias gradient from dY on the way); each tap is
-// a shifted descriptor into the one staged X tile.  The pixel dimension is split over persistent CTAs
-// (split-K); each CTA keeps its accumulators in TMEM across all its tiles and writes one fp32 partial, and a
-// fixed-order reduction kernel sums the partials straight into the flat OIHW gradient (deterministic).
+// with the pixel index as the reduction (K) dimension of tcgen05.mma and BOTH operands MN-major (pixels are the slow
+// dimension of NHWC tiles).  To fill the M dimension (min 64) the KS column shifts of a tap row are stacked along M:
+//
+//   D_r[m = s*NB + ci][n = co]  +=  A_r[m][k = pixel] * B[n][k],     A_r = [X shifted by (r,0) | (r,1) | (r,2)],  B = dY
+//
+// i.e. KS MMAs (M = KS*NB padded to 64/128, N = COB) per 16-pixel K step instead of KS*KS MMAs with 3/4 of M wasted
+// (an M=64, N=16 MMA costs 23 cycles of shared-memory operand fetch however many of its rows are useful).
+// Staging per 16x8-pixel tile: TMA fetches the dY tile and the (16+2)x(8+2) halo of the layer input once, both
+// directly in [8-channel chunk][pixel][8 ch] order (chunked 5-D maps).  The transform warps read the halo, apply the
+// producer's BatchNorm+LeakyReLU+dropout (and restore the conv zero padding), and write the KS column-shifted copies
+// [s][chunk][halo row][8 cols][8 ch]: with the copies contiguous, "8-row group g = s*(NB/8)+chunk" is an affine
+// address (SBO = one copy-chunk), so ONE descriptor spans all KS shifts; the tap row r is a start-address offset.
+// They also accumulate the bias gradient from dY.  The pixel dimension is split over persistent CTAs (split-K);
+// each CTA keeps its accumulators in TMEM across all its tiles and writes one fp32 partial, and a fixed-order
+// reduction kernel sums the partials straight into the flat OIHW gradient (deterministic).
 #include <algorithm>
 
 #include "conv_ref.cuh"
@@ -18,7 +25,7 @@
 
 namespace hpfg {
 
-constexpr int kWgXfThreads = 256;   // transform threads (warps 4-11): in-place loader transform of X + bias-gradient sums
+constexpr int kWgXfThreads = 256;   // transform threads (warps 4-11): loader transform of X into shifted copies + bias-gradient sums
 constexpr int kWgThreads = 128 + kWgXfThreads + 128;   // warps 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 transform, 12-15 epilogue
 constexpr int kWgSmemBudget = 222 * 1024;
 
@@ -26,23 +33,26 @@ template <int KS, int NB, int COB>
 struct WgCfg {
     static constexpr int PAD = KS / 2, KK = KS * KS;
     static constexpr int HH = kTH + KS - 1, HW = kTW + KS - 1, NPIX_X = HH * HW;
-    // both operand tiles land directly in UMMA order [8-channel chunk][pixel][8 ch] (chunked 5-D TMA maps)
-    static constexpr int X_CHS = NPIX_X * 16, X_OP = (NB / 8) * X_CHS;
-    static constexpr int D_CHS = 128 * 16, D_OP = (COB / 8) * D_CHS;
+    static constexpr int XR_CHS = NPIX_X * 16, XR_OP = (NB / 8) * XR_CHS;     // raw halo tile, TMA target: [chunk][halo pixel][8 ch]
+    static constexpr int XC = HH * kTW * 16;                                  // one chunk of one shifted copy: [halo row][8 cols][8 ch]
+    static constexpr int X3_OP = KS * (NB / 8) * XC;                          // A operand: [shift s][chunk][halo row][8 cols][8 ch]
+    static constexpr int D_CHS = 128 * 16, D_OP = (COB / 8) * D_CHS;          // dY tile, TMA target and B operand: [chunk][pixel][8 ch]
     static constexpr int al(int v) { return (v + 127) / 128 * 128; }
-    static constexpr int OFF_DOP = 0, OFF_XOP = al(D_OP);
-    static constexpr int STAGE_BYTES = OFF_XOP + al(X_OP);
-    static constexpr int UM = COB <= 64 ? 64 : 128;                 // UMMA M (accumulator rows = output channels of dY)
-    // the A descriptor spans UM/8 row groups; with COB < UM the groups past the real channels read
-    // whatever follows in shared memory (their D rows are never stored) -- keep those reads inside the allocation
-    static constexpr int TAIL_PAD = al((UM / 8 - COB / 8) * D_CHS);
+    static constexpr int OFF_DOP = 0, OFF_XR = al(D_OP), OFF_X3 = OFF_XR + al(XR_OP);
+    static constexpr int STAGE_BYTES = OFF_X3 + al(X3_OP);
+    static constexpr int MROWS = KS * NB;                                     // useful accumulator rows
+    static constexpr int UM = MROWS <= 64 ? 64 : 128;                         // UMMA M
+    // the A descriptor spans UM/8 row groups; the groups past MROWS read whatever follows the copies in shared memory
+    // (their D rows are never stored) -- keep those reads inside the allocation
+    static constexpr int TAIL_PAD = al((UM / 8 - MROWS / 8) * XC);
     static constexpr int FIXED_BYTES = 1024 + 2 * 256 * 4 + kWgXfThreads * 8 * 4 /*dbias reduce*/;
     static constexpr int STAGES_RAW = (kWgSmemBudget - FIXED_BYTES - TAIL_PAD) / STAGE_BYTES;
-    static constexpr int STAGES = STAGES_RAW > 12 ? 12 : STAGES_RAW;
+    static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_PAD + FIXED_BYTES + 1024;
-    static constexpr int TMEM_COLS = (KK * NB <= 32) ? 32 : (KK * NB <= 64) ? 64 : (KK * NB <= 128) ? 128 : (KK * NB <= 256) ? 256 : 512;
+    static constexpr int ACC = KS * COB;                                      // accumulator columns: D_r at column r*COB
+    static constexpr int TMEM_COLS = (ACC <= 32) ? 32 : (ACC <= 64) ? 64 : (ACC <= 128) ? 128 : (ACC <= 256) ? 256 : 512;
     static_assert(STAGES >= 2, "need at least a double buffer");
-    static_assert(KK * NB <= 512, "accumulators exceed TMEM");
+    static_assert(ACC <= 512 && MROWS <= 128, "accumulators exceed TMEM");
 };
 
 struct WgParams {
@@ -67,8 +77,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     float *s_shift = s_scale + 256;
     float *s_bias = s_shift + 256;                                 // [transform threads][8]
 
-    // broadcast from lane 0: tells the compiler the warp index is warp-uniform, so role branches and everything
-    // loop-carried inside them (stage counters, descriptor bases) can live in the uniform datapath
+    // broadcast from lane 0: the warp index is warp-uniform for the compiler (role code stays in the uniform datapath)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
     const uint32_t bar_full = ptx::smem_u32(bars), bar_xf = bar_full + 8 * C::STAGES, bar_empty = bar_xf + 8 * C::STAGES;
     const uint32_t bar_done = bar_empty + 8 * C::STAGES;
@@ -81,12 +90,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     const int ci0 = cib * NB, co0 = cob * COB;
     const int n_work = (P.m_tiles - split + P.S - 1) / P.S;        // tiles split, split+S, ...
     const bool xform = P.scale != nullptr, want_bias = cib == 0;
-    const bool use_xf = xform || want_bias;                       // transform warps touch the stage -> MMA waits for them
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(bar_full + 8 * s, 1);
-            ptx::mbar_init(bar_xf + 8 * s, kWgXfThreads);
+            ptx::mbar_init(bar_xf + 8 * s, kWgXfThreads / 32);
             ptx::mbar_init(bar_empty + 8 * s, 1);
         }
         ptx::mbar_init(bar_done, 1);
@@ -107,42 +115,42 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         TileIter ti;
         ti.init(split, P.S, P.tiles_h, P.tiles_w);
         int stage = 0, phase = 0;
+#pragma unroll 1
         for (int it = 0; it < n_work; ++it) {
             const int h0 = ti.th * kTH, w0 = ti.tw * kTW;
             ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 11);
             const uint32_t sb = smem_u32 + stage * C::STAGE_BYTES;
             if (ptx::elect_one()) {
-                ptx::mbar_expect_tx(bar_full + 8 * stage, C::D_OP + C::X_OP);
+                ptx::mbar_expect_tx(bar_full + 8 * stage, C::D_OP + C::XR_OP);
                 ptx::tma_load_5d(sb + C::OFF_DOP, &tmD, bar_full + 8 * stage, 0, w0, h0, co0 / 8, ti.n_img);
-                ptx::tma_load_5d(sb + C::OFF_XOP, &tmX, bar_full + 8 * stage, 0, w0 - C::PAD, h0 - C::PAD, ci0 / 8, ti.n_img);
+                ptx::tma_load_5d(sb + C::OFF_XR, &tmX, bar_full + 8 * stage, 0, w0 - C::PAD, h0 - C::PAD, ci0 / 8, ti.n_img);
             }
             __syncwarp();
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             ti.next(P.tiles_h, P.tiles_w);
         }
     } else if (warp == 1) {      // ==================================================== MMA issuer (warp-uniform)
-        constexpr uint32_t idesc = ptx::umma_idesc_bf16(C::UM, NB, 1, 1);   // both operands MN-major
+        constexpr uint32_t idesc = ptx::umma_idesc_bf16(C::UM, COB, 1, 1);   // both operands MN-major
         // descriptor words: hi = SBO | version, lo = (addr >> 4) | LBO << 16; per-MMA offsets are compile-time adds
-        // A = dY^T: M groups (8 co) SBO = chunk stride, K groups (8 pixels) LBO = 128 B
-        // B = X shifted by the tap: N groups (8 ci) SBO = chunk stride, K groups LBO = one halo row
-        constexpr uint32_t a_hi = (uint32_t)(C::D_CHS >> 4) | (1u << 14), b_hi = (uint32_t)(C::X_CHS >> 4) | (1u << 14);
-        const uint32_t a_lo0 = (((smem_u32 + C::OFF_DOP) >> 4) & 0x3FFFu) | ((uint32_t)(128 >> 4) << 16);
-        const uint32_t b_lo0 = (((smem_u32 + C::OFF_XOP) >> 4) & 0x3FFFu) | ((uint32_t)((C::HW * 16) >> 4) << 16);
+        // A = shifted X copies: M groups (8 rows = one (shift, chunk)) SBO = copy-chunk stride, K groups (8 pixels = one tile row) LBO = 128 B
+        // B = dY: N groups (8 co) SBO = chunk stride, K groups (8 pixels) LBO = 128 B
+        constexpr uint32_t a_hi = (uint32_t)(C::XC >> 4) | (1u << 14), b_hi = (uint32_t)(C::D_CHS >> 4) | (1u << 14);
+        const uint32_t a_lo0 = (((smem_u32 + C::OFF_X3) >> 4) & 0x3FFFu) | ((uint32_t)(128 >> 4) << 16);
+        const uint32_t b_lo0 = (((smem_u32 + C::OFF_DOP) >> 4) & 0x3FFFu) | ((uint32_t)(128 >> 4) << 16);
         int stage = 0, phase = 0;
+#pragma unroll 1
         for (int it = 0; it < n_work; ++it) {
-            ptx::mbar_wait(bar_full + 8 * stage, phase, 13);
-            if (use_xf) ptx::mbar_wait(bar_xf + 8 * stage, phase, 14);
+            ptx::mbar_wait(bar_xf + 8 * stage, phase, 14);         // transform warps arrive after the TMA data was consumed and the copies written
             ptx::tc_fence_after();
             const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4), b_lo = b_lo0 + stage * (C::STAGE_BYTES >> 4);
             if (ptx::elect_one()) {
-#pragma unroll
+#pragma unroll 2
                 for (int j = 0; j < 8; ++j) {            // K step = 16 pixels = tile rows 2j, 2j+1
-                    const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)((j * 256) >> 4));
+                    const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)((j * 256) >> 4));
 #pragma unroll
-                    for (int tap = 0; tap < C::KK; ++tap) {
-                        const uint32_t bo = (uint32_t)((((2 * j + tap / KS) * C::HW + tap % KS) * 16) >> 4);
-                        const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + bo);
-                        ptx::umma_bf16(tmem_base + tap * NB, ad, bd, idesc, (it == 0 && j == 0) ? 0u : 1u);
+                    for (int r = 0; r < KS; ++r) {       // tap row: start at halo row 2j + r of every copy
+                        const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(((2 * j + r) * 128) >> 4));
+                        ptx::umma_bf16(tmem_base + r * COB, ad, bd, idesc, (it == 0 && j == 0) ? 0u : 1u);
                     }
                 }
                 ptx::umma_commit(bar_empty + 8 * stage);
@@ -153,92 +161,102 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         }
     } else if (warp >= 4 && warp < 4 + kWgXfThreads / 32) {
         // ================================================================================ transform warps
-        if (use_xf) {
-            const int t = threadIdx.x - 128;
-            constexpr int XITEMS = C::NPIX_X * (NB / 8);
-            float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias-gradient partial sums of this thread's chunk
-            TileIter ti;
-            ti.init(split, P.S, P.tiles_h, P.tiles_w);
-            int stage = 0, phase = 0;
-            for (int it = 0; it < n_work; ++it) {
-                const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * kTW - C::PAD;
-                const size_t img_px = (size_t)ti.n_img * P.H;
-                ptx::mbar_wait(bar_full + 8 * stage, phase, 15);
-                const uint32_t sb = smem_u32 + stage * C::STAGE_BYTES;
-                if (want_bias) {
-                    // thread t owns chunk t / TPC and pixels (t % TPC), +TPC, ...: consecutive lanes read consecutive 16-byte units
-                    constexpr int TPC = kWgXfThreads / (COB / 8);
-                    const int bc = t / TPC;
-                    for (int px = t % TPC; px < 128; px += TPC) {
-                        float f[8];
-                        unpack8(ptx::lds128(sb + C::OFF_DOP + (bc * 128 + px) * 16), f);
+        const int t = threadIdx.x - 128;
+        constexpr int XITEMS = C::NPIX_X * (NB / 8);
+        float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias-gradient partial sums of this thread's chunk
+        TileIter ti;
+        ti.init(split, P.S, P.tiles_h, P.tiles_w);
+        int stage = 0, phase = 0;
+#pragma unroll 1
+        for (int it = 0; it < n_work; ++it) {
+            const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * kTW - C::PAD;
+            const size_t img_px = (size_t)ti.n_img * P.H;
+            ptx::mbar_wait(bar_full + 8 * stage, phase, 15);
+            const uint32_t sb = smem_u32 + stage * C::STAGE_BYTES;
+            if (want_bias) {
+                // thread t owns chunk t / TPC and pixels (t % TPC), +TPC, ...: consecutive lanes read consecutive 16-byte units
+                constexpr int TPC = kWgXfThreads / (COB / 8);
+                const int bc = t / TPC;
+                for (int px = t % TPC; px < 128; px += TPC) {
+                    float f[8];
+                    unpack8(ptx::lds128(sb + C::OFF_DOP + (bc * 128 + px) * 16), f);
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) bsum[k] += f[k];
-                    }
+                    for (int k = 0; k < 8; ++k) bsum[k] += f[k];
                 }
-                if (xform) {
-                    for (int i = t; i < XITEMS; i += kWgXfThreads) {
-                        const int c = i / C::NPIX_X, p = i % C::NPIX_X;
-                        const int gh = h0 + p / C::HW, gw = w0 + p % C::HW;
-                        uint4 v = make_uint4(0u, 0u, 0u, 0u);
-                        if (gh >= 0 && gh < P.H && gw >= 0 && gw < P.W) {
-                            float f[8];
-                            unpack8(ptx::lds128(sb + C::OFF_XOP + i * 16), f);
-                            const int ch = ci0 + c * 8;
-                            uint32_t keep = 0xffu;
-                            if (P.dropbits) keep = P.dropbits[(((img_px + gh) * P.W + gw) * P.Cin + ch) >> 3];
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {
-                                float a = fmaf(f[k], s_scale[ch + k], s_shift[ch + k]);
-                                a = fmaxf(a, kLeakySlope * a);
-                                if (P.dropbits) a = ((keep >> k) & 1u) ? a * P.inv_keep : 0.f;
-                                f[k] = a;
-                            }
-                            v = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
-                        }
-                        ptx::sts128(sb + C::OFF_XOP + i * 16, v);
-                    }
-                    ptx::fence_proxy_async_smem();
-                }
-                ptx::mbar_arrive(bar_xf + 8 * stage);
-                if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
-                ti.next(P.tiles_h, P.tiles_w);
             }
-            if (want_bias) {     // fixed-order reduce of the per-thread partial sums of each channel
+            for (int i = t; i < XITEMS; i += kWgXfThreads) {
+                const int c = i / C::NPIX_X, p = i % C::NPIX_X;
+                const int hr = p / C::HW, hc = p % C::HW;
+                uint4 v = ptx::lds128(sb + C::OFF_XR + i * 16);
+                if (xform) {
+                    const int gh = h0 + hr, gw = w0 + hc;
+                    if (gh >= 0 && gh < P.H && gw >= 0 && gw < P.W) {
+                        float f[8];
+                        unpack8(v, f);
+                        const int ch = ci0 + c * 8;
+                        uint32_t keep = 0xffu;
+                        if (P.dropbits) keep = P.dropbits[(((img_px + gh) * P.W + gw) * P.Cin + ch) >> 3];
 #pragma unroll
-                for (int k = 0; k < 8; ++k) s_bias[t * 8 + k] = bsum[k];
-                ptx::named_bar_sync(2, kWgXfThreads);
-                if (t < COB) {
-                    constexpr int TPC = kWgXfThreads / (COB / 8);
-                    const int c = t / 8, k = t % 8;
-                    float s = 0.f;
-                    for (int u = c * TPC; u < (c + 1) * TPC; ++u) s += s_bias[u * 8 + k];
-                    if (co0 + t < P.Cout)
-                        P.scratch[(size_t)split * ((size_t)C::KK * P.Cin * P.Cout + P.Cout) + (size_t)C::KK * P.Cin * P.Cout + co0 + t] = s;
+                        for (int k = 0; k < 8; ++k) {
+                            float a = fmaf(f[k], s_scale[ch + k], s_shift[ch + k]);
+                            a = fmaxf(a, kLeakySlope * a);
+                            if (P.dropbits) a = ((keep >> k) & 1u) ? a * P.inv_keep : 0.f;
+                            f[k] = a;
+                        }
+                        v = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
+                    } else {
+                        v = make_uint4(0u, 0u, 0u, 0u);        // conv zero padding applies AFTER the activation
+                    }
                 }
+                // halo column hc lands in copy s at column hc - s
+                const uint32_t dst = sb + C::OFF_X3 + c * C::XC + (hr * kTW + hc) * 16;
+#pragma unroll
+                for (int s = 0; s < KS; ++s)
+                    if (hc - s >= 0 && hc - s < kTW) ptx::sts128(dst + s * (NB / 8) * C::XC - s * 16, v);
+            }
+            ptx::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(bar_xf + 8 * stage);
+            if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
+            ti.next(P.tiles_h, P.tiles_w);
+        }
+        if (want_bias) {     // fixed-order reduce of the per-thread partial sums of each channel
+#pragma unroll
+            for (int k = 0; k < 8; ++k) s_bias[t * 8 + k] = bsum[k];
+            ptx::named_bar_sync(2, kWgXfThreads);
+            if (t < COB) {
+                constexpr int TPC = kWgXfThreads / (COB / 8);
+                const int c = t / 8, k = t % 8;
+                float s = 0.f;
+                for (int u = c * TPC; u < (c + 1) * TPC; ++u) s += s_bias[u * 8 + k];
+                if (co0 + t < P.Cout)
+                    P.scratch[(size_t)split * ((size_t)C::KK * P.Cin * P.Cout + P.Cout) + (size_t)C::KK * P.Cin * P.Cout + co0 + t] = s;
             }
         }
     } else if (warp >= 4 + kWgXfThreads / 32) {
         // ================================================================================ epilogue (once)
-        // accumulator row -> TMEM lane: M=128: lane = row; M=64: lane = (row/16)*32 + row%16 (measured, tests/probes)
+        // accumulator row m -> TMEM lane: M=128: lane = m; M=64: lane = (m/16)*32 + m%16 (measured, tests/probes)
         const int q = warp & 3;
-        const int row = C::UM == 128 ? q * 32 + lane : (lane < 16 ? q * 16 + lane : COB);
-        const int co = co0 + row;
+        const int row = C::UM == 128 ? q * 32 + lane : (lane < 16 ? q * 16 + lane : C::MROWS);
+        const int s_shift_idx = row / NB, ci = ci0 + row % NB;          // row = s*NB + ci
         if (n_work > 0) {
             ptx::mbar_wait(bar_done, 0, 16);
             ptx::tc_fence_after();
             float *dst = P.scratch + (size_t)split * ((size_t)C::KK * P.Cin * P.Cout + P.Cout);
 #pragma unroll 1
-            for (int tap = 0; tap < C::KK; ++tap) {
+            for (int r = 0; r < KS; ++r) {
 #pragma unroll 1
-                for (int n0 = 0; n0 < NB; n0 += 16) {
-                    uint32_t r[16];
-                    ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + tap * NB + n0, r);
+                for (int n0 = 0; n0 < COB; n0 += 16) {
+                    uint32_t v[16];
+                    ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + r * COB + n0, v);
                     ptx::tmem_ld_wait();
-                    if (row < COB && co < P.Cout) {
+                    if (row < C::MROWS && ci < P.Cin) {
+                        float *o = dst + ((size_t)(r * KS + s_shift_idx) * P.Cin + ci) * P.Cout + co0 + n0;
 #pragma unroll
-                        for (int j = 0; j < 16; ++j)
-                            dst[((size_t)tap * P.Cin + ci0 + n0 + j) * P.Cout + co] = __uint_as_float(r[j]);
+                        for (int jj = 0; jj < 16; jj += 4)
+                            if (co0 + n0 + jj < P.Cout)
+                                *reinterpret_cast<float4 *>(o + jj) = make_float4(__uint_as_float(v[jj]), __uint_as_float(v[jj + 1]),
+                                                                                  __uint_as_float(v[jj + 2]), __uint_as_float(v[jj + 3]));
                     }
                 }
             }
