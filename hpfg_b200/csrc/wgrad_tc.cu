@@ -29,14 +29,19 @@ constexpr int kWgXfThreads = 256;   // transform threads (warps 4-11): loader tr
 constexpr int kWgThreads = 128 + kWgXfThreads + 128;   // warps 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 transform, 12-15 epilogue
 constexpr int kWgSmemBudget = 222 * 1024;
 
-template <int KS, int NB, int COB>
+// MT: tile width multiplier (tile = 16 rows x 8*MT columns).  The TMA unit retires roughly one tensor load per ~500
+// cycles however small its box (tests/probes/tma_rate_probe.cu), so the 16-channel layers use wide tiles: two loads
+// then feed 256 instead of 128 pixels.
+template <int KS, int NB, int COB, int MT>
 struct WgCfg {
     static constexpr int PAD = KS / 2, KK = KS * KS;
-    static constexpr int HH = kTH + KS - 1, HW = kTW + KS - 1, NPIX_X = HH * HW;
+    static constexpr int TWP = kTW * MT, TPIX = kTH * TWP;                    // tile width / pixels
+    static constexpr int HH = kTH + KS - 1, HW = TWP + KS - 1, NPIX_X = HH * HW;
     static constexpr int XR_CHS = NPIX_X * 16, XR_OP = (NB / 8) * XR_CHS;     // raw halo tile, TMA target: [chunk][halo pixel][8 ch]
-    static constexpr int XC = HH * kTW * 16;                                  // one chunk of one shifted copy: [halo row][8 cols][8 ch]
-    static constexpr int X3_OP = KS * (NB / 8) * XC;                          // A operand: [shift s][chunk][halo row][8 cols][8 ch]
-    static constexpr int D_CHS = 128 * 16, D_OP = (COB / 8) * D_CHS;          // dY tile, TMA target and B operand: [chunk][pixel][8 ch]
+    static constexpr int ROWP = TWP * 16;                                     // bytes per tile row of one chunk
+    static constexpr int XC = HH * ROWP;                                      // one chunk of one shifted copy: [halo row][TWP cols][8 ch]
+    static constexpr int X3_OP = KS * (NB / 8) * XC;                          // A operand: [shift s][chunk][halo row][TWP cols][8 ch]
+    static constexpr int D_CHS = TPIX * 16, D_OP = (COB / 8) * D_CHS;         // dY tile, TMA target and B operand: [chunk][pixel][8 ch]
     static constexpr int al(int v) { return (v + 127) / 128 * 128; }
     static constexpr int OFF_DOP = 0, OFF_XR = al(D_OP), OFF_X3 = OFF_XR + al(XR_OP);
     static constexpr int STAGE_BYTES = OFF_X3 + al(X3_OP);
@@ -63,11 +68,11 @@ struct WgParams {
     int N, H, W, Cin, Cout, tiles_h, tiles_w, m_tiles, ci_blocks, co_blocks, S;
 };
 
-template <int KS, int NB, int COB>
+template <int KS, int NB, int COB, int MT>
 __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                  const __grid_constant__ CUtensorMap tmD, const WgParams P) {
     pdl_launch_dependents();
-    using C = WgCfg<KS, NB, COB>;
+    using C = WgCfg<KS, NB, COB, MT>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *fixed = smem + C::STAGES * C::STAGE_BYTES + C::TAIL_PAD;
@@ -117,7 +122,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         int stage = 0, phase = 0;
 #pragma unroll 1
         for (int it = 0; it < n_work; ++it) {
-            const int h0 = ti.th * kTH, w0 = ti.tw * kTW;
+            const int h0 = ti.th * kTH, w0 = ti.tw * C::TWP;
             ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 11);
             const uint32_t sb = smem_u32 + stage * C::STAGE_BYTES;
             if (ptx::elect_one()) {
@@ -132,11 +137,11 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     } else if (warp == 1) {      // ==================================================== MMA issuer (warp-uniform)
         constexpr uint32_t idesc = ptx::umma_idesc_bf16(C::UM, COB, 1, 1);   // both operands MN-major
         // descriptor words: hi = SBO | version, lo = (addr >> 4) | LBO << 16; per-MMA offsets are compile-time adds
-        // A = shifted X copies: M groups (8 rows = one (shift, chunk)) SBO = copy-chunk stride, K groups (8 pixels = one tile row) LBO = 128 B
-        // B = dY: N groups (8 co) SBO = chunk stride, K groups (8 pixels) LBO = 128 B
+        // A = shifted X copies: M groups (8 rows = one (shift, chunk)) SBO = copy-chunk stride, K groups (8 pixels of one tile row) LBO = row pitch
+        // B = dY: N groups (8 co) SBO = chunk stride, K groups (8 pixels of one tile row) LBO = row pitch
         constexpr uint32_t a_hi = (uint32_t)(C::XC >> 4) | (1u << 14), b_hi = (uint32_t)(C::D_CHS >> 4) | (1u << 14);
-        const uint32_t a_lo0 = (((smem_u32 + C::OFF_X3) >> 4) & 0x3FFFu) | ((uint32_t)(128 >> 4) << 16);
-        const uint32_t b_lo0 = (((smem_u32 + C::OFF_DOP) >> 4) & 0x3FFFu) | ((uint32_t)(128 >> 4) << 16);
+        const uint32_t a_lo0 = (((smem_u32 + C::OFF_X3) >> 4) & 0x3FFFu) | ((uint32_t)(C::ROWP >> 4) << 16);
+        const uint32_t b_lo0 = (((smem_u32 + C::OFF_DOP) >> 4) & 0x3FFFu) | ((uint32_t)(C::ROWP >> 4) << 16);
         int stage = 0, phase = 0;
 #pragma unroll 1
         for (int it = 0; it < n_work; ++it) {
@@ -145,11 +150,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
             const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4), b_lo = b_lo0 + stage * (C::STAGE_BYTES >> 4);
             if (ptx::elect_one()) {
 #pragma unroll 2
-                for (int j = 0; j < 8; ++j) {            // K step = 16 pixels = tile rows 2j, 2j+1
-                    const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)((j * 256) >> 4));
+                for (int j = 0; j < 8 * MT; ++j) {       // K step = 16 pixels = tile rows 2*jr, 2*jr+1 x columns 8*jc .. 8*jc+7
+                    const int jr = j / MT, jc = j % MT;
+                    const uint64_t bd = ((uint64_t)b_hi << 32) | (uint64_t)(b_lo + (uint32_t)((2 * jr * C::ROWP + jc * 128) >> 4));
 #pragma unroll
-                    for (int r = 0; r < KS; ++r) {       // tap row: start at halo row 2j + r of every copy
-                        const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(((2 * j + r) * 128) >> 4));
+                    for (int r = 0; r < KS; ++r) {       // tap row: start at halo row 2*jr + r of every copy
+                        const uint64_t ad = ((uint64_t)a_hi << 32) | (uint64_t)(a_lo + (uint32_t)(((2 * jr + r) * C::ROWP + jc * 128) >> 4));
                         ptx::umma_bf16(tmem_base + r * COB, ad, bd, idesc, (it == 0 && j == 0) ? 0u : 1u);
                     }
                 }
@@ -169,7 +175,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         int stage = 0, phase = 0;
 #pragma unroll 1
         for (int it = 0; it < n_work; ++it) {
-            const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * kTW - C::PAD;
+            const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * C::TWP - C::PAD;
             const size_t img_px = (size_t)ti.n_img * P.H;
             ptx::mbar_wait(bar_full + 8 * stage, phase, 15);
             const uint32_t sb = smem_u32 + stage * C::STAGE_BYTES;
@@ -177,9 +183,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
                 // thread t owns chunk t / TPC and pixels (t % TPC), +TPC, ...: consecutive lanes read consecutive 16-byte units
                 constexpr int TPC = kWgXfThreads / (COB / 8);
                 const int bc = t / TPC;
-                for (int px = t % TPC; px < 128; px += TPC) {
+                for (int px = t % TPC; px < C::TPIX; px += TPC) {
                     float f[8];
-                    unpack8(ptx::lds128(sb + C::OFF_DOP + (bc * 128 + px) * 16), f);
+                    unpack8(ptx::lds128(sb + C::OFF_DOP + (bc * C::TPIX + px) * 16), f);
 #pragma unroll
                     for (int k = 0; k < 8; ++k) bsum[k] += f[k];
                 }
@@ -209,10 +215,10 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
                     }
                 }
                 // halo column hc lands in copy s at column hc - s
-                const uint32_t dst = sb + C::OFF_X3 + c * C::XC + (hr * kTW + hc) * 16;
+                const uint32_t dst = sb + C::OFF_X3 + c * C::XC + (hr * C::TWP + hc) * 16;
 #pragma unroll
                 for (int s = 0; s < KS; ++s)
-                    if (hc - s >= 0 && hc - s < kTW) ptx::sts128(dst + s * (NB / 8) * C::XC - s * 16, v);
+                    if (hc - s >= 0 && hc - s < C::TWP) ptx::sts128(dst + s * (NB / 8) * C::XC - s * 16, v);
             }
             ptx::fence_proxy_async_smem();
             __syncwarp();
@@ -292,39 +298,48 @@ __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const float *__res
     }
 }
 
-static void wg_shape(int N, int H, int W, int Cin, int Cout, int &NB, int &COB, int &ci_blocks, int &co_blocks, int &S, int &m_tiles) {
+static void wg_shape(int ks, int N, int H, int W, int Cin, int Cout, int &NB, int &COB, int &MT, int &ci_blocks, int &co_blocks, int &S,
+                     int &m_tiles) {
     NB = Cin == 16 ? 16 : 32;
     COB = std::min(Cout, 128);
     ci_blocks = Cin / NB;
     co_blocks = Cout / COB;
-    m_tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
+    // wide tiles for the 16-channel layers on large images (TMA-issue bound otherwise; with 32 input channels the
+    // wider stage leaves too few pipeline stages in shared memory and measures slower)
+    MT = (ks == 3 && NB == 16 && COB <= 32 && W % (2 * kTW) == 0 && (int64_t)N * ((H + kTH - 1) / kTH) * (W / (2 * kTW)) >= 4 * kNumSMs) ? 2 : 1;
+    m_tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW * MT - 1) / (kTW * MT));
     S = std::max(1, std::min(kNumSMs / (ci_blocks * co_blocks), m_tiles));
 }
 
 int64_t tc_wgrad_scratch_floats(int N, int H, int W, int Cin, int Cout, int KS) {
-    int NB, COB, cib, cob, S, mt;
-    wg_shape(N, H, W, Cin, Cout, NB, COB, cib, cob, S, mt);
+    int NB, COB, MT, cib, cob, S, mt;
+    wg_shape(KS, N, H, W, Cin, Cout, NB, COB, MT, cib, cob, S, mt);
     return (int64_t)S * ((int64_t)KS * KS * Cin * Cout + Cout);
 }
 
-template <int KS, int NB, int COB>
+template <int KS, int NB, int COB, int MT>
 static int wg_launch(const CUtensorMap &mx, const CUtensorMap &md, const WgParams &P, cudaStream_t s) {
-    using C = WgCfg<KS, NB, COB>;
+    using C = WgCfg<KS, NB, COB, MT>;
     static bool attr_set = false;
     if (!attr_set) {
-        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<KS, NB, COB>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<KS, NB, COB, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
     const int grid = P.ci_blocks * P.co_blocks * P.S;
-    HPFG_CUDA_CHECK(launch_pdl(tc_wgrad_kernel<KS, NB, COB>, grid, kWgThreads, C::SMEM_BYTES, s, mx, md, P));
+    HPFG_CUDA_CHECK(launch_pdl(tc_wgrad_kernel<KS, NB, COB, MT>, grid, kWgThreads, C::SMEM_BYTES, s, mx, md, P));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
 
 template <int KS>
-static int wg_dispatch(int NB, int COB, const CUtensorMap &mx, const CUtensorMap &md, const WgParams &P, cudaStream_t s) {
-#define HPFG_WG_CASE(nb, cob) \
-    if (NB == nb && COB == cob) return wg_launch<KS, nb, cob>(mx, md, P, s);
+static int wg_dispatch(int NB, int COB, int MT, const CUtensorMap &mx, const CUtensorMap &md, const WgParams &P, cudaStream_t s) {
+#define HPFG_WG_CASE(nb, cob)                                                    \
+    if (NB == nb && COB == cob) {                                                \
+        if constexpr (KS == 3 && nb == 16 && cob <= 32) {                        \
+            if (MT == 2) return wg_launch<KS, nb, cob, 2>(mx, md, P, s);         \
+        }                                                                        \
+        return wg_launch<KS, nb, cob, 1>(mx, md, P, s);                          \
+    }
     HPFG_WG_CASE(16, 16) HPFG_WG_CASE(16, 32) HPFG_WG_CASE(16, 64) HPFG_WG_CASE(16, 128)
     HPFG_WG_CASE(32, 16) HPFG_WG_CASE(32, 32) HPFG_WG_CASE(32, 64) HPFG_WG_CASE(32, 128)
 #undef HPFG_WG_CASE
@@ -335,19 +350,19 @@ static int wg_dispatch(int NB, int COB, const CUtensorMap &mx, const CUtensorMap
 int tc_wgrad_run(int ks, int N, int H, int W, int Cin, int Cout, int cin_real, int cout_real, const void *x, LoadXform xf, const void *dy, float *scratch,
                  int64_t scratch_floats, float *dw_oihw, float *dbias, int accumulate, cudaStream_t s) {
     ProfScope _prof(PROF_WGRAD_TC, s);
-    int NB, COB;
+    int NB, COB, MT;
     WgParams P{};
-    wg_shape(N, H, W, Cin, Cout, NB, COB, P.ci_blocks, P.co_blocks, P.S, P.m_tiles);
+    wg_shape(ks, N, H, W, Cin, Cout, NB, COB, MT, P.ci_blocks, P.co_blocks, P.S, P.m_tiles);
     HPFG_REQUIRE(tc_wgrad_scratch_floats(N, H, W, Cin, Cout, ks) <= scratch_floats, "tc_wgrad: scratch too small");
     CUtensorMap mx, md;
-    HPFG_RETURN_IF(make_map_chunked(&mx, x, N, H, W, Cin, NB / 8, kTW + ks - 1, kTH + ks - 1));
-    HPFG_RETURN_IF(make_map_chunked(&md, dy, N, H, W, Cout, COB / 8, kTW, kTH));
+    HPFG_RETURN_IF(make_map_chunked(&mx, x, N, H, W, Cin, NB / 8, kTW * MT + ks - 1, kTH + ks - 1));
+    HPFG_RETURN_IF(make_map_chunked(&md, dy, N, H, W, Cout, COB / 8, kTW * MT, kTH));
     P.scale = xf.scale; P.shift = xf.shift;
     P.dropbits = reinterpret_cast<const uint8_t *>(xf.drop.bits); P.inv_keep = xf.drop.inv_keep;
     P.scratch = scratch;
     P.N = N; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
-    P.tiles_h = (H + kTH - 1) / kTH; P.tiles_w = (W + kTW - 1) / kTW;
-    HPFG_RETURN_IF(ks == 3 ? wg_dispatch<3>(NB, COB, mx, md, P, s) : wg_dispatch<1>(NB, COB, mx, md, P, s));
+    P.tiles_h = (H + kTH - 1) / kTH; P.tiles_w = (W + kTW * MT - 1) / (kTW * MT);
+    HPFG_RETURN_IF(ks == 3 ? wg_dispatch<3>(NB, COB, MT, mx, md, P, s) : wg_dispatch<1>(NB, COB, MT, mx, md, P, s));
     const int64_t per = (int64_t)ks * ks * Cin * Cout + Cout;
     const int blocks = (int)std::min<int64_t>((per + 255) / 256, (int64_t)kNumSMs * 4);
     HPFG_CUDA_CHECK(launch_pdl(tc_wgrad_reduce_kernel, blocks, 256, 0, s, scratch, P.S, Cin, Cout, ks * ks, cin_real, cout_real, dw_oihw, dbias, accumulate));
