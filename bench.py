@@ -171,12 +171,37 @@ def run_gpu(args):
     def resident_step():
         return step.step(x_dev, y_dev)
 
+    # End-to-end leg: every step's inputs start in pinned HOST memory and the step's loss is read back to the host and
+    # waited for (the reference trainers call loss.item() every iteration).  The copy of step k+1's batch is enqueued
+    # on a copy stream while step k computes (what a prefetching data loader does); all K copies and K loss
+    # read-backs happen inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [(torch.empty_like(x_dev), torch.empty_like(y_dev)) for _ in range(2)]
+    copied = [torch.cuda.Event() for _ in range(2)]
+    consumed = [torch.cuda.Event() for _ in range(2)]
+    state = {"k": 0, "primed": False}
+
+    def enqueue_copy(slot):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(consumed[slot])            # the step that last read this slot has finished
+            bufs[slot][0].copy_(x_pin, non_blocking=True)
+            bufs[slot][1].copy_(y_pin, non_blocking=True)
+            copied[slot].record(copy_stream)
+
     def e2e_step():
-        xd = x_pin.to(dev, non_blocking=True)
-        yd = y_pin.to(dev, non_blocking=True)
-        loss = step.step(xd, yd)
+        k = state["k"]
+        slot = k & 1
+        if not state["primed"]:                               # first step of a timed run: its copy is not hidden
+            enqueue_copy(slot)
+            state["primed"] = True
+        main = torch.cuda.current_stream()
+        main.wait_event(copied[slot])
+        loss = step.step(bufs[slot][0], bufs[slot][1])
+        consumed[slot].record(main)
+        enqueue_copy(slot ^ 1)                                # prefetch the next step's batch while this step computes
         loss_pin.copy_(loss.reshape(1), non_blocking=True)
-        torch.cuda.current_stream().synchronize()         # the host consumes the loss every step
+        main.synchronize()                                    # the host consumes the loss every step
+        state["k"] = k + 1
 
     for _ in range(max(args.warmup, 3)):
         resident_step()
@@ -190,6 +215,8 @@ def run_gpu(args):
         sampler.stop_flag = True
     for _ in range(2):
         e2e_step()
+    torch.cuda.synchronize()
+    state["primed"] = False
     ms_e2e = timed(e2e_step, args.steps)
     images = (N_L + N_U) * world
     value = images * args.steps / (ms * 1e-3)
