@@ -25,6 +25,7 @@ if ROOT not in sys.path:
 METRIC = "UNet SSL train images/sec @224x224 (Mean-Teacher step)"
 N_L, N_U, IN_CH, N_CLS, H, W = 8, 24, 1, 4, 224, 224
 F_FWD = 4516642816.0                 # conv FLOPs per image, forward
+TOP_KERNEL_DRAM_BYTES = 58.16e6      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_ncu_prof_fprop16_final_raw.txt)
 F_IN0 = 2.0 * 9 * H * W * IN_CH * 16
 MT_FLOP_PER_IMAGE = 4 * F_FWD - F_IN0    # student fwd+bwd + teacher fwd
 
@@ -203,33 +204,41 @@ def run_gpu(args):
         main.synchronize()                                    # the host consumes the loss every step
         state["k"] = k + 1
 
-    for _ in range(max(args.warmup, 3)):
-        resident_step()
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        resident_step()
     launches0 = lib.hpfg_launch_count()
     ms = timed(resident_step, args.steps)
     launches = lib.hpfg_launch_count() - launches0
-    if sampler:
-        sampler.stop_flag = True
     for _ in range(2):
         e2e_step()
     torch.cuda.synchronize()
     state["primed"] = False
     ms_e2e = timed(e2e_step, args.steps)
+    if sampler:
+        sampler.stop_flag = True
     images = (N_L + N_U) * world
     value = images * args.steps / (ms * 1e-3)
     e2e_value = images * args.steps / (ms_e2e * 1e-3)
 
     # ---- per-category device time (separate, untimed pass): roofline of the dominant kernel family
     prof_steps = 3
+    step.serialize = True                                # no side streams: per-category times must not overlap
+    resident_step()
     lib.hpfg_profile_begin()
     for _ in range(prof_steps):
         resident_step()
     cat_ms = (ctypes.c_double * 8)()
     cat_calls = (ctypes.c_int64 * 8)()
     lib.hpfg_profile_end(cat_ms, cat_calls)
+    step.serialize = False
+
+    def layer_us(op, cin, cout, ks, res, iters=20):
+        ms_l = ctypes.c_float()
+        L.check(lib.hpfg_conv_tc_bench(op, N_L + N_U, res, res, cin, cout, ks, iters, ctypes.byref(ms_l), L.stream_ptr(dev)), "hpfg_conv_tc_bench")
+        return ms_l.value * 1e3
     names = ["conv_tcgen05", "conv_cuda_core", "wgrad_cuda_core", "bn_pool_upsample_glue", "ssl_loss", "sgd_ema", "weight_pack", "wgrad_tcgen05"]
     prof = {names[i]: {"ms_per_step": cat_ms[i] / prof_steps, "calls_per_step": cat_calls[i] / prof_steps} for i in range(8)}
     pk = peaks()
@@ -245,6 +254,18 @@ def run_gpu(args):
         tc_ms = prof["conv_tcgen05"]["ms_per_step"]
         achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
         cpu_ips, cpu_sec = cpu_reference_steps(2, 1, 2, 6) if world == 1 and not args.no_cpu else (None, None)
+        # the single most expensive kernel instance: the 3x3 16->16 conv at 224x224 (4 launches per forward); it is bound by
+        # HBM / shared-memory operand bandwidth, not by the tensor pipe: algorithmic bytes = bf16 in + out once
+        top_bytes = n_img * H * W * (16 + 16) * 2.0
+        top_us = layer_us(0, 16, 16, 3, H) if world == 1 else None
+        layers = []
+        if world == 1:
+            for cin, cout, ks, res in [(16, 16, 3, 224), (32, 16, 3, 224), (32, 32, 3, 112), (64, 64, 3, 56), (128, 128, 3, 28), (256, 256, 3, 14)]:
+                px = n_img * res * res
+                t3 = [layer_us(op, cin, cout, ks, res) for op in (0, 1, 2)]
+                layers.append({"layer": "%dx%d conv %d->%d @%d" % (ks, ks, cin, cout, res), "fprop_us": t3[0], "dgrad_us": t3[1], "wgrad_us": t3[2],
+                               "fprop_hbm_frac": px * (cin + cout) * 2.0 / (t3[0] * 1e-6) / 1e9 / pk["hbm"],
+                               "fprop_tensor_frac": 2.0 * px * cin * cout * ks * ks / (t3[0] * 1e-6) / 1e12 / pk["tf_burst"]})
         line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
                 "data": "synthetic",
@@ -258,7 +279,14 @@ def run_gpu(args):
                                                  "frac_of_peak": value / world * MT_FLOP_PER_IMAGE / 1e12 / pk["tf_sustained"]},
                 "roofline": {"kernel": "tc_conv_kernel (tcgen05 implicit-GEMM conv family: fprop + dgrad + 1x1)", "bound": "tensor",
                              "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                             "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " sustained bf16"},
+                             "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
+                             "note": "all tensor-core conv launches of a step (serialized profiling pass); FLOPs = SURVEY 8d"},
+                "roofline_top_kernel": None if top_us is None else {
+                    "kernel": "tc_conv_kernel<3,16,16,RES,MT=4,XF=1> (3x3 16->16 @224, fused BN+LeakyReLU loader, BN-stat epilogue)",
+                    "bound": "hbm", "achieved": top_bytes / (top_us * 1e-6) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
+                    "frac": top_bytes / (top_us * 1e-6) / 1e9 / pk["hbm"], "us_per_launch": top_us,
+                    "traffic": TOP_KERNEL_DRAM_BYTES, "traffic_source": "ncu --set full, profiles/r01_ncu_prof_fprop16_final_raw.txt (dram read+write per launch; the 51 MB output mostly stays in the 126 MB L2)"},
+                "layer_table": layers,
                 "kernel_time_per_step": prof,
                 "clocks": sampler.summary() if sampler else None}
         if cpu_ips is not None:

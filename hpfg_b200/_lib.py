@@ -7,7 +7,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libhpfg_b200.so")
+LIB_PATH = os.environ.get("HPFG_B200_LIB") or os.path.join(_HERE, "libhpfg_b200.so")   # override: A/B builds under profiles/
 
 c_i64p = ctypes.POINTER(ctypes.c_int64)
 c_vp = ctypes.c_void_p

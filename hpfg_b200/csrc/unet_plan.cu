@@ -280,7 +280,7 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
     // Weight gradients run on the plan's side stream, concurrently with the data-gradient chain: wgrad(layer) and
     // dgrad(layer) both consume the layer's raw gradient and are independent of each other.  The raw gradient lives
     // in one of two alternating buffers; before a buffer is rewritten the main stream waits for the wgrad that read it.
-    cudaStream_t side = p->side;
+    cudaStream_t side = g_prof_on ? s : p->side;      // per-category timing (bench.py's roofline leg) wants serialized kernels
     void *dr[2] = {p->g[1], p->g[4]};
     bool dr_busy[2] = {false, false};
     int bi = 1;

@@ -168,7 +168,14 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     } else if (warp >= 4 && warp < 4 + kWgXfThreads / 32) {
         // ================================================================================ transform warps
         const int t = threadIdx.x - 128;
-        constexpr int XITEMS = C::NPIX_X * (NB / 8);
+        // thread -> one 8-channel chunk for the whole kernel (its affine lives in registers) and every XPSTEP-th halo pixel
+        // (two chunks: lanes alternate chunks and stay bank-conflict free; four chunks would conflict 2-way, so there a warp
+        // pair owns a chunk: consecutive lanes read consecutive pixels)
+        constexpr int NCHK = NB / 8, XPSTEP = kWgXfThreads / NCHK;
+        const int xc = NCHK == 2 ? t % NCHK : t / XPSTEP, xp0 = NCHK == 2 ? t / NCHK : t % XPSTEP, xch = ci0 + xc * 8;
+        float scl[8], shf[8];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { scl[k] = xform ? s_scale[xch + k] : 1.f; shf[k] = xform ? s_shift[xch + k] : 0.f; }
         float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias-gradient partial sums of this thread's chunk
         TileIter ti;
         ti.init(split, P.S, P.tiles_h, P.tiles_w);
@@ -190,21 +197,19 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
                     for (int k = 0; k < 8; ++k) bsum[k] += f[k];
                 }
             }
-            for (int i = t; i < XITEMS; i += kWgXfThreads) {
-                const int c = i / C::NPIX_X, p = i % C::NPIX_X;
+            for (int p = xp0; p < C::NPIX_X; p += XPSTEP) {
                 const int hr = p / C::HW, hc = p % C::HW;
-                uint4 v = ptx::lds128(sb + C::OFF_XR + i * 16);
+                uint4 v = ptx::lds128(sb + C::OFF_XR + (xc * C::NPIX_X + p) * 16);
                 if (xform) {
                     const int gh = h0 + hr, gw = w0 + hc;
                     if (gh >= 0 && gh < P.H && gw >= 0 && gw < P.W) {
                         float f[8];
                         unpack8(v, f);
-                        const int ch = ci0 + c * 8;
                         uint32_t keep = 0xffu;
-                        if (P.dropbits) keep = P.dropbits[(((img_px + gh) * P.W + gw) * P.Cin + ch) >> 3];
+                        if (P.dropbits) keep = P.dropbits[(((img_px + gh) * P.W + gw) * P.Cin + xch) >> 3];
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
-                            float a = fmaf(f[k], s_scale[ch + k], s_shift[ch + k]);
+                            float a = fmaf(f[k], scl[k], shf[k]);
                             a = fmaxf(a, kLeakySlope * a);
                             if (P.dropbits) a = ((keep >> k) & 1u) ? a * P.inv_keep : 0.f;
                             f[k] = a;
@@ -215,7 +220,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
                     }
                 }
                 // halo column hc lands in copy s at column hc - s
-                const uint32_t dst = sb + C::OFF_X3 + c * C::XC + (hr * C::TWP + hc) * 16;
+                const uint32_t dst = sb + C::OFF_X3 + xc * C::XC + (hr * C::TWP + hc) * 16;
 #pragma unroll
                 for (int s = 0; s < KS; ++s)
                     if (hc - s >= 0 && hc - s < C::TWP) ptx::sts128(dst + s * (NB / 8) * C::XC - s * 16, v);

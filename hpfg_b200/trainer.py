@@ -148,7 +148,8 @@ class MeanTeacherStep(_StepBase):
         n_l = labels.shape[0]
         # the teacher forward is independent of the student forward: it runs on a side stream so that each network's
         # small / dependent kernels fill the other's bubbles (the teacher sees the whole batch, 2017_03...:100)
-        main, side = torch.cuda.current_stream(x.device), self._side_stream(x.device)
+        main = torch.cuda.current_stream(x.device)
+        side = main if getattr(self, "serialize", False) else self._side_stream(x.device)   # serialize: profiling only
         side.wait_stream(main)
         shape = (x.shape[0], self.num_classes, x.shape[2], x.shape[3])
         with torch.cuda.stream(side):
