@@ -180,14 +180,24 @@ class CPSStep(_StepBase):
     def step(self, x, labels):
         self.cur_itrs += 1
         n_l = labels.shape[0]
-        p1, o1 = self._forward(self.m1, x, True)
-        p2, o2 = self._forward(self.m2, x, True)
+        # the two networks are independent except for the loss: network 2 runs on a side stream (forward, then backward + SGD)
+        main = torch.cuda.current_stream(x.device)
+        side = main if getattr(self, "serialize", False) else self._side_stream(x.device)
+        shape = (x.shape[0], self.num_classes, x.shape[2], x.shape[3])
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            p2, o2 = self._forward(self.m2, x, True, out=self._persistent("o2", shape, x.device))
+        p1, o1 = self._forward(self.m1, x, True, out=self._persistent("o1", shape, x.device))
+        main.wait_stream(side)
         w = self._consistency_weight()
         r = ssl_loss_raw(L.LOSS_CPS, o1, o2, labels, n_l, cons_weight=w, want_pseudo=False)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._backward(self.m2, p2, r["dother"], self.g2)
+            self._sgd(self.m2, self.g2, self.b2)
         self._backward(self.m1, p1, r["dstudent"], self.g1)
-        self._backward(self.m2, p2, r["dother"], self.g2)
         lr = self._sgd(self.m1, self.g1, self.b1)
-        self._sgd(self.m2, self.g2, self.b2)
+        main.wait_stream(side)
         self.last = dict(scalars=r["scalars"], lr=lr, w=w, logits1=o1, logits2=o2)
         return r["scalars"][0]
 
@@ -214,16 +224,24 @@ class UAMTStep(_StepBase):
         n_l = labels.shape[0]
         x_u = x[n_l:]
         n_u = x_u.shape[0]
-        plan, out = self._forward(self.model, x, True)
         if noise is None:
             noise = self.make_noise(x_u)
-        _, t_out = self._forward(self.ema_model, (x_u + noise).contiguous(), False)
         xr = x_u.repeat(2, 1, 1, 1)
-        mc = torch.empty((self.T * n_u, out.shape[1], x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
-        for i in range(self.T // 2):
-            nz = mc_noise[i] if mc_noise is not None else self.make_noise(xr)
-            _, o = self._forward(self.ema_model, (xr + nz).contiguous(), False)
-            mc[2 * n_u * i:2 * n_u * (i + 1)] = o
+        noises = [mc_noise[i] if mc_noise is not None else self.make_noise(xr) for i in range(self.T // 2)]
+        x_t = (x_u + noise).contiguous()
+        x_mc = [(xr + nz).contiguous() for nz in noises]
+        ncls, hh, ww = self.num_classes, x.shape[2], x.shape[3]
+        mc = self._persistent("mc", (self.T * n_u, ncls, hh, ww), x.device)
+        # the five teacher forwards are independent of the student forward: side stream
+        main = torch.cuda.current_stream(x.device)
+        side = main if getattr(self, "serialize", False) else self._side_stream(x.device)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _, t_out = self._forward(self.ema_model, x_t, False, out=self._persistent("t_out", (n_u, ncls, hh, ww), x.device))
+            for i in range(self.T // 2):
+                self._forward(self.ema_model, x_mc[i], False, out=mc[2 * n_u * i:2 * n_u * (i + 1)])
+        plan, out = self._forward(self.model, x, True, out=self._persistent("s_out", (x.shape[0], ncls, hh, ww), x.device))
+        main.wait_stream(side)
         w = self._consistency_weight()
         thr = (0.75 + 0.25 * sigmoid_rampup(self.cur_itrs, self.total_itrs)) * math.log(2)
         r = ssl_loss_raw(L.LOSS_UAMT, out, t_out, labels, n_l, cons_weight=w, mc_logits=mc, mc_passes=self.T,
