@@ -173,91 +173,99 @@ __device__ __forceinline__ void bilinear_src(int dst, float scale, int in_size, 
     l0 = 1.f - l1;
 }
 
+// blockIdx.y = 0: skip half (encoder feature = leaky(bn(raw))), 1: bilinearly upsampled half -- the two code paths never
+// share a warp (with one grid a warp held both kinds of channel vectors and executed both paths: 244 instructions per
+// 16-byte item, issue-bound at 20 % of HBM bandwidth in ncu).
 template <typename T>
 __global__ void __launch_bounds__(256) upcat_kernel(const T *__restrict__ raw_skip, BnState bn, const T *__restrict__ low,
                                                     T *__restrict__ cat, int N, int h, int w, int F, float sh_, float sw_,
-                                                    FastDiv dCV, FastDiv dW, FastDiv dH) {
+                                                    FastDiv dFV, FastDiv dW, FastDiv dH) {
     pdl_prologue();
     constexpr int V = Vec<T>::N;
-    const int H = 2 * h, W = 2 * w, FV = F / V;
-    const uint32_t total = (uint32_t)N * H * W * dCV.d;
-    // the grid stride is a multiple of CV: a thread keeps one channel vector of the concatenated tensor
+    const int H = 2 * h, W = 2 * w;
+    const uint32_t total = (uint32_t)N * H * W * dFV.d;
+    // the grid stride is a multiple of FV: a thread keeps one channel vector
     const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t cv = i0 - fast_div(i0, dCV) * dCV.d;
-    float sc[V], sf[V];
+    const uint32_t cv = i0 - fast_div(i0, dFV) * dFV.d;
+    if (blockIdx.y == 0) {
+        float sc[V], sf[V];
 #pragma unroll
-    for (int k = 0; k < V; ++k) {
-        sc[k] = cv < (uint32_t)FV ? bn.scale[cv * V + k] : 0.f;
-        sf[k] = cv < (uint32_t)FV ? bn.shift[cv * V + k] : 0.f;
-    }
-    for (uint32_t i = i0; i < total; i += gridDim.x * blockDim.x) {
-        uint32_t pix = fast_div(i, dCV), x, y, n;
-        fast_divmod(pix, dW, pix, x);
-        fast_divmod(pix, dH, n, y);
-        float out[V];
-        if (cv < FV) {   // skip half: the encoder feature = leaky(bn(raw))
-            float v[V];
-            Vec<T>::load(raw_skip + (((int64_t)n * H + y) * W + x) * F + cv * V, v);
+        for (int k = 0; k < V; ++k) { sc[k] = bn.scale[cv * V + k]; sf[k] = bn.shift[cv * V + k]; }
+        for (uint32_t i = i0; i < total; i += gridDim.x * blockDim.x) {
+            const uint32_t pix = fast_div(i, dFV);
+            float v[V], out[V];
+            Vec<T>::load(raw_skip + (int64_t)pix * F + cv * V, v);
 #pragma unroll
             for (int k = 0; k < V; ++k) out[k] = leaky(fmaf(v[k], sc[k], sf[k]));
-        } else {         // upsampled half
-            const int c0 = (cv - FV) * V;
+            Vec<T>::store(cat + (int64_t)pix * (2 * F) + cv * V, out);
+        }
+    } else {
+        for (uint32_t i = i0; i < total; i += gridDim.x * blockDim.x) {
+            uint32_t pix = fast_div(i, dFV), x, y, n;
+            const uint32_t opix = pix;
+            fast_divmod(pix, dW, pix, x);
+            fast_divmod(pix, dH, n, y);
             int y0, y1, x0, x1;
             float ly0, ly1, lx0, lx1;
             bilinear_src(y, sh_, h, y0, y1, ly0, ly1);
             bilinear_src(x, sw_, w, x0, x1, lx0, lx1);
-            float a[V], b[V], c[V], d[V];
-            const T *base = low + (int64_t)n * h * w * F + c0;
+            float a[V], b[V], c[V], d[V], out[V];
+            const T *base = low + (int64_t)n * h * w * F + cv * V;
             Vec<T>::load(base + ((int64_t)y0 * w + x0) * F, a);
             Vec<T>::load(base + ((int64_t)y0 * w + x1) * F, b);
             Vec<T>::load(base + ((int64_t)y1 * w + x0) * F, c);
             Vec<T>::load(base + ((int64_t)y1 * w + x1) * F, d);
 #pragma unroll
             for (int k = 0; k < V; ++k) out[k] = ly0 * (lx0 * a[k] + lx1 * b[k]) + ly1 * (lx0 * c[k] + lx1 * d[k]);
+            Vec<T>::store(cat + (int64_t)opix * (2 * F) + F + cv * V, out);
         }
-        Vec<T>::store(cat + (((int64_t)n * H + y) * W + x) * (2 * F) + cv * V, out);
     }
 }
 
 template <typename T>
 int upcat(const T *raw_skip, BnState bn_skip, const T *low, T *cat, int N, int h, int w, int F, cudaStream_t s) {
     ProfScope _prof(PROF_GLUE, s);
-    const int64_t total = (int64_t)N * 4 * h * w * (2 * F / Vec<T>::N);
+    const int64_t total = (int64_t)N * 4 * h * w * (F / Vec<T>::N);     // per half
     const float sh_ = (2 * h > 1) ? (float)(h - 1) / (float)(2 * h - 1) : 0.f;
     const float sw_ = (2 * w > 1) ? (float)(w - 1) / (float)(2 * w - 1) : 0.f;
     HPFG_REQUIRE(total < (1ll << 31), "upcat: tensor too large for 32-bit indexing");
-    HPFG_CUDA_CHECK(launch_pdl(upcat_kernel<T>, ew_grid(total), 256, 0, s, raw_skip, bn_skip, low, cat, N, h, w, F, sh_, sw_, make_fastdiv(2 * F / Vec<T>::N), make_fastdiv(2 * w), make_fastdiv(2 * h)));
+    HPFG_CUDA_CHECK(launch_pdl(upcat_kernel<T>, dim3((unsigned)ew_grid(total), 2), 256, 0, s, raw_skip, bn_skip, low, cat, N, h, w, F, sh_, sw_, make_fastdiv(F / Vec<T>::N), make_fastdiv(2 * w), make_fastdiv(2 * h)));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
 
 // ----------------------------------------------------------------------------------------------- bn_bwd
-// g = dact * dropout' * leaky'(z);  xhat = (raw-mean)*invstd.  MODE 0: reduce sum(g), sum(g*xhat) into partials.
-// MODE 1: draw = scale*(g - c1 - xhat*c2).
+// g = dact * dropout' * leaky'(z);  xhat = (raw-mean)*invstd.
+// MODE 0: reduce sum(g), sum(g*raw) into partials (the finalize kernel turns the raw moment into sum(g*xhat)).
+// MODE 1: draw = scale*(g - c1 - xhat*c2) = scale*g + B*raw + D with B = -scale*c2*invstd, D = -scale*c1 - B*mean.
+// Few per-channel constants on purpose: 64 registers per thread keep four CTAs per SM resident (ncu: at 84 registers
+// the kernel ran two CTAs per SM and reached 33-41 % of HBM bandwidth).
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256) bn_bwd_kernel(const T *__restrict__ dact, const T *__restrict__ raw,
-                                                     T *__restrict__ draw, int64_t M, int C, BnState bn, DropSpec drop,
-                                                     float *__restrict__ partials) {
+__global__ void __launch_bounds__(256, 4) bn_bwd_kernel(const T *__restrict__ dact, const T *__restrict__ raw,
+                                                        T *__restrict__ draw, int64_t M, int C, BnState bn, DropSpec drop,
+                                                        float *__restrict__ partials) {
     pdl_prologue();
     constexpr int V = Vec<T>::N;
     __shared__ float red[2 * 256 * V];
     const int CV = C / V, R = 256 / CV;
     const int cv = threadIdx.x % CV, r = threadIdx.x / CV;
     const bool active = r < R;
-    float sc[V], sh[V], mu[V], is[V], c1[V], c2[V], a0[V], a1[V];
+    float sc[V], sh[V], kb[V], kd[V];        // MODE 0: kb/kd are the running sums
 #pragma unroll
     for (int k = 0; k < V; ++k) {
         const int c = cv * V + k;
-        sc[k] = bn.scale[c]; sh[k] = bn.shift[c]; mu[k] = bn.mean[c]; is[k] = bn.invstd[c];
-        c1[k] = c2[k] = 0.f;
-        if (MODE == 1) { c1[k] = bn.c1[c]; c2[k] = bn.c2[c]; }
-        a0[k] = a1[k] = 0.f;
+        sc[k] = bn.scale[c]; sh[k] = bn.shift[c];
+        kb[k] = kd[k] = 0.f;
+        if (MODE == 1) {
+            kb[k] = -sc[k] * bn.c2[c] * bn.invstd[c];
+            kd[k] = -sc[k] * bn.c1[c] - kb[k] * bn.mean[c];
+        }
     }
     const int64_t rows_per_block = (M + gridDim.x - 1) / gridDim.x;
     const int64_t p0 = (int64_t)blockIdx.x * rows_per_block;
     const int64_t p1 = (p0 + rows_per_block < M) ? p0 + rows_per_block : M;
     if (active)
-#pragma unroll 4
+#pragma unroll 2
         for (int64_t p = p0 + r; p < p1; p += R) {
             float d[V], x[V];
             Vec<T>::load(dact + p * C + cv * V, d);
@@ -267,25 +275,23 @@ __global__ void __launch_bounds__(256) bn_bwd_kernel(const T *__restrict__ dact,
                 const int64_t e = p * C + cv * V;          // V divides 32, so the V bits sit in one word
                 mbits = drop.bits[e >> 5] >> (e & 31);
             }
-            float o[V];
 #pragma unroll
             for (int k = 0; k < V; ++k) {
                 const float z = fmaf(x[k], sc[k], sh[k]);
                 float g = d[k] * leaky_grad(z);
                 if (drop.bits) g = ((mbits >> k) & 1u) ? g * drop.inv_keep : 0.f;
-                const float xh = (x[k] - mu[k]) * is[k];
-                if (MODE == 0) { a0[k] += g; a1[k] += g * xh; }
-                else o[k] = sc[k] * (g - c1[k] - xh * c2[k]);
+                if (MODE == 0) { kb[k] += g; kd[k] = fmaf(g, x[k], kd[k]); }
+                else d[k] = fmaf(sc[k], g, fmaf(kb[k], x[k], kd[k]));
             }
-            if (MODE == 1) Vec<T>::store(draw + p * C + cv * V, o);
+            if (MODE == 1) Vec<T>::store(draw + p * C + cv * V, d);
         }
     if (MODE == 0) {
         // deterministic cross-row reduction through shared memory: red[which][r][c]
         if (active) {
 #pragma unroll
             for (int k = 0; k < V; ++k) {
-                red[(0 * 256 + r * CV + cv) * V + k] = a0[k];
-                red[(1 * 256 + r * CV + cv) * V + k] = a1[k];
+                red[(0 * 256 + r * CV + cv) * V + k] = kb[k];
+                red[(1 * 256 + r * CV + cv) * V + k] = kd[k];
             }
         }
         __syncthreads();
@@ -313,6 +319,7 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float *__res
     s = warp_sum(s);
     q = warp_sum(q);
     if (lane != 0) return;
+    q = (double)bn.invstd[c] * (q - (double)bn.mean[c] * s);      // partials hold sum(g*raw): xhat = (raw - mean) * invstd
     bn.c1[c] = (float)(s * inv_count);
     bn.c2[c] = (float)(q * inv_count);
     if (accumulate) { dgamma[c] += (float)q; dbeta[c] += (float)s; }
