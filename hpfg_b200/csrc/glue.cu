@@ -347,7 +347,7 @@ int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, D
 
 // ------------------------------------------------------------------------------------------ skip_pool_bwd
 template <typename T>
-__global__ void __launch_bounds__(256) skip_pool_bwd_kernel(const T *__restrict__ dcat, const T *__restrict__ dpooled,
+__global__ void __launch_bounds__(256, 4) skip_pool_bwd_kernel(const T *__restrict__ dcat, const T *__restrict__ dpooled,
                                                             const T *__restrict__ raw, BnState bn, T *__restrict__ dact,
                                                             int N, int H, int W, int F, FastDiv dFV, FastDiv dWo, FastDiv dHo) {
     pdl_prologue();
@@ -426,24 +426,36 @@ __global__ void __launch_bounds__(256) up_bwd_kernel(const T *__restrict__ dcat,
         float acc[V];
 #pragma unroll
         for (int k = 0; k < V; ++k) acc[k] = 0.f;
-        // destination rows whose bilinear footprint can touch source row y: dst in [2y-2, 2y+3]
-        for (int Y = max(0, 2 * y - 2); Y <= min(H - 1, 2 * y + 3); ++Y) {
-            int y0, y1; float ly0, ly1;
-            bilinear_src(Y, sh_, h, y0, y1, ly0, ly1);
-            float wy = 0.f;
-            if (y0 == y) wy += ly0;
-            if (y1 == y) wy += ly1;
-            if (wy == 0.f) continue;
-            for (int X = max(0, 2 * x - 2); X <= min(W - 1, 2 * x + 3); ++X) {
+        // destination rows / columns whose bilinear footprint can touch source row y / column x: dst in [2y-2, 2y+3];
+        // per-axis weights first (12 coordinate evaluations instead of 6 + 36)
+        float wy[6], wx[6];
+#pragma unroll
+        for (int t = 0; t < 6; ++t) {
+            const int Y = 2 * y - 2 + t, X = 2 * x - 2 + t;
+            wy[t] = wx[t] = 0.f;
+            if (Y >= 0 && Y < H) {
+                int y0, y1; float ly0, ly1;
+                bilinear_src(Y, sh_, h, y0, y1, ly0, ly1);
+                if (y0 == y) wy[t] += ly0;
+                if (y1 == y) wy[t] += ly1;
+            }
+            if (X >= 0 && X < W) {
                 int x0, x1; float lx0, lx1;
                 bilinear_src(X, sw_, w, x0, x1, lx0, lx1);
-                float wx = 0.f;
-                if (x0 == x) wx += lx0;
-                if (x1 == x) wx += lx1;
-                if (wx == 0.f) continue;
+                if (x0 == x) wx[t] += lx0;
+                if (x1 == x) wx[t] += lx1;
+            }
+        }
+#pragma unroll
+        for (int ty = 0; ty < 6; ++ty) {
+            if (wy[ty] == 0.f) continue;
+            const T *row = dcat + (((int64_t)n * H + (2 * y - 2 + ty)) * W + (2 * x - 2)) * (2 * F) + F + cv * V;
+#pragma unroll
+            for (int tx = 0; tx < 6; ++tx) {
+                if (wx[tx] == 0.f) continue;
                 float g[V];
-                Vec<T>::load(dcat + (((int64_t)n * H + Y) * W + X) * (2 * F) + F + cv * V, g);
-                const float wgt = wy * wx;
+                Vec<T>::load(row + (int64_t)tx * (2 * F), g);
+                const float wgt = wy[ty] * wx[tx];
 #pragma unroll
                 for (int k = 0; k < V; ++k) acc[k] = fmaf(wgt, g[k], acc[k]);
             }

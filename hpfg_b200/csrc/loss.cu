@@ -112,7 +112,7 @@ __device__ __forceinline__ void load_labels4(const int64_t *p, int (&lab)[4]) {
 
 // ---------------------------------------------------------------------------------------------- phase 1
 template <int C>
-__global__ void __launch_bounds__(256) loss_reduce_kernel(LossArgs A) {
+__global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {   // <= 128 registers: 177 left one CTA per SM (ncu: 12 % warps active)
     pdl_prologue();
     constexpr int NS = 3 * C + 2;
     __shared__ float smem[8 * (2 * NS + 3)];
