@@ -30,6 +30,8 @@ SIGNATURES = {
     "hpfg_unet_plan_workspace_bytes": (c_i64, [c_vp]),
     "hpfg_unet_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u64, c_u64,
                                   ctypes.POINTER(c_vp), c_vp]),
+    "hpfg_unet_forward_dv": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u64, c_vp,
+                                     ctypes.POINTER(c_vp), c_vp]),
     "hpfg_unet_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "hpfg_unet_num_buckets": (c_int, [c_vp]),
     "hpfg_unet_bucket_range": (c_int, [c_vp, c_int, c_i64p, c_i64p]),
@@ -42,11 +44,14 @@ SIGNATURES = {
     "hpfg_ssl_loss_workspace_bytes": (c_i64, [c_int] * 6),
     "hpfg_ssl_loss": (c_int, [c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_f,
                               ctypes.POINTER(c_f), c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hpfg_ssl_loss_dv": (c_int, [c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_f,
+                                 ctypes.POINTER(c_f), c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hpfg_dice_loss": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f), c_vp, c_vp, c_vp,
                                c_vp]),
     "hpfg_ema_update": (c_int, [c_vp, c_vp, c_i64, c_f, c_vp]),
     "hpfg_sgd_momentum": (c_int, [c_vp, c_vp, c_vp, c_i64, c_f, c_f, c_f, c_f, c_int, c_vp]),
     "hpfg_sgd_momentum_ema": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f, c_f, c_f, c_f, c_int, c_f, c_vp]),
+    "hpfg_sgd_momentum_ema_dv": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f, c_f, c_f, c_int, c_vp, c_vp]),
 }
 
 PREC_FP32, PREC_BF16 = 0, 1

@@ -494,10 +494,11 @@ struct DropJobs {
     DropJob j[8];
 };
 
-__global__ void __launch_bounds__(256) dropout_bits_kernel(const DropJobs J, int N, uint64_t seed, uint64_t offset) {
+__global__ void __launch_bounds__(256) dropout_bits_kernel(const DropJobs J, int N, uint64_t seed, uint64_t offset,
+                                                           const uint64_t *offset_dev) {
     pdl_prologue();
     const DropJob &D = J.j[blockIdx.y];
-    const uint64_t off = offset + blockIdx.y;
+    const uint64_t off = (offset_dev ? *offset_dev : offset) + blockIdx.y;   // device scalar: CUDA-graph replays
     for (long long wi = (long long)blockIdx.x * blockDim.x + threadIdx.x; wi < D.n_words; wi += (long long)gridDim.x * blockDim.x) {
         uint32_t word = 0;
         if (D.mask) {
@@ -530,7 +531,7 @@ __global__ void __launch_bounds__(256) dropout_bits_kernel(const DropJobs J, int
 }
 
 int dropout_bits_multi(int n_jobs, uint32_t *const *bits, const uint8_t *const *masks_nchw, int N, const int *H, const int *W,
-                       const int *C, const float *p, uint64_t seed, uint64_t offset, cudaStream_t s) {
+                       const int *C, const float *p, uint64_t seed, uint64_t offset, cudaStream_t s, const uint64_t *offset_dev) {
     ProfScope _prof(PROF_GLUE, s);
     HPFG_REQUIRE(n_jobs >= 1 && n_jobs <= 8, "dropout_bits_multi: 1..8 tensors per launch");
     DropJobs J{};
@@ -546,14 +547,14 @@ int dropout_bits_multi(int n_jobs, uint32_t *const *bits, const uint8_t *const *
         D.n_words = (D.total + 31) / 32;
         max_words = std::max(max_words, D.n_words);
     }
-    HPFG_CUDA_CHECK(launch_pdl(dropout_bits_kernel, dim3((unsigned)ew_grid(max_words), (unsigned)n_jobs), 256, 0, s, J, N, seed, offset));
+    HPFG_CUDA_CHECK(launch_pdl(dropout_bits_kernel, dim3((unsigned)ew_grid(max_words), (unsigned)n_jobs), 256, 0, s, J, N, seed, offset, offset_dev));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
 
 int dropout_bits(uint32_t *bits, const uint8_t *mask_nchw, int N, int H, int W, int C, float p, uint64_t seed,
                  uint64_t offset, cudaStream_t s) {
-    return dropout_bits_multi(1, &bits, mask_nchw ? &mask_nchw : nullptr, N, &H, &W, &C, &p, seed, offset, s);
+    return dropout_bits_multi(1, &bits, mask_nchw ? &mask_nchw : nullptr, N, &H, &W, &C, &p, seed, offset, s, nullptr);
 }
 
 // -------------------------------------------------------------------------------------- nhwc_to_nchw_f32

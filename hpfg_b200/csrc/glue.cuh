@@ -50,7 +50,8 @@ int dropout_bits(uint32_t *bits, const uint8_t *mask_nchw, int N, int H, int W, 
 
 // the same for up to 8 tensors in one launch (tensor i uses Philox offset + i)
 int dropout_bits_multi(int n_jobs, uint32_t *const *bits, const uint8_t *const *masks_nchw, int N, const int *H, const int *W,
-                       const int *C, const float *p, uint64_t seed, uint64_t offset, cudaStream_t s);
+                       const int *C, const float *p, uint64_t seed, uint64_t offset, cudaStream_t s,
+                       const uint64_t *offset_dev = nullptr);   // offset_dev: device scalar overriding offset
 
 // NHWC (T) -> NCHW fp32 copy with optional per-channel bias (debug taps)
 template <typename T>

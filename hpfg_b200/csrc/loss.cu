@@ -25,6 +25,7 @@ struct LossArgs {
     const float *student, *other, *mc;
     const int64_t *labels;
     float cons_weight, uamt_threshold, ce_coef, dice_coef;
+    const float *cons_weight_dev;   // optional device scalar overriding cons_weight (CUDA-graph replays)
     float class_w[kMaxC];
     float *dstudent, *dother, *scalars;
     int64_t *pseudo1, *pseudo2;
@@ -114,6 +115,7 @@ __device__ __forceinline__ void load_labels4(const int64_t *p, int (&lab)[4]) {
 template <int C>
 __global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {   // <= 128 registers: 177 left one CTA per SM (ncu: 12 % warps active)
     pdl_prologue();
+    if (A.cons_weight_dev) A.cons_weight = *A.cons_weight_dev;
     constexpr int NS = 3 * C + 2;
     __shared__ float smem[8 * (2 * NS + 3)];
     __shared__ int slots[2 * NS + 3];
@@ -289,6 +291,7 @@ __device__ __forceinline__ void store4(float *base, int64_t hw, const float (&g)
 template <int C>
 __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
     pdl_prologue();
+    if (A.cons_weight_dev) A.cons_weight = *A.cons_weight_dev;
     __shared__ SupCoef coef[4];   // [net*2 + set]
     __shared__ float s_cons;      // per-element consistency coefficient
     const bool cps = A.mode == HPFG_LOSS_CPS;
@@ -514,11 +517,11 @@ extern "C" int64_t hpfg_ssl_loss_workspace_bytes(int mode, int n_l, int n_u, int
     return kAccTotal * (int64_t)sizeof(double) + ((aux + 255) / 256) * 256;
 }
 
-extern "C" int hpfg_ssl_loss(int mode, const float *student, const float *other, const float *mc_logits,
-                             int mc_passes, const int64_t *labels, int n_l, int n_u, int num_classes, int height,
-                             int width, float cons_weight, float uamt_threshold, const float *class_weights_host,
-                             float ce_coef, float dice_coef, float *dstudent, float *dother, float *scalars_out,
-                             int64_t *pseudo1, int64_t *pseudo2, void *workspace, void *stream) {
+static int ssl_loss_impl(int mode, const float *student, const float *other, const float *mc_logits,
+                         int mc_passes, const int64_t *labels, int n_l, int n_u, int num_classes, int height,
+                         int width, float cons_weight, const float *cons_weight_dev, float uamt_threshold,
+                         const float *class_weights_host, float ce_coef, float dice_coef, float *dstudent, float *dother,
+                         float *scalars_out, int64_t *pseudo1, int64_t *pseudo2, void *workspace, void *stream) {
     HPFG_REQUIRE(mode >= HPFG_LOSS_SUP && mode <= HPFG_LOSS_UAMT, "hpfg_ssl_loss: unknown mode");
     HPFG_REQUIRE(student && dstudent && scalars_out && workspace, "hpfg_ssl_loss: null buffer");
     HPFG_REQUIRE(n_l >= 0 && n_u >= 0 && n_l + n_u > 0, "hpfg_ssl_loss: empty batch");
@@ -532,7 +535,7 @@ extern "C" int hpfg_ssl_loss(int mode, const float *student, const float *other,
     LossArgs A{};
     A.mode = mode; A.n_l = n_l; A.n_u = n_u; A.hw = height * width; A.mc_passes = mc_passes;
     A.student = student; A.other = other; A.mc = mc_logits; A.labels = labels;
-    A.cons_weight = cons_weight; A.uamt_threshold = uamt_threshold; A.ce_coef = ce_coef; A.dice_coef = dice_coef;
+    A.cons_weight = cons_weight; A.cons_weight_dev = cons_weight_dev; A.uamt_threshold = uamt_threshold; A.ce_coef = ce_coef; A.dice_coef = dice_coef;
     for (int c = 0; c < kMaxC; ++c) A.class_w[c] = (class_weights_host && c < num_classes) ? class_weights_host[c] : 1.f;
     A.dstudent = dstudent; A.dother = dother; A.scalars = scalars_out; A.pseudo1 = pseudo1; A.pseudo2 = pseudo2;
     A.acc = reinterpret_cast<double *>(workspace);
@@ -548,6 +551,28 @@ extern "C" int hpfg_ssl_loss(int mode, const float *student, const float *other,
         case 7: return launch_loss<7>(A, st);
         default: return launch_loss<8>(A, st);
     }
+}
+
+extern "C" int hpfg_ssl_loss(int mode, const float *student, const float *other, const float *mc_logits,
+                             int mc_passes, const int64_t *labels, int n_l, int n_u, int num_classes, int height,
+                             int width, float cons_weight, float uamt_threshold, const float *class_weights_host,
+                             float ce_coef, float dice_coef, float *dstudent, float *dother, float *scalars_out,
+                             int64_t *pseudo1, int64_t *pseudo2, void *workspace, void *stream) {
+    return ssl_loss_impl(mode, student, other, mc_logits, mc_passes, labels, n_l, n_u, num_classes, height, width, cons_weight, nullptr,
+                         uamt_threshold, class_weights_host, ce_coef, dice_coef, dstudent, dother, scalars_out, pseudo1, pseudo2,
+                         workspace, stream);
+}
+
+extern "C" int hpfg_ssl_loss_dv(int mode, const float *student, const float *other, const float *mc_logits,
+                                int mc_passes, const int64_t *labels, int n_l, int n_u, int num_classes, int height,
+                                int width, const float *cons_weight_dev, float uamt_threshold,
+                                const float *class_weights_host, float ce_coef, float dice_coef, float *dstudent,
+                                float *dother, float *scalars_out, int64_t *pseudo1, int64_t *pseudo2, void *workspace,
+                                void *stream) {
+    HPFG_REQUIRE(cons_weight_dev, "hpfg_ssl_loss_dv: cons_weight_dev is null");
+    return ssl_loss_impl(mode, student, other, mc_logits, mc_passes, labels, n_l, n_u, num_classes, height, width, 0.f, cons_weight_dev,
+                         uamt_threshold, class_weights_host, ce_coef, dice_coef, dstudent, dother, scalars_out, pseudo1, pseudo2,
+                         workspace, stream);
 }
 
 extern "C" int hpfg_dice_loss(const float *inputs, const int64_t *target, int n, int num_classes, int height,

@@ -39,6 +39,7 @@ __global__ void __launch_bounds__(256) ema_kernel(float *__restrict__ ema, const
 struct SgdArgs {
     float lr, momentum, weight_decay, grad_scale, ema_alpha, ema_one_minus;
     int first_step;
+    const float *dyn;      // optional device block {lr, ema_alpha, 1 - ema_alpha}: overrides the by-value fields (CUDA-graph replays)
 };
 
 template <bool kEma>
@@ -54,6 +55,7 @@ __global__ void __launch_bounds__(256) sgd_kernel(float *__restrict__ param, con
                                                   float *__restrict__ buf, float *__restrict__ ema, int64_t n,
                                                   SgdArgs a) {
     pdl_prologue();
+    if (a.dyn) { a.lr = a.dyn[0]; a.ema_alpha = a.dyn[1]; a.ema_one_minus = a.dyn[2]; }
     const int64_t n4 = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -112,7 +114,7 @@ extern "C" int hpfg_sgd_momentum(float *param, const float *grad, float *momentu
                  "hpfg_sgd_momentum: buffers must be 16-byte aligned");
     if (n == 0) return HPFG_OK;
     ProfScope _prof(PROF_OPTIM, (cudaStream_t)stream);
-    SgdArgs a{lr, momentum, weight_decay, grad_scale, 0.f, 0.f, first_step};
+    SgdArgs a{lr, momentum, weight_decay, grad_scale, 0.f, 0.f, first_step, nullptr};
     HPFG_CUDA_CHECK(launch_pdl(sgd_kernel<false>, flat_grid(n), 256, 0, (cudaStream_t)stream, param, grad, momentum_buf, nullptr, n, a));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
@@ -126,7 +128,21 @@ extern "C" int hpfg_sgd_momentum_ema(float *param, const float *grad, float *mom
                  "hpfg_sgd_momentum_ema: buffers must be 16-byte aligned");
     if (n == 0) return HPFG_OK;
     ProfScope _prof(PROF_OPTIM, (cudaStream_t)stream);
-    SgdArgs a{lr, momentum, weight_decay, grad_scale, ema_alpha, 1.0f - ema_alpha, first_step};
+    SgdArgs a{lr, momentum, weight_decay, grad_scale, ema_alpha, 1.0f - ema_alpha, first_step, nullptr};
+    HPFG_CUDA_CHECK(launch_pdl(sgd_kernel<true>, flat_grid(n), 256, 0, (cudaStream_t)stream, param, grad, momentum_buf, ema, n, a));
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+extern "C" int hpfg_sgd_momentum_ema_dv(float *param, const float *grad, float *momentum_buf, float *ema, int64_t n,
+                                        float momentum, float weight_decay, float grad_scale, int first_step,
+                                        const float *lr_alpha_dev, void *stream) {
+    HPFG_REQUIRE(param && grad && momentum_buf && ema && lr_alpha_dev && n >= 0, "hpfg_sgd_momentum_ema_dv: null buffer");
+    HPFG_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(momentum_buf) && aligned16(ema),
+                 "hpfg_sgd_momentum_ema_dv: buffers must be 16-byte aligned");
+    if (n == 0) return HPFG_OK;
+    ProfScope _prof(PROF_OPTIM, (cudaStream_t)stream);
+    SgdArgs a{0.f, momentum, weight_decay, grad_scale, 0.f, 0.f, first_step, lr_alpha_dev};
     HPFG_CUDA_CHECK(launch_pdl(sgd_kernel<true>, flat_grid(n), 256, 0, (cudaStream_t)stream, param, grad, momentum_buf, ema, n, a));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;

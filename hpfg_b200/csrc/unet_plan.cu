@@ -159,7 +159,7 @@ static void carve(hpfg_unet_plan *p, char *base, int64_t &total) {
 template <typename T>
 static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_running, int64_t *bn_counters, const float *x,
                         float *logits, int training, int no_dropout, int save, uint64_t seed, uint64_t offset,
-                        const uint8_t *const *masks, cudaStream_t s) {
+                        const uint8_t *const *masks, cudaStream_t s, const uint64_t *offset_dev = nullptr) {
     UNetDesc &d = p->d;
     const int N = p->N, H = p->H, W = p->W;
     const bool use_drop = training && !no_dropout;
@@ -174,7 +174,7 @@ static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_runnin
         int hs[5], wsz[5], cs[5];
         float ps[5];
         for (int l = 0; l < 5; ++l) { hs[l] = H >> l; wsz[l] = W >> l; cs[l] = kFt[l]; ps[l] = kEncDropout[l]; }
-        HPFG_RETURN_IF(dropout_bits_multi(5, p->dropbits, masks, N, hs, wsz, cs, ps, seed, offset, s));
+        HPFG_RETURN_IF(dropout_bits_multi(5, p->dropbits, masks, N, hs, wsz, cs, ps, seed, offset, s, offset_dev));
     }
 
     // conv + (train: statistics -> finalize | eval: running-stat affine)
@@ -605,4 +605,17 @@ extern "C" int hpfg_unet_debug_tap(hpfg_unet_plan_t p, const char *name, float *
         if (nm == "pooled" + std::to_string(l)) return copy(p->pooled[l], p->H >> l, p->W >> l, kFt[l - 1], nullptr);
     set_error("hpfg_unet_debug_tap: unknown tap '" + nm + "'");
     return HPFG_ERR_INVALID;
+}
+
+extern "C" int hpfg_unet_forward_dv(hpfg_unet_plan_t p, const float *params, float *bn_running, int64_t *bn_counters,
+                                    const float *x, float *logits, int training, int no_dropout, int save_for_backward,
+                                    uint64_t dropout_seed, const uint64_t *dropout_offset_dev,
+                                    const uint8_t *const *dropout_masks_host, void *stream) {
+    HPFG_REQUIRE(p && params && bn_running && x && logits && dropout_offset_dev, "hpfg_unet_forward_dv: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->precision == HPFG_PREC_FP32)
+        return forward_impl<float>(p, params, bn_running, bn_counters, x, logits, training, no_dropout, save_for_backward,
+                                   dropout_seed, 0, dropout_masks_host, s, dropout_offset_dev);
+    return forward_impl<bf16>(p, params, bn_running, bn_counters, x, logits, training, no_dropout, save_for_backward,
+                              dropout_seed, 0, dropout_masks_host, s, dropout_offset_dev);
 }

@@ -145,6 +145,8 @@ class MeanTeacherStep(_StepBase):
     def step(self, x, labels):
         """x: [n_l+n_u, C, H, W] fp32 CUDA (labeled slices first); labels: [n_l, H, W] int64 CUDA."""
         self.cur_itrs += 1
+        if self._graph_enabled and self.cur_itrs >= 2 and self.world == 1:
+            return self._step_graph(x, labels)
         n_l = labels.shape[0]
         # the teacher forward is independent of the student forward: it runs on a side stream so that each network's
         # small / dependent kernels fill the other's bubbles (the teacher sees the whole batch, 2017_03...:100)
@@ -163,6 +165,76 @@ class MeanTeacherStep(_StepBase):
         lr = self._sgd(self.model, self.grads, self.mom, self.ema_model, alpha)
         self.last = dict(scalars=r["scalars"], lr=lr, w=w, logits=out, teacher_logits=t_out)
         return r["scalars"][0]
+
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    _graph_enabled = False
+
+    def enable_graph(self, enabled=True):
+        """From the second iteration on, replay the step as ONE captured CUDA graph (both forwards on two streams, the
+        fused loss, backward with its side-stream weight gradients, fused SGD+EMA).  The scalars that change per
+        iteration -- learning rate, EMA alpha, consistency weight, dropout Philox offsets -- live in a small device
+        block that is refreshed before every replay (the `_dv` entry points read them at run time).  Single-process
+        only: with data parallelism the step stays eager."""
+        self._graph_enabled = bool(enabled)
+        if not enabled:
+            self._graph = None
+
+    def _step_graph(self, x, labels):
+        dev = x.device
+        if getattr(self, "_graph", None) is None or tuple(self._gx.shape) != tuple(x.shape) or tuple(self._gy.shape) != tuple(labels.shape):
+            self._gx, self._gy = torch.empty_like(x), torch.empty_like(labels)
+            self._dyn_f = torch.zeros(4, device=dev, dtype=torch.float32)        # lr, alpha, 1 - alpha, consistency weight
+            self._dyn_o = torch.zeros(2, device=dev, dtype=torch.int64)          # Philox offsets: student, teacher
+            self._dyn_f_host = torch.zeros(4, dtype=torch.float32).pin_memory()
+            self._dyn_o_host = torch.zeros(2, dtype=torch.int64).pin_memory()
+            self._graph = None
+        lr = medical_lr(self.cur_itrs, self.base_lr, self.total_itrs)
+        alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)
+        w = self._consistency_weight()
+        a32 = torch.tensor(alpha, dtype=torch.float32)
+        self._dyn_f_host[0], self._dyn_f_host[1], self._dyn_f_host[3] = lr, alpha, w
+        self._dyn_f_host[2] = 1.0 - a32                                          # fp32 subtraction, as the by-value entry point
+        self._dyn_o_host[0], self._dyn_o_host[1] = self.model._philox_offset, self.ema_model._philox_offset
+        self.model._philox_offset += 8
+        self.ema_model._philox_offset += 8
+        self._dyn_f.copy_(self._dyn_f_host, non_blocking=True)
+        self._dyn_o.copy_(self._dyn_o_host, non_blocking=True)
+        self._gx.copy_(x, non_blocking=True)
+        self._gy.copy_(labels, non_blocking=True)
+        if self._graph is None:
+            self.model.ensure_flat()
+            self.ema_model.ensure_flat()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self._graph_out = self._step_body_dv(self._gx, self._gy)
+            self._graph = g
+        self._graph.replay()
+        self.last = dict(scalars=self._graph_out["scalars"], lr=lr, w=w, logits=self._graph_out["logits"],
+                         teacher_logits=self._graph_out["teacher_logits"])
+        return self._graph_out["scalars"][0]
+
+    def _step_body_dv(self, x, labels):
+        """The step with every per-iteration scalar read from the device block (captured once, replayed)."""
+        n_l = labels.shape[0]
+        dev = x.device
+        main, side = torch.cuda.current_stream(dev), self._side_stream(dev)
+        shape = (x.shape[0], self.num_classes, x.shape[2], x.shape[3])
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            tplan = self.ema_model._acquire_plan(x, need_grad=False)
+            t_out = self.ema_model._run_forward(tplan, x, save=False, out=self._persistent("t_out", shape, dev),
+                                                offset_dev=self._dyn_o[1:2])
+        plan = self.model._acquire_plan(x, need_grad=True)
+        out = self.model._run_forward(plan, x, save=True, out=self._persistent("s_out", shape, dev), offset_dev=self._dyn_o[0:1])
+        main.wait_stream(side)
+        r = ssl_loss_raw(L.LOSS_MT, out, t_out[n_l:], labels, n_l, cons_weight_dev=self._dyn_f[3:4])
+        self._backward(self.model, plan, r["dstudent"], self.grads)
+        n = self.model.flat_params.numel()
+        L.check(L.lib().hpfg_sgd_momentum_ema_dv(L.ptr(self.model.flat_params), L.ptr(self.grads), L.ptr(self.mom),
+                                                 L.ptr(self.ema_model.flat_params), n, self.momentum, self.weight_decay,
+                                                 1.0 / self.world, 0, L.ptr(self._dyn_f), L.stream_ptr(dev)),
+                "hpfg_sgd_momentum_ema_dv")
+        return dict(scalars=r["scalars"], logits=out, teacher_logits=t_out)
 
 
 class CPSStep(_StepBase):

@@ -217,7 +217,7 @@ class UNet(nn.Module):
         pool.append(pl)
         return pl
 
-    def _run_forward(self, plan, x, save, out=None):
+    def _run_forward(self, plan, x, save, out=None, offset_dev=None):
         dev = x.device
         shape = (x.shape[0], self.num_classes, x.shape[2], x.shape[3])
         logits = out if out is not None else torch.empty(shape, device=dev, dtype=torch.float32)
@@ -227,8 +227,14 @@ class UNet(nn.Module):
             masks = (ctypes.c_void_p * L.NUM_DROPOUT)(*[m.data_ptr() for m in self._dropout_masks])
         seed = torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].initial_seed()
         offset = self._philox_offset
-        if self.training:
+        if self.training and offset_dev is None:      # (graph replays advance the offset themselves, once per replay)
             self._philox_offset += 8
+        if offset_dev is not None:       # CUDA-graph replays: the Philox offset is read from device memory at run time
+            L.check(L.lib().hpfg_unet_forward_dv(plan.handle, L.ptr(self.flat_params), L.ptr(self.bn_running),
+                                                 L.ptr(self.bn_counters), L.ptr(x), L.ptr(logits), int(self.training),
+                                                 int(self._no_dropout), int(save), seed & (2 ** 64 - 1), L.ptr(offset_dev),
+                                                 masks, L.stream_ptr(dev)), "hpfg_unet_forward_dv")
+            return logits
         L.check(L.lib().hpfg_unet_forward(plan.handle, L.ptr(self.flat_params), L.ptr(self.bn_running),
                                           L.ptr(self.bn_counters), L.ptr(x), L.ptr(logits), int(self.training),
                                           int(self._no_dropout), int(save), seed & (2 ** 64 - 1), offset, masks,

@@ -86,6 +86,16 @@ int hpfg_unet_forward(hpfg_unet_plan_t plan, const float *params, float *bn_runn
                       uint64_t dropout_seed, uint64_t dropout_offset, const uint8_t *const *dropout_masks_host,
                       void *stream);
 
+/* CUDA-graph friendly variants ("_dv": device values).  Scalars that change every iteration are read from device memory
+ * at execution time instead of being baked into the launch, so a captured step can be replayed after updating a small
+ * device block: the Philox offset of the dropout masks (hpfg_unet_forward_dv), the consistency weight
+ * (hpfg_ssl_loss_dv: utils/utils.py:67-79 ramp-up), and {lr, ema_alpha, 1-ema_alpha} (hpfg_sgd_momentum_ema_dv:
+ * utils/scheduler/medical_lr.py:13-17, utils/utils.py:84). */
+int hpfg_unet_forward_dv(hpfg_unet_plan_t plan, const float *params, float *bn_running, int64_t *bn_counters,
+                         const float *x, float *logits, int training, int no_dropout, int save_for_backward,
+                         uint64_t dropout_seed, const uint64_t *dropout_offset_dev,
+                         const uint8_t *const *dropout_masks_host, void *stream);
+
 /* Backward of the last save_for_backward forward on this plan.  dlogits: fp32 NCHW.  grads: flat fp32
  * buffer with the parameter layout; overwritten (accumulate == 0) or added to (accumulate != 0). */
 int hpfg_unet_backward(hpfg_unet_plan_t plan, const float *params, const float *dlogits, float *grads,
@@ -141,6 +151,12 @@ int hpfg_ssl_loss(int mode, const float *student, const float *other, const floa
                   float dice_coef, float *dstudent, float *dother, float *scalars_out, int64_t *pseudo1,
                   int64_t *pseudo2, void *workspace, void *stream);
 
+int hpfg_ssl_loss_dv(int mode, const float *student, const float *other, const float *mc_logits, int mc_passes,
+                     const int64_t *labels, int n_l, int n_u, int num_classes, int height, int width,
+                     const float *cons_weight_dev, float uamt_threshold, const float *class_weights, float ce_coef,
+                     float dice_coef, float *dstudent, float *dother, float *scalars_out, int64_t *pseudo1,
+                     int64_t *pseudo2, void *workspace, void *stream);
+
 /* DiceLoss.forward (utils/loss/diceloss.py:178-191) alone: inputs are probabilities (softmax == 0) or
  * logits (softmax != 0); target int64 [n,H,W]; dinputs optional. scalars_out: float[1+C] = {loss, dice_c..}. */
 int hpfg_dice_loss(const float *inputs, const int64_t *target, int n, int num_classes, int height, int width,
@@ -158,6 +174,11 @@ int hpfg_sgd_momentum(float *param, const float *grad, float *momentum_buf, int6
 int hpfg_sgd_momentum_ema(float *param, const float *grad, float *momentum_buf, float *ema, int64_t n, float lr,
                           float momentum, float weight_decay, float grad_scale, int first_step, float ema_alpha,
                           void *stream);
+
+/* lr_alpha_dev: device float[3] = {lr, ema_alpha, 1 - ema_alpha}. */
+int hpfg_sgd_momentum_ema_dv(float *param, const float *grad, float *momentum_buf, float *ema, int64_t n,
+                             float momentum, float weight_decay, float grad_scale, int first_step,
+                             const float *lr_alpha_dev, void *stream);
 
 #ifdef __cplusplus
 }
