@@ -168,6 +168,8 @@ class MeanTeacherStep(_StepBase):
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
     _graph_enabled = False
+    kernels_per_replay = 0
+    replayed_kernels = 0          # kernels executed through graph replays (the library's own counter sees host launches only)
 
     def enable_graph(self, enabled=True):
         """From the second iteration on, replay the step as ONE captured CUDA graph (both forwards on two streams, the
@@ -205,10 +207,13 @@ class MeanTeacherStep(_StepBase):
             self.model.ensure_flat()
             self.ema_model.ensure_flat()
             g = torch.cuda.CUDAGraph()
+            n0 = L.lib().hpfg_launch_count()
             with torch.cuda.graph(g):
                 self._graph_out = self._step_body_dv(self._gx, self._gy)
             self._graph = g
+            self.kernels_per_replay = int(L.lib().hpfg_launch_count() - n0)   # kernel nodes of the captured step
         self._graph.replay()
+        self.replayed_kernels += self.kernels_per_replay
         self.last = dict(scalars=self._graph_out["scalars"], lr=lr, w=w, logits=self._graph_out["logits"],
                          teacher_logits=self._graph_out["teacher_logits"])
         return self._graph_out["scalars"][0]
