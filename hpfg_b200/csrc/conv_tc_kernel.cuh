@@ -294,6 +294,18 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                         scl[0] = a0.x; scl[1] = a0.y; scl[2] = a0.z; scl[3] = a0.w; scl[4] = a1.x; scl[5] = a1.y; scl[6] = a1.z; scl[7] = a1.w;
                         shf[0] = b0.x; shf[1] = b0.y; shf[2] = b0.z; shf[3] = b0.w; shf[4] = b1.x; shf[5] = b1.y; shf[6] = b1.z; shf[7] = b1.w;
                     }
+                    // dropout keep bytes come from global memory: fetch them all BEFORE waiting for the stage, so their latency
+                    // hides behind the TMA wait instead of sitting inside the per-item dependency chain
+                    uint32_t keepv[XF == 2 ? ITERS : 1];
+                    if (XF == 2) {
+#pragma unroll
+                        for (int k = 0; k < ITERS; ++k) {
+                            const int gh = h0 + (hrc[k] >> 8), gw = w0 + (hrc[k] & 255);
+                            const bool ok = ((k + 1) * STEP <= C::NPIX || p0 + k * STEP < C::NPIX) &&
+                                            (unsigned)gh < (unsigned)P.H && (unsigned)gw < (unsigned)P.W;
+                            keepv[k] = ok ? P.dropbits[((img_row0 + gh) * P.W + gw) * (size_t)(P.Cin >> 3) + (ch >> 3)] : 0xffu;
+                        }
+                    }
                     ptx::mbar_wait(bar_full + 8 * stage, phase, 5);
                     const uint32_t base = stage_u32 + stage * C::STAGE_BYTES + c * C::CH_STRIDE + p0 * 16;
 #pragma unroll
@@ -302,8 +314,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                             const uint32_t addr = base + k * STEP * 16;
                             const int gh = h0 + (hrc[k] >> 8), gw = w0 + (hrc[k] & 255);
                             const bool inside = !border || ((unsigned)gh < (unsigned)P.H && (unsigned)gw < (unsigned)P.W);
-                            uint32_t keep = 0xffu;
-                            if (XF == 2 && inside) keep = P.dropbits[((img_row0 + gh) * P.W + gw) * (size_t)(P.Cin >> 3) + (ch >> 3)];
+                            const uint32_t keep = XF == 2 ? keepv[k] : 0xffu;
                             float f[8];
                             unpack8(ptx::lds128(addr), f);
 #pragma unroll
