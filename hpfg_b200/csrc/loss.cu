@@ -112,8 +112,10 @@ __device__ __forceinline__ void load_labels4(const int64_t *p, int (&lab)[4]) {
 }
 
 // ---------------------------------------------------------------------------------------------- phase 1
-template <int C>
-__global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {   // <= 128 registers: 177 left one CTA per SM (ncu: 12 % warps active)
+// MODE is a template parameter: the generic kernel carried four accumulator sets (177 registers, one CTA per SM, 12 %
+// warps active in ncu); Mean-Teacher needs one.
+template <int C, int MODE>
+__global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {
     pdl_prologue();
     if (A.cons_weight_dev) A.cons_weight = *A.cons_weight_dev;
     constexpr int NS = 3 * C + 2;
@@ -122,11 +124,14 @@ __global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {   // 
     const int64_t hw = A.hw, q_per_img = hw >> 2;
     const int64_t n_img = A.n_l + A.n_u;
     const int64_t total_q = n_img * q_per_img;
-    float sl[2][NS];   // labeled sums, net 0 / net 1
-    float su[2][NS];   // CPS: unlabeled sums wrt the peer's pseudo labels
+    constexpr int NSETS = MODE == HPFG_LOSS_CPS ? 2 : 1;
+    float sl[NSETS][NS];   // labeled sums, net 0 / net 1 (CPS)
+    float su[NSETS][NS];   // CPS: unlabeled sums wrt the peer's pseudo labels
     float misc[3] = {0.f, 0.f, 0.f};   // mse, mask_sum, masked_dist
 #pragma unroll
-    for (int i = 0; i < NS; ++i) sl[0][i] = sl[1][i] = su[0][i] = su[1][i] = 0.f;
+    for (int i = 0; i < NS; ++i)
+#pragma unroll
+        for (int e = 0; e < NSETS; ++e) sl[e][i] = su[e][i] = 0.f;
 
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_q;
          q += (int64_t)gridDim.x * blockDim.x) {
@@ -138,30 +143,30 @@ __global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {   // 
             int lab[4];
             load_labels4(A.labels + img * hw + pix, lab);
             acc_sup<C>(z, p, lse, lab, sl[0]);
-            if (A.mode == HPFG_LOSS_CPS) {
+            if (MODE == HPFG_LOSS_CPS) {
                 float z2[C][4], p2[C][4], lse2[4];
                 load4<C>(A.other + (img * C) * hw + pix, hw, z2);
                 softmax4<C>(z2, p2, lse2);
-                acc_sup<C>(z2, p2, lse2, lab, sl[1]);
+                acc_sup<C>(z2, p2, lse2, lab, sl[NSETS - 1]);
             }
-        } else if (A.mode != HPFG_LOSS_SUP) {
+        } else if (MODE != HPFG_LOSS_SUP) {
             const int64_t u = img - A.n_l;
             float z2[C][4], p2[C][4], lse2[4];
-            const float *ob = (A.mode == HPFG_LOSS_CPS) ? A.other + (img * C) * hw + pix
+            const float *ob = (MODE == HPFG_LOSS_CPS) ? A.other + (img * C) * hw + pix
                                                         : A.other + (u * C) * hw + pix;
             load4<C>(ob, hw, z2);
             softmax4<C>(z2, p2, lse2);
-            if (A.mode == HPFG_LOSS_MT) {
+            if (MODE == HPFG_LOSS_MT) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int c = 0; c < C; ++c) { const float d = p[c][j] - p2[c][j]; misc[0] += d * d; }
-            } else if (A.mode == HPFG_LOSS_CPS) {
+            } else if (MODE == HPFG_LOSS_CPS) {
                 int pl1[4], pl2[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { pl1[j] = argmax_first<C>(p, j); pl2[j] = argmax_first<C>(p2, j); }
                 acc_sup<C>(z, p, lse, pl2, su[0]);      // net 1 learns from net 2's labels
-                acc_sup<C>(z2, p2, lse2, pl1, su[1]);   // and vice versa
+                acc_sup<C>(z2, p2, lse2, pl1, su[NSETS - 1]);   // and vice versa
                 const int64_t o = u * hw + pix;
                 *reinterpret_cast<uchar4 *>(A.aux + o) = make_uchar4(pl1[0], pl1[1], pl1[2], pl1[3]);
                 *reinterpret_cast<uchar4 *>(A.aux + (int64_t)A.n_u * hw + o) = make_uchar4(pl2[0], pl2[1], pl2[2], pl2[3]);
@@ -211,12 +216,12 @@ __global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {   // 
     if (threadIdx.x < NS) slots[threadIdx.x] = slot_of(0, threadIdx.x);
     __syncthreads();
     flush<NS>(sl[0], A.acc + 0 * kAccPerSet, slots, smem);
-    if (A.mode == HPFG_LOSS_CPS) {
-        flush<NS>(sl[1], A.acc + 2 * kAccPerSet, slots, smem);
+    if (MODE == HPFG_LOSS_CPS) {
+        flush<NS>(sl[NSETS - 1], A.acc + 2 * kAccPerSet, slots, smem);
         flush<NS>(su[0], A.acc + 1 * kAccPerSet, slots, smem);
-        flush<NS>(su[1], A.acc + 3 * kAccPerSet, slots, smem);
+        flush<NS>(su[NSETS - 1], A.acc + 3 * kAccPerSet, slots, smem);
     }
-    if (A.mode == HPFG_LOSS_MT || A.mode == HPFG_LOSS_UAMT) {
+    if (MODE == HPFG_LOSS_MT || MODE == HPFG_LOSS_UAMT) {
         if (threadIdx.x < 3) slots[threadIdx.x] = threadIdx.x;
         __syncthreads();
         flush<3>(misc, A.acc + kAccMse, slots, smem);
@@ -487,7 +492,12 @@ static int loss_grid(int64_t quads) {
 template <int C>
 static int launch_loss(const LossArgs &A, cudaStream_t st) {
     const int grid = loss_grid((int64_t)(A.n_l + A.n_u) * (A.hw >> 2));
-    HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C>, grid, 256, 0, st, A));
+    switch (A.mode) {
+        case HPFG_LOSS_SUP: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_SUP>, grid, 256, 0, st, A)); break;
+        case HPFG_LOSS_MT: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_MT>, grid, 256, 0, st, A)); break;
+        case HPFG_LOSS_CPS: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_CPS>, grid, 256, 0, st, A)); break;
+        default: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_UAMT>, grid, 256, 0, st, A)); break;
+    }
     HPFG_LAUNCH_CHECK();
     HPFG_CUDA_CHECK(launch_pdl(loss_grad_kernel<C>, grid, 256, 0, st, A));
     HPFG_LAUNCH_CHECK();
