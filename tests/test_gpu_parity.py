@@ -312,3 +312,30 @@ def test_cps_and_uamt_steps_vs_oracle(precision):
         if f32:
             assert rel_l2(ustep.last["mc_logits"], r["mc_logits"]) < 1e-5
             assert ustep.last["scalars"][6].item() == r["mask"].sum().item()
+
+
+def test_full_size_bf16_vs_fp32_plan():
+    """BASELINE-size property check (224x224, wide-tile tensor-core kernels in the full network): the bf16 tensor-core plan
+    against the fp32 CUDA-core check path of this library (itself pinned to the oracle above), same weights / masks /
+    batch: loss within 1e-3, logits and flat gradient within the compounded-bf16 bound of SURVEY 7.2(5)."""
+    in_ch, n_cls, n_l, n_u, h, w = 1, 4, 2, 6, 224, 224
+    st = make_state(in_ch, n_cls, 91)
+    x_l, x_u, y = make_batch(n_l, n_u, in_ch, n_cls, h, w, 92)
+    x = torch.cat([x_l, x_u]).to(DEV)
+    res = {}
+    for prec in ("fp32", "bf16"):
+        m = _model(st, in_ch, n_cls, prec)
+        m.set_dropout_enabled(False)
+        m.train()
+        logits = m(x)
+        loss = hb.Med_Sup_Loss(n_cls)(logits[:n_l], y.to(DEV))
+        loss.backward()
+        res[prec] = (logits.detach().float().cpu(), loss.item(), m.last_flat_grad.detach().float().cpu())
+        del m
+        torch.cuda.empty_cache()
+    lf, ll, gf = res["fp32"]
+    lb, lbl, gb = res["bf16"]
+    assert abs(ll - lbl) / abs(ll) < 1e-3
+    assert rel_l2(lb, lf) < 5e-2
+    assert rel_l2(gb, gf) < 0.5
+    assert (lb.argmax(1) == lf.argmax(1)).float().mean().item() > 0.97
