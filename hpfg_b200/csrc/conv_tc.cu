@@ -40,9 +40,10 @@ struct PackTable {
 };
 
 // blockIdx.y = table entry (one layer, fprop or dgrad order); one thread packs 8 consecutive k (one 16-byte store)
-__global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ params, bf16 *__restrict__ dst, const PackTable T) {
+__global__ void __launch_bounds__(256) tc_pack_kernel(const float *__restrict__ params, bf16 *__restrict__ dst, const PackTable T, int skip_dgrad) {
     pdl_prologue();
     const PackEntry &E = T.e[blockIdx.y];
+    if (skip_dgrad && E.dgrad) return;        // forward-only plans (the teacher) never read the transposed weights
     const unsigned cin_v = E.dgrad ? E.cout : E.cin, cout_v = E.dgrad ? E.cin : E.cout;
     const unsigned groups = cin_v * cout_v * E.kk / 8;          // 8-element groups of this entry
     const unsigned k8s = E.KC / 8, k_chunks = cin_v / E.KC;
@@ -220,10 +221,10 @@ void tc_plan_free(hpfg_unet_plan *p) {
     p->tc = nullptr;
 }
 
-int tc_pack_all(hpfg_unet_plan *p, const float *params, cudaStream_t s) {
+int tc_pack_all(hpfg_unet_plan *p, const float *params, cudaStream_t s, bool need_dgrad) {
     ProfScope _prof(PROF_PACK, s);
     auto *st = reinterpret_cast<TcPlanState *>(p->tc);
-    HPFG_CUDA_CHECK(launch_pdl(tc_pack_kernel, pack_grid(st->table), 256, 0, s, params, st->packed, st->table));
+    HPFG_CUDA_CHECK(launch_pdl(tc_pack_kernel, pack_grid(st->table), 256, 0, s, params, st->packed, st->table, need_dgrad ? 0 : 1));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -310,7 +311,7 @@ extern "C" int hpfg_conv_tc_debug(int op, int N, int H, int W, int cin, int cout
     const int m_tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW - 1) / kTW);
     HPFG_CUDA_CHECK(cudaMalloc(&packed, (size_t)T.total * 2));
     HPFG_CUDA_CHECK(cudaMalloc(&partials, (size_t)m_tiles * 2 * cout_v * 4));
-    HPFG_CUDA_CHECK(launch_pdl(tc_pack_kernel, pack_grid(T), 256, 0, s, w_oihw, packed, T));
+    HPFG_CUDA_CHECK(launch_pdl(tc_pack_kernel, pack_grid(T), 256, 0, s, w_oihw, packed, T, 0));
     HPFG_LAUNCH_CHECK();
     LoadXform xf{};
     xf.scale = scale; xf.shift = shift; xf.drop.bits = nullptr; xf.drop.inv_keep = 1.f;

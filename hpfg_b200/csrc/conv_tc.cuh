@@ -9,7 +9,7 @@ namespace hpfg {
 int tc_plan_init(hpfg_unet_plan *p);
 void tc_plan_free(hpfg_unet_plan *p);
 // bf16 weight packing for all tensor-core layers (one pass per optimiser step)
-int tc_pack_all(hpfg_unet_plan *p, const float *params, cudaStream_t s);
+int tc_pack_all(hpfg_unet_plan *p, const float *params, cudaStream_t s, bool need_dgrad = true);
 // 3x3 fprop: in (bf16 NHWC, transformed on load by xf) -> out (bf16 NHWC, bias-free); stats partials [*P][2*Cout]
 int tc_fprop(hpfg_unet_plan *p, int conv, const void *in, void *out, LoadXform xf, float *stats, int *P, bool *done,
              cudaStream_t s);

@@ -169,7 +169,7 @@ static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_runnin
     if (!tc)
         for (auto &cv : d.convs)
             HPFG_RETURN_IF(pack_weights_ref(params + cv.w_off, cv.wf, cv.wd, cv.cin, cv.cout, cv.ks, s));
-    if (tc) HPFG_RETURN_IF(tc_pack_all(p, params, s));
+    if (tc) HPFG_RETURN_IF(tc_pack_all(p, params, s, save != 0 && training != 0));
     if (use_drop) {      // all five encoder keep-masks in one launch
         int hs[5], wsz[5], cs[5];
         float ps[5];
