@@ -145,7 +145,7 @@ class MeanTeacherStep(_StepBase):
     def step(self, x, labels):
         """x: [n_l+n_u, C, H, W] fp32 CUDA (labeled slices first); labels: [n_l, H, W] int64 CUDA."""
         self.cur_itrs += 1
-        if self._graph_enabled and self.cur_itrs >= 2 and self.world == 1:
+        if self._graph_enabled and self.cur_itrs >= 2 and (self.world == 1 or self._graph_dp):
             return self._step_graph(x, labels)
         n_l = labels.shape[0]
         # the teacher forward is independent of the student forward: it runs on a side stream so that each network's
@@ -171,13 +171,17 @@ class MeanTeacherStep(_StepBase):
     kernels_per_replay = 0
     replayed_kernels = 0          # kernels executed through graph replays (the library's own counter sees host launches only)
 
-    def enable_graph(self, enabled=True):
+    _graph_dp = False
+
+    def enable_graph(self, enabled=True, data_parallel=False):
         """From the second iteration on, replay the step as ONE captured CUDA graph (both forwards on two streams, the
         fused loss, backward with its side-stream weight gradients, fused SGD+EMA).  The scalars that change per
         iteration -- learning rate, EMA alpha, consistency weight, dropout Philox offsets -- live in a small device
-        block that is refreshed before every replay (the `_dv` entry points read them at run time).  Single-process
-        only: with data parallelism the step stays eager."""
+        block that is refreshed before every replay (the `_dv` entry points read them at run time).
+        data_parallel=True also captures the bucketed NCCL all-reduces of a multi-process run (measured on 2/4/8 B200);
+        by default a data-parallel step stays eager."""
         self._graph_enabled = bool(enabled)
+        self._graph_dp = bool(data_parallel)      # also capture the NCCL bucket all-reduces (torch >= 2.x captures NCCL work)
         if not enabled:
             self._graph = None
 
