@@ -43,21 +43,24 @@ struct WgCfg {
     static constexpr int X3_OP = KS * (NB / 8) * XC;                          // A operand: [shift s][chunk][halo row][TWP cols][8 ch]
     static constexpr int D_CHS = TPIX * 16, D_OP = (COB / 8) * D_CHS;         // dY tile, TMA target and B operand: [chunk][pixel][8 ch]
     static constexpr int al(int v) { return (v + 127) / 128 * 128; }
-    static constexpr int OFF_DOP = 0, OFF_XR = al(D_OP), OFF_X3 = OFF_XR + al(XR_OP);
-    static constexpr int STAGE_BYTES = OFF_X3 + al(X3_OP);
+    // + one more 8-row group after the copies holding the constant (1,0,...,0) per pixel: its first accumulator row is
+    // sum_pixels dY = the bias gradient, computed by the tensor core instead of an extra shared-memory pass over dY
+    static constexpr int OFF_DOP = 0, OFF_XR = al(D_OP), OFF_X3 = OFF_XR + al(XR_OP), OFF_ONE = OFF_X3 + X3_OP;
+    static constexpr int STAGE_BYTES = al(OFF_ONE + XC);
     static constexpr int MROWS = KS * NB;                                     // useful accumulator rows
-    static constexpr int UM = MROWS <= 64 ? 64 : 128;                         // UMMA M
+    static constexpr int UM = MROWS + 8 <= 64 ? 64 : 128;                     // UMMA M (useful rows + the ones group)
     // the A descriptor spans UM/8 row groups; the groups past MROWS read whatever follows the copies in shared memory
     // (their D rows are never stored) -- keep those reads inside the allocation
-    static constexpr int TAIL_PAD = al((UM / 8 - MROWS / 8) * XC);
-    static constexpr int FIXED_BYTES = 1024 + 2 * 256 * 4 + kWgXfThreads * 8 * 4 /*dbias reduce*/;
+    static constexpr int TAIL_PAD = al((UM / 8 - MROWS / 8 - 1) * XC);
+    static constexpr int FIXED_BYTES = 1024 + 2 * 256 * 4;
     static constexpr int STAGES_RAW = (kWgSmemBudget - FIXED_BYTES - TAIL_PAD) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_PAD + FIXED_BYTES + 1024;
     static constexpr int ACC = KS * COB;                                      // accumulator columns: D_r at column r*COB
     static constexpr int TMEM_COLS = (ACC <= 32) ? 32 : (ACC <= 64) ? 64 : (ACC <= 128) ? 128 : (ACC <= 256) ? 256 : 512;
     static_assert(STAGES >= 2, "need at least a double buffer");
-    static_assert(ACC <= 512 && MROWS <= 128, "accumulators exceed TMEM");
+    static_assert(ACC <= 512 && MROWS + 8 <= 128, "accumulators exceed TMEM");
+    static_assert(X3_OP % 128 == 0, "the ones group must start at the copies' group pitch");
 };
 
 struct WgParams {
@@ -80,7 +83,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fixed + 512);
     float *s_scale = reinterpret_cast<float *>(fixed + 1024);
     float *s_shift = s_scale + 256;
-    float *s_bias = s_shift + 256;                                 // [transform threads][8]
 
     // broadcast from lane 0: the warp index is warp-uniform for the compiler (role code stays in the uniform datapath)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -108,6 +110,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         ptx::prefetch_tensormap(&tmD);
     }
     if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
+    for (int i = threadIdx.x; i < C::STAGES * (C::XC / 16); i += blockDim.x)      // the constant ones group of every stage
+        ptx::sts128(smem_u32 + (i / (C::XC / 16)) * C::STAGE_BYTES + C::OFF_ONE + (i % (C::XC / 16)) * 16, make_uint4(0x3f80u, 0u, 0u, 0u));
+    ptx::fence_proxy_async_smem();
     pdl_wait();
     if (P.scale)
         for (int i = threadIdx.x; i < P.Cin; i += blockDim.x) { s_scale[i] = P.scale[i]; s_shift[i] = P.shift[i]; }
@@ -176,7 +181,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         float scl[8], shf[8];
 #pragma unroll
         for (int k = 0; k < 8; ++k) { scl[k] = xform ? s_scale[xch + k] : 1.f; shf[k] = xform ? s_shift[xch + k] : 0.f; }
-        float bsum[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};   // bias-gradient partial sums of this thread's chunk
         TileIter ti;
         ti.init(split, P.S, P.tiles_h, P.tiles_w);
         int stage = 0, phase = 0;
@@ -186,17 +190,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
             const size_t img_px = (size_t)ti.n_img * P.H;
             ptx::mbar_wait(bar_full + 8 * stage, phase, 15);
             const uint32_t sb = smem_u32 + stage * C::STAGE_BYTES;
-            if (want_bias) {
-                // thread t owns chunk t / TPC and pixels (t % TPC), +TPC, ...: consecutive lanes read consecutive 16-byte units
-                constexpr int TPC = kWgXfThreads / (COB / 8);
-                const int bc = t / TPC;
-                for (int px = t % TPC; px < C::TPIX; px += TPC) {
-                    float f[8];
-                    unpack8(ptx::lds128(sb + C::OFF_DOP + (bc * C::TPIX + px) * 16), f);
-#pragma unroll
-                    for (int k = 0; k < 8; ++k) bsum[k] += f[k];
-                }
-            }
             for (int p = xp0; p < C::NPIX_X; p += XPSTEP) {
                 const int hr = p / C::HW, hc = p % C::HW;
                 uint4 v = ptx::lds128(sb + C::OFF_XR + (xc * C::NPIX_X + p) * 16);
@@ -231,19 +224,6 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             ti.next(P.tiles_h, P.tiles_w);
         }
-        if (want_bias) {     // fixed-order reduce of the per-thread partial sums of each channel
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s_bias[t * 8 + k] = bsum[k];
-            ptx::named_bar_sync(2, kWgXfThreads);
-            if (t < COB) {
-                constexpr int TPC = kWgXfThreads / (COB / 8);
-                const int c = t / 8, k = t % 8;
-                float s = 0.f;
-                for (int u = c * TPC; u < (c + 1) * TPC; ++u) s += s_bias[u * 8 + k];
-                if (co0 + t < P.Cout)
-                    P.scratch[(size_t)split * ((size_t)C::KK * P.Cin * P.Cout + P.Cout) + (size_t)C::KK * P.Cin * P.Cout + co0 + t] = s;
-            }
-        }
     } else if (warp >= 4 + kWgXfThreads / 32) {
         // ================================================================================ epilogue (once)
         // accumulator row m -> TMEM lane: M=128: lane = m; M=64: lane = (m/16)*32 + m%16 (measured, tests/probes)
@@ -254,6 +234,20 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
             ptx::mbar_wait(bar_done, 0, 16);
             ptx::tc_fence_after();
             float *dst = P.scratch + (size_t)split * ((size_t)C::KK * P.Cin * P.Cout + P.Cout);
+            if (want_bias) {       // accumulator row MROWS of D_0 = ones x dY = sum of dY over this CTA's pixels
+                const bool mine = C::UM == 128 ? (q * 32 + lane == C::MROWS) : (lane < 16 && q * 16 + lane == C::MROWS);
+#pragma unroll 1
+                for (int n0 = 0; n0 < COB; n0 += 16) {
+                    uint32_t v[16];
+                    ptx::tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + n0, v);
+                    ptx::tmem_ld_wait();
+                    if (mine) {
+#pragma unroll
+                        for (int jj = 0; jj < 16; ++jj)
+                            if (co0 + n0 + jj < P.Cout) dst[(size_t)C::KK * P.Cin * P.Cout + co0 + n0 + jj] = __uint_as_float(v[jj]);
+                    }
+                }
+            }
 #pragma unroll 1
             for (int r = 0; r < KS; ++r) {
 #pragma unroll 1
