@@ -212,8 +212,17 @@ class MeanTeacherStep(_StepBase):
             self.ema_model.ensure_flat()
             g = torch.cuda.CUDAGraph()
             n0 = L.lib().hpfg_launch_count()
-            with torch.cuda.graph(g):
-                self._graph_out = self._step_body_dv(self._gx, self._gy)
+            try:
+                with torch.cuda.graph(g):
+                    self._graph_out = self._step_body_dv(self._gx, self._gy)
+            except Exception as exc:        # capture not possible here (e.g. a collective that refuses capture): stay eager
+                import warnings
+                warnings.warn("hpfg_b200: CUDA-graph capture of the step failed (%s); falling back to eager launches" % exc)
+                self._graph_enabled, self._graph = False, None
+                torch.cuda.synchronize()
+                out = self._step_body_dv(self._gx, self._gy)       # same device-value path, launched eagerly
+                self.last = dict(scalars=out["scalars"], lr=lr, w=w, logits=out["logits"], teacher_logits=out["teacher_logits"])
+                return out["scalars"][0]
             self._graph = g
             self.kernels_per_replay = int(L.lib().hpfg_launch_count() - n0)   # kernel nodes of the captured step
         self._graph.replay()
