@@ -313,6 +313,9 @@ extern "C" int hpfg_conv_tc_debug(int op, int N, int H, int W, int cin, int cout
     HPFG_CUDA_CHECK(cudaMalloc(&partials, (size_t)m_tiles * 2 * cout_v * 4));
     HPFG_CUDA_CHECK(launch_pdl(tc_pack_kernel, pack_grid(T), 256, 0, s, w_oihw, packed, T, 0));
     HPFG_LAUNCH_CHECK();
+    // the conv kernel requests its first weight stages before griddepcontrol.wait (safe in the network, where packing is
+    // at least two launches back); here packing is the direct predecessor, so finish it first
+    HPFG_CUDA_CHECK(cudaStreamSynchronize(s));
     LoadXform xf{};
     xf.scale = scale; xf.shift = shift; xf.drop.bits = nullptr; xf.drop.inv_keep = 1.f;
     int P = 0;

@@ -199,6 +199,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     const uint32_t bar_tfull = bar_empty + 8 * C::STAGES, bar_tempty = bar_tfull + 8 * C::NACC;
     const uint32_t stage_u32 = ptx::smem_u32(stage_base);
 
+    // this CTA's work items: fixed n-block, m-tiles mt0, mt0+mstep, ... (n_blocks divides the grid)
+    const int total_work = P.m_tiles * P.n_blocks;
+    const int nb = blockIdx.x % P.n_blocks, mt0 = blockIdx.x / P.n_blocks, mstep = gridDim.x / P.n_blocks;
+    const int n_work = (total_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+    // The packed weights were written several launches ago (tc_pack_kernel at the start of the pass), so the first
+    // ring of weight stages is requested BEFORE griddepcontrol.wait: their latency overlaps the previous kernel's tail.
+    const int total_flat = n_work * P.k_chunks;
+    const int pre = RES ? (total_flat > 0 ? 1 : 0) : (total_flat < C::STAGES ? total_flat : C::STAGES);
+    const uint32_t op_bytes = (P.dbg & 8) ? 0u : (uint32_t)C::OP_BYTES;
+
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(bar_full + 8 * s, 1);
@@ -211,6 +221,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&tmA);
+        const bf16 *bsrc0 = P.bpk + (size_t)nb * P.k_chunks * (C::B_BYTES / 2);
+        for (int f = 0; f < pre; ++f) {
+            const uint32_t fb = bar_full + 8 * f;
+            ptx::mbar_expect_tx(fb, op_bytes + C::B_BYTES);
+            if (RES) ptx::bulk_load(ptx::smem_u32(res_b), P.bpk, C::B_BYTES, fb);
+            else ptx::bulk_load(stage_u32 + f * C::STAGE_BYTES + C::OFF_B, bsrc0 + (size_t)(f % P.k_chunks) * (C::B_BYTES / 2), C::B_BYTES, fb);
+        }
     }
     if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
     pdl_wait();       // everything above is private setup; below reads what the previous kernel wrote
@@ -222,33 +239,29 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     const uint32_t tmem_base = *tmem_slot;
     if (P.trace && threadIdx.x == 0 && blockIdx.x == 0) P.trace[5 * 64] = clock64();
 
-    // this CTA's work items: fixed n-block, m-tiles mt0, mt0+mstep, ... (n_blocks divides the grid)
-    const int total_work = P.m_tiles * P.n_blocks;
-    const int nb = blockIdx.x % P.n_blocks, mt0 = blockIdx.x / P.n_blocks, mstep = gridDim.x / P.n_blocks;
-    const int n_work = (total_work - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
 
     if (warp == 0) {
         // ================================================================= TMA producer (warp-uniform, one lane issues)
         TileIter ti;
         ti.init(mt0, mstep, P.tiles_h, P.tiles_w);
-        int stage = 0, phase = 0;
-        const uint32_t op_bytes = (P.dbg & 8) ? 0u : (uint32_t)C::OP_BYTES;
+        int stage = 0, phase = 0, f = 0;
         const bf16 *bsrc = P.bpk + (size_t)nb * P.k_chunks * (C::B_BYTES / 2);
 #pragma unroll 1
         for (int it = 0; it < n_work; ++it) {
             const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * C::TWP - C::PAD;
 #pragma unroll 1
-            for (int kc = 0; kc < P.k_chunks; ++kc) {
+            for (int kc = 0; kc < P.k_chunks; ++kc, ++f) {
                 ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 1);
                 HPFG_TRACE(0, it);
                 const uint32_t sb = stage_u32 + stage * C::STAGE_BYTES, fb = bar_full + 8 * stage;
                 if (ptx::elect_one()) {
-                    if (RES) {       // weights ride along with the first tile only and stay resident
-                        ptx::mbar_expect_tx(fb, op_bytes + (it == 0 ? C::B_BYTES : 0));
-                        if (it == 0) ptx::bulk_load(ptx::smem_u32(res_b), P.bpk, C::B_BYTES, fb);
-                    } else {
-                        ptx::mbar_expect_tx(fb, op_bytes + C::B_BYTES);
-                        ptx::bulk_load(sb + C::OFF_B, bsrc + (size_t)kc * (C::B_BYTES / 2), C::B_BYTES, fb);
+                    if (f >= pre) {      // (the first `pre` stages already carry their expect_tx and weight load)
+                        if (RES) {       // resident weights: requested once, before the loop
+                            ptx::mbar_expect_tx(fb, op_bytes);
+                        } else {
+                            ptx::mbar_expect_tx(fb, op_bytes + C::B_BYTES);
+                            ptx::bulk_load(sb + C::OFF_B, bsrc + (size_t)kc * (C::B_BYTES / 2), C::B_BYTES, fb);
+                        }
                     }
                     if (!(P.dbg & 8)) ptx::tma_load_5d(sb, &tmA, fb, 0, w0, h0, kc * C::NCH, ti.n_img);
                 }
