@@ -46,6 +46,12 @@ SIGNATURES = {
                               ctypes.POINTER(c_f), c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
     "hpfg_ssl_loss_dv": (c_int, [c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_f,
                                  ctypes.POINTER(c_f), c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hpfg_ict_loss": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_vp, ctypes.POINTER(c_f),
+                              c_f, c_f, c_vp, c_vp, c_vp, c_vp]),
+    "hpfg_ict_mix": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
+    "hpfg_s4cv_loss": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_f, c_vp,
+                               ctypes.POINTER(c_f), c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hpfg_argmax_labels": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "hpfg_dice_loss": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f), c_vp, c_vp, c_vp,
                                c_vp]),
     "hpfg_ema_update": (c_int, [c_vp, c_vp, c_i64, c_f, c_vp]),
@@ -55,7 +61,7 @@ SIGNATURES = {
 }
 
 PREC_FP32, PREC_BF16 = 0, 1
-LOSS_SUP, LOSS_MT, LOSS_CPS, LOSS_UAMT = 0, 1, 2, 3
+LOSS_SUP, LOSS_MT, LOSS_CPS, LOSS_UAMT, LOSS_ICT, LOSS_S4CV = 0, 1, 2, 3, 4, 5
 NUM_BN, NUM_DROPOUT, NUM_PARAMS = 18, 5, 82
 
 _lib = None

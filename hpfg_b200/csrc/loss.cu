@@ -2,7 +2,9 @@
 // argmax pseudo-labelling and UAMT uncertainty masking, forward value AND d loss / d logits.
 //   utils/loss/medloss.py:5-56 (Med_Sup_Loss, DiceLoss), utils/loss/diceloss.py:64-81,155-191,
 //   2017_03_NIPS_Mean-Teacher_ACDC.py:97-106, 2021_06_CVPR_CPS_ACDC.py:99-111,
-//   2019_07_MICCAI_Uncertainty_Aware_ACDC.py:145-162.
+//   2019_07_MICCAI_Uncertainty_Aware_ACDC.py:145-162,
+//   2022_02_ISBI_ICT-MedSeg_ACDC.py:111-137 (ICT: consistency against a per-sample mix of two teacher softmaxes),
+//   2022_08_CVPR_S4CVNet_ACDC.py:124-156 (two students, Dice-only cross pseudo supervision + Mean-Teacher MSE).
 // Dice is a ratio of batch-wide sums, so the gradient needs those sums first: phase 1 (reduce kernel) streams
 // the logits once and reduces with warp shuffles -> one double atomic per block per quantity; phase 2 (grad
 // kernel) streams them again (L2-resident: the logits are << 126 MB) and writes dlogits.  Both are pure HBM
@@ -23,9 +25,12 @@ constexpr float kDiceSmooth = 1e-5f;
 struct LossArgs {
     int mode, n_l, n_u, hw, mc_passes;
     const float *student, *other, *mc;
+    const float *mix;               // ICT: per-sample mix factor lambda[n_u] (device)
     const int64_t *labels;
     float cons_weight, uamt_threshold, ce_coef, dice_coef;
+    float cons_weight2;             // S4CV: weight of the Mean-Teacher MSE terms (cons_weight = weight of the pseudo Dice terms)
     const float *cons_weight_dev;   // optional device scalar overriding cons_weight (CUDA-graph replays)
+    const float *cons_weight2_dev;  // same for cons_weight2
     float class_w[kMaxC];
     float *dstudent, *dother, *scalars;
     int64_t *pseudo1, *pseudo2;
@@ -115,19 +120,19 @@ __device__ __forceinline__ void load_labels4(const int64_t *p, int (&lab)[4]) {
 // MODE is a template parameter: the generic kernel carried four accumulator sets (177 registers, one CTA per SM, 12 %
 // warps active in ncu); Mean-Teacher needs one.
 template <int C, int MODE>
-__global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {
+__global__ void __launch_bounds__(256, MODE == HPFG_LOSS_S4CV ? 1 : 2) loss_reduce_kernel(LossArgs A) {
     pdl_prologue();
-    if (A.cons_weight_dev) A.cons_weight = *A.cons_weight_dev;
+    constexpr bool TWO = MODE == HPFG_LOSS_CPS || MODE == HPFG_LOSS_S4CV;   // two student networks
     constexpr int NS = 3 * C + 2;
     __shared__ float smem[8 * (2 * NS + 3)];
     __shared__ int slots[2 * NS + 3];
     const int64_t hw = A.hw, q_per_img = hw >> 2;
     const int64_t n_img = A.n_l + A.n_u;
     const int64_t total_q = n_img * q_per_img;
-    constexpr int NSETS = MODE == HPFG_LOSS_CPS ? 2 : 1;
-    float sl[NSETS][NS];   // labeled sums, net 0 / net 1 (CPS)
-    float su[NSETS][NS];   // CPS: unlabeled sums wrt the peer's pseudo labels
-    float misc[3] = {0.f, 0.f, 0.f};   // mse, mask_sum, masked_dist
+    constexpr int NSETS = TWO ? 2 : 1;
+    float sl[NSETS][NS];   // labeled sums, net 0 / net 1 (CPS, S4CV)
+    float su[NSETS][NS];   // CPS, S4CV: unlabeled sums wrt the peer's pseudo labels
+    float misc[3] = {0.f, 0.f, 0.f};   // mse, mask_sum, masked_dist (S4CV: mse net 1, mse net 2)
 #pragma unroll
     for (int i = 0; i < NS; ++i)
 #pragma unroll
@@ -143,7 +148,7 @@ __global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {
             int lab[4];
             load_labels4(A.labels + img * hw + pix, lab);
             acc_sup<C>(z, p, lse, lab, sl[0]);
-            if (MODE == HPFG_LOSS_CPS) {
+            if (TWO) {
                 float z2[C][4], p2[C][4], lse2[4];
                 load4<C>(A.other + (img * C) * hw + pix, hw, z2);
                 softmax4<C>(z2, p2, lse2);
@@ -152,8 +157,7 @@ __global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {
         } else if (MODE != HPFG_LOSS_SUP) {
             const int64_t u = img - A.n_l;
             float z2[C][4], p2[C][4], lse2[4];
-            const float *ob = (MODE == HPFG_LOSS_CPS) ? A.other + (img * C) * hw + pix
-                                                        : A.other + (u * C) * hw + pix;
+            const float *ob = TWO ? A.other + (img * C) * hw + pix : A.other + (u * C) * hw + pix;
             load4<C>(ob, hw, z2);
             softmax4<C>(z2, p2, lse2);
             if (MODE == HPFG_LOSS_MT) {
@@ -161,7 +165,19 @@ __global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {
                 for (int j = 0; j < 4; ++j)
 #pragma unroll
                     for (int c = 0; c < C; ++c) { const float d = p[c][j] - p2[c][j]; misc[0] += d * d; }
-            } else if (MODE == HPFG_LOSS_CPS) {
+            } else if (MODE == HPFG_LOSS_ICT) {   // target = (1-lambda)*softmax(teacher(ux0)) + lambda*softmax(teacher(ux1))
+                float z3[C][4], p3[C][4], lse3[4];
+                load4<C>(A.other + ((u + A.n_u) * C) * hw + pix, hw, z3);
+                softmax4<C>(z3, p3, lse3);
+                const float lam = __ldg(A.mix + u), oml = 1.0f - lam;
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+#pragma unroll
+                    for (int c = 0; c < C; ++c) {
+                        const float d = p[c][j] - (p2[c][j] * oml + p3[c][j] * lam);
+                        misc[0] += d * d;
+                    }
+            } else if (TWO) {
                 int pl1[4], pl2[4];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) { pl1[j] = argmax_first<C>(p, j); pl2[j] = argmax_first<C>(p2, j); }
@@ -174,6 +190,19 @@ __global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {
                     for (int j = 0; j < 4; ++j) A.pseudo1[o + j] = pl1[j];
                 if (A.pseudo2)
                     for (int j = 0; j < 4; ++j) A.pseudo2[o + j] = pl2[j];
+                if (MODE == HPFG_LOSS_S4CV && A.mc) {   // both students against the one EMA teacher
+                    float zt[C][4], pt[C][4], lt[4];
+                    load4<C>(A.mc + (u * C) * hw + pix, hw, zt);
+                    softmax4<C>(zt, pt, lt);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+#pragma unroll
+                        for (int c = 0; c < C; ++c) {
+                            const float d1 = p[c][j] - pt[c][j], d2 = p2[c][j] - pt[c][j];
+                            misc[0] += d1 * d1;
+                            misc[1] += d2 * d2;
+                        }
+                }
             } else {   // UAMT: mean softmax of the T stochastic teacher passes -> entropy -> mask
                 float mean[C][4];
 #pragma unroll
@@ -216,12 +245,12 @@ __global__ void __launch_bounds__(256, 2) loss_reduce_kernel(LossArgs A) {
     if (threadIdx.x < NS) slots[threadIdx.x] = slot_of(0, threadIdx.x);
     __syncthreads();
     flush<NS>(sl[0], A.acc + 0 * kAccPerSet, slots, smem);
-    if (MODE == HPFG_LOSS_CPS) {
+    if (TWO) {
         flush<NS>(sl[NSETS - 1], A.acc + 2 * kAccPerSet, slots, smem);
         flush<NS>(su[0], A.acc + 1 * kAccPerSet, slots, smem);
         flush<NS>(su[NSETS - 1], A.acc + 3 * kAccPerSet, slots, smem);
     }
-    if (MODE == HPFG_LOSS_MT || MODE == HPFG_LOSS_UAMT) {
+    if (MODE == HPFG_LOSS_MT || MODE == HPFG_LOSS_UAMT || MODE == HPFG_LOSS_ICT || MODE == HPFG_LOSS_S4CV) {
         if (threadIdx.x < 3) slots[threadIdx.x] = threadIdx.x;
         __syncthreads();
         flush<3>(misc, A.acc + kAccMse, slots, smem);
@@ -297,9 +326,13 @@ template <int C>
 __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
     pdl_prologue();
     if (A.cons_weight_dev) A.cons_weight = *A.cons_weight_dev;
+    if (A.cons_weight2_dev) A.cons_weight2 = *A.cons_weight2_dev;
     __shared__ SupCoef coef[4];   // [net*2 + set]
     __shared__ float s_cons;      // per-element consistency coefficient
-    const bool cps = A.mode == HPFG_LOSS_CPS;
+    const bool s4cv = A.mode == HPFG_LOSS_S4CV;
+    const bool cps = A.mode == HPFG_LOSS_CPS || s4cv;   // two student networks
+    // weights of the pseudo-label terms: CPS = Med_Sup_Loss on the peer's labels, S4CV = Dice only (2022_08...:139-140)
+    const float ps_ce = s4cv ? 0.f : A.ce_coef, ps_dice = s4cv ? 1.f : A.dice_coef;
     if (threadIdx.x == 0) {
         make_coef<C>(A.acc + 0 * kAccPerSet, A.class_w, coef[0]);
         if (cps) {
@@ -309,9 +342,12 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
         }
         float cons = 0.f, cons_val = 0.f;
         const double M = (double)A.n_u * C * (double)A.hw;
-        if (A.mode == HPFG_LOSS_MT) {
+        if (A.mode == HPFG_LOSS_MT || A.mode == HPFG_LOSS_ICT) {
             cons_val = (float)(A.acc[kAccMse] / M);
             cons = (float)(2.0 * A.cons_weight / M);
+        } else if (s4cv) {
+            cons_val = (float)((A.acc[kAccMse] + A.acc[kAccMse + 1]) / M);   // consistency_loss1 + consistency_loss2
+            cons = (float)(2.0 * A.cons_weight2 / M);
         } else if (A.mode == HPFG_LOSS_UAMT) {
             const double den = 2.0 * A.acc[kAccMaskSum] + 1e-16;
             cons_val = (float)(A.acc[kAccMaskedDist] / den);
@@ -323,18 +359,25 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
             float sup = sup0, aux = cons_val;
             if (cps) {
                 sup = sup0 + A.ce_coef * coef[2].ce + A.dice_coef * coef[2].dice;
-                aux = A.ce_coef * coef[1].ce + A.dice_coef * coef[1].dice + A.ce_coef * coef[3].ce +
-                      A.dice_coef * coef[3].dice;
+                aux = ps_ce * coef[1].ce + ps_dice * coef[1].dice + ps_ce * coef[3].ce + ps_dice * coef[3].dice;
             }
-            const float loss = (A.mode == HPFG_LOSS_SUP) ? sup : sup + A.cons_weight * aux;
+            float loss = (A.mode == HPFG_LOSS_SUP) ? sup : sup + A.cons_weight * aux;
+            float s6 = (float)A.acc[kAccMaskSum], s7 = 0.f;
+            if (s4cv) {   // loss_semi = w_cps*(ps1+ps2) + w_mt*(cl1+cl2); scalars: [2] loss_semi, [6] ps1+ps2, [7] cl1+cl2
+                const float semi = A.cons_weight * aux + A.cons_weight2 * cons_val;
+                loss = sup + semi;
+                s6 = aux;
+                s7 = cons_val;
+                aux = semi;
+            }
             A.scalars[0] = loss;
             A.scalars[1] = sup;
             A.scalars[2] = aux;
             A.scalars[3] = coef[0].ce;
             A.scalars[4] = coef[0].dice;
             A.scalars[5] = (float)A.acc[3 * kMaxC + 1];
-            A.scalars[6] = (float)A.acc[kAccMaskSum];
-            A.scalars[7] = 0.f;
+            A.scalars[6] = s6;
+            A.scalars[7] = s7;
         }
     }
     __syncthreads();
@@ -375,16 +418,47 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
             const uchar4 a1 = *reinterpret_cast<const uchar4 *>(A.aux + u * hw + pix);
             const uchar4 a2 = *reinterpret_cast<const uchar4 *>(A.aux + (int64_t)A.n_u * hw + u * hw + pix);
             const int pl1[4] = {a1.x, a1.y, a1.z, a1.w}, pl2[4] = {a2.x, a2.y, a2.z, a2.w};
-            grad_sup<C>(p, pl2, coef[1], A.ce_coef, A.dice_coef, A.cons_weight, g);
+            float zt[C][4], pt[C][4], lt[4], gm[C][4];
+            const bool mse = s4cv && A.mc != nullptr;
+            const float cf4[4] = {s_cons, s_cons, s_cons, s_cons};
+            if (mse) {
+                load4<C>(A.mc + (u * C) * hw + pix, hw, zt);
+                softmax4<C>(zt, pt, lt);
+            }
+            grad_sup<C>(p, pl2, coef[1], ps_ce, ps_dice, A.cons_weight, g);
+            if (mse) {
+                grad_mse<C>(p, pt, cf4, gm);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) g[c][j] += gm[c][j];
+            }
             store4<C>(A.dstudent + so, hw, g);
             load4<C>(A.other + so, hw, z);
             softmax4<C>(z, p, lse);
-            grad_sup<C>(p, pl1, coef[3], A.ce_coef, A.dice_coef, A.cons_weight, g);
+            grad_sup<C>(p, pl1, coef[3], ps_ce, ps_dice, A.cons_weight, g);
+            if (mse) {
+                grad_mse<C>(p, pt, cf4, gm);
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) g[c][j] += gm[c][j];
+            }
             store4<C>(A.dother + so, hw, g);
         } else {
             float z2[C][4], q2[C][4], l2[4], cf[4];
             load4<C>(A.other + (u * C) * hw + pix, hw, z2);
             softmax4<C>(z2, q2, l2);
+            if (A.mode == HPFG_LOSS_ICT) {
+                float z3[C][4], q3[C][4], l3[4];
+                load4<C>(A.other + ((u + A.n_u) * C) * hw + pix, hw, z3);
+                softmax4<C>(z3, q3, l3);
+                const float lam = __ldg(A.mix + u), oml = 1.0f - lam;
+#pragma unroll
+                for (int c = 0; c < C; ++c)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) q2[c][j] = q2[c][j] * oml + q3[c][j] * lam;
+            }
             if (A.mode == HPFG_LOSS_UAMT) {
                 const uchar4 mk = *reinterpret_cast<const uchar4 *>(A.aux + u * hw + pix);
                 cf[0] = mk.x ? s_cons : 0.f; cf[1] = mk.y ? s_cons : 0.f;
@@ -496,6 +570,8 @@ static int launch_loss(const LossArgs &A, cudaStream_t st) {
         case HPFG_LOSS_SUP: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_SUP>, grid, 256, 0, st, A)); break;
         case HPFG_LOSS_MT: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_MT>, grid, 256, 0, st, A)); break;
         case HPFG_LOSS_CPS: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_CPS>, grid, 256, 0, st, A)); break;
+        case HPFG_LOSS_ICT: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_ICT>, grid, 256, 0, st, A)); break;
+        case HPFG_LOSS_S4CV: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_S4CV>, grid, 256, 0, st, A)); break;
         default: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_UAMT>, grid, 256, 0, st, A)); break;
     }
     HPFG_LAUNCH_CHECK();
@@ -522,7 +598,7 @@ extern "C" int64_t hpfg_ssl_loss_workspace_bytes(int mode, int n_l, int n_u, int
                                                  int width) {
     (void)n_l; (void)num_classes;
     int64_t aux = 0;
-    if (mode == HPFG_LOSS_CPS) aux = 2LL * n_u * height * width;
+    if (mode == HPFG_LOSS_CPS || mode == HPFG_LOSS_S4CV) aux = 2LL * n_u * height * width;
     if (mode == HPFG_LOSS_UAMT) aux = 1LL * n_u * height * width;
     return kAccTotal * (int64_t)sizeof(double) + ((aux + 255) / 256) * 256;
 }
@@ -531,20 +607,24 @@ static int ssl_loss_impl(int mode, const float *student, const float *other, con
                          int mc_passes, const int64_t *labels, int n_l, int n_u, int num_classes, int height,
                          int width, float cons_weight, const float *cons_weight_dev, float uamt_threshold,
                          const float *class_weights_host, float ce_coef, float dice_coef, float *dstudent, float *dother,
-                         float *scalars_out, int64_t *pseudo1, int64_t *pseudo2, void *workspace, void *stream) {
-    HPFG_REQUIRE(mode >= HPFG_LOSS_SUP && mode <= HPFG_LOSS_UAMT, "hpfg_ssl_loss: unknown mode");
+                         float *scalars_out, int64_t *pseudo1, int64_t *pseudo2, void *workspace, void *stream,
+                         const float *mix = nullptr, float cons_weight2 = 0.f, const float *cons_weight2_dev = nullptr) {
+    HPFG_REQUIRE(mode >= HPFG_LOSS_SUP && mode <= HPFG_LOSS_S4CV, "hpfg_ssl_loss: unknown mode");
     HPFG_REQUIRE(student && dstudent && scalars_out && workspace, "hpfg_ssl_loss: null buffer");
     HPFG_REQUIRE(n_l >= 0 && n_u >= 0 && n_l + n_u > 0, "hpfg_ssl_loss: empty batch");
     HPFG_REQUIRE(n_l == 0 || labels, "hpfg_ssl_loss: labels required");
     HPFG_REQUIRE(num_classes >= 2 && num_classes <= kMaxC, "hpfg_ssl_loss: num_classes must be in [2,8]");
     HPFG_REQUIRE(((int64_t)height * width) % 4 == 0, "hpfg_ssl_loss: H*W must be a multiple of 4");
     if (mode != HPFG_LOSS_SUP && n_u > 0) HPFG_REQUIRE(other, "hpfg_ssl_loss: teacher/peer logits required");
-    if (mode == HPFG_LOSS_CPS) HPFG_REQUIRE(dother && other, "hpfg_ssl_loss: CPS needs peer logits and dother");
+    if (mode == HPFG_LOSS_CPS || mode == HPFG_LOSS_S4CV)
+        HPFG_REQUIRE(dother && other, "hpfg_ssl_loss: CPS / S4CV need peer logits and dother");
+    if (mode == HPFG_LOSS_ICT && n_u > 0) HPFG_REQUIRE(mix, "hpfg_ict_loss: mix_factors required");
     if (mode == HPFG_LOSS_UAMT) HPFG_REQUIRE(mc_logits && mc_passes > 0, "hpfg_ssl_loss: UAMT needs mc_logits");
     cudaStream_t st = (cudaStream_t)stream;
     LossArgs A{};
     A.mode = mode; A.n_l = n_l; A.n_u = n_u; A.hw = height * width; A.mc_passes = mc_passes;
     A.student = student; A.other = other; A.mc = mc_logits; A.labels = labels;
+    A.mix = mix; A.cons_weight2 = cons_weight2; A.cons_weight2_dev = cons_weight2_dev;
     A.cons_weight = cons_weight; A.cons_weight_dev = cons_weight_dev; A.uamt_threshold = uamt_threshold; A.ce_coef = ce_coef; A.dice_coef = dice_coef;
     for (int c = 0; c < kMaxC; ++c) A.class_w[c] = (class_weights_host && c < num_classes) ? class_weights_host[c] : 1.f;
     A.dstudent = dstudent; A.dother = dother; A.scalars = scalars_out; A.pseudo1 = pseudo1; A.pseudo2 = pseudo2;
@@ -568,6 +648,7 @@ extern "C" int hpfg_ssl_loss(int mode, const float *student, const float *other,
                              int width, float cons_weight, float uamt_threshold, const float *class_weights_host,
                              float ce_coef, float dice_coef, float *dstudent, float *dother, float *scalars_out,
                              int64_t *pseudo1, int64_t *pseudo2, void *workspace, void *stream) {
+    HPFG_REQUIRE(mode <= HPFG_LOSS_UAMT, "hpfg_ssl_loss: use hpfg_ict_loss / hpfg_s4cv_loss for the ICT / S4CV modes");
     return ssl_loss_impl(mode, student, other, mc_logits, mc_passes, labels, n_l, n_u, num_classes, height, width, cons_weight, nullptr,
                          uamt_threshold, class_weights_host, ce_coef, dice_coef, dstudent, dother, scalars_out, pseudo1, pseudo2,
                          workspace, stream);
@@ -580,6 +661,7 @@ extern "C" int hpfg_ssl_loss_dv(int mode, const float *student, const float *oth
                                 float *dother, float *scalars_out, int64_t *pseudo1, int64_t *pseudo2, void *workspace,
                                 void *stream) {
     HPFG_REQUIRE(cons_weight_dev, "hpfg_ssl_loss_dv: cons_weight_dev is null");
+    HPFG_REQUIRE(mode <= HPFG_LOSS_UAMT, "hpfg_ssl_loss_dv: use hpfg_ict_loss / hpfg_s4cv_loss for the ICT / S4CV modes");
     return ssl_loss_impl(mode, student, other, mc_logits, mc_passes, labels, n_l, n_u, num_classes, height, width, 0.f, cons_weight_dev,
                          uamt_threshold, class_weights_host, ce_coef, dice_coef, dstudent, dother, scalars_out, pseudo1, pseudo2,
                          workspace, stream);
@@ -606,5 +688,111 @@ extern "C" int hpfg_dice_loss(const float *inputs, const int64_t *target, int n,
         case 6: return launch_dice<6>(A, st);
         case 7: return launch_dice<7>(A, st);
         default: return launch_dice<8>(A, st);
+    }
+}
+
+// ---- ICT-MedSeg (2022_02_ISBI_ICT-MedSeg_ACDC.py:111-137) ---------------------------------------------------------
+extern "C" int hpfg_ict_loss(const float *student, const float *teacher_u, const float *mix_factors,
+                             const int64_t *labels, int n_l, int n_mixed, int num_classes, int height, int width,
+                             float cons_weight, const float *cons_weight_dev, const float *class_weights_host,
+                             float ce_coef, float dice_coef, float *dstudent, float *scalars_out, void *workspace,
+                             void *stream) {
+    return ssl_loss_impl(HPFG_LOSS_ICT, student, teacher_u, nullptr, 0, labels, n_l, n_mixed, num_classes, height, width,
+                         cons_weight, cons_weight_dev, 0.f, class_weights_host, ce_coef, dice_coef, dstudent, nullptr,
+                         scalars_out, nullptr, nullptr, workspace, stream, mix_factors);
+}
+
+// ---- S4CVNet (2022_08_CVPR_S4CVNet_ACDC.py:124-156) ----------------------------------------------------------------
+extern "C" int hpfg_s4cv_loss(const float *logits1, const float *logits2, const float *teacher_u,
+                              const int64_t *labels, int n_l, int n_u, int num_classes, int height, int width,
+                              float cps_weight, float mt_weight, const float *weights_dev,
+                              const float *class_weights_host, float ce_coef, float dice_coef, float *dlogits1,
+                              float *dlogits2, float *scalars_out, int64_t *pseudo1, int64_t *pseudo2, void *workspace,
+                              void *stream) {
+    return ssl_loss_impl(HPFG_LOSS_S4CV, logits1, logits2, teacher_u, 0, labels, n_l, n_u, num_classes, height, width,
+                         cps_weight, weights_dev, 0.f, class_weights_host, ce_coef, dice_coef, dlogits1, dlogits2,
+                         scalars_out, pseudo1, pseudo2, workspace, stream, nullptr, mt_weight,
+                         weights_dev ? weights_dev + 1 : nullptr);
+}
+
+namespace hpfg {
+// out[u] = a[u]*(1-lambda_u) + b[u]*lambda_u over whole images (the ICT input mix, 2022_02...:115-117); 128-bit accesses.
+__global__ void __launch_bounds__(256) ict_mix_kernel(const float4 *__restrict__ a, const float4 *__restrict__ b,
+                                                      const float *__restrict__ lam, float4 *__restrict__ out,
+                                                      int64_t quads_per_image, int64_t total_quads) {
+    pdl_prologue();
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += (int64_t)gridDim.x * blockDim.x) {
+        const float l = __ldg(lam + q / quads_per_image), o = __fsub_rn(1.0f, l);
+        const float4 x = __ldg(a + q), y = __ldg(b + q);
+        // separate roundings (no FMA contraction): bit-identical to torch's a*(1-l) + b*l
+        out[q] = make_float4(__fadd_rn(__fmul_rn(x.x, o), __fmul_rn(y.x, l)), __fadd_rn(__fmul_rn(x.y, o), __fmul_rn(y.y, l)),
+                             __fadd_rn(__fmul_rn(x.z, o), __fmul_rn(y.z, l)), __fadd_rn(__fmul_rn(x.w, o), __fmul_rn(y.w, l)));
+    }
+}
+
+// argmax over the class planes of NCHW fp32 logits, first maximum wins (torch.argmax; softmax is monotone, so
+// argmax(softmax(z)) == argmax(z) up to fp32 ties, which are resolved on the softmax values exactly as the reference
+// does: val.py:268-281 takes argmax(softmax(net(x)))).  4 pixels per thread, 128-bit loads per class plane.
+template <int C>
+__global__ void __launch_bounds__(256) argmax_kernel(const float *__restrict__ logits, int64_t hw, int64_t total_quads,
+                                                     int64_t *__restrict__ out_i64, uint8_t *__restrict__ out_u8) {
+    pdl_prologue();
+    const int64_t q_per_img = hw >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = q / q_per_img, pix = (q - img * q_per_img) << 2;
+        float z[C][4], p[C][4], lse[4];
+        load4<C>(logits + (img * C) * hw + pix, hw, z);
+        softmax4<C>(z, p, lse);
+        int best[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) best[j] = argmax_first<C>(p, j);
+        const int64_t o = img * hw + pix;
+        if (out_i64) {
+            *reinterpret_cast<longlong2 *>(out_i64 + o) = make_longlong2(best[0], best[1]);
+            *reinterpret_cast<longlong2 *>(out_i64 + o + 2) = make_longlong2(best[2], best[3]);
+        }
+        if (out_u8) *reinterpret_cast<uchar4 *>(out_u8 + o) = make_uchar4(best[0], best[1], best[2], best[3]);
+    }
+}
+
+template <int C>
+static int launch_argmax(const float *logits, int64_t hw, int64_t quads, int64_t *o64, uint8_t *o8, cudaStream_t st) {
+    HPFG_CUDA_CHECK(launch_pdl(argmax_kernel<C>, loss_grid(quads), 256, 0, st, logits, hw, quads, o64, o8));
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+}  // namespace hpfg
+
+extern "C" int hpfg_ict_mix(const float *a, const float *b, const float *mix_factors, int n, int64_t per_image,
+                            float *out, void *stream) {
+    HPFG_REQUIRE(a && b && mix_factors && out, "hpfg_ict_mix: null buffer");
+    HPFG_REQUIRE(n > 0 && per_image > 0 && per_image % 4 == 0, "hpfg_ict_mix: per_image must be a positive multiple of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t qpi = per_image / 4, total = qpi * n;
+    ProfScope _prof(PROF_LOSS, st);
+    HPFG_CUDA_CHECK(launch_pdl(ict_mix_kernel, loss_grid(total), 256, 0, st, reinterpret_cast<const float4 *>(a),
+                               reinterpret_cast<const float4 *>(b), mix_factors, reinterpret_cast<float4 *>(out), qpi, total));
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+extern "C" int hpfg_argmax_labels(const float *logits, int n, int num_classes, int height, int width,
+                                  int64_t *labels_i64, uint8_t *labels_u8, void *stream) {
+    HPFG_REQUIRE(logits && (labels_i64 || labels_u8), "hpfg_argmax_labels: null buffer");
+    HPFG_REQUIRE(n > 0, "hpfg_argmax_labels: empty batch");
+    HPFG_REQUIRE(num_classes >= 2 && num_classes <= kMaxC, "hpfg_argmax_labels: num_classes must be in [2,8]");
+    const int64_t hw = (int64_t)height * width;
+    HPFG_REQUIRE(hw % 4 == 0, "hpfg_argmax_labels: H*W must be a multiple of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t quads = (hw >> 2) * n;
+    ProfScope _prof(PROF_LOSS, st);
+    switch (num_classes) {
+        case 2: return launch_argmax<2>(logits, hw, quads, labels_i64, labels_u8, st);
+        case 3: return launch_argmax<3>(logits, hw, quads, labels_i64, labels_u8, st);
+        case 4: return launch_argmax<4>(logits, hw, quads, labels_i64, labels_u8, st);
+        case 5: return launch_argmax<5>(logits, hw, quads, labels_i64, labels_u8, st);
+        case 6: return launch_argmax<6>(logits, hw, quads, labels_i64, labels_u8, st);
+        case 7: return launch_argmax<7>(logits, hw, quads, labels_i64, labels_u8, st);
+        default: return launch_argmax<8>(logits, hw, quads, labels_i64, labels_u8, st);
     }
 }

@@ -158,3 +158,118 @@ def uamt_loss(student_logits, teacher_logits_u, mc_logits, labels, consistency_w
     return _SslLossFn.apply(student_logits, teacher_logits_u, L.LOSS_UAMT, labels, n_l,
                             dict(cons_weight=consistency_weight, mc_logits=mc_logits.contiguous().float(), mc_passes=T,
                                  uamt_threshold=threshold, ce_coef=ce, dice_coef=dice))
+
+
+# ---- ICT-MedSeg and S4CVNet step losses (same two kernels, extra modes) ----------------------
+def ict_mix_inputs(ux0, ux1, mix_factors):
+    """batch_ux_mixed = ux0*(1-l) + ux1*l  (2022_02_ISBI_ICT-MedSeg_ACDC.py:115-117); mix_factors: [n] or [n,1,1,1]."""
+    L.require_cuda(ux0, "ICT inputs")
+    a, b = ux0.contiguous().float(), ux1.contiguous().float()
+    assert a.shape == b.shape
+    lam = mix_factors.reshape(-1).to(device=a.device, dtype=torch.float32).contiguous()
+    assert lam.numel() == a.shape[0]
+    out = torch.empty_like(a)
+    L.check(L.lib().hpfg_ict_mix(L.ptr(a), L.ptr(b), L.ptr(lam), a.shape[0], a[0].numel(), L.ptr(out),
+                                 L.stream_ptr(a.device)), "hpfg_ict_mix")
+    return out
+
+
+def ict_loss_raw(student, teacher_u, mix_factors, labels, n_l, *, cons_weight=0.0, cons_weight_dev=None,
+                 class_weights=None, ce_coef=0.5, dice_coef=0.5):
+    """Thin wrapper of hpfg_ict_loss.  student [n_l+n_m,...], teacher_u [2*n_m,...] (ux0 half then ux1 half)."""
+    L.require_cuda(student, "logits")
+    student = student.contiguous().float()
+    n, c, h, w = student.shape
+    n_m = n - n_l
+    dev = student.device
+    teacher_u = teacher_u.contiguous().float()
+    assert teacher_u.shape == (2 * n_m, c, h, w), "teacher logits must cover both un-mixed halves"
+    lam = mix_factors.reshape(-1).to(device=dev, dtype=torch.float32).contiguous()
+    assert lam.numel() == n_m
+    labels = labels.contiguous().to(torch.int64)
+    assert labels.shape == (n_l, h, w), "labels must be [n_l,H,W]"
+    dstudent = torch.empty_like(student)
+    scalars = torch.empty(8, device=dev, dtype=torch.float32)
+    ws = _workspace(L.LOSS_ICT, n_l, n_m, c, h, w, dev)
+    L.check(L.lib().hpfg_ict_loss(L.ptr(student), L.ptr(teacher_u), L.ptr(lam), L.ptr(labels), n_l, n_m, c, h, w,
+                                  float(cons_weight), L.ptr(cons_weight_dev), _weights_arg(class_weights, c),
+                                  float(ce_coef), float(dice_coef), L.ptr(dstudent), L.ptr(scalars), L.ptr(ws),
+                                  L.stream_ptr(dev)), "hpfg_ict_loss")
+    return dict(scalars=scalars, dstudent=dstudent, dother=None)
+
+
+def s4cv_loss_raw(logits1, logits2, teacher_u, labels, n_l, *, cps_weight=0.0, mt_weight=0.0, weights_dev=None,
+                  class_weights=None, ce_coef=0.5, dice_coef=0.5, want_pseudo=False):
+    """Thin wrapper of hpfg_s4cv_loss.  teacher_u None = the reference's `cur_itrs < 1000` branch (no MSE terms)."""
+    L.require_cuda(logits1, "logits")
+    o1, o2 = logits1.contiguous().float(), logits2.contiguous().float()
+    assert o1.shape == o2.shape
+    n, c, h, w = o1.shape
+    n_u = n - n_l
+    dev = o1.device
+    if teacher_u is not None:
+        teacher_u = teacher_u.contiguous().float()
+        assert teacher_u.shape == (n_u, c, h, w)
+    labels = labels.contiguous().to(torch.int64)
+    assert labels.shape == (n_l, h, w), "labels must be [n_l,H,W]"
+    d1, d2 = torch.empty_like(o1), torch.empty_like(o2)
+    scalars = torch.empty(8, device=dev, dtype=torch.float32)
+    ws = _workspace(L.LOSS_S4CV, n_l, n_u, c, h, w, dev)
+    p1 = p2 = None
+    if want_pseudo:
+        p1 = torch.empty((n_u, h, w), device=dev, dtype=torch.int64)
+        p2 = torch.empty((n_u, h, w), device=dev, dtype=torch.int64)
+    L.check(L.lib().hpfg_s4cv_loss(L.ptr(o1), L.ptr(o2), L.ptr(teacher_u), L.ptr(labels), n_l, n_u, c, h, w,
+                                   float(cps_weight), float(mt_weight), L.ptr(weights_dev),
+                                   _weights_arg(class_weights, c), float(ce_coef), float(dice_coef), L.ptr(d1), L.ptr(d2),
+                                   L.ptr(scalars), L.ptr(p1), L.ptr(p2), L.ptr(ws), L.stream_ptr(dev)), "hpfg_s4cv_loss")
+    return dict(scalars=scalars, dstudent=d1, dother=d2, pseudo1=p1, pseudo2=p2)
+
+
+class _RawLossFn(torch.autograd.Function):
+    """autograd shim over a *_raw call that already produced d loss / d logits for up to two logit tensors."""
+
+    @staticmethod
+    def forward(ctx, a, b, fn):
+        r = fn(a.detach(), b.detach() if b is not None else None)
+        ctx.save_for_backward(r["dstudent"], r["dother"] if r["dother"] is not None else r["dstudent"].new_empty(0))
+        ctx.has_other = r["dother"] is not None
+        ctx.extras = r
+        return r["scalars"][0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        ds, do = ctx.saved_tensors
+        return ds * g, (do * g if ctx.has_other else None), None
+
+
+def ict_loss(student_logits, teacher_logits_u, mix_factors, labels, consistency_weight, ce=0.5, dice=0.5):
+    """supervised_loss + w*mean((softmax(s_mixed) - mix(softmax(t(ux0)), softmax(t(ux1))))^2)
+    (2022_02_ISBI_ICT-MedSeg_ACDC.py:121-137).  teacher_logits_u = cat([ema(ux0), ema(ux1)])."""
+    n_l = labels.shape[0]
+    t = teacher_logits_u.detach()
+    return _RawLossFn.apply(student_logits, None, lambda s, _: ict_loss_raw(
+        s, t, mix_factors, labels, n_l, cons_weight=consistency_weight, ce_coef=ce, dice_coef=dice))
+
+
+def s4cvnet_loss(logits1, logits2, teacher_logits_u, labels, cps_weight, mt_weight, ce=0.5, dice=0.5):
+    """loss_sup + loss_semi of 2022_08_CVPR_S4CVNet_ACDC.py:124-156 for any two segmentation networks' logits
+    (gradients flow to both).  cps_weight = 7*consistency_weight_cps; teacher_logits_u None or mt_weight applied to
+    consistency_loss1 + consistency_loss2 (pass None while cur_itrs < 1000, :143-145)."""
+    n_l = labels.shape[0]
+    t = teacher_logits_u.detach() if teacher_logits_u is not None else None
+    return _RawLossFn.apply(logits1, logits2, lambda a, b: s4cv_loss_raw(
+        a, b, t, labels, n_l, cps_weight=cps_weight, mt_weight=mt_weight, ce_coef=ce, dice_coef=dice))
+
+
+def argmax_labels(logits, dtype=torch.int64):
+    """torch.argmax(torch.softmax(logits, dim=1), dim=1) in one launch (val.py:275); int64 (default) or uint8 labels."""
+    L.require_cuda(logits, "logits")
+    z = logits.contiguous().float()
+    n, c, h, w = z.shape
+    assert dtype in (torch.int64, torch.uint8)
+    out = torch.empty((n, h, w), device=z.device, dtype=dtype)
+    L.check(L.lib().hpfg_argmax_labels(L.ptr(z), n, c, h, w, L.ptr(out) if dtype == torch.int64 else None,
+                                       L.ptr(out) if dtype == torch.uint8 else None, L.stream_ptr(z.device)),
+            "hpfg_argmax_labels")
+    return out

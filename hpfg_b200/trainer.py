@@ -3,6 +3,7 @@
 * ``MeanTeacherStep``  -- 2017_03_NIPS_Mean-Teacher_ACDC.py:89-113
 * ``CPSStep``          -- 2021_06_CVPR_CPS_ACDC.py:90-120
 * ``UAMTStep``         -- 2019_07_MICCAI_Uncertainty_Aware_ACDC.py:120-170
+* ``ICTStep``          -- 2022_02_ISBI_ICT-MedSeg_ACDC.py:96-140
 
 Each ``step()`` enqueues: student forward (activations kept in the plan), teacher/peer forward(s), ONE fused
 loss launch pair (value + dlogits), backward into a persistent flat gradient buffer, (data parallel: NCCL
@@ -15,7 +16,7 @@ import math
 import torch
 
 from . import _lib as L
-from .losses import ssl_loss_raw
+from .losses import ssl_loss_raw, ict_loss_raw, ict_mix_inputs
 from .utils import sigmoid_rampup
 
 
@@ -340,4 +341,60 @@ class UAMTStep(_StepBase):
         alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)
         lr = self._sgd(self.model, self.grads, self.mom, self.ema_model, alpha)
         self.last = dict(scalars=r["scalars"], lr=lr, w=w, threshold=thr, logits=out, teacher_logits=t_out, mc_logits=mc)
+        return r["scalars"][0]
+
+
+class ICTStep(_StepBase):
+    """Interpolation consistency training (2022_02_ISBI_ICT-MedSeg_ACDC.py:96-140): the student sees the labeled slices
+    and a per-sample mix of the two halves of the unlabeled batch; the EMA teacher sees the two un-mixed halves (two
+    forwards, as in the reference, so each has its own BatchNorm batch statistics) and the consistency target is the same
+    mix of its two softmaxes."""
+
+    def __init__(self, model, ema_model, *, ema_decay=0.99, ict_alpha=0.2, **kw):
+        super().__init__(**kw)
+        self.model, self.ema_model, self.ema_decay, self.ict_alpha = model, ema_model, ema_decay, ict_alpha
+        self.in_channels, self.num_classes = model.in_channels, model.num_classes
+        model.train()
+        model.ensure_flat()
+        ema_model.ensure_flat()
+        self.grads = torch.zeros_like(model.flat_params)
+        self.mom = torch.zeros_like(model.flat_params)
+
+    def draw_mix_factors(self, n_mixed):
+        """np.random.beta(alpha, alpha, size=(n_u//2,1,1,1)) (2022_02...:112-113): host RNG, as in the reference."""
+        import numpy as np
+        return torch.tensor(np.random.beta(self.ict_alpha, self.ict_alpha, size=(n_mixed,)), dtype=torch.float)
+
+    def step(self, x, labels, mix_factors=None):
+        """x: [n_l+n_u, C, H, W] (labeled first, n_u even); mix_factors: [n_u//2] floats (drawn here if None)."""
+        self.cur_itrs += 1
+        n_l = labels.shape[0]
+        n_u = x.shape[0] - n_l
+        assert n_u % 2 == 0, "ICT needs an even unlabeled batch"
+        n_m = n_u // 2
+        dev = x.device
+        if mix_factors is None:
+            mix_factors = self.draw_mix_factors(n_m)
+        lam = mix_factors.reshape(-1).to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        ux0, ux1 = x[n_l:n_l + n_m], x[n_l + n_m:]
+        ncls, hh, ww = self.num_classes, x.shape[2], x.shape[3]
+        main = torch.cuda.current_stream(dev)
+        side = main if getattr(self, "serialize", False) else self._side_stream(dev)
+        side.wait_stream(main)
+        t_out = self._persistent("t_out", (n_u, ncls, hh, ww), dev)
+        with torch.cuda.stream(side):            # the two teacher forwards are independent of the student forward
+            self._forward(self.ema_model, ux0, False, out=t_out[:n_m])
+            self._forward(self.ema_model, ux1, False, out=t_out[n_m:])
+        x_in = self._persistent("x_in", (n_l + n_m,) + tuple(x.shape[1:]), dev)
+        x_in[:n_l].copy_(x[:n_l])
+        L.check(L.lib().hpfg_ict_mix(L.ptr(ux0), L.ptr(ux1), L.ptr(lam), n_m, ux0[0].numel(), L.ptr(x_in[n_l:]),
+                                     L.stream_ptr(dev)), "hpfg_ict_mix")
+        plan, out = self._forward(self.model, x_in, True, out=self._persistent("s_out", (n_l + n_m, ncls, hh, ww), dev))
+        main.wait_stream(side)
+        w = self._consistency_weight()
+        r = ict_loss_raw(out, t_out, lam, labels, n_l, cons_weight=w)
+        self._backward(self.model, plan, r["dstudent"], self.grads)
+        alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)
+        lr = self._sgd(self.model, self.grads, self.mom, self.ema_model, alpha)
+        self.last = dict(scalars=r["scalars"], lr=lr, w=w, logits=out, teacher_logits=t_out, mix_factors=lam)
         return r["scalars"][0]

@@ -253,3 +253,22 @@ class UNet(nn.Module):
         if need_grad:
             return _UNetFunction.apply(x, self, *self.parameters())
         return self._run_forward(self._acquire_plan(x, False), x, save=False)
+
+
+def predict_volume(model, slices, max_batch=64, dtype=torch.int64):
+    """The network part of val.py:268-281 ``test_single_volume`` for a whole volume at once.
+
+    slices: [S,H,W] (single-channel volumes, as ACDC) or [S,Cin,H,W], already resampled to the test crop size; returns
+    ``argmax(softmax(net(slice)), dim=1)`` for every slice as [S,H,W] labels.  The reference loops slice by slice at
+    batch 1; in eval mode BatchNorm uses its running statistics and dropout is off, so every slice is independent and
+    batching them gives the same labels.  Like the reference (``net.eval()`` at :276) this leaves the model in eval mode.
+    Forward = ``hpfg_unet_forward(training=0)``, labels = ``hpfg_argmax_labels`` (one launch per chunk)."""
+    from .losses import argmax_labels
+    x = slices if slices.dim() == 4 else slices.unsqueeze(1)
+    L.require_cuda(x, "slices")
+    model.eval()
+    out = torch.empty((x.shape[0], x.shape[2], x.shape[3]), device=x.device, dtype=dtype)
+    with torch.no_grad():
+        for s in range(0, x.shape[0], max_batch):
+            out[s:s + max_batch] = argmax_labels(model(x[s:s + max_batch]), dtype=dtype)
+    return out

@@ -38,6 +38,8 @@ extern "C" {
 #define HPFG_LOSS_MT 1   /* + w * mean((softmax(s_u)-softmax(t_u))^2)        (Mean-Teacher)           */
 #define HPFG_LOSS_CPS 2  /* two nets, cross pseudo supervision                (CPS)                    */
 #define HPFG_LOSS_UAMT 3 /* + w * uncertainty-masked softmax-MSE              (UAMT)                   */
+#define HPFG_LOSS_ICT 4  /* + w * MSE against a per-sample mix of two teacher softmaxes (hpfg_ict_loss)  */
+#define HPFG_LOSS_S4CV 5 /* two nets: Dice-only cross pseudo supervision + teacher MSE (hpfg_s4cv_loss)  */
 
 #define HPFG_NUM_BN 18
 #define HPFG_NUM_DROPOUT 5
@@ -156,6 +158,38 @@ int hpfg_ssl_loss_dv(int mode, const float *student, const float *other, const f
                      const float *cons_weight_dev, float uamt_threshold, const float *class_weights, float ce_coef,
                      float dice_coef, float *dstudent, float *dother, float *scalars_out, int64_t *pseudo1,
                      int64_t *pseudo2, void *workspace, void *stream);
+
+/* ---- "next" rows of SURVEY 8f.4: the ICT-MedSeg and S4CVNet step losses on the same two kernels ------------------
+ * ICT (2022_02_ISBI_ICT-MedSeg_ACDC.py:111-137): student = logits of cat([labeled, mixed unlabeled]) [n_l+n_mixed,C,H,W];
+ * teacher_u = teacher logits of the 2*n_mixed un-mixed unlabeled slices (first half ux0, second half ux1);
+ * mix_factors = device float[n_mixed] (the Beta(alpha,alpha) draws).  loss = 0.5*(CE+Dice) on the labeled slices +
+ * w * mean((softmax(student_mixed) - ((1-l)*softmax(t(ux0)) + l*softmax(t(ux1))))^2).  cons_weight_dev (optional device
+ * scalar) overrides cons_weight (graph replay).  scalars_out as hpfg_ssl_loss ([2] = the unweighted consistency term).
+ * Workspace: hpfg_ssl_loss_workspace_bytes(HPFG_LOSS_ICT, n_l, n_mixed, ...). */
+int hpfg_ict_loss(const float *student, const float *teacher_u, const float *mix_factors, const int64_t *labels,
+                  int n_l, int n_mixed, int num_classes, int height, int width, float cons_weight,
+                  const float *cons_weight_dev, const float *class_weights, float ce_coef, float dice_coef,
+                  float *dstudent, float *scalars_out, void *workspace, void *stream);
+/* The ICT input mix out[u] = a[u]*(1-l_u) + b[u]*l_u over n images of per_image floats (2022_02...:115-117). */
+int hpfg_ict_mix(const float *a, const float *b, const float *mix_factors, int n, int64_t per_image, float *out,
+                 void *stream);
+/* S4CVNet (2022_08_CVPR_S4CVNet_ACDC.py:124-156): logits1/logits2 [n_l+n_u,C,H,W] of the two students, teacher_u
+ * [n_u,C,H,W] EMA-teacher logits (NULL = no Mean-Teacher term, the reference's cur_itrs < 1000 branch).
+ * loss = sup1 + sup2 + cps_weight*(Dice(softmax1_u, argmax2) + Dice(softmax2_u, argmax1))
+ *        + mt_weight*(mean((softmax1_u-softmax_t)^2) + mean((softmax2_u-softmax_t)^2));
+ * the caller passes cps_weight = 7*consistency*linear_rampup(...) (:148-149).  weights_dev: optional device float[2]
+ * {cps_weight, mt_weight} overriding the by-value weights.  scalars_out: {loss, loss_sup, loss_semi, ce1, dice1, n_valid,
+ * ps1+ps2, cl1+cl2}.  Workspace: hpfg_ssl_loss_workspace_bytes(HPFG_LOSS_S4CV, ...). */
+int hpfg_s4cv_loss(const float *logits1, const float *logits2, const float *teacher_u, const int64_t *labels, int n_l,
+                   int n_u, int num_classes, int height, int width, float cps_weight, float mt_weight,
+                   const float *weights_dev, const float *class_weights, float ce_coef, float dice_coef,
+                   float *dlogits1, float *dlogits2, float *scalars_out, int64_t *pseudo1, int64_t *pseudo2,
+                   void *workspace, void *stream);
+
+/* ---- inference side (val.py:268-281 test_single_volume): argmax(softmax(logits), dim=1), first maximum
+ * wins, for a whole batch of eval-mode logits in one launch.  Either output may be NULL. */
+int hpfg_argmax_labels(const float *logits, int n, int num_classes, int height, int width, int64_t *labels_i64,
+                       uint8_t *labels_u8, void *stream);
 
 /* DiceLoss.forward (utils/loss/diceloss.py:178-191) alone: inputs are probabilities (softmax == 0) or
  * logits (softmax != 0); target int64 [n,H,W]; dinputs optional. scalars_out: float[1+C] = {loss, dice_c..}. */

@@ -1,5 +1,6 @@
 """fp32 restatement of the SSL losses on the hot path (utils/loss/medloss.py:5-56,
-utils/loss/diceloss.py:64-81,155-191 and the inline trainer expressions cited per function)."""
+utils/loss/diceloss.py:64-81,155-191 and the inline trainer expressions cited per function).
+TEST INFRASTRUCTURE ONLY (see oracle/__init__.py)."""
 import torch
 import torch.nn.functional as F
 
@@ -73,3 +74,43 @@ def uamt_consistency(student_logits_u, teacher_logits_u, teacher_mc_logits, T, t
     mask = (uncertainty < threshold).float()
     loss = torch.sum(mask * dist) / (2 * torch.sum(mask) + 1e-16)     # the literal 2 is the reference's
     return loss, uncertainty, mask
+
+
+def ict_losses(student_logits, teacher_logits_u, mix_factors, target, label_bs, n_classes):
+    """ICT-MedSeg supervised + interpolation-consistency terms (2022_02_ISBI_ICT-MedSeg_ACDC.py:121-135).
+
+    student_logits [label_bs + n_m, C, H, W] = model(cat([labeled, mixed])); teacher_logits_u [2*n_m, ...] =
+    cat([ema(ux0), ema(ux1)]); mix_factors [n_m,1,1,1].  Returns (supervised_loss, consistency_loss)."""
+    n_m = student_logits.shape[0] - label_bs
+    soft = torch.softmax(student_logits, dim=1)
+    e0 = torch.softmax(teacher_logits_u[:n_m], dim=1)
+    e1 = torch.softmax(teacher_logits_u[n_m:], dim=1)
+    lam = mix_factors.reshape(n_m, 1, 1, 1).float()
+    pred_mixed = e0 * (1.0 - lam) + e1 * lam                                           # :125
+    loss_ce = ce_loss(student_logits[:label_bs], target)                               # :127
+    loss_dice = dice_loss(soft[:label_bs], target.unsqueeze(1), n_classes)             # :128
+    sup = 0.5 * (loss_dice + loss_ce)                                                  # :130
+    cons = torch.mean((soft[label_bs:] - pred_mixed) ** 2)                             # :133
+    return sup, cons
+
+
+def s4cv_losses(out1, out2, teacher_logits_u, target, label_bs, n_classes, cps_weight, mt_weight):
+    """S4CVNet loss (2022_08_CVPR_S4CVNet_ACDC.py:124-156).  cps_weight = 7*consistency_weight_cps (:148-149);
+    teacher_logits_u None = the `cur_itrs < 1000` branch (consistency_loss1/2 = 0.0, :143-145).
+    Returns (loss, loss_sup, loss_semi, pseudo1, pseudo2)."""
+    soft1, soft2 = torch.softmax(out1, dim=1), torch.softmax(out2, dim=1)
+    loss1 = 0.5 * (ce_loss(out1[:label_bs], target) + dice_loss(soft1[:label_bs], target.unsqueeze(1), n_classes))
+    loss2 = 0.5 * (ce_loss(out2[:label_bs], target) + dice_loss(soft2[:label_bs], target.unsqueeze(1), n_classes))
+    loss_sup = loss1 + loss2
+    pl1 = torch.argmax(soft1[label_bs:].detach(), dim=1, keepdim=False)
+    pl2 = torch.argmax(soft2[label_bs:].detach(), dim=1, keepdim=False)
+    ps1 = dice_loss(soft1[label_bs:], pl2.unsqueeze(1), n_classes)
+    ps2 = dice_loss(soft2[label_bs:], pl1.unsqueeze(1), n_classes)
+    if teacher_logits_u is None:
+        cl1 = cl2 = 0.0
+    else:
+        ema_soft = torch.softmax(teacher_logits_u, dim=1)
+        cl1 = torch.mean((soft1[label_bs:] - ema_soft) ** 2)
+        cl2 = torch.mean((soft2[label_bs:] - ema_soft) ** 2)
+    loss_semi = (cps_weight * ps1 + mt_weight * cl1) + (cps_weight * ps2 + mt_weight * cl2)
+    return loss_sup + loss_semi, loss_sup, loss_semi, pl1, pl2

@@ -48,5 +48,6 @@ def load_reference():
     ns.update_ema_variables = utils.update_ema_variables
     ns.get_current_consistency_weight = utils.get_current_consistency_weight
     ns.sigmoid_rampup = utils.sigmoid_rampup
+    ns.linear_rampup = utils.linear_rampup
     ns.Medical_LR = mlr.Medical_LR
     return ns

@@ -1,14 +1,15 @@
 """fp32 restatement of the trainer step bodies and the host-side schedules around the hot path
 (utils/utils.py:67-86, utils/scheduler/medical_lr.py:7-17, utils/__init__.py:14-16,
 2017_03_NIPS_Mean-Teacher_ACDC.py:89-113, 2021_06_CVPR_CPS_ACDC.py:90-120,
-2019_07_MICCAI_Uncertainty_Aware_ACDC.py:120-170)."""
+2019_07_MICCAI_Uncertainty_Aware_ACDC.py:120-170, 2022_02_ISBI_ICT-MedSeg_ACDC.py:96-140)."""
 import math
 
 import numpy as np
 import torch
 
 from .unet_ref import unet_forward, unet_param_spec
-from .losses_ref import med_sup_loss, mt_consistency, cps_losses, uamt_consistency, dice_loss, ce_loss
+from .losses_ref import (med_sup_loss, mt_consistency, cps_losses, uamt_consistency, dice_loss, ce_loss,
+                         ict_losses)
 
 
 def sigmoid_rampup(current, rampup_length):
@@ -166,3 +167,34 @@ def uamt_step(student, teacher, opt, x_l, x_u, y, cur_itrs, noise, mc_noise, *, 
     return dict(loss=float(loss.detach()), loss_sup=float(sup.detach()), loss_cons=float(cons.detach()), w=w, lr=lr, threshold=threshold,
                 logits=out.detach(), teacher_logits=t_out, mc_logits=preds, uncertainty=unc, mask=mask,
                 grads=grads)
+
+
+def ict_step(student, teacher, opt, x_l, x_u, y, cur_itrs, mix_factors, *, base_lr=0.01, max_iterations=30000,
+             ema_decay=0.99, consistency=0.1, consistency_rampup=200.0, student_masks=None, teacher_masks=None):
+    """One ICT-MedSeg iteration (2022_02_ISBI_ICT-MedSeg_ACDC.py:96-140).  mix_factors [n_u//2] are the
+    np.random.beta(ict_alpha, ict_alpha) draws (:112), supplied by the caller so both sides see identical bits.
+    teacher_masks: list of two dicts (one per teacher forward) or None.  The teacher is in train() mode (a freshly
+    built module that is never switched to eval before the loop, :57,76)."""
+    names, ncls = _names(student)
+    lb, n_u = x_l.shape[0], x_u.shape[0]
+    n_m = n_u // 2
+    lam = mix_factors.reshape(n_m, 1, 1, 1).float()
+    ux0, ux1 = x_u[:n_m], x_u[n_m:]
+    mixed = ux0 * (1.0 - lam) + ux1 * lam                                               # :117
+    x = torch.cat([x_l, mixed], dim=0)
+    out, leaves = _grad_forward(student, names, x, student_masks)
+    tm = teacher_masks if teacher_masks is not None else [None, None]
+    with torch.no_grad():
+        t0 = unet_forward(teacher, ux0, True, tm[0])                                    # :123
+        t1 = unet_forward(teacher, ux1, True, tm[1])                                    # :124
+    t_out = torch.cat([t0, t1], dim=0)
+    sup, cons = ict_losses(out, t_out, lam, y, lb, ncls)
+    w = consistency_weight(cur_itrs, consistency, consistency_rampup)
+    loss = sup + w * cons
+    grads = dict(zip(names, torch.autograd.grad(loss, [leaves[n] for n in names], allow_unused=True)))
+    lr = medical_lr(cur_itrs - 1, base_lr, max_iterations)
+    with torch.no_grad():
+        sgd_step(student, grads, opt, lr)
+        update_ema(student, teacher, ema_decay, cur_itrs, names)
+    return dict(loss=float(loss.detach()), loss_sup=float(sup.detach()), loss_cons=float(cons.detach()), w=w, lr=lr,
+                logits=out.detach(), teacher_logits=t_out, grads=grads, mixed=mixed)

@@ -43,6 +43,20 @@ def make_batch(n_l, n_u, in_ch, n_cls, h, w, seed, ignore_frac=0.0):
     return x_l, x_u, y
 
 
+def make_predict_case(in_ch, n_cls, n, h, w, seed):
+    """State + volume for the inference fixture: the output conv is scaled up and the slices are smooth blobs so that a
+    random-init network predicts a mix of classes (BN running buffers come from the fixture)."""
+    st = make_state(in_ch, n_cls, seed)
+    wo = st["decoder.out_conv.weight"]
+    st["decoder.out_conv.weight"] = (wo - wo.mean(dim=(1, 2, 3), keepdim=True)) * 40.0
+    st["decoder.out_conv.bias"] = torch.zeros_like(st["decoder.out_conv.bias"])
+    g = gen(seed + 50)
+    coarse = torch.rand(n, 1, 4, 6, generator=g)
+    vol = torch.nn.functional.interpolate(coarse, size=(h, w), mode="bilinear", align_corners=True)[:, 0]
+    vol = (vol + 0.05 * torch.rand(n, h, w, generator=g)).contiguous()
+    return st, vol
+
+
 def summarize(t, stride=97, full_below=20000):
     """Compact fingerprint of a tensor: full copy if small, else strided sample + sums (fp64)."""
     t = t.detach().double().flatten()

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.ref_loader import load_reference            # noqa: E402
-from tests.golden.common import (make_state, make_masks, make_batch, summarize, ENC_PREFIXES)  # noqa: E402
+from tests.golden.common import (make_state, make_masks, make_batch, summarize, ENC_PREFIXES, make_predict_case)  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ref = load_reference()
@@ -241,7 +241,183 @@ def golden_mt_steps(tag, in_ch, n_cls, n_l, n_u, h, w, seed, steps=3):
     print("mt_steps_%s:" % tag, [r["loss"] for r in recs])
 
 
+
+def golden_f4_losses():
+    """SURVEY 8f.4 loss modes on the reference's own DiceLoss / CrossEntropyLoss objects: the inline expressions of
+    2022_02_ISBI_ICT-MedSeg_ACDC.py:119-135 and 2022_08_CVPR_S4CVNet_ACDC.py:124-156, transcribed literally."""
+    g = torch.Generator().manual_seed(5151)
+    out = {}
+    for tag, (n_l, n_m, C, H, W) in {"c4": (3, 2, 4, 24, 40), "c2": (2, 3, 2, 16, 16)}.items():
+        rec = {"shape": (n_l, n_m, C, H, W)}
+        criterion = nn.CrossEntropyLoss(ignore_index=255)
+        dice_loss = ref.DiceLoss(C)
+        # ---- ICT: student sees n_l + n_m slices, the teacher the 2*n_m un-mixed ones
+        outputs = (3.0 * torch.randn(n_l + n_m, C, H, W, generator=g)).requires_grad_(True)
+        ema0 = 3.0 * torch.randn(n_m, C, H, W, generator=g)
+        ema1 = 3.0 * torch.randn(n_m, C, H, W, generator=g)
+        target_label = torch.randint(0, C, (n_l, H, W), generator=g)
+        target_label[torch.rand(target_label.shape, generator=g) < 0.05] = 255
+        ict_mix_factors = torch.rand(n_m, 1, 1, 1, generator=g)
+        label_bs = n_l
+        outputs_soft = torch.softmax(outputs, dim=1)
+        ema_output_ux0 = torch.softmax(ema0, dim=1)
+        ema_output_ux1 = torch.softmax(ema1, dim=1)
+        batch_pred_mixed = ema_output_ux0 * (1.0 - ict_mix_factors) + ema_output_ux1 * ict_mix_factors
+        loss_ce = criterion(outputs[:label_bs], target_label)
+        loss_dice = dice_loss(outputs_soft[:label_bs], target_label.unsqueeze(1))
+        supervised_loss = 0.5 * (loss_dice + loss_ce)
+        consistency_weight = 0.37
+        consistency_loss = torch.mean((outputs_soft[label_bs:] - batch_pred_mixed) ** 2)
+        loss = supervised_loss + consistency_weight * consistency_loss
+        (gr,) = torch.autograd.grad(loss, outputs)
+        rec["ict"] = dict(w=consistency_weight, loss=loss.item(), sup=supervised_loss.item(), cons=consistency_loss.item(),
+                          grad=gr.clone(), student=outputs.detach().clone(), teacher=torch.cat([ema0, ema1]).clone(),
+                          mix=ict_mix_factors.reshape(-1).clone(), y=target_label.clone())
+        # ---- S4CVNet: two students on n_l + n_u slices, one teacher on the n_u unlabeled ones
+        n_u = n_m + 1
+        outputs1 = (3.0 * torch.randn(n_l + n_u, C, H, W, generator=g)).requires_grad_(True)
+        outputs2 = (3.0 * torch.randn(n_l + n_u, C, H, W, generator=g)).requires_grad_(True)
+        ema_output = 3.0 * torch.randn(n_u, C, H, W, generator=g)
+        label_batch_size = n_l
+        s4 = {}
+        for branch, cur_itrs in (("early", 500), ("late", 1500)):
+            outputs_soft1 = torch.softmax(outputs1, dim=1)
+            outputs_soft2 = torch.softmax(outputs2, dim=1)
+            ema_output_soft = torch.softmax(ema_output, dim=1)
+            loss1 = 0.5 * (criterion(outputs1[:label_batch_size], target_label) +
+                           dice_loss(outputs_soft1[:label_batch_size], target_label.unsqueeze(1)))
+            loss2 = 0.5 * (criterion(outputs2[:label_batch_size], target_label) +
+                           dice_loss(outputs_soft2[:label_batch_size], target_label.unsqueeze(1)))
+            loss_sup = loss1 + loss2
+            pseudo_outputs1 = torch.argmax(outputs_soft1[label_batch_size:].detach(), dim=1, keepdim=False)
+            pseudo_outputs2 = torch.argmax(outputs_soft2[label_batch_size:].detach(), dim=1, keepdim=False)
+            pseudo_supervision1 = dice_loss(outputs_soft1[label_batch_size:], pseudo_outputs2.unsqueeze(1))
+            pseudo_supervision2 = dice_loss(outputs_soft2[label_batch_size:], pseudo_outputs1.unsqueeze(1))
+            consistency_weight_cps = 0.1 * ref.linear_rampup(cur_itrs // 150, 200.0)
+            consistency_weight_mt = 0.1 * ref.linear_rampup(cur_itrs // 150, 200.0)
+            if cur_itrs < 1000:
+                consistency_loss1 = 0.0
+                consistency_loss2 = 0.0
+            else:
+                consistency_loss1 = torch.mean((outputs_soft1[label_batch_size:] - ema_output_soft) ** 2)
+                consistency_loss2 = torch.mean((outputs_soft2[label_batch_size:] - ema_output_soft) ** 2)
+            model1_loss = 7 * consistency_weight_cps * pseudo_supervision1 + consistency_weight_mt * consistency_loss1
+            model2_loss = 7 * consistency_weight_cps * pseudo_supervision2 + consistency_weight_mt * consistency_loss2
+            loss_semi = model1_loss + model2_loss
+            loss = loss_sup + loss_semi
+            g1, g2 = torch.autograd.grad(loss, [outputs1, outputs2])
+            s4[branch] = dict(cur_itrs=cur_itrs, cps_weight=7 * consistency_weight_cps, mt_weight=consistency_weight_mt,
+                              loss=loss.item(), sup=loss_sup.item(), semi=loss_semi.item(), grad1=g1.clone(),
+                              grad2=g2.clone(), pl1=pseudo_outputs1.clone(), pl2=pseudo_outputs2.clone())
+        s4.update(logits1=outputs1.detach().clone(), logits2=outputs2.detach().clone(), teacher=ema_output.clone(),
+                  y=target_label.clone(), n_u=n_u)
+        rec["s4cv"] = s4
+        out[tag] = rec
+    torch.save(out, os.path.join(HERE, "f4_losses.pt"))
+    print("f4_losses: ict %.8f s4cv early %.8f late %.8f" % (out["c4"]["ict"]["loss"], out["c4"]["s4cv"]["early"]["loss"],
+                                                             out["c4"]["s4cv"]["late"]["loss"]))
+
+
+def golden_ict_steps(tag, in_ch, n_cls, n_l, n_u, h, w, seed, steps=2):
+    """Literal ICT-MedSeg step (2022_02_ISBI_ICT-MedSeg_ACDC.py:55-59,66-76,96-140) on reference objects; the Beta draws
+    are replaced by seeded uniform mix factors and .cuda() by the CPU device."""
+    st = make_state(in_ch, n_cls, seed)
+    model = ref_model(st, in_ch, n_cls)
+    ema_model = ref_model(make_state(in_ch, n_cls, seed + 7), in_ch, n_cls)      # built separately, as at :57
+    for name, param in ema_model.named_parameters():
+        param.requires_grad = False
+    args = Args(lr=0.01, momentum=0.9, weight_decay=1e-4, total_itrs=30000, ema_decay=0.99, consistency=0.1,
+                consistency_rampup=200.0, num_classes=n_cls)
+    optimizer = torch.optim.SGD(model.parameters(), lr=args.lr, momentum=args.momentum, weight_decay=args.weight_decay)
+    lr_scheduler = ref.Medical_LR(optimizer=optimizer, base_lr=args.lr, max_iterations=args.total_itrs)
+    criterion = nn.CrossEntropyLoss(ignore_index=255)
+    dice_loss = ref.DiceLoss(args.num_classes)
+    model.train()
+    recs = []
+    cur_itrs = 0
+    for it in range(steps):
+        cur_itrs += 1
+        img_labeled, img_unlabeled, target_label = make_batch(n_l, n_u, in_ch, n_cls, h, w, seed + 100 * cur_itrs)
+        label_bs = img_labeled.shape[0]
+        unlabel_bs = img_unlabeled.shape[0]
+        hs = inject_masks(model, make_masks(n_l + unlabel_bs // 2, h, w, seed + 100 * cur_itrs + 1))
+        hs += inject_masks(ema_model, make_masks(unlabel_bs // 2, h, w, seed + 100 * cur_itrs + 2))
+        ict_mix_factors = torch.rand(unlabel_bs // 2, 1, 1, 1, generator=torch.Generator().manual_seed(seed + 100 * cur_itrs + 3))
+        unlabeled_volume_batch_0 = img_unlabeled[0:unlabel_bs // 2, ...]
+        unlabeled_volume_batch_1 = img_unlabeled[unlabel_bs // 2:, ...]
+        batch_ux_mixed = unlabeled_volume_batch_0 * (1.0 - ict_mix_factors) + unlabeled_volume_batch_1 * ict_mix_factors
+        input_volume_batch = torch.cat([img_labeled, batch_ux_mixed], dim=0)
+        outputs = model(input_volume_batch)
+        outputs_soft = torch.softmax(outputs, dim=1)
+        with torch.no_grad():
+            ema0 = ema_model(unlabeled_volume_batch_0)
+            ema1 = ema_model(unlabeled_volume_batch_1)
+            ema_output_ux0 = torch.softmax(ema0, dim=1)
+            ema_output_ux1 = torch.softmax(ema1, dim=1)
+            batch_pred_mixed = ema_output_ux0 * (1.0 - ict_mix_factors) + ema_output_ux1 * ict_mix_factors
+        loss_ce = criterion(outputs[:label_bs], target_label)
+        loss_dice = dice_loss(outputs_soft[:label_bs], target_label.unsqueeze(1))
+        supervised_loss = 0.5 * (loss_dice + loss_ce)
+        consistency_weight = ref.get_current_consistency_weight(epoch=cur_itrs // 150, args=args)
+        consistency_loss = torch.mean((outputs_soft[label_bs:] - batch_pred_mixed) ** 2)
+        loss = supervised_loss + consistency_weight * consistency_loss
+        optimizer.zero_grad()
+        loss.backward()
+        lr = optimizer.param_groups[0]["lr"]
+        optimizer.step()
+        lr_scheduler.step()
+        ref.update_ema_variables(model, ema_model, args.ema_decay, cur_itrs)
+        for hnd in hs:
+            hnd.remove()
+        recs.append(dict(loss=loss.item(), sup=supervised_loss.item(), cons=consistency_loss.item(), w=consistency_weight,
+                         lr=lr, logits=summarize(outputs), teacher_logits=summarize(torch.cat([ema0, ema1])),
+                         student_sum=sum(p.double().sum().item() for p in model.parameters()),
+                         teacher_sum=sum(p.double().sum().item() for p in ema_model.parameters()),
+                         student_out_conv=model.decoder.out_conv.weight.detach().clone(),
+                         teacher_out_conv=ema_model.decoder.out_conv.weight.detach().clone(),
+                         teacher_rm=ema_model.encoder.in_conv.conv_conv[1].running_mean.clone()))
+    out = {"cfg": dict(in_ch=in_ch, n_cls=n_cls, n_l=n_l, n_u=n_u, h=h, w=w, seed=seed, steps=steps), "steps": recs}
+    torch.save(out, os.path.join(HERE, "ict_steps_%s.pt" % tag))
+    print("ict_steps_%s:" % tag, [r["loss"] for r in recs])
+
+
+def golden_predict(in_ch, n_cls, n, h, w, seed):
+    """val.py:268-281 network part: eval-mode argmax(softmax(net(slice))) slice by slice at batch 1, after a few
+    train-mode forwards so that the BatchNorm running statistics are non-trivial."""
+    st, vol = make_predict_case(in_ch, n_cls, n, h, w, seed)
+    net = ref_model(st, in_ch, n_cls)
+    hs = inject_masks(net, None)
+    with torch.no_grad():
+        for i in range(3):
+            net(torch.rand(4, in_ch, h, w, generator=torch.Generator().manual_seed(seed + 10 + i)))
+    for hnd in hs:
+        hnd.remove()
+    net.eval()
+    with torch.no_grad():                       # centre the class logits so that the labels are a mix of classes
+        net.decoder.out_conv.bias.copy_(-net(vol.unsqueeze(1)).mean(dim=(0, 2, 3)))
+    buffers = {k: v.clone() for k, v in net.state_dict().items() if "running_" in k or "num_batches" in k}
+    buffers["decoder.out_conv.bias"] = net.decoder.out_conv.bias.detach().clone()
+    preds, margins = [], []
+    for ind in range(n):
+        input = vol[ind].unsqueeze(0).unsqueeze(0).float()
+        net.eval()
+        with torch.no_grad():
+            soft = torch.softmax(net(input), dim=1)
+            preds.append(torch.argmax(soft, dim=1).squeeze(0))
+            top2 = soft.topk(2, dim=1).values
+            margins.append((top2[:, 0] - top2[:, 1]).squeeze(0))
+    out = dict(cfg=dict(in_ch=in_ch, n_cls=n_cls, n=n, h=h, w=w, seed=seed), buffers=buffers,
+               labels=torch.stack(preds).to(torch.uint8), margin=torch.stack(margins).half())
+    torch.save(out, os.path.join(HERE, "predict_acdc.pt"))
+    print("predict: label histogram", torch.bincount(out["labels"].flatten().long(), minlength=n_cls).tolist())
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "f4":      # only the SURVEY 8f.3 / 8f.4 fixtures (leaves the others untouched)
+        golden_f4_losses()
+        golden_ict_steps("acdc", 1, 4, 2, 4, 32, 32, 606)
+        golden_predict(1, 4, 5, 32, 48, 707)
+        sys.exit(0)
     golden_unet("acdc_masks", 1, 4, 2, 32, 48, 101, True)
     golden_unet("acdc_nodrop", 1, 4, 3, 32, 32, 202, False)
     golden_unet("isic_masks", 3, 2, 2, 48, 32, 303, True)
@@ -249,3 +425,6 @@ if __name__ == "__main__":
     golden_schedules()
     golden_mt_steps("acdc", 1, 4, 2, 2, 32, 32, 404)
     golden_mt_steps("isic", 3, 2, 1, 3, 32, 32, 505, steps=2)
+    golden_f4_losses()
+    golden_ict_steps("acdc", 1, 4, 2, 4, 32, 32, 606)
+    golden_predict(1, 4, 5, 32, 48, 707)

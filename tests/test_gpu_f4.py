@@ -1,0 +1,154 @@
+"""GPU parity tests (B200) for the SURVEY 8f.3 / 8f.4 rows: the ICT-MedSeg and S4CVNet step losses, the ICT step driver
+and the batched inference path, against golden vectors produced by the REAL reference (tests/golden/make_golden.py f4)
+and against the CPU oracle on seeded inputs.  Tolerances as in test_gpu_parity.py."""
+import pytest
+import torch
+
+import oracle
+import hpfg_b200 as hb
+from hpfg_b200 import _lib as L
+from tests.golden.common import make_state, make_masks, make_batch, make_predict_case
+from tests.helpers import load_golden, check_summary, rel_l2
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _model(st, in_ch, n_cls, precision):
+    m = hb.UNet(in_ch, n_cls, precision=precision)
+    m.load_state_dict(st)
+    return m.to(DEV)
+
+
+@pytest.mark.parametrize("tag", ["c4", "c2"])
+def test_ict_and_s4cv_losses_vs_reference_golden(tag):
+    g = load_golden("f4_losses.pt")[tag]
+    n_l, n_m, C, H, W = g["shape"]
+    ict = g["ict"]
+    s = ict["student"].to(DEV).requires_grad_(True)
+    l = hb.ict_loss(s, ict["teacher"].to(DEV), ict["mix"].to(DEV), ict["y"].to(DEV), ict["w"])
+    (gr,) = torch.autograd.grad(l, s)
+    assert abs(l.item() - ict["loss"]) / abs(ict["loss"]) < 1e-5
+    assert rel_l2(gr, ict["grad"]) < 1e-5
+    r = hb.ict_loss_raw(s.detach(), ict["teacher"].to(DEV), ict["mix"].to(DEV), ict["y"].to(DEV), n_l, cons_weight=ict["w"])
+    assert abs(r["scalars"][1].item() - ict["sup"]) / ict["sup"] < 1e-5
+    assert abs(r["scalars"][2].item() - ict["cons"]) / ict["cons"] < 1e-5
+    wdev = torch.tensor([ict["w"]], device=DEV, dtype=torch.float32)          # device-value variant (graph replay)
+    r2 = hb.ict_loss_raw(s.detach(), ict["teacher"].to(DEV), ict["mix"].to(DEV), ict["y"].to(DEV), n_l, cons_weight_dev=wdev)
+    assert torch.equal(r2["dstudent"], r["dstudent"]) and torch.equal(r2["scalars"], r["scalars"])
+    s4 = g["s4cv"]
+    y = s4["y"].to(DEV)
+    for branch in ("early", "late"):
+        b = s4[branch]
+        o1, o2 = s4["logits1"].to(DEV).requires_grad_(True), s4["logits2"].to(DEV).requires_grad_(True)
+        t = s4["teacher"].to(DEV) if b["cur_itrs"] >= 1000 else None
+        l = hb.s4cvnet_loss(o1, o2, t, y, b["cps_weight"], b["mt_weight"])
+        g1, g2 = torch.autograd.grad(l, [o1, o2])
+        assert abs(l.item() - b["loss"]) / abs(b["loss"]) < 1e-5
+        assert rel_l2(g1, b["grad1"]) < 1e-5 and rel_l2(g2, b["grad2"]) < 1e-5
+        r = hb.s4cv_loss_raw(o1.detach(), o2.detach(), t, y, n_l, cps_weight=b["cps_weight"], mt_weight=b["mt_weight"],
+                             want_pseudo=True)
+        assert torch.equal(r["pseudo1"].cpu(), b["pl1"]) and torch.equal(r["pseudo2"].cpu(), b["pl2"])
+        assert abs(r["scalars"][1].item() - b["sup"]) / b["sup"] < 1e-5
+        assert abs(r["scalars"][2].item() - b["semi"]) / b["semi"] < 1e-5
+        wdev = torch.tensor([b["cps_weight"], b["mt_weight"]], device=DEV, dtype=torch.float32)
+        r2 = hb.s4cv_loss_raw(o1.detach(), o2.detach(), t, y, n_l, weights_dev=wdev)
+        assert torch.equal(r2["dstudent"], r["dstudent"]) and torch.equal(r2["dother"], r["dother"])
+
+
+def test_ict_mix_and_argmax_kernels_exact():
+    g = torch.Generator().manual_seed(11)
+    a, b = torch.rand(5, 1, 224, 224, generator=g), torch.rand(5, 1, 224, 224, generator=g)
+    lam = torch.rand(5, 1, 1, 1, generator=g)
+    got = hb.ict_mix_inputs(a.to(DEV), b.to(DEV), lam.to(DEV))
+    assert torch.equal(got.cpu(), a * (1.0 - lam) + b * lam)                  # 2022_02...:117, bit-exact
+    for C in (2, 4, 7):
+        z = 3 * torch.randn(3, C, 32, 40, generator=g)
+        z[0, :, :4] = 0.25                                                      # exact ties -> first maximum
+        z[1, 1:, 5] = z[1, :1, 5]
+        ref = torch.argmax(torch.softmax(z, dim=1), dim=1)
+        assert torch.equal(hb.argmax_labels(z.to(DEV)).cpu(), ref)
+        assert torch.equal(hb.argmax_labels(z.to(DEV), dtype=torch.uint8).cpu().long(), ref)
+    with pytest.raises(L.HpfgError):
+        hb.argmax_labels(torch.zeros(1, 9, 8, 8, device=DEV))                  # more classes than the kernels carry
+
+
+def test_ict_loss_full_size_properties():
+    """At the YAML shape (8 labeled + 24 unlabeled -> 8 + 12 mixed, 4x224x224): against the oracle on the same seeded
+    logits, plus the size-independent properties that every pixel's gradient sums to zero over classes and that
+    lambda = 0 / 1 reduce the ICT term to the Mean-Teacher term against one teacher half."""
+    g = torch.Generator().manual_seed(6)
+    n_l, n_m = 8, 12
+    s = 2 * torch.randn(n_l + n_m, 4, 224, 224, generator=g)
+    t = 2 * torch.randn(2 * n_m, 4, 224, 224, generator=g)
+    y = torch.randint(0, 4, (n_l, 224, 224), generator=g)
+    lam = torch.rand(n_m, generator=g)
+    sr = s.clone().requires_grad_(True)
+    sup, cons = oracle.ict_losses(sr, t, lam, y, n_l, 4)
+    lo = sup + 0.05 * cons
+    (go,) = torch.autograd.grad(lo, sr)
+    sd, td, yd = s.to(DEV), t.to(DEV), y.to(DEV)
+    r = hb.ict_loss_raw(sd, td, lam.to(DEV), yd, n_l, cons_weight=0.05)
+    assert abs(r["scalars"][0].item() - lo.item()) / lo.item() < 1e-5
+    assert rel_l2(r["dstudent"], go) < 1e-5
+    assert r["dstudent"].sum(dim=1).abs().max().item() < 1e-9
+    for v, half in ((0.0, td[:n_m]), (1.0, td[n_m:])):
+        ri = hb.ict_loss_raw(sd, td, torch.full((n_m,), v, device=DEV), yd, n_l, cons_weight=0.05)
+        rm = hb.ssl_loss_raw(L.LOSS_MT, sd, half, yd, n_l, cons_weight=0.05)
+        assert rel_l2(ri["dstudent"], rm["dstudent"]) < 1e-6
+        assert abs(ri["scalars"][0].item() - rm["scalars"][0].item()) < 1e-6
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_ict_steps_vs_reference_golden(precision):
+    g = load_golden("ict_steps_acdc.pt")
+    c = g["cfg"]
+    f32 = precision == "fp32"
+    student = _model(make_state(c["in_ch"], c["n_cls"], c["seed"]), c["in_ch"], c["n_cls"], precision)
+    teacher = _model(make_state(c["in_ch"], c["n_cls"], c["seed"] + 7), c["in_ch"], c["n_cls"], precision)
+    step = hb.ICTStep(student, teacher)
+    n_m = c["n_u"] // 2
+    for i, rec in enumerate(g["steps"]):
+        it = i + 1
+        x_l, x_u, y = make_batch(c["n_l"], c["n_u"], c["in_ch"], c["n_cls"], c["h"], c["w"], c["seed"] + 100 * it)
+        student.set_dropout_masks(make_masks(c["n_l"] + n_m, c["h"], c["w"], c["seed"] + 100 * it + 1))
+        teacher.set_dropout_masks(make_masks(n_m, c["h"], c["w"], c["seed"] + 100 * it + 2))
+        lam = torch.rand(n_m, 1, 1, 1, generator=torch.Generator().manual_seed(c["seed"] + 100 * it + 3))
+        loss = step.step(torch.cat([x_l, x_u]).to(DEV), y.to(DEV), lam)
+        assert abs(loss.item() - rec["loss"]) / rec["loss"] < (1e-5 if f32 else 1e-3)
+        assert step.last["lr"] == pytest.approx(rec["lr"], rel=1e-12) and step.last["w"] == pytest.approx(rec["w"], rel=1e-12)
+        sc = step.last["scalars"]
+        assert abs(sc[2].item() - rec["cons"]) / rec["cons"] < (1e-4 if f32 else 1e-1)
+        check_summary(step.last["logits"], rec["logits"], rtol=1e-5 if f32 else 3e-2, what="logits")
+        check_summary(step.last["teacher_logits"], rec["teacher_logits"], rtol=1e-5 if f32 else 3e-2, what="teacher logits")
+        if f32:
+            sd, td = student.state_dict(), teacher.state_dict()
+            assert torch.allclose(sd["decoder.out_conv.weight"].cpu(), rec["student_out_conv"], atol=2e-6)
+            assert torch.allclose(td["decoder.out_conv.weight"].cpu(), rec["teacher_out_conv"], atol=2e-6)
+            assert torch.allclose(td["encoder.in_conv.conv_conv.1.running_mean"].cpu(), rec["teacher_rm"], atol=1e-6)
+            assert abs(float(student.flat_params.double().sum()) - rec["student_sum"]) < 1e-3
+            assert abs(float(teacher.flat_params.double().sum()) - rec["teacher_sum"]) < 1e-3
+    assert int(teacher.bn_counters[0]) == 2 * len(g["steps"])                 # two teacher forwards per step (:123-124)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_predict_volume_vs_reference_golden(precision):
+    """val.py:268-281: slice-by-slice eval-mode argmax labels of the real reference vs one batched predict_volume call."""
+    g = load_golden("predict_acdc.pt")
+    c = g["cfg"]
+    st, vol = make_predict_case(c["in_ch"], c["n_cls"], c["n"], c["h"], c["w"], c["seed"])
+    st.update(g["buffers"])
+    m = _model(st, c["in_ch"], c["n_cls"], precision)
+    m.train()
+    labels = hb.predict_volume(m, vol.to(DEV))
+    assert not m.training and labels.dtype == torch.int64 and tuple(labels.shape) == (c["n"], c["h"], c["w"])
+    ref, margin = g["labels"].long(), g["margin"].float()
+    agree = (labels.cpu() == ref).float().mean().item()
+    if precision == "fp32":
+        assert torch.equal(labels.cpu()[margin > 1e-3], ref[margin > 1e-3]) and agree > 0.999
+    else:
+        assert agree > 0.95, agree                   # bf16 activations under a x40 output conv: near-ties may flip
+        sure = margin > 0.5
+        assert (labels.cpu()[sure] == ref[sure]).float().mean().item() > 0.995
+    chunked = hb.predict_volume(m, vol.to(DEV), max_batch=2, dtype=torch.uint8)   # chunking does not change eval labels
+    assert (chunked.long() == labels).float().mean().item() > 0.9999

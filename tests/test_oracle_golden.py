@@ -117,3 +117,64 @@ def test_mt_steps(tag):
         ssum = sum(student[k].double().sum().item() for k in names)
         tsum = sum(teacher[k].double().sum().item() for k in names)
         assert math.isclose(ssum, rec["student_sum"], abs_tol=1e-3) and math.isclose(tsum, rec["teacher_sum"], abs_tol=1e-3)
+
+
+# ---- ICT-MedSeg, S4CVNet, inference ----------------------------------------------------
+@pytest.mark.parametrize("tag", ["c4", "c2"])
+def test_f4_losses(tag):
+    g = load_golden("f4_losses.pt")[tag]
+    n_l, n_m, C, H, W = g["shape"]
+    ict = g["ict"]
+    s = ict["student"].clone().requires_grad_(True)
+    sup, cons = oracle.ict_losses(s, ict["teacher"], ict["mix"], ict["y"], n_l, C)
+    l = sup + ict["w"] * cons
+    (gr,) = torch.autograd.grad(l, s)
+    assert abs(l.item() - ict["loss"]) < 1e-6 and abs(cons.item() - ict["cons"]) < 1e-8
+    assert rel_l2(gr, ict["grad"]) < 1e-6
+    s4 = g["s4cv"]
+    for branch in ("early", "late"):
+        b = s4[branch]
+        o1, o2 = s4["logits1"].clone().requires_grad_(True), s4["logits2"].clone().requires_grad_(True)
+        t = s4["teacher"] if b["cur_itrs"] >= 1000 else None
+        l, lsup, lsemi, pl1, pl2 = oracle.s4cv_losses(o1, o2, t, s4["y"], n_l, C, b["cps_weight"], b["mt_weight"])
+        g1, g2 = torch.autograd.grad(l, [o1, o2])
+        assert torch.equal(pl1, b["pl1"]) and torch.equal(pl2, b["pl2"])
+        assert abs(l.item() - b["loss"]) < 2e-6 and abs(lsemi.item() - b["semi"]) < 2e-6
+        assert rel_l2(g1, b["grad1"]) < 1e-6 and rel_l2(g2, b["grad2"]) < 1e-6
+
+
+def test_ict_steps():
+    g = load_golden("ict_steps_acdc.pt")
+    c = g["cfg"]
+    student = make_state(c["in_ch"], c["n_cls"], c["seed"])
+    teacher = make_state(c["in_ch"], c["n_cls"], c["seed"] + 7)
+    opt = oracle.SGDState()
+    n_m = c["n_u"] // 2
+    for i, rec in enumerate(g["steps"]):
+        it = i + 1
+        x_l, x_u, y = make_batch(c["n_l"], c["n_u"], c["in_ch"], c["n_cls"], c["h"], c["w"], c["seed"] + 100 * it)
+        ms = make_masks(c["n_l"] + n_m, c["h"], c["w"], c["seed"] + 100 * it + 1)
+        mt = make_masks(n_m, c["h"], c["w"], c["seed"] + 100 * it + 2)
+        lam = torch.rand(n_m, 1, 1, 1, generator=torch.Generator().manual_seed(c["seed"] + 100 * it + 3))
+        r = oracle.ict_step(student, teacher, opt, x_l, x_u, y, it, lam, student_masks=ms, teacher_masks=[mt, mt])
+        assert r["loss"] == pytest.approx(rec["loss"], abs=2e-6)
+        assert r["loss_cons"] == pytest.approx(rec["cons"], rel=1e-4)
+        assert r["lr"] == pytest.approx(rec["lr"], rel=1e-12) and r["w"] == pytest.approx(rec["w"], rel=1e-12)
+        check_summary(r["logits"], rec["logits"], rtol=1e-5, atol=1e-6, what="logits")
+        check_summary(r["teacher_logits"], rec["teacher_logits"], rtol=1e-5, atol=1e-6, what="teacher logits")
+        assert torch.allclose(student["decoder.out_conv.weight"], rec["student_out_conv"], atol=1e-6)
+        assert torch.allclose(teacher["decoder.out_conv.weight"], rec["teacher_out_conv"], atol=1e-6)
+        assert torch.allclose(teacher["encoder.in_conv.conv_conv.1.running_mean"], rec["teacher_rm"], atol=1e-6)
+
+
+def test_predict_labels():
+    from tests.golden.common import make_predict_case
+    g = load_golden("predict_acdc.pt")
+    c = g["cfg"]
+    st, vol = make_predict_case(c["in_ch"], c["n_cls"], c["n"], c["h"], c["w"], c["seed"])
+    st.update(g["buffers"])
+    soft = torch.softmax(oracle.unet_forward(st, vol.unsqueeze(1), False), dim=1)     # one batch == slice by slice in eval
+    labels = torch.argmax(soft, dim=1)
+    sure = g["margin"].float() > 1e-3
+    assert torch.equal(labels[sure], g["labels"].long()[sure])
+    assert (labels == g["labels"].long()).float().mean().item() > 0.999
