@@ -31,6 +31,7 @@ struct LossArgs {
     float cons_weight2;             // S4CV: weight of the Mean-Teacher MSE terms (cons_weight = weight of the pseudo Dice terms)
     const float *cons_weight_dev;   // optional device scalar overriding cons_weight (CUDA-graph replays)
     const float *cons_weight2_dev;  // same for cons_weight2
+    const float *uamt_threshold_dev;   // same for uamt_threshold
     float class_w[kMaxC];
     float *dstudent, *dother, *scalars;
     int64_t *pseudo1, *pseudo2;
@@ -123,6 +124,7 @@ template <int C, int MODE>
 __global__ void __launch_bounds__(256, MODE == HPFG_LOSS_S4CV ? 1 : 2) loss_reduce_kernel(LossArgs A) {
     pdl_prologue();
     constexpr bool TWO = MODE == HPFG_LOSS_CPS || MODE == HPFG_LOSS_S4CV;   // two student networks
+    if (MODE == HPFG_LOSS_UAMT && A.uamt_threshold_dev) A.uamt_threshold = *A.uamt_threshold_dev;
     constexpr int NS = 3 * C + 2;
     __shared__ float smem[8 * (2 * NS + 3)];
     __shared__ int slots[2 * NS + 3];
@@ -608,7 +610,8 @@ static int ssl_loss_impl(int mode, const float *student, const float *other, con
                          int width, float cons_weight, const float *cons_weight_dev, float uamt_threshold,
                          const float *class_weights_host, float ce_coef, float dice_coef, float *dstudent, float *dother,
                          float *scalars_out, int64_t *pseudo1, int64_t *pseudo2, void *workspace, void *stream,
-                         const float *mix = nullptr, float cons_weight2 = 0.f, const float *cons_weight2_dev = nullptr) {
+                         const float *mix = nullptr, float cons_weight2 = 0.f, const float *cons_weight2_dev = nullptr,
+                         const float *uamt_threshold_dev = nullptr) {
     HPFG_REQUIRE(mode >= HPFG_LOSS_SUP && mode <= HPFG_LOSS_S4CV, "hpfg_ssl_loss: unknown mode");
     HPFG_REQUIRE(student && dstudent && scalars_out && workspace, "hpfg_ssl_loss: null buffer");
     HPFG_REQUIRE(n_l >= 0 && n_u >= 0 && n_l + n_u > 0, "hpfg_ssl_loss: empty batch");
@@ -625,6 +628,7 @@ static int ssl_loss_impl(int mode, const float *student, const float *other, con
     A.mode = mode; A.n_l = n_l; A.n_u = n_u; A.hw = height * width; A.mc_passes = mc_passes;
     A.student = student; A.other = other; A.mc = mc_logits; A.labels = labels;
     A.mix = mix; A.cons_weight2 = cons_weight2; A.cons_weight2_dev = cons_weight2_dev;
+    A.uamt_threshold_dev = uamt_threshold_dev;
     A.cons_weight = cons_weight; A.cons_weight_dev = cons_weight_dev; A.uamt_threshold = uamt_threshold; A.ce_coef = ce_coef; A.dice_coef = dice_coef;
     for (int c = 0; c < kMaxC; ++c) A.class_w[c] = (class_weights_host && c < num_classes) ? class_weights_host[c] : 1.f;
     A.dstudent = dstudent; A.dother = dother; A.scalars = scalars_out; A.pseudo1 = pseudo1; A.pseudo2 = pseudo2;
@@ -665,6 +669,19 @@ extern "C" int hpfg_ssl_loss_dv(int mode, const float *student, const float *oth
     return ssl_loss_impl(mode, student, other, mc_logits, mc_passes, labels, n_l, n_u, num_classes, height, width, 0.f, cons_weight_dev,
                          uamt_threshold, class_weights_host, ce_coef, dice_coef, dstudent, dother, scalars_out, pseudo1, pseudo2,
                          workspace, stream);
+}
+
+extern "C" int hpfg_ssl_loss_dv2(int mode, const float *student, const float *other, const float *mc_logits,
+                                 int mc_passes, const int64_t *labels, int n_l, int n_u, int num_classes, int height,
+                                 int width, const float *cons_weight_dev, const float *uamt_threshold_dev,
+                                 const float *class_weights_host, float ce_coef, float dice_coef, float *dstudent,
+                                 float *dother, float *scalars_out, int64_t *pseudo1, int64_t *pseudo2, void *workspace,
+                                 void *stream) {
+    HPFG_REQUIRE(cons_weight_dev && uamt_threshold_dev, "hpfg_ssl_loss_dv2: null device scalar");
+    HPFG_REQUIRE(mode <= HPFG_LOSS_UAMT, "hpfg_ssl_loss_dv2: use hpfg_ict_loss / hpfg_s4cv_loss for the ICT / S4CV modes");
+    return ssl_loss_impl(mode, student, other, mc_logits, mc_passes, labels, n_l, n_u, num_classes, height, width, 0.f, cons_weight_dev,
+                         0.f, class_weights_host, ce_coef, dice_coef, dstudent, dother, scalars_out, pseudo1, pseudo2,
+                         workspace, stream, nullptr, 0.f, nullptr, uamt_threshold_dev);
 }
 
 extern "C" int hpfg_dice_loss(const float *inputs, const int64_t *target, int n, int num_classes, int height,

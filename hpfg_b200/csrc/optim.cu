@@ -55,7 +55,10 @@ __global__ void __launch_bounds__(256) sgd_kernel(float *__restrict__ param, con
                                                   float *__restrict__ buf, float *__restrict__ ema, int64_t n,
                                                   SgdArgs a) {
     pdl_prologue();
-    if (a.dyn) { a.lr = a.dyn[0]; a.ema_alpha = a.dyn[1]; a.ema_one_minus = a.dyn[2]; }
+    if (a.dyn) {
+        a.lr = a.dyn[0];
+        if (kEma) { a.ema_alpha = a.dyn[1]; a.ema_one_minus = a.dyn[2]; }
+    }
     const int64_t n4 = n >> 2;
     const int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
@@ -144,6 +147,20 @@ extern "C" int hpfg_sgd_momentum_ema_dv(float *param, const float *grad, float *
     ProfScope _prof(PROF_OPTIM, (cudaStream_t)stream);
     SgdArgs a{0.f, momentum, weight_decay, grad_scale, 0.f, 0.f, first_step, lr_alpha_dev};
     HPFG_CUDA_CHECK(launch_pdl(sgd_kernel<true>, flat_grid(n), 256, 0, (cudaStream_t)stream, param, grad, momentum_buf, ema, n, a));
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+extern "C" int hpfg_sgd_momentum_dv(float *param, const float *grad, float *momentum_buf, int64_t n, float momentum,
+                                    float weight_decay, float grad_scale, int first_step, const float *lr_dev,
+                                    void *stream) {
+    HPFG_REQUIRE(param && grad && momentum_buf && lr_dev && n >= 0, "hpfg_sgd_momentum_dv: null buffer");
+    HPFG_REQUIRE(aligned16(param) && aligned16(grad) && aligned16(momentum_buf),
+                 "hpfg_sgd_momentum_dv: buffers must be 16-byte aligned");
+    if (n == 0) return HPFG_OK;
+    ProfScope _prof(PROF_OPTIM, (cudaStream_t)stream);
+    SgdArgs a{0.f, momentum, weight_decay, grad_scale, 0.f, 0.f, first_step, lr_dev};
+    HPFG_CUDA_CHECK(launch_pdl(sgd_kernel<false>, flat_grid(n), 256, 0, (cudaStream_t)stream, param, grad, momentum_buf, nullptr, n, a));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }

@@ -72,6 +72,98 @@ class _StepBase:
         self._comm = None
         self.last = {}
 
+    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
+    _graph_enabled = False
+    _graph_dp = False
+    kernels_per_replay = 0
+    replayed_kernels = 0          # kernels executed through graph replays (the library's own counter sees host launches only)
+
+    def enable_graph(self, enabled=True, data_parallel=False):
+        """From the second iteration on, replay the step as ONE captured CUDA graph (all forwards on their streams, the
+        fused loss, backward with its side-stream weight gradients, fused SGD(+EMA)).  The scalars that change per
+        iteration -- learning rate, EMA alpha, consistency weight, UAMT threshold, dropout Philox offsets -- live in a
+        small device block that is refreshed before every replay (the `_dv` entry points read them at run time).
+        data_parallel=True also captures the bucketed NCCL all-reduces of a multi-process run (measured on 2/4/8 B200
+        for the Mean-Teacher step); by default a data-parallel step stays eager."""
+        self._graph_enabled = bool(enabled)
+        self._graph_dp = bool(data_parallel)      # also capture the NCCL bucket all-reduces (torch >= 2.x captures NCCL work)
+        if not enabled:
+            self._graph = None
+            self._ggraph = None
+
+    def _use_graph(self):
+        return self._graph_enabled and self.cur_itrs >= 2 and (self.world == 1 or self._graph_dp)
+
+    def _graph_replay(self, inputs, dyn_f, fwd_models, body):
+        """Generic capture-once / replay driver (CPS, UAMT, ICT; Mean-Teacher keeps its own copy below).
+        inputs: tensors copied into static buffers before each replay; dyn_f: python floats for the device block
+        (fp32); fwd_models: one entry per network forward in the eager call order -> one Philox-offset slot each (the
+        offsets advance exactly as the eager path advances them); body(static_inputs, dyn_f_dev, dyn_o_dev) enqueues the
+        step with the `_dv` entry points and returns its output dict (static tensors)."""
+        dev = inputs[0].device
+        sig = tuple((tuple(t.shape), t.dtype) for t in inputs) + (len(dyn_f), len(fwd_models))
+        if getattr(self, "_gsig", None) != sig:
+            self._gin = [torch.empty_like(t) for t in inputs]
+            self._gf = torch.zeros(len(dyn_f), device=dev, dtype=torch.float32)
+            self._go = torch.zeros(len(fwd_models), device=dev, dtype=torch.int64)
+            self._gf_host = torch.zeros(len(dyn_f), dtype=torch.float32).pin_memory()
+            self._go_host = torch.zeros(len(fwd_models), dtype=torch.int64).pin_memory()
+            self._ggraph, self._gsig = None, sig
+        for i, v in enumerate(dyn_f):
+            self._gf_host[i] = v
+        for i, m in enumerate(fwd_models):
+            self._go_host[i] = m._philox_offset
+            if m.training:
+                m._philox_offset += 8
+        self._gf.copy_(self._gf_host, non_blocking=True)
+        self._go.copy_(self._go_host, non_blocking=True)
+        for s, t in zip(self._gin, inputs):
+            s.copy_(t, non_blocking=True)
+        if self._ggraph is None:
+            for m in fwd_models:
+                m.ensure_flat()
+            g = torch.cuda.CUDAGraph()
+            n0 = L.lib().hpfg_launch_count()
+            try:
+                with torch.cuda.graph(g):
+                    self._gout = body(self._gin, self._gf, self._go)
+            except Exception as exc:        # capture not possible here: stay eager on the same device-value path
+                import warnings
+                warnings.warn("hpfg_b200: CUDA-graph capture of the step failed (%s); falling back to eager launches" % exc)
+                self._graph_enabled, self._ggraph = False, None
+                torch.cuda.synchronize()
+                return body(self._gin, self._gf, self._go)
+            self._ggraph = g
+            self.kernels_per_replay = int(L.lib().hpfg_launch_count() - n0)   # kernel nodes of the captured step
+        self._ggraph.replay()
+        self.replayed_kernels += self.kernels_per_replay
+        return self._gout
+
+    def _forward_dv(self, model, x, save, out, offset_dev):
+        plan = model._acquire_plan(x, need_grad=save)
+        return plan, model._run_forward(plan, x, save=save, out=out, offset_dev=offset_dev)
+
+    def _sgd_dv(self, model, grads, buf, dyn_f, ema_model=None):
+        """SGD(+EMA) with {lr, ema_alpha, 1-ema_alpha} read from the device block (first_step = 0: replays start at
+        iteration 2)."""
+        n = model.flat_params.numel()
+        st = L.stream_ptr(grads.device)
+        if ema_model is None:
+            L.check(L.lib().hpfg_sgd_momentum_dv(L.ptr(model.flat_params), L.ptr(grads), L.ptr(buf), n, self.momentum,
+                                                 self.weight_decay, 1.0 / self.world, 0, L.ptr(dyn_f), st),
+                    "hpfg_sgd_momentum_dv")
+        else:
+            L.check(L.lib().hpfg_sgd_momentum_ema_dv(L.ptr(model.flat_params), L.ptr(grads), L.ptr(buf),
+                                                     L.ptr(ema_model.flat_params), n, self.momentum, self.weight_decay,
+                                                     1.0 / self.world, 0, L.ptr(dyn_f), st), "hpfg_sgd_momentum_ema_dv")
+
+    def _dyn_scalars(self, ema_decay=None):
+        """[lr, ema_alpha, 1 - ema_alpha (fp32 subtraction, as the by-value entry point), consistency weight]."""
+        lr = medical_lr(self.cur_itrs, self.base_lr, self.total_itrs)
+        alpha = min(1 - 1 / (self.cur_itrs + 1), ema_decay) if ema_decay is not None else 0.0
+        w = self._consistency_weight()
+        return [lr, alpha, float(1.0 - torch.tensor(alpha, dtype=torch.float32)), w]
+
     def _side_stream(self, device):
         if getattr(self, "_side", None) is None:
             self._side = torch.cuda.Stream(device=device)
@@ -146,7 +238,7 @@ class MeanTeacherStep(_StepBase):
     def step(self, x, labels):
         """x: [n_l+n_u, C, H, W] fp32 CUDA (labeled slices first); labels: [n_l, H, W] int64 CUDA."""
         self.cur_itrs += 1
-        if self._graph_enabled and self.cur_itrs >= 2 and (self.world == 1 or self._graph_dp):
+        if self._use_graph():
             return self._step_graph(x, labels)
         n_l = labels.shape[0]
         # the teacher forward is independent of the student forward: it runs on a side stream so that each network's
@@ -166,25 +258,6 @@ class MeanTeacherStep(_StepBase):
         lr = self._sgd(self.model, self.grads, self.mom, self.ema_model, alpha)
         self.last = dict(scalars=r["scalars"], lr=lr, w=w, logits=out, teacher_logits=t_out)
         return r["scalars"][0]
-
-    # ------------------------------------------------------------------ CUDA-graph replay of the whole step
-    _graph_enabled = False
-    kernels_per_replay = 0
-    replayed_kernels = 0          # kernels executed through graph replays (the library's own counter sees host launches only)
-
-    _graph_dp = False
-
-    def enable_graph(self, enabled=True, data_parallel=False):
-        """From the second iteration on, replay the step as ONE captured CUDA graph (both forwards on two streams, the
-        fused loss, backward with its side-stream weight gradients, fused SGD+EMA).  The scalars that change per
-        iteration -- learning rate, EMA alpha, consistency weight, dropout Philox offsets -- live in a small device
-        block that is refreshed before every replay (the `_dv` entry points read them at run time).
-        data_parallel=True also captures the bucketed NCCL all-reduces of a multi-process run (measured on 2/4/8 B200);
-        by default a data-parallel step stays eager."""
-        self._graph_enabled = bool(enabled)
-        self._graph_dp = bool(data_parallel)      # also capture the NCCL bucket all-reduces (torch >= 2.x captures NCCL work)
-        if not enabled:
-            self._graph = None
 
     def _step_graph(self, x, labels):
         dev = x.device
@@ -270,6 +343,11 @@ class CPSStep(_StepBase):
 
     def step(self, x, labels):
         self.cur_itrs += 1
+        if self._use_graph():
+            dyn = self._dyn_scalars()
+            out = self._graph_replay([x, labels], dyn, [self.m1, self.m2], self._body_dv)
+            self.last = dict(scalars=out["scalars"], lr=dyn[0], w=dyn[3], logits1=out["logits1"], logits2=out["logits2"])
+            return out["scalars"][0]
         n_l = labels.shape[0]
         # the two networks are independent except for the loss: network 2 runs on a side stream (forward, then backward + SGD)
         main = torch.cuda.current_stream(x.device)
@@ -291,6 +369,27 @@ class CPSStep(_StepBase):
         main.wait_stream(side)
         self.last = dict(scalars=r["scalars"], lr=lr, w=w, logits1=o1, logits2=o2)
         return r["scalars"][0]
+
+
+    def _body_dv(self, ins, f, o):
+        x, labels = ins
+        n_l, dev = labels.shape[0], x.device
+        main, side = torch.cuda.current_stream(dev), self._side_stream(dev)
+        shape = (x.shape[0], self.num_classes, x.shape[2], x.shape[3])
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            p2, o2 = self._forward_dv(self.m2, x, True, self._persistent("o2", shape, dev), o[1:2])
+        p1, o1 = self._forward_dv(self.m1, x, True, self._persistent("o1", shape, dev), o[0:1])
+        main.wait_stream(side)
+        r = ssl_loss_raw(L.LOSS_CPS, o1, o2, labels, n_l, cons_weight_dev=f[3:4], want_pseudo=False)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            self._backward(self.m2, p2, r["dother"], self.g2)
+            self._sgd_dv(self.m2, self.g2, self.b2, f)
+        self._backward(self.m1, p1, r["dstudent"], self.g1)
+        self._sgd_dv(self.m1, self.g1, self.b1, f)
+        main.wait_stream(side)
+        return dict(scalars=r["scalars"], logits1=o1, logits2=o2)
 
 
 class UAMTStep(_StepBase):
@@ -318,6 +417,16 @@ class UAMTStep(_StepBase):
         if noise is None:
             noise = self.make_noise(x_u)
         xr = x_u.repeat(2, 1, 1, 1)
+        if self._use_graph():
+            if mc_noise is None:
+                mc_noise = torch.clamp(torch.randn((self.T // 2,) + tuple(xr.shape), device=x.device, dtype=x.dtype) * 0.1, -0.2, 0.2)
+            dyn = self._dyn_scalars(self.ema_decay)
+            thr = (0.75 + 0.25 * sigmoid_rampup(self.cur_itrs, self.total_itrs)) * math.log(2)
+            out = self._graph_replay([x, labels, noise, mc_noise.contiguous()], dyn + [thr],
+                                     [self.model] + [self.ema_model] * (1 + self.T // 2), self._body_dv)
+            self.last = dict(scalars=out["scalars"], lr=dyn[0], w=dyn[3], threshold=thr, logits=out["logits"],
+                             teacher_logits=out["teacher_logits"], mc_logits=out["mc_logits"])
+            return out["scalars"][0]
         noises = [mc_noise[i] if mc_noise is not None else self.make_noise(xr) for i in range(self.T // 2)]
         x_t = (x_u + noise).contiguous()
         x_mc = [(xr + nz).contiguous() for nz in noises]
@@ -342,6 +451,31 @@ class UAMTStep(_StepBase):
         lr = self._sgd(self.model, self.grads, self.mom, self.ema_model, alpha)
         self.last = dict(scalars=r["scalars"], lr=lr, w=w, threshold=thr, logits=out, teacher_logits=t_out, mc_logits=mc)
         return r["scalars"][0]
+
+
+    def _body_dv(self, ins, f, o):
+        x, labels, noise, mc_noise = ins
+        n_l, dev = labels.shape[0], x.device
+        x_u = x[n_l:]
+        n_u = x_u.shape[0]
+        xr = x_u.repeat(2, 1, 1, 1)
+        x_t = (x_u + noise).contiguous()
+        x_mc = [(xr + mc_noise[i]).contiguous() for i in range(self.T // 2)]
+        ncls, hh, ww = self.num_classes, x.shape[2], x.shape[3]
+        mc = self._persistent("mc", (self.T * n_u, ncls, hh, ww), dev)
+        main, side = torch.cuda.current_stream(dev), self._side_stream(dev)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):
+            _, t_out = self._forward_dv(self.ema_model, x_t, False, self._persistent("t_out", (n_u, ncls, hh, ww), dev), o[1:2])
+            for i in range(self.T // 2):
+                self._forward_dv(self.ema_model, x_mc[i], False, mc[2 * n_u * i:2 * n_u * (i + 1)], o[2 + i:3 + i])
+        plan, out = self._forward_dv(self.model, x, True, self._persistent("s_out", (x.shape[0], ncls, hh, ww), dev), o[0:1])
+        main.wait_stream(side)
+        r = ssl_loss_raw(L.LOSS_UAMT, out, t_out, labels, n_l, mc_logits=mc, mc_passes=self.T, cons_weight_dev=f[3:4],
+                         uamt_threshold_dev=f[4:5])
+        self._backward(self.model, plan, r["dstudent"], self.grads)
+        self._sgd_dv(self.model, self.grads, self.mom, f, self.ema_model)
+        return dict(scalars=r["scalars"], logits=out, teacher_logits=t_out, mc_logits=mc)
 
 
 class ICTStep(_StepBase):
@@ -376,6 +510,12 @@ class ICTStep(_StepBase):
         if mix_factors is None:
             mix_factors = self.draw_mix_factors(n_m)
         lam = mix_factors.reshape(-1).to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        if self._use_graph():
+            dyn = self._dyn_scalars(self.ema_decay)
+            out = self._graph_replay([x, labels, lam], dyn, [self.model, self.ema_model, self.ema_model], self._body_dv)
+            self.last = dict(scalars=out["scalars"], lr=dyn[0], w=dyn[3], logits=out["logits"],
+                             teacher_logits=out["teacher_logits"], mix_factors=lam)
+            return out["scalars"][0]
         ux0, ux1 = x[n_l:n_l + n_m], x[n_l + n_m:]
         ncls, hh, ww = self.num_classes, x.shape[2], x.shape[3]
         main = torch.cuda.current_stream(dev)
@@ -398,3 +538,26 @@ class ICTStep(_StepBase):
         lr = self._sgd(self.model, self.grads, self.mom, self.ema_model, alpha)
         self.last = dict(scalars=r["scalars"], lr=lr, w=w, logits=out, teacher_logits=t_out, mix_factors=lam)
         return r["scalars"][0]
+
+    def _body_dv(self, ins, f, o):
+        x, labels, lam = ins
+        n_l, dev = labels.shape[0], x.device
+        n_m = (x.shape[0] - n_l) // 2
+        ux0, ux1 = x[n_l:n_l + n_m], x[n_l + n_m:]
+        ncls, hh, ww = self.num_classes, x.shape[2], x.shape[3]
+        main, side = torch.cuda.current_stream(dev), self._side_stream(dev)
+        side.wait_stream(main)
+        t_out = self._persistent("t_out", (2 * n_m, ncls, hh, ww), dev)
+        with torch.cuda.stream(side):
+            self._forward_dv(self.ema_model, ux0, False, t_out[:n_m], o[1:2])
+            self._forward_dv(self.ema_model, ux1, False, t_out[n_m:], o[2:3])
+        x_in = self._persistent("x_in", (n_l + n_m,) + tuple(x.shape[1:]), dev)
+        x_in[:n_l].copy_(x[:n_l])
+        L.check(L.lib().hpfg_ict_mix(L.ptr(ux0), L.ptr(ux1), L.ptr(lam), n_m, ux0[0].numel(), L.ptr(x_in[n_l:]),
+                                     L.stream_ptr(dev)), "hpfg_ict_mix")
+        plan, out = self._forward_dv(self.model, x_in, True, self._persistent("s_out", (n_l + n_m, ncls, hh, ww), dev), o[0:1])
+        main.wait_stream(side)
+        r = ict_loss_raw(out, t_out, lam, labels, n_l, cons_weight_dev=f[3:4])
+        self._backward(self.model, plan, r["dstudent"], self.grads)
+        self._sgd_dv(self.model, self.grads, self.mom, f, self.ema_model)
+        return dict(scalars=r["scalars"], logits=out, teacher_logits=t_out)

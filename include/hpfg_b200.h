@@ -191,6 +191,13 @@ int hpfg_s4cv_loss(const float *logits1, const float *logits2, const float *teac
 int hpfg_argmax_labels(const float *logits, int n, int num_classes, int height, int width, int64_t *labels_i64,
                        uint8_t *labels_u8, void *stream);
 
+/* hpfg_ssl_loss_dv with the UAMT threshold (2019_07...:150, it ramps with the iteration count) read from device memory too. */
+int hpfg_ssl_loss_dv2(int mode, const float *student, const float *other, const float *mc_logits, int mc_passes,
+                      const int64_t *labels, int n_l, int n_u, int num_classes, int height, int width,
+                      const float *cons_weight_dev, const float *uamt_threshold_dev, const float *class_weights,
+                      float ce_coef, float dice_coef, float *dstudent, float *dother, float *scalars_out,
+                      int64_t *pseudo1, int64_t *pseudo2, void *workspace, void *stream);
+
 /* DiceLoss.forward (utils/loss/diceloss.py:178-191) alone: inputs are probabilities (softmax == 0) or
  * logits (softmax != 0); target int64 [n,H,W]; dinputs optional. scalars_out: float[1+C] = {loss, dice_c..}. */
 int hpfg_dice_loss(const float *inputs, const int64_t *target, int n, int num_classes, int height, int width,
@@ -213,6 +220,10 @@ int hpfg_sgd_momentum_ema(float *param, const float *grad, float *momentum_buf, 
 int hpfg_sgd_momentum_ema_dv(float *param, const float *grad, float *momentum_buf, float *ema, int64_t n,
                              float momentum, float weight_decay, float grad_scale, int first_step,
                              const float *lr_alpha_dev, void *stream);
+
+/* lr_dev: device float[1] = {lr} (the CPS networks have no EMA teacher). */
+int hpfg_sgd_momentum_dv(float *param, const float *grad, float *momentum_buf, int64_t n, float momentum,
+                         float weight_decay, float grad_scale, int first_step, const float *lr_dev, void *stream);
 
 #ifdef __cplusplus
 }
