@@ -148,7 +148,10 @@ def test_predict_volume_vs_reference_golden(precision):
         assert torch.equal(labels.cpu()[margin > 1e-3], ref[margin > 1e-3]) and agree > 0.999
     else:
         assert agree > 0.95, agree                   # bf16 activations under a x40 output conv: near-ties may flip
-        sure = margin > 0.5
-        assert (labels.cpu()[sure] == ref[sure]).float().mean().item() > 0.995
+        sure = margin > 0.1                      # top-2 softmax gap of the reference; ~10 % of this fixture's pixels
+        assert sure.sum().item() > 500
+        sure_agree = (labels.cpu()[sure] == ref[sure]).float().mean().item()
+        print("bf16 predict_volume agreement: all pixels %.4f, margin>0.1 %.4f" % (agree, sure_agree))
+        assert sure_agree > 0.98, sure_agree
     chunked = hb.predict_volume(m, vol.to(DEV), max_batch=2, dtype=torch.uint8)   # chunking does not change eval labels
     assert (chunked.long() == labels).float().mean().item() > 0.9999
