@@ -33,6 +33,8 @@ SIGNATURES = {
     "hpfg_unet_forward_dv": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u64, c_vp,
                                      ctypes.POINTER(c_vp), c_vp]),
     "hpfg_unet_backward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
+    "hpfg_unet_bottleneck": (c_int, [c_vp, c_vp, c_vp]),
+    "hpfg_unet_backward_ex": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_vp]),
     "hpfg_unet_num_buckets": (c_int, [c_vp]),
     "hpfg_unet_bucket_range": (c_int, [c_vp, c_int, c_i64p, c_i64p]),
     "hpfg_unet_bucket_wait": (c_int, [c_vp, c_int, c_vp]),

@@ -581,6 +581,69 @@ int nhwc_to_nchw_f32(const T *src, float *dst, int N, int H, int W, int C, const
     return HPFG_OK;
 }
 
+// ------------------------------------------------------- activated feature tap / external gradient (UNet_Plus necks)
+// dst[n,c,y,x] (fp32 NCHW) = leaky(raw[n,y,x,c]*scale[c] + shift[c]): the ConvBlock output the consumers' loaders would
+// build on the fly, materialised for a caller outside the plan (model/unet.py:196,201 feature[-1]).
+template <typename T>
+__global__ void act_nhwc_to_nchw_kernel(const T *__restrict__ raw, const float *__restrict__ scale,
+                                        const float *__restrict__ shift, float *__restrict__ dst, int N, int HW, int C) {
+    pdl_prologue();
+    __shared__ float tile[32][33];      // 32 pixels x 32 channels, transposed through shared memory (both sides coalesced)
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;     // 256 threads: 8 rows per pass
+    for (int r = ty; r < 32; r += 8) {
+        const int pix = p0 + r, c = c0 + tx;
+        float v = 0.f;
+        if (pix < HW && c < C) v = leaky(to_f32(raw[((int64_t)n * HW + pix) * C + c]) * scale[c] + shift[c]);
+        tile[r][tx] = v;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, pix = p0 + tx;
+        if (pix < HW && c < C) dst[((int64_t)n * C + c) * HW + pix] = tile[tx][r];
+    }
+}
+
+template <typename T>
+int act_nhwc_to_nchw_f32(const T *raw, BnState bn, float *dst, int N, int H, int W, int C, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
+    const int HW = H * W;
+    HPFG_CUDA_CHECK(launch_pdl(act_nhwc_to_nchw_kernel<T>, dim3((HW + 31) / 32, (C + 31) / 32, N), 256, 0, s, raw, bn.scale,
+                               bn.shift, dst, N, HW, C));
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+// dst[n,y,x,c] (T NHWC) += src[n,c,y,x] (fp32 NCHW): an external gradient joins the data-gradient chain.
+template <typename T>
+__global__ void add_nchw_to_nhwc_kernel(T *__restrict__ dst, const float *__restrict__ src, int N, int HW, int C) {
+    pdl_prologue();
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z, p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    for (int r = ty; r < 32; r += 8) {
+        const int c = c0 + r, pix = p0 + tx;
+        tile[r][tx] = (pix < HW && c < C) ? src[((int64_t)n * C + c) * HW + pix] : 0.f;
+    }
+    __syncthreads();
+    for (int r = ty; r < 32; r += 8) {
+        const int pix = p0 + r, c = c0 + tx;
+        if (pix < HW && c < C) {
+            T *d = dst + ((int64_t)n * HW + pix) * C + c;
+            *d = from_f32<T>(to_f32(*d) + tile[tx][r]);
+        }
+    }
+}
+
+template <typename T>
+int add_nchw_f32_to_nhwc(T *dst, const float *src, int N, int H, int W, int C, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
+    const int HW = H * W;
+    HPFG_CUDA_CHECK(launch_pdl(add_nchw_to_nhwc_kernel<T>, dim3((HW + 31) / 32, (C + 31) / 32, N), 256, 0, s, dst, src, N, HW, C));
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
 #define INSTANTIATE(T)                                                                                              \
     template int pool_act<T>(const T *, T *, int, int, int, int, BnState, cudaStream_t);                            \
     template int upcat<T>(const T *, BnState, const T *, T *, int, int, int, int, cudaStream_t);                    \
@@ -588,6 +651,8 @@ int nhwc_to_nchw_f32(const T *src, float *dst, int N, int H, int W, int C, const
                            float *, int, cudaStream_t);                                                             \
     template int skip_pool_bwd<T>(const T *, const T *, const T *, BnState, T *, int, int, int, int, cudaStream_t); \
     template int up_bwd<T>(const T *, T *, int, int, int, int, cudaStream_t);                                       \
+    template int act_nhwc_to_nchw_f32<T>(const T *, BnState, float *, int, int, int, int, cudaStream_t);           \
+    template int add_nchw_f32_to_nhwc<T>(T *, const float *, int, int, int, int, cudaStream_t);                      \
     template int nhwc_to_nchw_f32<T>(const T *, float *, int, int, int, int, const float *, cudaStream_t);
 INSTANTIATE(float)
 INSTANTIATE(bf16)

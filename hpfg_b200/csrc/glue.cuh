@@ -57,4 +57,11 @@ int dropout_bits_multi(int n_jobs, uint32_t *const *bits, const uint8_t *const *
 template <typename T>
 int nhwc_to_nchw_f32(const T *src, float *dst, int N, int H, int W, int C, const float *bias, cudaStream_t s);
 
+// activated ConvBlock output leaky(bn(raw)) as fp32 NCHW (feature tap for callers outside the plan), and its adjoint side:
+// an external fp32 NCHW gradient added into a T NHWC gradient buffer
+template <typename T>
+int act_nhwc_to_nchw_f32(const T *raw, BnState bn, float *dst, int N, int H, int W, int C, cudaStream_t s);
+template <typename T>
+int add_nchw_f32_to_nhwc(T *dst, const float *src, int N, int H, int W, int C, cudaStream_t s);
+
 }  // namespace hpfg

@@ -264,7 +264,7 @@ static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_runnin
 
 template <typename T>
 static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dlogits, float *grads, int acc,
-                         cudaStream_t s) {
+                         cudaStream_t s, const float *dbottleneck = nullptr) {
     UNetDesc &d = p->d;
     const int N = p->N, H = p->H, W = p->W;
     const bool tc = p->precision == HPFG_PREC_BF16;
@@ -374,6 +374,9 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
             HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[j == 3 ? 0 : 1], s));
         }
     }
+    // external gradient wrt the activated bottleneck feature (UNet_Plus projection neck, model/unet.py:201): joins the
+    // decoder's gradient before the down4 block is differentiated
+    if (dbottleneck) HPFG_RETURN_IF(add_nchw_f32_to_nhwc<T>((T *)a, dbottleneck, N, H >> 4, W >> 4, kFt[4], s));
     // ---- encoder, down4 .. in_conv
     void *dpooled = nullptr;
     for (int l = 4; l >= 0; --l) {
@@ -554,6 +557,25 @@ extern "C" int hpfg_unet_backward(hpfg_unet_plan_t p, const float *params, const
     cudaStream_t s = (cudaStream_t)stream;
     if (p->precision == HPFG_PREC_FP32) return backward_impl<float>(p, params, dlogits, grads, accumulate, s);
     return backward_impl<bf16>(p, params, dlogits, grads, accumulate, s);
+}
+
+extern "C" int hpfg_unet_backward_ex(hpfg_unet_plan_t p, const float *params, const float *dlogits,
+                                     const float *dbottleneck, float *grads, int accumulate, void *stream) {
+    HPFG_REQUIRE(p && params && dlogits && grads, "hpfg_unet_backward_ex: null argument");
+    HPFG_REQUIRE(p->saved, "hpfg_unet_backward_ex: no training forward with save_for_backward on this plan");
+    cudaStream_t s = (cudaStream_t)stream;
+    if (p->precision == HPFG_PREC_FP32) return backward_impl<float>(p, params, dlogits, grads, accumulate, s, dbottleneck);
+    return backward_impl<bf16>(p, params, dlogits, grads, accumulate, s, dbottleneck);
+}
+
+extern "C" int hpfg_unet_bottleneck(hpfg_unet_plan_t p, float *feature_nchw, void *stream) {
+    HPFG_REQUIRE(p && feature_nchw, "hpfg_unet_bottleneck: null argument");
+    HPFG_REQUIRE(p->saved_x != nullptr, "hpfg_unet_bottleneck: no forward has run on this plan");
+    cudaStream_t s = (cudaStream_t)stream;
+    BnLayer &b = p->d.bns[9];
+    if (p->precision == HPFG_PREC_FP32)
+        return act_nhwc_to_nchw_f32<float>((const float *)b.raw, b.st, feature_nchw, p->N, p->H >> 4, p->W >> 4, kFt[4], s);
+    return act_nhwc_to_nchw_f32<bf16>((const bf16 *)b.raw, b.st, feature_nchw, p->N, p->H >> 4, p->W >> 4, kFt[4], s);
 }
 
 extern "C" int hpfg_unet_num_buckets(hpfg_unet_plan_t p) { return p ? kNumBuckets : 0; }

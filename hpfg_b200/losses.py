@@ -280,3 +280,29 @@ def argmax_labels(logits, dtype=torch.int64):
                                        L.ptr(out) if dtype == torch.uint8 else None, L.stream_ptr(z.device)),
             "hpfg_argmax_labels")
     return out
+
+
+class Dense_Loss(nn.Module):
+    """``Dense_Loss(batch_size, device, temperature)(x, y)`` (utils/loss/dense_loss.py:5-40): SimCLR-style contrastive loss
+    on the (global vector, dense map) pairs the projection necks return.  A [2B, 2B] similarity matrix (B = 32): plain
+    library GEMM + elementwise work of a few kFLOP, kept in torch like the necks themselves."""
+
+    def __init__(self, batch_size=32, device=None, temperature=0.7):
+        super().__init__()
+        self.device, self.batch_size, self.temperature = device, batch_size, temperature
+
+    def contrastive_loss(self, out_1, out_2):
+        out_1 = torch.nn.functional.normalize(out_1, dim=1).flatten(1)
+        out_2 = torch.nn.functional.normalize(out_2, dim=1).flatten(1)
+        out = torch.cat([out_1, out_2], dim=0)
+        sim_matrix = torch.exp(torch.mm(out, out.t().contiguous()) / self.temperature)
+        mask = (torch.ones_like(sim_matrix) - torch.eye(2 * self.batch_size, device=sim_matrix.device)).bool()
+        sim_matrix = sim_matrix.masked_select(mask).view(2 * self.batch_size, -1)
+        pos_sim = torch.exp(torch.sum(out_1 * out_2, dim=-1) / self.temperature)
+        pos_sim = torch.cat([pos_sim, pos_sim], dim=0)
+        return (-torch.log(pos_sim / sim_matrix.sum(dim=-1))).mean()
+
+    def forward(self, x, y):
+        x1, x2 = x
+        y1, y2 = y
+        return 0.5 * (self.contrastive_loss(x1, y1.detach()) + self.contrastive_loss(x2, y2.detach()))

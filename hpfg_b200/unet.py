@@ -68,6 +68,41 @@ class _UNetFunction(torch.autograd.Function):
         return (None, None) + views
 
 
+def _bottleneck(plan, x, num_features=FT_CHNS[-1]):
+    feat = torch.empty((x.shape[0], num_features, x.shape[2] // 16, x.shape[3] // 16), device=x.device, dtype=torch.float32)
+    L.check(L.lib().hpfg_unet_bottleneck(plan.handle, L.ptr(feat), L.stream_ptr(x.device)), "hpfg_unet_bottleneck")
+    return feat
+
+
+class _UNetPlusFunction(torch.autograd.Function):
+    """UNet forward that also returns feature[-1] (model/unet.py:199-201); backward takes both gradients."""
+
+    @staticmethod
+    def forward(ctx, x, module, *params):
+        plan = module._acquire_plan(x, need_grad=True)
+        logits = module._run_forward(plan, x, save=True)
+        feat = _bottleneck(plan, x)
+        plan.busy = True
+        ctx.module, ctx.plan = module, plan
+        ctx.x = x
+        return logits, feat
+
+    @staticmethod
+    def backward(ctx, dlogits, dfeat):
+        m, plan = ctx.module, ctx.plan
+        grads = torch.empty_like(m.flat_params)
+        if dlogits is None:
+            dlogits = torch.zeros((ctx.x.shape[0], m.num_classes) + tuple(ctx.x.shape[2:]), device=grads.device)
+        dfeat = dfeat.contiguous().float() if dfeat is not None else None
+        L.check(L.lib().hpfg_unet_backward_ex(plan.handle, L.ptr(m.flat_params), L.ptr(dlogits.contiguous().float()),
+                                              L.ptr(dfeat), L.ptr(grads), 0, L.stream_ptr(grads.device)),
+                "hpfg_unet_backward_ex")
+        plan.busy = False
+        m.last_flat_grad = grads
+        views = tuple(grads[o:o + n].view(s) for o, n, s in m._layout)
+        return (None, None) + views
+
+
 class UNet(nn.Module):
     """``UNet(in_channels=1, num_classes=4)`` -- same signature as model/unet.py:156."""
 
@@ -102,8 +137,13 @@ class UNet(nn.Module):
     def _bn_modules(self):
         return [m for m in self.modules() if isinstance(m, nn.BatchNorm2d)]
 
+    def _core_parameters(self):
+        """The 82 encoder/decoder parameters that live in the flat buffer (== parameters() for the plain UNet; UNet_Plus
+        adds projection necks, which stay ordinary torch parameters)."""
+        return list(self.encoder.parameters()) + list(self.decoder.parameters())
+
     def _flatten(self):
-        params = list(self.parameters())
+        params = self._core_parameters()
         assert len(params) == L.NUM_PARAMS
         dev = params[0].device
         with torch.no_grad():
@@ -249,10 +289,67 @@ class UNet(nn.Module):
         if self.flat_params.device != x.device:
             raise L.HpfgError("model is on %s but the input is on %s" % (self.flat_params.device, x.device))
         x = x.contiguous().float()
-        need_grad = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self.parameters())
+        need_grad = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self._flat_params_list)
         if need_grad:
-            return _UNetFunction.apply(x, self, *self.parameters())
+            return _UNetFunction.apply(x, self, *self._flat_params_list)
         return self._run_forward(self._acquire_plan(x, False), x, save=False)
+
+
+class projection_conv(nn.Module):
+    """The DenseCL-style neck of model/unet.py:120-152 (same parameter names and shapes).  A global-average-pool +
+    fc-relu-fc branch and an adaptive-pool(s x s) + 1x1conv-relu-1x1conv branch on a [N, C, <=14, <=14] map: a few MFLOP
+    of plain library GEMMs, left to torch; the U-Net under it is what runs on the hand-written kernels."""
+
+    def __init__(self, in_dim, hid_dim=2048, out_dim=128, s=4):
+        super().__init__()
+        self.is_s = s
+        self.avgpool = nn.AdaptiveAvgPool2d((1, 1))
+        self.mlp = nn.Sequential(nn.Linear(in_dim, hid_dim), nn.ReLU(inplace=True), nn.Linear(hid_dim, out_dim))
+        self.mlp_conv = nn.Sequential(nn.Conv2d(in_dim, hid_dim, 1), nn.ReLU(inplace=True), nn.Conv2d(hid_dim, out_dim, 1))
+        self.pool = nn.AdaptiveAvgPool2d((s, s)) if self.is_s else None
+
+    def forward(self, x):
+        x1 = self.avgpool(x)
+        x1 = x1.reshape(x1.size(0), -1)
+        x1 = self.mlp(x1)
+        if self.is_s:
+            x = self.pool(x)
+        x2 = self.mlp_conv(x)
+        x2 = x2.view(x2.size(0), x2.size(1), -1)
+        return x1, x2
+
+
+class UNet_Plus(UNet):
+    """``UNet_Plus(in_channels=1, num_classes=4)`` (model/unet.py:178-206): the U-Net plus two projection necks;
+    ``forward`` returns ``(logits, high_feature, head_feature)``, ``val`` the logits only.  Parameter names, shapes and
+    order match the reference (encoder.*, decoder.*, dense_projection_high.*, dense_projection_head.*)."""
+
+    def __init__(self, in_channels=1, num_classes=4, precision="bf16"):
+        super().__init__(in_channels, num_classes, precision)
+        self.dense_projection_high = projection_conv(FT_CHNS[-1])
+        self.dense_projection_head = projection_conv(num_classes, hid_dim=1024)
+
+    def val(self, x):
+        return UNet.forward(self, x)
+
+    def forward(self, x):
+        L.require_cuda(x, "UNet_Plus input")
+        if x.dim() != 4 or x.shape[1] != self.in_channels:
+            raise ValueError("expected input [N,%d,H,W], got %s" % (self.in_channels, tuple(x.shape)))
+        self.ensure_flat()
+        if self.flat_params.device != x.device:
+            raise L.HpfgError("model is on %s but the input is on %s" % (self.flat_params.device, x.device))
+        x = x.contiguous().float()
+        need_grad = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self._flat_params_list)
+        if need_grad:
+            output, feature = _UNetPlusFunction.apply(x, self, *self._flat_params_list)
+        else:
+            plan = self._acquire_plan(x, False)
+            output = self._run_forward(plan, x, save=False)
+            feature = _bottleneck(plan, x)
+        high_feature = self.dense_projection_high(feature)
+        head_feature = self.dense_projection_head(output)
+        return output, high_feature, head_feature
 
 
 def predict_volume(model, slices, max_batch=64, dtype=torch.int64):

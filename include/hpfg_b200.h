@@ -103,6 +103,14 @@ int hpfg_unet_forward_dv(hpfg_unet_plan_t plan, const float *params, float *bn_r
 int hpfg_unet_backward(hpfg_unet_plan_t plan, const float *params, const float *dlogits, float *grads,
                        int accumulate, void *stream);
 
+/* UNet_Plus (model/unet.py:178-206) needs one tensor from inside the network and sends one gradient back:
+ * hpfg_unet_bottleneck copies feature[-1] of the last forward on this plan -- the activated output of the down4 ConvBlock,
+ * fp32 NCHW [batch, 256, H/16, W/16] -- for the dense_projection_high neck; hpfg_unet_backward_ex is hpfg_unet_backward
+ * with an optional gradient wrt that tensor (same layout, NULL = none) added where the decoder's gradient arrives. */
+int hpfg_unet_bottleneck(hpfg_unet_plan_t plan, float *feature_nchw, void *stream);
+int hpfg_unet_backward_ex(hpfg_unet_plan_t plan, const float *params, const float *dlogits, const float *dbottleneck,
+                          float *grads, int accumulate, void *stream);
+
 /* Data-parallel hook: gradients complete back-to-front.  The flat gradient buffer is cut into
  * hpfg_unet_num_buckets() contiguous ranges (bucket 0 = the tail: out_conv, up4, ...).  After
  * hpfg_unet_backward has been enqueued, hpfg_unet_bucket_wait makes comm_stream wait until bucket i is

@@ -13,8 +13,8 @@ pure PyTorch; every function cites the reference file:line it follows).  It is p
   (``tests/golden/make_golden.py``), which travel to the GPU box.
 """
 from .unet_ref import (unet_param_spec, unet_buffer_spec, init_unet_state, unet_forward,
-                       ENC_DROPOUT, FT_CHNS)
+                       ENC_DROPOUT, FT_CHNS, unet_plus_forward, unet_plus_neck_spec, projection_conv)
 from .losses_ref import (dice_loss, med_sup_loss, softmax_mse, mt_consistency, cps_losses,
-                         uamt_consistency, ce_loss, ict_losses, s4cv_losses)
+                         uamt_consistency, ce_loss, ict_losses, s4cv_losses, dense_loss, dense_contrastive)
 from .steps_ref import (update_ema, sigmoid_rampup, consistency_weight, medical_lr, SGDState,
                         sgd_step, mt_step, cps_step, uamt_step, ema_alpha, ict_step)

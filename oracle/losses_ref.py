@@ -114,3 +114,22 @@ def s4cv_losses(out1, out2, teacher_logits_u, target, label_bs, n_classes, cps_w
         cl2 = torch.mean((soft2[label_bs:] - ema_soft) ** 2)
     loss_semi = (cps_weight * ps1 + mt_weight * cl1) + (cps_weight * ps2 + mt_weight * cl2)
     return loss_sup + loss_semi, loss_sup, loss_semi, pl1, pl2
+
+
+def dense_contrastive(out_1, out_2, temperature=0.7):
+    """Dense_Loss.contrastive_loss (utils/loss/dense_loss.py:18-34) with batch_size = out_1.shape[0]."""
+    bs = out_1.shape[0]
+    out_1 = F.normalize(out_1, dim=1).flatten(1)
+    out_2 = F.normalize(out_2, dim=1).flatten(1)
+    out = torch.cat([out_1, out_2], dim=0)
+    sim = torch.exp(torch.mm(out, out.t().contiguous()) / temperature)
+    mask = (torch.ones_like(sim) - torch.eye(2 * bs)).bool()
+    sim = sim.masked_select(mask).view(2 * bs, -1)
+    pos = torch.exp(torch.sum(out_1 * out_2, dim=-1) / temperature)
+    pos = torch.cat([pos, pos], dim=0)
+    return (-torch.log(pos / sim.sum(dim=-1))).mean()
+
+
+def dense_loss(x, y, temperature=0.7):
+    """Dense_Loss.forward (utils/loss/dense_loss.py:36-40): x, y = (global vector, dense map) pairs; y is detached."""
+    return 0.5 * (dense_contrastive(x[0], y[0].detach(), temperature) + dense_contrastive(x[1], y[1].detach(), temperature))

@@ -42,8 +42,10 @@ def load_reference():
     utils = _load("_hpfg_ref_utils", os.path.join(root, "utils", "utils.py"))
     mlr = _load("_hpfg_ref_medical_lr", os.path.join(root, "utils", "scheduler", "medical_lr.py"))
     ns.UNet = unet.UNet
+    ns.UNet_Plus = unet.UNet_Plus
     ns.Med_Sup_Loss = medloss.Med_Sup_Loss
     ns.DiceLoss = diceloss.DiceLoss
+    ns.Dense_Loss = _load("_hpfg_ref_dense_loss", os.path.join(root, "utils", "loss", "dense_loss.py")).Dense_Loss
     ns.softmax_mse_loss = diceloss.softmax_mse_loss
     ns.update_ema_variables = utils.update_ema_variables
     ns.get_current_consistency_weight = utils.get_current_consistency_weight

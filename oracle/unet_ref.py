@@ -137,6 +137,7 @@ def unet_forward(st, x, training=True, dropout_masks=None, return_taps=False):
             h = F.max_pool2d(h, 2)                     # DownBlock (model/unet.py:31-42)
         h = _conv_block(st, prefix, h, p, training, dropout_masks, taps)
         feats.append(h)
+    taps["feature4"] = feats[4]                        # feature[-1]: what UNet_Plus feeds its high projection neck (:201)
     h = feats[4]
     for i, (prefix, _, _) in enumerate(dec):           # UpBlock.forward (model/unet.py:53-58)
         skip = feats[3 - i]
@@ -148,3 +149,36 @@ def unet_forward(st, x, training=True, dropout_masks=None, return_taps=False):
         h = _conv_block(st, prefix + ".conv", h, 0.0, training, dropout_masks, taps)
     out = F.conv2d(h, st["decoder.out_conv.weight"], st["decoder.out_conv.bias"], padding=1)   # :99,116
     return (out, taps) if return_taps else out
+
+
+# ---- UNet_Plus (model/unet.py:120-152,178-206) -----------------------------------------------------------------------
+NECKS = (("dense_projection_high", FT_CHNS[-1], 2048), ("dense_projection_head", None, 1024))   # (name, in_dim, hid_dim)
+
+
+def unet_plus_neck_spec(num_classes, out_dim=128):
+    """[(name, shape)] of the 16 projection-neck parameters in registration order (after the 82 U-Net parameters)."""
+    spec = []
+    for name, in_dim, hid in NECKS:
+        in_dim = num_classes if in_dim is None else in_dim
+        spec += [(name + ".mlp.0.weight", (hid, in_dim)), (name + ".mlp.0.bias", (hid,)),
+                 (name + ".mlp.2.weight", (out_dim, hid)), (name + ".mlp.2.bias", (out_dim,)),
+                 (name + ".mlp_conv.0.weight", (hid, in_dim, 1, 1)), (name + ".mlp_conv.0.bias", (hid,)),
+                 (name + ".mlp_conv.2.weight", (out_dim, hid, 1, 1)), (name + ".mlp_conv.2.bias", (out_dim,))]
+    return spec
+
+
+def projection_conv(st, prefix, x, s=4):
+    """projection_conv.forward (model/unet.py:140-152): (global vector [N,128], dense map [N,128,s*s])."""
+    x1 = F.adaptive_avg_pool2d(x, (1, 1)).reshape(x.size(0), -1)
+    x1 = F.linear(F.relu(F.linear(x1, st[prefix + ".mlp.0.weight"], st[prefix + ".mlp.0.bias"])),
+                  st[prefix + ".mlp.2.weight"], st[prefix + ".mlp.2.bias"])
+    xp = F.adaptive_avg_pool2d(x, (s, s)) if s else x
+    x2 = F.conv2d(F.relu(F.conv2d(xp, st[prefix + ".mlp_conv.0.weight"], st[prefix + ".mlp_conv.0.bias"])),
+                  st[prefix + ".mlp_conv.2.weight"], st[prefix + ".mlp_conv.2.bias"])
+    return x1, x2.view(x2.size(0), x2.size(1), -1)
+
+
+def unet_plus_forward(st, x, training=True, dropout_masks=None):
+    """UNet_Plus.forward (model/unet.py:198-204): (logits, high_feature, head_feature)."""
+    out, taps = unet_forward(st, x, training, dropout_masks, return_taps=True)
+    return out, projection_conv(st, "dense_projection_high", taps["feature4"]), projection_conv(st, "dense_projection_head", out)

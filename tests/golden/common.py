@@ -43,6 +43,18 @@ def make_batch(n_l, n_u, in_ch, n_cls, h, w, seed, ignore_frac=0.0):
     return x_l, x_u, y
 
 
+def make_plus_state(in_ch, n_cls, seed):
+    """make_state + the 16 projection-neck parameters of UNet_Plus (uniform +-1/sqrt(fan_in), seeded)."""
+    from oracle.unet_ref import unet_plus_neck_spec
+    st = make_state(in_ch, n_cls, seed)
+    g = gen(seed + 2)
+    for name, shape in unet_plus_neck_spec(n_cls):
+        fan_in = shape[1] if len(shape) > 1 else shape[0]
+        b = 1.0 / (fan_in ** 0.5)
+        st[name] = (2 * torch.rand(shape, generator=g) - 1) * b
+    return st
+
+
 def make_predict_case(in_ch, n_cls, n, h, w, seed):
     """State + volume for the inference fixture: the output conv is scaled up and the slices are smooth blobs so that a
     random-init network predicts a mix of classes (BN running buffers come from the fixture)."""

@@ -18,7 +18,7 @@ import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.ref_loader import load_reference            # noqa: E402
-from tests.golden.common import (make_state, make_masks, make_batch, summarize, ENC_PREFIXES, make_predict_case)  # noqa: E402
+from tests.golden.common import (make_state, make_masks, make_batch, summarize, ENC_PREFIXES, make_predict_case, make_plus_state)  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ref = load_reference()
@@ -412,11 +412,50 @@ def golden_predict(in_ch, n_cls, n, h, w, seed):
     print("predict: label histogram", torch.bincount(out["labels"].flatten().long(), minlength=n_cls).tolist())
 
 
+def golden_unet_plus(in_ch, n_cls, n, h, w, seed):
+    """The reference UNet_Plus + Dense_Loss (model/unet.py:178-206, utils/loss/dense_loss.py) the way main.py:151-170 uses
+    them for model2 / ema_model: supervised loss on the logits + contrastive loss between student and teacher necks."""
+    st = make_plus_state(in_ch, n_cls, seed)
+    model2 = ref.UNet_Plus(in_channels=in_ch, num_classes=n_cls)
+    model2.load_state_dict(st)
+    model2.train()
+    ema_model = ref.UNet_Plus(in_channels=in_ch, num_classes=n_cls)
+    ema_model.load_state_dict(make_plus_state(in_ch, n_cls, seed + 9))
+    ema_model.train()
+    volume_batch, _, target_label = make_batch(n, 0, in_ch, n_cls, h, w, seed + 7)
+    hs = inject_masks(model2, make_masks(n, h, w, seed + 11)) + inject_masks(ema_model, make_masks(n, h, w, seed + 12))
+    dense_loss = ref.Dense_Loss(batch_size=n, device=torch.device("cpu"))
+    criterion = nn.CrossEntropyLoss(ignore_index=255)
+    dice_loss = ref.DiceLoss(n_cls)
+    outputs2, h1, h2 = model2(volume_batch)
+    outputs_soft2 = torch.softmax(outputs2, dim=1)
+    with torch.no_grad():
+        ema_output, ema_h1, ema_h2 = ema_model(volume_batch)
+    loss2 = 0.5 * (criterion(outputs2, target_label) + dice_loss(outputs_soft2, target_label.unsqueeze(1)))
+    loss_constrivate = dense_loss(h1, ema_h1) + dense_loss(h2, ema_h2)
+    weight = 0.3
+    loss = loss2 + weight * loss_constrivate
+    loss.backward()
+    for hnd in hs:
+        hnd.remove()
+    model2.eval()
+    with torch.no_grad():
+        val = model2.val(volume_batch)
+    out = dict(cfg=dict(in_ch=in_ch, n_cls=n_cls, n=n, h=h, w=w, seed=seed, weight=weight), loss=loss.item(), sup=loss2.item(),
+               contrast=loss_constrivate.item(), logits=summarize(outputs2), val_logits=summarize(val),
+               h1=[h1[0].detach().clone(), h1[1].detach().clone()], h2=[h2[0].detach().clone(), h2[1].detach().clone()],
+               ema_h1=[ema_h1[0].clone(), ema_h1[1].clone()], ema_h2=[ema_h2[0].clone(), ema_h2[1].clone()],
+               grads={k: summarize(p.grad) for k, p in model2.named_parameters()})
+    torch.save(out, os.path.join(HERE, "unet_plus_acdc.pt"))
+    print("unet_plus: loss %.8f (sup %.8f, contrast %.8f)" % (out["loss"], out["sup"], out["contrast"]))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "f4":      # only the SURVEY 8f.3 / 8f.4 fixtures (leaves the others untouched)
         golden_f4_losses()
         golden_ict_steps("acdc", 1, 4, 2, 4, 32, 32, 606)
         golden_predict(1, 4, 5, 32, 48, 707)
+        golden_unet_plus(1, 4, 3, 64, 64, 808)
         sys.exit(0)
     golden_unet("acdc_masks", 1, 4, 2, 32, 48, 101, True)
     golden_unet("acdc_nodrop", 1, 4, 3, 32, 32, 202, False)
@@ -428,3 +467,4 @@ if __name__ == "__main__":
     golden_f4_losses()
     golden_ict_steps("acdc", 1, 4, 2, 4, 32, 32, 606)
     golden_predict(1, 4, 5, 32, 48, 707)
+    golden_unet_plus(1, 4, 3, 64, 64, 808)

@@ -155,3 +155,61 @@ def test_predict_volume_vs_reference_golden(precision):
         assert sure_agree > 0.98, sure_agree
     chunked = hb.predict_volume(m, vol.to(DEV), max_batch=2, dtype=torch.uint8)   # chunking does not change eval labels
     assert (chunked.long() == labels).float().mean().item() > 0.9999
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_unet_plus_and_dense_loss_vs_reference_golden(precision):
+    """SURVEY 8f.2 (model/unet.py:178-206, utils/loss/dense_loss.py, main.py:151-170): the UNet_Plus drop-in through plain
+    autograd -- logits, both projection necks, loss, and every one of the 98 parameter gradients (the bottleneck gradient
+    of the high neck enters the plan through hpfg_unet_backward_ex)."""
+    from tests.golden.common import make_plus_state
+    g = load_golden("unet_plus_acdc.pt")
+    c = g["cfg"]
+    f32 = precision == "fp32"
+    model2 = hb.build_model(type("A", (), dict(model="unet_plus", in_channels=c["in_ch"], num_classes=c["n_cls"], precision=precision))())
+    assert isinstance(model2, hb.UNet_Plus)
+    model2.load_state_dict(make_plus_state(c["in_ch"], c["n_cls"], c["seed"]))
+    model2 = model2.to(DEV)
+    ema_model = hb.UNet_Plus(c["in_ch"], c["n_cls"], precision=precision)
+    ema_model.load_state_dict(make_plus_state(c["in_ch"], c["n_cls"], c["seed"] + 9))
+    ema_model = ema_model.to(DEV)
+    for p in ema_model.parameters():
+        p.requires_grad = False
+    x, _, y = make_batch(c["n"], 0, c["in_ch"], c["n_cls"], c["h"], c["w"], c["seed"] + 7)
+    x, y = x.to(DEV), y.to(DEV)
+    model2.set_dropout_masks(make_masks(c["n"], c["h"], c["w"], c["seed"] + 11))
+    ema_model.set_dropout_masks(make_masks(c["n"], c["h"], c["w"], c["seed"] + 12))
+    dense_loss = hb.Dense_Loss(batch_size=c["n"], device=torch.device(DEV))
+    dice_loss = hb.DiceLoss(c["n_cls"])
+    criterion = torch.nn.CrossEntropyLoss(ignore_index=255)
+    outputs2, h1, h2 = model2(x)                                           # main.py:155-157, literally
+    outputs_soft2 = torch.softmax(outputs2, dim=1)
+    with torch.no_grad():
+        ema_output, ema_h1, ema_h2 = ema_model(x)
+    loss2 = 0.5 * (criterion(outputs2, y) + dice_loss(outputs_soft2, y.unsqueeze(1)))
+    loss_constrivate = dense_loss(h1, ema_h1) + dense_loss(h2, ema_h2)
+    loss = loss2 + c["weight"] * loss_constrivate
+    loss.backward()
+    tol = 1e-5 if f32 else 3e-2
+    check_summary(outputs2, g["logits"], rtol=tol, what="logits")
+    for a, b in zip(list(h1) + list(h2) + list(ema_h1) + list(ema_h2), g["h1"] + g["h2"] + g["ema_h1"] + g["ema_h2"]):
+        assert rel_l2(a, b) < (1e-4 if f32 else 5e-2)
+    assert abs(loss2.item() - g["sup"]) / g["sup"] < (1e-5 if f32 else 1e-3)
+    assert abs(loss_constrivate.item() - g["contrast"]) / g["contrast"] < (1e-4 if f32 else 2e-2)
+    grads = dict((k, p.grad) for k, p in model2.named_parameters())
+    assert list(grads) == list(g["grads"]) and all(v is not None for v in grads.values())
+    if f32:
+        for k, gr in grads.items():
+            check_summary(gr, g["grads"][k], rtol=5e-4, atol=1e-6, what=k)
+    else:      # bf16: whole-gradient direction (per-tensor comparison of tiny bias gradients is noise-dominated)
+        import math
+        dot = sum((gr.double().flatten()[::g["grads"][k].get("stride", 1)].cpu() * (g["grads"][k].get("full", g["grads"][k].get("sample")).double())).sum().item()
+                  for k, gr in grads.items())
+        na = math.sqrt(sum((gr.double().flatten()[::g["grads"][k].get("stride", 1)] ** 2).sum().item() for k, gr in grads.items()))
+        nb = math.sqrt(sum((g["grads"][k].get("full", g["grads"][k].get("sample")).double() ** 2).sum().item() for k in grads))
+        assert dot / (na * nb) > 0.995, dot / (na * nb)
+    # the encoder gradient must contain the bottleneck path: without the high neck's gradient it differs
+    model2.eval()
+    with torch.no_grad():
+        val = model2.val(x)
+    check_summary(val, g["val_logits"], rtol=tol, what="val logits")

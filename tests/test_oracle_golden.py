@@ -178,3 +178,33 @@ def test_predict_labels():
     sure = g["margin"].float() > 1e-3
     assert torch.equal(labels[sure], g["labels"].long()[sure])
     assert (labels == g["labels"].long()).float().mean().item() > 0.999
+
+
+def test_unet_plus_and_dense_loss():
+    """UNet_Plus + Dense_Loss restatement vs the reference-generated fixture (main.py:151-170 usage)."""
+    from tests.golden.common import make_plus_state
+    g = load_golden("unet_plus_acdc.pt")
+    c = g["cfg"]
+    st = make_plus_state(c["in_ch"], c["n_cls"], c["seed"])
+    te = make_plus_state(c["in_ch"], c["n_cls"], c["seed"] + 9)
+    x, _, y = make_batch(c["n"], 0, c["in_ch"], c["n_cls"], c["h"], c["w"], c["seed"] + 7)
+    names = [n for n, _ in oracle.unet_param_spec(c["in_ch"], c["n_cls"])] + [n for n, _ in oracle.unet_plus_neck_spec(c["n_cls"])]
+    assert names == list(g["grads"].keys())
+    leaves = {n: st[n].clone().requires_grad_(True) for n in names}
+    view = dict(st)
+    view.update(leaves)
+    out, h1, h2 = oracle.unet_plus_forward(view, x, True, make_masks(c["n"], c["h"], c["w"], c["seed"] + 11))
+    with torch.no_grad():
+        _, e1, e2 = oracle.unet_plus_forward(te, x, True, make_masks(c["n"], c["h"], c["w"], c["seed"] + 12))
+    check_summary(out, g["logits"], rtol=1e-5, atol=1e-6, what="logits")
+    for a, b in zip(h1 + h2 + e1 + e2, g["h1"] + g["h2"] + g["ema_h1"] + g["ema_h2"]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5)
+    sup = oracle.med_sup_loss(out, y, c["n_cls"])
+    con = oracle.dense_loss(h1, e1) + oracle.dense_loss(h2, e2)
+    loss = sup + c["weight"] * con
+    assert abs(sup.item() - g["sup"]) < 1e-6 and abs(con.item() - g["contrast"]) / g["contrast"] < 1e-5
+    assert abs(loss.item() - g["loss"]) / g["loss"] < 1e-5
+    grads = torch.autograd.grad(loss, [leaves[n] for n in names])
+    for n, gr in zip(names, grads):
+        check_summary(gr, g["grads"][n], rtol=2e-4, atol=1e-6, what=n)
+    check_summary(oracle.unet_forward(view, x, False), g["val_logits"], rtol=1e-5, atol=1e-6, what="val logits")
