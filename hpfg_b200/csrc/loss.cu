@@ -11,6 +11,7 @@
 // kernels: NCHW fp32, 4 consecutive pixels per thread, 128-bit loads per class plane.
 // Algorithmic bytes (MT): (n_l+n_u)*C*HW*4 read + n_u*C*HW*4 read + n_l*HW*8 read + (n_l+n_u)*C*HW*4 written.
 #include "common.cuh"
+#include <cstdlib>
 
 namespace hpfg {
 
@@ -558,9 +559,18 @@ __global__ void __launch_bounds__(256) dice_grad_kernel(DiceArgs A) {
     }
 }
 
+static int loss_ctas_per_sm() {      // A/B knob (profiles/config_throughput.py): HPFG_LOSS_CTAS_PER_SM; default 2 = the resident CTAs per SM of both kernels (one wave, ~5 grid-stride iterations per thread: 52.6 -> 44.8 us per MT loss call, profiles/r01_loss_grid_ab.txt)
+    static int v = [] {
+        const char *e = getenv("HPFG_LOSS_CTAS_PER_SM");
+        const int n = e ? atoi(e) : 0;
+        return n > 0 ? n : 2;
+    }();
+    return v;
+}
+
 static int loss_grid(int64_t quads) {
     int64_t blocks = (quads + 255) / 256;
-    const int64_t cap = (int64_t)kNumSMs * 8;
+    const int64_t cap = (int64_t)kNumSMs * loss_ctas_per_sm();
     if (blocks > cap) blocks = cap;
     return (int)(blocks < 1 ? 1 : blocks);
 }

@@ -157,6 +157,24 @@ def test_predict_volume_vs_reference_golden(precision):
     assert (chunked.long() == labels).float().mean().item() > 0.9999
 
 
+def _oracle_plus_grads(c, dtype):
+    """All 98 gradients of the fixture's loss from the CPU oracle in the given precision."""
+    from tests.golden.common import make_plus_state
+    cast = lambda d: {k: (v.to(dtype) if v.is_floating_point() else v) for k, v in d.items()}
+    st, te = cast(make_plus_state(c["in_ch"], c["n_cls"], c["seed"])), cast(make_plus_state(c["in_ch"], c["n_cls"], c["seed"] + 9))
+    x, _, y = make_batch(c["n"], 0, c["in_ch"], c["n_cls"], c["h"], c["w"], c["seed"] + 7)
+    x = x.to(dtype)
+    names = [n for n, _ in oracle.unet_param_spec(c["in_ch"], c["n_cls"])] + [n for n, _ in oracle.unet_plus_neck_spec(c["n_cls"])]
+    leaves = {n: st[n].clone().requires_grad_(True) for n in names}
+    view = dict(st)
+    view.update(leaves)
+    out, h1, h2 = oracle.unet_plus_forward(view, x, True, make_masks(c["n"], c["h"], c["w"], c["seed"] + 11))
+    with torch.no_grad():
+        _, e1, e2 = oracle.unet_plus_forward(te, x, True, make_masks(c["n"], c["h"], c["w"], c["seed"] + 12))
+    loss = oracle.med_sup_loss(out, y, c["n_cls"]) + c["weight"] * (oracle.dense_loss(h1, e1) + oracle.dense_loss(h2, e2))
+    return dict(zip(names, torch.autograd.grad(loss, [leaves[n] for n in names])))
+
+
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_unet_plus_and_dense_loss_vs_reference_golden(precision):
     """SURVEY 8f.2 (model/unet.py:178-206, utils/loss/dense_loss.py, main.py:151-170): the UNet_Plus drop-in through plain
@@ -200,11 +218,16 @@ def test_unet_plus_and_dense_loss_vs_reference_golden(precision):
     grads = dict((k, p.grad) for k, p in model2.named_parameters())
     assert list(grads) == list(g["grads"]) and all(v is not None for v in grads.values())
     if f32:
+        # conditioning: the reference's own fp32 gradients sit up to 3e-3 (rel-l2) from the fp64 truth on the up1 block
+        # of this fixture, so each tensor is held to 5e-4 plus three times the fp32-vs-fp64 distance of the oracle
+        o32, o64 = _oracle_plus_grads(c, torch.float32), _oracle_plus_grads(c, torch.float64)
         for k, gr in grads.items():
             if k.endswith(".bias") and g["grads"][k]["abs_sum"] < 1e-4:      # conv bias ahead of train-mode BN: analytically zero
                 assert gr.abs().max().item() < 1e-4, k
                 continue
-            check_summary(gr, g["grads"][k], rtol=5e-4, atol=1e-6, what=k)
+            rt = 5e-4 + 3 * rel_l2(o32[k], o64[k])
+            check_summary(gr, g["grads"][k], rtol=rt, atol=1e-6, what=k)
+            assert rel_l2(gr, o64[k]) < rt, (k, rel_l2(gr, o64[k]), rt)
     else:      # bf16: whole-gradient direction (per-tensor comparison of tiny bias gradients is noise-dominated)
         import math
         dot = sum((gr.double().flatten()[::g["grads"][k].get("stride", 1)].cpu() * (g["grads"][k].get("full", g["grads"][k].get("sample")).double())).sum().item()
