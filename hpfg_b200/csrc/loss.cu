@@ -568,9 +568,9 @@ static int loss_ctas_per_sm() {      // A/B knob (profiles/config_throughput.py)
     return v;
 }
 
-static int loss_grid(int64_t quads) {
+static int loss_grid(int64_t quads, int ctas_per_sm = 0) {
     int64_t blocks = (quads + 255) / 256;
-    const int64_t cap = (int64_t)kNumSMs * loss_ctas_per_sm();
+    const int64_t cap = (int64_t)kNumSMs * (ctas_per_sm > 0 ? ctas_per_sm : loss_ctas_per_sm());
     if (blocks > cap) blocks = cap;
     return (int)(blocks < 1 ? 1 : blocks);
 }
@@ -784,7 +784,7 @@ __global__ void __launch_bounds__(256) argmax_kernel(const float *__restrict__ l
 
 template <int C>
 static int launch_argmax(const float *logits, int64_t hw, int64_t quads, int64_t *o64, uint8_t *o8, cudaStream_t st) {
-    HPFG_CUDA_CHECK(launch_pdl(argmax_kernel<C>, loss_grid(quads), 256, 0, st, logits, hw, quads, o64, o8));
+    HPFG_CUDA_CHECK(launch_pdl(argmax_kernel<C>, loss_grid(quads, 6), 256, 0, st, logits, hw, quads, o64, o8));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -797,7 +797,7 @@ extern "C" int hpfg_ict_mix(const float *a, const float *b, const float *mix_fac
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t qpi = per_image / 4, total = qpi * n;
     ProfScope _prof(PROF_LOSS, st);
-    HPFG_CUDA_CHECK(launch_pdl(ict_mix_kernel, loss_grid(total), 256, 0, st, reinterpret_cast<const float4 *>(a),
+    HPFG_CUDA_CHECK(launch_pdl(ict_mix_kernel, loss_grid(total, 6), 256, 0, st, reinterpret_cast<const float4 *>(a),
                                reinterpret_cast<const float4 *>(b), mix_factors, reinterpret_cast<float4 *>(out), qpi, total));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;

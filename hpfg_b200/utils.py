@@ -42,10 +42,13 @@ def update_ema_variables(model, ema_model, alpha, global_step):
     BN buffers untouched.  Two hpfg_b200 UNets -> a single pass over their flat parameter buffers; any other
     pair of CUDA modules -> one launch per parameter tensor."""
     alpha = min(1 - 1 / (global_step + 1), alpha)
+    pairs = zip(ema_model.parameters(), model.parameters())
     if isinstance(model, UNet) and isinstance(ema_model, UNet):
         ema_update_flat(ema_model.ensure_flat(), model.ensure_flat(), alpha)
-        return
-    for ema_param, param in zip(ema_model.parameters(), model.parameters()):
+        # UNet_Plus: the projection-neck parameters live outside the flat buffer (they follow the 82 U-Net parameters)
+        core = {id(q) for q in ema_model._flat_params_list}
+        pairs = [(e, p) for e, p in zip(ema_model.parameters(), model.parameters()) if id(e) not in core]
+    for ema_param, param in pairs:
         e, p = ema_param.data, param.data
         if not (e.is_contiguous() and p.is_contiguous() and e.data_ptr() % 16 == 0 and p.data_ptr() % 16 == 0):
             raise L.HpfgError("update_ema_variables: parameters must be contiguous, 16-byte aligned CUDA fp32 tensors")

@@ -80,3 +80,91 @@ def summarize(t, stride=97, full_below=20000):
         d["sample"] = t[::stride].float().clone()
         d["stride"] = stride
     return d
+
+
+def make_cutmix_masks(n, h, w, seed):
+    """Seeded stand-in for BoxMaskGenerator.generate_params (main.py:92-97,140-142): [n,1,h,w] float masks that are 1
+    outside one random box and 0 inside (invert=True convention)."""
+    g = gen(seed)
+    m = torch.ones(n, 1, h, w)
+    for i in range(n):
+        y0, x0 = int(torch.randint(0, h // 2, (1,), generator=g)), int(torch.randint(0, w // 2, (1,), generator=g))
+        hh, ww = int(torch.randint(h // 4, h // 2, (1,), generator=g)), int(torch.randint(w // 4, w // 2, (1,), generator=g))
+        m[i, :, y0:y0 + hh, x0:x0 + ww] = 0.0
+    return m
+
+
+def hpfg_main_step(ns, model1, model2, ema_model, optimizer1, optimizer2, lr_scheduler1, lr_scheduler2, batch, cur_itrs,
+                   args, device):
+    """main.py:128-207 (the HPFG iteration) transcribed once and run with EITHER the reference's objects (make_golden.py,
+    CPU) OR hpfg_b200's drop-ins (tests, GPU): ``ns`` supplies DiceLoss / Dense_Loss / update_ema_variables /
+    linear_rampup, everything else is the caller code of the reference, unchanged."""
+    import torch.nn as nn
+    label_img, target_label, label_img1, target_label1, img_unlabel, cutmix_mask = batch
+    criterion = nn.CrossEntropyLoss(ignore_index=255)
+    dice_loss = ns.DiceLoss(args.num_classes)
+    dense_loss = ns.Dense_Loss(args.batch_size + args.unlabel_batch_size, device)
+    label_bs = label_img.shape[0]
+    unlabel_bs = img_unlabel.shape[0]
+    label_img = label_img.to(device).float()
+    img_unlabel = img_unlabel.to(device).float()
+    label_img1 = label_img1.repeat(int(unlabel_bs // label_bs), 1, 1, 1).to(device).float()
+    target_label1 = target_label1.repeat(int(unlabel_bs // label_bs), 1, 1).to(device).long()
+    target_label = target_label.to(device).long()
+    cutmix_mask = cutmix_mask.clone().float().to(device)
+    batch_un_mix = label_img1 * (1.0 - cutmix_mask) + img_unlabel * cutmix_mask
+    batch_mix = torch.cat([label_img, batch_un_mix], dim=0).to(device).float()
+    outputs1, _, _ = model1(batch_mix)
+    outputs_soft1 = torch.softmax(outputs1, dim=1)
+    volume_batch = torch.cat([label_img, img_unlabel], dim=0).to(device).float()
+    outputs2, h1, h2 = model2(volume_batch)
+    outputs_soft2 = torch.softmax(outputs2, dim=1)
+    with torch.no_grad():
+        ema_output, ema_h1, ema_h2 = ema_model(volume_batch)
+        ema_output_soft = torch.softmax(ema_output.detach(), dim=1)
+    loss1 = 0.5 * (criterion(outputs1[:label_bs], target_label) + dice_loss(outputs_soft1[:label_bs],
+                                                                            target_label.unsqueeze(1)))
+    loss2 = 0.5 * (criterion(outputs2[:label_bs], target_label) + dice_loss(outputs_soft2[:label_bs],
+                                                                            target_label.unsqueeze(1)))
+    loss_sup = loss1 + loss2
+    loss_constrivate = dense_loss(h1, ema_h1) + dense_loss(h2, ema_h2)
+    cutmix_mask = cutmix_mask.squeeze(1)
+    pseudo_outputs1 = torch.argmax(ema_output_soft[label_bs:], dim=1, keepdim=False)
+    pseudo_outputs1 = target_label1 * (1.0 - cutmix_mask) + pseudo_outputs1 * cutmix_mask
+    pseudo_supervision1 = dice_loss(outputs_soft1[label_bs:], pseudo_outputs1.unsqueeze(1))
+    consistency_weight_cps = args.consistency * ns.linear_rampup(cur_itrs // 150, args.consistency_rampup)
+    consistency_weight_mt = args.consistency * ns.linear_rampup(cur_itrs // 150, args.consistency_rampup)
+    if cur_itrs < 1000:
+        consistency_loss1 = 0.0
+        consistency_loss2 = 0.0
+    else:
+        consistency_loss1 = 0.0
+        consistency_loss2 = torch.mean((outputs_soft2[label_bs:] - ema_output_soft[label_bs:]) ** 2)
+    model1_loss = 7 * consistency_weight_cps * pseudo_supervision1 + consistency_weight_mt * consistency_loss1
+    model2_loss = consistency_weight_mt * consistency_loss2 + consistency_weight_mt * loss_constrivate
+    loss_semi = model1_loss + model2_loss
+    loss = loss_sup + loss_semi
+    optimizer1.zero_grad()
+    optimizer2.zero_grad()
+    loss.backward()
+    optimizer1.step()
+    optimizer2.step()
+    # update_ema_variables_backbone(model1, model2, ...) -- main.py:68-76: model2's backbone tracks model1's
+    alpha = min(1 - 1 / (cur_itrs + 1), args.ema_decay)
+    for ema_param, param in zip(model2.encoder.parameters(), model1.encoder.parameters()):
+        ema_param.data.mul_(alpha).add_(param.data, alpha=1 - alpha)
+    for ema_param, param in zip(model2.decoder.parameters(), model1.decoder.parameters()):
+        ema_param.data.mul_(alpha).add_(param.data, alpha=1 - alpha)
+    ns.update_ema_variables(model2, ema_model, args.ema_decay, cur_itrs)
+    lr_scheduler1.step()
+    lr_scheduler2.step()
+    return dict(loss=loss.item(), loss_sup=loss_sup.item(), loss_semi=loss_semi.item(),
+                contrast=loss_constrivate.item(), pseudo=pseudo_supervision1.item(),
+                cons2=float(consistency_loss2.detach()) if torch.is_tensor(consistency_loss2) else 0.0, outputs1=outputs1.detach(), outputs2=outputs2.detach(),
+                ema_output=ema_output.detach())
+
+
+def make_hpfg_batch(n_l, n_u, in_ch, n_cls, h, w, seed):
+    x_l, x_u, y = make_batch(n_l, n_u, in_ch, n_cls, h, w, seed)
+    x_l1, _, y1 = make_batch(n_l, 0, in_ch, n_cls, h, w, seed + 1)
+    return x_l, y, x_l1, y1, x_u, make_cutmix_masks(n_u, h, w, seed + 2)

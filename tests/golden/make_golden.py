@@ -18,7 +18,8 @@ import torch.nn.functional as F
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))))
 from oracle.ref_loader import load_reference            # noqa: E402
-from tests.golden.common import (make_state, make_masks, make_batch, summarize, ENC_PREFIXES, make_predict_case, make_plus_state)  # noqa: E402
+from tests.golden.common import (make_state, make_masks, make_batch, summarize, ENC_PREFIXES, make_predict_case, make_plus_state,
+                                 hpfg_main_step, make_hpfg_batch)  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ref = load_reference()
@@ -450,12 +451,44 @@ def golden_unet_plus(in_ch, n_cls, n, h, w, seed):
     print("unet_plus: loss %.8f (sup %.8f, contrast %.8f)" % (out["loss"], out["sup"], out["contrast"]))
 
 
+def golden_hpfg_step(in_ch, n_cls, n_l, n_u, h, w, seed, cur_itrs=1500):
+    """One iteration of main.py (HPFG, :128-207) on the reference's UNet_Plus x3, Dense_Loss, DiceLoss, SGD, Medical_LR."""
+    args = Args(num_classes=n_cls, batch_size=n_l, unlabel_batch_size=n_u, consistency=0.1, consistency_rampup=200.0,
+                ema_decay=0.99)
+    model1 = ref.UNet_Plus(in_channels=in_ch, num_classes=n_cls)
+    model1.load_state_dict(make_plus_state(in_ch, n_cls, seed))
+    model2 = ref.UNet_Plus(in_channels=in_ch, num_classes=n_cls)
+    model2.load_state_dict(make_plus_state(in_ch, n_cls, seed + 20))
+    ema_model = copy.deepcopy(model2)
+    for name, param in ema_model.named_parameters():
+        param.requires_grad = False
+    optimizer1 = torch.optim.SGD(model1.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0005)
+    optimizer2 = torch.optim.SGD(model2.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0005)
+    sch1 = ref.Medical_LR(optimizer=optimizer1, base_lr=0.01, max_iterations=30000)
+    sch2 = ref.Medical_LR(optimizer=optimizer2, base_lr=0.01, max_iterations=30000)
+    model1.train(), model2.train()
+    hs = inject_masks(model1, make_masks(n_l + n_u, h, w, seed + 31)) + inject_masks(model2, make_masks(n_l + n_u, h, w, seed + 32))
+    hs += inject_masks(ema_model, make_masks(n_l + n_u, h, w, seed + 33))
+    r = hpfg_main_step(ref, model1, model2, ema_model, optimizer1, optimizer2, sch1, sch2,
+                       make_hpfg_batch(n_l, n_u, in_ch, n_cls, h, w, seed + 40), cur_itrs, args, torch.device("cpu"))
+    for hnd in hs:
+        hnd.remove()
+    out = dict(cfg=dict(in_ch=in_ch, n_cls=n_cls, n_l=n_l, n_u=n_u, h=h, w=w, seed=seed, cur_itrs=cur_itrs),
+               scalars={k: v for k, v in r.items() if isinstance(v, float)},
+               outputs1=summarize(r["outputs1"]), outputs2=summarize(r["outputs2"]), ema_output=summarize(r["ema_output"]),
+               after={nm: {k: summarize(v, full_below=512) for k, v in m.state_dict().items() if "tracked" not in k}
+                      for nm, m in (("model1", model1), ("model2", model2), ("ema_model", ema_model))})
+    torch.save(out, os.path.join(HERE, "hpfg_step_acdc.pt"))
+    print("hpfg_step:", out["scalars"])
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "f4":      # only the SURVEY 8f.3 / 8f.4 fixtures (leaves the others untouched)
         golden_f4_losses()
         golden_ict_steps("acdc", 1, 4, 2, 4, 32, 32, 606)
         golden_predict(1, 4, 5, 32, 48, 707)
         golden_unet_plus(1, 4, 3, 64, 64, 808)
+        golden_hpfg_step(1, 4, 2, 4, 64, 64, 909)
         sys.exit(0)
     golden_unet("acdc_masks", 1, 4, 2, 32, 48, 101, True)
     golden_unet("acdc_nodrop", 1, 4, 3, 32, 32, 202, False)
@@ -468,3 +501,4 @@ if __name__ == "__main__":
     golden_ict_steps("acdc", 1, 4, 2, 4, 32, 32, 606)
     golden_predict(1, 4, 5, 32, 48, 707)
     golden_unet_plus(1, 4, 3, 64, 64, 808)
+    golden_hpfg_step(1, 4, 2, 4, 64, 64, 909)

@@ -241,3 +241,73 @@ def test_unet_plus_and_dense_loss_vs_reference_golden(precision):
     with torch.no_grad():
         val = model2.val(x)
     check_summary(val, g["val_logits"], rtol=tol, what="val logits")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_hpfg_main_step_vs_reference_golden(precision):
+    """main.py:128-207 (the HPFG iteration: three UNet_Plus networks, CutMix batch, supervised + Dice-on-mixed-pseudo-labels
+    + Mean-Teacher MSE + two Dense_Loss terms, two SGD steps, backbone EMA and teacher EMA).  The SAME transcription of the
+    caller code (tests/golden/common.py:hpfg_main_step) produced the fixture with the reference's objects on CPU and runs
+    here with hpfg_b200's drop-ins: only the imports differ."""
+    import copy
+    import types
+    from tests.golden.common import make_plus_state, hpfg_main_step, make_hpfg_batch
+    g = load_golden("hpfg_step_acdc.pt")
+    c = g["cfg"]
+    f32 = precision == "fp32"
+    torch.backends.cudnn.allow_tf32 = False
+    in_ch, n_cls, n_l, n_u, h, w, seed = c["in_ch"], c["n_cls"], c["n_l"], c["n_u"], c["h"], c["w"], c["seed"]
+    args = types.SimpleNamespace(num_classes=n_cls, batch_size=n_l, unlabel_batch_size=n_u, consistency=0.1,
+                                 consistency_rampup=200.0, ema_decay=0.99)
+    before1, before2 = make_plus_state(in_ch, n_cls, seed), make_plus_state(in_ch, n_cls, seed + 20)
+    model1 = hb.UNet_Plus(in_ch, n_cls, precision=precision)
+    model1.load_state_dict(before1)
+    model1 = model1.to(DEV)
+    model2 = hb.UNet_Plus(in_ch, n_cls, precision=precision)
+    model2.load_state_dict(before2)
+    model2 = model2.to(DEV)
+    ema_model = copy.deepcopy(model2)
+    for name, param in ema_model.named_parameters():
+        param.requires_grad = False
+    optimizer1 = torch.optim.SGD(model1.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0005)
+    optimizer2 = torch.optim.SGD(model2.parameters(), lr=0.01, momentum=0.9, weight_decay=0.0005)
+    lam = lambda e: (1.0 - (e - 1) / 30000) ** 0.9                         # Medical_LR (utils/scheduler/medical_lr.py:13-17)
+    sch1 = torch.optim.lr_scheduler.LambdaLR(optimizer1, lam)
+    sch2 = torch.optim.lr_scheduler.LambdaLR(optimizer2, lam)
+    model1.train(), model2.train()
+    model1.set_dropout_masks(make_masks(n_l + n_u, h, w, seed + 31))
+    model2.set_dropout_masks(make_masks(n_l + n_u, h, w, seed + 32))
+    ema_model.set_dropout_masks(make_masks(n_l + n_u, h, w, seed + 33))
+    ns = types.SimpleNamespace(DiceLoss=hb.DiceLoss, Dense_Loss=hb.Dense_Loss, update_ema_variables=hb.update_ema_variables,
+                               linear_rampup=hb.linear_rampup)
+    r = hpfg_main_step(ns, model1, model2, ema_model, optimizer1, optimizer2, sch1, sch2,
+                       make_hpfg_batch(n_l, n_u, in_ch, n_cls, h, w, seed + 40), c["cur_itrs"], args, torch.device(DEV))
+    sc = g["scalars"]
+    for k, tol32, tol16 in (("loss", 1e-5, 2e-3), ("loss_sup", 1e-5, 2e-3), ("contrast", 1e-4, 3e-2), ("pseudo", 1e-5, 5e-3),
+                            ("cons2", 1e-4, 1e-1)):
+        assert abs(r[k] - sc[k]) / abs(sc[k]) < (tol32 if f32 else tol16), (k, r[k], sc[k])
+    tol = 1e-5 if f32 else 3e-2
+    check_summary(r["outputs1"], g["outputs1"], rtol=tol, what="outputs1")
+    check_summary(r["outputs2"], g["outputs2"], rtol=tol, what="outputs2")
+    check_summary(r["ema_output"], g["ema_output"], rtol=tol, what="ema_output")
+    assert model1._is_flat() and model2._is_flat() and ema_model._is_flat()
+    if not f32:
+        return
+    for nm, m in (("model1", model1), ("model2", model2), ("ema_model", ema_model)):
+        sd = m.state_dict()
+        for k, summ in g["after"][nm].items():
+            check_summary(sd[k], summ, rtol=1e-4 if "running_" in k else 2e-5, atol=1e-6, what=nm + "." + k)
+    # the updates themselves (after - before), where the optimiser step and both EMA passes show: model1 moved by its SGD
+    # step, the teacher moved 1 % of the way towards the updated model2 (whose backbone moved 1 % towards model1)
+    for nm, m, before in (("model1", model1, before1), ("ema_model", ema_model, before2)):
+        sd = m.state_dict()
+        for k in ("encoder.down4.maxpool_conv.1.conv_conv.4.weight", "decoder.up4.conv.conv_conv.0.weight",
+                  "decoder.out_conv.weight", "dense_projection_high.mlp_conv.2.weight", "dense_projection_head.mlp.0.weight"):
+            summ = g["after"][nm][k]
+            ref_after = summ["full"] if "full" in summ else summ["sample"]
+            b = before[k].flatten()
+            got = sd[k].detach().cpu().flatten()
+            if "full" not in summ:
+                b, got = b[::summ["stride"]], got[::summ["stride"]]
+            d_ref, d_got = ref_after.double() - b.double(), got.double() - b.double()
+            assert (d_got - d_ref).norm() <= 2e-2 * d_ref.norm() + 1e-9, (nm, k, float((d_got - d_ref).norm() / d_ref.norm()))
