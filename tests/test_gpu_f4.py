@@ -310,4 +310,7 @@ def test_hpfg_main_step_vs_reference_golden(precision):
             if "full" not in summ:
                 b, got = b[::summ["stride"]], got[::summ["stride"]]
             d_ref, d_got = ref_after.double() - b.double(), got.double() - b.double()
-            assert (d_got - d_ref).norm() <= 2e-2 * d_ref.norm() + 1e-9, (nm, k, float((d_got - d_ref).norm() / d_ref.norm()))
+            # (2e-7 * |w|: fp32 rounding of the stored weights, which is all that is left of the teacher's 1 % step on
+            # tensors whose gradient is tiny)
+            assert (d_got - d_ref).norm() <= 2e-2 * d_ref.norm() + 2e-7 * b.double().norm(), \
+                (nm, k, float((d_got - d_ref).norm() / d_ref.norm()))
