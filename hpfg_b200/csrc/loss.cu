@@ -144,24 +144,27 @@ __global__ void __launch_bounds__(256, MODE == HPFG_LOSS_S4CV ? 1 : 2) loss_redu
     for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_q;
          q += (int64_t)gridDim.x * blockDim.x) {
         const int64_t img = q / q_per_img, pix = (q - img * q_per_img) << 2;
-        float z[C][4], p[C][4], lse[4];
+        // every global load of this quad is issued before any math: one DRAM round trip per iteration instead of two or
+        // three dependent ones (the loads sit behind warp-uniform branches, so the compiler cannot hoist them itself)
+        const bool labeled = img < A.n_l;
+        const int64_t u = img - A.n_l;
+        float z[C][4], p[C][4], lse[4], z2[C][4], z3[C][4];
+        int lab[4];
         load4<C>(A.student + (img * C) * hw + pix, hw, z);
+        if (labeled) load_labels4(A.labels + img * hw + pix, lab);
+        if (MODE != HPFG_LOSS_SUP && (TWO || !labeled))
+            load4<C>(TWO ? A.other + (img * C) * hw + pix : A.other + (u * C) * hw + pix, hw, z2);
+        if (MODE == HPFG_LOSS_ICT && !labeled) load4<C>(A.other + ((u + A.n_u) * C) * hw + pix, hw, z3);
         softmax4<C>(z, p, lse);
-        if (img < A.n_l) {
-            int lab[4];
-            load_labels4(A.labels + img * hw + pix, lab);
+        if (labeled) {
             acc_sup<C>(z, p, lse, lab, sl[0]);
             if (TWO) {
-                float z2[C][4], p2[C][4], lse2[4];
-                load4<C>(A.other + (img * C) * hw + pix, hw, z2);
+                float p2[C][4], lse2[4];
                 softmax4<C>(z2, p2, lse2);
                 acc_sup<C>(z2, p2, lse2, lab, sl[NSETS - 1]);
             }
         } else if (MODE != HPFG_LOSS_SUP) {
-            const int64_t u = img - A.n_l;
-            float z2[C][4], p2[C][4], lse2[4];
-            const float *ob = TWO ? A.other + (img * C) * hw + pix : A.other + (u * C) * hw + pix;
-            load4<C>(ob, hw, z2);
+            float p2[C][4], lse2[4];
             softmax4<C>(z2, p2, lse2);
             if (MODE == HPFG_LOSS_MT) {
 #pragma unroll
@@ -169,8 +172,7 @@ __global__ void __launch_bounds__(256, MODE == HPFG_LOSS_S4CV ? 1 : 2) loss_redu
 #pragma unroll
                     for (int c = 0; c < C; ++c) { const float d = p[c][j] - p2[c][j]; misc[0] += d * d; }
             } else if (MODE == HPFG_LOSS_ICT) {   // target = (1-lambda)*softmax(teacher(ux0)) + lambda*softmax(teacher(ux1))
-                float z3[C][4], p3[C][4], lse3[4];
-                load4<C>(A.other + ((u + A.n_u) * C) * hw + pix, hw, z3);
+                float p3[C][4], lse3[4];
                 softmax4<C>(z3, p3, lse3);
                 const float lam = __ldg(A.mix + u), oml = 1.0f - lam;
 #pragma unroll
@@ -415,7 +417,9 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
             store4<C>(A.dstudent + so, hw, g);
             continue;
         }
+        float z2[C][4];      // second source (peer / teacher), requested before the student's softmax math
         load4<C>(A.student + so, hw, z);
+        load4<C>(cps ? A.other + so : A.other + (u * C) * hw + pix, hw, z2);
         softmax4<C>(z, p, lse);
         if (cps) {
             const uchar4 a1 = *reinterpret_cast<const uchar4 *>(A.aux + u * hw + pix);
@@ -437,8 +441,7 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
                     for (int j = 0; j < 4; ++j) g[c][j] += gm[c][j];
             }
             store4<C>(A.dstudent + so, hw, g);
-            load4<C>(A.other + so, hw, z);
-            softmax4<C>(z, p, lse);
+            softmax4<C>(z2, p, lse);
             grad_sup<C>(p, pl1, coef[3], ps_ce, ps_dice, A.cons_weight, g);
             if (mse) {
                 grad_mse<C>(p, pt, cf4, gm);
@@ -449,8 +452,7 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
             }
             store4<C>(A.dother + so, hw, g);
         } else {
-            float z2[C][4], q2[C][4], l2[4], cf[4];
-            load4<C>(A.other + (u * C) * hw + pix, hw, z2);
+            float q2[C][4], l2[4], cf[4];
             softmax4<C>(z2, q2, l2);
             if (A.mode == HPFG_LOSS_ICT) {
                 float z3[C][4], q3[C][4], l3[4];
