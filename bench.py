@@ -30,6 +30,15 @@ F_IN0 = 2.0 * 9 * H * W * IN_CH * 16
 MT_FLOP_PER_IMAGE = 4 * F_FWD - F_IN0    # student fwd+bwd + teacher fwd
 
 
+def _hbm_roofline(kernel, algo_bytes, cat, pk, note):
+    """Achieved algorithmic GB/s of one kernel category of the serialized profiling pass (CUDA events in the library)."""
+    if cat["ms_per_step"] <= 0:
+        return None
+    gbs = algo_bytes / (cat["ms_per_step"] * 1e-3) / 1e9
+    return {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
+            "us_per_step": cat["ms_per_step"] * 1e3, "algorithmic_bytes": algo_bytes, "traffic": None, "note": note}
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -251,6 +260,7 @@ def run_gpu(args):
         # tensor-core conv family: algorithmic FLOPs = every conv except in_conv.0 / out_conv fwd+dgrad (CUDA cores)
         # and all wgrads that still run on CUDA cores are excluded from the numerator of THIS kernel's roofline.
         n_img = N_L + N_U
+        n_params = student.flat_params.numel()
         f_out = 2.0 * 9 * H * W * 16 * N_CLS
         tc_fwd = F_FWD - F_IN0 - f_out                   # per image per forward
         tc_flops = n_img * (2 * tc_fwd + tc_fwd)         # student fwd + teacher fwd + dgrad (same GEMMs transposed)
@@ -289,6 +299,14 @@ def run_gpu(args):
                     "bound": "hbm", "achieved": top_bytes / (top_us * 1e-6) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": top_bytes / (top_us * 1e-6) / 1e9 / pk["hbm"], "us_per_launch": top_us,
                     "traffic": TOP_KERNEL_DRAM_BYTES, "traffic_source": "ncu --set full, profiles/r01_ncu_prof_fprop16_final_raw.txt (dram read+write per launch; the 51 MB output mostly stays in the 126 MB L2)"},
+                "roofline_loss": _hbm_roofline(
+                    "loss_reduce_kernel<4,MT> + loss_grad_kernel<4> (fused SSL loss value + dlogits, one call per step)",
+                    ((N_L + N_U) * N_CLS * H * W * 4.0 * 2 + N_U * N_CLS * H * W * 4.0 + N_L * H * W * 8.0),
+                    prof["ssl_loss"], pk, "SURVEY 8d: student logits read + teacher logits read + int64 labels read + dlogits written, "
+                    "each once (the kernels read the logits twice: Dice needs batch-wide sums before the gradient)"),
+                "roofline_sgd_ema": _hbm_roofline(
+                    "sgd_kernel<EMA> (SGD momentum + weight decay + EMA teacher, one pass over the flat buffers)",
+                    28.0 * n_params, prof["sgd_ema"], pk, "28 B per parameter: read p, g, m, ema; write p, m, ema"),
                 "layer_table": layers,
                 "kernel_time_per_step": prof,
                 "clocks": sampler.summary() if sampler else None}
