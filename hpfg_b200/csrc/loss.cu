@@ -38,6 +38,7 @@ struct LossArgs {
     int64_t *pseudo1, *pseudo2;
     double *acc;
     uint8_t *aux;   // CPS: pl1 | pl2 (n_u*hw each); UAMT: mask (n_u*hw)
+    FastDiv qdiv;   // division by hw/4 without the 64-bit integer divide (quad index -> image, quad in image)
 };
 
 template <int C>
@@ -141,9 +142,10 @@ __global__ void __launch_bounds__(256, MODE == HPFG_LOSS_S4CV ? 1 : 2) loss_redu
 #pragma unroll
         for (int e = 0; e < NSETS; ++e) sl[e][i] = su[e][i] = 0.f;
 
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_q;
-         q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t img = q / q_per_img, pix = (q - img * q_per_img) << 2;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < (uint32_t)total_q; q += gridDim.x * blockDim.x) {
+        uint32_t img32, rem32;
+        fast_divmod(q, A.qdiv, img32, rem32);
+        const int64_t img = img32, pix = (int64_t)rem32 << 2;
         // every global load of this quad is issued before any math: one DRAM round trip per iteration instead of two or
         // three dependent ones (the loads sit behind warp-uniform branches, so the compiler cannot hoist them itself)
         const bool labeled = img < A.n_l;
@@ -388,9 +390,10 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
     __syncthreads();
     const int64_t hw = A.hw, q_per_img = hw >> 2;
     const int64_t total_q = (int64_t)(A.n_l + A.n_u) * q_per_img;
-    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_q;
-         q += (int64_t)gridDim.x * blockDim.x) {
-        const int64_t img = q / q_per_img, pix = (q - img * q_per_img) << 2;
+    for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < (uint32_t)total_q; q += gridDim.x * blockDim.x) {
+        uint32_t img32, rem32;
+        fast_divmod(q, A.qdiv, img32, rem32);
+        const int64_t img = img32, pix = (int64_t)rem32 << 2;
         const int64_t so = (img * C) * hw + pix;
         float z[C][4], p[C][4], lse[4], g[C][4];
         if (img < A.n_l) {
@@ -637,7 +640,9 @@ static int ssl_loss_impl(int mode, const float *student, const float *other, con
     if (mode == HPFG_LOSS_UAMT) HPFG_REQUIRE(mc_logits && mc_passes > 0, "hpfg_ssl_loss: UAMT needs mc_logits");
     cudaStream_t st = (cudaStream_t)stream;
     LossArgs A{};
+    HPFG_REQUIRE((int64_t)(n_l + n_u) * height * width / 4 < (1LL << 31), "hpfg_ssl_loss: batch too large for 32-bit quad indexing");
     A.mode = mode; A.n_l = n_l; A.n_u = n_u; A.hw = height * width; A.mc_passes = mc_passes;
+    A.qdiv = make_fastdiv((uint32_t)(A.hw >> 2));
     A.student = student; A.other = other; A.mc = mc_logits; A.labels = labels;
     A.mix = mix; A.cons_weight2 = cons_weight2; A.cons_weight2_dev = cons_weight2_dev;
     A.uamt_threshold_dev = uamt_threshold_dev;
