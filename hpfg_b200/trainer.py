@@ -416,10 +416,10 @@ class UAMTStep(_StepBase):
         n_u = x_u.shape[0]
         if noise is None:
             noise = self.make_noise(x_u)
-        xr = x_u.repeat(2, 1, 1, 1)
         if self._use_graph():
             if mc_noise is None:
-                mc_noise = torch.clamp(torch.randn((self.T // 2,) + tuple(xr.shape), device=x.device, dtype=x.dtype) * 0.1, -0.2, 0.2)
+                mc_noise = torch.clamp(torch.randn((self.T // 2, 2 * n_u) + tuple(x_u.shape[1:]), device=x.device,
+                                                   dtype=x.dtype) * 0.1, -0.2, 0.2)
             dyn = self._dyn_scalars(self.ema_decay)
             thr = (0.75 + 0.25 * sigmoid_rampup(self.cur_itrs, self.total_itrs)) * math.log(2)
             out = self._graph_replay([x, labels, noise, mc_noise.contiguous()], dyn + [thr],
@@ -427,6 +427,7 @@ class UAMTStep(_StepBase):
             self.last = dict(scalars=out["scalars"], lr=dyn[0], w=dyn[3], threshold=thr, logits=out["logits"],
                              teacher_logits=out["teacher_logits"], mc_logits=out["mc_logits"])
             return out["scalars"][0]
+        xr = x_u.repeat(2, 1, 1, 1)
         noises = [mc_noise[i] if mc_noise is not None else self.make_noise(xr) for i in range(self.T // 2)]
         x_t = (x_u + noise).contiguous()
         x_mc = [(xr + nz).contiguous() for nz in noises]
