@@ -5,10 +5,13 @@
 //   2019_07_MICCAI_Uncertainty_Aware_ACDC.py:145-162,
 //   2022_02_ISBI_ICT-MedSeg_ACDC.py:111-137 (ICT: consistency against a per-sample mix of two teacher softmaxes),
 //   2022_08_CVPR_S4CVNet_ACDC.py:124-156 (two students, Dice-only cross pseudo supervision + Mean-Teacher MSE).
-// Dice is a ratio of batch-wide sums, so the gradient needs those sums first: phase 1 (reduce kernel) streams
-// the logits once and reduces with warp shuffles -> one double atomic per block per quantity; phase 2 (grad
-// kernel) streams them again (L2-resident: the logits are << 126 MB) and writes dlogits.  Both are pure HBM
-// kernels: NCHW fp32, 4 consecutive pixels per thread, 128-bit loads per class plane.
+// Dice is a ratio of batch-wide sums, so the gradient needs those sums first: phase 1 (reduce kernel) streams the logits that
+// carry batch-wide sums and reduces with warp shuffles -> one double atomic per block per quantity; phase 2 (grad kernel)
+// streams all logits (L2-resident: they are << 126 MB) and writes dlogits.  Only the LABELED images carry such sums in the
+// SUP / Mean-Teacher / ICT modes (Dice and the CE normaliser); the consistency term's gradient 2w/M*(p-q) needs none, so
+// its VALUE is accumulated by the gradient kernel itself and the last CTA to finish writes the loss scalars -- the reduce
+// kernel then touches n_l of the n_l+n_u images.  CPS / S4CV (pseudo-label Dice over the unlabeled images) and UAMT
+// (mask count) still reduce over the whole batch.  NCHW fp32, 4 consecutive pixels per thread, 128-bit loads per class plane.
 // Algorithmic bytes (MT): (n_l+n_u)*C*HW*4 read + n_u*C*HW*4 read + n_l*HW*8 read + (n_l+n_u)*C*HW*4 written.
 #include "common.cuh"
 #include <cstdlib>
@@ -21,6 +24,7 @@ constexpr int kAccMse = 4 * kAccPerSet;     // after the 4 (net,set) groups
 constexpr int kAccMaskSum = kAccMse + 1;
 constexpr int kAccMaskedDist = kAccMse + 2;
 constexpr int kAccTotal = 128;
+constexpr int kAccTicket = kAccTotal - 1;   // last slot, used as an unsigned block counter by the gradient kernel (MT / ICT)
 constexpr float kDiceSmooth = 1e-5f;
 
 struct LossArgs {
@@ -38,6 +42,7 @@ struct LossArgs {
     int64_t *pseudo1, *pseudo2;
     double *acc;
     uint8_t *aux;   // CPS: pl1 | pl2 (n_u*hw each); UAMT: mask (n_u*hw)
+    int reduce_imgs;   // images the reduce kernel streams: n_l for SUP / MT / ICT (their global sums only involve labeled pixels)
     FastDiv qdiv;   // division by hw/4 without the 64-bit integer divide (quad index -> image, quad in image)
 };
 
@@ -131,7 +136,7 @@ __global__ void __launch_bounds__(256, MODE == HPFG_LOSS_S4CV ? 1 : 2) loss_redu
     __shared__ float smem[8 * (2 * NS + 3)];
     __shared__ int slots[2 * NS + 3];
     const int64_t hw = A.hw, q_per_img = hw >> 2;
-    const int64_t n_img = A.n_l + A.n_u;
+    const int64_t n_img = A.reduce_imgs;
     const int64_t total_q = n_img * q_per_img;
     constexpr int NSETS = TWO ? 2 : 1;
     float sl[NSETS][NS];   // labeled sums, net 0 / net 1 (CPS, S4CV)
@@ -311,12 +316,17 @@ __device__ __forceinline__ void grad_sup(const float (&p)[C][4], const int (&lab
 
 template <int C>
 __device__ __forceinline__ void grad_mse(const float (&p)[C][4], const float (&q)[C][4], const float (&coef)[4],
-                                         float (&g)[C][4]) {
+                                         float (&g)[C][4], float *sq = nullptr) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
         float a[C], dot = 0.f;
 #pragma unroll
-        for (int c = 0; c < C; ++c) { a[c] = coef[j] * (p[c][j] - q[c][j]); dot += p[c][j] * a[c]; }
+        for (int c = 0; c < C; ++c) {
+            const float d = p[c][j] - q[c][j];
+            if (sq) *sq += d * d;
+            a[c] = coef[j] * d;
+            dot += p[c][j] * a[c];
+        }
 #pragma unroll
         for (int c = 0; c < C; ++c) g[c][j] = p[c][j] * (a[c] - dot);
     }
@@ -338,6 +348,10 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
     __shared__ float s_cons;      // per-element consistency coefficient
     const bool s4cv = A.mode == HPFG_LOSS_S4CV;
     const bool cps = A.mode == HPFG_LOSS_CPS || s4cv;   // two student networks
+    // Mean-Teacher / ICT: the consistency VALUE is accumulated here, next to its gradient, so the reduce kernel only has to
+    // stream the labeled images (the Dice / CE sums); the last CTA to finish writes loss and consistency term
+    const bool late_mse = A.mode == HPFG_LOSS_MT || A.mode == HPFG_LOSS_ICT;
+    float mse_local = 0.f;
     // weights of the pseudo-label terms: CPS = Med_Sup_Loss on the peer's labels, S4CV = Dice only (2022_08...:139-140)
     const float ps_ce = s4cv ? 0.f : A.ce_coef, ps_dice = s4cv ? 1.f : A.dice_coef;
     if (threadIdx.x == 0) {
@@ -349,8 +363,7 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
         }
         float cons = 0.f, cons_val = 0.f;
         const double M = (double)A.n_u * C * (double)A.hw;
-        if (A.mode == HPFG_LOSS_MT || A.mode == HPFG_LOSS_ICT) {
-            cons_val = (float)(A.acc[kAccMse] / M);
+        if (late_mse) {   // the squared distance is summed by THIS kernel (below); its gradient needs no global sum
             cons = (float)(2.0 * A.cons_weight / M);
         } else if (s4cv) {
             cons_val = (float)((A.acc[kAccMse] + A.acc[kAccMse + 1]) / M);   // consistency_loss1 + consistency_loss2
@@ -377,9 +390,11 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
                 s7 = cons_val;
                 aux = semi;
             }
-            A.scalars[0] = loss;
+            if (!late_mse) {
+                A.scalars[0] = loss;
+                A.scalars[2] = aux;
+            }
             A.scalars[1] = sup;
-            A.scalars[2] = aux;
             A.scalars[3] = coef[0].ce;
             A.scalars[4] = coef[0].dice;
             A.scalars[5] = (float)A.acc[3 * kMaxC + 1];
@@ -474,8 +489,29 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
             } else {
                 cf[0] = cf[1] = cf[2] = cf[3] = s_cons;
             }
-            grad_mse<C>(p, q2, cf, g);
+            grad_mse<C>(p, q2, cf, g, &mse_local);
             store4<C>(A.dstudent + so, hw, g);
+        }
+    }
+    if (late_mse) {
+        __shared__ float s_part[8];
+        const float v = warp_sum(mse_local);
+        if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double sum = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += (double)s_part[w];
+            atomicAdd(A.acc + kAccMse, sum);
+            __threadfence();
+            const unsigned ticket = atomicAdd(reinterpret_cast<unsigned *>(A.acc + kAccTicket), 1u);
+            if (ticket == gridDim.x - 1) {      // every CTA's partial is in: finish the scalars
+                __threadfence();
+                const double total = atomicAdd(A.acc + kAccMse, 0.0);
+                const float cons_val = (float)(total / ((double)A.n_u * C * (double)A.hw));
+                const float sup = A.ce_coef * coef[0].ce + A.dice_coef * coef[0].dice;
+                A.scalars[0] = sup + A.cons_weight * cons_val;
+                A.scalars[2] = cons_val;
+            }
         }
     }
 }
@@ -583,13 +619,14 @@ static int loss_grid(int64_t quads, int ctas_per_sm = 0) {
 template <int C>
 static int launch_loss(const LossArgs &A, cudaStream_t st) {
     const int grid = loss_grid((int64_t)(A.n_l + A.n_u) * (A.hw >> 2));
+    const int rgrid = loss_grid((int64_t)A.reduce_imgs * (A.hw >> 2));
     switch (A.mode) {
-        case HPFG_LOSS_SUP: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_SUP>, grid, 256, 0, st, A)); break;
-        case HPFG_LOSS_MT: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_MT>, grid, 256, 0, st, A)); break;
-        case HPFG_LOSS_CPS: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_CPS>, grid, 256, 0, st, A)); break;
-        case HPFG_LOSS_ICT: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_ICT>, grid, 256, 0, st, A)); break;
-        case HPFG_LOSS_S4CV: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_S4CV>, grid, 256, 0, st, A)); break;
-        default: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_UAMT>, grid, 256, 0, st, A)); break;
+        case HPFG_LOSS_SUP:      // SUP / MT / ICT: only the labeled images carry batch-wide sums (Dice, CE)
+        case HPFG_LOSS_MT:
+        case HPFG_LOSS_ICT: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_SUP>, rgrid, 256, 0, st, A)); break;
+        case HPFG_LOSS_CPS: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_CPS>, rgrid, 256, 0, st, A)); break;
+        case HPFG_LOSS_S4CV: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_S4CV>, rgrid, 256, 0, st, A)); break;
+        default: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_UAMT>, rgrid, 256, 0, st, A)); break;
     }
     HPFG_LAUNCH_CHECK();
     HPFG_CUDA_CHECK(launch_pdl(loss_grad_kernel<C>, grid, 256, 0, st, A));
@@ -643,6 +680,7 @@ static int ssl_loss_impl(int mode, const float *student, const float *other, con
     HPFG_REQUIRE((int64_t)(n_l + n_u) * height * width / 4 < (1LL << 31), "hpfg_ssl_loss: batch too large for 32-bit quad indexing");
     A.mode = mode; A.n_l = n_l; A.n_u = n_u; A.hw = height * width; A.mc_passes = mc_passes;
     A.qdiv = make_fastdiv((uint32_t)(A.hw >> 2));
+    A.reduce_imgs = (mode == HPFG_LOSS_SUP || mode == HPFG_LOSS_MT || mode == HPFG_LOSS_ICT) ? n_l : n_l + n_u;
     A.student = student; A.other = other; A.mc = mc_logits; A.labels = labels;
     A.mix = mix; A.cons_weight2 = cons_weight2; A.cons_weight2_dev = cons_weight2_dev;
     A.uamt_threshold_dev = uamt_threshold_dev;

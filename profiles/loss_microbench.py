@@ -35,6 +35,7 @@ for _ in range(iters):           # L2 flushed between calls (the 45 MB of logits
     torch.cuda.synchronize()
     tot += e0.elapsed_time(e1)
 us = tot / iters * 1e3
+algo = (n_l + n_u) * C * H * W * 4 * 2 + n_u * C * H * W * 4 + n_l * H * W * 8      # every tensor once
 # host-independent number: 20 calls captured into one CUDA graph, replayed (L2 warm: the 45 MB of logits stay resident,
 # which is also the in-step situation, where the conv kernel has just written them)
 gr = torch.cuda.CUDAGraph()
@@ -49,7 +50,7 @@ for _ in range(10):
 e1.record()
 torch.cuda.synchronize()
 us_graph = e0.elapsed_time(e1) / 200 * 1e3
-print("graph replay, L2 warm: %.2f us per call (memset + reduce + grad)" % us_graph)
-algo = (n_l + n_u) * C * H * W * 4 * 2 + n_u * C * H * W * 4 * 2 + n_l * H * W * 8 * 2 + (n_l + n_u) * C * H * W * 4
+print("graph replay, L2 warm: %.2f us per call (memset + reduce + grad) -> %.0f GB/s algorithmic (%.1f %% of 6553)"
+      % (us_graph, algo / us_graph / 1e3, 100 * algo / us_graph / 1e3 / 6553))
 print("HPFG_LOSS_CTAS_PER_SM=%s: memset + reduce + grad = %.2f us per call (L2 flushed), %.1f MB algorithmic -> %.0f GB/s (%.1f %% of 6553)"
       % (os.environ.get("HPFG_LOSS_CTAS_PER_SM", "default"), us, algo / 1e6, algo / us / 1e3, 100 * algo / us / 1e3 / 6553), "loss", sc[0].item())
