@@ -26,7 +26,7 @@ METRIC = "UNet SSL train images/sec @224x224 (Mean-Teacher step)"
 N_L, N_U, IN_CH, N_CLS, H, W = 8, 24, 1, 4, 224, 224
 F_FWD = 4516642816.0                 # conv FLOPs per image, forward
 TOP_KERNEL_DRAM_BYTES = 58.16e6      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_ncu_prof_fprop16_final_raw.txt)
-LOSS_DRAM_BYTES = 48197120 + 76288 + 48244992 + 1316352      # reduce read+write, gradient read+write (profiles/r01_ncu_loss_kernels.csv)
+LOSS_DRAM_BYTES = 9657856 + 2048 + 48247552 + 169216      # reduce read+write, gradient read+write (profiles/r01_ncu_loss_kernels.csv)
 F_IN0 = 2.0 * 9 * H * W * IN_CH * 16
 MT_FLOP_PER_IMAGE = 4 * F_FWD - F_IN0    # student fwd+bwd + teacher fwd
 
@@ -305,10 +305,10 @@ def run_gpu(args):
                     "loss_reduce_kernel<4,MT> + loss_grad_kernel<4> (fused SSL loss value + dlogits, one call per step)",
                     ((N_L + N_U) * N_CLS * H * W * 4.0 * 2 + N_U * N_CLS * H * W * 4.0 + N_L * H * W * 8.0),
                     prof["ssl_loss"], pk, "SURVEY 8d: student logits read + teacher logits read + int64 labels read + dlogits written, "
-                    "each once (the kernels read the logits twice: Dice needs batch-wide sums before the gradient); issue-bound "
-                    "(accurate expf softmax, ~700 instructions per 4-pixel quad), not HBM-bound: profiles/README.md",
+                    "each once (the labeled logits are read twice: Dice needs batch-wide sums before the gradient); issue-bound "
+                    "(accurate expf softmax of student and teacher, ~640 instructions per 4-pixel quad), not HBM-bound: profiles/README.md",
                     traffic=LOSS_DRAM_BYTES, traffic_source="ncu, profiles/r01_ncu_loss_kernels.csv (dram read+write of reduce + gradient, "
-                    "L2 flushed before the call: both kernels fetch the 48.2 MB of inputs from DRAM, the dlogits stay in L2)"),
+                    "L2 flushed before the call: the reduce kernel fetches the labeled 9.7 MB, the gradient kernel all 48.2 MB of inputs; the dlogits stay in L2)"),
                 "roofline_sgd_ema": _hbm_roofline(
                     "sgd_kernel<EMA> (SGD momentum + weight decay + EMA teacher, one pass over the flat buffers)",
                     28.0 * n_params, prof["sgd_ema"], pk, "28 B per parameter: read p, g, m, ema; write p, m, ema"),
