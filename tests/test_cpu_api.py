@@ -83,3 +83,32 @@ def test_host_schedules_match_oracle():
     a = type("A", (), dict(consistency=0.1, consistency_rampup=200.0))()
     for it in (1, 150, 1500, 40000):
         assert hb.get_current_consistency_weight(it // 150, a) == pytest.approx(oracle.consistency_weight(it), rel=1e-14)
+
+
+def test_python_constants_match_the_header():
+    header = open(os.path.join(ROOT, "include", "hpfg_b200.h")).read()
+    defs = dict(re.findall(r"#define\s+(HPFG_[A-Z0-9_]+)\s+(\d+)", header))
+    for name in ("SUP", "MT", "CPS", "UAMT", "ICT", "S4CV"):
+        assert int(defs["HPFG_LOSS_" + name]) == getattr(L, "LOSS_" + name), name
+    assert int(defs["HPFG_PREC_FP32"]) == L.PREC_FP32 and int(defs["HPFG_PREC_BF16"]) == L.PREC_BF16
+    assert int(defs["HPFG_NUM_BN"]) == L.NUM_BN and int(defs["HPFG_NUM_DROPOUT"]) == L.NUM_DROPOUT
+
+
+def test_unet_plus_mirrors_reference_structure():
+    """UNet_Plus (model/unet.py:178-206): 82 flat U-Net parameters + 16 neck parameters in the reference's order; the
+    necks stay ordinary torch parameters, deepcopy / load_state_dict keep the flat views intact."""
+    torch.manual_seed(4)
+    m = hb.build_model(type("A", (), dict(model="unet_plus", in_channels=1, num_classes=4))())
+    assert isinstance(m, hb.UNet_Plus)
+    names = [n for n, _ in m.named_parameters()]
+    spec = oracle.unet_param_spec(1, 4) + oracle.unet_plus_neck_spec(4)
+    assert [(n, tuple(p.shape)) for n, p in m.named_parameters()] == spec and len(names) == 98
+    assert m._is_flat() and len(m._flat_params_list) == 82
+    m2 = copy.deepcopy(m)
+    assert m2._is_flat() and m2.dense_projection_high.mlp[0].weight.data_ptr() != m.dense_projection_high.mlp[0].weight.data_ptr()
+    m2.load_state_dict(m.state_dict())
+    assert m2._is_flat() and all(torch.equal(a, b) for a, b in zip(m.parameters(), m2.parameters()))
+    with pytest.raises(L.HpfgError):
+        m(torch.zeros(1, 1, 32, 32))                      # CPU tensor: no fallback
+    with pytest.raises(NotImplementedError):
+        hb.build_model(type("A", (), dict(model="swinunet_plus", in_channels=1, num_classes=4))())
