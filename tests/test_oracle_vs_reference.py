@@ -68,3 +68,44 @@ def test_full_size_mt_step_matches_reference_objects():
         assert torch.allclose(student[k].float(), v.float(), atol=1e-6), k
     for k, v in ema.state_dict().items():
         assert torch.allclose(teacher[k].float(), v.float(), atol=1e-6), k
+
+
+def _same(a, b, path=""):
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and list(a.keys()) == list(b.keys()), path
+        for k in a:
+            _same(a[k], b[k], path + "/" + str(k))
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _same(x, y, path + "[%d]" % i)
+    elif torch.is_tensor(a):
+        assert torch.is_tensor(b) and a.dtype == b.dtype and a.shape == b.shape, path
+        assert torch.allclose(a.double(), b.double(), rtol=1e-5, atol=1e-7), path
+    elif isinstance(a, float):
+        assert a == pytest.approx(b, rel=1e-5, abs=1e-8), path
+    else:
+        assert a == b, path
+
+
+def test_committed_8f_fixtures_are_what_the_reference_produces(tmp_path, monkeypatch):
+    """Re-run tests/golden/make_golden.py's SURVEY-8f generators against the REAL reference modules (UNet_Plus, Dense_Loss,
+    DiceLoss, Medical_LR, update_ema_variables ...) and compare with the committed fixtures the GPU tests use."""
+    import importlib.util
+    import os
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    monkeypatch.setattr(sys, "argv", ["make_golden.py"])
+    spec = importlib.util.spec_from_file_location("_make_golden_check", os.path.join(here, "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    monkeypatch.setattr(mg, "HERE", str(tmp_path))
+    mg.golden_f4_losses()
+    mg.golden_ict_steps("acdc", 1, 4, 2, 4, 32, 32, 606)
+    mg.golden_predict(1, 4, 5, 32, 48, 707)
+    mg.golden_unet_plus(1, 4, 3, 64, 64, 808)
+    mg.golden_hpfg_step(1, 4, 2, 4, 64, 64, 909)
+    for name in ("f4_losses.pt", "ict_steps_acdc.pt", "predict_acdc.pt", "unet_plus_acdc.pt", "hpfg_step_acdc.pt"):
+        new = torch.load(os.path.join(str(tmp_path), name), weights_only=False)
+        old = torch.load(os.path.join(here, "golden", name), weights_only=False)
+        _same(old, new, name)
