@@ -65,7 +65,9 @@ def _worker(rank, world, port, q):
         grads[nm] = flat[off:off + n].view(st[nm].shape)
         off += n
     oracle.sgd_step(st, grads, opt, 0.01)
-    q.put((rank, order, torch.cat([st[nm].reshape(-1) for nm in names])))
+    # numpy, not a torch tensor: tensors travel through a file-descriptor side channel that dies with the worker, so a
+    # worker that exits before the parent has unpickled its result made the test flaky (FileNotFoundError in q.get)
+    q.put((rank, order, torch.cat([st[nm].reshape(-1) for nm in names]).numpy()))
     dist.destroy_process_group()
 
 
@@ -92,6 +94,7 @@ def test_two_rank_gloo_matches_mean_gradient_update():
     for p in procs:
         p.start()
     res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    res = [(r, o, torch.from_numpy(a)) for r, o, a in res]
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
