@@ -83,16 +83,19 @@ class _StepBase:
         fused loss, backward with its side-stream weight gradients, fused SGD(+EMA)).  The scalars that change per
         iteration -- learning rate, EMA alpha, consistency weight, UAMT threshold, dropout Philox offsets -- live in a
         small device block that is refreshed before every replay (the `_dv` entry points read them at run time).
-        data_parallel=True also captures the bucketed NCCL all-reduces of a multi-process run (measured on 2/4/8 B200
-        for the Mean-Teacher step); by default a data-parallel step stays eager."""
+        data_parallel=True also captures the bucketed NCCL all-reduces of a multi-process run (Mean-Teacher driver only,
+        measured on 2/4/8 B200; the other drivers stay eager when data parallel); by default a data-parallel step stays eager."""
         self._graph_enabled = bool(enabled)
         self._graph_dp = bool(data_parallel)      # also capture the NCCL bucket all-reduces (torch >= 2.x captures NCCL work)
         if not enabled:
             self._graph = None
             self._ggraph = None
 
+    _graph_dp_capable = False     # only the Mean-Teacher driver's capture with the NCCL all-reduces inside has been measured
+
     def _use_graph(self):
-        return self._graph_enabled and self.cur_itrs >= 2 and (self.world == 1 or self._graph_dp)
+        dp_ok = self.world == 1 or (self._graph_dp and self._graph_dp_capable)
+        return self._graph_enabled and self.cur_itrs >= 2 and dp_ok
 
     def _graph_replay(self, inputs, dyn_f, fwd_models, body):
         """Generic capture-once / replay driver (CPS, UAMT, ICT; Mean-Teacher keeps its own copy below).
@@ -224,6 +227,8 @@ class _StepBase:
 
 
 class MeanTeacherStep(_StepBase):
+    _graph_dp_capable = True
+
     def __init__(self, model, ema_model, *, ema_decay=0.99, **kw):
         super().__init__(**kw)
         self.model, self.ema_model, self.ema_decay = model, ema_model, ema_decay
