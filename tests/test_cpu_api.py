@@ -112,3 +112,24 @@ def test_unet_plus_mirrors_reference_structure():
         m(torch.zeros(1, 1, 32, 32))                      # CPU tensor: no fallback
     with pytest.raises(NotImplementedError):
         hb.build_model(type("A", (), dict(model="swinunet_plus", in_channels=1, num_classes=4))())
+
+
+def test_graph_replay_policy_host_logic():
+    """Which steps replay a CUDA graph is pure host logic: never the first iteration; under data parallelism only the
+    Mean-Teacher driver (whose capture with the NCCL all-reduces inside was measured) and only when asked to."""
+    a, b = hb.UNet(1, 4), hb.UNet(1, 4)
+    mt, cps, ict = hb.MeanTeacherStep(a, copy.deepcopy(a)), hb.CPSStep(a, b), hb.ICTStep(a, b)
+    for st in (mt, cps, ict):
+        assert not st._use_graph()
+        st.enable_graph(True)
+        st.cur_itrs = 1
+        assert not st._use_graph()
+        st.cur_itrs = 2
+        assert st._use_graph()
+        st.world = 2
+        assert not st._use_graph()                       # data parallel stays eager unless asked
+        st.enable_graph(True, data_parallel=True)
+    assert mt._use_graph() and not cps._use_graph() and not ict._use_graph()
+    mt.enable_graph(False)
+    assert not mt._use_graph()
+    assert mt._dyn_scalars(0.99)[0] == pytest.approx(hb.medical_lr(2, 0.01, 30000))
