@@ -173,6 +173,8 @@ __global__ void __launch_bounds__(256, MODE == HPFG_LOSS_S4CV ? 1 : 2) loss_redu
         } else if (MODE != HPFG_LOSS_SUP) {
             float p2[C][4], lse2[4];
             softmax4<C>(z2, p2, lse2);
+            // (the MT and ICT branches below are kept for reference but no longer instantiated: launch_loss runs the SUP
+            // instantiation over the labeled images for those modes and the gradient kernel sums the consistency value)
             if (MODE == HPFG_LOSS_MT) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
