@@ -292,15 +292,19 @@ class Dense_Loss(nn.Module):
         self.device, self.batch_size, self.temperature = device, batch_size, temperature
 
     def contrastive_loss(self, out_1, out_2):
-        out_1 = torch.nn.functional.normalize(out_1, dim=1).flatten(1)
-        out_2 = torch.nn.functional.normalize(out_2, dim=1).flatten(1)
-        out = torch.cat([out_1, out_2], dim=0)
-        sim_matrix = torch.exp(torch.mm(out, out.t().contiguous()) / self.temperature)
-        mask = (torch.ones_like(sim_matrix) - torch.eye(2 * self.batch_size, device=sim_matrix.device)).bool()
-        sim_matrix = sim_matrix.masked_select(mask).view(2 * self.batch_size, -1)
-        pos_sim = torch.exp(torch.sum(out_1 * out_2, dim=-1) / self.temperature)
-        pos_sim = torch.cat([pos_sim, pos_sim], dim=0)
-        return (-torch.log(pos_sim / sim_matrix.sum(dim=-1))).mean()
+        """-log(exp(s_i,pos / t) / sum_{j != i} exp(s_ij / t)) averaged over the 2B rows, s = <z_i, z_j> of the
+        channel-normalised, flattened features (utils/loss/dense_loss.py:18-34)."""
+        a = torch.nn.functional.normalize(out_1, dim=1).flatten(1)
+        b = torch.nn.functional.normalize(out_2, dim=1).flatten(1)
+        z = torch.cat([a, b], dim=0)
+        rows = z.shape[0]
+        if rows != 2 * self.batch_size:        # the reference builds its mask from the constructor's batch size
+            raise RuntimeError("Dense_Loss was built for batch %d, got %d" % (self.batch_size, rows // 2))
+        sim = torch.exp(z @ z.t() / self.temperature)
+        off_diag = ~torch.eye(rows, dtype=torch.bool, device=sim.device)
+        denom = (sim * off_diag).sum(dim=-1)          # the diagonal is the largest entry: mask it, never subtract it
+        pos = torch.exp((a * b).sum(dim=-1) / self.temperature).repeat(2)
+        return (-torch.log(pos / denom)).mean()
 
     def forward(self, x, y):
         x1, x2 = x

@@ -309,14 +309,10 @@ class projection_conv(nn.Module):
         self.pool = nn.AdaptiveAvgPool2d((s, s)) if self.is_s else None
 
     def forward(self, x):
-        x1 = self.avgpool(x)
-        x1 = x1.reshape(x1.size(0), -1)
-        x1 = self.mlp(x1)
-        if self.is_s:
-            x = self.pool(x)
-        x2 = self.mlp_conv(x)
-        x2 = x2.view(x2.size(0), x2.size(1), -1)
-        return x1, x2
+        pooled = self.pool(x) if self.is_s else x                      # dense branch input: [N, C, s, s]
+        global_vec = self.mlp(self.avgpool(x).flatten(1))              # [N, out_dim]
+        dense_map = self.mlp_conv(pooled).flatten(2)                   # [N, out_dim, s*s]
+        return global_vec, dense_map
 
 
 class UNet_Plus(UNet):
