@@ -168,3 +168,32 @@ def make_hpfg_batch(n_l, n_u, in_ch, n_cls, h, w, seed):
     x_l, x_u, y = make_batch(n_l, n_u, in_ch, n_cls, h, w, seed)
     x_l1, _, y1 = make_batch(n_l, 0, in_ch, n_cls, h, w, seed + 1)
     return x_l, y, x_l1, y1, x_u, make_cutmix_masks(n_u, h, w, seed + 2)
+
+
+# ---- BASELINE.json shapes (tests/golden/make_golden_full.py -> full_<tag>.pt; tests/test_gpu_full_size.py)
+FULL_CONFIGS = {
+    "mt_cfg1": dict(kind="mt", in_ch=1, n_cls=4, n_l=12, n_u=12, h=224, w=224, seed=1100, steps=1),
+    "mt_cfg2": dict(kind="mt", in_ch=1, n_cls=4, n_l=8, n_u=24, h=224, w=224, seed=1200, steps=2),
+    "cps": dict(kind="cps", in_ch=1, n_cls=4, n_l=8, n_u=24, h=224, w=224, seed=1300, steps=1),
+    "uamt": dict(kind="uamt", in_ch=1, n_cls=4, n_l=12, n_u=12, h=224, w=224, seed=1400, steps=1, T=8, teacher_gain=40.0),
+    "mt_isic": dict(kind="mt", in_ch=3, n_cls=2, n_l=12, n_u=12, h=224, w=224, seed=1500, steps=1),
+}
+
+
+def make_uamt_noise(n_u, in_ch, h, w, T, seed):
+    """The clamped Gaussian perturbations of 2019_07_MICCAI_Uncertainty_Aware_ACDC.py:130,141, seeded: one for the
+    teacher's consistency forward [n_u,...] and T//2 for the Monte-Carlo forwards over the batch repeated twice."""
+    g = gen(seed)
+    noise = torch.clamp(torch.randn(n_u, in_ch, h, w, generator=g) * 0.1, -0.2, 0.2)
+    mc = torch.clamp(torch.randn(T // 2, 2 * n_u, in_ch, h, w, generator=g) * 0.1, -0.2, 0.2)
+    return noise, mc
+
+
+def make_uamt_teacher_state(in_ch, n_cls, seed, gain):
+    """Teacher weights for the UAMT fixture: a random-init 4-class network is maximally uncertain everywhere (entropy ~ ln 4 >
+    the 0.75 ln 2 threshold of 2019_07...:158), which would leave the masked consistency term identically zero; the
+    output conv is centred and scaled by ``gain`` so that part of the pixels falls under the threshold."""
+    st = make_state(in_ch, n_cls, seed)
+    wo = st["decoder.out_conv.weight"]
+    st["decoder.out_conv.weight"] = (wo - wo.mean(dim=(1, 2, 3), keepdim=True)) * gain
+    return st
