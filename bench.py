@@ -1,15 +1,18 @@
 #!/usr/bin/env python
-"""bench.py -- throughput of the HPFG semi-supervised U-Net training step (Mean-Teacher) on B200.
+"""bench.py -- throughput of the HPFG semi-supervised U-Net training step on B200.
 
-    python bench.py --gpus N --steps K --warmup W              # this repo's sm_100a path
-    python bench.py --impl reference --gpus N --steps K --warmup W   # the reference algorithm on the host CPU cores
+    python bench.py --gpus N --steps K --warmup W                      # this repo's sm_100a path, BASELINE config 2 (Mean-Teacher 8+24)
+    python bench.py --config {mt_acdc,mt_cfg1,mt_isic,cps,uamt} ...    # the other BASELINE.json configurations
+    python bench.py --impl reference --gpus N --steps K --warmup W     # the reference algorithm on the host CPU cores
 
-A "step" is one Mean-Teacher iteration (2017_03_NIPS_Mean-Teacher_ACDC.py:89-113): student forward+backward,
-teacher forward, fused SSL loss, SGD and EMA, over one synthetic batch of ACDC-shaped 1x224x224 slices
-(config mean_teacher_unet_30k_224x224_ACDC: 8 labeled + 24 unlabeled per GPU, bf16 kernels).  Prints ONE JSON
-line (rank 0).  N>1 is launched by torchrun, one rank per GPU, data parallel (weak scaling: 32 images per GPU).
-"""
+A "step" is one training iteration of the configured trainer over one synthetic batch of 224x224 slices:
+  mt_*  2017_03_NIPS_Mean-Teacher_ACDC.py:89-113      student forward+backward, teacher forward, fused SSL loss, SGD, EMA
+  cps   2021_06_CVPR_CPS_ACDC.py:90-120               two students forward+backward, cross pseudo supervision, two SGD steps
+  uamt  2019_07_MICCAI_Uncertainty_Aware_ACDC.py:120-170   student forward+backward, 1 + T/2 noisy teacher forwards (T=8), masked MSE, SGD, EMA
+Prints ONE JSON line (rank 0).  N>1 is launched by torchrun, one rank per GPU, data parallel, weak scaling (the configured
+per-GPU batch on every rank, rank-distinct data, bucketed NCCL gradient all-reduce overlapped with backward)."""
 import argparse
+import copy
 import ctypes
 import json
 import os
@@ -22,13 +25,71 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "UNet SSL train images/sec @224x224 (Mean-Teacher step)"
-N_L, N_U, IN_CH, N_CLS, H, W = 8, 24, 1, 4, 224, 224
-F_FWD = 4516642816.0                 # conv FLOPs per image, forward
-TOP_KERNEL_DRAM_BYTES = 58.16e6      # dram__bytes_read.sum + dram__bytes_write.sum of one launch (profiles/r01_ncu_prof_fprop16_final_raw.txt)
+H, W = 224, 224
+F_FWD = 4516642816.0                 # conv FLOPs per image, forward (identical for 1ch/4cls and 3ch/2cls)
+CONFIGS = {
+    # BASELINE.json configs[1]: the configuration the metric is quoted on (config/mean_teacher_unet_30k_224x224_ACDC.yaml:13-14)
+    "mt_acdc": dict(kind="mt", in_ch=1, n_cls=4, n_l=8, n_u=24,
+                    workload="mean_teacher_unet_30k_224x224_ACDC (UNet 1ch/4cls, 8 labeled + 24 unlabeled 224x224 per GPU per step)"),
+    # configs[0]: the reference's own CPU-runnable case
+    "mt_cfg1": dict(kind="mt", in_ch=1, n_cls=4, n_l=12, n_u=12,
+                    workload="Mean-Teacher step, UNet 1ch/4cls, 12 labeled + 12 unlabeled 224x224 per GPU per step"),
+    # configs[4]: ISIC shape, 24 images per GPU (global 192 on 8 GPUs)
+    "mt_isic": dict(kind="mt", in_ch=3, n_cls=2, n_l=12, n_u=12,
+                    workload="Mean-Teacher step, ISIC-shape UNet 3ch/2cls, 12 labeled + 12 unlabeled 224x224 per GPU per step (global 192 on 8 GPUs)"),
+    # configs[2]: CPS (config/cps_unet_30k_224x224_ACDC.yaml:13-14)
+    "cps": dict(kind="cps", in_ch=1, n_cls=4, n_l=8, n_u=24,
+                workload="CPS cross pseudo supervision, two UNets 1ch/4cls, 8 labeled + 24 unlabeled 224x224 per GPU per step"),
+    # configs[3]: UAMT, T = 8 stochastic teacher forwards
+    "uamt": dict(kind="uamt", in_ch=1, n_cls=4, n_l=12, n_u=12, T=8,
+                 workload="UAMT uncertainty-aware Mean-Teacher, T=8, UNet 1ch/4cls, 12 labeled + 12 unlabeled 224x224 per GPU per step"),
+}
+METRICS = {"mt": "UNet SSL train images/sec @224x224 (Mean-Teacher step)", "cps": "UNet SSL train images/sec @224x224 (CPS step)",
+           "uamt": "UNet SSL train images/sec @224x224 (UAMT step, T=8)"}
+# dram__bytes_read.sum + dram__bytes_write.sum from ncu (see the named profile); None until measured for the current kernels
+TOP_KERNEL_DRAM_BYTES = 58.16e6      # one launch of the 3x3 16->16 @224 fprop (profiles/r01_ncu_prof_fprop16_final_raw.txt)
 LOSS_DRAM_BYTES = 9657856 + 2048 + 48247552 + 169216      # reduce read+write, gradient read+write (profiles/r01_ncu_loss_kernels.csv)
-F_IN0 = 2.0 * 9 * H * W * IN_CH * 16
-MT_FLOP_PER_IMAGE = 4 * F_FWD - F_IN0    # student fwd+bwd + teacher fwd
+CONV_FAMILY_DRAM_BYTES = None        # all tc_conv_kernel launches of one mt_acdc step
+CONV_FAMILY_DRAM_SOURCE = None
+
+
+def flops_per_step(c):
+    """Algorithmic conv FLOPs of one step: forward F_FWD per image; backward 2*F_FWD - f_in0."""
+    f_in0 = 2.0 * 9 * H * W * c["in_ch"] * 16
+    n = c["n_l"] + c["n_u"]
+    if c["kind"] == "mt":
+        return n * (4 * F_FWD - f_in0)                        # student fwd+bwd, teacher fwd on the whole batch
+    if c["kind"] == "cps":
+        return n * 2 * (3 * F_FWD - f_in0)
+    return n * (3 * F_FWD - f_in0) + c["n_u"] * F_FWD + c["T"] * c["n_u"] * F_FWD      # uamt: + teacher on n_u + T/2 forwards of 2*n_u
+
+
+def tc_conv_flops_per_step(c):
+    """FLOPs of the launches timed under the tensor-core conv category: EVERY forward conv (in_conv.0 padded to 16 channels
+    and out_conv included -- both run on the tensor-core kernel) of all forwards + every data gradient (all convs but in_conv.0)."""
+    f_in0 = 2.0 * 9 * H * W * c["in_ch"] * 16
+    n = c["n_l"] + c["n_u"]
+    if c["kind"] == "mt":
+        return n * (2 * F_FWD + (F_FWD - f_in0))
+    if c["kind"] == "cps":
+        return n * 2 * (F_FWD + (F_FWD - f_in0))
+    return n * (F_FWD + (F_FWD - f_in0)) + (c["n_u"] + c["T"] * c["n_u"]) * F_FWD
+
+
+def config_block(c, world):
+    """Identical in both arms (the driver compares them)."""
+    n = c["n_l"] + c["n_u"]
+    return {"workload": c["workload"], "global_batch": n * world, "parallelism": "dp%d" % world,
+            "l2": "per-step working set (~2 GB of activations per network) exceeds the 126 MB L2"}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                    src="MEASURED_PEAKS.json")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback (B200_PROFILING.md)")
 
 
 def _hbm_roofline(kernel, algo_bytes, cat, pk, note, traffic=None, traffic_source=None):
@@ -39,15 +100,6 @@ def _hbm_roofline(kernel, algo_bytes, cat, pk, note, traffic=None, traffic_sourc
     return {"kernel": kernel, "bound": "hbm", "achieved": gbs, "peak": pk["hbm"], "unit": "GB/s", "frac": gbs / pk["hbm"],
             "us_per_step": cat["ms_per_step"] * 1e3, "algorithmic_bytes": algo_bytes, "traffic": traffic,
             "traffic_source": traffic_source, "note": note}
-
-
-def peaks():
-    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.isfile(p):
-        d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sustained=d.get("bf16_tflops_sustained", d["bf16_tflops"]),
-                    src="measured")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sustained=1400.0, src="fallback")
 
 
 class ClockSampler(threading.Thread):
@@ -81,65 +133,166 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.samples)}
 
 
-def synthetic_batch(seed):
+def synthetic_batch(c, seed):
     import torch
     g = torch.Generator().manual_seed(seed)
-    x = torch.rand(N_L + N_U, IN_CH, H, W, generator=g)
-    y = torch.randint(0, N_CLS, (N_L, H, W), generator=g)
+    x = torch.rand(c["n_l"] + c["n_u"], c["in_ch"], H, W, generator=g)
+    y = torch.randint(0, c["n_cls"], (c["n_l"], H, W), generator=g)
     return x, y
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs
-def cpu_reference_steps(steps, warmup, n_l, n_u):
-    """The reference algorithm (oracle port of the MT step, torch CPU fp32, all host threads) on a bounded sample."""
+def _find_real_reference():
+    """The reference's own files, if a copy travelled to this machine ($HPFG_REF or baseline/_ref); None on the GPU box."""
+    for p in (os.environ.get("HPFG_REF"), os.path.join(ROOT, "baseline", "_ref")):
+        if p and os.path.isfile(os.path.join(p, "model", "unet.py")):
+            return p
+    return None
+
+
+def cpu_reference_steps(c, steps, warmup):
+    """The reference's CPU path (config `cuda: False`) for one step of config c, torch CPU fp32 on all host threads.
+    kind 'reference': the reference's own UNet / Med_Sup_Loss / update_ema_variables / Medical_LR objects loaded by file
+    path (Mean-Teacher only); kind 'port': oracle/ (the restatement pinned to them by tests/test_oracle_vs_reference.py)."""
     import torch
     import oracle
     torch.set_num_threads(os.cpu_count())
     torch.manual_seed(1337)
-    st = oracle.init_unet_state(IN_CH, N_CLS)
-    te = {k: v.clone() for k, v in st.items()}
-    opt = oracle.SGDState()
+    n_l, n_u, in_ch, n_cls = c["n_l"], c["n_u"], c["in_ch"], c["n_cls"]
     g = torch.Generator().manual_seed(1337)
-    x_l = torch.rand(n_l, IN_CH, H, W, generator=g)
-    x_u = torch.rand(n_u, IN_CH, H, W, generator=g)
-    y = torch.randint(0, N_CLS, (n_l, H, W), generator=g)
+    x_l = torch.rand(n_l, in_ch, H, W, generator=g)
+    x_u = torch.rand(n_u, in_ch, H, W, generator=g)
+    y = torch.randint(0, n_cls, (n_l, H, W), generator=g)
+    ref_root = _find_real_reference() if c["kind"] == "mt" else None
+    if ref_root is not None:
+        os.environ["HPFG_REF"] = ref_root
+        from oracle.ref_loader import load_reference
+        ref = load_reference()
+        model = ref.UNet(in_channels=in_ch, num_classes=n_cls)
+        ema_model = copy.deepcopy(model)
+        for p in ema_model.parameters():
+            p.requires_grad = False
+        optimizer = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
+        sched = ref.Medical_LR(optimizer=optimizer, base_lr=0.01, max_iterations=30000)
+        med_loss = ref.Med_Sup_Loss(n_cls)
+        args = type("A", (), dict(consistency=0.1, consistency_rampup=200.0))()
+        model.train()
+        ema_model.train()
+        x = torch.cat([x_l, x_u])
+
+        def one(it):                                     # 2017_03_NIPS_Mean-Teacher_ACDC.py:94-113
+            output = model(x)
+            output_soft = torch.softmax(output, dim=1)
+            with torch.no_grad():
+                ema_soft = torch.softmax(ema_model(x), dim=1)
+            loss = med_loss(output[:n_l], y) + ref.get_current_consistency_weight(it // 150, args) * \
+                torch.mean((output_soft[n_l:] - ema_soft[n_l:]) ** 2)
+            optimizer.zero_grad()
+            loss.backward()
+            optimizer.step()
+            sched.step()
+            ref.update_ema_variables(model, ema_model, 0.99, it)
+            return loss.item()
+        kind = "reference"
+    else:
+        st = oracle.init_unet_state(in_ch, n_cls)
+        opt = oracle.SGDState()
+        if c["kind"] == "mt":
+            te = {k: v.clone() for k, v in st.items()}
+            one = lambda it: oracle.mt_step(st, te, opt, x_l, x_u, y, it)          # noqa: E731
+        elif c["kind"] == "cps":
+            st2, opt2 = oracle.init_unet_state(in_ch, n_cls), oracle.SGDState()
+            one = lambda it: oracle.cps_step(st, st2, opt, opt2, x_l, x_u, y, it)  # noqa: E731
+        else:
+            te = oracle.init_unet_state(in_ch, n_cls)
+            T = c["T"]
+
+            def one(it):
+                noise = torch.clamp(torch.randn(x_u.shape) * 0.1, -0.2, 0.2)
+                mc = torch.clamp(torch.randn((T // 2, 2 * n_u) + tuple(x_u.shape[1:])) * 0.1, -0.2, 0.2)
+                return oracle.uamt_step(st, te, opt, x_l, x_u, y, it, noise, mc)
+        kind = "port"
     it = 0
     for _ in range(warmup):
         it += 1
-        oracle.mt_step(st, te, opt, x_l, x_u, y, it)
+        one(it)
     t0 = time.perf_counter()
     for _ in range(steps):
         it += 1
-        oracle.mt_step(st, te, opt, x_l, x_u, y, it)
+        one(it)
     dt = time.perf_counter() - t0
-    return (n_l + n_u) * steps / dt, dt / steps
+    return (n_l + n_u) * steps / dt, dt / steps, kind
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_l, n_u = 2, 6                                   # a quarter of the configured batch per step (bounded sample)
-    ips, sec = cpu_reference_steps(args.steps, args.warmup, n_l, n_u)
+    c = CONFIGS[args.config]
+    # every step is the full configured batch (BatchNorm / Dice see the real batch): ~1.7 s of host work per Mean-Teacher step
+    # on 16 cores; K and W are honoured up to 100 steps in total
+    steps = min(args.steps, 100)
+    warmup = min(args.warmup, 100 - steps) if steps < 100 else 0
+    ips, sec, kind = cpu_reference_steps(c, steps, warmup)
     cores = os.cpu_count()
-    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "mean_teacher_unet_30k_224x224_ACDC (UNet 1ch/4cls, 8 labeled + 24 unlabeled 224x224 per step)",
-                       "note": "reference algorithm on host CPU cores (cuda: False path), oracle port, torch fp32"},
-            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": "port",
-                             "sample": "%d+%d images per step (1/4 of the configured 8+24 batch), %d steps" % (n_l, n_u, args.steps)},
+    line = {"impl": "reference", "metric": METRICS[c["kind"]], "value": ips, "unit": "images/s", "n_gpus": args.gpus, "steps": steps,
+            "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config_block(c, args.gpus),
+            "note": "the reference's CPU path (config cuda: False) on the host cores of this box, one process, all threads; "
+                    "requested --steps %d --warmup %d bounded to %d + %d" % (args.steps, args.warmup, steps, warmup),
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": cores, "kind": kind,
+                             "sample": "the configured %d+%d images per step, %d timed steps after %d warm-up (%.2f s per step), torch fp32"
+                                       % (c["n_l"], c["n_u"], steps, warmup, sec)},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
+# ------------------------------------------------------------------------------------------------ torch-eager incumbent
+def incumbent_torch_eager(c, dev, steps=6, warm=3):
+    """SURVEY 8d "second baseline": the reference's module graph (the same Conv2d / BatchNorm2d / LeakyReLU / Dropout /
+    MaxPool2d / Upsample modules, wired as model/unet.py:12-117) and its Mean-Teacher step body in plain torch eager on this
+    GPU with cudnn.benchmark = True (2017_03...:44), fp32 and autocast(bf16) + channels_last.  Reported, not the product."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "profiles"))
+    import incumbent_baseline as ib
+    old = torch.backends.cudnn.benchmark
+    torch.backends.cudnn.benchmark = True
+    out = {}
+    try:
+        for amp in (False, True):
+            ms, _ = ib.run(dev, steps, warm, amp, n_l=c["n_l"], n_u=c["n_u"], in_ch=c["in_ch"], n_cls=c["n_cls"])
+            out["autocast_bf16_channels_last" if amp else "fp32"] = {"ms_per_step": ms, "images_per_s": (c["n_l"] + c["n_u"]) / ms * 1e3}
+    finally:
+        torch.backends.cudnn.benchmark = old
+    out["note"] = "torch %s eager, cudnn.benchmark=True, same module graph and step body as the reference trainer" % torch.__version__
+    return out
+
+
 # ------------------------------------------------------------------------------------------------ GPU arm
+def make_step(c, dev, graph_on, world):
+    import torch
+    import hpfg_b200 as hb
+    torch.manual_seed(1337)                              # identical replicas on every rank
+    a = hb.UNet(c["in_ch"], c["n_cls"], precision="bf16").to(dev)
+    if c["kind"] == "cps":
+        b = hb.UNet(c["in_ch"], c["n_cls"], precision="bf16").to(dev)
+        step = hb.CPSStep(a, b)
+    elif c["kind"] == "uamt":
+        b = hb.UNet(c["in_ch"], c["n_cls"], precision="bf16").to(dev)      # a separately built teacher (2019_07...:55)
+        step = hb.UAMTStep(a, b, T=c["T"])
+    else:
+        b = copy.deepcopy(a)
+        step = hb.MeanTeacherStep(a, b)
+    step.enable_graph(graph_on, data_parallel=world > 1)
+    return step, a, b
+
+
 def run_gpu(args):
     import torch
     import torch.distributed as dist
-    import hpfg_b200 as hb
     from hpfg_b200 import _lib as L
 
+    c = CONFIGS[args.config]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -150,15 +303,10 @@ def run_gpu(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = L.lib()
-
-    torch.manual_seed(1337)                              # identical replicas on every rank
-    student = hb.UNet(IN_CH, N_CLS, precision="bf16").to(dev)
-    import copy
-    teacher = copy.deepcopy(student)
-    step = hb.MeanTeacherStep(student, teacher)
     graph_on = not args.eager
-    step.enable_graph(graph_on, data_parallel=world > 1)     # whole-step CUDA graph replay (NCCL bucket all-reduces captured too); --eager disables it
-    x_cpu, y_cpu = synthetic_batch(1337 + rank)          # rank-distinct data, weak scaling
+    n_img = c["n_l"] + c["n_u"]
+
+    x_cpu, y_cpu = synthetic_batch(c, 1337 + rank)          # rank-distinct data, weak scaling
     x_pin, y_pin = x_cpu.pin_memory(), y_cpu.pin_memory()
     x_dev, y_dev = x_pin.to(dev), y_pin.to(dev)
     loss_pin = torch.empty(1, dtype=torch.float32).pin_memory()
@@ -168,6 +316,34 @@ def run_gpu(args):
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    # ---- data-parallel parity check (N > 1): the graph-replayed step with the NCCL all-reduces captured inside against the
+    # same step launched eagerly, and replica consistency across ranks -- so the scaling record carries DP parity
+    dp_check = None
+    if world > 1:
+        sa, ma, ea = make_step(c, dev, graph_on, world)
+        sb, mb, eb = make_step(c, dev, False, world)
+        dl = []
+        for _ in range(4):
+            la, lb = sa.step(x_dev, y_dev), sb.step(x_dev, y_dev)
+            dl.append(abs(la.item() - lb.item()))
+        barrier()
+
+        def digest(t):
+            return torch.stack([t.double().sum(), t.double().abs().sum(), (t.double() * (torch.arange(t.numel(), device=dev, dtype=torch.float64) % 7)).sum()])
+        dg = torch.cat([digest(ma.flat_params), digest(ea.flat_params), digest(ma.bn_running if c["kind"] == "cps" else sa.mom)])
+        allg = [torch.empty_like(dg) for _ in range(world)]
+        dist.all_gather(allg, dg)
+        same = all(torch.equal(allg[0][:6], g[:6]) for g in allg)         # parameters of both networks identical on every rank
+        dp_check = {"steps": 4, "graph_vs_eager_max_abs_loss_diff": max(dl),
+                    "graph_vs_eager_max_abs_param_diff": (ma.flat_params - mb.flat_params).abs().max().item(),
+                    "replicas_identical_across_ranks": bool(same), "loss_step4": la.item(),
+                    "note": "4 iterations on this rank's batch with two fresh replica sets: whole-step CUDA-graph replay incl. the "
+                            "captured NCCL bucket all-reduces vs eager launches; parameter digests all-gathered and compared"}
+        del sa, sb, ma, mb, ea, eb
+        torch.cuda.empty_cache()
+
+    step, student, other = make_step(c, dev, graph_on, world)
 
     def timed(fn, steps):
         barrier()
@@ -220,7 +396,8 @@ def run_gpu(args):
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    for _ in range(max(args.warmup, 3)):
+    warmup = max(args.warmup, 3)
+    for _ in range(warmup):
         resident_step()
     launches0 = lib.hpfg_launch_count() + step.replayed_kernels
     ms = timed(resident_step, args.steps)
@@ -232,9 +409,10 @@ def run_gpu(args):
     ms_e2e = timed(e2e_step, args.steps)
     if sampler:
         sampler.stop_flag = True
-    images = (N_L + N_U) * world
+    images = n_img * world
     value = images * args.steps / (ms * 1e-3)
     e2e_value = images * args.steps / (ms_e2e * 1e-3)
+    final_loss = step.last["scalars"][0].item()
 
     # ---- per-category device time (separate, untimed pass): roofline of the dominant kernel family
     prof_steps = 3
@@ -251,75 +429,84 @@ def run_gpu(args):
 
     def layer_us(op, cin, cout, ks, res, iters=20):
         ms_l = ctypes.c_float()
-        L.check(lib.hpfg_conv_tc_bench(op, N_L + N_U, res, res, cin, cout, ks, iters, ctypes.byref(ms_l), L.stream_ptr(dev)), "hpfg_conv_tc_bench")
+        L.check(lib.hpfg_conv_tc_bench(op, n_img, res, res, cin, cout, ks, iters, ctypes.byref(ms_l), L.stream_ptr(dev)), "hpfg_conv_tc_bench")
         return ms_l.value * 1e3
     names = ["conv_tcgen05", "conv_cuda_core", "wgrad_cuda_core", "bn_pool_upsample_glue", "ssl_loss", "sgd_ema", "weight_pack", "wgrad_tcgen05"]
     prof = {names[i]: {"ms_per_step": cat_ms[i] / prof_steps, "calls_per_step": cat_calls[i] / prof_steps} for i in range(8)}
     pk = peaks()
-    final_loss = step.last["scalars"][0].item()
 
     if rank == 0:
-        # tensor-core conv family: algorithmic FLOPs = every conv except in_conv.0 / out_conv fwd+dgrad (CUDA cores)
-        # and all wgrads that still run on CUDA cores are excluded from the numerator of THIS kernel's roofline.
-        n_img = N_L + N_U
         n_params = student.flat_params.numel()
-        f_out = 2.0 * 9 * H * W * 16 * N_CLS
-        tc_fwd = F_FWD - F_IN0 - f_out                   # per image per forward
-        tc_flops = n_img * (2 * tc_fwd + tc_fwd)         # student fwd + teacher fwd + dgrad (same GEMMs transposed)
+        tc_flops = tc_conv_flops_per_step(c)
         tc_ms = prof["conv_tcgen05"]["ms_per_step"]
         achieved = tc_flops / (tc_ms * 1e-3) / 1e12 if tc_ms > 0 else 0.0
-        # CPU baseline: the FULL configured batch (8+24: BatchNorm and Dice see the real batch), 1 warm-up + 5 timed steps
-        # = about 10 s of host work on the 16-core box
-        cpu_ips, cpu_sec = cpu_reference_steps(5, 1, N_L, N_U) if world == 1 and not args.no_cpu else (None, None)
-        # the single most expensive kernel instance: the 3x3 16->16 conv at 224x224 (4 launches per forward); it is bound by
-        # HBM / shared-memory operand bandwidth, not by the tensor pipe: algorithmic bytes = bf16 in + out once
+        step_flops = flops_per_step(c)
+        whole = value / images * step_flops / 1e12         # per-GPU TFLOP/s over the whole step (BASELINE.md's formula)
+        main_cfg = world == 1 and not args.quick
+        cpu = cpu_reference_steps(c, 5 if c["kind"] == "mt" else 3, 1) if world == 1 and not args.no_cpu else None
+        # the single most expensive kernel instance: the 3x3 16->16 conv at 224x224; bound by HBM / shared-memory operand
+        # bandwidth, not by the tensor pipe: algorithmic bytes = bf16 in + out once
         top_bytes = n_img * H * W * (16 + 16) * 2.0
-        top_us = layer_us(0, 16, 16, 3, H) if world == 1 else None
+        top_us = layer_us(0, 16, 16, 3, H) if main_cfg else None
         layers = []
-        if world == 1:
-            for cin, cout, ks, res in [(16, 16, 3, 224), (32, 16, 3, 224), (32, 32, 3, 112), (64, 64, 3, 56), (128, 128, 3, 28), (256, 256, 3, 14)]:
+        if main_cfg:
+            for cin, cout, ks, res in [(16, 16, 3, 224), (32, 16, 3, 224), (32, 32, 3, 112), (64, 64, 3, 56), (128, 64, 3, 56), (128, 128, 3, 28),
+                                       (256, 128, 3, 28), (256, 256, 3, 14)]:
                 px = n_img * res * res
                 t3 = [layer_us(op, cin, cout, ks, res) for op in (0, 1, 2)]
+                fl = 2.0 * px * cin * cout * ks * ks
                 layers.append({"layer": "%dx%d conv %d->%d @%d" % (ks, ks, cin, cout, res), "fprop_us": t3[0], "dgrad_us": t3[1], "wgrad_us": t3[2],
                                "fprop_hbm_frac": px * (cin + cout) * 2.0 / (t3[0] * 1e-6) / 1e9 / pk["hbm"],
-                               "fprop_tensor_frac": 2.0 * px * cin * cout * ks * ks / (t3[0] * 1e-6) / 1e12 / pk["tf_burst"]})
-        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                               "fprop_tensor_frac": fl / (t3[0] * 1e-6) / 1e12 / pk["tf_burst"],
+                               "dgrad_tensor_frac": fl / (t3[1] * 1e-6) / 1e12 / pk["tf_burst"],
+                               "wgrad_tensor_frac": fl / (t3[2] * 1e-6) / 1e12 / pk["tf_burst"]})
+        cfg = config_block(c, world)
+        line = {"metric": METRICS[c["kind"]], "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
-                "data": "synthetic",
-                "config": {"workload": "mean_teacher_unet_30k_224x224_ACDC (UNet 1ch/4cls, 8 labeled + 24 unlabeled 224x224 per GPU per step)",
-                           "global_batch": images, "parallelism": "dp%d" % world, "launch": "cuda-graph replay" if graph_on else "eager (PDL)", "l2": "per-step working set (~2 GB of activations) exceeds the 126 MB L2",
-                           "final_loss": final_loss},
+                "data": "synthetic", "config": cfg,
+                "run": {"config_name": args.config, "launch": "cuda-graph replay" if graph_on else "eager (PDL)", "final_loss": final_loss},
                 "e2e": {"value": e2e_value, "unit": "images/s", "ms_per_step": ms_e2e / args.steps,
                         "h2d_bytes_per_step": x_pin.numel() * 4 + y_pin.numel() * 8, "d2h_bytes_per_step": 4},
                 "gpu_launches": int(launches),
-                "conv_tensor_fraction_of_step": {"achieved_tflops_whole_step": value / world * MT_FLOP_PER_IMAGE / 1e12,
-                                                 "frac_of_peak": value / world * MT_FLOP_PER_IMAGE / 1e12 / pk["tf_sustained"]},
-                "roofline": {"kernel": "tc_conv_kernel (tcgen05 implicit-GEMM conv family: fprop + dgrad + 1x1)", "bound": "tensor",
-                             "achieved": achieved, "peak": pk["tf_sustained"], "unit": "TFLOP/s",
-                             "frac": achieved / pk["tf_sustained"], "traffic": None, "peak_source": pk["src"] + " sustained bf16",
-                             "note": "all tensor-core conv launches of a step (serialized profiling pass); FLOPs = SURVEY 8d"},
+                "conv_tensor_fraction_of_step": {"achieved_tflops_whole_step": whole, "frac_of_burst_peak": whole / pk["tf_burst"],
+                                                 "note": "images/s/GPU x algorithmic conv FLOPs per image (SURVEY 8d) over the WHOLE step time"},
+                "roofline": {"kernel": "tc_conv_kernel (tcgen05 implicit-GEMM conv family: every fprop incl. in_conv.0 and the logits conv, dgrad, 1x1)",
+                             "bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
+                             "traffic": CONV_FAMILY_DRAM_BYTES, "traffic_source": CONV_FAMILY_DRAM_SOURCE,
+                             "peak_source": pk["src"] + ", burst bf16", "launches_per_step": prof["conv_tcgen05"]["calls_per_step"],
+                             "us_per_step": tc_ms * 1e3, "algorithmic_flops_per_step": tc_flops,
+                             "note": "ALL tensor-core conv launches of a step (serialized profiling pass, CUDA events in the library) "
+                                     "over the algorithmic FLOPs of exactly those launches (SURVEY 8d)"},
                 "roofline_top_kernel": None if top_us is None else {
                     "kernel": "tc_conv_kernel<3,16,16,RES,MT=4,XF=1> (3x3 16->16 @224, fused BN+LeakyReLU loader, BN-stat epilogue)",
                     "bound": "hbm", "achieved": top_bytes / (top_us * 1e-6) / 1e9, "peak": pk["hbm"], "unit": "GB/s",
                     "frac": top_bytes / (top_us * 1e-6) / 1e9 / pk["hbm"], "us_per_launch": top_us,
                     "traffic": TOP_KERNEL_DRAM_BYTES, "traffic_source": "ncu --set full, profiles/r01_ncu_prof_fprop16_final_raw.txt (dram read+write per launch; the 51 MB output mostly stays in the 126 MB L2)"},
-                "roofline_loss": _hbm_roofline(
-                    "loss_reduce_kernel<4,MT> + loss_grad_kernel<4> (fused SSL loss value + dlogits, one call per step)",
-                    ((N_L + N_U) * N_CLS * H * W * 4.0 * 2 + N_U * N_CLS * H * W * 4.0 + N_L * H * W * 8.0),
-                    prof["ssl_loss"], pk, "SURVEY 8d: student logits read + teacher logits read + int64 labels read + dlogits written, "
-                    "each once (the labeled logits are read twice: Dice needs batch-wide sums before the gradient); issue-bound "
-                    "(accurate expf softmax of student and teacher, ~640 instructions per 4-pixel quad), not HBM-bound: profiles/README.md",
-                    traffic=LOSS_DRAM_BYTES, traffic_source="ncu, profiles/r01_ncu_loss_kernels.csv (dram read+write of reduce + gradient, "
-                    "L2 flushed before the call: the reduce kernel fetches the labeled 9.7 MB, the gradient kernel all 48.2 MB of inputs; the dlogits stay in L2)"),
                 "roofline_sgd_ema": _hbm_roofline(
-                    "sgd_kernel<EMA> (SGD momentum + weight decay + EMA teacher, one pass over the flat buffers)",
-                    28.0 * n_params, prof["sgd_ema"], pk, "28 B per parameter: read p, g, m, ema; write p, m, ema"),
+                    "sgd_kernel (SGD momentum + weight decay (+ EMA teacher), one pass per network over the flat buffers)",
+                    (28.0 if c["kind"] != "cps" else 2 * 20.0) * n_params, prof["sgd_ema"], pk,
+                    "28 B per parameter with EMA: read p, g, m, ema; write p, m, ema (20 B without)"),
                 "layer_table": layers,
                 "kernel_time_per_step": prof,
                 "clocks": sampler.summary() if sampler else None}
-        if cpu_ips is not None:
-            line["cpu_baseline"] = {"value": cpu_ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
-                                    "sample": "the configured 8+24 images per step, 5 timed steps after 1 warm-up (%.1f s per step), torch fp32, all host threads" % cpu_sec}
+        if c["kind"] == "mt":
+            line["roofline_loss"] = _hbm_roofline(
+                "loss_reduce_kernel<MT> + loss_grad_kernel (fused SSL loss value + dlogits, one call per step)",
+                (n_img * c["n_cls"] * H * W * 4.0 * 2 + c["n_u"] * c["n_cls"] * H * W * 4.0 + c["n_l"] * H * W * 8.0),
+                prof["ssl_loss"], pk, "SURVEY 8d: student logits read + teacher logits read + int64 labels read + dlogits written, each once",
+                traffic=LOSS_DRAM_BYTES if args.config == "mt_acdc" else None,
+                traffic_source="ncu, profiles/r01_ncu_loss_kernels.csv (dram read+write of reduce + gradient, L2 flushed before the call)")
+        if dp_check is not None:
+            line["dp_check"] = dp_check
+        if cpu is not None:
+            line["cpu_baseline"] = {"value": cpu[0], "unit": "images/s", "cores": os.cpu_count(), "kind": cpu[2],
+                                    "sample": "the configured %d+%d images per step, %d timed steps after 1 warm-up (%.2f s per step), torch fp32, all host threads"
+                                              % (c["n_l"], c["n_u"], 5 if c["kind"] == "mt" else 3, cpu[1])}
+        if main_cfg and c["kind"] == "mt" and not args.no_incumbent:
+            try:
+                line["incumbent_torch_eager"] = incumbent_torch_eager(c, dev)
+            except Exception as exc:                     # a reported extra; never fails the bench line
+                line["incumbent_torch_eager"] = {"error": str(exc)[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -331,7 +518,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--config", default="mt_acdc", choices=sorted(CONFIGS))
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-incumbent", action="store_true", help="skip the torch-eager incumbent leg")
+    ap.add_argument("--quick", action="store_true", help="skip the per-layer table and the incumbent leg")
     ap.add_argument("--eager", action="store_true", help="launch every kernel from the host each step instead of replaying a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -28,6 +28,7 @@ SIGNATURES = {
     "hpfg_unet_plan_create": (c_int, [c_int, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_vp)]),
     "hpfg_unet_plan_destroy": (c_int, [c_vp]),
     "hpfg_unet_plan_workspace_bytes": (c_i64, [c_vp]),
+    "hpfg_unet_plan_set_bwd_fusion": (c_int, [c_vp, c_int]),
     "hpfg_unet_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u64, c_u64,
                                   ctypes.POINTER(c_vp), c_vp]),
     "hpfg_unet_forward_dv": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u64, c_vp,
@@ -43,6 +44,9 @@ SIGNATURES = {
     "hpfg_conv_tc_debug": (c_int, [c_int] * 7 + [c_vp] * 8),
     "hpfg_conv_tc_bench": (c_int, [c_int] * 8 + [ctypes.POINTER(c_f), c_vp]),
     "hpfg_wgrad_tc_debug": (c_int, [c_int] * 6 + [c_vp] * 7),
+    "hpfg_dgrad_tc_fused_debug": (c_int, [c_int] * 6 + [c_vp] * 10 + [c_f] + [c_vp] * 3),
+    "hpfg_wgrad_tc_fused_debug": (c_int, [c_int] * 6 + [c_vp] * 11),
+    "hpfg_glue_debug": (c_int, [c_int] * 5 + [c_vp] * 8 + [c_f] + [c_vp] * 3),
     "hpfg_ssl_loss_workspace_bytes": (c_i64, [c_int] * 6),
     "hpfg_ssl_loss": (c_int, [c_int, c_vp, c_vp, c_vp, c_int, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_f,
                               ctypes.POINTER(c_f), c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
@@ -55,6 +59,7 @@ SIGNATURES = {
     "hpfg_ict_mix": (c_int, [c_vp, c_vp, c_vp, c_int, c_i64, c_vp, c_vp]),
     "hpfg_s4cv_loss": (c_int, [c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_f, c_f, c_vp,
                                ctypes.POINTER(c_f), c_f, c_f, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_vp]),
+    "hpfg_softmax_mse": (c_int, [c_vp, c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, c_vp, c_vp]),
     "hpfg_argmax_labels": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "hpfg_dice_loss": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f), c_vp, c_vp, c_vp,
                                c_vp]),

@@ -134,6 +134,11 @@ __device__ __forceinline__ void fast_divmod(uint32_t n, const FastDiv &f, uint32
     r = n - q * f.d;
 }
 
+// Persistent-CTA budget of the tensor-core kernels per kind (0 forward convs, 1 data gradients, 2 weight gradients).  A kernel
+// with one 200 KB CTA per SM on all 148 SMs leaves no room for the kernels of the other stream; capping the grids lets the two
+// streams of a step (student | teacher forward, dgrad chain | weight gradients) run on disjoint SMs at the same time.
+int tc_cta_cap(int kind);
+
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
 
 // ---- optional per-category device timing (bench.py's roofline leg): CUDA events around each host launcher ----

@@ -85,10 +85,11 @@ static void pick_cfg(int cin_v, int cout_v, int &KC, int &BN) {
 }
 
 // explicit instantiations live in conv_tc_inst*.cu
-static int launch_ks(int ks, int KC, int BN, int mt, int xf, bool nchw, const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+static int launch_ks(int ks, int KC, int BN, int mt, int xf, int epi, const CUtensorMap &map, const CUtensorMap &map2, const TcConvParams &P,
+                     cudaStream_t s) {
 #define HPFG_TC_CASE(kc, bn)                                                        \
     if (KC == kc && BN == bn)                                                       \
-        return ks == 3 ? tc_launch<3, kc, bn>(mt, xf, nchw, map, P, s) : tc_launch<1, kc, bn>(mt, xf, nchw, map, P, s);
+        return ks == 3 ? tc_launch<3, kc, bn>(mt, xf, epi, map, map2, P, s) : tc_launch<1, kc, bn>(mt, xf, epi, map, map2, P, s);
     HPFG_TC_CASE(16, 16) HPFG_TC_CASE(16, 32) HPFG_TC_CASE(16, 128) HPFG_TC_CASE(32, 16) HPFG_TC_CASE(32, 32) HPFG_TC_CASE(32, 64)
 #undef HPFG_TC_CASE
     set_error("tc conv: no kernel for KC=" + std::to_string(KC) + " BN=" + std::to_string(BN));
@@ -96,12 +97,13 @@ static int launch_ks(int ks, int KC, int BN, int mt, int xf, bool nchw, const CU
 }
 
 static long long *g_tc_trace = nullptr;
+static int g_tc_kind = 0;   // 0 forward conv, 1 data gradient (set by the entry points around tc_run: single host thread per plan)
 static int g_tc_dbg = 0;   // bottleneck-isolation switches, set only by the micro-benchmark entry (never by the product path)
 
 // Run one convolution (conv-view channels cin_v -> cout_v) on the tensor cores.
 static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void *in, void *out, const bf16 *bpk,
                   const float *bias, LoadXform xf, float *stats, int *P_out, cudaStream_t s, float *out_nchw = nullptr,
-                  int out_c_real = 0) {
+                  int out_c_real = 0, const TcBwdFuse *fuse = nullptr) {
     ProfScope _prof(PROF_CONV_TC, s);
     int KC, BN;
     pick_cfg(cin_v, cout_v, KC, BN);
@@ -112,8 +114,11 @@ static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void
         if (W % (4 * kTW) == 0 && N * th * (W / (4 * kTW)) >= 2 * kNumSMs) mt = 4;
         else if (W % (2 * kTW) == 0 && N * th * (W / (2 * kTW)) >= 2 * kNumSMs) mt = 2;
     }
-    CUtensorMap map;
+    CUtensorMap map, map2;
     HPFG_RETURN_IF(make_map_chunked(&map, in, N, H, W, cin_v, KC / 8, kTW * mt + ks - 1, kTH + ks - 1));
+    map2 = map;
+    const bool two = fuse && fuse->in_raw, gstat = fuse && fuse->out_raw;
+    if (two) HPFG_RETURN_IF(make_map_chunked(&map2, fuse->in_raw, N, H, W, cin_v, KC / 8, kTW * mt + ks - 1, kTH + ks - 1));
     TcConvParams P{};
     P.bpk = bpk; P.out = (bf16 *)out; P.bias = bias;
     P.scale = xf.scale; P.shift = xf.shift;
@@ -125,14 +130,23 @@ static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void
     P.m_tiles = N * P.tiles_h * P.tiles_w; P.n_blocks = cout_v / BN; P.k_chunks = cin_v / KC;
     P.dbg = g_tc_dbg;
     P.trace = g_tc_trace;
-    if (P_out) *P_out = std::min(P.m_tiles * P.n_blocks, kNumSMs);
-    const int xfm = xf.scale ? (xf.drop.bits ? 2 : 1) : 0;
-    return launch_ks(ks, KC, BN, mt, xfm, out_nchw != nullptr, map, P, s);
+    P.max_ctas = tc_cta_cap(g_tc_kind);
+    if (P_out) *P_out = std::min(P.m_tiles * P.n_blocks, P.max_ctas);
+    int xfm = xf.scale ? (xf.drop.bits ? 2 : 1) : 0;
+    if (two) {          // BatchNorm backward in the loader: draw = sc*g + kb*raw + kd
+        xfm = 3;
+        P.scale = fuse->sc; P.shift = fuse->kb; P.kd = fuse->kd;
+    }
+    if (gstat) {
+        P.gs_raw = (const bf16 *)fuse->out_raw; P.gs_scale = fuse->gs_scale; P.gs_shift = fuse->gs_shift;
+        P.gs_dropbits = reinterpret_cast<const uint16_t *>(fuse->gs_dropbits); P.gs_inv_keep = fuse->gs_inv_keep;
+    }
+    return launch_ks(ks, KC, BN, mt, xfm, out_nchw != nullptr ? 1 : (gstat ? 2 : 0), map, map2, P, s);
 }
 
 // micro-benchmark entry (wgrad_tc.cu: hpfg_conv_tc_bench): packs once per call (cheap) and launches one convolution
 int tc_run_bench(int op, int ks, int N, int H, int W, int cin, int cout, const void *in, void *out, const float *w, const float *scale,
-                 const float *shift, float *stats, cudaStream_t s) {
+                 const float *shift, float *stats, cudaStream_t s, int fuse_mode, const void *aux) {
     static bf16 *packed = nullptr;
     static long long packed_n = 0;
     const long long n = (long long)cin * cout * ks * ks;
@@ -150,7 +164,11 @@ int tc_run_bench(int op, int ks, int N, int H, int W, int cin, int cout, const v
     const bool want_trace = getenv("HPFG_TC_TRACE") != nullptr;
     if (want_trace && !g_tc_trace) cudaMalloc(&g_tc_trace, 6 * 64 * 8);
     if (!want_trace) g_tc_trace = nullptr;
-    const int rc = tc_run(ks, N, H, W, cin_v, cout_v, in, out, packed, nullptr, xf, stats, nullptr, s);
+    TcBwdFuse f;        // fuse_mode (data gradients only): bit 0 two-source loader, bit 1 GSTAT epilogue; aux = a second bf16 tensor
+    if (fuse_mode & 1) { f.in_raw = aux; f.sc = scale; f.kb = scale; f.kd = scale; }
+    if (fuse_mode & 2) { f.out_raw = aux; f.gs_scale = scale; f.gs_shift = scale; }
+    if (fuse_mode) { xf.scale = nullptr; xf.shift = nullptr; }
+    const int rc = tc_run(ks, N, H, W, cin_v, cout_v, in, out, packed, nullptr, xf, stats, nullptr, s, nullptr, 0, fuse_mode ? &f : nullptr);
     g_tc_dbg = 0;
     if (want_trace && getenv("HPFG_TC_TRACE_DUMP")) {       // print CTA 0's per-role timestamps (cycles since the CTA's setup barrier)
         long long h[6 * 64];
@@ -258,23 +276,28 @@ int tc_fprop_logits(hpfg_unet_plan *p, int conv, const void *in, LoadXform xf, c
                   logits_nchw, cv.cout);
 }
 
-int tc_dgrad(hpfg_unet_plan *p, int conv, const void *dout, void *din, bool *done, cudaStream_t s) {
+int tc_dgrad(hpfg_unet_plan *p, int conv, const void *dout, void *din, bool *done, cudaStream_t s, const TcBwdFuse *fuse, float *stats,
+             int *P) {
     auto *st = reinterpret_cast<TcPlanState *>(p->tc);
     const ConvLayer &cv = p->d.convs[conv];
     *done = false;
     if (st->d_off[conv] < 0) return HPFG_OK;
     const LoadXform none{};
-    HPFG_RETURN_IF(tc_run(cv.ks, p->N, cv.H, cv.W, pad16(cv.cout), cv.cin, dout, din, st->packed + st->d_off[conv], nullptr, none, nullptr, nullptr, s));
+    g_tc_kind = 1;
+    const int rc = tc_run(cv.ks, p->N, cv.H, cv.W, pad16(cv.cout), cv.cin, dout, din, st->packed + st->d_off[conv], nullptr, none,
+                          (fuse && fuse->out_raw) ? stats : nullptr, P, s, nullptr, 0, fuse);
+    g_tc_kind = 0;
+    HPFG_RETURN_IF(rc);
     *done = true;
     return HPFG_OK;
 }
 
 int tc_wgrad(hpfg_unet_plan *p, int conv, const void *in, LoadXform xf, const void *dout, float *dw_oihw, float *dbias,
-             int accumulate, bool *done, cudaStream_t s) {
+             int accumulate, bool *done, cudaStream_t s, const TcBwdFuse *fuse) {
     const ConvLayer &cv = p->d.convs[conv];
     *done = false;
     HPFG_RETURN_IF(tc_wgrad_run(cv.ks, p->N, cv.H, cv.W, pad16(cv.cin), pad16(cv.cout), cv.cin, cv.cout, in, xf, dout, p->wscratch,
-                                p->wscratch_floats, dw_oihw, dbias, accumulate, s));
+                                p->wscratch_floats, dw_oihw, dbias, accumulate, s, fuse));
     *done = true;
     return HPFG_OK;
 }
@@ -327,6 +350,53 @@ extern "C" int hpfg_conv_tc_debug(int op, int N, int H, int W, int cin, int cout
     cudaStreamSynchronize(s);
     cudaFree(packed);
     cudaFree(partials);
+    if (rc == HPFG_OK) HPFG_CUDA_CHECK(cudaGetLastError());
+    return rc;
+}
+
+// Layer-isolated hook for the BatchNorm-backward fusions of the data-gradient kernel (see include/hpfg_b200.h).
+extern "C" int hpfg_dgrad_tc_fused_debug(int N, int H, int W, int cin, int cout, int ks, const void *g_in, const void *raw_in,
+                                         const float *sc, const float *kb, const float *kd, const float *w_oihw, const void *raw_out,
+                                         const float *gs_scale, const float *gs_shift, const uint8_t *gs_keep_mask_nchw, float gs_p_drop,
+                                         void *out_bf16_nhwc, float *stats_out, void *stream) {
+    HPFG_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && (ks == 1 || ks == 3), "hpfg_dgrad_tc_fused_debug: unsupported shape");
+    HPFG_REQUIRE(g_in && w_oihw && out_bf16_nhwc, "hpfg_dgrad_tc_fused_debug: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    PackTable T{};
+    T.n = 1;
+    T.total = (long long)cin * cout * ks * ks;
+    pick_cfg(cout, cin, T.e[0].KC, T.e[0].BN);
+    T.e[0].dst_begin = 0; T.e[0].w_off = 0; T.e[0].cin = cin; T.e[0].cout = cout; T.e[0].kk = ks * ks; T.e[0].dgrad = 1;
+    T.e[0].cin_real = cin; T.e[0].cout_real = cout;
+    bf16 *packed = nullptr;
+    float *partials = nullptr;
+    uint32_t *bits = nullptr;
+    HPFG_CUDA_CHECK(cudaMalloc(&packed, (size_t)T.total * 2));
+    HPFG_CUDA_CHECK(cudaMalloc(&partials, (size_t)kNumSMs * 2 * cin * 4));
+    HPFG_CUDA_CHECK(launch_pdl(tc_pack_kernel, pack_grid(T), 256, 0, s, w_oihw, packed, T, 0));
+    HPFG_LAUNCH_CHECK();
+    if (gs_keep_mask_nchw) {
+        HPFG_CUDA_CHECK(cudaMalloc(&bits, ((size_t)N * H * W * cin + 31) / 32 * 4));
+        HPFG_RETURN_IF(dropout_bits(bits, gs_keep_mask_nchw, N, H, W, cin, gs_p_drop, 0, 0, s));
+    }
+    HPFG_CUDA_CHECK(cudaStreamSynchronize(s));
+    TcBwdFuse f;
+    if (raw_in) { f.in_raw = raw_in; f.sc = sc; f.kb = kb; f.kd = kd; }
+    if (raw_out) {
+        f.out_raw = raw_out; f.gs_scale = gs_scale; f.gs_shift = gs_shift;
+        f.gs_dropbits = bits; f.gs_inv_keep = bits ? 1.f / (1.f - gs_p_drop) : 1.f;
+    }
+    const LoadXform none{};
+    int P = 0;
+    int rc = tc_run(ks, N, H, W, cout, cin, g_in, out_bf16_nhwc, packed, nullptr, none, raw_out ? partials : nullptr, &P, s, nullptr, 0, &f);
+    if (rc == HPFG_OK && stats_out && raw_out) {
+        HPFG_CUDA_CHECK(launch_pdl(tc_debug_reduce_stats, (2 * cin + 127) / 128, 128, 0, s, partials, P, 2 * cin, stats_out));
+        ++g_launch_count;
+    }
+    cudaStreamSynchronize(s);
+    cudaFree(packed);
+    cudaFree(partials);
+    if (bits) cudaFree(bits);
     if (rc == HPFG_OK) HPFG_CUDA_CHECK(cudaGetLastError());
     return rc;
 }

@@ -27,9 +27,16 @@ constexpr int kXfWarps = 8;                // loader-transform warps (warps 4-11
 constexpr int kXfThreads = kXfWarps * 32;
 constexpr int kTcThreads = 128 + kXfThreads + 128;   // + warps 0-3 (TMA, MMA, TMEM alloc, idle) + 4 epilogue warps
 constexpr int kMaxStages = 12;
-constexpr int kSmemBudget = 200 * 1024;
+constexpr int kSmemBudget = 216 * 1024;
 
-template <int KS, int KC, int BN, bool RES, int MT>
+// Loader transforms (XF): 0 none; 1 BatchNorm affine + LeakyReLU of the producer; 2 = 1 + dropout keep bits;
+// 3 = BatchNorm BACKWARD of the layer this data gradient enters through: the operand is built from TWO staged tiles,
+//     draw = sc*g + kb*raw + kd  (g = dact * leaky' * dropout', raw = the layer's saved conv output; glue.cuh BnState).
+// Epilogues (EPI): 0 bf16 NHWC store (+ BatchNorm statistics partials when P.stats); 1 fp32 NCHW logits + bias;
+// 2 = "GSTAT": the accumulator is the gradient wrt the ACTIVATED output of a BatchNorm layer; the epilogue reads that
+//     layer's raw tensor at the same pixel, stores g = dact * leaky'(bn(raw)) * dropout' and accumulates the two
+//     BatchNorm-backward sums (sum g | sum g*raw) into the statistics partials -- bn_bwd pass 0 never runs.
+template <int KS, int KC, int BN, bool RES, int MT, bool TWO = false>
 struct TcCfg {
     static constexpr int PAD = KS / 2, KK = KS * KS;
     static constexpr int TWP = kTW * MT;
@@ -44,9 +51,10 @@ struct TcCfg {
     static constexpr int al(int v) { return (v + 127) / 128 * 128; }
     static constexpr int OFF_B = al(OP_BYTES);
     // RES: the whole packed weight of the layer (one k-chunk, one n-block) stays resident in shared memory
-    static constexpr int STAGE_BYTES = OFF_B + (RES ? 0 : al(B_BYTES));
+    static constexpr int OFF_R = OFF_B + (RES ? 0 : al(B_BYTES));      // second source tile (TWO: the raw tensor of XF = 3)
+    static constexpr int STAGE_BYTES = OFF_R + (TWO ? al(OP_BYTES) : 0);
     static constexpr int RESB_BYTES = RES ? al(B_BYTES) : 0;
-    static constexpr int FIXED_BYTES = 1024 /*barriers*/ + 2 * 256 * 4 /*scale,shift*/ + 4 * 2 * BN * 4 /*stat partials*/;
+    static constexpr int FIXED_BYTES = 1024 /*barriers*/ + 5 * 256 * 4 /*scale,shift,kd | epilogue scale,shift*/ + 4 * 2 * BN * 4 /*stat partials*/;
     static constexpr int STAGES_RAW = (kSmemBudget - FIXED_BYTES - RESB_BYTES) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > kMaxStages ? kMaxStages : STAGES_RAW;
     static constexpr int SMEM_BYTES = RESB_BYTES + STAGES * STAGE_BYTES + FIXED_BYTES + 1024 /*alignment slack*/;
@@ -61,13 +69,20 @@ struct TcConvParams {
     const bf16 *bpk;          // packed weights: [n_block][k_chunk][tap][KC/8][BN][8]
     bf16 *out;                // NHWC [N,H,W,Cout]
     const float *bias;        // Cout floats or nullptr
-    const float *scale, *shift;   // per input channel (producer's fused BN affine); required when XF > 0
+    const float *scale, *shift;   // per input channel (producer's fused BN affine); required when XF > 0.  XF == 3: sc, kb
+    const float *kd;          // XF == 3: the third BatchNorm-backward constant per input channel
     const uint8_t *dropbits;  // producer's dropout keep bits, NHWC bit order; required when XF == 2
+    // EPI == 2 (GSTAT): the BatchNorm layer whose activated-output gradient this kernel produces
+    const bf16 *gs_raw;       // its raw conv output, NHWC [N,H,W,Cout]
+    const float *gs_scale, *gs_shift;   // its fused forward affine (z = raw*scale + shift)
+    const uint16_t *gs_dropbits;        // its dropout keep bits (16 channels per halfword) or nullptr
+    float gs_inv_keep;
     float inv_keep;
     float *stats;             // [gridDim.x][2*Cout] per-CTA partial sums (sum | sum of squares) or nullptr
     float *out_nchw;          // NCHW kernels: fp32 [N,out_c_real,H,W] (+bias) instead of bf16 NHWC (out_conv logits)
     int out_c_real;
     int N, H, W, Cin, Cout, tiles_h, tiles_w, m_tiles, n_blocks, k_chunks;
+    int max_ctas;             // grid cap (a multiple of n_blocks): persistent CTAs of this launch
     long long *trace;         // optional (micro-benchmark only): CTA 0 records clock64 per role and stage, [role][64]
     int dbg;                  // bottleneck-isolation switches (env HPFG_TC_DBG, profiles/ only): 1 no MMA, 2 no stores, 4 no stats, 8 no TMA
 };
@@ -110,7 +125,7 @@ template <int KS, int KC, int BN, bool RES, int MT, int XF>
 __device__ __forceinline__ void tc_mma_role(uint32_t bar_full, uint32_t bar_xf, uint32_t bar_empty, uint32_t bar_tfull, uint32_t bar_tempty,
                                          uint32_t stage_u32, uint32_t res_u32, uint32_t tmem_base, int n_work, int k_chunks, int dbg,
                                          long long *trace) {
-    using C = TcCfg<KS, KC, BN, RES, MT>;
+    using C = TcCfg<KS, KC, BN, RES, MT, XF == 3>;
     const int lane = threadIdx.x & 31;
     {
         constexpr uint32_t idesc = ptx::umma_idesc_bf16(128, BN, 0, 0);
@@ -177,9 +192,11 @@ __device__ __forceinline__ void tc_mma_role(uint32_t bar_full, uint32_t bar_xf, 
 }
 
 // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-11 transform (XF > 0 only), 12-15 epilogue.
-template <int KS, int KC, int BN, bool RES, int MT, int XF, bool NCHW>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const TcConvParams P) {
-    using C = TcCfg<KS, KC, BN, RES, MT>;
+template <int KS, int KC, int BN, bool RES, int MT, int XF, int EPI>
+__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmR,
+                                                                const TcConvParams P) {
+    using C = TcCfg<KS, KC, BN, RES, MT, XF == 3>;
+    constexpr bool NCHW = EPI == 1, GSTAT = EPI == 2;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *res_b = smem;                                         // resident weights (RES only)
@@ -189,7 +206,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fixed + 512);
     float *s_scale = reinterpret_cast<float *>(fixed + 1024);
     float *s_shift = s_scale + 256;
-    float *s_part = s_shift + 256;                                 // [4 warps][2*BN]
+    float *s_kd = s_shift + 256;
+    float *s_gsc = s_kd + 256;                                     // GSTAT: forward affine of the output-side BatchNorm
+    float *s_gsh = s_gsc + 256;
+    float *s_part = s_gsh + 256;                                   // [4 warps][2*BN]
 
     pdl_launch_dependents();
     // broadcast from lane 0: tells the compiler the warp index is warp-uniform, so role branches and everything
@@ -207,7 +227,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     // ring of weight stages is requested BEFORE griddepcontrol.wait: their latency overlaps the previous kernel's tail.
     const int total_flat = n_work * P.k_chunks;
     const int pre = RES ? (total_flat > 0 ? 1 : 0) : (total_flat < C::STAGES ? total_flat : C::STAGES);
-    const uint32_t op_bytes = (P.dbg & 8) ? 0u : (uint32_t)C::OP_BYTES;
+    const uint32_t op_bytes = (P.dbg & 8) ? 0u : (uint32_t)(C::OP_BYTES * (XF == 3 ? 2 : 1));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
@@ -221,6 +241,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&tmA);
+        if (XF == 3) ptx::prefetch_tensormap(&tmR);
         const bf16 *bsrc0 = P.bpk + (size_t)nb * P.k_chunks * (C::B_BYTES / 2);
         for (int f = 0; f < pre; ++f) {
             const uint32_t fb = bar_full + 8 * f;
@@ -232,7 +253,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
     pdl_wait();       // everything above is private setup; below reads what the previous kernel wrote
     if (XF > 0)
-        for (int i = threadIdx.x; i < P.Cin; i += blockDim.x) { s_scale[i] = P.scale[i]; s_shift[i] = P.shift[i]; }
+        for (int i = threadIdx.x; i < P.Cin; i += blockDim.x) {
+            s_scale[i] = P.scale[i];
+            s_shift[i] = P.shift[i];
+            if (XF == 3) s_kd[i] = P.kd[i];
+        }
+    if (GSTAT)
+        for (int i = threadIdx.x; i < P.Cout; i += blockDim.x) { s_gsc[i] = P.gs_scale[i]; s_gsh[i] = P.gs_shift[i]; }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -263,7 +290,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                             ptx::bulk_load(sb + C::OFF_B, bsrc + (size_t)kc * (C::B_BYTES / 2), C::B_BYTES, fb);
                         }
                     }
-                    if (!(P.dbg & 8)) ptx::tma_load_5d(sb, &tmA, fb, 0, w0, h0, kc * C::NCH, ti.n_img);
+                    if (!(P.dbg & 8)) {
+                        ptx::tma_load_5d(sb, &tmA, fb, 0, w0, h0, kc * C::NCH, ti.n_img);
+                        if (XF == 3) ptx::tma_load_5d(sb + C::OFF_R, &tmR, fb, 0, w0, h0, kc * C::NCH, ti.n_img);
+                    }
                 }
                 __syncwarp();
                 if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
@@ -300,12 +330,16 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
 #pragma unroll 1
                 for (int kc = 0; kc < P.k_chunks; ++kc) {
                     const int ch = kc * KC + c * 8;
-                    float scl[8], shf[8];
+                    float scl[8], shf[8], kdv[XF == 3 ? 8 : 1];
                     {
                         const float4 a0 = *reinterpret_cast<const float4 *>(s_scale + ch), a1 = *reinterpret_cast<const float4 *>(s_scale + ch + 4);
                         const float4 b0 = *reinterpret_cast<const float4 *>(s_shift + ch), b1 = *reinterpret_cast<const float4 *>(s_shift + ch + 4);
                         scl[0] = a0.x; scl[1] = a0.y; scl[2] = a0.z; scl[3] = a0.w; scl[4] = a1.x; scl[5] = a1.y; scl[6] = a1.z; scl[7] = a1.w;
                         shf[0] = b0.x; shf[1] = b0.y; shf[2] = b0.z; shf[3] = b0.w; shf[4] = b1.x; shf[5] = b1.y; shf[6] = b1.z; shf[7] = b1.w;
+                        if (XF == 3) {
+                            const float4 d0 = *reinterpret_cast<const float4 *>(s_kd + ch), d1 = *reinterpret_cast<const float4 *>(s_kd + ch + 4);
+                            kdv[0] = d0.x; kdv[1] = d0.y; kdv[2] = d0.z; kdv[3] = d0.w; kdv[4] = d1.x; kdv[5] = d1.y; kdv[6] = d1.z; kdv[7] = d1.w;
+                        }
                     }
                     // dropout keep bytes come from global memory: fetch them all BEFORE waiting for the stage, so their latency
                     // hides behind the TMA wait instead of sitting inside the per-item dependency chain
@@ -330,12 +364,19 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                             const uint32_t keep = XF == 2 ? keepv[k] : 0xffu;
                             float f[8];
                             unpack8(ptx::lds128(addr), f);
+                            if (XF == 3) {
+                                float r[8];
+                                unpack8(ptx::lds128(addr + C::OFF_R), r);
 #pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                float a = fmaf(f[j], scl[j], shf[j]);
-                                a = fmaxf(a, kLeakySlope * a);
-                                if (XF == 2) a = ((keep >> j) & 1u) ? a * P.inv_keep : 0.f;
-                                f[j] = a;
+                                for (int j = 0; j < 8; ++j) f[j] = fmaf(scl[j], f[j], fmaf(shf[j], r[j], kdv[j]));
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) {
+                                    float a = fmaf(f[j], scl[j], shf[j]);
+                                    a = fmaxf(a, kLeakySlope * a);
+                                    if (XF == 2) a = ((keep >> j) & 1u) ? a * P.inv_keep : 0.f;
+                                    f[j] = a;
+                                }
                             }
                             uint4 v = make_uint4(pack2(f[0], f[1]), pack2(f[2], f[3]), pack2(f[4], f[5]), pack2(f[6], f[7]));
                             if (!inside) v = make_uint4(0u, 0u, 0u, 0u);
@@ -357,9 +398,11 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         const int mr = m / kTW, mc = m % kTW;
         const int et = threadIdx.x - (128 + kXfThreads);
         constexpr int NG = BN / 16;
-        // BatchNorm statistics.  BN <= 32: lane-private running sums over ALL pixels this lane ever sees (one FADD + one
-        // FFMA per value), reduced across lanes once per CTA.  BN >= 64: per-tile shuffle butterfly into one running
-        // value per 16-column group (register budget).  Either way: one partial row per CTA, fixed summation order.
+        // Per-channel sums (train-mode BatchNorm statistics: sum x | sum x^2; GSTAT: sum g | sum g*raw).
+        // BN <= 32: lane-private running sums over ALL pixels this lane ever sees (one FADD + one FFMA per value), reduced
+        // across lanes once per CTA.  BN >= 64: per-tile shuffle butterfly into one running value per 16-column group
+        // (register budget; a shared-memory transpose of the 32 x 16 block measured SLOWER: 7.1 k vs 5.5 k cycles per
+        // 128 x 128 tile, profiles/README.md).  Either way: one partial row per CTA, fixed summation order.
         constexpr bool LANE_STATS = BN <= 32;
         constexpr int NRUN = LANE_STATS ? BN : NG;
         float run1[NRUN], run2[NRUN];
@@ -367,7 +410,6 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         for (int i = 0; i < NRUN; ++i) run1[i] = run2[i] = 0.f;
         const bool want_stats = !NCHW && P.stats != nullptr && !(P.dbg & 4);    // the logits layer has no BatchNorm
         const bool no_store = (P.dbg & 2) != 0;
-        // store one tile-row pixel: NC consecutive output channels starting at channel c0 of this n-block
         // NCHW (logits) kernels: BN == 16, one n-block; the bias of the real output channels lives in registers
         float bias_r[NCHW ? 16 : 1];
         const size_t plane = (size_t)P.H * P.W;
@@ -375,6 +417,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
 #pragma unroll
             for (int i = 0; i < 16; ++i) bias_r[i] = (P.bias && i < P.out_c_real) ? P.bias[i] : 0.f;
         }
+        // store one pixel's 16 consecutive output channels starting at channel c0 of this n-block
         auto store16 = [&](const float *v, size_t pix, int n_img, int gh, int gw, int c0) {
             if constexpr (NCHW) {
                 float *o = P.out_nchw + ((size_t)n_img * P.out_c_real * P.H + gh) * P.W + gw;
@@ -385,77 +428,103 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                 bf16 *orow = P.out + pix * P.Cout + nb * BN + c0;
                 float b[16];
 #pragma unroll
-                for (int i = 0; i < 16; ++i) b[i] = v[i] + (P.bias ? P.bias[nb * BN + c0 + i] : 0.f);
+                for (int i = 0; i < 16; ++i) b[i] = v[i] + ((!GSTAT && P.bias) ? P.bias[nb * BN + c0 + i] : 0.f);
                 *reinterpret_cast<uint4 *>(orow) = make_uint4(pack2(b[0], b[1]), pack2(b[2], b[3]), pack2(b[4], b[5]), pack2(b[6], b[7]));
                 *reinterpret_cast<uint4 *>(orow + 8) = make_uint4(pack2(b[8], b[9]), pack2(b[10], b[11]), pack2(b[12], b[13]), pack2(b[14], b[15]));
             }
         };
+        // One 16-channel group of one pixel: accumulator values v (fp32) -> the stored values (in place) and the two summed
+        // quantities a | b.  GSTAT needs the output-side raw tensor (and dropout bits) of the same pixel / channels.
+        auto transform16 = [&](float *v, float *b2, bool valid, const uint4 &r0, const uint4 &r1, uint32_t keep16, int c0) {
+            if constexpr (GSTAT) {
+                float xa[8], xb[8], x[16];
+                unpack8(r0, xa);
+                unpack8(r1, xb);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) { x[i] = xa[i]; x[8 + i] = xb[i]; }
+                const float *gsc = s_gsc + nb * BN + c0, *gsh = s_gsh + nb * BN + c0;
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    const float z = fmaf(x[i], gsc[i], gsh[i]);
+                    float g = z > 0.f ? v[i] : kLeakySlope * v[i];
+                    if (P.gs_dropbits) g = ((keep16 >> i) & 1u) ? g * P.gs_inv_keep : 0.f;
+                    g = valid ? g : 0.f;
+                    v[i] = g;
+                    b2[i] = g * x[i];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 16; ++i) {
+                    v[i] = valid ? v[i] : 0.f;
+                    b2[i] = v[i] * v[i];
+                }
+            }
+        };
+        // groups of one work item: grp -> (UMMA tile j = grp / NG, channel group gi = grp % NG); batches of GB groups share one
+        // tcgen05.wait::ld (register budget: GB * 16 accumulator registers + the running sums)
+        constexpr int TG = MT * NG;
+        constexpr int GB0 = LANE_STATS ? (BN == 16 ? (GSTAT ? 2 : 4) : (GSTAT ? 1 : 2)) : (GSTAT ? 2 : 4);
+        constexpr int GB = GB0 < TG ? GB0 : TG;
         TileIter ti;
         ti.init(mt0, mstep, P.tiles_h, P.tiles_w);
 #pragma unroll 1
         for (int it = 0; it < n_work; ++it) {
             const int acc = it % C::NACC, acc_phase = (it / C::NACC) & 1;
-            ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase, 6);
-            ptx::tc_fence_after();
-            if (q == 0) HPFG_TRACE(3, it);
             const int gh = ti.th * kTH + mr, gw0 = ti.tw * C::TWP + mc;
             const size_t pix0 = ((size_t)ti.n_img * P.H + gh) * P.W + gw0;
-            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
-            if constexpr (LANE_STATS) {
-                // the accumulator loads of a batch of tiles are issued before the single wait (latency overlap)
-                constexpr int TPB0 = BN == 16 ? 4 : 1;     // register budget: 32 running sums + 64 loaded values (BN=16), 64 + 32 (BN=32)
-                constexpr int TPB = TPB0 < MT ? TPB0 : MT;
-#pragma unroll 1
-                for (int j0 = 0; j0 < MT; j0 += TPB) {
-                    uint32_t r[TPB][BN];
+            // GSTAT: the first batch's raw values are requested before the accumulator wait (their latency hides behind it)
+            uint4 rw[GSTAT ? GB : 1][2];
+            uint32_t kp[GSTAT ? GB : 1];
+            auto load_raw = [&](int b0) {
+                if constexpr (GSTAT) {
 #pragma unroll
-                    for (int t = 0; t < TPB; ++t)
-#pragma unroll
-                        for (int gidx = 0; gidx < NG; ++gidx) ptx::tmem_ld16(taddr + (j0 + t) * BN + gidx * 16, r[t] + gidx * 16);
-                    ptx::tmem_ld_wait();
-#pragma unroll
-                    for (int t = 0; t < TPB; ++t) {
-                        const int gw = gw0 + (j0 + t) * kTW;
-                        const bool valid = gh < P.H && gw < P.W;
-                        float v[BN];
-#pragma unroll
-                        for (int i = 0; i < BN; ++i) v[i] = valid ? __uint_as_float(r[t][i]) : 0.f;
-                        if (want_stats) {
-#pragma unroll
-                            for (int i = 0; i < BN; ++i) { run1[i] += v[i]; run2[i] = fmaf(v[i], v[i], run2[i]); }
-                        }
-                        if (valid && !no_store) {
-#pragma unroll
-                            for (int gidx = 0; gidx < NG; ++gidx) store16(v + gidx * 16, pix0 + (j0 + t) * kTW, ti.n_img, gh, gw, gidx * 16);
+                    for (int t = 0; t < GB; ++t) {
+                        const int grp = b0 + t, j = grp / NG, c0 = (grp % NG) * 16;
+                        const bool valid = gh < P.H && gw0 + j * kTW < P.W;
+                        const size_t e = (pix0 + j * kTW) * P.Cout + nb * BN + c0;
+                        rw[t][0] = rw[t][1] = make_uint4(0u, 0u, 0u, 0u);
+                        kp[t] = 0xffffu;
+                        if (valid) {
+                            rw[t][0] = *reinterpret_cast<const uint4 *>(P.gs_raw + e);
+                            rw[t][1] = *reinterpret_cast<const uint4 *>(P.gs_raw + e + 8);
+                            if (P.gs_dropbits) kp[t] = P.gs_dropbits[e >> 4];
                         }
                     }
                 }
-            } else {
-#pragma unroll 1
-                for (int j = 0; j < MT; ++j) {
+            };
+            load_raw(0);
+            ptx::mbar_wait(bar_tfull + 8 * acc, acc_phase, 6);
+            ptx::tc_fence_after();
+            if (q == 0) HPFG_TRACE(3, it);
+            const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + acc * C::ACC_COLS;
+#pragma unroll
+            for (int b0 = 0; b0 < TG; b0 += GB) {
+                uint32_t r[GB][16];
+#pragma unroll
+                for (int t = 0; t < GB; ++t) ptx::tmem_ld16(taddr + (b0 + t) * 16, r[t]);      // column of group grp = j*BN + gi*16 = grp*16
+                if (b0 > 0) load_raw(b0);
+                ptx::tmem_ld_wait();
+#pragma unroll
+                for (int t = 0; t < GB; ++t) {
+                    constexpr int dummy = 0;
+                    (void)dummy;
+                    const int grp = b0 + t, j = grp / NG, gi = grp % NG;
                     const int gw = gw0 + j * kTW;
                     const bool valid = gh < P.H && gw < P.W;
+                    float v[16], b2[16];
 #pragma unroll
-                    for (int g0 = 0; g0 < NG; g0 += 4) {
-                        uint32_t r[4][16];
+                    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[t][i]);
+                    transform16(v, b2, valid, rw[GSTAT ? t : 0][0], rw[GSTAT ? t : 0][1], kp[GSTAT ? t : 0], gi * 16);
+                    if (want_stats) {
+                        if constexpr (LANE_STATS) {
 #pragma unroll
-                        for (int t = 0; t < 4; ++t) ptx::tmem_ld16(taddr + j * BN + (g0 + t) * 16, r[t]);
-                        ptx::tmem_ld_wait();
-#pragma unroll
-                        for (int t = 0; t < 4; ++t) {
-                            float v[16];
-#pragma unroll
-                            for (int i = 0; i < 16; ++i) v[i] = valid ? __uint_as_float(r[t][i]) : 0.f;
-                            if (want_stats) {
-                                float sq[16];
-#pragma unroll
-                                for (int i = 0; i < 16; ++i) sq[i] = v[i] * v[i];
-                                run1[g0 + t] += butterfly16(v, lane);
-                                run2[g0 + t] += butterfly16(sq, lane);
-                            }
-                            if (valid && !no_store) store16(v, pix0 + j * kTW, ti.n_img, gh, gw, (g0 + t) * 16);
+                            for (int i = 0; i < 16; ++i) { run1[gi * 16 + i] += v[i]; run2[gi * 16 + i] += b2[i]; }
+                        } else {
+                            run1[gi] += butterfly16(v, lane);
+                            run2[gi] += butterfly16(b2, lane);
                         }
                     }
+                    if (valid && !no_store) store16(v, pix0 + j * kTW, ti.n_img, gh, gw, gi * 16);
                 }
             }
             ptx::tc_fence_before();
@@ -467,17 +536,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         if (!NCHW && P.stats) {    // once per CTA: combine lanes and the four epilogue warps, write this CTA's partial row
 #pragma unroll
             for (int gidx = 0; gidx < NG; ++gidx) {
-                float c1, c2;
                 if constexpr (LANE_STATS) {
-                    c1 = butterfly16(run1 + gidx * 16, lane);
-                    c2 = butterfly16(run2 + gidx * 16, lane);
-                } else {
-                    c1 = run1[gidx];
-                    c2 = run2[gidx];
-                }
-                if ((lane & 1) == 0) {
-                    s_part[q * 2 * BN + gidx * 16 + col16(lane)] = c1;
-                    s_part[q * 2 * BN + BN + gidx * 16 + col16(lane)] = c2;
+                    const float c1 = butterfly16(run1 + gidx * 16, lane), c2 = butterfly16(run2 + gidx * 16, lane);
+                    if ((lane & 1) == 0) {
+                        s_part[q * 2 * BN + gidx * 16 + col16(lane)] = c1;
+                        s_part[q * 2 * BN + BN + gidx * 16 + col16(lane)] = c2;
+                    }
+                } else if ((lane & 1) == 0) {
+                    s_part[q * 2 * BN + gidx * 16 + col16(lane)] = run1[gidx];
+                    s_part[q * 2 * BN + BN + gidx * 16 + col16(lane)] = run2[gidx];
                 }
             }
             ptx::named_bar_sync(1, 128);
@@ -502,58 +569,63 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
 
 // ------------------------------------------------------------------------------------------ launch dispatch
 // One function per (KS, KC, BN), explicitly instantiated in conv_tc_inst*.cu so the kernel variants compile in
-// parallel.  mt: stage width (1/2/4 UMMA tiles); xf: loader transform (0 none, 1 affine+LeakyReLU, 2 +dropout).
+// parallel.  mt: stage width (1/2/4 UMMA tiles); xf: loader transform (0..3); epi: epilogue (0..2).
 template <int KS, int KC, int BN>
-int tc_launch(int mt, int xf, bool nchw, const CUtensorMap &map, const TcConvParams &P, cudaStream_t s);
+int tc_launch(int mt, int xf, int epi, const CUtensorMap &map, const CUtensorMap &map2, const TcConvParams &P, cudaStream_t s);
 
-template <int KS, int KC, int BN, bool RES, int MT, int XF, bool NCHW>
-static int tc_launch_one(const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
-    using C = TcCfg<KS, KC, BN, RES, MT>;
+template <int KS, int KC, int BN, bool RES, int MT, int XF, int EPI>
+static int tc_launch_one(const CUtensorMap &map, const CUtensorMap &map2, const TcConvParams &P, cudaStream_t s) {
+    using C = TcCfg<KS, KC, BN, RES, MT, XF == 3>;
     static bool attr_set = false;
     if (!attr_set) {
-        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<KS, KC, BN, RES, MT, XF, NCHW>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<KS, KC, BN, RES, MT, XF, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
     const int total = P.m_tiles * P.n_blocks;
-    const int grid = total < kNumSMs ? total : kNumSMs;
-    HPFG_CUDA_CHECK(launch_pdl(tc_conv_kernel<KS, KC, BN, RES, MT, XF, NCHW>, grid, kTcThreads, C::SMEM_BYTES, s, map, P));
+    const int grid = total < P.max_ctas ? total : P.max_ctas;
+    HPFG_CUDA_CHECK(launch_pdl(tc_conv_kernel<KS, KC, BN, RES, MT, XF, EPI>, grid, kTcThreads, C::SMEM_BYTES, s, map, map2, P));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
 
+// (xf, epi) pairs that exist: forward (0..2, 0), logits (1, 1), data gradients (0 | 3, 0 | 2)
 template <int KS, int KC, int BN, bool RES, int MT>
-static int tc_launch_xf(int xf, bool nchw, const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+static int tc_launch_xf(int xf, int epi, const CUtensorMap &map, const CUtensorMap &map2, const TcConvParams &P, cudaStream_t s) {
     if constexpr (KS == 3 && KC == 16 && BN == 16 && RES) {     // out_conv: fp32 NCHW logits epilogue
-        if (nchw) return tc_launch_one<KS, KC, BN, RES, MT, 1, true>(map, P, s);
+        if (epi == 1 && xf == 1) return tc_launch_one<KS, KC, BN, RES, MT, 1, 1>(map, map2, P, s);
     }
-    if (nchw) {
-        set_error("tc conv: NCHW epilogue only exists for the 3x3 16->16 resident-weight kernel");
-        return HPFG_ERR_UNSUPPORTED;
+    if (epi == 0) {
+        if constexpr (KS == 3) {                                   // dropout only follows the first conv of an encoder ConvBlock
+            if (xf == 2) return tc_launch_one<KS, KC, BN, RES, MT, 2, 0>(map, map2, P, s);
+            if (xf == 3) return tc_launch_one<KS, KC, BN, RES, MT, 3, 0>(map, map2, P, s);
+        }
+        if (xf == 1) return tc_launch_one<KS, KC, BN, RES, MT, 1, 0>(map, map2, P, s);
+        if (xf == 0) return tc_launch_one<KS, KC, BN, RES, MT, 0, 0>(map, map2, P, s);
+    } else if (epi == 2) {
+        if constexpr (KS == 3) {
+            if (xf == 3) return tc_launch_one<KS, KC, BN, RES, MT, 3, 2>(map, map2, P, s);
+        }
+        if (xf == 0) return tc_launch_one<KS, KC, BN, RES, MT, 0, 2>(map, map2, P, s);
     }
-    if constexpr (KS == 3) {                                   // dropout only follows the first conv of an encoder ConvBlock
-        if (xf == 2) return tc_launch_one<KS, KC, BN, RES, MT, 2, false>(map, P, s);
-    }
-    if (xf == 1) return tc_launch_one<KS, KC, BN, RES, MT, 1, false>(map, P, s);
-    if (xf == 0) return tc_launch_one<KS, KC, BN, RES, MT, 0, false>(map, P, s);
-    set_error("tc conv: unsupported loader transform");
+    set_error("tc conv: unsupported loader transform / epilogue combination xf=" + std::to_string(xf) + " epi=" + std::to_string(epi));
     return HPFG_ERR_UNSUPPORTED;
 }
 
 template <int KS, int KC, int BN, bool RES>
-static int tc_launch_mt(int mt, int xf, bool nchw, const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+static int tc_launch_mt(int mt, int xf, int epi, const CUtensorMap &map, const CUtensorMap &map2, const TcConvParams &P, cudaStream_t s) {
     if constexpr (KS == 3 && BN <= 32) {      // wide stages only where per-tile overheads dominate (few channels, large images)
-        if (mt == 4) return tc_launch_xf<KS, KC, BN, RES, 4>(xf, nchw, map, P, s);
-        if (mt == 2) return tc_launch_xf<KS, KC, BN, RES, 2>(xf, nchw, map, P, s);
+        if (mt == 4) return tc_launch_xf<KS, KC, BN, RES, 4>(xf, epi, map, map2, P, s);
+        if (mt == 2) return tc_launch_xf<KS, KC, BN, RES, 2>(xf, epi, map, map2, P, s);
     }
-    return tc_launch_xf<KS, KC, BN, RES, 1>(xf, nchw, map, P, s);
+    return tc_launch_xf<KS, KC, BN, RES, 1>(xf, epi, map, map2, P, s);
 }
 
 template <int KS, int KC, int BN>
-int tc_launch(int mt, int xf, bool nchw, const CUtensorMap &map, const TcConvParams &P, cudaStream_t s) {
+int tc_launch(int mt, int xf, int epi, const CUtensorMap &map, const CUtensorMap &map2, const TcConvParams &P, cudaStream_t s) {
     if constexpr (BN <= 64) {     // resident weights whenever the layer's whole weight is one (k-chunk, n-block) stage
-        if (P.k_chunks == 1 && P.n_blocks == 1) return tc_launch_mt<KS, KC, BN, true>(mt, xf, nchw, map, P, s);
+        if (P.k_chunks == 1 && P.n_blocks == 1) return tc_launch_mt<KS, KC, BN, true>(mt, xf, epi, map, map2, P, s);
     }
-    return tc_launch_mt<KS, KC, BN, false>(mt, xf, nchw, map, P, s);
+    return tc_launch_mt<KS, KC, BN, false>(mt, xf, epi, map, map2, P, s);
 }
 
 }  // namespace hpfg

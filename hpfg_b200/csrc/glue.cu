@@ -322,6 +322,12 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float *__res
     q = (double)bn.invstd[c] * (q - (double)bn.mean[c] * s);      // partials hold sum(g*raw): xhat = (raw - mean) * invstd
     bn.c1[c] = (float)(s * inv_count);
     bn.c2[c] = (float)(q * inv_count);
+    {   // folded constants of pass 1 (computed as bn_bwd_kernel<1> computes them, in fp32, from the rounded c1 / c2)
+        const float sc = bn.scale[c];
+        const float kb = -sc * bn.c2[c] * bn.invstd[c];
+        bn.kb[c] = kb;
+        bn.kd[c] = -sc * bn.c1[c] - kb * bn.mean[c];
+    }
     if (accumulate) { dgamma[c] += (float)q; dbeta[c] += (float)s; }
     else { dgamma[c] = (float)q; dbeta[c] = (float)s; }
 }
@@ -345,13 +351,31 @@ int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, D
     return HPFG_OK;
 }
 
+int bn_bwd_reduce(const float *partials, int P, int C, int64_t count, BnState bn, float *dgamma, float *dbeta, int accumulate,
+                  cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
+    HPFG_CUDA_CHECK(launch_pdl(bn_bwd_finalize_kernel, ceil_div(C * 32, 256), 256, 0, s, partials, P, C, 1.0 / (double)count, bn, dgamma, dbeta,
+                               accumulate));
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
 // ------------------------------------------------------------------------------------------ skip_pool_bwd
-template <typename T>
-__global__ void __launch_bounds__(256, 4) skip_pool_bwd_kernel(const T *__restrict__ dcat, const T *__restrict__ dpooled,
+// GSTAT: store g = dact * leaky'(bn(raw)) instead of dact and reduce (sum g | sum g*raw) per channel into one partial row per
+// block (BatchNorm-backward pass 0 of the feature's own BatchNorm, fused: the kernel reads raw anyway).
+template <typename T, bool GSTAT>
+__global__ void __launch_bounds__(256, GSTAT ? 2 : 4) skip_pool_bwd_kernel(const T *__restrict__ dcat, const T *__restrict__ dpooled,
                                                             const T *__restrict__ raw, BnState bn, T *__restrict__ dact,
-                                                            int N, int H, int W, int F, FastDiv dFV, FastDiv dWo, FastDiv dHo) {
+                                                            int N, int H, int W, int F, FastDiv dFV, FastDiv dWo, FastDiv dHo,
+                                                            float *__restrict__ partials) {
     pdl_prologue();
     constexpr int V = Vec<T>::N;
+    __shared__ float red[GSTAT ? 2 * 256 * V : 1];
+    float s1[GSTAT ? V : 1], s2[GSTAT ? V : 1];
+    if (GSTAT) {
+#pragma unroll
+        for (int k = 0; k < V; ++k) s1[k] = s2[k] = 0.f;
+    }
     const int Ho = H >> 1, Wo = W >> 1;
     const uint32_t total = (uint32_t)N * Ho * Wo * dFV.d;
     const uint32_t i0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -368,6 +392,7 @@ __global__ void __launch_bounds__(256, 4) skip_pool_bwd_kernel(const T *__restri
 #pragma unroll
         for (int k = 0; k < V; ++k) { dp[k] = 0.f; arg[k] = 0; best[k] = 0.f; }
         if (dpooled) Vec<T>::load(dpooled + (((int64_t)n * Ho + ho) * Wo + wo) * F + cv * V, dp);
+        float rawv[GSTAT ? 4 : 1][V];
 #pragma unroll
         for (int d = 0; d < 4; ++d) {   // first maximum in (h,w) scan order, as max_pool2d_with_indices
             const int h = 2 * ho + (d >> 1), w = 2 * wo + (d & 1);
@@ -377,6 +402,7 @@ __global__ void __launch_bounds__(256, 4) skip_pool_bwd_kernel(const T *__restri
             for (int k = 0; k < V; ++k) {
                 const float a = leaky(fmaf(v[k], sc[k], sh[k]));
                 if (d == 0 || a > best[k]) { best[k] = a; arg[k] = d; }
+                if (GSTAT) rawv[d][k] = v[k];
             }
         }
 #pragma unroll
@@ -393,7 +419,34 @@ __global__ void __launch_bounds__(256, 4) skip_pool_bwd_kernel(const T *__restri
 #pragma unroll
                 for (int k = 0; k < V; ++k) if (arg[k] == d) o[k] += dp[k];
             }
+            if (GSTAT) {
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    const float x = rawv[d][k];
+                    const float g = o[k] * leaky_grad(fmaf(x, sc[k], sh[k]));
+                    o[k] = g;
+                    s1[k] += g;
+                    s2[k] = fmaf(g, x, s2[k]);
+                }
+            }
             Vec<T>::store(dact + p * F + cv * V, o);
+        }
+    }
+    if (GSTAT) {
+        // deterministic block reduction: thread t owns channel vector cv = t % FV (the grid stride is a multiple of FV)
+        const int FV = (int)dFV.d, R = 256 / FV, r = threadIdx.x / FV, c0 = threadIdx.x % FV;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            red[threadIdx.x * V + k] = s1[k];
+            red[(256 + threadIdx.x) * V + k] = s2[k];
+        }
+        (void)r; (void)c0;
+        __syncthreads();
+        for (int o = threadIdx.x; o < 2 * F; o += 256) {
+            const int which = o / F, c = o % F;
+            float s = 0.f;
+            for (int rr = 0; rr < R; ++rr) s += red[(which * 256 + rr * FV + c / V) * V + (c % V)];
+            partials[(int64_t)blockIdx.x * 2 * F + o] = s;
         }
     }
 }
@@ -404,8 +457,23 @@ int skip_pool_bwd(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *
     ProfScope _prof(PROF_GLUE, s);
     const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (F / Vec<T>::N);
     HPFG_REQUIRE(total < (1ll << 31), "skip_pool_bwd: tensor too large for 32-bit indexing");
-    HPFG_CUDA_CHECK(launch_pdl(skip_pool_bwd_kernel<T>, ew_grid(total), 256, 0, s, dcat, dpooled, raw, bn, dact, N, H, W, F, make_fastdiv(F / Vec<T>::N), make_fastdiv(W / 2), make_fastdiv(H / 2)));
+    HPFG_CUDA_CHECK(launch_pdl(skip_pool_bwd_kernel<T, false>, ew_grid(total), 256, 0, s, dcat, dpooled, raw, bn, dact, N, H, W, F, make_fastdiv(F / Vec<T>::N), make_fastdiv(W / 2), make_fastdiv(H / 2), (float *)nullptr));
     HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+template <typename T>
+int skip_pool_bwd_gstat(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *g_out, int N, int H, int W, int F,
+                        float *partials, int max_partials, int *P, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
+    const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (F / Vec<T>::N);
+    HPFG_REQUIRE(total < (1ll << 31), "skip_pool_bwd: tensor too large for 32-bit indexing");
+    HPFG_REQUIRE(256 % (F / Vec<T>::N) == 0, "skip_pool_bwd_gstat: channel vectors must divide the block");
+    int grid = ew_grid(total);
+    grid = std::min(grid, std::min(kNumSMs * 4, max_partials));       // one partial row per block
+    HPFG_CUDA_CHECK(launch_pdl(skip_pool_bwd_kernel<T, true>, grid, 256, 0, s, dcat, dpooled, raw, bn, g_out, N, H, W, F, make_fastdiv(F / Vec<T>::N), make_fastdiv(W / 2), make_fastdiv(H / 2), partials));
+    HPFG_LAUNCH_CHECK();
+    *P = grid;
     return HPFG_OK;
 }
 
@@ -650,6 +718,7 @@ int add_nchw_f32_to_nhwc(T *dst, const float *src, int N, int H, int W, int C, c
     template int bn_bwd<T>(const T *, const T *, T *, int64_t, int, BnState, DropSpec, float *, int, float *,       \
                            float *, int, cudaStream_t);                                                             \
     template int skip_pool_bwd<T>(const T *, const T *, const T *, BnState, T *, int, int, int, int, cudaStream_t); \
+    template int skip_pool_bwd_gstat<T>(const T *, const T *, const T *, BnState, T *, int, int, int, int, float *, int, int *, cudaStream_t); \
     template int up_bwd<T>(const T *, T *, int, int, int, int, cudaStream_t);                                       \
     template int act_nhwc_to_nchw_f32<T>(const T *, BnState, float *, int, int, int, int, cudaStream_t);           \
     template int add_nchw_f32_to_nhwc<T>(T *, const float *, int, int, int, int, cudaStream_t);                      \
@@ -658,3 +727,58 @@ INSTANTIATE(float)
 INSTANTIATE(bf16)
 
 }  // namespace hpfg
+
+// ---- layer-isolated test hook for the bf16 glue kernels (include/hpfg_b200.h: hpfg_glue_debug) -----------------------------
+using namespace hpfg;
+extern "C" int hpfg_glue_debug(int op, int N, int H, int W, int C, const void *a, const void *b, const void *c, const float *scale,
+                               const float *shift, const float *mean, const float *invstd, const uint8_t *keep_mask_nchw, float p_drop,
+                               void *out_bf16, float *out_f32, void *stream) {
+    HPFG_REQUIRE(op >= 0 && op <= 5 && a && out_bf16, "hpfg_glue_debug: bad arguments");
+    HPFG_REQUIRE(C % 16 == 0 && C <= 256, "hpfg_glue_debug: C must be a multiple of 16, at most 256");
+    cudaStream_t s = (cudaStream_t)stream;
+    float *mem = nullptr, *partials = nullptr;
+    uint32_t *bits = nullptr;
+    const int max_partials = kNumSMs * 8;
+    HPFG_CUDA_CHECK(cudaMalloc(&mem, 8 * 256 * 4));
+    HPFG_CUDA_CHECK(cudaMalloc(&partials, (size_t)max_partials * 2 * 256 * 4));
+    HPFG_CUDA_CHECK(cudaMemsetAsync(mem, 0, 8 * 256 * 4, s));
+    BnState st{mem, mem + 256, mem + 512, mem + 768, mem + 1024, mem + 1280, mem + 1536, mem + 1792};
+    if (scale) HPFG_CUDA_CHECK(cudaMemcpyAsync(st.scale, scale, C * 4, cudaMemcpyDeviceToDevice, s));
+    if (shift) HPFG_CUDA_CHECK(cudaMemcpyAsync(st.shift, shift, C * 4, cudaMemcpyDeviceToDevice, s));
+    if (mean) HPFG_CUDA_CHECK(cudaMemcpyAsync(st.mean, mean, C * 4, cudaMemcpyDeviceToDevice, s));
+    if (invstd) HPFG_CUDA_CHECK(cudaMemcpyAsync(st.invstd, invstd, C * 4, cudaMemcpyDeviceToDevice, s));
+    if (keep_mask_nchw) {
+        HPFG_CUDA_CHECK(cudaMalloc(&bits, ((size_t)N * H * W * C + 31) / 32 * 4));
+        HPFG_RETURN_IF(dropout_bits(bits, keep_mask_nchw, N, H, W, C, p_drop, 0, 0, s));
+    }
+    int rc = HPFG_OK;
+    const bf16 *A = (const bf16 *)a, *B = (const bf16 *)b, *Cc = (const bf16 *)c;
+    bf16 *O = (bf16 *)out_bf16;
+    switch (op) {
+        case 0: rc = pool_act<bf16>(A, O, N, H, W, C, st, s); break;                       // a = raw [N,H,W,C] -> [N,H/2,W/2,C]
+        case 1: rc = upcat<bf16>(A, st, B, O, N, H, W, C, s); break;                       // a = skip raw [N,2H,2W,C], b = low [N,H,W,C] -> cat [N,2H,2W,2C]
+        case 2: {                                                                          // a = dact, b = raw [N,H,W,C] -> draw; out_f32 = dgamma | dbeta
+            DropSpec ds{bits, bits ? 1.f / (1.f - p_drop) : 1.f};
+            rc = bn_bwd<bf16>(A, B, O, (int64_t)N * H * W, C, st, ds, partials, max_partials, out_f32, out_f32 + C, 0, s);
+            break;
+        }
+        case 3: rc = skip_pool_bwd<bf16>(A, B, Cc, st, O, N, H, W, C, s); break;           // a = dcat [N,H,W,2C], b = dpooled [N,H/2,W/2,C], c = raw [N,H,W,C]
+        case 4: rc = up_bwd<bf16>(A, O, N, H, W, C, s); break;                             // a = dcat [N,2H,2W,2C] -> dlow [N,H,W,C]
+        case 5: {                                                                          // as 3, fused with BatchNorm-backward pass 0: out = g; out_f32 = dgamma | dbeta | kb | kd
+            int P = 0;
+            rc = skip_pool_bwd_gstat<bf16>(A, B, Cc, st, O, N, H, W, C, partials, max_partials, &P, s);
+            if (rc == HPFG_OK) rc = bn_bwd_reduce(partials, P, C, (int64_t)N * H * W, st, out_f32, out_f32 + C, 0, s);
+            if (rc == HPFG_OK) {
+                cudaMemcpyAsync(out_f32 + 2 * C, st.kb, C * 4, cudaMemcpyDeviceToDevice, s);
+                cudaMemcpyAsync(out_f32 + 3 * C, st.kd, C * 4, cudaMemcpyDeviceToDevice, s);
+            }
+            break;
+        }
+    }
+    cudaStreamSynchronize(s);
+    cudaFree(mem);
+    cudaFree(partials);
+    if (bits) cudaFree(bits);
+    if (rc == HPFG_OK) HPFG_CUDA_CHECK(cudaGetLastError());
+    return rc;
+}

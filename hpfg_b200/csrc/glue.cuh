@@ -11,6 +11,7 @@ struct BnState {
     float *scale, *shift;      // fused affine: y = x*scale + shift  (scale = gamma*invstd, shift = beta - mean*scale)
     float *mean, *invstd;      // batch statistics of the bias-free conv output (saved for backward)
     float *c1, *c2;            // backward: mean(g), mean(g*xhat)
+    float *kb, *kd;            // backward, folded: draw = scale*g + kb*raw + kd  (kb = -scale*c2*invstd, kd = -scale*c1 - kb*mean)
 };
 
 struct DropSpec {
@@ -39,6 +40,14 @@ int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, D
 // grad wrt an encoder feature = skip half of dcat (+) un-pooled grad of the pooled tensor
 template <typename T>
 int skip_pool_bwd(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *dact, int N, int H, int W, int F,
+                  cudaStream_t s);
+// The same, fused with BatchNorm-backward pass 0 of that feature's own BatchNorm: stores g = dact * leaky'(bn(raw)) and
+// writes the partial sums (sum g | sum g*raw) as [*P][2*F] rows; bn_bwd_reduce turns them into c1/c2/kb/kd + dgamma/dbeta.
+template <typename T>
+int skip_pool_bwd_gstat(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *g_out, int N, int H, int W, int F,
+                        float *partials, int max_partials, int *P, cudaStream_t s);
+// BatchNorm-backward reduction of [P][2*C] partials (sum g | sum g*raw) -> bn.c1/c2/kb/kd, dgamma, dbeta (count = N*H*W)
+int bn_bwd_reduce(const float *partials, int P, int C, int64_t count, BnState bn, float *dgamma, float *dbeta, int accumulate,
                   cudaStream_t s);
 // adjoint of the bilinear x2 (align_corners) upsample: dcat[..., F:2F] at (2h,2w) -> dlow at (h,w)
 template <typename T>

@@ -835,6 +835,69 @@ static int launch_argmax(const float *logits, int64_t hw, int64_t quads, int64_t
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
+
+// softmax_mse_loss (utils/loss/diceloss.py:64-81): the UNREDUCED (softmax(a) - softmax(b))^2 map (or sigmoid), and its
+// backward wrt a for an arbitrary upstream gradient: da_k = p_k * (u_k - sum_j u_j p_j), u_j = 2 gout_j (p_j - q_j).
+// BWD = false: out = the map; BWD = true: out = da (gout read).  4 pixels per thread, 128-bit accesses per class plane.
+template <int C, bool BWD, bool SIGMOID>
+__global__ void __launch_bounds__(256) softmax_mse_kernel(const float *__restrict__ a, const float *__restrict__ b,
+                                                          const float *__restrict__ gout, float *__restrict__ out, int64_t hw,
+                                                          int64_t total_quads) {
+    pdl_prologue();
+    const int64_t q_per_img = hw >> 2;
+    for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < total_quads; q += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t img = q / q_per_img, pix = (q - img * q_per_img) << 2;
+        const int64_t o = (img * C) * hw + pix;
+        float za[C][4], zb[C][4], pa[C][4], pb[C][4], g[C][4], l1[4], l2[4];
+        load4<C>(a + o, hw, za);
+        load4<C>(b + o, hw, zb);
+        if (BWD) load4<C>(gout + o, hw, g);
+        if (SIGMOID) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    pa[c][j] = 1.f / (1.f + expf(-za[c][j]));
+                    pb[c][j] = 1.f / (1.f + expf(-zb[c][j]));
+                }
+        } else {
+            softmax4<C>(za, pa, l1);
+            softmax4<C>(zb, pb, l2);
+        }
+        float r[C][4];
+        if (!BWD) {
+#pragma unroll
+            for (int c = 0; c < C; ++c)
+#pragma unroll
+                for (int j = 0; j < 4; ++j) { const float d = pa[c][j] - pb[c][j]; r[c][j] = d * d; }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                float u[C], dot = 0.f;
+#pragma unroll
+                for (int c = 0; c < C; ++c) { u[c] = 2.f * g[c][j] * (pa[c][j] - pb[c][j]); dot = fmaf(u[c], pa[c][j], dot); }
+#pragma unroll
+                for (int c = 0; c < C; ++c) r[c][j] = SIGMOID ? u[c] * pa[c][j] * (1.f - pa[c][j]) : pa[c][j] * (u[c] - dot);
+            }
+        }
+        store4<C>(out + o, hw, r);
+    }
+}
+
+template <int C>
+static int launch_softmax_mse(const float *a, const float *b, const float *gout, float *out, int64_t hw, int64_t quads, bool sigmoid,
+                              cudaStream_t st) {
+    const int grid = loss_grid(quads, 6);
+    if (gout) {
+        if (sigmoid) HPFG_CUDA_CHECK(launch_pdl(softmax_mse_kernel<C, true, true>, grid, 256, 0, st, a, b, gout, out, hw, quads));
+        else HPFG_CUDA_CHECK(launch_pdl(softmax_mse_kernel<C, true, false>, grid, 256, 0, st, a, b, gout, out, hw, quads));
+    } else {
+        if (sigmoid) HPFG_CUDA_CHECK(launch_pdl(softmax_mse_kernel<C, false, true>, grid, 256, 0, st, a, b, gout, out, hw, quads));
+        else HPFG_CUDA_CHECK(launch_pdl(softmax_mse_kernel<C, false, false>, grid, 256, 0, st, a, b, gout, out, hw, quads));
+    }
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
 }  // namespace hpfg
 
 extern "C" int hpfg_ict_mix(const float *a, const float *b, const float *mix_factors, int n, int64_t per_image,
@@ -868,5 +931,27 @@ extern "C" int hpfg_argmax_labels(const float *logits, int n, int num_classes, i
         case 6: return launch_argmax<6>(logits, hw, quads, labels_i64, labels_u8, st);
         case 7: return launch_argmax<7>(logits, hw, quads, labels_i64, labels_u8, st);
         default: return launch_argmax<8>(logits, hw, quads, labels_i64, labels_u8, st);
+    }
+}
+
+extern "C" int hpfg_softmax_mse(const float *input_logits, const float *target_logits, const float *grad_out, int n,
+                                int num_classes, int height, int width, int sigmoid, float *out, void *stream) {
+    HPFG_REQUIRE(input_logits && target_logits && out, "hpfg_softmax_mse: null buffer");
+    HPFG_REQUIRE(n > 0, "hpfg_softmax_mse: empty batch");
+    HPFG_REQUIRE(num_classes >= 1 && num_classes <= kMaxC, "hpfg_softmax_mse: num_classes must be in [1,8]");
+    const int64_t hw = (int64_t)height * width;
+    HPFG_REQUIRE(hw % 4 == 0, "hpfg_softmax_mse: H*W must be a multiple of 4");
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t quads = (hw >> 2) * n;
+    ProfScope _prof(PROF_LOSS, st);
+    switch (num_classes) {
+        case 1: return launch_softmax_mse<1>(input_logits, target_logits, grad_out, out, hw, quads, sigmoid != 0, st);
+        case 2: return launch_softmax_mse<2>(input_logits, target_logits, grad_out, out, hw, quads, sigmoid != 0, st);
+        case 3: return launch_softmax_mse<3>(input_logits, target_logits, grad_out, out, hw, quads, sigmoid != 0, st);
+        case 4: return launch_softmax_mse<4>(input_logits, target_logits, grad_out, out, hw, quads, sigmoid != 0, st);
+        case 5: return launch_softmax_mse<5>(input_logits, target_logits, grad_out, out, hw, quads, sigmoid != 0, st);
+        case 6: return launch_softmax_mse<6>(input_logits, target_logits, grad_out, out, hw, quads, sigmoid != 0, st);
+        case 7: return launch_softmax_mse<7>(input_logits, target_logits, grad_out, out, hw, quads, sigmoid != 0, st);
+        default: return launch_softmax_mse<8>(input_logits, target_logits, grad_out, out, hw, quads, sigmoid != 0, st);
     }
 }

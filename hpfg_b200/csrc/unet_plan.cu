@@ -2,6 +2,7 @@
 // Wiring follows model/unet.py: Encoder :61-82, Decoder :85-117, ConvBlock :12-28, DownBlock :31-42, UpBlock :45-58.
 #include "unet_plan.cuh"
 
+#include <cstdlib>
 #include <cstring>
 
 #include "conv_tc.cuh"
@@ -11,6 +12,21 @@ namespace hpfg {
 static thread_local std::string g_error;
 int64_t g_launch_count = 0;
 void set_error(const std::string &msg) { g_error = msg; }
+
+int tc_cta_cap(int kind) {
+    static int caps[3] = {-1, -1, -1};
+    if (caps[0] < 0) {
+        const char *names[3] = {"HPFG_CTAS_FWD", "HPFG_CTAS_DGRAD", "HPFG_CTAS_WGRAD"};
+        const int defaults[3] = {kNumSMs, kNumSMs, kNumSMs};
+        for (int i = 0; i < 3; ++i) {
+            const char *e = getenv(names[i]);
+            int v = e ? atoi(e) : defaults[i];
+            if (v < 2 || v > kNumSMs) v = kNumSMs;
+            caps[i] = v & ~1;               // even: the two n-blocks of a wide layer alternate over the grid
+        }
+    }
+    return caps[kind];
+}
 
 bool g_prof_on = false;
 struct ProfRec { int cat; cudaEvent_t a, b; };
@@ -137,14 +153,14 @@ static void carve(hpfg_unet_plan *p, char *base, int64_t &total) {
     p->wscratch_floats = wf;
     c.take(p->wscratch, wf * 4);
     int64_t bnf = 0;
-    for (auto &b : p->d.bns) bnf += 6 * (int64_t)align_up(b.C, 64);
+    for (auto &b : p->d.bns) bnf += 8 * (int64_t)align_up(b.C, 64);
     c.take(p->bnmem, bnf * 4);
     if (base) {
         float *q = p->bnmem;
         for (auto &b : p->d.bns) {
             const int64_t s = align_up(b.C, 64);
-            b.st = BnState{q, q + s, q + 2 * s, q + 3 * s, q + 4 * s, q + 5 * s};
-            q += 6 * s;
+            b.st = BnState{q, q + s, q + 2 * s, q + 3 * s, q + 4 * s, q + 5 * s, q + 6 * s, q + 7 * s};
+            q += 8 * s;
         }
     }
     for (auto &cv : p->d.convs) {
@@ -259,6 +275,171 @@ static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_runnin
     p->saved = save != 0 && training != 0;
     p->saved_dropout = use_drop;
     p->saved_x = x;
+    return HPFG_OK;
+}
+
+// HPFG_BWD_FUSE=1 selects the bf16 backward with BatchNorm backward folded into the tensor-core kernels (backward_fused below).
+// It is NOT the default: measured on B200 it is slower than the three streaming bn_bwd launches it removes (3.62 vs 3.39 ms
+// per Mean-Teacher step, profiles/README.md) -- the fusion moves bytes from 5 TB/s streaming kernels into 3 TB/s conv kernels.
+static bool bwd_fused_enabled() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("HPFG_BWD_FUSE");
+        v = (e && e[0] == '1') ? 1 : 0;
+    }
+    return v != 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// bf16 plans: backward with BatchNorm backward folded into the tensor-core kernels (north_star: "the backward pass is fused
+// the same way").  Per BatchNorm layer X the unfused schedule ran  bn_bwd<0> -> finalize -> bn_bwd<1> -> {wgrad, dgrad};  here
+//   * the kernel that PRODUCES the gradient wrt X's activated output (a data-gradient conv, or skip_pool_bwd for the encoder
+//     features) stores g = dact * leaky' * dropout' and writes the partial sums (sum g | sum g*raw)       [GSTAT epilogue]
+//   * bn_bwd_reduce turns them into c1/c2 + the folded constants kb/kd (+ dgamma/dbeta)                   [one tiny launch]
+//   * the kernels that CONSUME the raw gradient (dgrad and wgrad of X's conv) build it on load from g and raw:
+//     draw = scale*g + kb*raw + kd                                                                         [two-source loaders]
+// so the raw-gradient tensor never exists and two full tensor passes + one launch per BatchNorm leave the chain.
+// Gradient buffers rotate through four slots; a slot is rewritten only after the side-stream weight gradient that read it.
+static int backward_fused(hpfg_unet_plan *p, const float *params, const float *dlogits, float *grads, int acc, cudaStream_t s,
+                          const float *dbottleneck) {
+    using T = bf16;
+    UNetDesc &d = p->d;
+    const int N = p->N, H = p->H, W = p->W;
+    const LoadXform none{};
+    auto xf_of = [&](int bn, const uint32_t *bits, float p_drop) {
+        LoadXform xf{};
+        xf.scale = d.bns[bn].st.scale;
+        xf.shift = d.bns[bn].st.shift;
+        xf.drop.bits = bits;
+        xf.drop.inv_keep = bits ? 1.f / (1.f - p_drop) : 1.f;
+        return xf;
+    };
+    cudaStream_t side = g_prof_on ? s : p->side;
+    void *slot[4] = {p->g[0], p->g[1], p->g[2], p->g[4]};
+    bool busy[4] = {false, false, false, false};
+    int cur = -1;
+    auto acquire = [&](void *&out) -> int {      // next gradient slot; waits (stream-level) for its last side-stream reader
+        cur = (cur + 1) & 3;
+        if (busy[cur]) HPFG_CUDA_CHECK(cudaStreamWaitEvent(s, p->ev_slot[cur], 0));
+        busy[cur] = false;
+        out = slot[cur];
+        return HPFG_OK;
+    };
+    auto fuse_in = [&](int bn) {                 // two-source loader constants of BatchNorm `bn`
+        TcBwdFuse f;
+        f.in_raw = d.bns[bn].raw;
+        f.sc = d.bns[bn].st.scale; f.kb = d.bns[bn].st.kb; f.kd = d.bns[bn].st.kd;
+        return f;
+    };
+    auto fuse_out = [&](TcBwdFuse &f, int bn, const uint32_t *bits, float p_drop) {
+        f.out_raw = d.bns[bn].raw;
+        f.gs_scale = d.bns[bn].st.scale; f.gs_shift = d.bns[bn].st.shift;
+        f.gs_dropbits = bits; f.gs_inv_keep = bits ? 1.f / (1.f - p_drop) : 1.f;
+    };
+    // weight gradient of conv `ci` on the side stream; dy = g of the conv's own BatchNorm (fuse != null) or a plain gradient
+    auto wgrad = [&](int ci, void *in, LoadXform xf, void *dy, const TcBwdFuse *fuse) -> int {
+        ConvLayer &cv = d.convs[ci];
+        HPFG_CUDA_CHECK(cudaEventRecord(p->ev_ready, s));
+        HPFG_CUDA_CHECK(cudaStreamWaitEvent(side, p->ev_ready, 0));
+        bool done = false;
+        HPFG_RETURN_IF(tc_wgrad(p, ci, in, xf, dy, grads + cv.w_off, grads + cv.b_off, acc, &done, side, fuse));
+        for (int k = 0; k < 4; ++k)
+            if (dy == slot[k]) {
+                HPFG_CUDA_CHECK(cudaEventRecord(p->ev_slot[k], side));
+                busy[k] = true;
+            }
+        return HPFG_OK;
+    };
+    auto join_side = [&]() -> int {
+        HPFG_CUDA_CHECK(cudaEventRecord(p->ev_join, side));
+        HPFG_CUDA_CHECK(cudaStreamWaitEvent(s, p->ev_join, 0));
+        return HPFG_OK;
+    };
+    // data gradient of conv `ci`; gs_bn >= 0: the output is the gradient wrt BatchNorm gs_bn's activated output -> GSTAT + reduce
+    auto dgrad = [&](int ci, void *dy, const TcBwdFuse *fin, void *din, int gs_bn, const uint32_t *bits, float p_drop) -> int {
+        TcBwdFuse f = fin ? *fin : TcBwdFuse{};
+        int P = 0;
+        if (gs_bn >= 0) fuse_out(f, gs_bn, bits, p_drop);
+        bool done = false;
+        HPFG_RETURN_IF(tc_dgrad(p, ci, dy, din, &done, s, (fin || gs_bn >= 0) ? &f : nullptr, p->stats, &P));
+        HPFG_REQUIRE(done, "backward_fused: layer not on the tensor-core path");
+        if (gs_bn >= 0) {
+            BnLayer &bl = d.bns[gs_bn];
+            HPFG_RETURN_IF(bn_bwd_reduce(p->stats, P, bl.C, (int64_t)N * bl.H * bl.W, bl.st, grads + bl.g_off, grads + bl.b_off, acc, s));
+        }
+        return HPFG_OK;
+    };
+
+    // ---- out_conv: dlogits fp32 NCHW -> bf16 NHWC16; its data gradient is the gradient wrt up4's activated output (BN 17)
+    HPFG_RETURN_IF(pad_to_nhwc16(dlogits, p->dlpad, N, p->n_cls, H, W, s));
+    HPFG_RETURN_IF(wgrad(22, d.bns[17].raw, xf_of(17, nullptr, 0.f), p->dlpad, nullptr));
+    void *a = nullptr, *c = nullptr, *b = nullptr;
+    HPFG_RETURN_IF(acquire(a));
+    HPFG_RETURN_IF(dgrad(22, p->dlpad, nullptr, a, 17, nullptr, 0.f));
+    // ---- decoder, up4 .. up1 (a = g of the block's second BatchNorm)
+    for (int j = 4; j >= 1; --j) {
+        const int lvl = 4 - j, c1x1 = 10 + 3 * (j - 1), cA = c1x1 + 1, cB = c1x1 + 2;
+        const int bA = d.convs[cA].bn, bB = d.convs[cB].bn;
+        TcBwdFuse fB = fuse_in(bB), fA = fuse_in(bA);
+        HPFG_RETURN_IF(wgrad(cB, d.bns[bA].raw, xf_of(bA, nullptr, 0.f), a, &fB));
+        HPFG_RETURN_IF(acquire(c));
+        HPFG_RETURN_IF(dgrad(cB, a, &fB, c, bA, nullptr, 0.f));                     // -> g(A) in c
+        HPFG_RETURN_IF(wgrad(cA, p->cat[j], none, c, &fA));
+        HPFG_RETURN_IF(dgrad(cA, c, &fA, p->dcat[j], -1, nullptr, 0.f));             // -> dcat (skip | upsampled)
+        const int F = kFt[lvl], hl = H >> (lvl + 1), wl = W >> (lvl + 1);
+        HPFG_RETURN_IF(acquire(b));
+        HPFG_RETURN_IF(up_bwd<T>((const T *)p->dcat[j], (T *)b, N, hl, wl, F, s));   // -> dlow in b
+        const int prev_bn = (j == 1) ? 9 : d.convs[cB - 3].bn;
+        HPFG_RETURN_IF(wgrad(c1x1, d.bns[prev_bn].raw, xf_of(prev_bn, nullptr, 0.f), b, nullptr));
+        HPFG_RETURN_IF(acquire(a));
+        const bool plain = (j == 1 && dbottleneck != nullptr);      // an external gradient joins first: BatchNorm 9 goes the unfused way
+        HPFG_RETURN_IF(dgrad(c1x1, b, nullptr, a, plain ? -1 : prev_bn, nullptr, 0.f));   // -> g(prev) (or dact(prev)) in a
+        if (j == 3 || j == 1) {
+            HPFG_RETURN_IF(join_side());
+            HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[j == 3 ? 0 : 1], s));
+        }
+    }
+    bool a_is_dact = false;
+    if (dbottleneck) {
+        HPFG_RETURN_IF(add_nchw_f32_to_nhwc<T>((T *)a, dbottleneck, N, H >> 4, W >> 4, kFt[4], s));
+        a_is_dact = true;
+    }
+    // ---- encoder, down4 .. in_conv
+    void *dpooled = nullptr;
+    for (int l = 4; l >= 0; --l) {
+        const int cA = 2 * l, cB = 2 * l + 1, bA = cA, bB = cB, h = H >> l, w = W >> l;
+        const uint32_t *bits = p->saved_dropout ? p->dropbits[l] : nullptr;
+        BnLayer &blB = d.bns[bB];
+        if (l < 4) {  // g of the encoder feature's BatchNorm from: skip half of dcat + un-pooled grad from the level below
+            HPFG_RETURN_IF(acquire(a));
+            int P = 0;
+            HPFG_RETURN_IF(skip_pool_bwd_gstat<T>((const T *)p->dcat[4 - l], (const T *)dpooled, (const T *)blB.raw, blB.st, (T *)a, N, h, w,
+                                                  kFt[l], p->stats, (int)(p->stats_floats / (2 * blB.C)), &P, s));
+            HPFG_RETURN_IF(bn_bwd_reduce(p->stats, P, blB.C, (int64_t)N * h * w, blB.st, grads + blB.g_off, grads + blB.b_off, acc, s));
+        } else if (a_is_dact) {   // UNet_Plus: dact(9) with the neck's gradient added -> the two-pass BatchNorm backward, materialised
+            HPFG_RETURN_IF(acquire(c));
+            DropSpec ds{nullptr, 1.f};
+            HPFG_RETURN_IF(bn_bwd<T>((const T *)a, (const T *)blB.raw, (T *)c, (int64_t)N * h * w, blB.C, blB.st, ds, p->stats,
+                                     (int)(p->stats_floats / (2 * blB.C)), grads + blB.g_off, grads + blB.b_off, acc, s));
+            a = c;
+        }
+        const bool fusedB = !(l == 4 && a_is_dact);
+        TcBwdFuse fB = fuse_in(bB), fA = fuse_in(bA);
+        HPFG_RETURN_IF(wgrad(cB, d.bns[bA].raw, xf_of(bA, bits, kEncDropout[l]), a, fusedB ? &fB : nullptr));
+        HPFG_RETURN_IF(acquire(c));
+        HPFG_RETURN_IF(dgrad(cB, a, fusedB ? &fB : nullptr, c, bA, bits, kEncDropout[l]));   // -> g(A) in c
+        if (l == 0) {
+            HPFG_RETURN_IF(wgrad(0, p->xpad, none, c, &fA));
+        } else {
+            HPFG_RETURN_IF(wgrad(cA, p->pooled[l], none, c, &fA));
+            HPFG_RETURN_IF(dgrad(cA, c, &fA, p->g[3], -1, nullptr, 0.f));            // dpooled for level l-1
+            dpooled = p->g[3];
+        }
+        if (l == 4 || l == 0) {
+            HPFG_RETURN_IF(join_side());
+            HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[l == 4 ? 2 : 3], s));
+        }
+    }
     return HPFG_OK;
 }
 
@@ -492,6 +673,7 @@ extern "C" int hpfg_unet_plan_create(int batch, int in_channels, int num_classes
     auto *p = new hpfg_unet_plan();
     p->N = batch; p->in_ch = in_channels; p->n_cls = num_classes; p->H = height; p->W = width; p->precision = precision;
     p->elt = precision == HPFG_PREC_FP32 ? 4 : 2;
+    p->bwd_fusion = precision == HPFG_PREC_BF16 && bwd_fused_enabled();
     describe_unet(in_channels, num_classes, height, width, p->d);
     int64_t total = 0;
     carve(p, nullptr, total);
@@ -507,6 +689,7 @@ extern "C" int hpfg_unet_plan_create(int batch, int in_channels, int num_classes
     HPFG_CUDA_CHECK(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
     HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming));
     for (int k = 0; k < 2; ++k) HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_done[k], cudaEventDisableTiming));
+    for (int k = 0; k < 4; ++k) HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_slot[k], cudaEventDisableTiming));
     HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     if (precision == HPFG_PREC_BF16) {
         const int rc = tc_plan_init(p);
@@ -529,6 +712,8 @@ extern "C" int hpfg_unet_plan_destroy(hpfg_unet_plan_t p) {
     if (p->ev_join) cudaEventDestroy(p->ev_join);
     for (int k = 0; k < 2; ++k)
         if (p->ev_done[k]) cudaEventDestroy(p->ev_done[k]);
+    for (int k = 0; k < 4; ++k)
+        if (p->ev_slot[k]) cudaEventDestroy(p->ev_slot[k]);
     if (p->side) cudaStreamDestroy(p->side);
     if (p->ws) cudaFree(p->ws);
     delete p;
@@ -536,6 +721,13 @@ extern "C" int hpfg_unet_plan_destroy(hpfg_unet_plan_t p) {
 }
 
 extern "C" int64_t hpfg_unet_plan_workspace_bytes(hpfg_unet_plan_t p) { return p ? p->ws_bytes : 0; }
+
+extern "C" int hpfg_unet_plan_set_bwd_fusion(hpfg_unet_plan_t p, int enabled) {
+    HPFG_REQUIRE(p, "hpfg_unet_plan_set_bwd_fusion: null plan");
+    HPFG_REQUIRE(!enabled || p->precision == HPFG_PREC_BF16, "hpfg_unet_plan_set_bwd_fusion: only bf16 plans have the fused backward");
+    p->bwd_fusion = enabled != 0;
+    return HPFG_OK;
+}
 
 extern "C" int hpfg_unet_forward(hpfg_unet_plan_t p, const float *params, float *bn_running, int64_t *bn_counters,
                                  const float *x, float *logits, int training, int no_dropout, int save_for_backward,
@@ -556,6 +748,7 @@ extern "C" int hpfg_unet_backward(hpfg_unet_plan_t p, const float *params, const
     HPFG_REQUIRE(p->saved, "hpfg_unet_backward: no training forward with save_for_backward on this plan");
     cudaStream_t s = (cudaStream_t)stream;
     if (p->precision == HPFG_PREC_FP32) return backward_impl<float>(p, params, dlogits, grads, accumulate, s);
+    if (p->bwd_fusion) return backward_fused(p, params, dlogits, grads, accumulate, s, nullptr);
     return backward_impl<bf16>(p, params, dlogits, grads, accumulate, s);
 }
 
@@ -565,6 +758,7 @@ extern "C" int hpfg_unet_backward_ex(hpfg_unet_plan_t p, const float *params, co
     HPFG_REQUIRE(p->saved, "hpfg_unet_backward_ex: no training forward with save_for_backward on this plan");
     cudaStream_t s = (cudaStream_t)stream;
     if (p->precision == HPFG_PREC_FP32) return backward_impl<float>(p, params, dlogits, grads, accumulate, s, dbottleneck);
+    if (p->bwd_fusion) return backward_fused(p, params, dlogits, grads, accumulate, s, dbottleneck);
     return backward_impl<bf16>(p, params, dlogits, grads, accumulate, s, dbottleneck);
 }
 

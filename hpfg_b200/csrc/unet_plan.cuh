@@ -67,10 +67,11 @@ struct hpfg_unet_plan {
     int64_t wscratch_floats = 0;
     float *bnmem = nullptr;           // BnState arrays
     bool saved = false, saved_dropout = false;
+    bool bwd_fusion = false;          // bf16: BatchNorm backward folded into the dgrad / wgrad kernels (unet_plan.cu: backward_fused)
     const float *saved_x = nullptr;
     cudaEvent_t bucket_ev[hpfg::kNumBuckets] = {};
     // weight gradients run on a side stream, concurrently with the data-gradient chain of the same layer
     cudaStream_t side = nullptr;
-    cudaEvent_t ev_ready = nullptr, ev_join = nullptr, ev_done[2] = {};
+    cudaEvent_t ev_ready = nullptr, ev_join = nullptr, ev_done[2] = {}, ev_slot[4] = {};
     void *tc = nullptr;               // tensor-core path state (conv_tc.cu), bf16 plans only
 };

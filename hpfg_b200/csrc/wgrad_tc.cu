@@ -32,7 +32,9 @@ constexpr int kWgSmemBudget = 222 * 1024;
 // MT: tile width multiplier (tile = 16 rows x 8*MT columns).  The TMA unit retires roughly one tensor load per ~500
 // cycles however small its box (tests/probes/tma_rate_probe.cu), so the 16-channel layers use wide tiles: two loads
 // then feed 256 instead of 128 pixels.
-template <int KS, int NB, int COB, int MT>
+// TWO: the dY operand is built by the transform warps from two staged tiles, draw = sc*g + kb*raw + kd (BatchNorm backward of
+// the layer's own BatchNorm folded into this kernel: the raw gradient tensor is never materialised).
+template <int KS, int NB, int COB, int MT, bool TWO = false>
 struct WgCfg {
     static constexpr int PAD = KS / 2, KK = KS * KS;
     static constexpr int TWP = kTW * MT, TPIX = kTH * TWP;                    // tile width / pixels
@@ -45,14 +47,15 @@ struct WgCfg {
     static constexpr int al(int v) { return (v + 127) / 128 * 128; }
     // + one more 8-row group after the copies holding the constant (1,0,...,0) per pixel: its first accumulator row is
     // sum_pixels dY = the bias gradient, computed by the tensor core instead of an extra shared-memory pass over dY
-    static constexpr int OFF_DOP = 0, OFF_XR = al(D_OP), OFF_X3 = OFF_XR + al(XR_OP), OFF_ONE = OFF_X3 + X3_OP;
+    static constexpr int OFF_DOP = 0, OFF_DRAW = al(D_OP), OFF_XR = OFF_DRAW + (TWO ? al(D_OP) : 0), OFF_X3 = OFF_XR + al(XR_OP),
+                         OFF_ONE = OFF_X3 + X3_OP;
     static constexpr int STAGE_BYTES = al(OFF_ONE + XC);
     static constexpr int MROWS = KS * NB;                                     // useful accumulator rows
     static constexpr int UM = MROWS + 8 <= 64 ? 64 : 128;                     // UMMA M (useful rows + the ones group)
     // the A descriptor spans UM/8 row groups; the groups past MROWS read whatever follows the copies in shared memory
     // (their D rows are never stored) -- keep those reads inside the allocation
     static constexpr int TAIL_PAD = al((UM / 8 - MROWS / 8 - 1) * XC);
-    static constexpr int FIXED_BYTES = 1024 + 2 * 256 * 4;
+    static constexpr int FIXED_BYTES = 1024 + 5 * 256 * 4;
     static constexpr int STAGES_RAW = (kWgSmemBudget - FIXED_BYTES - TAIL_PAD) / STAGE_BYTES;
     static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + TAIL_PAD + FIXED_BYTES + 1024;
@@ -65,17 +68,19 @@ struct WgCfg {
 
 struct WgParams {
     const float *scale, *shift;     // producer transform of X (nullptr = identity)
+    const float *dsc, *dkb, *dkd;   // TWO: BatchNorm-backward constants per output channel (draw = dsc*g + dkb*raw + dkd)
     const uint8_t *dropbits;
     float inv_keep;
     float *scratch;                 // [S][KK*Cin*Cout + Cout] fp32 partials
     int N, H, W, Cin, Cout, tiles_h, tiles_w, m_tiles, ci_blocks, co_blocks, S;
 };
 
-template <int KS, int NB, int COB, int MT>
+template <int KS, int NB, int COB, int MT, bool TWO>
 __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
-                                                                 const __grid_constant__ CUtensorMap tmD, const WgParams P) {
+                                                                 const __grid_constant__ CUtensorMap tmD,
+                                                                 const __grid_constant__ CUtensorMap tmR, const WgParams P) {
     pdl_launch_dependents();
-    using C = WgCfg<KS, NB, COB, MT>;
+    using C = WgCfg<KS, NB, COB, MT, TWO>;
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t *fixed = smem + C::STAGES * C::STAGE_BYTES + C::TAIL_PAD;
@@ -83,6 +88,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(fixed + 512);
     float *s_scale = reinterpret_cast<float *>(fixed + 1024);
     float *s_shift = s_scale + 256;
+    float *s_dsc = s_shift + 256, *s_dkb = s_dsc + 256, *s_dkd = s_dkb + 256;
 
     // broadcast from lane 0: the warp index is warp-uniform for the compiler (role code stays in the uniform datapath)
     const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
@@ -108,6 +114,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&tmX);
         ptx::prefetch_tensormap(&tmD);
+        if (TWO) ptx::prefetch_tensormap(&tmR);
     }
     if (warp == 2) ptx::tmem_alloc(ptx::smem_u32(tmem_slot), C::TMEM_COLS);
     for (int i = threadIdx.x; i < C::STAGES * (C::XC / 16); i += blockDim.x)      // the constant ones group of every stage
@@ -116,6 +123,12 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     pdl_wait();
     if (P.scale)
         for (int i = threadIdx.x; i < P.Cin; i += blockDim.x) { s_scale[i] = P.scale[i]; s_shift[i] = P.shift[i]; }
+    if (TWO)
+        for (int i = threadIdx.x; i < COB; i += blockDim.x) {
+            const int co = co0 + i;
+            const bool ok = co < P.Cout;
+            s_dsc[i] = ok ? P.dsc[co] : 0.f; s_dkb[i] = ok ? P.dkb[co] : 0.f; s_dkd[i] = ok ? P.dkd[co] : 0.f;
+        }
     ptx::tc_fence_before();
     __syncthreads();
     ptx::tc_fence_after();
@@ -131,8 +144,9 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
             ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 11);
             const uint32_t sb = smem_u32 + stage * C::STAGE_BYTES;
             if (ptx::elect_one()) {
-                ptx::mbar_expect_tx(bar_full + 8 * stage, C::D_OP + C::XR_OP);
+                ptx::mbar_expect_tx(bar_full + 8 * stage, C::D_OP * (TWO ? 2 : 1) + C::XR_OP);
                 ptx::tma_load_5d(sb + C::OFF_DOP, &tmD, bar_full + 8 * stage, 0, w0, h0, co0 / 8, ti.n_img);
+                if (TWO) ptx::tma_load_5d(sb + C::OFF_DRAW, &tmR, bar_full + 8 * stage, 0, w0, h0, co0 / 8, ti.n_img);
                 ptx::tma_load_5d(sb + C::OFF_XR, &tmX, bar_full + 8 * stage, 0, w0 - C::PAD, h0 - C::PAD, ci0 / 8, ti.n_img);
             }
             __syncwarp();
@@ -217,6 +231,34 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
 #pragma unroll
                 for (int s = 0; s < KS; ++s)
                     if (hc - s >= 0 && hc - s < C::TWP) ptx::sts128(dst + s * (NB / 8) * C::XC - s * 16, v);
+            }
+            if constexpr (TWO) {
+                // dY operand in place: [chunk of 8 co][tile pixel][8 co] <- dsc*g + dkb*raw + dkd, zero outside the image
+                // (a warp works on one chunk at a time: consecutive lanes = consecutive pixels, conflict-free 128-bit accesses)
+                constexpr int NCD = COB / 8, GW = NCD >= 8 ? 1 : 8 / NCD;          // warps sharing one chunk
+                const int xw = warp - 4;
+                const bool tile_border = h0 + C::PAD + kTH > P.H || w0 + C::PAD + C::TWP > P.W;
+#pragma unroll 1
+                for (int dc = NCD >= 8 ? xw : xw % NCD; dc < NCD; dc += 8) {
+                    float a[8], b[8], d[8];
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) { a[k] = s_dsc[dc * 8 + k]; b[k] = s_dkb[dc * 8 + k]; d[k] = s_dkd[dc * 8 + k]; }
+#pragma unroll 2
+                    for (int px = (NCD >= 8 ? 0 : (xw / NCD) * 32) + lane; px < C::TPIX; px += 32 * GW) {
+                        const uint32_t addr = sb + C::OFF_DOP + (dc * C::TPIX + px) * 16;
+                        float g[8], r[8];
+                        unpack8(ptx::lds128(addr), g);
+                        unpack8(ptx::lds128(addr + C::OFF_DRAW), r);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) g[k] = fmaf(a[k], g[k], fmaf(b[k], r[k], d[k]));
+                        uint4 v = make_uint4(pack2(g[0], g[1]), pack2(g[2], g[3]), pack2(g[4], g[5]), pack2(g[6], g[7]));
+                        if (tile_border) {
+                            const int gh = h0 + C::PAD + px / C::TWP, gw = w0 + C::PAD + px % C::TWP;
+                            if (gh >= P.H || gw >= P.W) v = make_uint4(0u, 0u, 0u, 0u);
+                        }
+                        ptx::sts128(addr, v);
+                    }
+                }
             }
             ptx::fence_proxy_async_smem();
             __syncwarp();
@@ -310,71 +352,93 @@ __global__ void __launch_bounds__(256) tc_wgrad_reduce_kernel(const float *__res
     }
 }
 
-static void wg_shape(int ks, int N, int H, int W, int Cin, int Cout, int &NB, int &COB, int &MT, int &ci_blocks, int &co_blocks, int &S,
+static void wg_shape(int ks, int N, int H, int W, int Cin, int Cout, bool two, int &NB, int &COB, int &MT, int &ci_blocks, int &co_blocks, int &S,
                      int &m_tiles) {
     NB = Cin == 16 ? 16 : 32;
-    COB = std::min(Cout, 128);
+    COB = std::min(Cout, two ? 64 : 128);      // two-source dY: a second 16 KB tile per 64 output channels must fit next to three pipeline stages
     ci_blocks = Cin / NB;
     co_blocks = Cout / COB;
     // wide tiles for the 16-channel layers on large images (TMA-issue bound otherwise; with 32 input channels the
     // wider stage leaves too few pipeline stages in shared memory and measures slower)
     MT = (ks == 3 && NB == 16 && COB <= 32 && W % (2 * kTW) == 0 && (int64_t)N * ((H + kTH - 1) / kTH) * (W / (2 * kTW)) >= 4 * kNumSMs) ? 2 : 1;
     m_tiles = N * ((H + kTH - 1) / kTH) * ((W + kTW * MT - 1) / (kTW * MT));
-    S = std::max(1, std::min(kNumSMs / (ci_blocks * co_blocks), m_tiles));
+    S = std::max(1, std::min(tc_cta_cap(2) / (ci_blocks * co_blocks), m_tiles));
 }
 
 int64_t tc_wgrad_scratch_floats(int N, int H, int W, int Cin, int Cout, int KS) {
-    int NB, COB, MT, cib, cob, S, mt;
-    wg_shape(KS, N, H, W, Cin, Cout, NB, COB, MT, cib, cob, S, mt);
-    return (int64_t)S * ((int64_t)KS * KS * Cin * Cout + Cout);
+    int64_t need = 0;
+    for (int two = 0; two < 2; ++two) {
+        int NB, COB, MT, cib, cob, S, mt;
+        wg_shape(KS, N, H, W, Cin, Cout, two != 0, NB, COB, MT, cib, cob, S, mt);
+        need = std::max(need, (int64_t)S * ((int64_t)KS * KS * Cin * Cout + Cout));
+    }
+    return need;
 }
 
-template <int KS, int NB, int COB, int MT>
-static int wg_launch(const CUtensorMap &mx, const CUtensorMap &md, const WgParams &P, cudaStream_t s) {
-    using C = WgCfg<KS, NB, COB, MT>;
+template <int KS, int NB, int COB, int MT, bool TWO>
+static int wg_launch(const CUtensorMap &mx, const CUtensorMap &md, const CUtensorMap &mr, const WgParams &P, cudaStream_t s) {
+    using C = WgCfg<KS, NB, COB, MT, TWO>;
     static bool attr_set = false;
     if (!attr_set) {
-        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<KS, NB, COB, MT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        HPFG_CUDA_CHECK(cudaFuncSetAttribute(tc_wgrad_kernel<KS, NB, COB, MT, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         attr_set = true;
     }
     const int grid = P.ci_blocks * P.co_blocks * P.S;
-    HPFG_CUDA_CHECK(launch_pdl(tc_wgrad_kernel<KS, NB, COB, MT>, grid, kWgThreads, C::SMEM_BYTES, s, mx, md, P));
+    HPFG_CUDA_CHECK(launch_pdl(tc_wgrad_kernel<KS, NB, COB, MT, TWO>, grid, kWgThreads, C::SMEM_BYTES, s, mx, md, mr, P));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
 
 template <int KS>
-static int wg_dispatch(int NB, int COB, int MT, const CUtensorMap &mx, const CUtensorMap &md, const WgParams &P, cudaStream_t s) {
-#define HPFG_WG_CASE(nb, cob)                                                    \
-    if (NB == nb && COB == cob) {                                                \
-        if constexpr (KS == 3 && nb == 16 && cob <= 32) {                        \
-            if (MT == 2) return wg_launch<KS, nb, cob, 2>(mx, md, P, s);         \
-        }                                                                        \
-        return wg_launch<KS, nb, cob, 1>(mx, md, P, s);                          \
+static int wg_dispatch(int NB, int COB, int MT, bool two, const CUtensorMap &mx, const CUtensorMap &md, const CUtensorMap &mr, const WgParams &P,
+                       cudaStream_t s) {
+#define HPFG_WG_CASE(nb, cob)                                                               \
+    if (NB == nb && COB == cob) {                                                           \
+        if constexpr (KS == 3 && cob <= 64) {       /* only 3x3 convolutions are followed by a BatchNorm */ \
+            if (two) {                                                                      \
+                if constexpr (nb == 16 && cob <= 32) {                                      \
+                    if (MT == 2) return wg_launch<KS, nb, cob, 2, true>(mx, md, mr, P, s);  \
+                }                                                                           \
+                return wg_launch<KS, nb, cob, 1, true>(mx, md, mr, P, s);                   \
+            }                                                                               \
+        }                                                                                   \
+        if (two) break;                                                                     \
+        if constexpr (KS == 3 && nb == 16 && cob <= 32) {                                   \
+            if (MT == 2) return wg_launch<KS, nb, cob, 2, false>(mx, md, mr, P, s);         \
+        }                                                                                   \
+        return wg_launch<KS, nb, cob, 1, false>(mx, md, mr, P, s);                          \
     }
+    do {
     HPFG_WG_CASE(16, 16) HPFG_WG_CASE(16, 32) HPFG_WG_CASE(16, 64) HPFG_WG_CASE(16, 128)
     HPFG_WG_CASE(32, 16) HPFG_WG_CASE(32, 32) HPFG_WG_CASE(32, 64) HPFG_WG_CASE(32, 128)
 #undef HPFG_WG_CASE
-    set_error("tc wgrad: no kernel for NB=" + std::to_string(NB) + " COB=" + std::to_string(COB));
+    } while (0);
+    set_error("tc wgrad: no kernel for NB=" + std::to_string(NB) + " COB=" + std::to_string(COB) + (two ? " (two-source dY)" : ""));
     return HPFG_ERR_UNSUPPORTED;
 }
 
 int tc_wgrad_run(int ks, int N, int H, int W, int Cin, int Cout, int cin_real, int cout_real, const void *x, LoadXform xf, const void *dy, float *scratch,
-                 int64_t scratch_floats, float *dw_oihw, float *dbias, int accumulate, cudaStream_t s) {
+                 int64_t scratch_floats, float *dw_oihw, float *dbias, int accumulate, cudaStream_t s, const TcBwdFuse *fuse) {
     ProfScope _prof(PROF_WGRAD_TC, s);
     int NB, COB, MT;
     WgParams P{};
-    wg_shape(ks, N, H, W, Cin, Cout, NB, COB, MT, P.ci_blocks, P.co_blocks, P.S, P.m_tiles);
+    const bool two = fuse && fuse->in_raw;
+    wg_shape(ks, N, H, W, Cin, Cout, two, NB, COB, MT, P.ci_blocks, P.co_blocks, P.S, P.m_tiles);
     HPFG_REQUIRE(tc_wgrad_scratch_floats(N, H, W, Cin, Cout, ks) <= scratch_floats, "tc_wgrad: scratch too small");
-    CUtensorMap mx, md;
+    CUtensorMap mx, md, mr;
     HPFG_RETURN_IF(make_map_chunked(&mx, x, N, H, W, Cin, NB / 8, kTW * MT + ks - 1, kTH + ks - 1));
     HPFG_RETURN_IF(make_map_chunked(&md, dy, N, H, W, Cout, COB / 8, kTW * MT, kTH));
+    mr = md;
+    if (two) {
+        HPFG_RETURN_IF(make_map_chunked(&mr, fuse->in_raw, N, H, W, Cout, COB / 8, kTW * MT, kTH));
+        P.dsc = fuse->sc; P.dkb = fuse->kb; P.dkd = fuse->kd;
+    }
     P.scale = xf.scale; P.shift = xf.shift;
     P.dropbits = reinterpret_cast<const uint8_t *>(xf.drop.bits); P.inv_keep = xf.drop.inv_keep;
     P.scratch = scratch;
     P.N = N; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
     P.tiles_h = (H + kTH - 1) / kTH; P.tiles_w = (W + kTW * MT - 1) / (kTW * MT);
-    HPFG_RETURN_IF(ks == 3 ? wg_dispatch<3>(NB, COB, MT, mx, md, P, s) : wg_dispatch<1>(NB, COB, MT, mx, md, P, s));
+    HPFG_RETURN_IF(ks == 3 ? wg_dispatch<3>(NB, COB, MT, two, mx, md, mr, P, s) : wg_dispatch<1>(NB, COB, MT, two, mx, md, mr, P, s));
     const int64_t per = (int64_t)ks * ks * Cin * Cout + Cout;
     const int blocks = (int)((per + 31) / 32);
     HPFG_CUDA_CHECK(launch_pdl(tc_wgrad_reduce_kernel, blocks, 256, 0, s, scratch, P.S, Cin, Cout, ks * ks, cin_real, cout_real, dw_oihw, dbias, accumulate));
@@ -432,7 +496,27 @@ extern "C" int hpfg_wgrad_tc_debug(int N, int H, int W, int cin, int cout, int k
     HPFG_CUDA_CHECK(cudaMalloc(&scratch, (size_t)nf * 4));
     LoadXform xf{};
     xf.scale = scale; xf.shift = shift; xf.drop.bits = nullptr; xf.drop.inv_keep = 1.f;
-    const int rc = tc_wgrad_run(ks, N, H, W, cin, cout, cin, cout, x_bf16_nhwc, xf, dy_bf16_nhwc, scratch, nf, dw_oihw, dbias, 0, s);
+    const int rc = tc_wgrad_run(ks, N, H, W, cin, cout, cin, cout, x_bf16_nhwc, xf, dy_bf16_nhwc, scratch, nf, dw_oihw, dbias, 0, s, nullptr);
+    cudaStreamSynchronize(s);
+    cudaFree(scratch);
+    if (rc == HPFG_OK) HPFG_CUDA_CHECK(cudaGetLastError());
+    return rc;
+}
+
+extern "C" int hpfg_wgrad_tc_fused_debug(int N, int H, int W, int cin, int cout, int ks, const void *x_bf16_nhwc, const void *g_bf16_nhwc,
+                                         const void *raw_bf16_nhwc, const float *sc, const float *kb, const float *kd, const float *scale,
+                                         const float *shift, float *dw_oihw, float *dbias, void *stream) {
+    HPFG_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && ks == 3, "hpfg_wgrad_tc_fused_debug: unsupported shape");
+    HPFG_REQUIRE(x_bf16_nhwc && g_bf16_nhwc && raw_bf16_nhwc && sc && kb && kd, "hpfg_wgrad_tc_fused_debug: null argument");
+    cudaStream_t s = (cudaStream_t)stream;
+    const int64_t nf = tc_wgrad_scratch_floats(N, H, W, cin, cout, ks);
+    float *scratch = nullptr;
+    HPFG_CUDA_CHECK(cudaMalloc(&scratch, (size_t)nf * 4));
+    LoadXform xf{};
+    xf.scale = scale; xf.shift = shift; xf.drop.bits = nullptr; xf.drop.inv_keep = 1.f;
+    TcBwdFuse f;
+    f.in_raw = raw_bf16_nhwc; f.sc = sc; f.kb = kb; f.kd = kd;
+    const int rc = tc_wgrad_run(ks, N, H, W, cin, cout, cin, cout, x_bf16_nhwc, xf, g_bf16_nhwc, scratch, nf, dw_oihw, dbias, 0, s, &f);
     cudaStreamSynchronize(s);
     cudaFree(scratch);
     if (rc == HPFG_OK) HPFG_CUDA_CHECK(cudaGetLastError());
@@ -444,7 +528,7 @@ extern "C" int hpfg_wgrad_tc_debug(int N, int H, int W, int cin, int cout, int k
 // buffers with CUDA events on `stream`; returns the average milliseconds per launch.
 namespace hpfg {
 int tc_run_bench(int op, int ks, int N, int H, int W, int cin, int cout, const void *in, void *out, const float *w, const float *scale,
-                 const float *shift, float *stats, cudaStream_t s);   // conv_tc.cu
+                 const float *shift, float *stats, cudaStream_t s, int fuse_mode, const void *aux);   // conv_tc.cu
 }
 __global__ void fill_pattern_bf16(__nv_bfloat16 *p, size_t n, float scale) {
     pdl_prologue();
@@ -452,14 +536,17 @@ __global__ void fill_pattern_bf16(__nv_bfloat16 *p, size_t n, float scale) {
         p[i] = __float2bfloat16(scale * (float)((int)((i * 2654435761u) >> 24) - 128) / 128.f);
 }
 extern "C" int hpfg_conv_tc_bench(int op, int N, int H, int W, int cin, int cout, int ks, int iters, float *ms_out_host, void *stream) {
-    HPFG_REQUIRE(op >= 0 && op <= 2 && iters > 0 && ms_out_host, "hpfg_conv_tc_bench: bad arguments");
+    // op 3 / 4 / 5: data gradient with the two-source loader / the GSTAT epilogue / both; op 6: weight gradient with the two-source dY
+    HPFG_REQUIRE(op >= 0 && op <= 6 && iters > 0 && ms_out_host, "hpfg_conv_tc_bench: bad arguments");
     cudaStream_t s = (cudaStream_t)stream;
     const size_t px = (size_t)N * H * W;
-    __nv_bfloat16 *a = nullptr, *b = nullptr;
+    __nv_bfloat16 *a = nullptr, *b = nullptr, *aux = nullptr;
     float *w = nullptr, *sc = nullptr, *stats = nullptr, *scratch = nullptr, *dw = nullptr;
     const int64_t nf = tc_wgrad_scratch_floats(N, H, W, cin, cout, ks);
     HPFG_CUDA_CHECK(cudaMalloc(&a, px * std::max(cin, cout) * 2));
     HPFG_CUDA_CHECK(cudaMalloc(&b, px * std::max(cin, cout) * 2));
+    HPFG_CUDA_CHECK(cudaMalloc(&aux, px * std::max(cin, cout) * 2));
+    HPFG_CUDA_CHECK(cudaMemsetAsync(aux, 0, px * std::max(cin, cout) * 2, s));
     HPFG_CUDA_CHECK(cudaMalloc(&w, (size_t)cin * cout * ks * ks * 4));
     HPFG_CUDA_CHECK(cudaMalloc(&sc, 2 * 256 * 4));
     HPFG_CUDA_CHECK(cudaMalloc(&stats, (size_t)kNumSMs * 2 * 256 * 4 * 4));
@@ -477,8 +564,15 @@ extern "C" int hpfg_conv_tc_bench(int op, int N, int H, int W, int cin, int cout
     int rc = HPFG_OK;
     for (int i = -2; i < iters && rc == HPFG_OK; ++i) {
         if (i == 0) cudaEventRecord(e0, s);
-        if (op == 2) rc = tc_wgrad_run(ks, N, H, W, cin, cout, cin, cout, a, xf, b, scratch, nf, dw, dw + (size_t)cin * cout * ks * ks, 0, s);
-        else rc = tc_run_bench(op, ks, N, H, W, cin, cout, a, b, w, op == 0 ? sc : nullptr, op == 0 ? sc + 256 : nullptr, op == 0 ? stats : nullptr, s);
+        if (op == 2 || op == 6) {
+            TcBwdFuse f;
+            f.in_raw = aux; f.sc = sc; f.kb = sc; f.kd = sc;
+            rc = tc_wgrad_run(ks, N, H, W, cin, cout, cin, cout, a, xf, b, scratch, nf, dw, dw + (size_t)cin * cout * ks * ks, 0, s, op == 6 ? &f : nullptr);
+        } else if (op >= 3) {
+            rc = tc_run_bench(1, ks, N, H, W, cin, cout, a, b, w, sc, sc + 256, stats, s, op - 2, aux);
+        } else {
+            rc = tc_run_bench(op, ks, N, H, W, cin, cout, a, b, w, op == 0 ? sc : nullptr, op == 0 ? sc + 256 : nullptr, op == 0 ? stats : nullptr, s, 0, nullptr);
+        }
     }
     cudaEventRecord(e1, s);
     cudaStreamSynchronize(s);
@@ -486,7 +580,7 @@ extern "C" int hpfg_conv_tc_bench(int op, int N, int H, int W, int cin, int cout
     cudaEventElapsedTime(&ms, e0, e1);
     *ms_out_host = ms / iters;
     cudaEventDestroy(e0); cudaEventDestroy(e1);
-    cudaFree(a); cudaFree(b); cudaFree(w); cudaFree(sc); cudaFree(stats); cudaFree(scratch); cudaFree(dw);
+    cudaFree(a); cudaFree(b); cudaFree(aux); cudaFree(w); cudaFree(sc); cudaFree(stats); cudaFree(scratch); cudaFree(dw);
     if (rc == HPFG_OK) HPFG_CUDA_CHECK(cudaGetLastError());
     return rc;
 }

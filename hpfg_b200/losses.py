@@ -133,13 +133,37 @@ class DiceLoss(nn.Module):
         return _DiceFn.apply(inputs, target, self.n_classes, weight, softmax)
 
 
+class _SoftmaxMseFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, sigmoid):
+        L.require_cuda(a, "softmax_mse_loss input")
+        a32, b32 = a.contiguous().float(), b.detach().contiguous().float()
+        n, c, h, w = a32.shape
+        out = torch.empty_like(a32)
+        L.check(L.lib().hpfg_softmax_mse(L.ptr(a32), L.ptr(b32), None, n, c, h, w, int(bool(sigmoid)), L.ptr(out),
+                                         L.stream_ptr(a32.device)), "hpfg_softmax_mse")
+        ctx.save_for_backward(a32, b32)
+        ctx.sigmoid = bool(sigmoid)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        a32, b32 = ctx.saved_tensors
+        n, c, h, w = a32.shape
+        da = torch.empty_like(a32)
+        L.check(L.lib().hpfg_softmax_mse(L.ptr(a32), L.ptr(b32), L.ptr(g.contiguous().float()), n, c, h, w, int(ctx.sigmoid),
+                                         L.ptr(da), L.stream_ptr(a32.device)), "hpfg_softmax_mse")
+        return da, None, None
+
+
 def softmax_mse_loss(input_logits, target_logits, sigmoid=False):
-    """Unreduced (softmax(a)-softmax(b))**2 (utils/loss/diceloss.py:64-81).  Element-wise map kept in torch:
-    the fused kernels consume the reduced forms (mean / uncertainty-masked mean) directly."""
+    """Unreduced (softmax(a)-softmax(b))**2 over dim 1, or of the sigmoids (utils/loss/diceloss.py:64-81), on the
+    `hpfg_softmax_mse` kernel (forward map and the gradient wrt ``input_logits``; the target is the no_grad teacher output
+    in every trainer that calls this, 2019_07...:134-148, and carries no gradient here).  [N,C,H,W] CUDA logits, C <= 8."""
     assert input_logits.size() == target_logits.size()
-    if sigmoid:
-        return (torch.sigmoid(input_logits) - torch.sigmoid(target_logits)) ** 2
-    return (torch.softmax(input_logits, dim=1) - torch.softmax(target_logits, dim=1)) ** 2
+    if input_logits.dim() != 4:
+        raise L.HpfgError("softmax_mse_loss: expected [N,C,H,W] logits, got %s" % (tuple(input_logits.shape),))
+    return _SoftmaxMseFn.apply(input_logits, target_logits, sigmoid)
 
 
 # ---- fused whole-step losses (what the MT / CPS / UAMT trainers compute inline) ---------------------------

@@ -88,49 +88,72 @@ class _StepBase:
         self._graph_enabled = bool(enabled)
         self._graph_dp = bool(data_parallel)      # also capture the NCCL bucket all-reduces (torch >= 2.x captures NCCL work)
         if not enabled:
-            self._graph = None
             self._ggraph = None
+            self._gsig = None
 
-    _graph_dp_capable = False     # only the Mean-Teacher driver's capture with the NCCL all-reduces inside has been measured
+    _graph_dp_capable = True      # the bucketed NCCL all-reduces are captured with the step (a refused capture falls back to eager launches)
 
     def _use_graph(self):
         dp_ok = self.world == 1 or (self._graph_dp and self._graph_dp_capable)
         return self._graph_enabled and self.cur_itrs >= 2 and dp_ok
 
     def _graph_replay(self, inputs, dyn_f, fwd_models, body):
-        """Generic capture-once / replay driver (CPS, UAMT, ICT; Mean-Teacher keeps its own copy below).
+        """Generic capture-once / replay driver (all step drivers).
         inputs: tensors copied into static buffers before each replay; dyn_f: python floats for the device block
         (fp32); fwd_models: one entry per network forward in the eager call order -> one Philox-offset slot each (the
         offsets advance exactly as the eager path advances them); body(static_inputs, dyn_f_dev, dyn_o_dev) enqueues the
-        step with the `_dv` entry points and returns its output dict (static tensors)."""
+        step with the `_dv` entry points and returns its output dict (static tensors).
+
+        The per-iteration scalars travel through a RING of pinned host slots: an async H2D copy reads pinned memory when
+        the stream reaches it, not at enqueue time, so a slot is only rewritten after the event recorded behind its copy
+        has completed (the host may run up to `_RING` replays ahead of the device without syncing).
+        The captured graph bakes in raw pointers (flat parameters, BN buffers, plan workspaces, gradient / momentum
+        buffers): they are part of the signature, and a change (`.to()`, `load_state_dict(assign=True)`, ...) drops the
+        graph and captures again."""
         dev = inputs[0].device
-        sig = tuple((tuple(t.shape), t.dtype) for t in inputs) + (len(dyn_f), len(fwd_models))
+        models = []
+        for m in fwd_models:
+            if not any(m is q for q in models):
+                models.append(m)
+        for m in models:
+            m.ensure_flat()
+        ptrs = tuple((m.flat_params.data_ptr(), m.bn_running.data_ptr(), m.bn_counters.data_ptr(), id(m._plans)) for m in models)
+        ptrs += tuple(t.data_ptr() for t in self._state_tensors())
+        sig = tuple((tuple(t.shape), t.dtype) for t in inputs) + (len(dyn_f), len(fwd_models), ptrs)
         if getattr(self, "_gsig", None) != sig:
             self._gin = [torch.empty_like(t) for t in inputs]
             self._gf = torch.zeros(len(dyn_f), device=dev, dtype=torch.float32)
             self._go = torch.zeros(len(fwd_models), device=dev, dtype=torch.int64)
-            self._gf_host = torch.zeros(len(dyn_f), dtype=torch.float32).pin_memory()
-            self._go_host = torch.zeros(len(fwd_models), dtype=torch.int64).pin_memory()
+            self._ring = [(torch.zeros(len(dyn_f), dtype=torch.float32).pin_memory(),
+                           torch.zeros(len(fwd_models), dtype=torch.int64).pin_memory(), torch.cuda.Event())
+                          for _ in range(self._RING)]
+            self._ring_used = [False] * self._RING
+            self._ring_pos = 0
             self._ggraph, self._gsig = None, sig
+        k = self._ring_pos
+        self._ring_pos = (k + 1) % self._RING
+        f_host, o_host, ev = self._ring[k]
+        if self._ring_used[k]:
+            ev.synchronize()               # only blocks when the host is a whole ring ahead of the device
         for i, v in enumerate(dyn_f):
-            self._gf_host[i] = v
+            f_host[i] = v
         for i, m in enumerate(fwd_models):
-            self._go_host[i] = m._philox_offset
+            o_host[i] = m._philox_offset
             if m.training:
                 m._philox_offset += 8
-        self._gf.copy_(self._gf_host, non_blocking=True)
-        self._go.copy_(self._go_host, non_blocking=True)
+        self._gf.copy_(f_host, non_blocking=True)
+        self._go.copy_(o_host, non_blocking=True)
+        ev.record()
+        self._ring_used[k] = True
         for s, t in zip(self._gin, inputs):
             s.copy_(t, non_blocking=True)
         if self._ggraph is None:
-            for m in fwd_models:
-                m.ensure_flat()
             g = torch.cuda.CUDAGraph()
             n0 = L.lib().hpfg_launch_count()
             try:
                 with torch.cuda.graph(g):
                     self._gout = body(self._gin, self._gf, self._go)
-            except Exception as exc:        # capture not possible here: stay eager on the same device-value path
+            except Exception as exc:        # capture not possible here (e.g. a collective that refuses capture): stay eager
                 import warnings
                 warnings.warn("hpfg_b200: CUDA-graph capture of the step failed (%s); falling back to eager launches" % exc)
                 self._graph_enabled, self._ggraph = False, None
@@ -141,6 +164,71 @@ class _StepBase:
         self._ggraph.replay()
         self.replayed_kernels += self.kernels_per_replay
         return self._gout
+
+    _RING = 8
+
+    def _state_tensors(self):
+        """Optimiser-side device buffers of this driver (gradient + momentum buffers), in a fixed order."""
+        return [getattr(self, n) for n in ("grads", "mom", "g1", "b1", "g2", "b2") if hasattr(self, n)]
+
+    def _models(self):
+        return [getattr(self, n) for n in ("model", "ema_model", "m1", "m2") if hasattr(self, n)]
+
+    # ------------------------------------------------------------------ checkpoint / resume (2017_03...:126-133)
+    def state_dict(self):
+        """{cur_itrs, philox offsets, optimizer}: `optimizer` holds torch.optim.SGD-style per-parameter momentum buffers
+        (state[i]['momentum_buffer'] in model.parameters() order) so that a reference checkpoint's optimizer state and
+        this driver's flat momentum buffer interchange."""
+        out = {"cur_itrs": self.cur_itrs, "philox": [m._philox_offset for m in self._models()], "optimizers": []}
+        pairs = [(getattr(self, a, None), getattr(self, b, None)) for a, b in (("model", "mom"), ("m1", "b1"), ("m2", "b2"))]
+        for model, buf in pairs:
+            if model is None or buf is None:
+                continue
+            state = {i: {"momentum_buffer": buf[o:o + n].view(shape).clone()} for i, (o, n, shape) in enumerate(model._layout)}
+            out["optimizers"].append({"state": state if self.cur_itrs > 0 else {},
+                                      "param_groups": [{"lr": medical_lr(self.cur_itrs + 1, self.base_lr, self.total_itrs),
+                                                        "momentum": self.momentum, "weight_decay": self.weight_decay,
+                                                        "params": list(range(len(model._layout)))}]})
+        return out
+
+    def load_state_dict(self, sd):
+        self.cur_itrs = int(sd["cur_itrs"])
+        for m, off in zip(self._models(), sd.get("philox", [])):
+            m._philox_offset = int(off)
+        pairs = [(getattr(self, a, None), getattr(self, b, None)) for a, b in (("model", "mom"), ("m1", "b1"), ("m2", "b2"))]
+        pairs = [(m, b) for m, b in pairs if m is not None and b is not None]
+        for (model, buf), opt in zip(pairs, sd.get("optimizers", [])):
+            buf.zero_()
+            for i, (o, n, shape) in enumerate(model._layout):
+                st = opt["state"].get(i)
+                if st is not None and st.get("momentum_buffer") is not None:
+                    buf[o:o + n].copy_(st["momentum_buffer"].reshape(-1))
+
+    def _check_buffers(self):
+        """The flat gradient / momentum buffers must match the (possibly re-flattened or moved) parameter buffer."""
+        for model, names in ((getattr(self, "model", None), ("grads", "mom")), (getattr(self, "m1", None), ("g1", "b1")),
+                             (getattr(self, "m2", None), ("g2", "b2"))):
+            if model is None:
+                continue
+            flat = model.flat_params
+            for n in names:
+                buf = getattr(self, n)
+                if buf.device != flat.device or buf.numel() != flat.numel():
+                    raise L.HpfgError("step driver buffer '%s' (%s, %d) no longer matches the model's flat parameters (%s, %d): "
+                                      "build the step driver after moving the model" % (n, buf.device, buf.numel(), flat.device, flat.numel()))
+            if flat.is_cuda and flat.device.index != torch.cuda.current_device():
+                raise L.HpfgError("the model lives on %s but the current CUDA device is %d: call torch.cuda.set_device first "
+                                  "(the library launches on the current device)" % (flat.device, torch.cuda.current_device()))
+
+    def _broadcast_from_rank0(self):
+        """Data parallel: every rank starts from rank 0's parameters / BN buffers (what DDP does at construction)."""
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        for m in self._models():
+            m.ensure_flat()
+            for t in (m.flat_params, m.bn_running, m.bn_counters):
+                dist.broadcast(t, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
 
     def _forward_dv(self, model, x, save, out, offset_dev):
         plan = model._acquire_plan(x, need_grad=save)
@@ -239,10 +327,13 @@ class MeanTeacherStep(_StepBase):
         ema_model.ensure_flat()
         self.grads = torch.zeros_like(model.flat_params)
         self.mom = torch.zeros_like(model.flat_params)
+        self._check_buffers()
+        self._broadcast_from_rank0()
 
     def step(self, x, labels):
         """x: [n_l+n_u, C, H, W] fp32 CUDA (labeled slices first); labels: [n_l, H, W] int64 CUDA."""
         self.cur_itrs += 1
+        self._check_buffers()
         if self._use_graph():
             return self._step_graph(x, labels)
         n_l = labels.shape[0]
@@ -265,53 +356,14 @@ class MeanTeacherStep(_StepBase):
         return r["scalars"][0]
 
     def _step_graph(self, x, labels):
-        dev = x.device
-        if getattr(self, "_graph", None) is None or tuple(self._gx.shape) != tuple(x.shape) or tuple(self._gy.shape) != tuple(labels.shape):
-            self._gx, self._gy = torch.empty_like(x), torch.empty_like(labels)
-            self._dyn_f = torch.zeros(4, device=dev, dtype=torch.float32)        # lr, alpha, 1 - alpha, consistency weight
-            self._dyn_o = torch.zeros(2, device=dev, dtype=torch.int64)          # Philox offsets: student, teacher
-            self._dyn_f_host = torch.zeros(4, dtype=torch.float32).pin_memory()
-            self._dyn_o_host = torch.zeros(2, dtype=torch.int64).pin_memory()
-            self._graph = None
-        lr = medical_lr(self.cur_itrs, self.base_lr, self.total_itrs)
-        alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)
-        w = self._consistency_weight()
-        a32 = torch.tensor(alpha, dtype=torch.float32)
-        self._dyn_f_host[0], self._dyn_f_host[1], self._dyn_f_host[3] = lr, alpha, w
-        self._dyn_f_host[2] = 1.0 - a32                                          # fp32 subtraction, as the by-value entry point
-        self._dyn_o_host[0], self._dyn_o_host[1] = self.model._philox_offset, self.ema_model._philox_offset
-        self.model._philox_offset += 8
-        self.ema_model._philox_offset += 8
-        self._dyn_f.copy_(self._dyn_f_host, non_blocking=True)
-        self._dyn_o.copy_(self._dyn_o_host, non_blocking=True)
-        self._gx.copy_(x, non_blocking=True)
-        self._gy.copy_(labels, non_blocking=True)
-        if self._graph is None:
-            self.model.ensure_flat()
-            self.ema_model.ensure_flat()
-            g = torch.cuda.CUDAGraph()
-            n0 = L.lib().hpfg_launch_count()
-            try:
-                with torch.cuda.graph(g):
-                    self._graph_out = self._step_body_dv(self._gx, self._gy)
-            except Exception as exc:        # capture not possible here (e.g. a collective that refuses capture): stay eager
-                import warnings
-                warnings.warn("hpfg_b200: CUDA-graph capture of the step failed (%s); falling back to eager launches" % exc)
-                self._graph_enabled, self._graph = False, None
-                torch.cuda.synchronize()
-                out = self._step_body_dv(self._gx, self._gy)       # same device-value path, launched eagerly
-                self.last = dict(scalars=out["scalars"], lr=lr, w=w, logits=out["logits"], teacher_logits=out["teacher_logits"])
-                return out["scalars"][0]
-            self._graph = g
-            self.kernels_per_replay = int(L.lib().hpfg_launch_count() - n0)   # kernel nodes of the captured step
-        self._graph.replay()
-        self.replayed_kernels += self.kernels_per_replay
-        self.last = dict(scalars=self._graph_out["scalars"], lr=lr, w=w, logits=self._graph_out["logits"],
-                         teacher_logits=self._graph_out["teacher_logits"])
-        return self._graph_out["scalars"][0]
+        dyn = self._dyn_scalars(self.ema_decay)
+        out = self._graph_replay([x, labels], dyn, [self.model, self.ema_model], self._step_body_dv)
+        self.last = dict(scalars=out["scalars"], lr=dyn[0], w=dyn[3], logits=out["logits"], teacher_logits=out["teacher_logits"])
+        return out["scalars"][0]
 
-    def _step_body_dv(self, x, labels):
+    def _step_body_dv(self, ins, dyn_f, dyn_o):
         """The step with every per-iteration scalar read from the device block (captured once, replayed)."""
+        x, labels = ins
         n_l = labels.shape[0]
         dev = x.device
         main, side = torch.cuda.current_stream(dev), self._side_stream(dev)
@@ -320,16 +372,16 @@ class MeanTeacherStep(_StepBase):
         with torch.cuda.stream(side):
             tplan = self.ema_model._acquire_plan(x, need_grad=False)
             t_out = self.ema_model._run_forward(tplan, x, save=False, out=self._persistent("t_out", shape, dev),
-                                                offset_dev=self._dyn_o[1:2])
+                                                offset_dev=dyn_o[1:2])
         plan = self.model._acquire_plan(x, need_grad=True)
-        out = self.model._run_forward(plan, x, save=True, out=self._persistent("s_out", shape, dev), offset_dev=self._dyn_o[0:1])
+        out = self.model._run_forward(plan, x, save=True, out=self._persistent("s_out", shape, dev), offset_dev=dyn_o[0:1])
         main.wait_stream(side)
-        r = ssl_loss_raw(L.LOSS_MT, out, t_out[n_l:], labels, n_l, cons_weight_dev=self._dyn_f[3:4])
+        r = ssl_loss_raw(L.LOSS_MT, out, t_out[n_l:], labels, n_l, cons_weight_dev=dyn_f[3:4])
         self._backward(self.model, plan, r["dstudent"], self.grads)
         n = self.model.flat_params.numel()
         L.check(L.lib().hpfg_sgd_momentum_ema_dv(L.ptr(self.model.flat_params), L.ptr(self.grads), L.ptr(self.mom),
                                                  L.ptr(self.ema_model.flat_params), n, self.momentum, self.weight_decay,
-                                                 1.0 / self.world, 0, L.ptr(self._dyn_f), L.stream_ptr(dev)),
+                                                 1.0 / self.world, 0, L.ptr(dyn_f), L.stream_ptr(dev)),
                 "hpfg_sgd_momentum_ema_dv")
         return dict(scalars=r["scalars"], logits=out, teacher_logits=t_out)
 
@@ -345,9 +397,12 @@ class CPSStep(_StepBase):
         model2.ensure_flat()
         self.g1, self.g2 = torch.zeros_like(model1.flat_params), torch.zeros_like(model2.flat_params)
         self.b1, self.b2 = torch.zeros_like(model1.flat_params), torch.zeros_like(model2.flat_params)
+        self._check_buffers()
+        self._broadcast_from_rank0()
 
     def step(self, x, labels):
         self.cur_itrs += 1
+        self._check_buffers()
         if self._use_graph():
             dyn = self._dyn_scalars()
             out = self._graph_replay([x, labels], dyn, [self.m1, self.m2], self._body_dv)
@@ -408,20 +463,26 @@ class UAMTStep(_StepBase):
         ema_model.ensure_flat()
         self.grads = torch.zeros_like(model.flat_params)
         self.mom = torch.zeros_like(model.flat_params)
+        self._check_buffers()
+        self._broadcast_from_rank0()
 
     @staticmethod
     def make_noise(like):
         return torch.clamp(torch.randn_like(like) * 0.1, -0.2, 0.2)      # 2019_07...:130,141
 
-    def step(self, x, labels, noise=None, mc_noise=None):
-        """noise [n_u,...] / mc_noise [T//2, 2*n_u, ...]: the clamped perturbations; drawn here if None."""
+    def step(self, x, labels, noise=None, mc_noise=None, teacher_masks=None):
+        """noise [n_u,...] / mc_noise [T//2, 2*n_u, ...]: the clamped perturbations; drawn here if None.
+        teacher_masks (parity harness only, eager path): 1 + T//2 dropout keep-mask sets, one per teacher forward in call
+        order (the consistency forward on n_u slices, then the T//2 Monte-Carlo forwards on 2*n_u slices) -- every
+        stochastic teacher pass draws its own masks, as nn.Dropout does in the reference (2019_07...:134-143)."""
         self.cur_itrs += 1
+        self._check_buffers()
         n_l = labels.shape[0]
         x_u = x[n_l:]
         n_u = x_u.shape[0]
         if noise is None:
             noise = self.make_noise(x_u)
-        if self._use_graph():
+        if self._use_graph() and teacher_masks is None:
             if mc_noise is None:
                 mc_noise = torch.clamp(torch.randn((self.T // 2, 2 * n_u) + tuple(x_u.shape[1:]), device=x.device,
                                                    dtype=x.dtype) * 0.1, -0.2, 0.2)
@@ -442,9 +503,21 @@ class UAMTStep(_StepBase):
         main = torch.cuda.current_stream(x.device)
         side = main if getattr(self, "serialize", False) else self._side_stream(x.device)
         side.wait_stream(main)
+        if teacher_masks is not None:
+            assert len(teacher_masks) == 1 + self.T // 2, "one mask set per teacher forward"
+            dev_sets = []                  # uploaded on the main stream before the fork; kept alive until the next step
+            for ms in teacher_masks:
+                self.ema_model.set_dropout_masks(ms)
+                dev_sets.append(self.ema_model._dropout_masks)
+            self._mask_keepalive = dev_sets
+            side.wait_stream(main)
         with torch.cuda.stream(side):
+            if teacher_masks is not None:
+                self.ema_model._dropout_masks = dev_sets[0]
             _, t_out = self._forward(self.ema_model, x_t, False, out=self._persistent("t_out", (n_u, ncls, hh, ww), x.device))
             for i in range(self.T // 2):
+                if teacher_masks is not None:
+                    self.ema_model._dropout_masks = dev_sets[1 + i]
                 self._forward(self.ema_model, x_mc[i], False, out=mc[2 * n_u * i:2 * n_u * (i + 1)])
         plan, out = self._forward(self.model, x, True, out=self._persistent("s_out", (x.shape[0], ncls, hh, ww), x.device))
         main.wait_stream(side)
@@ -499,6 +572,8 @@ class ICTStep(_StepBase):
         ema_model.ensure_flat()
         self.grads = torch.zeros_like(model.flat_params)
         self.mom = torch.zeros_like(model.flat_params)
+        self._check_buffers()
+        self._broadcast_from_rank0()
 
     def draw_mix_factors(self, n_mixed):
         """np.random.beta(alpha, alpha, size=(n_u//2,1,1,1)) (2022_02...:112-113): host RNG, as in the reference."""
@@ -508,6 +583,7 @@ class ICTStep(_StepBase):
     def step(self, x, labels, mix_factors=None):
         """x: [n_l+n_u, C, H, W] (labeled first, n_u even); mix_factors: [n_u//2] floats (drawn here if None)."""
         self.cur_itrs += 1
+        self._check_buffers()
         n_l = labels.shape[0]
         n_u = x.shape[0] - n_l
         assert n_u % 2 == 0, "ICT needs an even unlabeled batch"

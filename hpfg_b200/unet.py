@@ -31,10 +31,12 @@ def _conv_block(cin, cout, p):
 class _Plan:
     """One C-side plan (workspace + saved activations) for a given batch shape."""
 
-    def __init__(self, n, in_ch, n_cls, h, w, precision):
+    def __init__(self, n, in_ch, n_cls, h, w, precision, bwd_fusion=None):
         self.handle = ctypes.c_void_p()
         L.check(L.lib().hpfg_unet_plan_create(n, in_ch, n_cls, h, w, precision, ctypes.byref(self.handle)),
                 "hpfg_unet_plan_create")
+        if bwd_fusion is not None:
+            L.check(L.lib().hpfg_unet_plan_set_bwd_fusion(self.handle, int(bool(bwd_fusion))), "hpfg_unet_plan_set_bwd_fusion")
         self.busy = False           # holds activations of a forward whose backward has not run yet
 
     def __del__(self):
@@ -46,12 +48,28 @@ class _Plan:
             pass
 
 
+class _PlanLease:
+    """Marks a plan busy (it holds the activations of a forward whose backward has not run) until backward runs OR the
+    autograd node is dropped without one (outputs only inspected, exception, graph freed): no plan is leaked."""
+
+    def __init__(self, plan):
+        self.plan = plan
+        plan.busy = True
+
+    def release(self):
+        if self.plan is not None:
+            self.plan.busy = False
+            self.plan = None
+
+    __del__ = release
+
+
 class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, module, *params):
         plan = module._acquire_plan(x, need_grad=True)
         logits = module._run_forward(plan, x, save=True)
-        plan.busy = True
+        ctx.lease = _PlanLease(plan)
         ctx.module, ctx.plan = module, plan
         ctx.x = x        # the first layer's weight gradient re-reads the input: keep it alive until backward
         return logits
@@ -62,7 +80,7 @@ class _UNetFunction(torch.autograd.Function):
         grads = torch.empty_like(m.flat_params)        # fresh buffer: param.grad views must not alias a reused one
         L.check(L.lib().hpfg_unet_backward(plan.handle, L.ptr(m.flat_params), L.ptr(dlogits.contiguous().float()),
                                            L.ptr(grads), 0, L.stream_ptr(grads.device)), "hpfg_unet_backward")
-        plan.busy = False
+        ctx.lease.release()
         m.last_flat_grad = grads
         views = tuple(grads[o:o + n].view(s) for o, n, s in m._layout)
         return (None, None) + views
@@ -82,7 +100,7 @@ class _UNetPlusFunction(torch.autograd.Function):
         plan = module._acquire_plan(x, need_grad=True)
         logits = module._run_forward(plan, x, save=True)
         feat = _bottleneck(plan, x)
-        plan.busy = True
+        ctx.lease = _PlanLease(plan)
         ctx.module, ctx.plan = module, plan
         ctx.x = x
         return logits, feat
@@ -97,7 +115,7 @@ class _UNetPlusFunction(torch.autograd.Function):
         L.check(L.lib().hpfg_unet_backward_ex(plan.handle, L.ptr(m.flat_params), L.ptr(dlogits.contiguous().float()),
                                               L.ptr(dfeat), L.ptr(grads), 0, L.stream_ptr(grads.device)),
                 "hpfg_unet_backward_ex")
-        plan.busy = False
+        ctx.lease.release()
         m.last_flat_grad = grads
         views = tuple(grads[o:o + n].view(s) for o, n, s in m._layout)
         return (None, None) + views
@@ -130,6 +148,7 @@ class UNet(nn.Module):
         self._dropout_masks = None
         self._no_dropout = False
         self._philox_offset = 0
+        self.bwd_fusion = None          # None: library default; True / False: backward schedule of new plans (hpfg_unet_plan_set_bwd_fusion)
         self.last_flat_grad = None
         self._flatten()
 
@@ -253,7 +272,7 @@ class UNet(nn.Module):
                 return pl
         n, c, h, w = x.shape
         prec = {"fp32": L.PREC_FP32, "bf16": L.PREC_BF16}[self.precision]
-        pl = _Plan(n, c, self.num_classes, h, w, prec)
+        pl = _Plan(n, c, self.num_classes, h, w, prec, getattr(self, "bwd_fusion", None))
         pool.append(pl)
         return pl
 

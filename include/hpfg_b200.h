@@ -73,6 +73,11 @@ int hpfg_unet_plan_create(int batch, int in_channels, int num_classes, int heigh
                           hpfg_unet_plan_t *plan_out);
 int hpfg_unet_plan_destroy(hpfg_unet_plan_t plan);
 int64_t hpfg_unet_plan_workspace_bytes(hpfg_unet_plan_t plan);
+/* bf16 plans: select the backward schedule.  0 (default; env HPFG_BWD_FUSE=1 flips the default): BatchNorm backward as streaming
+ * kernels (two passes + finalize) that materialise the raw gradient; 1: folded into the tensor-core kernels -- the producing
+ * data-gradient epilogue stores g = dact*leaky'*dropout' with the two BatchNorm sums, the consuming dgrad / wgrad loaders build
+ * draw = scale*g + kb*raw + kd on the fly.  Same results to bf16 rounding; measured slower on B200 (profiles/README.md). */
+int hpfg_unet_plan_set_bwd_fusion(hpfg_unet_plan_t plan, int enabled);
 
 /* UNet.forward.  x: fp32 NCHW [batch,in_channels,H,W]; logits: fp32 NCHW [batch,num_classes,H,W].
  * training != 0: BatchNorm uses batch statistics and updates bn_running / bn_counters (+1 each), dropout is
@@ -140,6 +145,27 @@ int hpfg_wgrad_tc_debug(int batch, int height, int width, int cin, int cout, int
                         const void *dy_bf16_nhwc, const float *scale, const float *shift, float *dw_oihw, float *dbias,
                         void *stream);
 
+/* Layer-isolated hooks for the BatchNorm-backward fusions (bf16 plans).
+ * hpfg_dgrad_tc_fused_debug: din = conv_transpose(draw, w) with
+ *   raw_in  != NULL: draw = sc*g_in + kb*raw_in + kd built in the loader (g_in / raw_in bf16 NHWC [N,H,W,cout], constants float[cout]),
+ *                    else draw = g_in;
+ *   raw_out != NULL: the output is turned into g = din * leaky'(raw_out*gs_scale + gs_shift) * keep/(1-p) in the epilogue
+ *                    (raw_out bf16 NHWC [N,H,W,cin]; gs_keep_mask_nchw uint8 [N,cin,H,W] or NULL) and stats_out (float[2*cin]) receives
+ *                    sum g | sum g*raw_out per channel.
+ * hpfg_wgrad_tc_fused_debug: dw = sum_pixels act(x)[pixel+tap] * draw[pixel] with draw = sc*g + kb*raw + kd built inside the kernel.
+ * hpfg_glue_debug: one bf16 glue kernel on caller tensors; op 0 pool_act, 1 upcat, 2 bn_bwd (out_f32 = dgamma|dbeta), 3 skip_pool_bwd,
+ *   4 up_bwd, 5 skip_pool_bwd fused with BatchNorm-backward pass 0 (out = g, out_f32 = dgamma|dbeta|kb|kd); shapes in csrc/glue.cu. */
+int hpfg_dgrad_tc_fused_debug(int batch, int height, int width, int cin, int cout, int ksize, const void *g_in, const void *raw_in,
+                              const float *sc, const float *kb, const float *kd, const float *w_oihw, const void *raw_out,
+                              const float *gs_scale, const float *gs_shift, const uint8_t *gs_keep_mask_nchw, float gs_p_drop,
+                              void *out_bf16_nhwc, float *stats_out, void *stream);
+int hpfg_wgrad_tc_fused_debug(int batch, int height, int width, int cin, int cout, int ksize, const void *x_bf16_nhwc,
+                              const void *g_bf16_nhwc, const void *raw_bf16_nhwc, const float *sc, const float *kb, const float *kd,
+                              const float *scale, const float *shift, float *dw_oihw, float *dbias, void *stream);
+int hpfg_glue_debug(int op, int batch, int height, int width, int channels, const void *a, const void *b, const void *c,
+                    const float *scale, const float *shift, const float *mean, const float *invstd, const uint8_t *keep_mask_nchw,
+                    float p_drop, void *out_bf16, float *out_f32, void *stream);
+
 /* Layer micro-benchmark: average milliseconds of `iters` back-to-back launches of one tensor-core convolution
  * (op 0 fprop incl. fused loader and BN-stat epilogue, 1 dgrad, 2 wgrad) on internally allocated buffers. */
 int hpfg_conv_tc_bench(int op, int batch, int height, int width, int cin, int cout, int ksize, int iters,
@@ -198,6 +224,13 @@ int hpfg_s4cv_loss(const float *logits1, const float *logits2, const float *teac
  * wins, for a whole batch of eval-mode logits in one launch.  Either output may be NULL. */
 int hpfg_argmax_labels(const float *logits, int n, int num_classes, int height, int width, int64_t *labels_i64,
                        uint8_t *labels_u8, void *stream);
+
+/* softmax_mse_loss (utils/loss/diceloss.py:64-81): the UNREDUCED map (softmax(input) - softmax(target))^2 over dim 1
+ * (sigmoid != 0: element-wise sigmoids instead), all tensors fp32 NCHW [n,C,H,W].  grad_out == NULL: out = the map;
+ * grad_out != NULL: out = d(sum(grad_out * map)) / d input_logits (the target carries no gradient, as in the trainers,
+ * where it is the no_grad teacher output: 2019_07...:134-143,148). */
+int hpfg_softmax_mse(const float *input_logits, const float *target_logits, const float *grad_out, int n, int num_classes,
+                     int height, int width, int sigmoid, float *out, void *stream);
 
 /* hpfg_ssl_loss_dv with the UAMT threshold (2019_07...:150, it ramps with the iteration count) read from device memory too. */
 int hpfg_ssl_loss_dv2(int mode, const float *student, const float *other, const float *mc_logits, int mc_passes,

@@ -44,9 +44,10 @@ def dice(probs, target, n_classes):
     return loss / n_classes
 
 
-def run(dev, steps, warm, amp, h=H, w=W, n_l=N_L, n_u=N_U):
+def run(dev, steps, warm, amp, h=H, w=W, n_l=N_L, n_u=N_U, in_ch=1, n_cls=C):
     torch.manual_seed(0)
-    model = hb.UNet(1, C).to(dev)
+    C = n_cls
+    model = hb.UNet(in_ch, n_cls).to(dev)
     ema = copy.deepcopy(model)
     for p in ema.parameters():
         p.requires_grad = False
@@ -55,7 +56,7 @@ def run(dev, steps, warm, amp, h=H, w=W, n_l=N_L, n_u=N_U):
         model, ema = model.to(memory_format=torch.channels_last), ema.to(memory_format=torch.channels_last)
     opt = torch.optim.SGD(model.parameters(), lr=0.01, momentum=0.9, weight_decay=1e-4)
     g = torch.Generator().manual_seed(1)
-    x = torch.rand(n_l + n_u, 1, h, w, generator=g).to(dev)
+    x = torch.rand(n_l + n_u, in_ch, h, w, generator=g).to(dev)
     y = torch.randint(0, C, (n_l, h, w), generator=g).to(dev)
     if amp:
         x = x.contiguous(memory_format=torch.channels_last)
@@ -106,6 +107,6 @@ if __name__ == "__main__":
     for amp in (False, True):
         ms, loss = run(dev, steps, 3, amp, **kw)
         n = (kw.get("n_l", N_L) + kw.get("n_u", N_U))
-        print("torch eager %-28s %8.3f ms/step  %8.0f images/s  (loss %.4f; cudnn.benchmark off, conv TF32 %s)"
-              % ("autocast bf16 + channels_last" if amp else "fp32", ms, n / ms * 1e3, loss,
+        print("torch eager %-28s %8.3f ms/step  %8.0f images/s  (loss %.4f; cudnn.benchmark %s, conv TF32 %s)"
+              % ("autocast bf16 + channels_last" if amp else "fp32", ms, n / ms * 1e3, loss, torch.backends.cudnn.benchmark,
                  torch.backends.cudnn.allow_tf32), flush=True)

@@ -35,6 +35,16 @@ if __name__ == "__main__":
                 os.environ["HPFG_TC_DBG"] = "0"
                 print("(%s) op=%d  dbg:us  %s" % (shape, op, "  ".join(row)), flush=True)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "fused":
+        # BatchNorm-backward fusions: dgrad plain / two-source loader / GSTAT epilogue / both, wgrad plain / two-source dY
+        n = int(sys.argv[2]) if len(sys.argv) > 2 else 32
+        print("batch %d; us per launch" % n)
+        print("%-22s %9s %9s %9s %9s %9s %9s" % ("layer (cin,cout,k,res)", "dgrad", "dg+2src", "dg+gstat", "dg+both", "wgrad", "wg+2src"))
+        for cin, cout, ks, res in LAYERS:
+            ops = (1, 3, 4, 5, 2, 6) if ks == 3 else (1, 1, 4, 4, 2, 2)
+            t = [1e3 * run(op, n, cin, cout, ks, res) for op in ops]
+            print("%-22s %9.1f %9.1f %9.1f %9.1f %9.1f %9.1f" % ((str((cin, cout, ks, res)),) + tuple(t)), flush=True)
+        sys.exit(0)
     if len(sys.argv) > 2:
         n, op, cin, cout, ks, res, iters = [int(v) for v in sys.argv[1:8]]
         print("%.2f us" % (1e3 * run(op, n, cin, cout, ks, res, iters)))

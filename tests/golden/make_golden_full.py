@@ -4,7 +4,7 @@ config 3 (CPS 8+24), config 4 (UAMT 12+12, T=8, a separate dropout mask set for 
 (ISIC-shape 3ch / 2 classes 12+12).  Only fingerprints are stored (strided samples + fp64 sums, a few hundred KB per
 config); inputs, weights, dropout masks and noise are regenerated from seeds by tests/golden/common.py on both sides.
 
-    python tests/golden/make_golden_full.py            # all configs (~3 min on 8 cores, ~12 GB of RAM)
+    python tests/golden/make_golden_full.py            # all configs (~15 min on 8 cores, ~25 GB of RAM: fp32 pass + fp64 pass)
     python tests/golden/make_golden_full.py mt_cfg1    # one config
 
 The step bodies are literal transcriptions of 2017_03_NIPS_Mean-Teacher_ACDC.py:89-113, 2021_06_CVPR_CPS_ACDC.py:90-120
@@ -38,11 +38,20 @@ ARGS = dict(lr=0.01, momentum=0.9, weight_decay=1e-4, total_itrs=30000, ema_deca
             consistency_rampup=200.0)
 
 
+DTYPE = torch.float32        # the second pass of every config runs in fp64: the reference's own fp32 rounding noise is measured
+
+
 def ref_model(st, in_ch, n_cls):
     m = ref.UNet(in_channels=in_ch, num_classes=n_cls)
     m.load_state_dict(st)
+    m = m.to(DTYPE)
     m.train()
     return m
+
+
+def batch_of(*a, **k):
+    x_l, x_u, y = make_batch(*a, **k)
+    return x_l.to(DTYPE), x_u.to(DTYPE), y
 
 
 class MaskFeed:
@@ -107,7 +116,7 @@ def mean_teacher(c):
     recs, cur_itrs = [], 0
     for it in range(c["steps"]):
         cur_itrs += 1
-        label_img, unlabel_img, target_label = make_batch(n_l, n_u, in_ch, n_cls, h, w, seed + 100 * cur_itrs)
+        label_img, unlabel_img, target_label = batch_of(n_l, n_u, in_ch, n_cls, h, w, seed + 100 * cur_itrs)
         fs.masks = make_masks(n_l + n_u, h, w, seed + 100 * cur_itrs + 1)
         ft.masks = make_masks(n_l + n_u, h, w, seed + 100 * cur_itrs + 2)
         label_bs = label_img.shape[0]
@@ -152,7 +161,7 @@ def cps(c):
     recs, cur_itrs = [], 0
     for it in range(c["steps"]):
         cur_itrs += 1
-        label_img, unlabel_img, target_label = make_batch(n_l, n_u, in_ch, n_cls, h, w, seed + 100 * cur_itrs)
+        label_img, unlabel_img, target_label = batch_of(n_l, n_u, in_ch, n_cls, h, w, seed + 100 * cur_itrs)
         f1.masks = make_masks(n_l + n_u, h, w, seed + 100 * cur_itrs + 1)
         f2.masks = make_masks(n_l + n_u, h, w, seed + 100 * cur_itrs + 2)
         label_bs = label_img.shape[0]
@@ -203,8 +212,8 @@ def uamt(c):
     recs, cur_itrs = [], 0
     for it in range(c["steps"]):
         cur_itrs += 1
-        img_labeled, unlabeled_volume_batch, target_label = make_batch(n_l, n_u, in_ch, n_cls, h, w, seed + 100 * cur_itrs)
-        noise0, mc_noise = make_uamt_noise(n_u, in_ch, h, w, c["T"], seed + 100 * cur_itrs + 3)
+        img_labeled, unlabeled_volume_batch, target_label = batch_of(n_l, n_u, in_ch, n_cls, h, w, seed + 100 * cur_itrs)
+        noise0, mc_noise = [t.to(DTYPE) for t in make_uamt_noise(n_u, in_ch, h, w, c["T"], seed + 100 * cur_itrs + 3)]
         fs.masks = make_masks(n_l + n_u, h, w, seed + 100 * cur_itrs + 1)
         label_bs = img_labeled.shape[0]
         volume_batch = torch.cat([img_labeled, unlabeled_volume_batch], dim=0)
@@ -219,7 +228,7 @@ def uamt(c):
         _, _, w_, h_ = unlabeled_volume_batch.shape
         volume_batch_r = unlabeled_volume_batch.repeat(2, 1, 1, 1)
         stride = volume_batch_r.shape[0] // 2
-        preds = torch.zeros([stride * T, args.num_classes, w_, h_])
+        preds = torch.zeros([stride * T, args.num_classes, w_, h_], dtype=DTYPE)
         for i in range(T // 2):
             ema_inputs = volume_batch_r + mc_noise[i]
             ft.masks = make_masks(2 * n_u, h, w, seed + 100 * cur_itrs + 11 + i)
@@ -263,6 +272,19 @@ if __name__ == "__main__":
     for tag in want:
         c = FULL_CONFIGS[tag]
         print("full_%s: %s" % (tag, c), flush=True)
-        out = {"cfg": c, "steps": RUNNERS[c["kind"]](c), "torch": torch.__version__}
+        DTYPE = torch.float32
+        steps = RUNNERS[c["kind"]](c)
+        # fp64 pass of the same iterations: the gradients / loss the fp32 reference is itself an approximation of.  At these
+        # sizes the reference's fp32 gradients differ from the fp64 ones by 1e-3 .. 7e-3 (rel-L2 per parameter: sums over 1.2 M
+        # pixels behind 18 train-mode BatchNorms cancel heavily), so an fp32 implementation is judged against the fp64 values
+        # with the reference's own fp32 error as the yardstick (tests/test_gpu_full_size.py).
+        DTYPE = torch.float64
+        print("  fp64 pass", flush=True)
+        steps64 = RUNNERS[c["kind"]](c)
+        for r32, r64 in zip(steps, steps64):
+            for k in list(r64):
+                if k.startswith("grads") or k == "loss":
+                    r32[k + "64"] = r64[k]
+        out = {"cfg": c, "steps": steps, "torch": torch.__version__}
         torch.save(out, os.path.join(HERE, "full_%s.pt" % tag))
         print("  -> %.0f KB" % (os.path.getsize(os.path.join(HERE, "full_%s.pt" % tag)) / 1024), flush=True)

@@ -53,12 +53,22 @@ def test_unet_forward_backward_vs_reference_golden(tag, precision):
         if atol:
             assert p.grad.abs().max().item() < (1e-4 if precision == "fp32" else 2e-3), n
             continue
-        rt = tol_grad
         if precision == "bf16" and not n.startswith("decoder.out_conv"):
-            # end-to-end bf16 error compounds through the backward chain (torch's own bf16 autocast shows the same,
-            # SURVEY 7.2 item 5); the layer-isolated 1e-2 bar is checked in test_gpu_conv_layers.py
-            rt = 0.7
-        check_summary(p.grad, s, rtol=rt, atol=1e-7, what=n)
+            # End-to-end bf16 gradients of a random-init network on random labels are ill-conditioned (the reference's own fp32
+            # gradients are only good to ~5e-3 against fp64, torch's bf16 autocast to ~0.5: tests/test_gpu_full_size.py measures
+            # both and asserts this path against those yardsticks).  Every kernel of the chain is pinned at 1e-2 in isolation
+            # (test_gpu_conv_layers.py, test_gpu_glue_layers.py); here only the aggregate is bounded.
+            worst = max(worst, rel_l2(p.grad.flatten()[::s.get("stride", 1)] if "sample" in s else p.grad, s.get("sample", s.get("full"))))
+            continue
+        check_summary(p.grad, s, rtol=tol_grad, atol=1e-7, what=n)
+    if precision == "bf16":
+        import os
+        try:
+            with open(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out", "full_size_report.txt"), "a") as f:
+                f.write("small golden %s bf16: worst per-tensor gradient rel-l2 %.3e\n" % (tag, worst))
+        except OSError:
+            pass
+        assert worst < 0.6, worst
     for k, v in g["buffers"].items():
         got = m.state_dict()[k].cpu()
         if "tracked" in k:
@@ -312,30 +322,3 @@ def test_cps_and_uamt_steps_vs_oracle(precision):
         if f32:
             assert rel_l2(ustep.last["mc_logits"], r["mc_logits"]) < 1e-5
             assert ustep.last["scalars"][6].item() == r["mask"].sum().item()
-
-
-def test_full_size_bf16_vs_fp32_plan():
-    """BASELINE-size property check (224x224, wide-tile tensor-core kernels in the full network): the bf16 tensor-core plan
-    against the fp32 CUDA-core check path of this library (itself pinned to the oracle above), same weights / masks /
-    batch: loss within 1e-3, logits and flat gradient within the compounded-bf16 bound of SURVEY 7.2(5)."""
-    in_ch, n_cls, n_l, n_u, h, w = 1, 4, 2, 6, 224, 224
-    st = make_state(in_ch, n_cls, 91)
-    x_l, x_u, y = make_batch(n_l, n_u, in_ch, n_cls, h, w, 92)
-    x = torch.cat([x_l, x_u]).to(DEV)
-    res = {}
-    for prec in ("fp32", "bf16"):
-        m = _model(st, in_ch, n_cls, prec)
-        m.set_dropout_enabled(False)
-        m.train()
-        logits = m(x)
-        loss = hb.Med_Sup_Loss(n_cls)(logits[:n_l], y.to(DEV))
-        loss.backward()
-        res[prec] = (logits.detach().float().cpu(), loss.item(), m.last_flat_grad.detach().float().cpu())
-        del m
-        torch.cuda.empty_cache()
-    lf, ll, gf = res["fp32"]
-    lb, lbl, gb = res["bf16"]
-    assert abs(ll - lbl) / abs(ll) < 1e-3
-    assert rel_l2(lb, lf) < 5e-2
-    assert rel_l2(gb, gf) < 0.5
-    assert (lb.argmax(1) == lf.argmax(1)).float().mean().item() > 0.97
