@@ -29,6 +29,7 @@ SIGNATURES = {
     "hpfg_unet_plan_destroy": (c_int, [c_vp]),
     "hpfg_unet_plan_workspace_bytes": (c_i64, [c_vp]),
     "hpfg_unet_plan_set_bwd_fusion": (c_int, [c_vp, c_int]),
+    "hpfg_unet_plan_set_forward_ctas": (c_int, [c_vp, c_int]),
     "hpfg_unet_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u64, c_u64,
                                   ctypes.POINTER(c_vp), c_vp]),
     "hpfg_unet_forward_dv": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u64, c_vp,

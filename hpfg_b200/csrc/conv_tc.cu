@@ -97,6 +97,7 @@ static int launch_ks(int ks, int KC, int BN, int mt, int xf, int epi, const CUte
 }
 
 static long long *g_tc_trace = nullptr;
+static int g_tc_fwd_cap = 0;   // > 0: persistent-CTA budget of the forward convolutions of the plan being run (hpfg_unet_plan_set_forward_ctas)
 static int g_tc_kind = 0;   // 0 forward conv, 1 data gradient (set by the entry points around tc_run: single host thread per plan)
 static int g_tc_dbg = 0;   // bottleneck-isolation switches, set only by the micro-benchmark entry (never by the product path)
 
@@ -131,6 +132,7 @@ static int tc_run(int ks, int N, int H, int W, int cin_v, int cout_v, const void
     P.dbg = g_tc_dbg;
     P.trace = g_tc_trace;
     P.max_ctas = tc_cta_cap(g_tc_kind);
+    if (g_tc_kind == 0 && g_tc_fwd_cap > 0) P.max_ctas = std::min(P.max_ctas, g_tc_fwd_cap);
     if (P_out) *P_out = std::min(P.m_tiles * P.n_blocks, P.max_ctas);
     int xfm = xf.scale ? (xf.drop.bits ? 2 : 1) : 0;
     if (two) {          // BatchNorm backward in the loader: draw = sc*g + kb*raw + kd
@@ -158,6 +160,7 @@ int tc_run_bench(int op, int ks, int N, int H, int W, int cin, int cout, const v
     }
     (void)w;
     { const char *e = getenv("HPFG_TC_DBG"); g_tc_dbg = e ? atoi(e) : 0; }
+    g_tc_fwd_cap = 0;
     const int cin_v = op ? cout : cin, cout_v = op ? cin : cout;
     LoadXform xf{};
     xf.scale = scale; xf.shift = shift; xf.drop.bits = nullptr; xf.drop.inv_keep = 1.f;
@@ -249,6 +252,7 @@ int tc_pack_all(hpfg_unet_plan *p, const float *params, cudaStream_t s, bool nee
 
 int tc_fprop(hpfg_unet_plan *p, int conv, const void *in, void *out, LoadXform xf, float *stats, int *P, bool *done,
              cudaStream_t s) {
+    g_tc_fwd_cap = p->fwd_ctas & ~1;
     auto *st = reinterpret_cast<TcPlanState *>(p->tc);
     const ConvLayer &cv = p->d.convs[conv];
     *done = false;
@@ -260,6 +264,7 @@ int tc_fprop(hpfg_unet_plan *p, int conv, const void *in, void *out, LoadXform x
 
 int tc_fprop_1x1(hpfg_unet_plan *p, int conv, const void *in, void *out, LoadXform xf, const float *bias, bool *done,
                  cudaStream_t s) {
+    g_tc_fwd_cap = p->fwd_ctas & ~1;
     auto *st = reinterpret_cast<TcPlanState *>(p->tc);
     const ConvLayer &cv = p->d.convs[conv];
     *done = false;
@@ -270,6 +275,7 @@ int tc_fprop_1x1(hpfg_unet_plan *p, int conv, const void *in, void *out, LoadXfo
 }
 
 int tc_fprop_logits(hpfg_unet_plan *p, int conv, const void *in, LoadXform xf, const float *bias, float *logits_nchw, cudaStream_t s) {
+    g_tc_fwd_cap = p->fwd_ctas & ~1;
     auto *st = reinterpret_cast<TcPlanState *>(p->tc);
     const ConvLayer &cv = p->d.convs[conv];
     return tc_run(cv.ks, p->N, cv.H, cv.W, cv.cin, pad16(cv.cout), in, nullptr, st->packed + st->f_off[conv], bias, xf, nullptr, nullptr, s,
@@ -320,6 +326,7 @@ extern "C" int hpfg_conv_tc_debug(int op, int N, int H, int W, int cin, int cout
                                   const float *w_oihw, const float *bias, const float *scale, const float *shift,
                                   void *out_bf16_nhwc, float *stats_out, void *stream) {
     HPFG_REQUIRE(op == 0 || op == 1, "hpfg_conv_tc_debug: op must be 0 (fprop) or 1 (dgrad)");
+    g_tc_fwd_cap = 0;
     HPFG_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && (ks == 1 || ks == 3), "hpfg_conv_tc_debug: unsupported shape");
     cudaStream_t s = (cudaStream_t)stream;
     const int cin_v = op ? cout : cin, cout_v = op ? cin : cout;
@@ -361,6 +368,7 @@ extern "C" int hpfg_dgrad_tc_fused_debug(int N, int H, int W, int cin, int cout,
                                          void *out_bf16_nhwc, float *stats_out, void *stream) {
     HPFG_REQUIRE(cin % 16 == 0 && cout % 16 == 0 && (ks == 1 || ks == 3), "hpfg_dgrad_tc_fused_debug: unsupported shape");
     HPFG_REQUIRE(g_in && w_oihw && out_bf16_nhwc, "hpfg_dgrad_tc_fused_debug: null argument");
+    g_tc_fwd_cap = 0;
     cudaStream_t s = (cudaStream_t)stream;
     PackTable T{};
     T.n = 1;

@@ -23,9 +23,12 @@
 
 namespace hpfg {
 
-constexpr int kXfWarps = 8;                // loader-transform warps (warps 4-11)
-constexpr int kXfThreads = kXfWarps * 32;
-constexpr int kTcThreads = 128 + kXfThreads + 128;   // + warps 0-3 (TMA, MMA, TMEM alloc, idle) + 4 epilogue warps
+// 16 warps: 0-3 TMA producer / MMA issuer / TMEM allocator / idle, then the loader-transform warps, then the epilogue warps.
+// Narrow layers (BN <= 32) are transform-heavy (612-pixel halo tiles): 8 transform + 4 epilogue warps.  Wide layers (BN >= 64)
+// have small halo tiles but a 64..128-column epilogue with BatchNorm statistics that was the pipeline bottleneck with four
+// warps (per-role trace: 5.5 k cycles per 128 x 128 tile): 4 transform + 8 epilogue warps, two per TMEM lane quarter, each
+// taking half of the columns.
+constexpr int kTcThreads = 512;
 constexpr int kMaxStages = 12;
 constexpr int kSmemBudget = 216 * 1024;
 
@@ -60,6 +63,8 @@ struct TcCfg {
     static constexpr int SMEM_BYTES = RESB_BYTES + STAGES * STAGE_BYTES + FIXED_BYTES + 1024 /*alignment slack*/;
     static constexpr int ACC_COLS = MT * BN;                       // accumulator columns per TMEM buffer
     static constexpr int NACC = (4 * ACC_COLS <= 512) ? 4 : 2;      // accumulator buffers: MMA runs up to NACC-1 stages ahead of the epilogue
+    static constexpr int XFW = BN >= 64 ? 4 : 8;                    // loader-transform warps
+    static constexpr int EPW = 12 - XFW;                            // epilogue warps (EPW / 4 per TMEM lane quarter)
     static constexpr int TMEM_COLS = (NACC * ACC_COLS <= 32) ? 32 : (NACC * ACC_COLS <= 64) ? 64 : (NACC * ACC_COLS <= 128) ? 128 : (NACC * ACC_COLS <= 256) ? 256 : 512;
     static_assert(STAGES >= 2, "need at least a double buffer");
     static_assert(NACC * ACC_COLS <= 512, "accumulators exceed TMEM");
@@ -232,12 +237,12 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
     if (threadIdx.x == 0) {
         for (int s = 0; s < C::STAGES; ++s) {
             ptx::mbar_init(bar_full + 8 * s, 1);
-            ptx::mbar_init(bar_xf + 8 * s, kXfWarps);
+            ptx::mbar_init(bar_xf + 8 * s, C::XFW);
             ptx::mbar_init(bar_empty + 8 * s, 1);
         }
         for (int a = 0; a < C::NACC; ++a) {
             ptx::mbar_init(bar_tfull + 8 * a, 1);
-            ptx::mbar_init(bar_tempty + 8 * a, 4);
+            ptx::mbar_init(bar_tempty + 8 * a, C::EPW);
         }
         ptx::fence_barrier_init();
         ptx::prefetch_tensormap(&tmA);
@@ -304,12 +309,13 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         // ================================================================= MMA issuer (separate function: own register allocation)
         tc_mma_role<KS, KC, BN, RES, MT, XF>(bar_full, bar_xf, bar_empty, bar_tfull, bar_tempty, stage_u32, ptx::smem_u32(res_b),
                                              tmem_base, n_work, P.k_chunks, P.dbg, P.trace);
-    } else if (warp >= 4 && warp < 4 + kXfWarps) {
+    } else if (warp >= 4 && warp < 4 + C::XFW) {
         // ================================================================= loader-transform warps (in place)
         if (XF > 0) {
             // warp -> one 8-channel chunk (scale/shift live in registers), lanes -> 32 consecutive halo pixels
             // (512 contiguous bytes: conflict-free 128-bit shared accesses)
-            constexpr int G = kXfWarps / C::NCH, STEP = 32 * G, ITERS = (C::NPIX + STEP - 1) / STEP;
+            constexpr int G = C::XFW / C::NCH, STEP = 32 * G, ITERS = (C::NPIX + STEP - 1) / STEP;
+            static_assert(G >= 1, "more channel chunks per stage than transform warps");
             const int xw = warp - 4, c = xw % C::NCH, p0 = (xw / C::NCH) * 32 + lane;
             // halo coordinates of this thread's pixels are the same for every tile: (row << 8) | col
             int hrc[ITERS];
@@ -391,20 +397,23 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                 ti.next(P.tiles_h, P.tiles_w);
             }
         }
-    } else if (warp >= 4 + kXfWarps) {
+    } else if (warp >= 4 + C::XFW) {
         // ================================================================= epilogue warps
         const int q = warp & 3;                      // TMEM lane quarter this warp may read
         const int m = q * 32 + lane;                 // output pixel within the tile
         const int mr = m / kTW, mc = m % kTW;
-        const int et = threadIdx.x - (128 + kXfThreads);
+        const int et = threadIdx.x - (128 + C::XFW * 32);
+        const int half = (warp - (4 + C::XFW)) >> 2;     // EPW == 8: which half of the n-block's channels this warp owns
         constexpr int NG = BN / 16;
+        constexpr int NGW = NG / (C::EPW / 4);           // 16-channel groups per tile handled by one warp
+        constexpr int CW = NGW * 16;                     // channels per warp
         // Per-channel sums (train-mode BatchNorm statistics: sum x | sum x^2; GSTAT: sum g | sum g*raw).
         // BN <= 32: lane-private running sums over ALL pixels this lane ever sees (one FADD + one FFMA per value), reduced
         // across lanes once per CTA.  BN >= 64: per-tile shuffle butterfly into one running value per 16-column group
         // (register budget; a shared-memory transpose of the 32 x 16 block measured SLOWER: 7.1 k vs 5.5 k cycles per
         // 128 x 128 tile, profiles/README.md).  Either way: one partial row per CTA, fixed summation order.
-        constexpr bool LANE_STATS = BN <= 32;
-        constexpr int NRUN = LANE_STATS ? BN : NG;
+        constexpr bool LANE_STATS = CW <= 32;
+        constexpr int NRUN = LANE_STATS ? CW : NGW;
         float run1[NRUN], run2[NRUN];
 #pragma unroll
         for (int i = 0; i < NRUN; ++i) run1[i] = run2[i] = 0.f;
@@ -462,8 +471,8 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
         };
         // groups of one work item: grp -> (UMMA tile j = grp / NG, channel group gi = grp % NG); batches of GB groups share one
         // tcgen05.wait::ld (register budget: GB * 16 accumulator registers + the running sums)
-        constexpr int TG = MT * NG;
-        constexpr int GB0 = LANE_STATS ? (BN == 16 ? (GSTAT ? 2 : 4) : (GSTAT ? 1 : 2)) : (GSTAT ? 2 : 4);
+        constexpr int TG = MT * NGW;
+        constexpr int GB0 = LANE_STATS ? (CW == 16 ? (GSTAT ? 2 : 4) : (GSTAT ? 1 : 2)) : (GSTAT ? 2 : 4);
         constexpr int GB = GB0 < TG ? GB0 : TG;
         TileIter ti;
         ti.init(mt0, mstep, P.tiles_h, P.tiles_w);
@@ -479,7 +488,7 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                 if constexpr (GSTAT) {
 #pragma unroll
                     for (int t = 0; t < GB; ++t) {
-                        const int grp = b0 + t, j = grp / NG, c0 = (grp % NG) * 16;
+                        const int grp = b0 + t, j = grp / NGW, c0 = (half * NGW + grp % NGW) * 16;
                         const bool valid = gh < P.H && gw0 + j * kTW < P.W;
                         const size_t e = (pix0 + j * kTW) * P.Cout + nb * BN + c0;
                         rw[t][0] = rw[t][1] = make_uint4(0u, 0u, 0u, 0u);
@@ -501,14 +510,15 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             for (int b0 = 0; b0 < TG; b0 += GB) {
                 uint32_t r[GB][16];
 #pragma unroll
-                for (int t = 0; t < GB; ++t) ptx::tmem_ld16(taddr + (b0 + t) * 16, r[t]);      // column of group grp = j*BN + gi*16 = grp*16
+                for (int t = 0; t < GB; ++t)
+                    ptx::tmem_ld16(taddr + ((b0 + t) / NGW) * BN + (half * NGW + (b0 + t) % NGW) * 16, r[t]);   // tile j, channel group gi
                 if (b0 > 0) load_raw(b0);
                 ptx::tmem_ld_wait();
 #pragma unroll
                 for (int t = 0; t < GB; ++t) {
                     constexpr int dummy = 0;
                     (void)dummy;
-                    const int grp = b0 + t, j = grp / NG, gi = grp % NG;
+                    const int grp = b0 + t, j = grp / NGW, gl = grp % NGW, gi = half * NGW + gl;
                     const int gw = gw0 + j * kTW;
                     const bool valid = gh < P.H && gw < P.W;
                     float v[16], b2[16];
@@ -518,10 +528,10 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
                     if (want_stats) {
                         if constexpr (LANE_STATS) {
 #pragma unroll
-                            for (int i = 0; i < 16; ++i) { run1[gi * 16 + i] += v[i]; run2[gi * 16 + i] += b2[i]; }
+                            for (int i = 0; i < 16; ++i) { run1[gl * 16 + i] += v[i]; run2[gl * 16 + i] += b2[i]; }
                         } else {
-                            run1[gi] += butterfly16(v, lane);
-                            run2[gi] += butterfly16(b2, lane);
+                            run1[gl] += butterfly16(v, lane);
+                            run2[gl] += butterfly16(b2, lane);
                         }
                     }
                     if (valid && !no_store) store16(v, pix0 + j * kTW, ti.n_img, gh, gw, gi * 16);
@@ -533,27 +543,31 @@ __global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_con
             if (q == 0) HPFG_TRACE(4, it);
             ti.next(P.tiles_h, P.tiles_w);
         }
-        if (!NCHW && P.stats) {    // once per CTA: combine lanes and the four epilogue warps, write this CTA's partial row
+        if (!NCHW && P.stats) {    // once per CTA: combine lanes and the epilogue warps, write this CTA's partial row
+            float *mine = s_part + (warp - (4 + C::XFW)) * 2 * CW;          // [EPW warps][sum(CW) | second sum(CW)]
 #pragma unroll
-            for (int gidx = 0; gidx < NG; ++gidx) {
+            for (int gl = 0; gl < NGW; ++gl) {
+                float c1, c2;
                 if constexpr (LANE_STATS) {
-                    const float c1 = butterfly16(run1 + gidx * 16, lane), c2 = butterfly16(run2 + gidx * 16, lane);
-                    if ((lane & 1) == 0) {
-                        s_part[q * 2 * BN + gidx * 16 + col16(lane)] = c1;
-                        s_part[q * 2 * BN + BN + gidx * 16 + col16(lane)] = c2;
-                    }
-                } else if ((lane & 1) == 0) {
-                    s_part[q * 2 * BN + gidx * 16 + col16(lane)] = run1[gidx];
-                    s_part[q * 2 * BN + BN + gidx * 16 + col16(lane)] = run2[gidx];
+                    c1 = butterfly16(run1 + gl * 16, lane);
+                    c2 = butterfly16(run2 + gl * 16, lane);
+                } else {
+                    c1 = run1[gl];
+                    c2 = run2[gl];
+                }
+                if ((lane & 1) == 0) {
+                    mine[gl * 16 + col16(lane)] = c1;
+                    mine[CW + gl * 16 + col16(lane)] = c2;
                 }
             }
-            ptx::named_bar_sync(1, 128);
-            for (int i = et; i < 2 * P.Cout; i += 128) {
+            ptx::named_bar_sync(1, C::EPW * 32);
+            for (int i = et; i < 2 * P.Cout; i += C::EPW * 32) {
                 const int which = i / P.Cout, c = i % P.Cout, n = c - nb * BN;
                 float sum = 0.f;
-                if (n >= 0 && n < BN && n_work > 0)
-                    sum = s_part[which * BN + n] + s_part[2 * BN + which * BN + n] + s_part[4 * BN + which * BN + n] +
-                          s_part[6 * BN + which * BN + n];
+                if (n >= 0 && n < BN && n_work > 0) {
+                    const float *src = s_part + (n / CW) * 4 * 2 * CW + which * CW + n % CW;     // the four lane quarters of that half
+                    sum = src[0] + src[2 * CW] + src[4 * CW] + src[6 * CW];
+                }
                 P.stats[(size_t)blockIdx.x * 2 * P.Cout + i] = sum;
             }
         }

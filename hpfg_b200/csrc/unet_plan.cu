@@ -722,6 +722,12 @@ extern "C" int hpfg_unet_plan_destroy(hpfg_unet_plan_t p) {
 
 extern "C" int64_t hpfg_unet_plan_workspace_bytes(hpfg_unet_plan_t p) { return p ? p->ws_bytes : 0; }
 
+extern "C" int hpfg_unet_plan_set_forward_ctas(hpfg_unet_plan_t p, int ctas) {
+    HPFG_REQUIRE(p && ctas >= 0 && ctas <= kNumSMs, "hpfg_unet_plan_set_forward_ctas: 0 (no cap) .. 148");
+    p->fwd_ctas = ctas;
+    return HPFG_OK;
+}
+
 extern "C" int hpfg_unet_plan_set_bwd_fusion(hpfg_unet_plan_t p, int enabled) {
     HPFG_REQUIRE(p, "hpfg_unet_plan_set_bwd_fusion: null plan");
     HPFG_REQUIRE(!enabled || p->precision == HPFG_PREC_BF16, "hpfg_unet_plan_set_bwd_fusion: only bf16 plans have the fused backward");

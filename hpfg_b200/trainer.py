@@ -230,8 +230,18 @@ class _StepBase:
             for t in (m.flat_params, m.bn_running, m.bn_counters):
                 dist.broadcast(t, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
 
+    # Two forwards enqueued on two streams share the machine: half of the SMs each (hpfg_unet_plan_set_forward_ctas)
+    SHARED_FORWARD_CTAS = 74
+
+    def _set_forward_share(self, plan, shared):
+        want = self.SHARED_FORWARD_CTAS if shared else 0
+        if getattr(plan, "fwd_ctas", 0) != want:
+            L.check(L.lib().hpfg_unet_plan_set_forward_ctas(plan.handle, want), "hpfg_unet_plan_set_forward_ctas")
+            plan.fwd_ctas = want
+
     def _forward_dv(self, model, x, save, out, offset_dev):
         plan = model._acquire_plan(x, need_grad=save)
+        self._set_forward_share(plan, True)              # (graph replays always run the forwards on two streams)
         return plan, model._run_forward(plan, x, save=save, out=out, offset_dev=offset_dev)
 
     def _sgd_dv(self, model, grads, buf, dyn_f, ema_model=None):
@@ -266,6 +276,7 @@ class _StepBase:
     def _forward(self, model, x, save, out=None):
         model.ensure_flat()
         plan = model._acquire_plan(x, need_grad=save)
+        self._set_forward_share(plan, not getattr(self, "serialize", False))
         logits = model._run_forward(plan, x, save=save, out=out)
         return plan, logits
 
@@ -371,9 +382,11 @@ class MeanTeacherStep(_StepBase):
         side.wait_stream(main)
         with torch.cuda.stream(side):
             tplan = self.ema_model._acquire_plan(x, need_grad=False)
+            self._set_forward_share(tplan, True)
             t_out = self.ema_model._run_forward(tplan, x, save=False, out=self._persistent("t_out", shape, dev),
                                                 offset_dev=dyn_o[1:2])
         plan = self.model._acquire_plan(x, need_grad=True)
+        self._set_forward_share(plan, True)
         out = self.model._run_forward(plan, x, save=True, out=self._persistent("s_out", shape, dev), offset_dev=dyn_o[0:1])
         main.wait_stream(side)
         r = ssl_loss_raw(L.LOSS_MT, out, t_out[n_l:], labels, n_l, cons_weight_dev=dyn_f[3:4])

@@ -67,7 +67,7 @@ class _PlanLease:
 class _UNetFunction(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, module, *params):
-        plan = module._acquire_plan(x, need_grad=True)
+        plan = module._own_machine(module._acquire_plan(x, need_grad=True))
         logits = module._run_forward(plan, x, save=True)
         ctx.lease = _PlanLease(plan)
         ctx.module, ctx.plan = module, plan
@@ -97,7 +97,7 @@ class _UNetPlusFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, module, *params):
-        plan = module._acquire_plan(x, need_grad=True)
+        plan = module._own_machine(module._acquire_plan(x, need_grad=True))
         logits = module._run_forward(plan, x, save=True)
         feat = _bottleneck(plan, x)
         ctx.lease = _PlanLease(plan)
@@ -276,6 +276,14 @@ class UNet(nn.Module):
         pool.append(pl)
         return pl
 
+    @staticmethod
+    def _own_machine(plan):
+        """A plan last used by a step driver that shares the SMs between two concurrent forwards goes back to the full grid."""
+        if getattr(plan, "fwd_ctas", 0):
+            L.check(L.lib().hpfg_unet_plan_set_forward_ctas(plan.handle, 0), "hpfg_unet_plan_set_forward_ctas")
+            plan.fwd_ctas = 0
+        return plan
+
     def _run_forward(self, plan, x, save, out=None, offset_dev=None):
         dev = x.device
         shape = (x.shape[0], self.num_classes, x.shape[2], x.shape[3])
@@ -311,7 +319,7 @@ class UNet(nn.Module):
         need_grad = torch.is_grad_enabled() and self.training and any(p.requires_grad for p in self._flat_params_list)
         if need_grad:
             return _UNetFunction.apply(x, self, *self._flat_params_list)
-        return self._run_forward(self._acquire_plan(x, False), x, save=False)
+        return self._run_forward(self._own_machine(self._acquire_plan(x, False)), x, save=False)
 
 
 class projection_conv(nn.Module):
@@ -359,7 +367,7 @@ class UNet_Plus(UNet):
         if need_grad:
             output, feature = _UNetPlusFunction.apply(x, self, *self._flat_params_list)
         else:
-            plan = self._acquire_plan(x, False)
+            plan = self._own_machine(self._acquire_plan(x, False))
             output = self._run_forward(plan, x, save=False)
             feature = _bottleneck(plan, x)
         high_feature = self.dense_projection_high(feature)

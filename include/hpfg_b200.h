@@ -73,6 +73,11 @@ int hpfg_unet_plan_create(int batch, int in_channels, int num_classes, int heigh
                           hpfg_unet_plan_t *plan_out);
 int hpfg_unet_plan_destroy(hpfg_unet_plan_t plan);
 int64_t hpfg_unet_plan_workspace_bytes(hpfg_unet_plan_t plan);
+/* Cap on the persistent CTAs of this plan's forward convolutions (0 = none: one CTA per SM on all 148 SMs).  A tensor-core
+ * convolution CTA owns a whole SM (~200 KB of shared memory, the full register file), so two forwards enqueued on two streams
+ * (student | teacher, the two CPS networks) take turns kernel by kernel; with 74 CTAs each they run side by side on disjoint SMs
+ * and the latency-bound deep layers overlap (measured +1.8 % Mean-Teacher step throughput, profiles/README.md). */
+int hpfg_unet_plan_set_forward_ctas(hpfg_unet_plan_t plan, int ctas);
 /* bf16 plans: select the backward schedule.  0 (default; env HPFG_BWD_FUSE=1 flips the default): BatchNorm backward as streaming
  * kernels (two passes + finalize) that materialise the raw gradient; 1: folded into the tensor-core kernels -- the producing
  * data-gradient epilogue stores g = dact*leaky'*dropout' with the two BatchNorm sums, the consuming dgrad / wgrad loaders build
