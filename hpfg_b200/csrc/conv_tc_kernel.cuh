@@ -30,7 +30,13 @@ namespace hpfg {
 // taking half of the columns.
 constexpr int kTcThreads = 512;
 constexpr int kMaxStages = 12;
-constexpr int kSmemBudget = 216 * 1024;
+#ifndef HPFG_TC_SMEM_KB
+#define HPFG_TC_SMEM_KB 216
+#endif
+#ifndef HPFG_TC_LB_THREADS
+#define HPFG_TC_LB_THREADS 512      // launch bound used for register allocation (640 -> at most 96 registers per thread)
+#endif
+constexpr int kSmemBudget = HPFG_TC_SMEM_KB * 1024;
 
 // Loader transforms (XF): 0 none; 1 BatchNorm affine + LeakyReLU of the producer; 2 = 1 + dropout keep bits;
 // 3 = BatchNorm BACKWARD of the layer this data gradient enters through: the operand is built from TWO staged tiles,
@@ -198,7 +204,7 @@ __device__ __forceinline__ void tc_mma_role(uint32_t bar_full, uint32_t bar_xf, 
 
 // warps: 0 TMA producer, 1 MMA issuer, 2 TMEM alloc, 3 idle, 4-11 transform (XF > 0 only), 12-15 epilogue.
 template <int KS, int KC, int BN, bool RES, int MT, int XF, int EPI>
-__global__ void __launch_bounds__(kTcThreads, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmR,
+__global__ void __launch_bounds__(HPFG_TC_LB_THREADS, 1) tc_conv_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmR,
                                                                 const TcConvParams P) {
     using C = TcCfg<KS, KC, BN, RES, MT, XF == 3>;
     constexpr bool NCHW = EPI == 1, GSTAT = EPI == 2;

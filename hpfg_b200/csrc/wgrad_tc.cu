@@ -18,6 +18,7 @@
 // each CTA keeps its accumulators in TMEM across all its tiles and writes one fp32 partial, and a fixed-order
 // reduction kernel sums the partials straight into the flat OIHW gradient (deterministic).
 #include <algorithm>
+#include <cstdlib>
 
 #include "conv_ref.cuh"
 #include "conv_tc.cuh"
@@ -27,7 +28,10 @@ namespace hpfg {
 
 constexpr int kWgXfThreads = 256;   // transform threads (warps 4-11): loader transform of X into shifted copies + bias-gradient sums
 constexpr int kWgThreads = 128 + kWgXfThreads + 128;   // warps 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 transform, 12-15 epilogue
-constexpr int kWgSmemBudget = 222 * 1024;
+#ifndef HPFG_WG_SMEM_KB
+#define HPFG_WG_SMEM_KB 222
+#endif
+constexpr int kWgSmemBudget = HPFG_WG_SMEM_KB * 1024;
 
 // MT: tile width multiplier (tile = 16 rows x 8*MT columns).  The TMA unit retires roughly one tensor load per ~500
 // cycles however small its box (tests/probes/tma_rate_probe.cu), so the 16-channel layers use wide tiles: two loads
@@ -73,7 +77,9 @@ struct WgParams {
     float inv_keep;
     float *scratch;                 // [S][KK*Cin*Cout + Cout] fp32 partials
     int N, H, W, Cin, Cout, tiles_h, tiles_w, m_tiles, ci_blocks, co_blocks, S;
+    long long *trace;               // optional (profiles/ only): CTA 0 records clock64 per role and tile, [role][32]
 };
+#define WG_TRACE(role, idx) do { if (P.trace && blockIdx.x == 0 && lane == 0 && (idx) < 32) P.trace[(role) * 32 + (idx)] = clock64(); } while (0)
 
 template <int KS, int NB, int COB, int MT, bool TWO>
 __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
@@ -133,6 +139,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[5 * 32 + 2] = clock64();
 
     if (warp == 0) {             // ==================================================== TMA producer (warp-uniform)
         TileIter ti;
@@ -142,6 +149,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         for (int it = 0; it < n_work; ++it) {
             const int h0 = ti.th * kTH, w0 = ti.tw * C::TWP;
             ptx::mbar_wait(bar_empty + 8 * stage, phase ^ 1, 11);
+            WG_TRACE(0, it);
             const uint32_t sb = smem_u32 + stage * C::STAGE_BYTES;
             if (ptx::elect_one()) {
                 ptx::mbar_expect_tx(bar_full + 8 * stage, C::D_OP * (TWO ? 2 : 1) + C::XR_OP);
@@ -166,6 +174,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         for (int it = 0; it < n_work; ++it) {
             ptx::mbar_wait(bar_xf + 8 * stage, phase, 14);         // transform warps arrive after the TMA data was consumed and the copies written
             ptx::tc_fence_after();
+            WG_TRACE(3, it);
             const uint32_t a_lo = a_lo0 + stage * (C::STAGE_BYTES >> 4), b_lo = b_lo0 + stage * (C::STAGE_BYTES >> 4);
             if (ptx::elect_one()) {
 #pragma unroll 2
@@ -182,6 +191,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
                 if (it == n_work - 1) ptx::umma_commit(bar_done);
             }
             __syncwarp();
+            WG_TRACE(4, it);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
         }
     } else if (warp >= 4 && warp < 4 + kWgXfThreads / 32) {
@@ -203,6 +213,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
             const int h0 = ti.th * kTH - C::PAD, w0 = ti.tw * C::TWP - C::PAD;
             const size_t img_px = (size_t)ti.n_img * P.H;
             ptx::mbar_wait(bar_full + 8 * stage, phase, 15);
+            if (warp == 4) WG_TRACE(1, it);
             const uint32_t sb = smem_u32 + stage * C::STAGE_BYTES;
             for (int p = xp0; p < C::NPIX_X; p += XPSTEP) {
                 const int hr = p / C::HW, hc = p % C::HW;
@@ -263,6 +274,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
             ptx::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive(bar_xf + 8 * stage);
+            if (warp == 4) WG_TRACE(2, it);
             if (++stage == C::STAGES) { stage = 0; phase ^= 1; }
             ti.next(P.tiles_h, P.tiles_w);
         }
@@ -275,6 +287,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
         if (n_work > 0) {
             ptx::mbar_wait(bar_done, 0, 16);
             ptx::tc_fence_after();
+            if (q == 0) WG_TRACE(5, 0);
             float *dst = P.scratch + (size_t)split * ((size_t)C::KK * P.Cin * P.Cout + P.Cout);
             if (want_bias) {       // accumulator row MROWS of D_0 = ones x dY = sum of dY over this CTA's pixels
                 const bool mine = C::UM == 128 ? (q * 32 + lane == C::MROWS) : (lane < 16 && q * 16 + lane == C::MROWS);
@@ -311,6 +324,7 @@ __global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_co
     }
     ptx::tc_fence_before();
     __syncthreads();
+    if (P.trace && blockIdx.x == 0 && threadIdx.x == 0) P.trace[5 * 32 + 1] = clock64();
     if (warp == 2) {
         ptx::tc_fence_after();
         ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
@@ -438,7 +452,27 @@ int tc_wgrad_run(int ks, int N, int H, int W, int Cin, int Cout, int cin_real, i
     P.scratch = scratch;
     P.N = N; P.H = H; P.W = W; P.Cin = Cin; P.Cout = Cout;
     P.tiles_h = (H + kTH - 1) / kTH; P.tiles_w = (W + kTW * MT - 1) / (kTW * MT);
+    static long long *trace_buf = nullptr;
+    const bool want_trace = getenv("HPFG_WG_TRACE") != nullptr;
+    if (want_trace && !trace_buf) cudaMalloc(&trace_buf, 6 * 32 * 8);
+    if (want_trace) cudaMemsetAsync(trace_buf, 0, 6 * 32 * 8, s);
+    P.trace = want_trace ? trace_buf : nullptr;
     HPFG_RETURN_IF(ks == 3 ? wg_dispatch<3>(NB, COB, MT, two, mx, md, mr, P, s) : wg_dispatch<1>(NB, COB, MT, two, mx, md, mr, P, s));
+    if (want_trace && getenv("HPFG_WG_TRACE_DUMP")) {
+        long long h[6 * 32];
+        cudaStreamSynchronize(s);
+        cudaMemcpy(h, trace_buf, sizeof(h), cudaMemcpyDeviceToHost);
+        const long long t0 = h[5 * 32 + 2];
+        const char *names[5] = {"tma:slot-free", "xf:tile-landed", "xf:done", "mma:operands-ready", "mma:issued"};
+        printf("wgrad trace (CTA 0, cycles since setup): NB=%d COB=%d MT=%d S=%d grid=%d; epilogue starts %lld, kernel ends %lld\n", NB, COB, MT, P.S,
+               P.ci_blocks * P.co_blocks * P.S, h[5 * 32] - t0, h[5 * 32 + 1] - t0);
+        for (int r = 0; r < 5; ++r) {
+            printf("%-20s", names[r]);
+            for (int i = 0; i < 12; ++i) printf(" %6lld", h[r * 32 + i] ? h[r * 32 + i] - t0 : -1);
+            printf("\n");
+        }
+        fflush(stdout);
+    }
     const int64_t per = (int64_t)ks * ks * Cin * Cout + Cout;
     const int blocks = (int)((per + 31) / 32);
     HPFG_CUDA_CHECK(launch_pdl(tc_wgrad_reduce_kernel, blocks, 256, 0, s, scratch, P.S, Cin, Cout, ks * ks, cin_real, cout_real, dw_oihw, dbias, accumulate));

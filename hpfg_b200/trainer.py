@@ -4,6 +4,8 @@
 * ``CPSStep``          -- 2021_06_CVPR_CPS_ACDC.py:90-120
 * ``UAMTStep``         -- 2019_07_MICCAI_Uncertainty_Aware_ACDC.py:120-170
 * ``ICTStep``          -- 2022_02_ISBI_ICT-MedSeg_ACDC.py:96-140
+* ``S4CVStep``         -- 2022_08_CVPR_S4CVNet_ACDC.py:108-167
+* ``HPFGStep``         -- main.py:128-207, the HPFG iteration itself
 
 Each ``step()`` enqueues: student forward (activations kept in the plan), teacher/peer forward(s), ONE fused
 loss launch pair (value + dlogits), backward into a persistent flat gradient buffer, (data parallel: NCCL
@@ -16,8 +18,8 @@ import math
 import torch
 
 from . import _lib as L
-from .losses import ssl_loss_raw, ict_loss_raw, ict_mix_inputs
-from .utils import sigmoid_rampup
+from .losses import ssl_loss_raw, ict_loss_raw, ict_mix_inputs, s4cv_loss_raw
+from .utils import sigmoid_rampup, linear_rampup
 
 
 def medical_lr(cur_itrs, base_lr, max_iterations):
@@ -656,3 +658,179 @@ class ICTStep(_StepBase):
         self._backward(self.model, plan, r["dstudent"], self.grads)
         self._sgd_dv(self.model, self.grads, self.mom, f, self.ema_model)
         return dict(scalars=r["scalars"], logits=out, teacher_logits=t_out)
+
+
+class S4CVStep(_StepBase):
+    """S4CVNet (2022_08_CVPR_S4CVNet_ACDC.py:108-167): two student networks trained with cross pseudo supervision (Dice only,
+    weight 7w) plus, from iteration ``mt_start`` on, Mean-Teacher MSE of both students against the EMA teacher of student 2,
+    which sees the noise-perturbed unlabeled slices.  w = consistency * linear_rampup(cur_itrs // 150, rampup) (:148-149).
+    One fused loss call (``hpfg_s4cv_loss``) produces the value and both logit gradients."""
+
+    def __init__(self, model1, model2, ema_model, *, ema_decay=0.99, mt_start=1000, **kw):
+        super().__init__(**kw)
+        self.m1, self.m2, self.ema_model, self.ema_decay, self.mt_start = model1, model2, ema_model, ema_decay, mt_start
+        self.in_channels, self.num_classes = model1.in_channels, model1.num_classes
+        model1.train()
+        model2.train()
+        for m in (model1, model2, ema_model):
+            m.ensure_flat()
+        self.g1, self.g2 = torch.zeros_like(model1.flat_params), torch.zeros_like(model2.flat_params)
+        self.b1, self.b2 = torch.zeros_like(model1.flat_params), torch.zeros_like(model2.flat_params)
+        self._check_buffers()
+        self._broadcast_from_rank0()
+
+    def _models(self):
+        return [self.m1, self.m2, self.ema_model]
+
+    def _consistency_weight(self):
+        return self.consistency * linear_rampup(self.cur_itrs // 150, self.consistency_rampup)
+
+    @staticmethod
+    def make_noise(like):
+        return torch.clamp(torch.randn_like(like) * 0.1, -0.2, 0.2)      # 2022_08...:111
+
+    def step(self, x, labels, noise=None):
+        """x: [n_l+n_u, C, H, W] (labeled first); labels: [n_l, H, W]; noise [n_u, ...]: drawn here if None."""
+        self.cur_itrs += 1
+        self._check_buffers()
+        n_l, dev = labels.shape[0], x.device
+        x_u = x[n_l:]
+        if noise is None:
+            noise = self.make_noise(x_u)
+        x_t = (x_u + noise).contiguous()
+        ncls, hh, ww = self.num_classes, x.shape[2], x.shape[3]
+        main = torch.cuda.current_stream(dev)
+        side = main if getattr(self, "serialize", False) else self._side_stream(dev)
+        shape = (x.shape[0], ncls, hh, ww)
+        side.wait_stream(main)
+        with torch.cuda.stream(side):               # student 2 and its teacher on the side stream, student 1 on the main stream
+            p2, o2 = self._forward(self.m2, x, True, out=self._persistent("o2", shape, dev))
+            _, t_out = self._forward(self.ema_model, x_t, False, out=self._persistent("t_out", (x_u.shape[0], ncls, hh, ww), dev))
+        p1, o1 = self._forward(self.m1, x, True, out=self._persistent("o1", shape, dev))
+        main.wait_stream(side)
+        w = self._consistency_weight()
+        mt_on = self.cur_itrs >= self.mt_start
+        r = s4cv_loss_raw(o1, o2, t_out if mt_on else None, labels, n_l, cps_weight=7.0 * w, mt_weight=w)
+        side.wait_stream(main)
+        alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)
+        with torch.cuda.stream(side):
+            self._backward(self.m2, p2, r["dother"], self.g2)
+            self._sgd(self.m2, self.g2, self.b2, self.ema_model, alpha)      # SGD of student 2 + EMA into its teacher, one pass
+        self._backward(self.m1, p1, r["dstudent"], self.g1)
+        lr = self._sgd(self.m1, self.g1, self.b1)
+        main.wait_stream(side)
+        self.last = dict(scalars=r["scalars"], lr=lr, w=w, logits1=o1, logits2=o2, teacher_logits=t_out)
+        return r["scalars"][0]
+
+
+class HPFGStep(_StepBase):
+    """The HPFG iteration of main.py:128-207 on three ``UNet_Plus`` networks (model1 sees the CutMix batch, model2 and the EMA
+    teacher the plain batch).  The U-Net bodies run on the library's kernels through ``UNet_Plus``'s autograd Function; the
+    projection necks and ``Dense_Loss`` are small torch modules, so the step goes through autograd once (``loss.backward()``)
+    and the optimiser side is fused: flat SGD over the 82 U-Net tensors of each student, one launch per neck tensor, the
+    backbone EMA model2 <- model1 (main.py:68-76) and the teacher EMA (utils/utils.py:82-86) as flat passes.
+
+    step(label_img, target_label, label_img1, target_label1, img_unlabel, cutmix_mask): the tensors main.py:128-150 builds
+    (label_img1 / target_label1: the second labeled draw, repeated to the unlabeled batch size here as at :139-140;
+    cutmix_mask [n_u,1,H,W] from BoxMaskGenerator)."""
+
+    def __init__(self, model1, model2, ema_model, *, ema_decay=0.99, mt_start=1000, temperature=0.7, **kw):
+        super().__init__(**kw)
+        from .losses import DiceLoss, Dense_Loss
+        self.m1, self.m2, self.ema_model, self.ema_decay, self.mt_start = model1, model2, ema_model, ema_decay, mt_start
+        self.in_channels, self.num_classes = model1.in_channels, model1.num_classes
+        model1.train()
+        model2.train()
+        for m in (model1, model2, ema_model):
+            m.ensure_flat()
+        for p in ema_model.parameters():
+            p.requires_grad = False
+        self.dice = DiceLoss(self.num_classes)
+        self.temperature = temperature
+        self._dense = None
+        self._DenseLoss = Dense_Loss
+        self.b1, self.b2 = torch.zeros_like(model1.flat_params), torch.zeros_like(model2.flat_params)
+        self._neck_mom = {}                         # id(parameter) -> momentum buffer of the neck tensors (outside the flat buffer)
+        self._check_buffers()
+        self._broadcast_from_rank0()
+
+    def _models(self):
+        return [self.m1, self.m2, self.ema_model]
+
+    def _state_tensors(self):
+        return [self.b1, self.b2]
+
+    def _check_buffers(self):
+        for model, buf in ((self.m1, self.b1), (self.m2, self.b2)):
+            if buf.device != model.flat_params.device or buf.numel() != model.flat_params.numel():
+                raise L.HpfgError("HPFGStep: momentum buffer no longer matches the model's flat parameters")
+
+    def _consistency_weight(self):
+        return self.consistency * linear_rampup(self.cur_itrs // 150, self.consistency_rampup)
+
+    def _sgd_model(self, model, buf, lr, first):
+        """torch.optim.SGD semantics over all parameters of a UNet_Plus: the flat U-Net buffer in one pass + the neck tensors."""
+        st = L.stream_ptr(model.flat_params.device)
+        lib = L.lib()
+        g = model.last_flat_grad
+        L.check(lib.hpfg_sgd_momentum(L.ptr(model.flat_params), L.ptr(g), L.ptr(buf), model.flat_params.numel(), lr, self.momentum,
+                                      self.weight_decay, 1.0 / self.world, first, st), "hpfg_sgd_momentum")
+        core = {id(q) for q in model._flat_params_list}
+        for p in model.parameters():
+            if id(p) in core or p.grad is None:
+                continue
+            mom = self._neck_mom.get(id(p))
+            if mom is None:
+                mom = self._neck_mom[id(p)] = torch.zeros_like(p.data)
+            L.check(lib.hpfg_sgd_momentum(L.ptr(p.data), L.ptr(p.grad.contiguous()), L.ptr(mom), p.numel(), lr, self.momentum,
+                                          self.weight_decay, 1.0 / self.world, first, st),
+                    "hpfg_sgd_momentum")
+
+    def step(self, label_img, target_label, label_img1, target_label1, img_unlabel, cutmix_mask, lr=None):
+        """lr: override of the Medical_LR value of this iteration (resuming with a fresh scheduler; parity harness)."""
+        import torch.nn.functional as F
+        from .utils import update_ema_variables, ema_update_flat
+        self.cur_itrs += 1
+        self._check_buffers()
+        m1, m2, ema = self.m1, self.m2, self.ema_model
+        label_bs, unlabel_bs = label_img.shape[0], img_unlabel.shape[0]
+        rep = int(unlabel_bs // label_bs)
+        label_img1 = label_img1.repeat(rep, 1, 1, 1).float()
+        target_label1 = target_label1.repeat(rep, 1, 1).long()
+        cutmix_mask = cutmix_mask.float()
+        batch_un_mix = label_img1 * (1.0 - cutmix_mask) + img_unlabel * cutmix_mask          # main.py:145
+        batch_mix = torch.cat([label_img, batch_un_mix], dim=0).float()
+        volume_batch = torch.cat([label_img, img_unlabel], dim=0).float()
+        if self._dense is None or self._dense.batch_size != label_bs + unlabel_bs:
+            self._dense = self._DenseLoss(label_bs + unlabel_bs, volume_batch.device, self.temperature)
+        for m in (m1, m2):
+            for p in m.parameters():
+                p.grad = None
+        outputs1, _, _ = m1(batch_mix)
+        outputs2, h1, h2 = m2(volume_batch)
+        with torch.no_grad():
+            ema_output, ema_h1, ema_h2 = ema(volume_batch)
+            ema_soft = torch.softmax(ema_output, dim=1)
+        soft1, soft2 = torch.softmax(outputs1, dim=1), torch.softmax(outputs2, dim=1)
+        tl = target_label.long()
+        loss_sup = 0.5 * (F.cross_entropy(outputs1[:label_bs], tl, ignore_index=255) + self.dice(soft1[:label_bs], tl.unsqueeze(1))) + \
+            0.5 * (F.cross_entropy(outputs2[:label_bs], tl, ignore_index=255) + self.dice(soft2[:label_bs], tl.unsqueeze(1)))
+        loss_contrast = self._dense(h1, ema_h1) + self._dense(h2, ema_h2)
+        cm = cutmix_mask.squeeze(1)
+        pseudo = torch.argmax(ema_soft[label_bs:], dim=1, keepdim=False)
+        pseudo = target_label1 * (1.0 - cm) + pseudo * cm                                        # main.py:172
+        pseudo_sup = self.dice(soft1[label_bs:], pseudo.unsqueeze(1))
+        w = self._consistency_weight()
+        cons2 = torch.mean((soft2[label_bs:] - ema_soft[label_bs:]) ** 2) if self.cur_itrs >= self.mt_start else 0.0
+        loss = loss_sup + 7 * w * pseudo_sup + w * cons2 + w * loss_contrast
+        loss.backward()
+        lr = medical_lr(self.cur_itrs, self.base_lr, self.total_itrs) if lr is None else lr
+        first = int(self.cur_itrs == 1)
+        self._sgd_model(m1, self.b1, lr, first)
+        self._sgd_model(m2, self.b2, lr, first)
+        alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)
+        ema_update_flat(m2.ensure_flat(), m1.ensure_flat(), alpha)          # update_ema_variables_backbone: encoder + decoder = the flat buffer
+        update_ema_variables(m2, ema, self.ema_decay, self.cur_itrs)
+        self.last = dict(loss=loss.detach(), loss_sup=loss_sup.detach(), contrast=loss_contrast.detach(), pseudo=pseudo_sup.detach(),
+                         lr=lr, w=w, outputs1=outputs1.detach(), outputs2=outputs2.detach(), ema_output=ema_output)
+        return loss.detach()

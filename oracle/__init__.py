@@ -17,4 +17,4 @@ from .unet_ref import (unet_param_spec, unet_buffer_spec, init_unet_state, unet_
 from .losses_ref import (dice_loss, med_sup_loss, softmax_mse, mt_consistency, cps_losses,
                          uamt_consistency, ce_loss, ict_losses, s4cv_losses, dense_loss, dense_contrastive)
 from .steps_ref import (update_ema, sigmoid_rampup, consistency_weight, medical_lr, SGDState,
-                        sgd_step, mt_step, cps_step, uamt_step, ema_alpha, ict_step)
+                        sgd_step, mt_step, cps_step, uamt_step, ema_alpha, ict_step, s4cv_step, linear_rampup)

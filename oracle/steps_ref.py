@@ -198,3 +198,36 @@ def ict_step(student, teacher, opt, x_l, x_u, y, cur_itrs, mix_factors, *, base_
         update_ema(student, teacher, ema_decay, cur_itrs, names)
     return dict(loss=float(loss.detach()), loss_sup=float(sup.detach()), loss_cons=float(cons.detach()), w=w, lr=lr,
                 logits=out.detach(), teacher_logits=t_out, grads=grads, mixed=mixed)
+
+
+def linear_rampup(current, rampup_length):
+    """utils/utils.py:89-95."""
+    if current >= rampup_length:
+        return 1.0
+    return current / rampup_length
+
+
+def s4cv_step(m1, m2, teacher, opt1, opt2, x_l, x_u, y, cur_itrs, noise, *, base_lr=0.01, max_iterations=30000, ema_decay=0.99,
+              consistency=0.1, consistency_rampup=200.0, mt_start=1000, masks1=None, masks2=None, teacher_masks=None):
+    """One S4CVNet iteration (2022_08_CVPR_S4CVNet_ACDC.py:108-167): two students on cat([labeled, unlabeled]), the EMA
+    teacher of student 2 on the noise-perturbed unlabeled slices (forward every iteration, :117-133; its output enters the
+    loss from iteration `mt_start` on, :143-149), loss of :124-156, two SGD steps, EMA of student 2 into the teacher (:166)."""
+    names, ncls = _names(m1)
+    lb = x_l.shape[0]
+    x = torch.cat([x_l, x_u], dim=0)
+    out1, l1 = _grad_forward(m1, names, x, masks1)
+    out2, l2 = _grad_forward(m2, names, x, masks2)
+    with torch.no_grad():
+        t_out = unet_forward(teacher, x_u + noise, True, teacher_masks)
+    w = consistency * linear_rampup(cur_itrs // 150, consistency_rampup)
+    from .losses_ref import s4cv_losses
+    loss, loss_sup, loss_semi, pl1, pl2 = s4cv_losses(out1, out2, t_out if cur_itrs >= mt_start else None, y, lb, ncls, 7 * w, w)
+    gs = torch.autograd.grad(loss, [l1[n] for n in names] + [l2[n] for n in names], allow_unused=True)
+    g1, g2 = dict(zip(names, gs[:len(names)])), dict(zip(names, gs[len(names):]))
+    lr = medical_lr(cur_itrs - 1, base_lr, max_iterations)
+    with torch.no_grad():
+        sgd_step(m1, g1, opt1, lr)
+        sgd_step(m2, g2, opt2, lr)
+        update_ema(m2, teacher, ema_decay, cur_itrs, names)
+    return dict(loss=float(loss.detach()), loss_sup=float(loss_sup.detach()), loss_semi=float(loss_semi.detach()), w=w, lr=lr,
+                logits1=out1.detach(), logits2=out2.detach(), teacher_logits=t_out, grads1=g1, grads2=g2)

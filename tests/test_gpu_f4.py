@@ -314,3 +314,84 @@ def test_hpfg_main_step_vs_reference_golden(precision):
             # tensors whose gradient is tiny)
             assert (d_got - d_ref).norm() <= 2e-2 * d_ref.norm() + 2e-7 * b.double().norm(), \
                 (nm, k, float((d_got - d_ref).norm() / d_ref.norm()))
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_hpfg_step_driver_vs_reference_golden(precision):
+    """``HPFGStep`` (the packaged driver of main.py:128-207: autograd through the three UNet_Plus networks, fused flat SGD for
+    the U-Net tensors + per-tensor SGD for the necks, flat backbone / teacher EMA passes) against the same reference fixture
+    as the transcription test above."""
+    import copy
+    from tests.golden.common import make_plus_state, make_hpfg_batch
+    g = load_golden("hpfg_step_acdc.pt")
+    c = g["cfg"]
+    f32 = precision == "fp32"
+    torch.backends.cudnn.allow_tf32 = False
+    in_ch, n_cls, n_l, n_u, h, w, seed = c["in_ch"], c["n_cls"], c["n_l"], c["n_u"], c["h"], c["w"], c["seed"]
+    before1, before2 = make_plus_state(in_ch, n_cls, seed), make_plus_state(in_ch, n_cls, seed + 20)
+    model1 = hb.UNet_Plus(in_ch, n_cls, precision=precision)
+    model1.load_state_dict(before1)
+    model1 = model1.to(DEV)
+    model2 = hb.UNet_Plus(in_ch, n_cls, precision=precision)
+    model2.load_state_dict(before2)
+    model2 = model2.to(DEV)
+    ema_model = copy.deepcopy(model2)
+    step = hb.HPFGStep(model1, model2, ema_model, weight_decay=0.0005)
+    model1.set_dropout_masks(make_masks(n_l + n_u, h, w, seed + 31))
+    model2.set_dropout_masks(make_masks(n_l + n_u, h, w, seed + 32))
+    ema_model.set_dropout_masks(make_masks(n_l + n_u, h, w, seed + 33))
+    step.cur_itrs = c["cur_itrs"] - 1
+    batch = [t.to(DEV) for t in make_hpfg_batch(n_l, n_u, in_ch, n_cls, h, w, seed + 40)]
+    loss = step.step(*batch, lr=0.01 * (1.0 + 1.0 / 30000) ** 0.9)          # the fixture's fresh Medical_LR scheduler
+    sc = g["scalars"]
+    got = dict(loss=loss.item(), loss_sup=step.last["loss_sup"].item(), contrast=step.last["contrast"].item(),
+               pseudo=step.last["pseudo"].item())
+    for k, tol32, tol16 in (("loss", 1e-5, 2e-3), ("loss_sup", 1e-5, 2e-3), ("contrast", 1e-4, 3e-2), ("pseudo", 1e-5, 5e-3)):
+        assert abs(got[k] - sc[k]) / abs(sc[k]) < (tol32 if f32 else tol16), (k, got[k], sc[k])
+    tol = 1e-5 if f32 else 3e-2
+    check_summary(step.last["outputs1"], g["outputs1"], rtol=tol, what="outputs1")
+    check_summary(step.last["outputs2"], g["outputs2"], rtol=tol, what="outputs2")
+    assert model1._is_flat() and model2._is_flat() and ema_model._is_flat()
+    if f32:
+        for nm, m in (("model1", model1), ("model2", model2), ("ema_model", ema_model)):
+            sd = m.state_dict()
+            for k, summ in g["after"][nm].items():
+                check_summary(sd[k], summ, rtol=1e-4 if "running_" in k else 2e-5, atol=1e-6, what=nm + "." + k)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_s4cv_step_driver_vs_oracle(precision):
+    """``S4CVStep`` (2022_08_CVPR_S4CVNet_ACDC.py:108-167) against the oracle's restatement of the iteration: before and
+    after the Mean-Teacher terms switch on (mt_start), with dropout masks and the teacher's input noise supplied."""
+    import oracle
+    from tests.golden.common import make_state, make_batch
+    in_ch, n_cls, n_l, n_u, h, w = 1, 4, 2, 4, 32, 48
+    f32 = precision == "fp32"
+    st1, st2 = make_state(in_ch, n_cls, 131), make_state(in_ch, n_cls, 132)
+    m1, m2 = hb.UNet(in_ch, n_cls, precision=precision), hb.UNet(in_ch, n_cls, precision=precision)
+    m1.load_state_dict(st1)
+    m2.load_state_dict(st2)
+    m1, m2 = m1.to(DEV), m2.to(DEV)
+    import copy
+    te = copy.deepcopy(m2)
+    o1, o2 = {k: v.clone() for k, v in st1.items()}, {k: v.clone() for k, v in st2.items()}
+    ot = {k: v.clone() for k, v in st2.items()}
+    step = hb.S4CVStep(m1, m2, te, mt_start=2)
+    opt1, opt2 = oracle.SGDState(), oracle.SGDState()
+    gen = torch.Generator().manual_seed(9)
+    for it in (1, 2, 3):
+        x_l, x_u, y = make_batch(n_l, n_u, in_ch, n_cls, h, w, 140 + it)
+        noise = torch.clamp(torch.randn(x_u.shape, generator=gen) * 0.1, -0.2, 0.2)
+        k1, k2, kt = make_masks(n_l + n_u, h, w, 150 + it), make_masks(n_l + n_u, h, w, 160 + it), make_masks(n_u, h, w, 170 + it)
+        m1.set_dropout_masks(k1)
+        m2.set_dropout_masks(k2)
+        te.set_dropout_masks(kt)
+        loss = step.step(torch.cat([x_l, x_u]).to(DEV), y.to(DEV), noise.to(DEV))
+        r = oracle.s4cv_step(o1, o2, ot, opt1, opt2, x_l, x_u, y, it, noise, mt_start=2, masks1=k1, masks2=k2, teacher_masks=kt)
+        assert abs(loss.item() - r["loss"]) / r["loss"] < (2e-5 if f32 else 2e-2), (it, loss.item(), r["loss"])
+        if f32:
+            assert rel_l2(step.last["logits1"], r["logits1"]) < 1e-5 and rel_l2(step.last["teacher_logits"], r["teacher_logits"]) < 1e-5
+            for m, o in ((m1, o1), (m2, o2), (te, ot)):
+                sd = m.state_dict()
+                for k in ("decoder.out_conv.weight", "encoder.in_conv.conv_conv.0.weight", "encoder.down4.maxpool_conv.1.conv_conv.5.running_var"):
+                    assert torch.allclose(sd[k].cpu(), o[k], rtol=1e-4, atol=5e-6), (it, k)
