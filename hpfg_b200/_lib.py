@@ -30,6 +30,9 @@ SIGNATURES = {
     "hpfg_unet_plan_workspace_bytes": (c_i64, [c_vp]),
     "hpfg_unet_plan_set_bwd_fusion": (c_int, [c_vp, c_int]),
     "hpfg_unet_plan_set_forward_ctas": (c_int, [c_vp, c_int]),
+    "hpfg_unet_plan_set_sync_bn": (c_int, [c_vp, c_int]),
+    "hpfg_ssl_loss_set_global_sums": (c_int, [c_int]),
+    "hpfg_set_allreduce_hook": (c_int, [c_vp, c_vp, c_int]),
     "hpfg_unet_forward": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u64, c_u64,
                                   ctypes.POINTER(c_vp), c_vp]),
     "hpfg_unet_forward_dv": (c_int, [c_vp, c_vp, c_vp, c_vp, c_vp, c_vp, c_int, c_int, c_int, c_u64, c_vp,
@@ -116,3 +119,36 @@ def stream_ptr(device=None):
 def require_cuda(t, what):
     if not t.is_cuda:
         raise HpfgError("%s must be a CUDA tensor: hpfg_b200 has no CPU path (got device %s)" % (what, t.device))
+
+
+# ---- exact-global data-parallel mode: the library's sum-all-reduce hook, served by torch.distributed -------------------------
+ALLREDUCE_FN = ctypes.CFUNCTYPE(None, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p)
+_hook_keepalive = {}
+
+
+class _DevBuf:
+    """Zero-copy view of a raw device pointer for torch.as_tensor (CUDA array interface)."""
+
+    def __init__(self, ptr, count, is_double):
+        self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": "<f8" if is_double else "<f4", "data": (int(ptr), False),
+                                         "version": 2}
+
+
+def install_allreduce_hook(group=None):
+    """Register torch.distributed's all_reduce(SUM) over ``group`` as the library's hook (hpfg_set_allreduce_hook)."""
+    import torch.distributed as dist
+    world = dist.get_world_size(group)
+
+    def _hook(ctx, ptr, count, is_double, stream):
+        # Exact-global mode is a verification mode (one small collective per BatchNorm, eager launches): every collective is
+        # host-synchronised on both sides.  Stream-ordered hand-over between the library's programmatically-launched kernels
+        # and ProcessGroupNCCL's internal stream was measured unreliable on the legacy default stream (profiles/README.md).
+        dev = torch.cuda.current_device()
+        t = torch.as_tensor(_DevBuf(ptr, count, is_double), device=torch.device("cuda", dev))
+        torch.cuda.synchronize(dev)
+        dist.all_reduce(t, group=group)
+        torch.cuda.synchronize(dev)
+    cb = ALLREDUCE_FN(_hook)
+    _hook_keepalive["cb"] = cb
+    check(lib().hpfg_set_allreduce_hook(ctypes.cast(cb, ctypes.c_void_p), None, world), "hpfg_set_allreduce_hook")
+    return world

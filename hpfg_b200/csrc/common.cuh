@@ -115,6 +115,20 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
 }
 
+// Plain (fully stream-ordered) launch: used for the kernel that follows a host-enqueued all-reduce in exact-global mode -- a
+// programmatic dependent launch there may start on the trigger of the kernel BEFORE the collective's event wait.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_plain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = s;
+    cfg.attrs = nullptr;
+    cfg.numAttrs = 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+
 // ---- division by a runtime constant without the (very slow) 64-bit integer divide ------------------------------
 // q = (umulhi(n, m) + n) >> s, exact for n < 2^31 (all element counts here are checked against that on the host).
 struct FastDiv {
@@ -140,6 +154,13 @@ __device__ __forceinline__ void fast_divmod(uint32_t n, const FastDiv &f, uint32
 int tc_cta_cap(int kind);
 
 inline int ceil_div(int64_t a, int64_t b) { return (int)((a + b - 1) / b); }
+
+// ---- exact-global data-parallel mode (SURVEY 8e caveats 1-3): the library has no communicator of its own; the host registers a
+// sum-all-reduce hook (hpfg_set_allreduce_hook) that is called, in stream order, on the few small device buffers that carry
+// batch-wide sums: BatchNorm statistics (forward and backward) and the loss accumulators.
+int sync_world();
+int sync_allreduce(void *device_ptr, int64_t count, bool is_double, cudaStream_t s);   // HPFG_OK when no hook is registered and world == 1
+extern bool g_loss_global_sums;
 
 // ---- optional per-category device timing (bench.py's roofline leg): CUDA events around each host launcher ----
 enum ProfCat { PROF_CONV_TC = 0, PROF_CONV_CUDA = 1, PROF_WGRAD = 2, PROF_GLUE = 3, PROF_LOSS = 4, PROF_OPTIM = 5, PROF_PACK = 6, PROF_WGRAD_TC = 7, PROF_NCAT = 8 };

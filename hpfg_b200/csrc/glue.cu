@@ -84,10 +84,80 @@ __global__ void __launch_bounds__(256) bn_finalize_kernel(const float *__restric
     }
 }
 
+// ---- exact-global mode: partial rows -> fp64 sums[2C] (one launch), all-reduce of those sums over the ranks (host hook), then the
+// same finalisation from the summed values with the global element count.
+__global__ void __launch_bounds__(256) bn_sum_partials_kernel(const float *__restrict__ partials, int P, int C2, double *__restrict__ sums,
+                                                              double *__restrict__ copy) {
+    pdl_prologue();
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    if (warp >= C2) return;
+    double s = 0.0;
+    for (int p = lane; p < P; p += 32) s += (double)partials[(int64_t)p * C2 + warp];
+    s = warp_sum(s);
+    if (lane == 0) {
+        sums[warp] = s;
+        if (copy) copy[warp] = s;
+    }
+}
+
+__global__ void __launch_bounds__(256) bn_finalize_sums_kernel(const double *__restrict__ sums, int C, double inv_count, double unbias,
+                                                               const float *__restrict__ gamma, const float *__restrict__ beta,
+                                                               const float *__restrict__ conv_bias, float *running_mean,
+                                                               float *running_var, int64_t *counter, int training, BnState st) {
+    pdl_prologue();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double mean = sums[c] * inv_count;
+    double var = sums[C + c] * inv_count - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const double invstd = 1.0 / sqrt(var + (double)kBnEps);
+    st.scale[c] = (float)((double)gamma[c] * invstd);
+    st.shift[c] = (float)((double)beta[c] - mean * (double)gamma[c] * invstd);
+    st.mean[c] = (float)mean;
+    st.invstd[c] = (float)invstd;
+    if (training) {
+        const float b = conv_bias ? conv_bias[c] : 0.f;
+        running_mean[c] = (1.f - kBnMomentum) * running_mean[c] + kBnMomentum * ((float)mean + b);
+        running_var[c] = (1.f - kBnMomentum) * running_var[c] + kBnMomentum * (float)(var * unbias);
+        if (c == 0 && counter) *counter += 1;
+    }
+}
+
+// backward: c1 / c2 / kb / kd from the GLOBAL sums (sums_g), dgamma / dbeta from this rank's LOCAL sums (the gradient all-reduce adds
+// the ranks' contributions afterwards)
+__global__ void __launch_bounds__(256) bn_bwd_finalize_sums_kernel(const double *__restrict__ sums_l, const double *__restrict__ sums_g, int C,
+                                                                   double inv_count, BnState bn, float *dgamma, float *dbeta, int accumulate) {
+    pdl_prologue();
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    const double invstd = (double)bn.invstd[c], mean = (double)bn.mean[c];
+    const double sg = sums_g[c], qg = invstd * (sums_g[C + c] - mean * sg);
+    const double sl = sums_l[c], ql = invstd * (sums_l[C + c] - mean * sl);
+    bn.c1[c] = (float)(sg * inv_count);
+    bn.c2[c] = (float)(qg * inv_count);
+    const float sc = bn.scale[c];
+    const float kb = -sc * bn.c2[c] * bn.invstd[c];
+    bn.kb[c] = kb;
+    bn.kd[c] = -sc * bn.c1[c] - kb * bn.mean[c];
+    if (accumulate) { dgamma[c] += (float)ql; dbeta[c] += (float)sl; }
+    else { dgamma[c] = (float)ql; dbeta[c] = (float)sl; }
+}
+
 int bn_finalize(const float *partials, int P, int C, int64_t count, const float *gamma, const float *beta,
                 const float *conv_bias, float *running_mean, float *running_var, int64_t *counter, int training,
-                BnState st, cudaStream_t s) {
+                BnState st, cudaStream_t s, double *sync_sums) {
     ProfScope _prof(PROF_GLUE, s);
+    if (sync_sums && training) {
+        const int64_t gcount = count * sync_world();
+        const double unbias_g = gcount > 1 ? (double)gcount / (double)(gcount - 1) : 1.0;
+        HPFG_CUDA_CHECK(launch_plain(bn_sum_partials_kernel, ceil_div(2 * C * 32, 256), 256, 0, s, partials, P, 2 * C, sync_sums, (double *)nullptr));
+        HPFG_LAUNCH_CHECK();
+        HPFG_RETURN_IF(sync_allreduce(sync_sums, 2 * C, true, s));
+        HPFG_CUDA_CHECK(launch_plain(bn_finalize_sums_kernel, ceil_div(C, 256), 256, 0, s, (const double *)sync_sums, C, 1.0 / (double)gcount, unbias_g,
+                                   gamma, beta, conv_bias, running_mean, running_var, counter, training, st));
+        HPFG_LAUNCH_CHECK();
+        return HPFG_OK;
+    }
     const double unbias = count > 1 ? (double)count / (double)(count - 1) : 1.0;
     HPFG_CUDA_CHECK(launch_pdl(bn_finalize_kernel, ceil_div(C * 32, 256), 256, 0, s, partials, P, C, 1.0 / (double)count, unbias, gamma,
                                                              beta, conv_bias, running_mean, running_var, counter,
@@ -334,16 +404,26 @@ __global__ void __launch_bounds__(256) bn_bwd_finalize_kernel(const float *__res
 
 template <typename T>
 int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, DropSpec drop, float *partials,
-           int max_partials, float *dgamma, float *dbeta, int accumulate, cudaStream_t s) {
+           int max_partials, float *dgamma, float *dbeta, int accumulate, cudaStream_t s, double *sync_sums) {
     ProfScope _prof(PROF_GLUE, s);
     int P = (int)((M + 63) / 64);
     if (P > kNumSMs * 4) P = kNumSMs * 4;
     if (P > max_partials) P = max_partials;
     HPFG_CUDA_CHECK(launch_pdl(bn_bwd_kernel<T, 0>, P, 256, 0, s, dact, raw, draw, M, C, bn, drop, partials));
     HPFG_LAUNCH_CHECK();
-    HPFG_CUDA_CHECK(launch_pdl(bn_bwd_finalize_kernel, ceil_div(C * 32, 256), 256, 0, s, partials, P, C, 1.0 / (double)M, bn, dgamma, dbeta,
-                                                                 accumulate));
-    HPFG_LAUNCH_CHECK();
+    if (sync_sums) {     // exact-global mode: local sums -> copy -> all-reduce -> finalize from (local, global)
+        double *loc = sync_sums, *glob = sync_sums + 2 * 256;
+        HPFG_CUDA_CHECK(launch_plain(bn_sum_partials_kernel, ceil_div(2 * C * 32, 256), 256, 0, s, (const float *)partials, P, 2 * C, loc, glob));
+        HPFG_LAUNCH_CHECK();
+        HPFG_RETURN_IF(sync_allreduce(glob, 2 * C, true, s));
+        HPFG_CUDA_CHECK(launch_plain(bn_bwd_finalize_sums_kernel, ceil_div(C, 256), 256, 0, s, (const double *)loc, (const double *)glob, C,
+                                   1.0 / ((double)M * sync_world()), bn, dgamma, dbeta, accumulate));
+        HPFG_LAUNCH_CHECK();
+    } else {
+        HPFG_CUDA_CHECK(launch_pdl(bn_bwd_finalize_kernel, ceil_div(C * 32, 256), 256, 0, s, partials, P, C, 1.0 / (double)M, bn, dgamma, dbeta,
+                                   accumulate));
+        HPFG_LAUNCH_CHECK();
+    }
     int P2 = (int)((M + 63) / 64);
     if (P2 > kNumSMs * 8) P2 = kNumSMs * 8;
     HPFG_CUDA_CHECK(launch_pdl(bn_bwd_kernel<T, 1>, P2, 256, 0, s, dact, raw, draw, M, C, bn, drop, nullptr));
@@ -716,7 +796,7 @@ int add_nchw_f32_to_nhwc(T *dst, const float *src, int N, int H, int W, int C, c
     template int pool_act<T>(const T *, T *, int, int, int, int, BnState, cudaStream_t);                            \
     template int upcat<T>(const T *, BnState, const T *, T *, int, int, int, int, cudaStream_t);                    \
     template int bn_bwd<T>(const T *, const T *, T *, int64_t, int, BnState, DropSpec, float *, int, float *,       \
-                           float *, int, cudaStream_t);                                                             \
+                           float *, int, cudaStream_t, double *);                                                   \
     template int skip_pool_bwd<T>(const T *, const T *, const T *, BnState, T *, int, int, int, int, cudaStream_t); \
     template int skip_pool_bwd_gstat<T>(const T *, const T *, const T *, BnState, T *, int, int, int, int, float *, int, int *, cudaStream_t); \
     template int up_bwd<T>(const T *, T *, int, int, int, int, cudaStream_t);                                       \
@@ -759,7 +839,7 @@ extern "C" int hpfg_glue_debug(int op, int N, int H, int W, int C, const void *a
         case 1: rc = upcat<bf16>(A, st, B, O, N, H, W, C, s); break;                       // a = skip raw [N,2H,2W,C], b = low [N,H,W,C] -> cat [N,2H,2W,2C]
         case 2: {                                                                          // a = dact, b = raw [N,H,W,C] -> draw; out_f32 = dgamma | dbeta
             DropSpec ds{bits, bits ? 1.f / (1.f - p_drop) : 1.f};
-            rc = bn_bwd<bf16>(A, B, O, (int64_t)N * H * W, C, st, ds, partials, max_partials, out_f32, out_f32 + C, 0, s);
+            rc = bn_bwd<bf16>(A, B, O, (int64_t)N * H * W, C, st, ds, partials, max_partials, out_f32, out_f32 + C, 0, s, nullptr);
             break;
         }
         case 3: rc = skip_pool_bwd<bf16>(A, B, Cc, st, O, N, H, W, C, s); break;           // a = dcat [N,H,W,2C], b = dpooled [N,H/2,W/2,C], c = raw [N,H,W,C]

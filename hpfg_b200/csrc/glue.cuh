@@ -22,7 +22,7 @@ struct DropSpec {
 // stats partials: [P][2*C] floats (sum | sum of squares); finalize -> BnState (+ running stats when training)
 int bn_finalize(const float *partials, int P, int C, int64_t count, const float *gamma, const float *beta,
                 const float *conv_bias, float *running_mean, float *running_var, int64_t *counter, int training,
-                BnState st, cudaStream_t s);
+                BnState st, cudaStream_t s, double *sync_sums = nullptr);   // sync_sums (4*256 doubles): statistics over all ranks
 // eval mode: scale/shift from the running statistics (conv bias folded in)
 int bn_eval_affine(int C, const float *gamma, const float *beta, const float *conv_bias, const float *running_mean,
                    const float *running_var, BnState st, cudaStream_t s);
@@ -35,7 +35,7 @@ int upcat(const T *raw_skip, BnState bn_skip, const T *low, T *cat, int N, int h
 // BatchNorm (+LeakyReLU +dropout) backward.  dact: grad wrt dropout(leaky(bn(raw))).  draw: grad wrt raw.
 template <typename T>
 int bn_bwd(const T *dact, const T *raw, T *draw, int64_t M, int C, BnState bn, DropSpec drop, float *partials,
-           int max_partials, float *dgamma, float *dbeta, int accumulate, cudaStream_t s);
+           int max_partials, float *dgamma, float *dbeta, int accumulate, cudaStream_t s, double *sync_sums = nullptr);
 
 // grad wrt an encoder feature = skip half of dcat (+) un-pooled grad of the pooled tensor
 template <typename T>

@@ -42,6 +42,7 @@ struct LossArgs {
     int64_t *pseudo1, *pseudo2;
     double *acc;
     uint8_t *aux;   // CPS: pl1 | pl2 (n_u*hw each); UAMT: mask (n_u*hw)
+    int world;         // exact-global mode: number of ranks whose sums were all-reduced into acc (1 otherwise)
     int reduce_imgs;   // images the reduce kernel streams: n_l for SUP / MT / ICT (their global sums only involve labeled pixels)
     FastDiv qdiv;   // division by hw/4 without the 64-bit integer divide (quad index -> image, quad in image)
 };
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
             make_coef<C>(A.acc + 3 * kAccPerSet, A.class_w, coef[3]);
         }
         float cons = 0.f, cons_val = 0.f;
-        const double M = (double)A.n_u * C * (double)A.hw;
+        const double M = (double)A.n_u * C * (double)A.hw * (double)A.world;      // elements of the consistency mean (all ranks)
         if (late_mse) {   // the squared distance is summed by THIS kernel (below); its gradient needs no global sum
             cons = (float)(2.0 * A.cons_weight / M);
         } else if (s4cv) {
@@ -528,7 +529,7 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
             if (ticket == gridDim.x - 1) {      // every CTA's partial is in: finish the scalars
                 __threadfence();
                 const double total = atomicAdd(A.acc + kAccMse, 0.0);
-                const float cons_val = (float)(total / ((double)A.n_u * C * (double)A.hw));
+                const float cons_val = (float)(total / ((double)A.n_u * C * (double)A.hw * (double)A.world));   // this rank's share
                 const float sup = A.ce_coef * coef[0].ce + A.dice_coef * coef[0].dice;
                 A.scalars[0] = sup + A.cons_weight * cons_val;
                 A.scalars[2] = cons_val;
@@ -650,7 +651,14 @@ static int launch_loss(const LossArgs &A, cudaStream_t st) {
         default: HPFG_CUDA_CHECK(launch_pdl(loss_reduce_kernel<C, HPFG_LOSS_UAMT>, rgrid, 256, 0, st, A)); break;
     }
     HPFG_LAUNCH_CHECK();
-    HPFG_CUDA_CHECK(launch_pdl(loss_grad_kernel<C>, grid, 256, 0, st, A));
+    // exact-global mode: Dice / CE / pseudo-label / mask sums over the batch of ALL ranks before any coefficient is formed
+    // (the last slot is the gradient kernel's block counter: still zero everywhere, so it may take part)
+    if (A.world > 1) {
+        HPFG_RETURN_IF(sync_allreduce(A.acc, kAccTotal, true, st));
+        HPFG_CUDA_CHECK(launch_plain(loss_grad_kernel<C>, grid, 256, 0, st, A));     // (no programmatic launch across the collective)
+    } else {
+        HPFG_CUDA_CHECK(launch_pdl(loss_grad_kernel<C>, grid, 256, 0, st, A));
+    }
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -700,6 +708,7 @@ static int ssl_loss_impl(int mode, const float *student, const float *other, con
     LossArgs A{};
     HPFG_REQUIRE((int64_t)(n_l + n_u) * height * width / 4 < (1LL << 31), "hpfg_ssl_loss: batch too large for 32-bit quad indexing");
     A.mode = mode; A.n_l = n_l; A.n_u = n_u; A.hw = height * width; A.mc_passes = mc_passes;
+    A.world = g_loss_global_sums ? sync_world() : 1;
     A.qdiv = make_fastdiv((uint32_t)(A.hw >> 2));
     A.reduce_imgs = (mode == HPFG_LOSS_SUP || mode == HPFG_LOSS_MT || mode == HPFG_LOSS_ICT) ? n_l : n_l + n_u;
     A.student = student; A.other = other; A.mc = mc_logits; A.labels = labels;

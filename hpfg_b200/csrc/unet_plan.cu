@@ -13,6 +13,22 @@ static thread_local std::string g_error;
 int64_t g_launch_count = 0;
 void set_error(const std::string &msg) { g_error = msg; }
 
+typedef void (*hpfg_allreduce_fn)(void *, void *, int64_t, int, void *);
+static hpfg_allreduce_fn g_sync_fn = nullptr;
+static void *g_sync_ctx = nullptr;
+static int g_sync_world = 1;
+bool g_loss_global_sums = false;
+int sync_world() { return g_sync_world; }
+int sync_allreduce(void *device_ptr, int64_t count, bool is_double, cudaStream_t s) {
+    if (g_sync_world <= 1) return HPFG_OK;
+    if (!g_sync_fn) {
+        set_error("exact-global mode needs an all-reduce hook (hpfg_set_allreduce_hook)");
+        return HPFG_ERR_INVALID;
+    }
+    g_sync_fn(g_sync_ctx, device_ptr, count, is_double ? 1 : 0, (void *)s);
+    return HPFG_OK;
+}
+
 int tc_cta_cap(int kind) {
     static int caps[3] = {-1, -1, -1};
     if (caps[0] < 0) {
@@ -155,6 +171,7 @@ static void carve(hpfg_unet_plan *p, char *base, int64_t &total) {
     int64_t bnf = 0;
     for (auto &b : p->d.bns) bnf += 8 * (int64_t)align_up(b.C, 64);
     c.take(p->bnmem, bnf * 4);
+    c.take(p->sync_sums, 4 * 256 * 8);      // exact-global mode: [local | global] x (2 x 256) fp64 sums
     if (base) {
         float *q = p->bnmem;
         for (auto &b : p->d.bns) {
@@ -213,7 +230,7 @@ static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_runnin
         if (training)
             return bn_finalize(p->stats, P, b.C, (int64_t)N * cv.H * cv.W, params + b.g_off, params + b.b_off,
                                params + cv.b_off, bn_running + b.run_off, bn_running + b.run_off + b.C,
-                               bn_counters ? bn_counters + cv.bn : nullptr, 1, b.st, s);
+                               bn_counters ? bn_counters + cv.bn : nullptr, 1, b.st, s, p->sync_bn ? p->sync_sums : nullptr);
         return bn_eval_affine(b.C, params + b.g_off, params + b.b_off, params + cv.b_off, bn_running + b.run_off,
                               bn_running + b.run_off + b.C, b.st, s);
     };
@@ -509,7 +526,8 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
         BnLayer &bl = d.bns[bn];
         DropSpec ds{bits, bits ? 1.f / (1.f - p_drop) : 1.f};
         return bn_bwd<T>((const T *)dact, (const T *)bl.raw, (T *)draw, (int64_t)N * bl.H * bl.W, bl.C, bl.st, ds, p->stats,
-                         (int)(p->stats_floats / (2 * bl.C)), grads + bl.g_off, grads + bl.b_off, acc, s);
+                         (int)(p->stats_floats / (2 * bl.C)), grads + bl.g_off, grads + bl.b_off, acc, s,
+                         p->sync_bn ? p->sync_sums : nullptr);
     };
 
     // ---- out_conv
@@ -722,6 +740,25 @@ extern "C" int hpfg_unet_plan_destroy(hpfg_unet_plan_t p) {
 
 extern "C" int64_t hpfg_unet_plan_workspace_bytes(hpfg_unet_plan_t p) { return p ? p->ws_bytes : 0; }
 
+extern "C" int hpfg_set_allreduce_hook(void (*fn)(void *, void *, int64_t, int, void *), void *ctx, int world_size) {
+    HPFG_REQUIRE(world_size >= 1 && (fn || world_size == 1), "hpfg_set_allreduce_hook: a hook is required when world_size > 1");
+    g_sync_fn = fn;
+    g_sync_ctx = ctx;
+    g_sync_world = world_size;
+    return HPFG_OK;
+}
+
+extern "C" int hpfg_ssl_loss_set_global_sums(int enabled) {
+    g_loss_global_sums = enabled != 0;
+    return HPFG_OK;
+}
+
+extern "C" int hpfg_unet_plan_set_sync_bn(hpfg_unet_plan_t p, int enabled) {
+    HPFG_REQUIRE(p, "hpfg_unet_plan_set_sync_bn: null plan");
+    p->sync_bn = enabled != 0;
+    return HPFG_OK;
+}
+
 extern "C" int hpfg_unet_plan_set_forward_ctas(hpfg_unet_plan_t p, int ctas) {
     HPFG_REQUIRE(p && ctas >= 0 && ctas <= kNumSMs, "hpfg_unet_plan_set_forward_ctas: 0 (no cap) .. 148");
     p->fwd_ctas = ctas;
@@ -754,7 +791,7 @@ extern "C" int hpfg_unet_backward(hpfg_unet_plan_t p, const float *params, const
     HPFG_REQUIRE(p->saved, "hpfg_unet_backward: no training forward with save_for_backward on this plan");
     cudaStream_t s = (cudaStream_t)stream;
     if (p->precision == HPFG_PREC_FP32) return backward_impl<float>(p, params, dlogits, grads, accumulate, s);
-    if (p->bwd_fusion) return backward_fused(p, params, dlogits, grads, accumulate, s, nullptr);
+    if (p->bwd_fusion && !p->sync_bn) return backward_fused(p, params, dlogits, grads, accumulate, s, nullptr);
     return backward_impl<bf16>(p, params, dlogits, grads, accumulate, s);
 }
 
@@ -764,7 +801,7 @@ extern "C" int hpfg_unet_backward_ex(hpfg_unet_plan_t p, const float *params, co
     HPFG_REQUIRE(p->saved, "hpfg_unet_backward_ex: no training forward with save_for_backward on this plan");
     cudaStream_t s = (cudaStream_t)stream;
     if (p->precision == HPFG_PREC_FP32) return backward_impl<float>(p, params, dlogits, grads, accumulate, s, dbottleneck);
-    if (p->bwd_fusion) return backward_fused(p, params, dlogits, grads, accumulate, s, dbottleneck);
+    if (p->bwd_fusion && !p->sync_bn) return backward_fused(p, params, dlogits, grads, accumulate, s, dbottleneck);
     return backward_impl<bf16>(p, params, dlogits, grads, accumulate, s, dbottleneck);
 }
 

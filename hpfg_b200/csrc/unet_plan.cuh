@@ -67,6 +67,8 @@ struct hpfg_unet_plan {
     int64_t wscratch_floats = 0;
     float *bnmem = nullptr;           // BnState arrays
     bool saved = false, saved_dropout = false;
+    bool sync_bn = false;             // BatchNorm statistics (forward and backward) over the batch of ALL ranks (hpfg_unet_plan_set_sync_bn)
+    double *sync_sums = nullptr;
     int fwd_ctas = 0;                 // > 0: cap on the persistent CTAs of the forward convolutions (two concurrent forwards share the SMs)
     bool bwd_fusion = false;          // bf16: BatchNorm backward folded into the dgrad / wgrad kernels (unet_plan.cu: backward_fused)
     const float *saved_x = nullptr;

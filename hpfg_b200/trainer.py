@@ -63,7 +63,7 @@ def shard_batch(x_l, x_u, y, rank, world):
 
 class _StepBase:
     def __init__(self, *, lr=0.01, momentum=0.9, weight_decay=1e-4, total_itrs=30000, consistency=0.1,
-                 consistency_rampup=200.0, process_group=None):
+                 consistency_rampup=200.0, process_group=None, exact_global=False):
         self.base_lr, self.momentum, self.weight_decay = lr, momentum, weight_decay
         self.total_itrs, self.consistency, self.consistency_rampup = total_itrs, consistency, consistency_rampup
         self.cur_itrs = 0
@@ -73,6 +73,14 @@ class _StepBase:
             self.world = torch.distributed.get_world_size(process_group)
         self._comm = None
         self.last = {}
+        # Data parallel semantics: default = what wrapping the reference in DDP gives (BatchNorm / Dice / CE /
+        # consistency means over each rank's shard, gradients averaged).  exact_global=True = the single-GPU reference on the
+        # CONCATENATED batch: BatchNorm statistics (forward and backward) and the loss sums are all-reduced over the ranks
+        # through the library's hook, parameter gradients are summed.  Eager launches only (one small all-reduce per BatchNorm).
+        self.exact_global = bool(exact_global) and self.world > 1
+        self._grad_scale = 1.0 if self.exact_global else 1.0 / self.world
+        if self.exact_global:
+            L.install_allreduce_hook(self.pg)
 
     # ------------------------------------------------------------------ CUDA-graph replay of the whole step
     _graph_enabled = False
@@ -97,7 +105,30 @@ class _StepBase:
 
     def _use_graph(self):
         dp_ok = self.world == 1 or (self._graph_dp and self._graph_dp_capable)
-        return self._graph_enabled and self.cur_itrs >= 2 and dp_ok
+        return self._graph_enabled and self.cur_itrs >= 2 and dp_ok and not getattr(self, "exact_global", False)
+
+    class _GlobalSums:
+        """Loss sums over the batch of all ranks while a fused loss call is enqueued (hpfg_ssl_loss_set_global_sums)."""
+
+        def __init__(self, on):
+            self.on = on
+
+        def __enter__(self):
+            if self.on:
+                L.check(L.lib().hpfg_ssl_loss_set_global_sums(1), "hpfg_ssl_loss_set_global_sums")
+
+        def __exit__(self, *exc):
+            if self.on:
+                L.check(L.lib().hpfg_ssl_loss_set_global_sums(0), "hpfg_ssl_loss_set_global_sums")
+
+    def _global_sums(self):
+        return self._GlobalSums(getattr(self, "exact_global", False))
+
+    def _global_consistency_value(self, scalars, w):
+        """Mean-Teacher / ICT in exact-global mode: the kernel's consistency value is this rank's share of the global mean."""
+        if getattr(self, "exact_global", False):
+            torch.distributed.all_reduce(scalars[2:3], group=self.pg)
+            scalars[0:1].copy_(scalars[1:2] + w * scalars[2:3])
 
     def _graph_replay(self, inputs, dyn_f, fwd_models, body):
         """Generic capture-once / replay driver (all step drivers).
@@ -236,6 +267,9 @@ class _StepBase:
     SHARED_FORWARD_CTAS = 74
 
     def _set_forward_share(self, plan, shared):
+        if getattr(self, "exact_global", False) and not getattr(plan, "sync_bn", False):
+            L.check(L.lib().hpfg_unet_plan_set_sync_bn(plan.handle, 1), "hpfg_unet_plan_set_sync_bn")
+            plan.sync_bn = True
         want = self.SHARED_FORWARD_CTAS if shared else 0
         if getattr(plan, "fwd_ctas", 0) != want:
             L.check(L.lib().hpfg_unet_plan_set_forward_ctas(plan.handle, want), "hpfg_unet_plan_set_forward_ctas")
@@ -319,11 +353,11 @@ class _StepBase:
         first = int(self.cur_itrs == 1)
         if ema_model is None:
             L.check(L.lib().hpfg_sgd_momentum(L.ptr(model.flat_params), L.ptr(grads), L.ptr(buf), n, lr, self.momentum,
-                                              self.weight_decay, 1.0 / self.world, first, st), "hpfg_sgd_momentum")
+                                              self.weight_decay, self._grad_scale, first, st), "hpfg_sgd_momentum")
         else:
             L.check(L.lib().hpfg_sgd_momentum_ema(L.ptr(model.flat_params), L.ptr(grads), L.ptr(buf),
                                                   L.ptr(ema_model.flat_params), n, lr, self.momentum, self.weight_decay,
-                                                  1.0 / self.world, first, ema_alpha, st), "hpfg_sgd_momentum_ema")
+                                                  self._grad_scale, first, ema_alpha, st), "hpfg_sgd_momentum_ema")
         return lr
 
 
@@ -361,7 +395,9 @@ class MeanTeacherStep(_StepBase):
         plan, out = self._forward(self.model, x, True, out=self._persistent("s_out", shape, x.device))
         main.wait_stream(side)
         w = self._consistency_weight()
-        r = ssl_loss_raw(L.LOSS_MT, out, t_out[n_l:], labels, n_l, cons_weight=w)
+        with self._global_sums():
+            r = ssl_loss_raw(L.LOSS_MT, out, t_out[n_l:], labels, n_l, cons_weight=w)
+        self._global_consistency_value(r["scalars"], w)
         self._backward(self.model, plan, r["dstudent"], self.grads)
         alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)      # utils/utils.py:84
         lr = self._sgd(self.model, self.grads, self.mom, self.ema_model, alpha)
@@ -434,7 +470,8 @@ class CPSStep(_StepBase):
         p1, o1 = self._forward(self.m1, x, True, out=self._persistent("o1", shape, x.device))
         main.wait_stream(side)
         w = self._consistency_weight()
-        r = ssl_loss_raw(L.LOSS_CPS, o1, o2, labels, n_l, cons_weight=w, want_pseudo=False)
+        with self._global_sums():
+            r = ssl_loss_raw(L.LOSS_CPS, o1, o2, labels, n_l, cons_weight=w, want_pseudo=False)
         side.wait_stream(main)
         with torch.cuda.stream(side):
             self._backward(self.m2, p2, r["dother"], self.g2)
@@ -538,8 +575,9 @@ class UAMTStep(_StepBase):
         main.wait_stream(side)
         w = self._consistency_weight()
         thr = (0.75 + 0.25 * sigmoid_rampup(self.cur_itrs, self.total_itrs)) * math.log(2)
-        r = ssl_loss_raw(L.LOSS_UAMT, out, t_out, labels, n_l, cons_weight=w, mc_logits=mc, mc_passes=self.T,
-                         uamt_threshold=thr)
+        with self._global_sums():
+            r = ssl_loss_raw(L.LOSS_UAMT, out, t_out, labels, n_l, cons_weight=w, mc_logits=mc, mc_passes=self.T,
+                             uamt_threshold=thr)
         self._backward(self.model, plan, r["dstudent"], self.grads)
         alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)
         lr = self._sgd(self.model, self.grads, self.mom, self.ema_model, alpha)
@@ -629,7 +667,9 @@ class ICTStep(_StepBase):
         plan, out = self._forward(self.model, x_in, True, out=self._persistent("s_out", (n_l + n_m, ncls, hh, ww), dev))
         main.wait_stream(side)
         w = self._consistency_weight()
-        r = ict_loss_raw(out, t_out, lam, labels, n_l, cons_weight=w)
+        with self._global_sums():
+            r = ict_loss_raw(out, t_out, lam, labels, n_l, cons_weight=w)
+        self._global_consistency_value(r["scalars"], w)
         self._backward(self.model, plan, r["dstudent"], self.grads)
         alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)
         lr = self._sgd(self.model, self.grads, self.mom, self.ema_model, alpha)
@@ -710,7 +750,8 @@ class S4CVStep(_StepBase):
         main.wait_stream(side)
         w = self._consistency_weight()
         mt_on = self.cur_itrs >= self.mt_start
-        r = s4cv_loss_raw(o1, o2, t_out if mt_on else None, labels, n_l, cps_weight=7.0 * w, mt_weight=w)
+        with self._global_sums():
+            r = s4cv_loss_raw(o1, o2, t_out if mt_on else None, labels, n_l, cps_weight=7.0 * w, mt_weight=w)
         side.wait_stream(main)
         alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)
         with torch.cuda.stream(side):
@@ -774,7 +815,7 @@ class HPFGStep(_StepBase):
         lib = L.lib()
         g = model.last_flat_grad
         L.check(lib.hpfg_sgd_momentum(L.ptr(model.flat_params), L.ptr(g), L.ptr(buf), model.flat_params.numel(), lr, self.momentum,
-                                      self.weight_decay, 1.0 / self.world, first, st), "hpfg_sgd_momentum")
+                                      self.weight_decay, self._grad_scale, first, st), "hpfg_sgd_momentum")
         core = {id(q) for q in model._flat_params_list}
         for p in model.parameters():
             if id(p) in core or p.grad is None:
@@ -783,7 +824,7 @@ class HPFGStep(_StepBase):
             if mom is None:
                 mom = self._neck_mom[id(p)] = torch.zeros_like(p.data)
             L.check(lib.hpfg_sgd_momentum(L.ptr(p.data), L.ptr(p.grad.contiguous()), L.ptr(mom), p.numel(), lr, self.momentum,
-                                          self.weight_decay, 1.0 / self.world, first, st),
+                                          self.weight_decay, self._grad_scale, first, st),
                     "hpfg_sgd_momentum")
 
     def step(self, label_img, target_label, label_img1, target_label1, img_unlabel, cutmix_mask, lr=None):

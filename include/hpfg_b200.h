@@ -73,6 +73,18 @@ int hpfg_unet_plan_create(int batch, int in_channels, int num_classes, int heigh
                           hpfg_unet_plan_t *plan_out);
 int hpfg_unet_plan_destroy(hpfg_unet_plan_t plan);
 int64_t hpfg_unet_plan_workspace_bytes(hpfg_unet_plan_t plan);
+/* ---- exact-global data-parallel mode (SURVEY 8e caveats 1-3) -------------------------------------------------------------
+ * Default data parallelism has DDP semantics: every rank normalises BatchNorm, Dice, CE and the consistency mean over ITS shard.
+ * In exact-global mode an N-rank step computes what the single-GPU reference computes on the concatenated batch: the library
+ * calls `fn(ctx, device_ptr, count, is_double, stream)` -- a SUM all-reduce over the ranks, enqueued in stream order by the host
+ * (NCCL through torch.distributed in hpfg_b200/_lib.py) -- on the 2*C BatchNorm sums of every BatchNorm forward and backward
+ * (plans with hpfg_unet_plan_set_sync_bn) and on the 128 loss accumulators between the loss reduce and gradient launches
+ * (hpfg_ssl_loss_set_global_sums).  Parameter gradients are then SUMMED over the ranks (grad_scale 1, not 1/world). */
+int hpfg_set_allreduce_hook(void (*fn)(void *ctx, void *device_ptr, int64_t count, int is_double, void *stream), void *ctx,
+                            int world_size);
+int hpfg_unet_plan_set_sync_bn(hpfg_unet_plan_t plan, int enabled);
+int hpfg_ssl_loss_set_global_sums(int enabled);
+
 /* Cap on the persistent CTAs of this plan's forward convolutions (0 = none: one CTA per SM on all 148 SMs).  A tensor-core
  * convolution CTA owns a whole SM (~200 KB of shared memory, the full register file), so two forwards enqueued on two streams
  * (student | teacher, the two CPS networks) take turns kernel by kernel; with 74 CTAs each they run side by side on disjoint SMs
