@@ -49,8 +49,9 @@ METRICS = {"mt": "UNet SSL train images/sec @224x224 (Mean-Teacher step)", "cps"
 # dram__bytes_read.sum + dram__bytes_write.sum from ncu (see the named profile); None until measured for the current kernels
 TOP_KERNEL_DRAM_BYTES = 58.16e6      # one launch of the 3x3 16->16 @224 fprop (profiles/r01_ncu_prof_fprop16_final_raw.txt)
 LOSS_DRAM_BYTES = 9657856 + 2048 + 48247552 + 169216      # reduce read+write, gradient read+write (profiles/r01_ncu_loss_kernels.csv)
-CONV_FAMILY_DRAM_BYTES = None        # all tc_conv_kernel launches of one mt_acdc step
-CONV_FAMILY_DRAM_SOURCE = None
+CONV_FAMILY_DRAM_BYTES = 1710.8e6    # all 68 tc_conv_kernel launches of one mt_acdc step (25 MB per launch on average)
+CONV_FAMILY_DRAM_SOURCE = ("ncu dram__bytes_read.sum + dram__bytes_write.sum over the 68 tc_conv_kernel launches of one steady-state step, "
+                           "profiles/r02_launch_summary.txt (whole step: 5.66 GB of DRAM traffic)")
 
 
 def flops_per_step(c):
@@ -475,7 +476,8 @@ def run_gpu(args):
                                                  "note": "images/s/GPU x algorithmic conv FLOPs per image (SURVEY 8d) over the WHOLE step time"},
                 "roofline": {"kernel": "tc_conv_kernel (tcgen05 implicit-GEMM conv family: every fprop incl. in_conv.0 and the logits conv, dgrad, 1x1)",
                              "bound": "tensor", "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
-                             "traffic": CONV_FAMILY_DRAM_BYTES, "traffic_source": CONV_FAMILY_DRAM_SOURCE,
+                             "traffic": CONV_FAMILY_DRAM_BYTES if args.config == "mt_acdc" else None,
+                             "traffic_source": CONV_FAMILY_DRAM_SOURCE if args.config == "mt_acdc" else None,
                              "peak_source": pk["src"] + ", burst bf16", "launches_per_step": prof["conv_tcgen05"]["calls_per_step"],
                              "us_per_step": tc_ms * 1e3, "algorithmic_flops_per_step": tc_flops,
                              "note": "ALL tensor-core conv launches of a step (serialized profiling pass, CUDA events in the library) "

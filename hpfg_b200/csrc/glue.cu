@@ -308,6 +308,7 @@ int upcat(const T *raw_skip, BnState bn_skip, const T *low, T *cat, int N, int h
 // g = dact * dropout' * leaky'(z);  xhat = (raw-mean)*invstd.
 // MODE 0: reduce sum(g), sum(g*raw) into partials (the finalize kernel turns the raw moment into sum(g*xhat)).
 // MODE 1: draw = scale*(g - c1 - xhat*c2) = scale*g + B*raw + D with B = -scale*c2*invstd, D = -scale*c1 - B*mean.
+// MODE 2: as MODE 1 when the first tensor already holds g (written by skip_pool_bwd_gstat): no activation / dropout math.
 // Few per-channel constants on purpose: 64 registers per thread keep four CTAs per SM resident (ncu: at 84 registers
 // the kernel ran two CTAs per SM and reached 33-41 % of HBM bandwidth).
 template <typename T, int MODE>
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_kernel(const T *__restrict__ da
         const int c = cv * V + k;
         sc[k] = bn.scale[c]; sh[k] = bn.shift[c];
         kb[k] = kd[k] = 0.f;
-        if (MODE == 1) {
+        if (MODE >= 1) {
             kb[k] = -sc[k] * bn.c2[c] * bn.invstd[c];
             kd[k] = -sc[k] * bn.c1[c] - kb[k] * bn.mean[c];
         }
@@ -347,13 +348,16 @@ __global__ void __launch_bounds__(256, 4) bn_bwd_kernel(const T *__restrict__ da
             }
 #pragma unroll
             for (int k = 0; k < V; ++k) {
-                const float z = fmaf(x[k], sc[k], sh[k]);
-                float g = d[k] * leaky_grad(z);
-                if (drop.bits) g = ((mbits >> k) & 1u) ? g * drop.inv_keep : 0.f;
+                float g = d[k];
+                if (MODE != 2) {
+                    const float z = fmaf(x[k], sc[k], sh[k]);
+                    g = d[k] * leaky_grad(z);
+                    if (drop.bits) g = ((mbits >> k) & 1u) ? g * drop.inv_keep : 0.f;
+                }
                 if (MODE == 0) { kb[k] += g; kd[k] = fmaf(g, x[k], kd[k]); }
                 else d[k] = fmaf(sc[k], g, fmaf(kb[k], x[k], kd[k]));
             }
-            if (MODE == 1) Vec<T>::store(draw + p * C + cv * V, d);
+            if (MODE >= 1) Vec<T>::store(draw + p * C + cv * V, d);
         }
     if (MODE == 0) {
         // deterministic cross-row reduction through shared memory: red[which][r][c]
@@ -538,6 +542,18 @@ int skip_pool_bwd(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *
     const int64_t total = (int64_t)N * (H / 2) * (W / 2) * (F / Vec<T>::N);
     HPFG_REQUIRE(total < (1ll << 31), "skip_pool_bwd: tensor too large for 32-bit indexing");
     HPFG_CUDA_CHECK(launch_pdl(skip_pool_bwd_kernel<T, false>, ew_grid(total), 256, 0, s, dcat, dpooled, raw, bn, dact, N, H, W, F, make_fastdiv(F / Vec<T>::N), make_fastdiv(W / 2), make_fastdiv(H / 2), (float *)nullptr));
+    HPFG_LAUNCH_CHECK();
+    return HPFG_OK;
+}
+
+// pass 1 alone on a tensor that already holds g (after skip_pool_bwd_gstat + bn_bwd_reduce): draw = scale*g + kb*raw + kd
+template <typename T>
+int bn_bwd_from_g(const T *g, const T *raw, T *draw, int64_t M, int C, BnState bn, cudaStream_t s) {
+    ProfScope _prof(PROF_GLUE, s);
+    int P2 = (int)((M + 63) / 64);
+    if (P2 > kNumSMs * 8) P2 = kNumSMs * 8;
+    DropSpec none{nullptr, 1.f};
+    HPFG_CUDA_CHECK(launch_pdl(bn_bwd_kernel<T, 2>, P2, 256, 0, s, g, raw, draw, M, C, bn, none, (float *)nullptr));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
 }
@@ -798,6 +814,7 @@ int add_nchw_f32_to_nhwc(T *dst, const float *src, int N, int H, int W, int C, c
     template int bn_bwd<T>(const T *, const T *, T *, int64_t, int, BnState, DropSpec, float *, int, float *,       \
                            float *, int, cudaStream_t, double *);                                                   \
     template int skip_pool_bwd<T>(const T *, const T *, const T *, BnState, T *, int, int, int, int, cudaStream_t); \
+    template int bn_bwd_from_g<T>(const T *, const T *, T *, int64_t, int, BnState, cudaStream_t);                   \
     template int skip_pool_bwd_gstat<T>(const T *, const T *, const T *, BnState, T *, int, int, int, int, float *, int, int *, cudaStream_t); \
     template int up_bwd<T>(const T *, T *, int, int, int, int, cudaStream_t);                                       \
     template int act_nhwc_to_nchw_f32<T>(const T *, BnState, float *, int, int, int, int, cudaStream_t);           \

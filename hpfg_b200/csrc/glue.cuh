@@ -46,6 +46,8 @@ int skip_pool_bwd(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *
 template <typename T>
 int skip_pool_bwd_gstat(const T *dcat, const T *dpooled, const T *raw, BnState bn, T *g_out, int N, int H, int W, int F,
                         float *partials, int max_partials, int *P, cudaStream_t s);
+template <typename T>
+int bn_bwd_from_g(const T *g, const T *raw, T *draw, int64_t M, int C, BnState bn, cudaStream_t s);
 // BatchNorm-backward reduction of [P][2*C] partials (sum g | sum g*raw) -> bn.c1/c2/kb/kd, dgamma, dbeta (count = N*H*W)
 int bn_bwd_reduce(const float *partials, int P, int C, int64_t count, BnState bn, float *dgamma, float *dbeta, int accumulate,
                   cudaStream_t s);

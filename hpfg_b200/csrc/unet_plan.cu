@@ -103,7 +103,7 @@ void describe_unet(int in_ch, int n_cls, int H, int W, UNetDesc &d) {
     int64_t bounds[5] = {0, 0, 0, 0, 0};
     add_block("encoder.in_conv", in_ch, kFt[0], H, W);
     for (int l = 1; l < 5; ++l) {
-        if (l == 4) bounds[1] = off;
+        if (l == 3) bounds[1] = off;      // last (exposed) bucket = in_conv .. down2 only: 72 k parameters
         add_block("encoder.down" + std::to_string(l) + ".maxpool_conv.1", kFt[l - 1], kFt[l], H >> l, W >> l);
     }
     for (int j = 1; j < 5; ++j) {
@@ -452,9 +452,9 @@ static int backward_fused(hpfg_unet_plan *p, const float *params, const float *d
             HPFG_RETURN_IF(dgrad(cA, c, &fA, p->g[3], -1, nullptr, 0.f));            // dpooled for level l-1
             dpooled = p->g[3];
         }
-        if (l == 4 || l == 0) {
+        if (l == 3 || l == 0) {
             HPFG_RETURN_IF(join_side());
-            HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[l == 4 ? 2 : 3], s));
+            HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[l == 3 ? 2 : 3], s));
         }
     }
     return HPFG_OK;
@@ -581,11 +581,26 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
     for (int l = 4; l >= 0; --l) {
         const int cA = 2 * l, cB = 2 * l + 1, bA = cA, bB = cB, h = H >> l, w = W >> l;
         const uint32_t *bits = p->saved_dropout ? p->dropbits[l] : nullptr;
-        if (l < 4)   // grad wrt the encoder feature = skip half of dcat + un-pooled grad from the level below
-            HPFG_RETURN_IF(skip_pool_bwd<T>((const T *)p->dcat[4 - l], (const T *)dpooled, (const T *)d.bns[bB].raw, d.bns[bB].st,
-                                            (T *)a, N, h, w, kFt[l], s));
-        HPFG_RETURN_IF(next_b());
-        HPFG_RETURN_IF(bnb(bB, a, b, nullptr, 0.f));                                // draw(B) in b
+        // grad wrt the encoder feature = skip half of dcat + un-pooled grad from the level below.  bf16 plans: the same kernel
+        // already reads the feature's raw tensor, so it also does BatchNorm-backward pass 0 (stores g, writes the two sums):
+        // one full tensor pass and one launch less per encoder level than skip_pool_bwd -> bn_bwd<0>.
+        static const bool gstat_on = !(getenv("HPFG_SKIP_GSTAT") && getenv("HPFG_SKIP_GSTAT")[0] == '0');     // A/B switch (profiles/)
+        const bool gstat = l < 4 && tc && !p->sync_bn && gstat_on;
+        if (gstat) {
+            BnLayer &bl = d.bns[bB];
+            int P = 0;
+            HPFG_RETURN_IF(skip_pool_bwd_gstat<T>((const T *)p->dcat[4 - l], (const T *)dpooled, (const T *)bl.raw, bl.st, (T *)a, N, h, w,
+                                                  kFt[l], p->stats, (int)(p->stats_floats / (2 * bl.C)), &P, s));
+            HPFG_RETURN_IF(bn_bwd_reduce(p->stats, P, bl.C, (int64_t)N * h * w, bl.st, grads + bl.g_off, grads + bl.b_off, acc, s));
+            HPFG_RETURN_IF(next_b());
+            HPFG_RETURN_IF(bn_bwd_from_g<T>((const T *)a, (const T *)bl.raw, (T *)b, (int64_t)N * h * w, bl.C, bl.st, s));
+        } else {
+            if (l < 4)
+                HPFG_RETURN_IF(skip_pool_bwd<T>((const T *)p->dcat[4 - l], (const T *)dpooled, (const T *)d.bns[bB].raw, d.bns[bB].st,
+                                                (T *)a, N, h, w, kFt[l], s));
+            HPFG_RETURN_IF(next_b());
+            HPFG_RETURN_IF(bnb(bB, a, b, nullptr, 0.f));                            // draw(B) in b
+        }
         HPFG_RETURN_IF(wgrad(cB, d.bns[bA].raw, xf_of(bA, bits, kEncDropout[l]), b));
         HPFG_RETURN_IF(dgrad(cB, b, c));                                            // dact(A) in c
         HPFG_RETURN_IF(next_b());
@@ -604,9 +619,9 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
             HPFG_RETURN_IF(dgrad(cA, b, p->g[3]));                                  // dpooled for level l-1
             dpooled = p->g[3];
         }
-        if (l == 4 || l == 0) {
+        if (l == 3 || l == 0) {
             HPFG_RETURN_IF(join_side());
-            HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[l == 4 ? 2 : 3], s));
+            HPFG_CUDA_CHECK(cudaEventRecord(p->bucket_ev[l == 3 ? 2 : 3], s));
         }
     }
     return HPFG_OK;

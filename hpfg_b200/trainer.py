@@ -29,7 +29,8 @@ def medical_lr(cur_itrs, base_lr, max_iterations):
 
 def gradient_buckets(in_channels, num_classes):
     """[(offset, count)] of the flat-gradient buckets in the order backward completes them (tail of the
-    parameter list first: out_conv/up4/up3 | up2/up1 | down4 | in_conv..down3)."""
+    parameter list first: out_conv/up4/up3 | up2/up1 | down4/down3 | in_conv..down2: the last bucket, whose all-reduce cannot
+    overlap backward, is the smallest)."""
     import ctypes
     offs, cnts = (ctypes.c_int64 * 4)(), (ctypes.c_int64 * 4)()
     L.check(L.lib().hpfg_unet_bucket_layout(in_channels, num_classes, offs, cnts), "hpfg_unet_bucket_layout")
