@@ -153,6 +153,8 @@ class _StepBase:
             m.ensure_flat()
         ptrs = tuple((m.flat_params.data_ptr(), m.bn_running.data_ptr(), m.bn_counters.data_ptr(), id(m._plans)) for m in models)
         ptrs += tuple(t.data_ptr() for t in self._state_tensors())
+        # (the dropout seed is a by-value launch argument: a re-seeded generator needs a new capture)
+        ptrs += (torch.cuda.default_generators[dev.index if dev.index is not None else torch.cuda.current_device()].initial_seed(),)
         sig = tuple((tuple(t.shape), t.dtype) for t in inputs) + (len(dyn_f), len(fwd_models), ptrs)
         if getattr(self, "_gsig", None) != sig:
             self._gin = [torch.empty_like(t) for t in inputs]
@@ -264,8 +266,11 @@ class _StepBase:
             for t in (m.flat_params, m.bn_running, m.bn_counters):
                 dist.broadcast(t, src=dist.get_global_rank(self.pg, 0) if self.pg is not None else 0, group=self.pg)
 
-    # Two forwards enqueued on two streams share the machine: half of the SMs each (hpfg_unet_plan_set_forward_ctas)
+    # Two forwards enqueued on two streams share the machine: half of the SMs each (hpfg_unet_plan_set_forward_ctas).  Only the
+    # drivers whose two streams carry about the same forward work do this (Mean-Teacher, CPS, ICT); with unbalanced streams
+    # (UAMT: one student forward next to five teacher forwards; S4CVNet) the longer stream would finish on half a machine.
     SHARED_FORWARD_CTAS = 74
+    share_forward = True
 
     def _set_forward_share(self, plan, shared):
         if getattr(self, "exact_global", False) and not getattr(plan, "sync_bn", False):
@@ -278,7 +283,7 @@ class _StepBase:
 
     def _forward_dv(self, model, x, save, out, offset_dev):
         plan = model._acquire_plan(x, need_grad=save)
-        self._set_forward_share(plan, True)              # (graph replays always run the forwards on two streams)
+        self._set_forward_share(plan, self.share_forward)      # (graph replays always run the forwards on two streams)
         return plan, model._run_forward(plan, x, save=save, out=out, offset_dev=offset_dev)
 
     def _sgd_dv(self, model, grads, buf, dyn_f, ema_model=None):
@@ -313,7 +318,7 @@ class _StepBase:
     def _forward(self, model, x, save, out=None):
         model.ensure_flat()
         plan = model._acquire_plan(x, need_grad=save)
-        self._set_forward_share(plan, not getattr(self, "serialize", False))
+        self._set_forward_share(plan, self.share_forward and not getattr(self, "serialize", False))
         logits = model._run_forward(plan, x, save=save, out=out)
         return plan, logits
 
@@ -506,6 +511,8 @@ class CPSStep(_StepBase):
 
 
 class UAMTStep(_StepBase):
+    share_forward = False
+
     def __init__(self, model, ema_model, *, ema_decay=0.99, T=8, **kw):
         super().__init__(**kw)
         self.model, self.ema_model, self.ema_decay, self.T = model, ema_model, ema_decay, T
@@ -706,6 +713,7 @@ class S4CVStep(_StepBase):
     weight 7w) plus, from iteration ``mt_start`` on, Mean-Teacher MSE of both students against the EMA teacher of student 2,
     which sees the noise-perturbed unlabeled slices.  w = consistency * linear_rampup(cur_itrs // 150, rampup) (:148-149).
     One fused loss call (``hpfg_s4cv_loss``) produces the value and both logit gradients."""
+    share_forward = False
 
     def __init__(self, model1, model2, ema_model, *, ema_decay=0.99, mt_start=1000, **kw):
         super().__init__(**kw)
