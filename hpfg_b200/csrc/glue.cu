@@ -311,8 +311,11 @@ int upcat(const T *raw_skip, BnState bn_skip, const T *low, T *cat, int N, int h
 // MODE 2: as MODE 1 when the first tensor already holds g (written by skip_pool_bwd_gstat): no activation / dropout math.
 // Few per-channel constants on purpose: 64 registers per thread keep four CTAs per SM resident (ncu: at 84 registers
 // the kernel ran two CTAs per SM and reached 33-41 % of HBM bandwidth).
+#ifndef HPFG_GLUE_MINBLOCKS
+#define HPFG_GLUE_MINBLOCKS 4
+#endif
 template <typename T, int MODE>
-__global__ void __launch_bounds__(256, 4) bn_bwd_kernel(const T *__restrict__ dact, const T *__restrict__ raw,
+__global__ void __launch_bounds__(256, HPFG_GLUE_MINBLOCKS) bn_bwd_kernel(const T *__restrict__ dact, const T *__restrict__ raw,
                                                         T *__restrict__ draw, int64_t M, int C, BnState bn, DropSpec drop,
                                                         float *__restrict__ partials) {
     pdl_prologue();

@@ -491,9 +491,20 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
         return HPFG_OK;
     };
     // weight gradient of conv `ci`: in (T NHWC, optionally transformed on load) x dout (T NHWC)
+    // Order of submission per layer: the raw gradient is ready -> mark_ready() records the event on the main stream, the DATA
+    // gradient is enqueued first (it is on the critical path and should get the SMs first), then the weight gradient on the side
+    // stream, which waits for the event only (not for the data gradient) and fills in next to the following BatchNorm kernels.
+    static const bool dgrad_first = !(getenv("HPFG_DGRAD_FIRST") && getenv("HPFG_DGRAD_FIRST")[0] == '0');      // A/B switch (profiles/)
+    bool ready_marked = false;
+    auto mark_ready = [&]() -> int {
+        HPFG_CUDA_CHECK(cudaEventRecord(p->ev_ready, s));
+        ready_marked = true;
+        return HPFG_OK;
+    };
     auto wgrad = [&](int ci, void *in, LoadXform xf, void *dout) -> int {
         ConvLayer &cv = d.convs[ci];
-        HPFG_CUDA_CHECK(cudaEventRecord(p->ev_ready, s));
+        if (!ready_marked) HPFG_CUDA_CHECK(cudaEventRecord(p->ev_ready, s));
+        ready_marked = false;
         HPFG_CUDA_CHECK(cudaStreamWaitEvent(side, p->ev_ready, 0));
         bool done = false;
         if (tc) HPFG_RETURN_IF(tc_wgrad(p, ci, in, xf, dout, grads + cv.w_off, grads + cv.b_off, acc, &done, side));
@@ -533,8 +544,10 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
     // ---- out_conv
     if (tc) {   // dlogits: fp32 NCHW -> bf16 NHWC16, then regular tensor-core wgrad / dgrad with Cout padded to 16
         HPFG_RETURN_IF(pad_to_nhwc16(dlogits, p->dlpad, N, p->n_cls, H, W, s));
+        if (dgrad_first) HPFG_RETURN_IF(mark_ready());
+        if (dgrad_first) HPFG_RETURN_IF(dgrad(22, p->dlpad, p->g[0]));
         HPFG_RETURN_IF(wgrad(22, d.bns[17].raw, xf_of(17, nullptr, 0.f), p->dlpad));
-        HPFG_RETURN_IF(dgrad(22, p->dlpad, p->g[0]));
+        if (!dgrad_first) HPFG_RETURN_IF(dgrad(22, p->dlpad, p->g[0]));
     } else {
         ConvLayer &oc = d.convs[22];       // (all weight gradients share wscratch, so this one is ordered on the side stream too)
         HPFG_CUDA_CHECK(cudaEventRecord(p->ev_ready, s));
@@ -555,18 +568,24 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
         const int bA = d.convs[cA].bn, bB = d.convs[cB].bn;
         HPFG_RETURN_IF(next_b());
         HPFG_RETURN_IF(bnb(bB, a, b, nullptr, 0.f));                                // a -> draw(B) in b
+        if (dgrad_first) HPFG_RETURN_IF(mark_ready());
+        if (dgrad_first) HPFG_RETURN_IF(dgrad(cB, b, c));                           // -> dact(A) in c
         HPFG_RETURN_IF(wgrad(cB, d.bns[bA].raw, xf_of(bA, nullptr, 0.f), b));
-        HPFG_RETURN_IF(dgrad(cB, b, c));                                            // -> dact(A) in c
+        if (!dgrad_first) HPFG_RETURN_IF(dgrad(cB, b, c));
         HPFG_RETURN_IF(next_b());
         HPFG_RETURN_IF(bnb(bA, c, b, nullptr, 0.f));                                // -> draw(A) in b
+        if (dgrad_first) HPFG_RETURN_IF(mark_ready());
+        if (dgrad_first) HPFG_RETURN_IF(dgrad(cA, b, p->dcat[j]));                  // -> dcat (skip | upsampled)
         HPFG_RETURN_IF(wgrad(cA, p->cat[j], none, b));
-        HPFG_RETURN_IF(dgrad(cA, b, p->dcat[j]));                                   // -> dcat (skip | upsampled)
+        if (!dgrad_first) HPFG_RETURN_IF(dgrad(cA, b, p->dcat[j]));
         const int F = kFt[lvl], hl = H >> (lvl + 1), wl = W >> (lvl + 1);
         HPFG_RETURN_IF(next_b());
         HPFG_RETURN_IF(up_bwd<T>((const T *)p->dcat[j], (T *)b, N, hl, wl, F, s));  // -> dlow in b
         const int prev_bn = (j == 1) ? 9 : d.convs[cB - 3].bn;
+        if (dgrad_first) HPFG_RETURN_IF(mark_ready());
+        if (dgrad_first) HPFG_RETURN_IF(dgrad(c1x1, b, c));                         // -> dact(prev) in c
         HPFG_RETURN_IF(wgrad(c1x1, d.bns[prev_bn].raw, xf_of(prev_bn, nullptr, 0.f), b));
-        HPFG_RETURN_IF(dgrad(c1x1, b, c));                                          // -> dact(prev) in c
+        if (!dgrad_first) HPFG_RETURN_IF(dgrad(c1x1, b, c));
         std::swap(a, c);
         if (j == 3 || j == 1) {
             HPFG_RETURN_IF(join_side());
@@ -601,8 +620,10 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
             HPFG_RETURN_IF(next_b());
             HPFG_RETURN_IF(bnb(bB, a, b, nullptr, 0.f));                            // draw(B) in b
         }
+        if (dgrad_first) HPFG_RETURN_IF(mark_ready());
+        if (dgrad_first) HPFG_RETURN_IF(dgrad(cB, b, c));                           // dact(A) in c
         HPFG_RETURN_IF(wgrad(cB, d.bns[bA].raw, xf_of(bA, bits, kEncDropout[l]), b));
-        HPFG_RETURN_IF(dgrad(cB, b, c));                                            // dact(A) in c
+        if (!dgrad_first) HPFG_RETURN_IF(dgrad(cB, b, c));
         HPFG_RETURN_IF(next_b());
         HPFG_RETURN_IF(bnb(bA, c, b, bits, kEncDropout[l]));                        // draw(A) in b
         if (l == 0 && tc) {
@@ -615,8 +636,10 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
                                                      nhwc_view(b, H, W, 16), N, H, W, p->in_ch, 16, 3, none, p->wscratch,
                                                      p->wscratch_floats, grads + cv.w_off, grads + cv.b_off, acc, side)));
         } else {
+            if (dgrad_first) HPFG_RETURN_IF(mark_ready());
+            if (dgrad_first) HPFG_RETURN_IF(dgrad(cA, b, p->g[3]));                 // dpooled for level l-1
             HPFG_RETURN_IF(wgrad(cA, p->pooled[l], none, b));
-            HPFG_RETURN_IF(dgrad(cA, b, p->g[3]));                                  // dpooled for level l-1
+            if (!dgrad_first) HPFG_RETURN_IF(dgrad(cA, b, p->g[3]));
             dpooled = p->g[3];
         }
         if (l == 3 || l == 0) {

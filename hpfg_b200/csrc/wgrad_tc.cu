@@ -29,7 +29,7 @@ namespace hpfg {
 constexpr int kWgXfThreads = 256;   // transform threads (warps 4-11): loader transform of X into shifted copies + bias-gradient sums
 constexpr int kWgThreads = 128 + kWgXfThreads + 128;   // warps 0 TMA, 1 MMA, 2 TMEM alloc, 3 idle, 4-11 transform, 12-15 epilogue
 #ifndef HPFG_WG_SMEM_KB
-#define HPFG_WG_SMEM_KB 222
+#define HPFG_WG_SMEM_KB 198      // leaves room for the streaming BatchNorm kernels' static shared memory next to a weight-gradient CTA
 #endif
 constexpr int kWgSmemBudget = HPFG_WG_SMEM_KB * 1024;
 
@@ -81,8 +81,13 @@ struct WgParams {
 };
 #define WG_TRACE(role, idx) do { if (P.trace && blockIdx.x == 0 && lane == 0 && (idx) < 32) P.trace[(role) * 32 + (idx)] = clock64(); } while (0)
 
+#ifndef HPFG_WG_MINBLOCKS
+#define HPFG_WG_MINBLOCKS 2      // at most 64 registers per thread (the kernels need 52-64): two 256-thread glue CTAs of the
+                                 // main-stream BatchNorm / gather chain then fit next to a weight-gradient CTA and the two streams of
+                                 // the backward pass really overlap (+2.2 % step throughput, profiles/r02_ab_wgrad_coresidency.txt)
+#endif
 template <int KS, int NB, int COB, int MT, bool TWO>
-__global__ void __launch_bounds__(kWgThreads, 1) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
+__global__ void __launch_bounds__(kWgThreads, HPFG_WG_MINBLOCKS) tc_wgrad_kernel(const __grid_constant__ CUtensorMap tmX,
                                                                  const __grid_constant__ CUtensorMap tmD,
                                                                  const __grid_constant__ CUtensorMap tmR, const WgParams P) {
     pdl_launch_dependents();
