@@ -742,7 +742,12 @@ extern "C" int hpfg_unet_plan_create(int batch, int in_channels, int num_classes
     p->ws_bytes = total;
     carve(p, p->ws, total);
     for (int b = 0; b < kNumBuckets; ++b) HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->bucket_ev[b], cudaEventDisableTiming));
-    HPFG_CUDA_CHECK(cudaStreamCreateWithFlags(&p->side, cudaStreamNonBlocking));
+    {   // the weight-gradient stream; HPFG_SIDE_PRIO=1 (profiles/ A/B) creates it at the highest priority
+        int least = 0, greatest = 0;
+        HPFG_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+        const char *e = getenv("HPFG_SIDE_PRIO");
+        HPFG_CUDA_CHECK(cudaStreamCreateWithPriority(&p->side, cudaStreamNonBlocking, (e && e[0] == '1') ? greatest : least));
+    }
     HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming));
     for (int k = 0; k < 2; ++k) HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_done[k], cudaEventDisableTiming));
     for (int k = 0; k < 4; ++k) HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_slot[k], cudaEventDisableTiming));

@@ -150,7 +150,7 @@ class _StepBase:
             if not any(m is q for q in models):
                 models.append(m)
         for m in models:
-            m.ensure_flat()
+            m.ensure_flat(quick=True)
         ptrs = tuple((m.flat_params.data_ptr(), m.bn_running.data_ptr(), m.bn_counters.data_ptr(), id(m._plans)) for m in models)
         ptrs += tuple(t.data_ptr() for t in self._state_tensors())
         # (the dropout seed is a by-value launch argument: a re-seeded generator needs a new capture)
@@ -316,7 +316,7 @@ class _StepBase:
         return self.consistency * sigmoid_rampup(self.cur_itrs // 150, self.consistency_rampup)
 
     def _forward(self, model, x, save, out=None):
-        model.ensure_flat()
+        model.ensure_flat(quick=True)
         plan = model._acquire_plan(x, need_grad=save)
         self._set_forward_share(plan, self.share_forward and not getattr(self, "serialize", False))
         logits = model._run_forward(plan, x, save=save, out=out)

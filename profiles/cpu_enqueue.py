@@ -10,6 +10,7 @@ torch.manual_seed(0)
 student = hb.UNet(1, 4, precision="bf16").to(dev)
 teacher = copy.deepcopy(student)
 step = hb.MeanTeacherStep(student, teacher)
+step.enable_graph(bool(int(os.environ.get("GRAPH", "1"))))
 x = torch.rand(32, 1, 224, 224, device=dev)
 y = torch.randint(0, 4, (8, 224, 224), device=dev)
 for _ in range(5):
