@@ -299,11 +299,12 @@ int tc_dgrad(hpfg_unet_plan *p, int conv, const void *dout, void *din, bool *don
 }
 
 int tc_wgrad(hpfg_unet_plan *p, int conv, const void *in, LoadXform xf, const void *dout, float *dw_oihw, float *dbias,
-             int accumulate, bool *done, cudaStream_t s, const TcBwdFuse *fuse) {
+             int accumulate, bool *done, cudaStream_t s, const TcBwdFuse *fuse, const TcWgradStreams *ws) {
     const ConvLayer &cv = p->d.convs[conv];
     *done = false;
-    HPFG_RETURN_IF(tc_wgrad_run(cv.ks, p->N, cv.H, cv.W, pad16(cv.cin), pad16(cv.cout), cv.cin, cv.cout, in, xf, dout, p->wscratch,
-                                p->wscratch_floats, dw_oihw, dbias, accumulate, s, fuse));
+    float *scratch = (ws && ws->scratch) ? ws->scratch : p->wscratch;
+    HPFG_RETURN_IF(tc_wgrad_run(cv.ks, p->N, cv.H, cv.W, pad16(cv.cin), pad16(cv.cout), cv.cin, cv.cout, in, xf, dout, scratch,
+                                p->wscratch_floats, dw_oihw, dbias, accumulate, s, fuse, ws));
     *done = true;
     return HPFG_OK;
 }

@@ -32,13 +32,21 @@ struct TcBwdFuse {
 };
 int tc_dgrad(hpfg_unet_plan *p, int conv, const void *dout, void *din, bool *done, cudaStream_t s, const TcBwdFuse *fuse = nullptr,
              float *stats = nullptr, int *P = nullptr);
+// Optional stream split of a weight gradient: partials into `scratch`, `ev_partials` recorded behind the tensor-core kernel on its
+// stream, the fixed-order reduction on `reduce_stream` (waits for ev_partials, records ev_reduced).  Default: everything on one stream.
+struct TcWgradStreams {
+    float *scratch = nullptr;
+    cudaStream_t reduce_stream = nullptr;
+    cudaEvent_t ev_partials = nullptr, ev_reduced = nullptr;
+};
 int tc_wgrad(hpfg_unet_plan *p, int conv, const void *in, LoadXform xf, const void *dout, float *dw_oihw, float *dbias,
-             int accumulate, bool *done, cudaStream_t s, const TcBwdFuse *fuse = nullptr);
+             int accumulate, bool *done, cudaStream_t s, const TcBwdFuse *fuse = nullptr, const TcWgradStreams *ws = nullptr);
 
 // tensor-core wgrad (wgrad_tc.cu)
 int64_t tc_wgrad_scratch_floats(int N, int H, int W, int Cin, int Cout, int KS);
 int tc_wgrad_run(int ks, int N, int H, int W, int Cin, int Cout, int cin_real, int cout_real, const void *x, LoadXform xf, const void *dy, float *scratch,
-                 int64_t scratch_floats, float *dw_oihw, float *dbias, int accumulate, cudaStream_t s, const TcBwdFuse *fuse = nullptr);
+                 int64_t scratch_floats, float *dw_oihw, float *dbias, int accumulate, cudaStream_t s, const TcBwdFuse *fuse = nullptr,
+                 const TcWgradStreams *ws = nullptr);
 
 // fp32 NCHW [N,C,H,W] -> bf16 NHWC with the channel count padded to 16 (zeros): network input and dlogits
 int pad_to_nhwc16(const float *src_nchw, void *dst_bf16_nhwc16, int N, int C, int H, int W, cudaStream_t s);

@@ -168,6 +168,7 @@ static void carve(hpfg_unet_plan *p, char *base, int64_t &total) {
     }
     p->wscratch_floats = wf;
     c.take(p->wscratch, wf * 4);
+    if (p->precision == HPFG_PREC_BF16) c.take(p->wscratch2, wf * 4);
     int64_t bnf = 0;
     for (auto &b : p->d.bns) bnf += 8 * (int64_t)align_up(b.C, 64);
     c.take(p->bnmem, bnf * 4);
@@ -479,6 +480,8 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
     // dgrad(layer) both consume the layer's raw gradient and are independent of each other.  The raw gradient lives
     // in one of two alternating buffers; before a buffer is rewritten the main stream waits for the wgrad that read it.
     cudaStream_t side = g_prof_on ? s : p->side;      // per-category timing (bench.py's roofline leg) wants serialized kernels
+    p->wg_count = 0;
+    p->reduced_pending[0] = p->reduced_pending[1] = false;      // (events of an earlier pass / capture are never waited on)
     void *dr[2] = {p->g[1], p->g[4]};
     bool dr_busy[2] = {false, false};
     int bi = 1;
@@ -507,7 +510,22 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
         ready_marked = false;
         HPFG_CUDA_CHECK(cudaStreamWaitEvent(side, p->ev_ready, 0));
         bool done = false;
-        if (tc) HPFG_RETURN_IF(tc_wgrad(p, ci, in, xf, dout, grads + cv.w_off, grads + cv.b_off, acc, &done, side));
+        if (tc) {
+            // split-K partials go to one of two scratch halves; the fixed-order reduction runs on a third stream, so the next
+            // weight gradient does not queue behind it
+            static const bool split = !(getenv("HPFG_WG_REDUCE_STREAM") && getenv("HPFG_WG_REDUCE_STREAM")[0] == '0');   // A/B switch (profiles/)
+            TcWgradStreams ws;
+            const int k = p->wg_count++ & 1;
+            if (split && !g_prof_on) {
+                ws.scratch = k ? p->wscratch2 : p->wscratch;
+                ws.reduce_stream = p->side2;
+                ws.ev_partials = p->ev_partials[k];
+                ws.ev_reduced = p->ev_reduced[k];
+                if (p->reduced_pending[k]) HPFG_CUDA_CHECK(cudaStreamWaitEvent(side, p->ev_reduced[k], 0));   // reduce(n-2) has read this half
+                p->reduced_pending[k] = true;
+            }
+            HPFG_RETURN_IF(tc_wgrad(p, ci, in, xf, dout, grads + cv.w_off, grads + cv.b_off, acc, &done, side, nullptr, &ws));
+        }
         if (!done)
             HPFG_RETURN_IF((conv_ref_wgrad<T, T>(nhwc_view(in, cv.H, cv.W, cv.cin), nhwc_view(dout, cv.H, cv.W, cv.cout), N, cv.H,
                                                  cv.W, cv.cin, cv.cout, cv.ks, xf, p->wscratch, p->wscratch_floats,
@@ -519,9 +537,13 @@ static int backward_impl(hpfg_unet_plan *p, const float *params, const float *dl
             }
         return HPFG_OK;
     };
-    auto join_side = [&]() -> int {     // main stream waits for every weight gradient enqueued so far
+    auto join_side = [&]() -> int {     // main stream waits for every weight gradient (and its reduction) enqueued so far
         HPFG_CUDA_CHECK(cudaEventRecord(p->ev_join, side));
         HPFG_CUDA_CHECK(cudaStreamWaitEvent(s, p->ev_join, 0));
+        for (int k = 0; k < 2; ++k)
+            if (p->reduced_pending[k]) {
+                HPFG_CUDA_CHECK(cudaStreamWaitEvent(s, p->ev_reduced[k], 0));
+            }
         return HPFG_OK;
     };
     // data gradient of conv `ci`: din[.., cin] = conv(dout[.., cout], flipped weights)
@@ -751,6 +773,11 @@ extern "C" int hpfg_unet_plan_create(int batch, int in_channels, int num_classes
     HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_ready, cudaEventDisableTiming));
     for (int k = 0; k < 2; ++k) HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_done[k], cudaEventDisableTiming));
     for (int k = 0; k < 4; ++k) HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_slot[k], cudaEventDisableTiming));
+    HPFG_CUDA_CHECK(cudaStreamCreateWithFlags(&p->side2, cudaStreamNonBlocking));
+    for (int k = 0; k < 2; ++k) {
+        HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_partials[k], cudaEventDisableTiming));
+        HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_reduced[k], cudaEventDisableTiming));
+    }
     HPFG_CUDA_CHECK(cudaEventCreateWithFlags(&p->ev_join, cudaEventDisableTiming));
     if (precision == HPFG_PREC_BF16) {
         const int rc = tc_plan_init(p);
@@ -776,6 +803,11 @@ extern "C" int hpfg_unet_plan_destroy(hpfg_unet_plan_t p) {
     for (int k = 0; k < 4; ++k)
         if (p->ev_slot[k]) cudaEventDestroy(p->ev_slot[k]);
     if (p->side) cudaStreamDestroy(p->side);
+    if (p->side2) cudaStreamDestroy(p->side2);
+    for (int k = 0; k < 2; ++k) {
+        if (p->ev_partials[k]) cudaEventDestroy(p->ev_partials[k]);
+        if (p->ev_reduced[k]) cudaEventDestroy(p->ev_reduced[k]);
+    }
     if (p->ws) cudaFree(p->ws);
     delete p;
     return HPFG_OK;

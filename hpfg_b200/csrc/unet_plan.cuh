@@ -63,7 +63,8 @@ struct hpfg_unet_plan {
     uint32_t *dropbits[5] = {};
     float *stats = nullptr;           // BN statistics partials
     int64_t stats_floats = 0;
-    float *wscratch = nullptr;        // wgrad split partials
+    float *wscratch = nullptr;        // wgrad split partials (bf16 plans: two halves, used alternately)
+    float *wscratch2 = nullptr;
     int64_t wscratch_floats = 0;
     float *bnmem = nullptr;           // BnState arrays
     bool saved = false, saved_dropout = false;
@@ -75,6 +76,10 @@ struct hpfg_unet_plan {
     cudaEvent_t bucket_ev[hpfg::kNumBuckets] = {};
     // weight gradients run on a side stream, concurrently with the data-gradient chain of the same layer
     cudaStream_t side = nullptr;
+    cudaStream_t side2 = nullptr;     // the split-K reductions of the weight gradients (tiny kernels: off the weight-gradient stream's chain)
+    cudaEvent_t ev_partials[2] = {}, ev_reduced[2] = {};
+    bool reduced_pending[2] = {false, false};
+    int wg_count = 0;
     cudaEvent_t ev_ready = nullptr, ev_join = nullptr, ev_done[2] = {}, ev_slot[4] = {};
     void *tc = nullptr;               // tensor-core path state (conv_tc.cu), bf16 plans only
 };

@@ -437,7 +437,8 @@ static int wg_dispatch(int NB, int COB, int MT, bool two, const CUtensorMap &mx,
 }
 
 int tc_wgrad_run(int ks, int N, int H, int W, int Cin, int Cout, int cin_real, int cout_real, const void *x, LoadXform xf, const void *dy, float *scratch,
-                 int64_t scratch_floats, float *dw_oihw, float *dbias, int accumulate, cudaStream_t s, const TcBwdFuse *fuse) {
+                 int64_t scratch_floats, float *dw_oihw, float *dbias, int accumulate, cudaStream_t s, const TcBwdFuse *fuse,
+                 const TcWgradStreams *ws) {
     ProfScope _prof(PROF_WGRAD_TC, s);
     int NB, COB, MT;
     WgParams P{};
@@ -480,6 +481,15 @@ int tc_wgrad_run(int ks, int N, int H, int W, int Cin, int Cout, int cin_real, i
     }
     const int64_t per = (int64_t)ks * ks * Cin * Cout + Cout;
     const int blocks = (int)((per + 31) / 32);
+    if (ws && ws->reduce_stream) {     // reduction on its own stream, ordered by events (plain launch: its predecessor is on another stream)
+        HPFG_CUDA_CHECK(cudaEventRecord(ws->ev_partials, s));
+        HPFG_CUDA_CHECK(cudaStreamWaitEvent(ws->reduce_stream, ws->ev_partials, 0));
+        HPFG_CUDA_CHECK(launch_plain(tc_wgrad_reduce_kernel, blocks, 256, 0, ws->reduce_stream, (const float *)scratch, P.S, Cin, Cout, ks * ks, cin_real,
+                                     cout_real, dw_oihw, dbias, accumulate));
+        HPFG_LAUNCH_CHECK();
+        HPFG_CUDA_CHECK(cudaEventRecord(ws->ev_reduced, ws->reduce_stream));
+        return HPFG_OK;
+    }
     HPFG_CUDA_CHECK(launch_pdl(tc_wgrad_reduce_kernel, blocks, 256, 0, s, scratch, P.S, Cin, Cout, ks * ks, cin_real, cout_real, dw_oihw, dbias, accumulate));
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;
