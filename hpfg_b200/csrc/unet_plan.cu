@@ -204,11 +204,22 @@ static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_runnin
         for (auto &cv : d.convs)
             HPFG_RETURN_IF(pack_weights_ref(params + cv.w_off, cv.wf, cv.wd, cv.cin, cv.cout, cv.ks, s));
     if (tc) HPFG_RETURN_IF(tc_pack_all(p, params, s, save != 0 && training != 0));
-    if (use_drop) {      // all five encoder keep-masks in one launch
+    bool drop_on_side = false;
+    if (use_drop) {      // all five encoder keep-masks in one launch, on the plan's side stream: nothing reads them before the second
+                         // convolution of in_conv, so the 30 us launch overlaps weight packing, input padding and the first convolution
         int hs[5], wsz[5], cs[5];
         float ps[5];
         for (int l = 0; l < 5; ++l) { hs[l] = H >> l; wsz[l] = W >> l; cs[l] = kFt[l]; ps[l] = kEncDropout[l]; }
-        HPFG_RETURN_IF(dropout_bits_multi(5, p->dropbits, masks, N, hs, wsz, cs, ps, seed, offset, s, offset_dev));
+        static const bool side_ok = !(getenv("HPFG_DROP_SIDE") && getenv("HPFG_DROP_SIDE")[0] == '0');      // A/B switch (profiles/)
+        drop_on_side = side_ok && !g_prof_on;
+        cudaStream_t ds = drop_on_side ? p->side : s;
+        if (drop_on_side) {
+            HPFG_CUDA_CHECK(cudaEventRecord(p->ev_ready, s));
+            HPFG_CUDA_CHECK(cudaStreamWaitEvent(p->side, p->ev_ready, 0));
+            // (the input's bf16 NHWC16 copy on this stream as well measured SLOWER: 3.18-3.23 vs 3.14 ms, profiles/README.md)
+        }
+        HPFG_RETURN_IF(dropout_bits_multi(5, p->dropbits, masks, N, hs, wsz, cs, ps, seed, offset, ds, offset_dev));
+        if (drop_on_side) HPFG_CUDA_CHECK(cudaEventRecord(p->ev_join, p->side));
     }
 
     // conv + (train: statistics -> finalize | eval: running-stat affine)
@@ -255,6 +266,7 @@ static int forward_impl(hpfg_unet_plan *p, const float *params, float *bn_runnin
             HPFG_RETURN_IF(conv_bn(c0, nchw_view(const_cast<float *>(x), p->in_ch, H, W), true, none));
         else
             HPFG_RETURN_IF(conv_bn(c0, nhwc_view(p->pooled[l], h, w, kFt[l - 1]), false, none));
+        if (l == 0 && drop_on_side) HPFG_CUDA_CHECK(cudaStreamWaitEvent(s, p->ev_join, 0));     // keep-masks ready
         HPFG_RETURN_IF(conv_bn(c1, nhwc_view(d.bns[c0].raw, h, w, kFt[l]), false,
                                xf_of(c0, use_drop ? p->dropbits[l] : nullptr, kEncDropout[l])));
         if (l < 4)
