@@ -67,6 +67,11 @@ SIGNATURES = {
     "hpfg_argmax_labels": (c_int, [c_vp, c_int, c_int, c_int, c_int, c_vp, c_vp, c_vp]),
     "hpfg_dice_loss": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_int, c_int, ctypes.POINTER(c_f), c_vp, c_vp, c_vp,
                                c_vp]),
+    "hpfg_neck_forward": (c_int, [c_vp] + [c_int] * 7 + [ctypes.POINTER(c_vp)] + [c_vp] * 5),
+    "hpfg_neck_backward": (c_int, [c_vp, c_vp] + [c_int] * 7 + [ctypes.POINTER(c_vp), c_vp, c_vp, ctypes.POINTER(c_vp), c_vp, c_vp,
+                                                               c_vp]),
+    "hpfg_dense_contrastive_workspace_floats": (c_i64, [c_int, c_int, c_int]),
+    "hpfg_dense_contrastive": (c_int, [c_vp, c_vp, c_int, c_int, c_int, c_f, c_vp, c_vp, c_vp, c_vp]),
     "hpfg_ema_update": (c_int, [c_vp, c_vp, c_i64, c_f, c_vp]),
     "hpfg_sgd_momentum": (c_int, [c_vp, c_vp, c_vp, c_i64, c_f, c_f, c_f, c_f, c_int, c_vp]),
     "hpfg_sgd_momentum_ema": (c_int, [c_vp, c_vp, c_vp, c_vp, c_i64, c_f, c_f, c_f, c_f, c_int, c_f, c_vp]),

@@ -306,10 +306,37 @@ def argmax_labels(logits, dtype=torch.int64):
     return out
 
 
+class _ContrastFn(torch.autograd.Function):
+    """Dense_Loss.contrastive_loss on ``hpfg_dense_contrastive`` (csrc/neck.cu): value, and the gradient wrt out_1 computed by
+    the same call when out_1 needs it."""
+
+    @staticmethod
+    def forward(ctx, out_1, out_2, temperature):
+        L.require_cuda(out_1, "Dense_Loss input")
+        L.require_cuda(out_2, "Dense_Loss input")
+        a, b = out_1.contiguous().float(), out_2.detach().contiguous().float()
+        batch, dim = a.shape[0], a.shape[1]
+        positions = a[0, 0].numel()
+        lib = L.lib()
+        work = torch.empty(lib.hpfg_dense_contrastive_workspace_floats(batch, dim, positions), device=a.device, dtype=torch.float32)
+        loss = torch.empty((), device=a.device, dtype=torch.float32)
+        d_a = torch.empty_like(a) if ctx.needs_input_grad[0] else None
+        L.check(lib.hpfg_dense_contrastive(L.ptr(a), L.ptr(b), batch, dim, positions, float(temperature), L.ptr(loss), L.ptr(d_a),
+                                           L.ptr(work), L.stream_ptr(a.device)), "hpfg_dense_contrastive")
+        ctx.save_for_backward(d_a)
+        return loss
+
+    @staticmethod
+    def backward(ctx, g):
+        (d_a,) = ctx.saved_tensors
+        return (d_a * g if d_a is not None else None), None, None
+
+
 class Dense_Loss(nn.Module):
     """``Dense_Loss(batch_size, device, temperature)(x, y)`` (utils/loss/dense_loss.py:5-40): SimCLR-style contrastive loss
-    on the (global vector, dense map) pairs the projection necks return.  A [2B, 2B] similarity matrix (B = 32): plain
-    library GEMM + elementwise work of a few kFLOP, kept in torch like the necks themselves."""
+    on the (global vector, dense map) pairs the projection necks return; ``y`` is the detached teacher side.  Each
+    ``contrastive_loss`` is one ``hpfg_dense_contrastive`` call (normalise, [2B,2B] similarities, masked row sums, loss and
+    the gradient wrt the first argument); CUDA tensors only."""
 
     def __init__(self, batch_size=32, device=None, temperature=0.7):
         super().__init__()
@@ -317,18 +344,13 @@ class Dense_Loss(nn.Module):
 
     def contrastive_loss(self, out_1, out_2):
         """-log(exp(s_i,pos / t) / sum_{j != i} exp(s_ij / t)) averaged over the 2B rows, s = <z_i, z_j> of the
-        channel-normalised, flattened features (utils/loss/dense_loss.py:18-34)."""
-        a = torch.nn.functional.normalize(out_1, dim=1).flatten(1)
-        b = torch.nn.functional.normalize(out_2, dim=1).flatten(1)
-        z = torch.cat([a, b], dim=0)
-        rows = z.shape[0]
-        if rows != 2 * self.batch_size:        # the reference builds its mask from the constructor's batch size
-            raise RuntimeError("Dense_Loss was built for batch %d, got %d" % (self.batch_size, rows // 2))
-        sim = torch.exp(z @ z.t() / self.temperature)
-        off_diag = ~torch.eye(rows, dtype=torch.bool, device=sim.device)
-        denom = (sim * off_diag).sum(dim=-1)          # the diagonal is the largest entry: mask it, never subtract it
-        pos = torch.exp((a * b).sum(dim=-1) / self.temperature).repeat(2)
-        return (-torch.log(pos / denom)).mean()
+        channel-normalised, flattened features (utils/loss/dense_loss.py:18-34); out_1, out_2: [B,D] or [B,D,S]."""
+        if out_1.shape != out_2.shape or out_1.dim() < 2:
+            raise RuntimeError("Dense_Loss: expected two [B,D(,S)] tensors of one shape, got %s and %s"
+                               % (tuple(out_1.shape), tuple(out_2.shape)))
+        if out_1.shape[0] != self.batch_size:        # the reference builds its mask from the constructor's batch size
+            raise RuntimeError("Dense_Loss was built for batch %d, got %d" % (self.batch_size, out_1.shape[0]))
+        return _ContrastFn.apply(out_1, out_2, self.temperature)
 
     def forward(self, x, y):
         x1, x2 = x

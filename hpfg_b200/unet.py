@@ -338,10 +338,49 @@ class UNet(nn.Module):
         return self._run_forward(self._own_machine(self._acquire_plan(x, False)), x, save=False)
 
 
+class _NeckFunction(torch.autograd.Function):
+    """projection_conv.forward / its adjoint on ``hpfg_neck_forward`` / ``hpfg_neck_backward`` (csrc/neck.cu)."""
+
+    @staticmethod
+    def forward(ctx, x, s, *params):
+        n, c, h, w = x.shape
+        hid, out = params[0].shape[0], params[2].shape[0]
+        rows = n * (1 + s * s)
+        dev = x.device
+        pooled = torch.empty((rows, c), device=dev, dtype=torch.float32)
+        hidden = torch.empty((rows, hid), device=dev, dtype=torch.float32)
+        out_global = torch.empty((n, out), device=dev, dtype=torch.float32)
+        out_dense = torch.empty((n, out, s * s), device=dev, dtype=torch.float32)
+        ps = [p.detach().contiguous() for p in params]
+        L.check(L.lib().hpfg_neck_forward(L.ptr(x), n, c, h, w, s, hid, out, (ctypes.c_void_p * 8)(*[p.data_ptr() for p in ps]),
+                                          L.ptr(pooled), L.ptr(hidden), L.ptr(out_global), L.ptr(out_dense), L.stream_ptr(dev)),
+                "hpfg_neck_forward")
+        ctx.save_for_backward(pooled, hidden, *ps)
+        ctx.geom = (n, c, h, w, s, hid, out)
+        return out_global, out_dense
+
+    @staticmethod
+    def backward(ctx, d_global, d_dense):
+        pooled, hidden, *ps = ctx.saved_tensors
+        n, c, h, w, s, hid, out = ctx.geom
+        dev = pooled.device
+        rows = n * (1 + s * s)
+        grads = [torch.empty_like(p) for p in ps]
+        dx = torch.empty((n, c, h, w), device=dev, dtype=torch.float32) if ctx.needs_input_grad[0] else None
+        scratch = torch.empty(n * s * s * out + rows * (hid + c), device=dev, dtype=torch.float32)
+        d_global, d_dense = d_global.contiguous().float(), d_dense.contiguous().float()
+        L.check(L.lib().hpfg_neck_backward(L.ptr(d_global), L.ptr(d_dense), n, c, h, w, s,
+                                           hid, out, (ctypes.c_void_p * 8)(*[p.data_ptr() for p in ps]), L.ptr(pooled), L.ptr(hidden),
+                                           (ctypes.c_void_p * 8)(*[g.data_ptr() for g in grads]), L.ptr(dx), L.ptr(scratch),
+                                           L.stream_ptr(dev)), "hpfg_neck_backward")
+        return (dx, None) + tuple(grads)
+
+
 class projection_conv(nn.Module):
-    """The DenseCL-style neck of model/unet.py:120-152 (same parameter names and shapes).  A global-average-pool +
-    fc-relu-fc branch and an adaptive-pool(s x s) + 1x1conv-relu-1x1conv branch on a [N, C, <=14, <=14] map: a few MFLOP
-    of plain library GEMMs, left to torch; the U-Net under it is what runs on the hand-written kernels."""
+    """The DenseCL-style neck of model/unet.py:120-152 (same constructor, parameter names and shapes): a global-average-pool +
+    fc-relu-fc branch and an adaptive-pool(s x s) + 1x1conv-relu-1x1conv branch, returned as ([N,out_dim], [N,out_dim,s*s]).
+    The Linear / Conv2d submodules only hold the parameters; ``forward`` and its gradients run on the library's neck kernels
+    (pooling of both branches in one pass, fp32 GEMMs with bias / ReLU epilogues), so there is no CPU path."""
 
     def __init__(self, in_dim, hid_dim=2048, out_dim=128, s=4):
         super().__init__()
@@ -351,11 +390,21 @@ class projection_conv(nn.Module):
         self.mlp_conv = nn.Sequential(nn.Conv2d(in_dim, hid_dim, 1), nn.ReLU(inplace=True), nn.Conv2d(hid_dim, out_dim, 1))
         self.pool = nn.AdaptiveAvgPool2d((s, s)) if self.is_s else None
 
+    def _param_list(self):
+        return [self.mlp[0].weight, self.mlp[0].bias, self.mlp[2].weight, self.mlp[2].bias,
+                self.mlp_conv[0].weight, self.mlp_conv[0].bias, self.mlp_conv[2].weight, self.mlp_conv[2].bias]
+
     def forward(self, x):
-        pooled = self.pool(x) if self.is_s else x                      # dense branch input: [N, C, s, s]
-        global_vec = self.mlp(self.avgpool(x).flatten(1))              # [N, out_dim]
-        dense_map = self.mlp_conv(pooled).flatten(2)                   # [N, out_dim, s*s]
-        return global_vec, dense_map
+        L.require_cuda(x, "projection_conv input")
+        if x.dim() != 4 or x.shape[1] != self.mlp[0].in_features:
+            raise ValueError("expected input [N,%d,H,W], got %s" % (self.mlp[0].in_features, tuple(x.shape)))
+        if not self.is_s:
+            raise L.HpfgError("projection_conv(s=0) (dense branch without pooling) is not built: UNet_Plus always uses s=4 "
+                              "(model/unet.py:192-193)")
+        params = self._param_list()
+        if any(p.device != x.device or p.dtype != torch.float32 for p in params):
+            raise L.HpfgError("projection_conv: parameters must be fp32 on %s" % (x.device,))
+        return _NeckFunction.apply(x.contiguous().float(), int(self.is_s), *params)
 
 
 class UNet_Plus(UNet):

@@ -262,6 +262,30 @@ int hpfg_dice_loss(const float *inputs, const int64_t *target, int n, int num_cl
                    int softmax, const float *class_weights, float *dinputs, float *scalars_out, void *workspace,
                    void *stream);
 
+/* ---- UNet_Plus projection necks and Dense_Loss ----------------------------------------------------
+ * projection_conv.forward (model/unet.py:140-152) on x [n,channels,H,W] fp32 NCHW:
+ *   out_global [n,out]     = mlp(AdaptiveAvgPool2d((1,1))(x))            (Linear -> ReLU -> Linear)
+ *   out_dense  [n,out,s*s] = mlp_conv(AdaptiveAvgPool2d((s,s))(x))       (1x1 conv -> ReLU -> 1x1 conv), s >= 1.
+ * params[8]: mlp.0.weight [hid,channels], mlp.0.bias, mlp.2.weight [out,hid], mlp.2.bias, mlp_conv.0.weight
+ * [hid,channels(,1,1)], mlp_conv.0.bias, mlp_conv.2.weight [out,hid(,1,1)], mlp_conv.2.bias -- the module's registration
+ * order.  pooled [n*(1+s*s), channels] and hidden [n*(1+s*s), hid] are written here and read by hpfg_neck_backward
+ * (rows 0..n-1: the global branch; row n + image*s*s + i*s + j: bin (i,j)). */
+int hpfg_neck_forward(const float *x, int n, int channels, int height, int width, int s, int hid, int out,
+                      const float *const *params, float *pooled, float *hidden, float *out_global, float *out_dense,
+                      void *stream);
+/* Adjoint of hpfg_neck_forward: d_global [n,out], d_dense [n,out,s*s] -> grads[8] (same order and shapes as params,
+ * overwritten) and, when dx != NULL, dx [n,channels,H,W] (overwritten).  scratch: n*s*s*out + n*(1+s*s)*(hid+channels)
+ * floats. */
+int hpfg_neck_backward(const float *d_global, const float *d_dense, int n, int channels, int height, int width, int s,
+                       int hid, int out, const float *const *params, const float *pooled, const float *hidden,
+                       float *const *grads, float *dx, float *scratch, void *stream);
+/* Dense_Loss.contrastive_loss (utils/loss/dense_loss.py:18-34) with batch_size = batch: out1, out2 [batch,dim,positions]
+ * fp32 (positions = 1 for the global vectors); loss[1]; d_out1 (optional) = d loss / d out1 (out2 is the detached teacher
+ * side, :38-39).  workspace: hpfg_dense_contrastive_workspace_floats(batch, dim, positions) floats. */
+int64_t hpfg_dense_contrastive_workspace_floats(int batch, int dim, int positions);
+int hpfg_dense_contrastive(const float *out1, const float *out2, int batch, int dim, int positions, float temperature,
+                           float *loss, float *d_out1, float *workspace, void *stream);
+
 /* ---- optimiser-side passes over the flat buffers --------------------------------------------------- */
 /* update_ema_variables (utils/utils.py:82-86): ema <- alpha*ema + (1-alpha)*param, alpha already clamped. */
 int hpfg_ema_update(float *ema, const float *param, int64_t n, float alpha, void *stream);

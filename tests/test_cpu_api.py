@@ -135,16 +135,19 @@ def test_graph_replay_policy_host_logic():
     assert mt._dyn_scalars(0.99)[0] == pytest.approx(hb.medical_lr(2, 0.01, 30000))
 
 
-def test_dense_loss_and_necks_against_oracle():
-    """The torch-side pieces of UNet_Plus (projection necks, Dense_Loss) against the oracle restatement on CPU."""
+def test_necks_and_dense_loss_have_no_cpu_path():
+    """The projection necks and Dense_Loss run on the library's kernels (csrc/neck.cu): the modules keep the reference's
+    parameter names / shapes, and CPU tensors raise instead of falling back to torch (parity with the oracle: GPU tests)."""
     torch.manual_seed(8)
     m = hb.UNet_Plus(1, 4)
-    st = {k: v.detach().clone() for k, v in m.state_dict().items()}
-    f = torch.randn(3, 256, 4, 4)
-    for prefix, neck, inp in (("dense_projection_high", m.dense_projection_high, f),
-                              ("dense_projection_head", m.dense_projection_head, torch.randn(3, 4, 64, 64))):
-        (a1, a2), (b1, b2) = neck(inp), oracle.projection_conv(st, prefix, inp)
-        assert torch.allclose(a1, b1, atol=1e-6) and torch.allclose(a2, b2, atol=1e-6) and a2.shape == (3, 128, 16)
+    assert [(n, tuple(p.shape)) for n, p in m.named_parameters()][82:] == oracle.unet_plus_neck_spec(4)
+    with pytest.raises(L.HpfgError):
+        m.dense_projection_high(torch.randn(3, 256, 4, 4))
+    with pytest.raises(L.HpfgError):
+        hb.projection_conv(4, hid_dim=8, s=0)(torch.randn(1, 4, 8, 8))
     x = (torch.randn(3, 128), torch.randn(3, 128, 16))
     y = (torch.randn(3, 128), torch.randn(3, 128, 16))
-    assert hb.Dense_Loss(batch_size=3)(x, y).item() == pytest.approx(oracle.dense_loss(x, y).item(), rel=1e-6)
+    with pytest.raises(L.HpfgError):
+        hb.Dense_Loss(batch_size=3)(x, y)
+    with pytest.raises(RuntimeError):
+        hb.Dense_Loss(batch_size=5)(x, y)                  # the reference's mask is built for the constructor's batch size
