@@ -48,10 +48,10 @@ METRICS = {"mt": "UNet SSL train images/sec @224x224 (Mean-Teacher step)", "cps"
            "uamt": "UNet SSL train images/sec @224x224 (UAMT step, T=8)"}
 # dram__bytes_read.sum + dram__bytes_write.sum from ncu (see the named profile); None until measured for the current kernels
 TOP_KERNEL_DRAM_BYTES = 58.16e6      # one launch of the 3x3 16->16 @224 fprop (profiles/r01_ncu_prof_fprop16_final_raw.txt)
-LOSS_DRAM_BYTES = 9657856 + 2048 + 48247552 + 169216      # reduce read+write, gradient read+write (profiles/r01_ncu_loss_kernels.csv)
-CONV_FAMILY_DRAM_BYTES = 1710.8e6    # all 68 tc_conv_kernel launches of one mt_acdc step (25 MB per launch on average)
+LOSS_DRAM_BYTES = 49748736 + 5297408      # dram read + write of the one-launch Mean-Teacher loss kernel (profiles/r02b_loss_mt_one_ncu.txt)
+CONV_FAMILY_DRAM_BYTES = 1712.0e6    # all 68 tc_conv_kernel launches of one mt_acdc step (25 MB per launch on average)
 CONV_FAMILY_DRAM_SOURCE = ("ncu dram__bytes_read.sum + dram__bytes_write.sum over the 68 tc_conv_kernel launches of one steady-state step, "
-                           "profiles/r02_launch_summary.txt (whole step: 5.66 GB of DRAM traffic)")
+                           "profiles/r02b_launch_summary.txt (whole step: 5.65 GB of DRAM traffic)")
 
 
 def flops_per_step(c):
@@ -501,11 +501,12 @@ def run_gpu(args):
                 "clocks": sampler.summary() if sampler else None}
         if c["kind"] == "mt":
             line["roofline_loss"] = _hbm_roofline(
-                "loss_reduce_kernel<MT> + loss_grad_kernel (fused SSL loss value + dlogits, one call per step)",
+                "loss_mt_one_kernel (fused SSL loss value + dlogits in ONE launch per step: labeled Dice/CE sums | unlabeled consistency "
+                "gradient | grid barrier | labeled gradient)",
                 (n_img * c["n_cls"] * H * W * 4.0 * 2 + c["n_u"] * c["n_cls"] * H * W * 4.0 + c["n_l"] * H * W * 8.0),
                 prof["ssl_loss"], pk, "SURVEY 8d: student logits read + teacher logits read + int64 labels read + dlogits written, each once",
                 traffic=LOSS_DRAM_BYTES if args.config == "mt_acdc" else None,
-                traffic_source="ncu, profiles/r01_ncu_loss_kernels.csv (dram read+write of reduce + gradient, L2 flushed before the call)")
+                traffic_source="ncu --set full, profiles/r02b_loss_mt_one_ncu.txt (dram read+write of the launch, L2 flushed before the call: the dlogits mostly stay in L2)")
         if dp_check is not None:
             line["dp_check"] = dp_check
         if cpu is not None:

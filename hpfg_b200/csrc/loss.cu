@@ -16,6 +16,10 @@
 #include "common.cuh"
 #include <cstdlib>
 
+#ifndef HPFG_LOSS_MT_MINBLOCKS
+#define HPFG_LOSS_MT_MINBLOCKS 3
+#endif
+
 namespace hpfg {
 
 constexpr int kMaxC = 8;
@@ -361,9 +365,13 @@ __device__ __forceinline__ void store4(float *base, int64_t hw, const float (&g)
         *reinterpret_cast<float4 *>(base + (int64_t)c * hw) = make_float4(g[c][0], g[c][1], g[c][2], g[c][3]);
 }
 
-template <int C>
-__global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
+// MODE: a compile-time copy of A.mode for the modes that get their own instantiation (Mean-Teacher: the headline step), -1 = read
+// A.mode at run time.  Same expressions either way; the specialised kernel drops the CPS / S4CV / UAMT / ICT paths and their
+// registers (128 -> see -Xptxas -v), so more CTAs are resident per SM and more loads are in flight.
+template <int C, int MODE>
+__global__ void __launch_bounds__(256, MODE == HPFG_LOSS_MT ? HPFG_LOSS_MT_MINBLOCKS : 1) loss_grad_kernel(LossArgs A) {
     pdl_prologue();
+    if (MODE >= 0) A.mode = MODE;
     if (A.cons_weight_dev) A.cons_weight = *A.cons_weight_dev;
     if (A.cons_weight2_dev) A.cons_weight2 = *A.cons_weight2_dev;
     __shared__ SupCoef coef[4];   // [net*2 + set]
@@ -538,6 +546,129 @@ __global__ void __launch_bounds__(256) loss_grad_kernel(LossArgs A) {
     }
 }
 
+// ------------------------------------------------------------------------------------ Mean-Teacher, one launch
+// The Mean-Teacher step (2017_03_NIPS_Mean-Teacher_ACDC.py:97-106) in ONE launch on a co-resident grid:
+//   phase A  Dice / CE sums of the labeled images (accurate softmax, as loss_reduce_kernel) -> double atomics, then ARRIVE;
+//   phase B  gradient and value of the consistency term on the unlabeled images -- 3/4 of the bytes, needs no batch-wide sum,
+//            so it runs while the other CTAs' phase-A atomics land;
+//   barrier  wait until every CTA has arrived (all CTAs are resident: the host clamps the grid to the occupancy of this kernel,
+//            and the dependent kernel is only released -- griddepcontrol.launch_dependents -- after the barrier, so its CTAs can
+//            never hold the slots of CTAs the barrier is waiting for);
+//   phase C  coefficients from the sums, gradient of the labeled images (their logits are L2 hits by now); the last CTA to finish
+//            writes the scalars.
+// Replaces the reduce launch (8.8 us for 9.6 MB: a latency-bound launch on the critical path) of the two-launch scheme.
+constexpr int kAccBarrier = kAccTotal - 2;    // unsigned arrive counter of the grid barrier
+
+template <int C>
+__global__ void __launch_bounds__(256, 3) loss_mt_one_kernel(LossArgs A) {
+    pdl_wait();
+    if (A.cons_weight_dev) A.cons_weight = *A.cons_weight_dev;
+    constexpr int NS = 3 * C + 2;
+    __shared__ float smem[8 * NS];
+    __shared__ int slots[NS];
+    __shared__ SupCoef coef;
+    __shared__ float s_part[8];
+    const int64_t hw = A.hw, q_per_img = hw >> 2;
+    const uint32_t lab_q = (uint32_t)(A.n_l * q_per_img), total_q = (uint32_t)((A.n_l + A.n_u) * q_per_img);
+    const uint32_t tid0 = blockIdx.x * blockDim.x + threadIdx.x, stride = gridDim.x * blockDim.x;
+    // ---- phase A
+    {
+        float sl[NS];
+#pragma unroll
+        for (int i = 0; i < NS; ++i) sl[i] = 0.f;
+        for (uint32_t q = tid0; q < lab_q; q += stride) {
+            uint32_t img32, rem32;
+            fast_divmod(q, A.qdiv, img32, rem32);
+            const int64_t img = img32, pix = (int64_t)rem32 << 2;
+            float z[C][4], p[C][4], lse[4];
+            int lab[4];
+            load4<C>(A.student + (img * C) * hw + pix, hw, z);
+            load_labels4(A.labels + img * hw + pix, lab);
+            softmax4<C>(z, p, lse);
+            acc_sup<C>(z, p, lse, lab, sl);
+        }
+        if (threadIdx.x < NS) {
+            const int i = threadIdx.x, grp = i / C, c = i % C;
+            slots[i] = grp < 3 ? grp * kMaxC + c : 3 * kMaxC + (i - 3 * C);
+        }
+        __syncthreads();
+        flush<NS>(sl, A.acc, slots, smem);          // ends with __syncthreads(): this CTA's atomics are issued
+    }
+    unsigned *arrive = reinterpret_cast<unsigned *>(A.acc + kAccBarrier);
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(arrive, 1u);
+    }
+    // ---- phase B
+    const float cons = (float)(2.0 * A.cons_weight / ((double)A.n_u * C * (double)A.hw));
+    const float cf[4] = {cons, cons, cons, cons};
+    float mse_local = 0.f;
+    for (uint32_t q = lab_q + tid0; q < total_q; q += stride) {
+        uint32_t img32, rem32;
+        fast_divmod(q, A.qdiv, img32, rem32);
+        const int64_t img = img32, pix = (int64_t)rem32 << 2, u = img - A.n_l;
+        const int64_t so = (img * C) * hw + pix;
+        float z[C][4], z2[C][4], p[C][4], q2[C][4], g[C][4];
+        load4<C>(A.student + so, hw, z);
+        load4<C>(A.other + (u * C) * hw + pix, hw, z2);
+        softmax4g<C>(z, p);
+        softmax4g<C>(z2, q2);
+        grad_mse<C>(p, q2, cf, g, &mse_local);
+        store4<C>(A.dstudent + so, hw, g);
+    }
+    // ---- barrier: every CTA's phase-A sums are in
+    if (threadIdx.x == 0) {
+        while (*reinterpret_cast<volatile unsigned *>(arrive) < gridDim.x) __nanosleep(40);
+        __threadfence();
+        double acc[3 * kMaxC + 2];
+        for (int i = 0; i < 3 * kMaxC + 2; ++i) acc[i] = __ldcg(A.acc + i);
+        make_coef<C>(acc, A.class_w, coef);
+        if (blockIdx.x == 0) {
+            A.scalars[1] = A.ce_coef * coef.ce + A.dice_coef * coef.dice;
+            A.scalars[3] = coef.ce;
+            A.scalars[4] = coef.dice;
+            A.scalars[5] = (float)acc[3 * kMaxC + 1];
+            A.scalars[6] = 0.f;
+            A.scalars[7] = 0.f;
+        }
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+    // ---- phase C
+    for (uint32_t q = tid0; q < lab_q; q += stride) {
+        uint32_t img32, rem32;
+        fast_divmod(q, A.qdiv, img32, rem32);
+        const int64_t img = img32, pix = (int64_t)rem32 << 2;
+        const int64_t so = (img * C) * hw + pix;
+        float z[C][4], p[C][4], g[C][4];
+        int lab[4];
+        load_labels4(A.labels + img * hw + pix, lab);
+        load4<C>(A.student + so, hw, z);
+        softmax4g<C>(z, p);
+        grad_sup<C>(p, lab, coef, A.ce_coef, A.dice_coef, 1.f, g);
+        store4<C>(A.dstudent + so, hw, g);
+    }
+    // ---- consistency value; the last CTA to finish writes loss and consistency term
+    const float v = warp_sum(mse_local);
+    if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = v;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double sum = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) sum += (double)s_part[w];
+        atomicAdd(A.acc + kAccMse, sum);
+        __threadfence();
+        const unsigned ticket = atomicAdd(reinterpret_cast<unsigned *>(A.acc + kAccTicket), 1u);
+        if (ticket == gridDim.x - 1) {
+            __threadfence();
+            const double total = atomicAdd(A.acc + kAccMse, 0.0);
+            const float cons_val = (float)(total / ((double)A.n_u * C * (double)A.hw));
+            const float sup = A.ce_coef * coef.ce + A.dice_coef * coef.dice;
+            A.scalars[0] = sup + A.cons_weight * cons_val;
+            A.scalars[2] = cons_val;
+        }
+    }
+}
+
 // -------------------------------------------------------------------------- stand-alone DiceLoss.forward
 struct DiceArgs {
     const float *inputs;
@@ -631,6 +762,15 @@ static int loss_ctas_per_sm() {      // A/B knob (profiles/config_throughput.py)
     return v;
 }
 
+static int loss_mt_ctas_per_sm() {   // grid of the Mean-Teacher gradient kernel in CTAs per SM (its own instantiation, HPFG_LOSS_MT_MINBLOCKS resident)
+    static int v = [] {
+        const char *e = getenv("HPFG_LOSS_MT_CTAS_PER_SM");
+        const int n = e ? atoi(e) : 0;
+        return n > 0 ? n : HPFG_LOSS_MT_MINBLOCKS > 2 ? HPFG_LOSS_MT_MINBLOCKS : 2;
+    }();
+    return v;
+}
+
 static int loss_grid(int64_t quads, int ctas_per_sm = 0) {
     int64_t blocks = (quads + 255) / 256;
     const int64_t cap = (int64_t)kNumSMs * (ctas_per_sm > 0 ? ctas_per_sm : loss_ctas_per_sm());
@@ -638,8 +778,40 @@ static int loss_grid(int64_t quads, int ctas_per_sm = 0) {
     return (int)(blocks < 1 ? 1 : blocks);
 }
 
+static bool loss_mt_one_launch() {   // A/B knob: HPFG_LOSS_MT_ONE=0 keeps the reduce + gradient launches for Mean-Teacher
+    static bool v = [] {
+        const char *e = getenv("HPFG_LOSS_MT_ONE");
+        return !(e && atoi(e) == 0);
+    }();
+    return v;
+}
+
+// co-resident CTA capacity of the one-launch kernel on the current device (its grid barrier needs every CTA resident)
+template <int C>
+static int loss_mt_one_capacity() {
+    static int cap = [] {
+        int dev = 0, sms = 0, per_sm = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+            cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, loss_mt_one_kernel<C>, 256, 0) != cudaSuccess)
+            return 0;
+        if (per_sm > 3) per_sm = 3;
+        return sms * per_sm;
+    }();
+    return cap;
+}
+
 template <int C>
 static int launch_loss(const LossArgs &A, cudaStream_t st) {
+    if (A.mode == HPFG_LOSS_MT && A.world == 1 && A.n_l > 0 && A.n_u > 0 && loss_mt_one_launch()) {
+        const int cap = loss_mt_one_capacity<C>();
+        if (cap > 0) {
+            int64_t blocks = ((int64_t)A.n_u * (A.hw >> 2) + 255) / 256;     // at most one unlabeled quad per thread ...
+            if (blocks > cap) blocks = cap;                                   // ... and never more CTAs than are resident at once
+            HPFG_CUDA_CHECK(launch_pdl(loss_mt_one_kernel<C>, (int)blocks, 256, 0, st, A));
+            HPFG_LAUNCH_CHECK();
+            return HPFG_OK;
+        }
+    }
     const int grid = loss_grid((int64_t)(A.n_l + A.n_u) * (A.hw >> 2));
     const int rgrid = loss_grid((int64_t)A.reduce_imgs * (A.hw >> 2));
     switch (A.mode) {
@@ -653,11 +825,14 @@ static int launch_loss(const LossArgs &A, cudaStream_t st) {
     HPFG_LAUNCH_CHECK();
     // exact-global mode: Dice / CE / pseudo-label / mask sums over the batch of ALL ranks before any coefficient is formed
     // (the last slot is the gradient kernel's block counter: still zero everywhere, so it may take part)
+    const bool mt = A.mode == HPFG_LOSS_MT;
+    auto grad = mt ? loss_grad_kernel<C, HPFG_LOSS_MT> : loss_grad_kernel<C, -1>;
+    const int ggrid = mt ? loss_grid((int64_t)(A.n_l + A.n_u) * (A.hw >> 2), loss_mt_ctas_per_sm()) : grid;
     if (A.world > 1) {
         HPFG_RETURN_IF(sync_allreduce(A.acc, kAccTotal, true, st));
-        HPFG_CUDA_CHECK(launch_plain(loss_grad_kernel<C>, grid, 256, 0, st, A));     // (no programmatic launch across the collective)
+        HPFG_CUDA_CHECK(launch_plain(grad, ggrid, 256, 0, st, A));     // (no programmatic launch across the collective)
     } else {
-        HPFG_CUDA_CHECK(launch_pdl(loss_grad_kernel<C>, grid, 256, 0, st, A));
+        HPFG_CUDA_CHECK(launch_pdl(grad, ggrid, 256, 0, st, A));
     }
     HPFG_LAUNCH_CHECK();
     return HPFG_OK;

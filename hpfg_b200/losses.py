@@ -96,18 +96,25 @@ class Med_Sup_Loss(nn.Module):
                                 dict(ce_coef=self.ce, dice_coef=self.dice))
 
 
+def dice_loss_raw(inputs, target, softmax=False, weight=None, want_grad=True):
+    """Thin wrapper of hpfg_dice_loss: (scalars[1+C] = {loss, per-class dice}, d loss / d inputs or None).  inputs [n,C,H,W]
+    probabilities (or logits with softmax=True), target any [n,(1,)H,W] tensor of class ids."""
+    L.require_cuda(inputs, "DiceLoss inputs")
+    x = inputs.contiguous().float()
+    n, c, h, w = x.shape
+    t = target.reshape(n, h, w).contiguous().to(torch.int64)
+    dx = torch.empty_like(x) if want_grad else None
+    scalars = torch.empty(1 + c, device=x.device, dtype=torch.float32)
+    ws = torch.empty(2048, dtype=torch.uint8, device=x.device)
+    L.check(L.lib().hpfg_dice_loss(L.ptr(x), L.ptr(t), n, c, h, w, int(bool(softmax)), _weights_arg(weight, c),
+                                   L.ptr(dx), L.ptr(scalars), L.ptr(ws), L.stream_ptr(x.device)), "hpfg_dice_loss")
+    return scalars, dx
+
+
 class _DiceFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, inputs, target, n_classes, weight, softmax):
-        L.require_cuda(inputs, "DiceLoss inputs")
-        x = inputs.contiguous().float()
-        n, c, h, w = x.shape
-        t = target.reshape(n, h, w).contiguous().to(torch.int64)
-        dx = torch.empty_like(x) if inputs.requires_grad else None
-        scalars = torch.empty(1 + c, device=x.device, dtype=torch.float32)
-        ws = torch.empty(2048, dtype=torch.uint8, device=x.device)
-        L.check(L.lib().hpfg_dice_loss(L.ptr(x), L.ptr(t), n, c, h, w, int(bool(softmax)), _weights_arg(weight, c),
-                                       L.ptr(dx), L.ptr(scalars), L.ptr(ws), L.stream_ptr(x.device)), "hpfg_dice_loss")
+        scalars, dx = dice_loss_raw(inputs, target, softmax, weight, want_grad=inputs.requires_grad)
         if dx is not None:
             ctx.save_for_backward(dx)
         ctx.class_wise = scalars[1:]

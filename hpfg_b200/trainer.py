@@ -775,10 +775,12 @@ class S4CVStep(_StepBase):
 
 class HPFGStep(_StepBase):
     """The HPFG iteration of main.py:128-207 on three ``UNet_Plus`` networks (model1 sees the CutMix batch, model2 and the EMA
-    teacher the plain batch).  The U-Net bodies run on the library's kernels through ``UNet_Plus``'s autograd Function; the
-    projection necks and ``Dense_Loss`` are small torch modules, so the step goes through autograd once (``loss.backward()``)
-    and the optimiser side is fused: flat SGD over the 82 U-Net tensors of each student, one launch per neck tensor, the
-    backbone EMA model2 <- model1 (main.py:68-76) and the teacher EMA (utils/utils.py:82-86) as flat passes.
+    teacher the plain batch).  U-Net bodies, projection necks and ``Dense_Loss`` run on the library's kernels behind autograd
+    Functions; the pixel losses do not go through autograd at all: model2's supervised + Mean-Teacher terms are the MT mode of the
+    fused loss kernels, model1's supervised term the SUP mode, its Dice against the CutMix-pasted pseudo-labels ``hpfg_dice_loss``,
+    and their logits gradients are fed to ONE ``torch.autograd.backward`` together with the contrastive term.  The optimiser side is
+    fused: flat SGD over the 82 U-Net tensors of each student, one launch per neck tensor, the backbone EMA model2 <- model1
+    (main.py:68-76) and the teacher EMA (utils/utils.py:82-86) as flat passes.
 
     step(label_img, target_label, label_img1, target_label1, img_unlabel, cutmix_mask): the tensors main.py:128-150 builds
     (label_img1 / target_label1: the second labeled draw, repeated to the unlabeled batch size here as at :139-140;
@@ -786,7 +788,7 @@ class HPFGStep(_StepBase):
 
     def __init__(self, model1, model2, ema_model, *, ema_decay=0.99, mt_start=1000, temperature=0.7, **kw):
         super().__init__(**kw)
-        from .losses import DiceLoss, Dense_Loss
+        from .losses import Dense_Loss
         self.m1, self.m2, self.ema_model, self.ema_decay, self.mt_start = model1, model2, ema_model, ema_decay, mt_start
         self.in_channels, self.num_classes = model1.in_channels, model1.num_classes
         model1.train()
@@ -795,7 +797,6 @@ class HPFGStep(_StepBase):
             m.ensure_flat()
         for p in ema_model.parameters():
             p.requires_grad = False
-        self.dice = DiceLoss(self.num_classes)
         self.temperature = temperature
         self._dense = None
         self._DenseLoss = Dense_Loss
@@ -837,9 +838,10 @@ class HPFGStep(_StepBase):
                     "hpfg_sgd_momentum")
 
     def step(self, label_img, target_label, label_img1, target_label1, img_unlabel, cutmix_mask, lr=None):
-        """lr: override of the Medical_LR value of this iteration (resuming with a fresh scheduler; parity harness)."""
-        import torch.nn.functional as F
+        """lr: override of the Medical_LR value of this iteration (resuming with a fresh scheduler; parity harness).
+        cutmix_mask: the 0/1 box masks of BoxMaskGenerator (main.py:141-143)."""
         from .utils import update_ema_variables, ema_update_flat
+        from .losses import ssl_loss_raw, dice_loss_raw, argmax_labels
         self.cur_itrs += 1
         self._check_buffers()
         m1, m2, ema = self.m1, self.m2, self.ema_model
@@ -860,20 +862,24 @@ class HPFGStep(_StepBase):
         outputs2, h1, h2 = m2(volume_batch)
         with torch.no_grad():
             ema_output, ema_h1, ema_h2 = ema(volume_batch)
-            ema_soft = torch.softmax(ema_output, dim=1)
-        soft1, soft2 = torch.softmax(outputs1, dim=1), torch.softmax(outputs2, dim=1)
         tl = target_label.long()
-        loss_sup = 0.5 * (F.cross_entropy(outputs1[:label_bs], tl, ignore_index=255) + self.dice(soft1[:label_bs], tl.unsqueeze(1))) + \
-            0.5 * (F.cross_entropy(outputs2[:label_bs], tl, ignore_index=255) + self.dice(soft2[:label_bs], tl.unsqueeze(1)))
-        loss_contrast = self._dense(h1, ema_h1) + self._dense(h2, ema_h2)
-        cm = cutmix_mask.squeeze(1)
-        pseudo = torch.argmax(ema_soft[label_bs:], dim=1, keepdim=False)
-        pseudo = target_label1 * (1.0 - cm) + pseudo * cm                                        # main.py:172
-        pseudo_sup = self.dice(soft1[label_bs:], pseudo.unsqueeze(1))
         w = self._consistency_weight()
-        cons2 = torch.mean((soft2[label_bs:] - ema_soft[label_bs:]) ** 2) if self.cur_itrs >= self.mt_start else 0.0
-        loss = loss_sup + 7 * w * pseudo_sup + w * cons2 + w * loss_contrast
-        loss.backward()
+        # model2 (main.py:157-158,183,186): supervised + w * mean((softmax2_u - softmax_ema_u)^2) = the Mean-Teacher mode of the fused
+        # loss kernels (value, loss_sup, consistency value and d/d outputs2 in two launches); the MSE term is 0 before mt_start
+        r2 = ssl_loss_raw(L.LOSS_MT, outputs2.detach(), ema_output[label_bs:], tl, label_bs,
+                          cons_weight=w if self.cur_itrs >= self.mt_start else 0.0)
+        # model1 (main.py:154-155,170-175,185): supervised (SUP mode: zero gradient on the unlabeled images) + 7w * Dice of
+        # softmax1_u against the teacher's argmax pasted into the second labeled draw's labels by the CutMix mask
+        r1 = ssl_loss_raw(L.LOSS_SUP, outputs1.detach(), None, tl, label_bs)
+        pseudo = torch.where(cutmix_mask.squeeze(1) > 0.5, argmax_labels(ema_output[label_bs:]), target_label1)      # main.py:171-172
+        ps, d_ps = dice_loss_raw(outputs1.detach()[label_bs:], pseudo, softmax=True)
+        dlogits1 = r1["dstudent"]
+        dlogits1[label_bs:].add_(d_ps, alpha=7.0 * w)
+        loss_contrast = self._dense(h1, ema_h1) + self._dense(h2, ema_h2)                     # main.py:166 (autograd: the necks)
+        loss_sup = r1["scalars"][1] + r2["scalars"][1]
+        loss = r1["scalars"][0] + 7 * w * ps[0] + r2["scalars"][0] + w * loss_contrast
+        # one backward pass: the loss kernels' gradients enter at the logits, the contrastive term through the necks of model2
+        torch.autograd.backward([outputs1, outputs2, w * loss_contrast], [dlogits1, r2["dstudent"], None])
         lr = medical_lr(self.cur_itrs, self.base_lr, self.total_itrs) if lr is None else lr
         first = int(self.cur_itrs == 1)
         self._sgd_model(m1, self.b1, lr, first)
@@ -881,6 +887,6 @@ class HPFGStep(_StepBase):
         alpha = min(1 - 1 / (self.cur_itrs + 1), self.ema_decay)
         ema_update_flat(m2.ensure_flat(), m1.ensure_flat(), alpha)          # update_ema_variables_backbone: encoder + decoder = the flat buffer
         update_ema_variables(m2, ema, self.ema_decay, self.cur_itrs)
-        self.last = dict(loss=loss.detach(), loss_sup=loss_sup.detach(), contrast=loss_contrast.detach(), pseudo=pseudo_sup.detach(),
+        self.last = dict(loss=loss.detach(), loss_sup=loss_sup, contrast=loss_contrast.detach(), pseudo=ps[0], cons2=r2["scalars"][2],
                          lr=lr, w=w, outputs1=outputs1.detach(), outputs2=outputs2.detach(), ema_output=ema_output)
         return loss.detach()
