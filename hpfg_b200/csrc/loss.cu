@@ -618,7 +618,15 @@ __global__ void __launch_bounds__(256, 3) loss_mt_one_kernel(LossArgs A) {
     }
     // ---- barrier: every CTA's phase-A sums are in
     if (threadIdx.x == 0) {
-        while (*reinterpret_cast<volatile unsigned *>(arrive) < gridDim.x) __nanosleep(40);
+        const long long t0 = clock64();
+        while (*reinterpret_cast<volatile unsigned *>(arrive) < gridDim.x) {
+            __nanosleep(40);
+            if (clock64() - t0 > 6000000000LL) {      // bounded wait (~3 s): a protocol bug must trap, not hang the GPU
+                printf("hpfg_b200: loss_mt_one_kernel grid barrier timed out (block %d of %d, arrived %u)\n", (int)blockIdx.x, (int)gridDim.x,
+                       *reinterpret_cast<volatile unsigned *>(arrive));
+                __trap();
+            }
+        }
         __threadfence();
         double acc[3 * kMaxC + 2];
         for (int i = 0; i < 3 * kMaxC + 2; ++i) acc[i] = __ldcg(A.acc + i);
