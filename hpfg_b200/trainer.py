@@ -819,6 +819,37 @@ class HPFGStep(_StepBase):
     def _consistency_weight(self):
         return self.consistency * linear_rampup(self.cur_itrs // 150, self.consistency_rampup)
 
+    @staticmethod
+    def _neck_params(model):
+        """The 16 projection-neck tensors of a UNet_Plus: parameters() order after the 82 U-Net tensors of the flat buffer."""
+        core = {id(q) for q in model._flat_params_list}
+        return [p for p in model.parameters() if id(p) not in core]
+
+    def state_dict(self):
+        """As ``_StepBase.state_dict``, with the neck tensors' momentum buffers at their torch.optim.SGD indices (82..97 of
+        ``model.parameters()``); tensors that never received a gradient (model1's necks: main.py:148 drops their outputs) have
+        no state, as in torch."""
+        out = super().state_dict()
+        for model, opt in zip((self.m1, self.m2), out["optimizers"]):
+            base = len(model._layout)
+            necks = self._neck_params(model)
+            opt["param_groups"][0]["params"] = list(range(base + len(necks)))
+            for j, p in enumerate(necks):
+                mom = self._neck_mom.get(id(p))
+                if mom is not None and self.cur_itrs > 0:
+                    opt["state"][base + j] = {"momentum_buffer": mom.clone()}
+        return out
+
+    def load_state_dict(self, sd):
+        super().load_state_dict(sd)
+        self._neck_mom = {}
+        for model, opt in zip((self.m1, self.m2), sd.get("optimizers", [])):
+            base = len(model._layout)
+            for j, p in enumerate(self._neck_params(model)):
+                st = opt["state"].get(base + j)
+                if st is not None and st.get("momentum_buffer") is not None:
+                    self._neck_mom[id(p)] = st["momentum_buffer"].to(device=p.device, dtype=p.dtype).reshape(p.shape).clone()
+
     def _sgd_model(self, model, buf, lr, first):
         """torch.optim.SGD semantics over all parameters of a UNet_Plus: the flat U-Net buffer in one pass + the neck tensors."""
         st = L.stream_ptr(model.flat_params.device)
@@ -826,15 +857,15 @@ class HPFGStep(_StepBase):
         g = model.last_flat_grad
         L.check(lib.hpfg_sgd_momentum(L.ptr(model.flat_params), L.ptr(g), L.ptr(buf), model.flat_params.numel(), lr, self.momentum,
                                       self.weight_decay, self._grad_scale, first, st), "hpfg_sgd_momentum")
-        core = {id(q) for q in model._flat_params_list}
-        for p in model.parameters():
-            if id(p) in core or p.grad is None:
+        for p in self._neck_params(model):
+            if p.grad is None:
                 continue
             mom = self._neck_mom.get(id(p))
-            if mom is None:
+            fresh = mom is None                       # torch.optim.SGD: the first gradient a tensor sees initialises its buffer
+            if fresh:
                 mom = self._neck_mom[id(p)] = torch.zeros_like(p.data)
             L.check(lib.hpfg_sgd_momentum(L.ptr(p.data), L.ptr(p.grad.contiguous()), L.ptr(mom), p.numel(), lr, self.momentum,
-                                          self.weight_decay, self._grad_scale, first, st),
+                                          self.weight_decay, self._grad_scale, int(fresh), st),
                     "hpfg_sgd_momentum")
 
     def step(self, label_img, target_label, label_img1, target_label1, img_unlabel, cutmix_mask, lr=None):

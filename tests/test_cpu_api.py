@@ -151,3 +151,32 @@ def test_necks_and_dense_loss_have_no_cpu_path():
         hb.Dense_Loss(batch_size=3)(x, y)
     with pytest.raises(RuntimeError):
         hb.Dense_Loss(batch_size=5)(x, y)                  # the reference's mask is built for the constructor's batch size
+
+
+def test_hpfg_step_checkpoint_carries_neck_momentum():
+    """HPFGStep.state_dict(): torch.optim.SGD layout over all 98 parameters of each UNet_Plus -- the flat U-Net momentum at
+    indices 0..81, the neck tensors' buffers at 82..97 (only for tensors that have seen a gradient) -- and it round-trips."""
+    torch.manual_seed(9)
+    m1, m2 = hb.UNet_Plus(1, 4), hb.UNet_Plus(1, 4)
+    st = hb.HPFGStep(m1, m2, copy.deepcopy(m2))
+    st.cur_itrs = 7
+    st.b1.uniform_(-1, 1)
+    st.b2.uniform_(-1, 1)
+    necks2 = st._neck_params(m2)
+    assert len(necks2) == 16 and [tuple(p.shape) for p in necks2] == [s for _, s in oracle.unet_plus_neck_spec(4)]
+    for p in necks2:
+        st._neck_mom[id(p)] = torch.randn_like(p)
+    sd = st.state_dict()
+    assert sd["cur_itrs"] == 7 and len(sd["optimizers"]) == 2
+    o1, o2 = sd["optimizers"]
+    assert o1["param_groups"][0]["params"] == list(range(98)) and sorted(o1["state"]) == list(range(82))      # model1's necks: no state
+    assert sorted(o2["state"]) == list(range(98))
+    ref = torch.optim.SGD(m2.parameters(), lr=0.01, momentum=0.9)
+    ref.load_state_dict({"state": o2["state"], "param_groups": [dict(ref.state_dict()["param_groups"][0], **o2["param_groups"][0])]})
+    n1, n2 = hb.UNet_Plus(1, 4), hb.UNet_Plus(1, 4)
+    st2 = hb.HPFGStep(n1, n2, copy.deepcopy(n2))
+    st2.load_state_dict(sd)
+    assert st2.cur_itrs == 7 and torch.equal(st2.b1, st.b1) and torch.equal(st2.b2, st.b2)
+    for p, q in zip(necks2, st2._neck_params(n2)):
+        assert torch.equal(st2._neck_mom[id(q)], st._neck_mom[id(p)])
+    assert not any(id(q) in st2._neck_mom for q in st2._neck_params(n1))
