@@ -469,6 +469,37 @@ def run_gpu(args):
                                "fprop_tensor_frac": fl / (t3[0] * 1e-6) / 1e12 / pk["tf_burst"],
                                "dgrad_tensor_frac": fl / (t3[1] * 1e-6) / 1e12 / pk["tf_burst"],
                                "wgrad_tensor_frac": fl / (t3[2] * 1e-6) / 1e12 / pk["tf_burst"]})
+        # the 7.26 MB flat buffers are launch-latency dominated (and L2-resident), so the optimiser passes are also timed
+        # as a pure HBM stream on x64 replicated buffers (464 MB per array): the bandwidth the same kernels reach once size is out of the way
+        stream_x64 = None
+        if world == 1 and c["kind"] == "mt":
+            try:
+                rep_n = n_params * 64
+                bufs64 = [torch.randn(rep_n, device=dev) for _ in range(4)]
+                p64, g64, m64, e64 = [ctypes.c_void_p(t.data_ptr()) for t in bufs64]
+                sp = L.stream_ptr(dev)
+                calls = {"ema_kernel (update_ema_variables, 12 B per parameter)": (12.0, lambda: lib.hpfg_ema_update(e64, p64, rep_n, 0.99, sp)),
+                         "sgd_kernel<EMA> (SGD momentum + weight decay + EMA, 28 B per parameter)": (
+                             28.0, lambda: lib.hpfg_sgd_momentum_ema(p64, g64, m64, e64, rep_n, 0.01, 0.9, 1e-4, 1.0, 0, 0.99, sp))}
+                stream_x64 = []
+                for name, (bpp, fn) in calls.items():
+                    for _ in range(3):
+                        L.check(fn(), name)
+                    torch.cuda.synchronize()
+                    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    ev0.record()
+                    for _ in range(10):
+                        L.check(fn(), name)
+                    ev1.record()
+                    torch.cuda.synchronize()
+                    us = ev0.elapsed_time(ev1) / 10 * 1e3
+                    gbs = rep_n * bpp / (us * 1e-6) / 1e9
+                    stream_x64.append({"kernel": name, "bound": "hbm", "params": rep_n, "us_per_call": us, "achieved": gbs, "peak": pk["hbm"],
+                                       "unit": "GB/s", "frac": gbs / pk["hbm"]})
+                del bufs64
+                torch.cuda.empty_cache()
+            except Exception as exc:                     # a reported extra; never fails the bench line
+                stream_x64 = {"error": str(exc)[:200]}
         cfg = config_block(c, world)
         line = {"metric": METRICS[c["kind"]], "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps, "warmup": warmup,
                 "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
@@ -496,6 +527,7 @@ def run_gpu(args):
                     "sgd_kernel (SGD momentum + weight decay (+ EMA teacher), one pass per network over the flat buffers)",
                     (28.0 if c["kind"] != "cps" else 2 * 20.0) * n_params, prof["sgd_ema"], pk,
                     "28 B per parameter with EMA: read p, g, m, ema; write p, m, ema (20 B without)"),
+                "roofline_optimiser_x64_stream": stream_x64,
                 "layer_table": layers,
                 "kernel_time_per_step": prof,
                 "clocks": sampler.summary() if sampler else None}
