@@ -17,9 +17,9 @@ from .losses import (Med_Sup_Loss, DiceLoss, softmax_mse_loss, mean_teacher_loss
 from .utils import (update_ema_variables, get_current_consistency_weight, sigmoid_rampup, linear_rampup,
                     ema_update_flat)
 from .trainer import (MeanTeacherStep, CPSStep, UAMTStep, ICTStep, S4CVStep, HPFGStep, medical_lr, gradient_buckets, allreduce_flat_buckets,
-                      shard_batch)
+                      allreduce_tensor_list, shard_batch)
 
 __all__ = ["build_model", "UNet", "UNet_Plus", "projection_conv", "Dense_Loss", "Med_Sup_Loss", "DiceLoss", "softmax_mse_loss", "mean_teacher_loss", "cps_loss",
            "uamt_loss", "ssl_loss_raw", "update_ema_variables", "get_current_consistency_weight", "sigmoid_rampup",
            "linear_rampup", "ema_update_flat", "MeanTeacherStep", "CPSStep", "UAMTStep", "ICTStep", "S4CVStep", "HPFGStep", "ict_loss", "ict_loss_raw",
-           "ict_mix_inputs", "s4cvnet_loss", "s4cv_loss_raw", "argmax_labels", "predict_volume", "medical_lr", "gradient_buckets", "allreduce_flat_buckets", "shard_batch"]
+           "ict_mix_inputs", "s4cvnet_loss", "s4cv_loss_raw", "argmax_labels", "predict_volume", "medical_lr", "gradient_buckets", "allreduce_flat_buckets", "allreduce_tensor_list", "shard_batch"]

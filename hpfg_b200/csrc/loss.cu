@@ -12,6 +12,9 @@
 // its VALUE is accumulated by the gradient kernel itself and the last CTA to finish writes the loss scalars -- the reduce
 // kernel then touches n_l of the n_l+n_u images.  CPS / S4CV (pseudo-label Dice over the unlabeled images) and UAMT
 // (mask count) still reduce over the whole batch.  NCHW fp32, 4 consecutive pixels per thread, 128-bit loads per class plane.
+// Mean-Teacher (the headline step) goes one step further: loss_mt_one_kernel does both phases in ONE launch on a co-resident
+// grid with a grid barrier between the labeled sums and the labeled gradient (the unlabeled gradient runs in between); the
+// two-launch path remains for the other modes and for the exact-global data-parallel mode (an all-reduce sits between the phases).
 // Algorithmic bytes (MT): (n_l+n_u)*C*HW*4 read + n_u*C*HW*4 read + n_l*HW*8 read + (n_l+n_u)*C*HW*4 written.
 #include "common.cuh"
 #include <cstdlib>

@@ -53,6 +53,21 @@ def allreduce_flat_buckets(flat_grad, buckets, group=None, before_bucket=None, s
     return works
 
 
+def allreduce_tensor_list(tensors, group=None):
+    """Sum-all-reduce a list of (small) tensors as ONE flat buffer and scatter the sums back in place: the neck gradients of a
+    UNet_Plus (16 tensors) travel as one collective instead of 16.  CPU + gloo and CUDA + NCCL alike."""
+    import torch.distributed as dist
+    tensors = [t for t in tensors if t is not None]
+    if not tensors:
+        return
+    flat = torch.cat([t.reshape(-1) for t in tensors])
+    dist.all_reduce(flat, group=group)
+    off = 0
+    for t in tensors:
+        t.copy_(flat[off:off + t.numel()].view_as(t))
+        off += t.numel()
+
+
 def shard_batch(x_l, x_u, y, rank, world):
     """Data-parallel split that keeps the labeled:unlabeled ratio per rank (both sub-batches are split, because the
     supervised and consistency terms normalise over their own pixels)."""
@@ -819,6 +834,17 @@ class HPFGStep(_StepBase):
     def _consistency_weight(self):
         return self.consistency * linear_rampup(self.cur_itrs // 150, self.consistency_rampup)
 
+    def _broadcast_from_rank0(self):
+        """The flat buffers as in ``_StepBase``, plus the neck tensors (they live outside the flat buffer)."""
+        super()._broadcast_from_rank0()
+        if self.world <= 1:
+            return
+        import torch.distributed as dist
+        src = dist.get_global_rank(self.pg, 0) if self.pg is not None else 0
+        for m in self._models():
+            for p in self._neck_params(m):
+                dist.broadcast(p.data, src=src, group=self.pg)
+
     @staticmethod
     def _neck_params(model):
         """The 16 projection-neck tensors of a UNet_Plus: parameters() order after the 82 U-Net tensors of the flat buffer."""
@@ -911,6 +937,11 @@ class HPFGStep(_StepBase):
         loss = r1["scalars"][0] + 7 * w * ps[0] + r2["scalars"][0] + w * loss_contrast
         # one backward pass: the loss kernels' gradients enter at the logits, the contrastive term through the necks of model2
         torch.autograd.backward([outputs1, outputs2, w * loss_contrast], [dlogits1, r2["dstudent"], None])
+        if self.world > 1:      # data parallel (main.py itself is single-process): gradients summed here, scaled by 1/world in the SGD pass
+            import torch.distributed as dist
+            for m in (m1, m2):
+                dist.all_reduce(m.last_flat_grad, group=self.pg)
+                allreduce_tensor_list([p.grad for p in self._neck_params(m)], group=self.pg)
         lr = medical_lr(self.cur_itrs, self.base_lr, self.total_itrs) if lr is None else lr
         first = int(self.cur_itrs == 1)
         self._sgd_model(m1, self.b1, lr, first)

@@ -112,3 +112,40 @@ def test_two_rank_gloo_matches_mean_gradient_update():
     oracle.sgd_step(st, grads, oracle.SGDState(), 0.01)
     ref = torch.cat([st[nm].reshape(-1) for nm in names])
     assert torch.allclose(res[0][2], ref, rtol=0, atol=1e-7)
+
+
+def _hpfg_worker(rank, world, port, q):
+    """HPFGStep's data-parallel host logic on CPU: replicas built from DIFFERENT seeds are made identical at construction
+    (flat U-Net buffers and the neck tensors outside them), and the neck gradients travel as one coalesced sum-all-reduce."""
+    import copy
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(2)
+    torch.manual_seed(100 + rank)
+    m1, m2 = hb.UNet_Plus(IN_CH, N_CLS), hb.UNet_Plus(IN_CH, N_CLS)
+    step = hb.HPFGStep(m1, m2, copy.deepcopy(m2))
+    assert step.world == world and step._grad_scale == 1.0 / world
+    digest = torch.cat([p.detach().reshape(-1) for m in (m1, m2, step.ema_model) for p in m.parameters()])
+    necks = step._neck_params(m2)
+    grads = [torch.full_like(p, float(rank + 1)) * (i + 1) for i, p in enumerate(necks)]
+    grads[3] = None                                            # a tensor without gradient is skipped on every rank alike
+    hb.allreduce_tensor_list(grads, group=None)
+    sums = [float(g.flatten()[0]) if g is not None else None for g in grads]
+    q.put((rank, digest.double().sum().item(), digest.abs().double().sum().item(), sums))
+    dist.destroy_process_group()
+
+
+def test_hpfg_step_two_rank_gloo_replicas_and_neck_allreduce():
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_hpfg_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=300) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert res[0][1:3] == res[1][1:3]                           # all 3 x 98 parameter tensors identical after the broadcast
+    want = [3.0 * (i + 1) if i != 3 else None for i in range(16)]        # (1 + 2) * (i + 1)
+    assert res[0][3] == want and res[1][3] == want
