@@ -2,7 +2,7 @@
 utils/loss/diceloss.py:155-191 ``DiceLoss``, :64-81 ``softmax_mse_loss``) plus the fused whole-step SSL losses
 of the Mean-Teacher / CPS / UAMT trainers, all running on the fused CUDA loss kernels (csrc/loss.cu).
 
-Each fused call produces the loss value AND d loss / d logits in the same two launches; the autograd
+Each fused call produces the loss value AND d loss / d logits in the same launch(es) (Mean-Teacher: one; other modes: two); the autograd
 Function just hands the stored gradient back scaled by grad_output."""
 import ctypes
 

@@ -922,7 +922,7 @@ class HPFGStep(_StepBase):
         tl = target_label.long()
         w = self._consistency_weight()
         # model2 (main.py:157-158,183,186): supervised + w * mean((softmax2_u - softmax_ema_u)^2) = the Mean-Teacher mode of the fused
-        # loss kernels (value, loss_sup, consistency value and d/d outputs2 in two launches); the MSE term is 0 before mt_start
+        # loss kernels (value, loss_sup, consistency value and d/d outputs2 in one launch); the MSE term is 0 before mt_start
         r2 = ssl_loss_raw(L.LOSS_MT, outputs2.detach(), ema_output[label_bs:], tl, label_bs,
                           cons_weight=w if self.cur_itrs >= self.mt_start else 0.0)
         # model1 (main.py:154-155,170-175,185): supervised (SUP mode: zero gradient on the unlabeled images) + 7w * Dice of
