@@ -180,3 +180,21 @@ def test_hpfg_step_checkpoint_carries_neck_momentum():
     for p, q in zip(necks2, st2._neck_params(n2)):
         assert torch.equal(st2._neck_mom[id(q)], st._neck_mom[id(p)])
     assert not any(id(q) in st2._neck_mom for q in st2._neck_params(n1))
+
+
+def test_oracle_is_test_infrastructure_only():
+    """oracle/ may be imported by tests/, __graft_entry__.smoke() and bench.py's CPU legs only: nothing under hpfg_b200/
+    (Python or CUDA) refers to it, and importing the package does not pull it in."""
+    import re
+    import subprocess
+    import sys
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "hpfg_b200")
+    pat = re.compile(r"^\s*(import|from)\s+oracle\b|oracle/", re.M)
+    for root, _, files in os.walk(pkg):
+        if "build" in root.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert not pat.search(open(os.path.join(root, f)).read()), os.path.join(root, f)
+    code = "import sys, hpfg_b200; assert not any(m == 'oracle' or m.startswith('oracle.') for m in sys.modules), 'oracle imported'"
+    assert subprocess.run([sys.executable, "-c", code], cwd=os.path.dirname(pkg)).returncode == 0
